@@ -1,0 +1,153 @@
+/*
+ * iiseg.h -- C ABI of libiiseg.so: the B200 (sm_100a) kernels behind the
+ * iterative-inference hot path of adri-romsor/iterative_inference_segm.
+ *
+ * The reference has no FFI of its own; its seams are the four compiled Theano
+ * callables pred_fcn_fn / pred_dae_fn / de_fn / val_fn
+ * (iterative_inference.py:187-210).  Each entry point below replaces the
+ * Theano/Lasagne op (cited per function) those callables are built from.  The
+ * Python host (iterative_inference_segm_b200/) binds this library with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator);
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on
+ *    that stream and safe to capture into a CUDA Graph;
+ *  - return value: 0 = OK, negative = error, text via iiseg_last_error();
+ *  - activations are NHWC bf16 with the channel count padded (see each call);
+ *    the boundary tensors (images, y, targets) are the reference's NCHW fp32;
+ *  - no call falls back to the CPU.
+ */
+#ifndef IISEG_H_
+#define IISEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IISEG_ABI_VERSION 1
+
+/* ---- library ----------------------------------------------------------- */
+int iiseg_abi_version(void);
+const char* iiseg_last_error(void);
+/* 0 if device `dev` is compute capability 10.x; negative otherwise. */
+int iiseg_device_check(int dev);
+/* After a failed stream sync: copies the kernels' pinned-host diagnostic words
+ * (which pipeline barrier timed out) into out[0..n). Returns words written. */
+int iiseg_read_diag(int32_t* out, int n);
+/* Number of kernel launches issued through this library since load. */
+int64_t iiseg_launch_count(void);
+
+/* ---- layout conversion at the boundary ---------------------------------- */
+/* NCHW fp32 [N,C,H,W] -> NHWC bf16 [N,H,W,Cpad], channels >= C zero-filled. */
+int iiseg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C,
+                                     int H, int W, int Cpad, void* stream);
+/* NHWC bf16 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W] (first C channels). */
+int iiseg_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C,
+                                       int H, int W, int Cpad, void* stream);
+/* NHWC fp32 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W]. */
+int iiseg_unpack_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C,
+                                      int H, int W, int Cpad, void* stream);
+
+/* ---- convolution: lasagne Conv2DLayer(flip_filters=False) ---------------
+ * Replaces every Conv2DLayer on the path (models/fcn_down.py:102-104,
+ * models/fcn_up.py:84-86, models/fcn8.py:33-85): stride-1 cross-correlation as
+ * an implicit GEMM on tcgen05 tensor cores (TMA-fed, TMEM accumulators), with
+ * bias, optional ReLU and optional skip-sum (ElemwiseSumLayer,
+ * models/fcn_up.py:96-102) fused in the epilogue and the channel concat of a
+ * second source (ConcatLayer((h, pool4)), models/model_helpers.py:93-94) done
+ * in the loader: the K loop walks src0's channels, then src1's. */
+typedef struct iiseg_conv_desc {
+  const void* src0;   /* NHWC bf16 [N,H,W,C0]; C0 multiple of 64            */
+  const void* src1;   /* NHWC bf16 [N,H,W,C1] or NULL; C1 multiple of 64    */
+  int N, H, W;        /* input extent                                       */
+  int C0, C1;
+  const void* weight; /* bf16 [Cout][R*S][C0+C1] (K-major GEMM B operand)   */
+  const float* bias;  /* fp32 [Cout]                                        */
+  int Cout;           /* padded: 16, or a multiple of 64                    */
+  int R, S, pad;      /* filter extent and symmetric zero padding           */
+  /* Output window: out pixel (oh,ow) is conv pixel (oh+oh0, ow+ow0); only the
+   * OH x OW window is computed (centre crop of up_conv1, CroppingLayer,
+   * layers/mylayers.py:36-57).                                             */
+  int oh0, ow0, OH, OW;
+  void* out;          /* NHWC [N,OH,OW,Cout], bf16 or fp32 per out_f32      */
+  const void* addend; /* NHWC bf16 [N,OH,OW,Cout] added before store, or NULL */
+  int relu;           /* 1: rectify (Lasagne default), 0: linear            */
+  int out_f32;        /* 1: fp32 output (only Cout == 16)                   */
+} iiseg_conv_desc;
+int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
+
+/* ---- pooling: lasagne Pool2DLayer(2) + DePool2D -------------------------
+ * 2x2/stride-2 max, floor (models/fcn_down.py:122).  `mask` (may be NULL)
+ * receives the tie-inclusive argmax mask DePool2D derives with
+ * T.grad(pool, ones) (layers/mylayers.py:111-112): one 4-bit nibble per
+ * (window, channel), bit (2*dy+dx) set iff x[2oh+dy, 2ow+dx] == window max;
+ * eight channels per uint32, layout [N,H/2,W/2,C/8].  C multiple of 8. */
+int iiseg_maxpool2_mask_fwd(const void* x, void* pooled, uint32_t* mask, int N,
+                            int H, int W, int C, void* stream);
+/* DePool2D (layers/mylayers.py:88-115): out[2oh+dy,2ow+dx] = u[oh,ow] where
+ * the mask bit is set, else 0; trailing odd row/col of the HxW output = 0. */
+int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N,
+                           int H, int W, int C, void* stream);
+
+/* ---- transposed convolution: lasagne Deconv2DLayer ----------------------
+ * models/fcn8.py:90-91,100-101,109-110 (crop='valid', flip_filters=False,
+ * linear) on <=16-channel score maps, fp32 NHWC16 in and out.  Computes the
+ * out window [oh0,oh0+OH) x [ow0,ow0+OW) of the (H-1)*stride+k output, adds
+ * bias and, if `addend` != NULL, addend[(oh+ah0),(ow+aw0)] (ElemwiseSumLayer
+ * with centre cropping, models/fcn8.py:94-97).  weight fp32 [k][k][16][16] =
+ * Wt[a][b][ci][co], already flipped/transposed by the host packer. */
+typedef struct iiseg_deconv_desc {
+  const float* x; int N, H, W;       /* NHWC16 fp32 input                  */
+  const float* weight; const float* bias; int k, stride;
+  int oh0, ow0, OH, OW;
+  const float* addend; int AH, AW, ah0, aw0;  /* NHWC16 fp32 [N,AH,AW,16]  */
+  float* out;                        /* NHWC16 fp32 [N,OH,OW,16]           */
+} iiseg_deconv_desc;
+int iiseg_deconv2d_fwd(const iiseg_deconv_desc* d, void* stream);
+
+/* ---- softmax tail + iterative-inference update --------------------------
+ * Channel softmax (models/fcn_up.py:154-169, models/fcn8.py:120-191) of fp32
+ * NHWC16 logits [N,H,W,16] over the first C channels.
+ * iiseg_softmax_nchw: p -> NCHW fp32 [N,C,H,W]; if y_bf16 != NULL also the
+ *   NHWC bf16 [N,H,W,Cpad] copy the DAE's first conv reads.
+ * iiseg_softmax_update: the loop body iterative_inference.py:267-277 for every
+ *   image with active[n] != 0:  g = y - p;  y <- clip(y - step*g, 0, 1)
+ *   (y NCHW fp32 master, updated in place, plus its NHWC bf16 copy);
+ *   per-block partial sums of ||g||_2 over channels go to norm_partial
+ *   [N][nblk] (nblk = iiseg_update_blocks(H,W)); p is also stored to p_out
+ *   (NCHW fp32) when p_out != NULL.
+ * iiseg_norm_finalize: norm[n] = sum(partials)/(H*W) in fixed order;
+ *   n_exec[n] += 1; if norm[n] < eps: active[n] = 0 (the `break`,
+ *   iterative_inference.py:275-277).  Inactive images are untouched. */
+int iiseg_update_blocks(int H, int W);
+int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, int N, int C,
+                       int H, int W, int Cpad, void* stream);
+int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
+                         float* p_out, const int32_t* active,
+                         float* norm_partial, int N, int C, int H, int W,
+                         int Cpad, float step, void* stream);
+int iiseg_norm_finalize(const float* norm_partial, float* norm, int32_t* active,
+                        int32_t* n_exec, int N, int H, int W, float eps,
+                        void* stream);
+
+/* ---- metrics: metrics.py jaccard / accuracy / squared_error --------------
+ * One pass over y (NCHW fp32 [N,C,H,W]) and the target, per image n with
+ * active[n] != 0 (active may be NULL = all), ACCUMULATING into
+ *   cm     int64 [N][C*C]  cm[pred*C+true] += 1 for true < C (metrics.py:22-27)
+ *   counts int64 [N][2]    {#(pred==true, true!=void), #(true!=void)} (:40-65)
+ *   sqerr  fp64  [N][2]    {sum_pix mask*mean_c (y-t)^2, sum_pix mask} (:144-156)
+ * argmax ties -> first index.  Target is either one-hot NCHW fp32
+ * [N,C+1,H,W] (`onehot`) or int32 labels [N,H,W] (`labels`); exactly one is
+ * non-NULL.  void_label < 0 means no void class. */
+int iiseg_metrics_accumulate(const float* y, const float* onehot,
+                             const int32_t* labels, const int32_t* active,
+                             int64_t* cm, int64_t* counts, double* sqerr, int N,
+                             int C, int H, int W, int void_label, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IISEG_H_ */

@@ -1,0 +1,75 @@
+// Library-level pieces of the C ABI: error text, device check, pipeline diagnostics.
+#include <atomic>
+#include <mutex>
+#include <string.h>
+
+#include "common.cuh"
+#include "../../include/iiseg.h"
+
+namespace iiseg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int32_t* g_diag_host = nullptr;
+static int32_t* g_diag_dev = nullptr;
+static std::once_flag g_diag_once;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+// 64 pinned, device-mapped words.  A kernel whose mbarrier wait times out writes
+// {magic, code, block, aux} here before trapping; host memory survives the dead context.
+int32_t* diag_device_ptr() {
+  std::call_once(g_diag_once, [] {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64 * sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess) {
+      memset(h, 0, 64 * sizeof(int32_t));
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+        g_diag_host = static_cast<int32_t*>(h);
+        g_diag_dev = static_cast<int32_t*>(d);
+      }
+    }
+  });
+  return g_diag_dev;
+}
+
+}  // namespace iiseg
+
+extern "C" int iiseg_abi_version(void) { return IISEG_ABI_VERSION; }
+
+extern "C" const char* iiseg_last_error(void) { return iiseg::g_err; }
+
+extern "C" int iiseg_device_check(int dev) {
+  using namespace iiseg;
+  int major = 0, minor = 0;
+  IISEG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  IISEG_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  IISEG_CHECK(major == 10, "device %d is sm_%d%d; libiiseg is built for sm_100a only", dev, major, minor);
+  return 0;
+}
+
+extern "C" int iiseg_read_diag(int32_t* out, int n) {
+  if (iiseg::g_diag_host == nullptr || out == nullptr) return 0;
+  if (n > 64) n = 64;
+  for (int i = 0; i < n; ++i) out[i] = iiseg::g_diag_host[i];
+  return n;
+}
+
+extern "C" int64_t iiseg_launch_count(void) { return iiseg::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,68 @@
+// Shared host/device helpers for libiiseg (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+namespace iiseg {
+
+// ---- error reporting -------------------------------------------------------
+void set_error(const char* fmt, ...);
+int32_t* diag_device_ptr();   // pinned, mapped host words the kernels write on a pipeline timeout
+void count_launch(int n = 1);
+
+#define IISEG_CHECK(cond, ...)                                 \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      ::iiseg::set_error(__VA_ARGS__);                         \
+      return -1;                                               \
+    }                                                          \
+  } while (0)
+
+#define IISEG_CUDA(call)                                                          \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      ::iiseg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                         cudaGetErrorString(e_));                                 \
+      return -2;                                                                  \
+    }                                                                             \
+  } while (0)
+
+#define IISEG_LAUNCH_CHECK()                                                      \
+  do {                                                                            \
+    ::iiseg::count_launch();                                                      \
+    cudaError_t e_ = cudaPeekAtLastError();                                       \
+    if (e_ != cudaSuccess) {                                                      \
+      ::iiseg::set_error("%s:%d launch -> %s", __FILE__, __LINE__,                \
+                         cudaGetErrorString(e_));                                 \
+      return -3;                                                                  \
+    }                                                                             \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();
+
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace iiseg

@@ -1,0 +1,540 @@
+// Implicit-GEMM convolution on Blackwell tensor cores (sm_100a).
+//
+// Replaces lasagne Conv2DLayer(flip_filters=False) on the iterative-inference
+// path (models/fcn_down.py:102-104, models/fcn_up.py:84-86, models/fcn8.py:33-85).
+//
+//   D[pixel, cout] = sum_{r,s,c} X[n, oh+r-pad, ow+s-pad, c] * W[cout, r, s, c]
+//
+// GEMM view: M = a TH x TW box of output pixels (<= 128 rows), N = BN output
+// channels, K = R*S*(C0+C1) walked tap by tap in 64-channel blocks.
+//   * A operand: one 4-D TMA box load (64 ch, TW, TH, 1 image) per (tap, channel
+//     block) whose start coordinate is shifted by the tap; zero padding, the
+//     pad=100 first layer and ragged image edges are all TMA out-of-bounds fill,
+//     so every output pixel is accumulated by the SAME K sequence (spatially
+//     constant regions stay bit-constant, which the tie-inclusive pool mask
+//     downstream depends on).  A second tensor map supplies the channels of the
+//     concatenated `h` source -- the concat never exists in memory.
+//   * B operand: [Cout][K] K-major weights, 2-D TMA box (64, BN).
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) M=128, N=BN, K=16, issued by
+//     one thread; accumulators live in TMEM, double-buffered (2 x BN columns) so
+//     the epilogue of tile i overlaps the main loop of tile i+1.
+//   * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+//     allocator, warps 4-7 epilogue (tcgen05.ld -> bias/ReLU/skip-sum -> bf16 ->
+//     swizzled smem -> TMA store, or direct fp32/bf16 stores for 16-channel
+//     outputs).  Persistent CTAs, one per SM, static round-robin tile schedule.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/iiseg.h"
+
+namespace iiseg {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // bf16 elements: one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAStageBytes = kBlockM * 128;  // 16 KiB
+constexpr int kStagingBytes = kBlockM * 128; // one 64-channel bf16 output chunk
+constexpr int kNumThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr long long kTimeoutCycles = 4000000000LL;  // ~2 s: a stuck pipeline traps instead of hanging
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kBStageBytes = BN * 128;
+  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr bool kTmaStore = BN >= 64;
+  static constexpr int kStagingTotal = kTmaStore ? 2 * kStagingBytes : 0;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStagingTotal;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingTotal + 256;
+  static_assert(kStages >= 2, "pipeline too shallow");
+};
+
+struct alignas(64) ConvParams {
+  CUtensorMap tm_src0;
+  CUtensorMap tm_src1;
+  CUtensorMap tm_w;
+  CUtensorMap tm_out;
+  const float* bias;
+  const __nv_bfloat16* addend;
+  void* out;
+  int32_t* diag;
+  int n_cblk0, n_cblk1;     // 64-channel blocks of src0 / src1
+  int R, S;
+  int in_off_h, in_off_w;   // input row of tap r for local output row o: o + in_off_h + r
+  int TH, TW;
+  int tiles_h, tiles_w, n_ntiles, num_tiles;
+  int OH, OW, Cout;
+  int relu, out_f32;
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: on timeout write (code, block, aux) to pinned host memory and trap, so a
+// broken pipeline surfaces as a launch failure with a readable cause, never a hung GPU.
+__device__ __noinline__ void mbar_timeout(int32_t* diag, int code, int aux) {
+  if (diag != nullptr) {
+    diag[1] = code; diag[2] = static_cast<int32_t>(blockIdx.x); diag[3] = aux;
+    diag[0] = 0x0BADBA55;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* diag, int code, int aux) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kTimeoutCycles) mbar_timeout(diag, code, aux);
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 UMMA):
+// start address >> 4, LBO unused (one swizzle atom along K), SBO = 8 rows * 128 B,
+// descriptor version 1, layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = BN.
+template <int BN>
+__device__ __forceinline__ constexpr uint32_t make_instr_desc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+         (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------
+struct TileCoord { int n, th, tw, nt; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  c.nt = t % p.n_ntiles; t /= p.n_ntiles;
+  c.tw = t % p.tiles_w;  t /= p.tiles_w;
+  c.th = t % p.tiles_h;  c.n = t / p.tiles_h;
+  return c;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + kStages * kAStageBytes;
+  const uint32_t smem_stage_out = smem_b + kStages * Cfg::kBStageBytes;
+  const uint32_t bars = smem_stage_out + Cfg::kStagingTotal;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (kStages + i); };
+  auto tmem_full_bar = [&](int i) { return bars + 8u * (2 * kStages + i); };
+  auto tmem_empty_bar = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of the aligned base
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_src0);
+    prefetch_tmap(&p.tm_src1);
+    prefetch_tmap(&p.tm_w);
+    if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int n_cblk = p.n_cblk0 + p.n_cblk1;
+  const int num_k_blocks = p.R * p.S * n_cblk;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t a_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int h_base = tc.th * p.TH + p.in_off_h;
+        const int w_base = tc.tw * p.TW + p.in_off_w;
+        int kb = 0;
+        for (int r = 0; r < p.R; ++r) {
+          for (int s = 0; s < p.S; ++s) {
+            for (int cb = 0; cb < n_cblk; ++cb, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u, p.diag, 1, stage);
+              mbar_arrive_expect_tx(full_bar(stage), a_bytes + Cfg::kBStageBytes);
+              if (cb < p.n_cblk0)
+                tma_load_4d(smem_a + stage * kAStageBytes, &p.tm_src0, full_bar(stage), cb * kBlockK, w_base + s, h_base + r, tc.n);
+              else
+                tma_load_4d(smem_a + stage * kAStageBytes, &p.tm_src1, full_bar(stage), (cb - p.n_cblk0) * kBlockK, w_base + s, h_base + r, tc.n);
+              tma_load_2d(smem_b + stage * Cfg::kBStageBytes, &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_instr_desc<BN>();
+      int stage = 0; uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase, p.diag, 3, stage);
+          tcgen05_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_a + stage * kAStageBytes);
+          const uint64_t b_desc = make_smem_desc(smem_b + stage * Cfg::kBStageBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar(as));  // accumulator ready
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== Epilogue =====================
+    const int q = warp - 4;                 // TMEM lane quadrant of this warp
+    const int m = q * 32 + lane;            // accumulator row = pixel index inside the box
+    const int epi_tid = threadIdx.x - 128;
+    const int hl = m / p.TW, wl = m - hl * p.TW;
+    int iter = 0;
+    int store_buf = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+      const bool valid = (hl < p.TH) && (oh < p.OH) && (ow < p.OW);
+      const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+      mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      const int n0 = tc.nt * BN;
+
+      if constexpr (Cfg::kTmaStore) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 64; ++chunk) {
+          const int cbase = n0 + chunk * 64;
+          // skip-sum operand: this pixel's 64 channels = 128 contiguous bytes
+          uint4 add[8];
+          if (p.addend != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              add[j] = valid ? ldg_nc_v4(p.addend + pix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
+          }
+          // the staging buffer we are about to overwrite must have been read by its TMA store
+          if (epi_tid == 0) tma_store_wait_read<1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
+#pragma unroll
+          for (int half = 0; half < 4; ++half) {
+            uint32_t v[16];
+            tmem_ld_x16(taddr + chunk * 64 + half * 16, v);
+            tmem_ld_wait();
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = half * 16 + 2 * j;
+              float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + c);
+              float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + c + 1);
+              if (p.addend != nullptr) {
+                const uint4& a4 = add[half * 2 + (j >> 2)];
+                const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
+                f0 += bf16_lo(aw); f1 += bf16_hi(aw);
+              }
+              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              packed[j] = pack_bf16x2(f0, f1);
+            }
+            // two 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int chunk16 = half * 2 + cc;
+              const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
+                           "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
+            }
+          }
+          if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
+            tcgen05_fence_before();
+            mbar_arrive(tmem_empty_bar(as));
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (epi_tid == 0) {
+            tma_store_4d(&p.tm_out, sbuf, cbase, tc.tw * p.TW, tc.th * p.TH, tc.n);
+            tma_store_commit();
+          }
+          store_buf ^= 1;
+        }
+      } else {
+        // 16-channel outputs (score maps, logits): direct stores from registers
+        static_assert(BN == 16 || Cfg::kTmaStore, "direct-store epilogue is written for BN == 16");
+        uint32_t v[16];
+        tmem_ld_x16(taddr, v);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar(as));
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[j] = __uint_as_float(v[j]) + __ldg(p.bias + n0 + j);
+        }
+        if (p.addend != nullptr && valid) {
+          const uint4 a0 = ldg_nc_v4(p.addend + pix * p.Cout + n0);
+          const uint4 a1 = ldg_nc_v4(p.addend + pix * p.Cout + n0 + 8);
+          const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              stg_v4(o + 8 * j, make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
+          }
+        }
+      }
+    }
+    if (Cfg::kTmaStore && epi_tid == 0) tma_store_wait_read<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// NHWC bf16 tensor seen as (C, W, H, N); box (64, TW, TH, 1); 128B swizzle; OOB reads give zeros.
+static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW) {
+  EncodeTiledFn fn = get_encode_fn();
+  IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc N=%d H=%d W=%d C=%d box %dx%d) failed: %d", N, H, W, C, TH, TW, (int)r);
+  return 0;
+}
+
+// [Cout][K] bf16 weights seen as (K, Cout); box (64, BN).
+static int encode_weight(CUtensorMap* tm, const void* base, int Cout, int K, int BN) {
+  EncodeTiledFn fn = get_encode_fn();
+  IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight Cout=%d K=%d BN=%d) failed: %d", Cout, K, BN, (int)r);
+  return 0;
+}
+
+// Pick the TH x TW (<= 128 pixels) box that covers OH x OW with the fewest tiles; ties -> widest box.
+static void choose_box(int OH, int OW, int* TH, int* TW) {
+  long best = -1; int bh = 1, bw = 1;
+  const int wmax = OW < 128 ? OW : 128;
+  for (int tw = 1; tw <= wmax; ++tw) {
+    int th = 128 / tw; if (th > OH) th = OH;
+    if (th > 256) th = 256;
+    const long tiles = (long)ceil_div(OW, tw) * ceil_div(OH, th);
+    if (best < 0 || tiles < best || (tiles == best && tw >= bw)) { best = tiles; bh = th; bw = tw; }
+  }
+  *TH = bh; *TW = bw;
+}
+
+template <int BN>
+static int launch_conv(const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace iiseg
+
+extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(d != nullptr, "conv: null descriptor");
+  IISEG_CHECK(d->src0 != nullptr && d->weight != nullptr && d->bias != nullptr && d->out != nullptr, "conv: null tensor");
+  IISEG_CHECK(d->C0 > 0 && d->C0 % 64 == 0, "conv: C0=%d must be a positive multiple of 64", d->C0);
+  IISEG_CHECK(d->C1 >= 0 && d->C1 % 64 == 0 && (d->C1 == 0) == (d->src1 == nullptr), "conv: bad second source (C1=%d)", d->C1);
+  IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
+  IISEG_CHECK(d->out_f32 == 0 || d->Cout == 16, "conv: fp32 output only for Cout == 16");
+  IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
+  const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
+  IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
+              "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
+  IISEG_CHECK(d->N >= 1, "conv: empty batch");
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  const int BN = d->Cout == 16 ? 16 : (d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64));
+  choose_box(d->OH, d->OW, &p.TH, &p.TW);
+  if (encode_nhwc(&p.tm_src0, d->src0, d->N, d->H, d->W, d->C0, p.TH, p.TW)) return -1;
+  if (d->src1 != nullptr) {
+    if (encode_nhwc(&p.tm_src1, d->src1, d->N, d->H, d->W, d->C1, p.TH, p.TW)) return -1;
+  } else {
+    p.tm_src1 = p.tm_src0;
+  }
+  const int K = d->R * d->S * (d->C0 + d->C1);
+  if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN)) return -1;
+  if (BN >= 64) {
+    if (encode_nhwc(&p.tm_out, d->out, d->N, d->OH, d->OW, d->Cout, p.TH, p.TW)) return -1;
+  } else {
+    p.tm_out = p.tm_src0;
+  }
+  p.bias = d->bias;
+  p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
+  p.out = d->out;
+  p.diag = diag_device_ptr();
+  p.n_cblk0 = d->C0 / 64; p.n_cblk1 = d->C1 / 64;
+  p.R = d->R; p.S = d->S;
+  p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
+  p.tiles_h = ceil_div(d->OH, p.TH); p.tiles_w = ceil_div(d->OW, p.TW);
+  p.n_ntiles = d->Cout / BN;
+  p.num_tiles = d->N * p.tiles_h * p.tiles_w * p.n_ntiles;
+  p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
+  p.relu = d->relu; p.out_f32 = d->out_f32;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (BN) {
+    case 16: return launch_conv<16>(p, s);
+    case 64: return launch_conv<64>(p, s);
+    case 128: return launch_conv<128>(p, s);
+    default: return launch_conv<256>(p, s);
+  }
+}

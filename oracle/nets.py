@@ -1,0 +1,169 @@
+"""FCN8 and DAE_h forward passes restated on torch CPU (test oracle).
+
+Parameters are flat lists in Lasagne `get_all_param_values` order (the order of
+the reference's positional `.npz` checkpoints, models/DAE_h.py:52-57,
+models/fcn8.py:177-180).
+"""
+import torch
+
+from . import lasagne_semantics as L
+
+# ---------------------------------------------------------------------------
+# FCN8 (models/fcn8.py:16-200)
+# ---------------------------------------------------------------------------
+
+VGG_CFG = [  # (name, out_channels) grouped per pooling stage; models/fcn8.py:33-72
+    [('conv1_1', 64), ('conv1_2', 64)],
+    [('conv2_1', 128), ('conv2_2', 128)],
+    [('conv3_1', 256), ('conv3_2', 256), ('conv3_3', 256)],
+    [('conv4_1', 512), ('conv4_2', 512), ('conv4_3', 512)],
+    [('conv5_1', 512), ('conv5_2', 512), ('conv5_3', 512)],
+]
+
+
+def fcn8_param_shapes(nb_in_channels, n_classes):
+    """[(name, W shape, b shape)] in checkpoint order: 13 VGG convs, fc6, fc7,
+    score_fr, score2, score_pool4, score4, score_pool3, upsample (42 arrays).
+    Conv W is (out,in,kh,kw); Deconv W is (in,out,kh,kw)."""
+    shapes = []
+    cin = nb_in_channels
+    for stage in VGG_CFG:
+        for name, cout in stage:
+            shapes.append((name, (cout, cin, 3, 3), (cout,)))
+            cin = cout
+    shapes.append(('fc6', (4096, 512, 7, 7), (4096,)))
+    shapes.append(('fc7', (4096, 4096, 1, 1), (4096,)))
+    shapes.append(('score_fr', (n_classes, 4096, 1, 1), (n_classes,)))
+    shapes.append(('score2', (n_classes, n_classes, 4, 4), (n_classes,)))
+    shapes.append(('score_pool4', (n_classes, 512, 1, 1), (n_classes,)))
+    shapes.append(('score4', (n_classes, n_classes, 4, 4), (n_classes,)))
+    shapes.append(('score_pool3', (n_classes, 256, 1, 1), (n_classes,)))
+    shapes.append(('upsample', (n_classes, n_classes, 16, 16), (n_classes,)))
+    return shapes
+
+
+def fcn8_forward(params, X, n_classes, layer=('pool4', 'probs_dimshuffle'),
+                 temperature=1.0):
+    """models/fcn8.py:30-130,187-200.  Returns [net[el] for el in layer].
+    `temperature` divides upsample.W and .b (models/fcn8.py:193-198).
+    Dropout layers are identity (deterministic=True, iterative_inference.py:187).
+    NOTE score_fr / score_pool4 / score_pool3 keep Lasagne's default rectify."""
+    names = [s[0] for s in fcn8_param_shapes(X.shape[1], n_classes)]
+    P = {n: (params[2 * i], params[2 * i + 1]) for i, n in enumerate(names)}
+    net = {}
+    x = X
+    for si, stage in enumerate(VGG_CFG):
+        for ci, (name, _) in enumerate(stage):
+            pad = 100 if name == 'conv1_1' else 'same'
+            x = L.conv2d(x, *P[name], pad=pad, relu=True)
+            net[name] = x
+        x = L.maxpool2(x)
+        net['pool%d' % (si + 1)] = x
+    x = L.conv2d(x, *P['fc6'], pad='valid', relu=True)
+    net['fc6'] = x
+    x = L.conv2d(x, *P['fc7'], pad='valid', relu=True)
+    net['fc7'] = x
+    x = L.conv2d(x, *P['score_fr'], pad='valid', relu=True)
+    net['score_fr'] = x
+    s2 = L.deconv2d(x, *P['score2'], stride=2)
+    net['score2'] = s2
+    sp4 = L.conv2d(net['pool4'], *P['score_pool4'], pad='same', relu=True)
+    a, b = L.center_crop_pair(s2, sp4)
+    net['score_fused'] = a + b
+    s4 = L.deconv2d(net['score_fused'], *P['score4'], stride=2)
+    net['score4'] = s4
+    sp3 = L.conv2d(net['pool3'], *P['score_pool3'], pad='valid', relu=True)
+    a, b = L.center_crop_pair(s4, sp3)
+    net['score_final'] = a + b
+    Wu, bu = P['upsample']
+    up = L.deconv2d(net['score_final'], Wu / temperature, bu / temperature, stride=8)
+    net['upsample'] = up
+    net['score'] = L.center_crop_to(up, X.shape[2], X.shape[3])
+    net['probs_dimshuffle'] = L.channel_softmax(net['score'])
+    return [net[el] for el in layer]
+
+
+# ---------------------------------------------------------------------------
+# DAE_h (models/DAE_h.py:12-63, models/fcn_down.py:9-138, models/fcn_up.py:11-172)
+# kind='standard', unpool_type='trackind', conv_before_pool=1, skip=True, bn=0,
+# dropout=0, noise=0 (parity is pinned at noise=0: layers/mylayers.py:91-93
+# rebuilds the mask sub-graph non-deterministically otherwise).
+# ---------------------------------------------------------------------------
+
+def dae_levels(concat_h=('pool4',), additional_pool=2):
+    """n_pool from the last concat name + additional_pool (models/DAE_h.py:36-39)."""
+    last = concat_h[-1]
+    n_pool = int(last[-1]) if 'pool' in last else 0
+    return n_pool, n_pool + additional_pool
+
+
+def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
+                     concat_h=('pool4',), additional_pool=2):
+    """[(name, W shape, b shape)] in checkpoint order: conv1_1..convP_1 then
+    up_convP..up_conv1.  Filter counts: n_filters*2**p for p<6
+    (models/fcn_down.py:96-99); up_conv_p outputs the channel count of
+    pool_{p-1}'s input, or n_classes for p==1 (models/fcn_up.py:29-34)."""
+    n_pool, total = dae_levels(concat_h, additional_pool)
+    shapes = []
+    cin = n_classes
+    if concat_h[-1] == 'input':
+        cin += nb_features_to_concat
+    conv_out = []
+    filters = n_filters
+    for p in range(total):
+        if p < 6:
+            filters = n_filters * (2 ** p)
+        shapes.append(('conv%d_1' % (p + 1), (filters, cin, 3, 3), (filters,)))
+        conv_out.append(filters)
+        cin = filters
+        if p + 1 == n_pool and n_pool > 0:  # concat h after pool{n_pool}
+            cin += nb_features_to_concat
+    up_in = conv_out[-1]
+    for p in range(total, 0, -1):
+        # pool_{p-1}.input_shape[1]: the (un-concatenated) conv output of level p-1
+        n_cl = n_classes if p == 1 else conv_out[p - 2]
+        shapes.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
+        up_in = n_cl
+    return shapes
+
+
+def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
+                return_logits=False):
+    """One application DAE(y, h) -> probabilities, same size as y.
+
+    Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
+    conv when concatenating at a pool layer and padding>0, else 'same'),
+    maxpool2; h is concatenated BEFORE the DAE's own pool{n_pool} channels
+    (models/model_helpers.py:93-94).
+    Up (models/fcn_up.py:65-113): DePool2D with the tie mask of level p's
+    pre-pool map, conv3x3 'same' linear, skip-sum with the un-concatenated
+    pool_{p-1} (p>1) or centre crop to the input size (p==1); channel softmax.
+    """
+    n_pool, total = dae_levels(concat_h, additional_pool)
+    Wd = [(params[2 * i], params[2 * i + 1]) for i in range(total)]
+    Wu = [(params[2 * (total + i)], params[2 * (total + i) + 1]) for i in range(total)]
+    x = y
+    if concat_h[-1] == 'input':
+        x = torch.cat([h, x], dim=1)
+    pre, pools = [], []
+    for p in range(total):
+        first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input'
+                     and padding > 0)
+        x = L.conv2d(x, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+        pre.append(x)
+        x = L.maxpool2(x)
+        pools.append(x)
+        if p + 1 == n_pool and n_pool > 0:
+            x = torch.cat([h, x], dim=1)
+    u = pools[-1]
+    for i, p in enumerate(range(total, 0, -1)):
+        u = L.depool2d(u, pre[p - 1])
+        u = L.conv2d(u, *Wu[i], pad='same', relu=False)
+        if p > 1:
+            a, b = L.center_crop_pair(u, pools[p - 2])
+            u = a + b
+        else:
+            u = L.center_crop_to(u, y.shape[2], y.shape[3])
+    if return_logits:
+        return u
+    return L.channel_softmax(u)

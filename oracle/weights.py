@@ -1,0 +1,78 @@
+"""Lasagne-style initialisers, positional .npz checkpoints and the synthetic
+benchmark recipe (test oracle; also the single source of synthetic weights so
+the CUDA path and the oracle see identical numbers).
+
+Checkpoint format: np.savez(path, *get_all_param_values(net)) -> arr_0..arr_k
+(train_dae.py:436-445; loaded at models/DAE_h.py:52-57, models/fcn8.py:177-180).
+"""
+import numpy as np
+import torch
+
+from .nets import dae_param_shapes, fcn8_param_shapes
+
+
+def glorot_uniform(shape, gen):
+    """lasagne.init.GlorotUniform: a = sqrt(6 / ((n1 + n2) * receptive_field)),
+    n1, n2 = shape[:2]."""
+    rf = int(np.prod(shape[2:]))
+    a = np.sqrt(6.0 / ((shape[0] + shape[1]) * rf))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * a
+
+
+def he_uniform(shape, gen):
+    """lasagne.init.HeUniform(gain='relu'): a = sqrt(6 / fan_in),
+    fan_in = prod(shape[1:])."""
+    a = np.sqrt(6.0 / int(np.prod(shape[1:])))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * a
+
+
+def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
+    """He-uniform W, zero b.  With random weights the FCN8 logits are tiny, so
+    `logit_gain` rescales the final `upsample` kernel to give peaky y0 (the
+    same lever as temperature<1, models/fcn8.py:193-198)."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, ws, bs in fcn8_param_shapes(nb_in_channels, n_classes):
+        W = he_uniform(ws, gen)
+        if name == 'upsample':
+            W = W * logit_gain
+        params += [W, torch.zeros(bs)]
+    return params
+
+
+def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
+                         concat_h=('pool4',), additional_pool=2, out_gain=1.0):
+    """Lasagne defaults: GlorotUniform W, zero b (the benign
+    regime).  `out_gain` rescales the last conv (up_conv1): with random weights
+    the iterated map amplifies pool-mask flips, and out_gain < 1 makes it
+    contractive so that free-running parity is well defined
+    (oracle/validate_recipe.py measures the fp32-vs-fp64 drift)."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, ws, bs in dae_param_shapes(n_classes, nb_features_to_concat, n_filters,
+                                         concat_h, additional_pool):
+        W = glorot_uniform(ws, gen)
+        if name == 'up_conv1':
+            W = W * out_gain
+        params += [W, torch.zeros(bs)]
+    return params
+
+
+def save_npz(path, params):
+    np.savez(path, *[np.asarray(p, dtype=np.float32) for p in params])
+
+
+def load_npz(path):
+    with np.load(path) as f:
+        return [torch.from_numpy(f['arr_%d' % i]) for i in range(len(f.files))]
+
+
+def synthetic_batch(B, H, W, n_classes=11, seed=0):
+    """CamVid-shaped synthetic batch: X ~ U[0,1) (B,3,H,W);
+    labels randint(0, n_classes+1) with n_classes = void, one-hot float32
+    (B, n_classes+1, H, W)."""
+    gen = torch.Generator().manual_seed(seed)
+    X = torch.rand((B, 3, H, W), generator=gen, dtype=torch.float32)
+    lab = torch.randint(0, n_classes + 1, (B, H, W), generator=gen)
+    L = torch.nn.functional.one_hot(lab, n_classes + 1).permute(0, 3, 1, 2).float()
+    return X, L.contiguous(), lab
