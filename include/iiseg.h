@@ -129,6 +129,9 @@ int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
                          float* p_out, const int32_t* active,
                          float* norm_partial, int N, int C, int H, int W,
                          int Cpad, float step, void* stream);
+/* de_fn (iterative_inference.py:203-204): grad = y - softmax(logits), NCHW fp32. */
+int iiseg_softmax_grad(const float* logits, const float* y, float* grad, int N, int C,
+                       int H, int W, void* stream);
 int iiseg_norm_finalize(const float* norm_partial, float* norm, int32_t* active,
                         int32_t* n_exec, int N, int H, int W, float eps,
                         void* stream);

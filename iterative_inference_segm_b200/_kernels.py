@@ -1,0 +1,205 @@
+"""Torch-tensor front end of the C ABI: shape bookkeeping + pointer passing.
+
+PyTorch is only the allocator and the stream here; every function launches the
+library's sm_100a kernels on torch's current CUDA stream (so calls can be
+captured by torch.cuda.graph).  Nothing in this module computes on the CPU.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _chk(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+        raise _lib.IisegError('%s must be a contiguous CUDA %s tensor' % (name, dtype))
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise _lib.IisegError('no CUDA device: libiiseg has no CPU fallback')
+    _lib.call('iiseg_device_check', torch.cuda.current_device())
+
+
+def pad_channels(c, conv_input=True):
+    """Channel padding rule of the kernels: conv inputs are multiples of 64
+    (one 128-byte TMA row); small outputs (score maps / logits) are 16."""
+    if not conv_input and c <= 16:
+        return 16
+    return (c + 63) // 64 * 64
+
+
+# ---- layout ---------------------------------------------------------------
+def pack_nchw(src, cpad, out=None):
+    _chk(src, F32, 'src')
+    N, Cc, H, W = src.shape
+    if out is None:
+        out = torch.empty((N, H, W, cpad), dtype=BF16, device=src.device)
+    _lib.call('iiseg_pack_nchw_f32_to_nhwc_bf16', _ptr(src), _ptr(out), N, Cc, H, W, cpad, _stream())
+    return out
+
+
+def unpack_nhwc(src, c, out=None):
+    N, H, W, cpad = src.shape
+    if out is None:
+        out = torch.empty((N, c, H, W), dtype=F32, device=src.device)
+    if src.dtype == BF16:
+        _lib.call('iiseg_unpack_nhwc_bf16_to_nchw_f32', _ptr(src), _ptr(out), N, c, H, W, cpad, _stream())
+    else:
+        _chk(src, F32, 'src')
+        _lib.call('iiseg_unpack_nhwc_f32_to_nchw_f32', _ptr(src), _ptr(out), N, c, H, W, cpad, _stream())
+    return out
+
+
+# ---- convolution ------------------------------------------------------------
+def conv_out_size(H, W, R, S, pad):
+    return H + 2 * pad - R + 1, W + 2 * pad - S + 1
+
+
+def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
+           out_f32=False):
+    """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
+    window = (oh0, ow0, OH, OW) selects the output window (default: all)."""
+    _chk(src0, BF16, 'src0')
+    _chk(weight, BF16, 'weight')
+    _chk(bias, F32, 'bias')
+    N, H, W, C0 = src0.shape
+    C1 = 0
+    if src1 is not None:
+        _chk(src1, BF16, 'src1')
+        assert src1.shape[:3] == src0.shape[:3]
+        C1 = src1.shape[3]
+    Cout = weight.shape[0]
+    assert weight.shape[1] == R * S * (C0 + C1), (tuple(weight.shape), R, S, C0, C1)
+    fOH, fOW = conv_out_size(H, W, R, S, pad)
+    oh0, ow0, OH, OW = window if window is not None else (0, 0, fOH, fOW)
+    if out is None:
+        out = torch.empty((N, OH, OW, Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
+    else:
+        _chk(out, F32 if out_f32 else BF16, 'out')
+        assert tuple(out.shape) == (N, OH, OW, Cout), (tuple(out.shape), (N, OH, OW, Cout))
+    if addend is not None:
+        _chk(addend, BF16, 'addend')
+        assert tuple(addend.shape) == (N, OH, OW, Cout)
+    d = _lib.ConvDesc(src0=src0.data_ptr(), src1=src1.data_ptr() if src1 is not None else None,
+                      N=N, H=H, W=W, C0=C0, C1=C1, weight=weight.data_ptr(), bias=bias.data_ptr(),
+                      Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
+                      out=out.data_ptr(), addend=addend.data_ptr() if addend is not None else None,
+                      relu=int(bool(relu)), out_f32=int(bool(out_f32)))
+    _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
+    return out
+
+
+# ---- pool / unpool ----------------------------------------------------------
+def maxpool2(x, with_mask, pooled=None, mask=None):
+    _chk(x, BF16, 'x')
+    N, H, W, Cc = x.shape
+    if pooled is None:
+        pooled = torch.empty((N, H // 2, W // 2, Cc), dtype=BF16, device=x.device)
+    if with_mask and mask is None:
+        mask = torch.empty((N, H // 2, W // 2, Cc // 8), dtype=torch.int32, device=x.device)
+    _lib.call('iiseg_maxpool2_mask_fwd', _ptr(x), _ptr(pooled), _ptr(mask) if with_mask else C.c_void_p(0),
+              N, H, W, Cc, _stream())
+    return (pooled, mask) if with_mask else pooled
+
+
+def unpool2(u, mask, H, W, out=None):
+    _chk(u, BF16, 'u')
+    _chk(mask, torch.int32, 'mask')
+    N, H2, W2, Cc = u.shape
+    assert (H2, W2) == (H // 2, W // 2)
+    if out is None:
+        out = torch.empty((N, H, W, Cc), dtype=BF16, device=u.device)
+    _lib.call('iiseg_unpool2_mask_fwd', _ptr(u), _ptr(mask), _ptr(out), N, H, W, Cc, _stream())
+    return out
+
+
+# ---- transposed conv on 16-channel fp32 maps --------------------------------
+def deconv16(x, weight, bias, k, stride, window=None, addend=None, addend_off=(0, 0), out=None):
+    _chk(x, F32, 'x')
+    _chk(weight, F32, 'weight')
+    _chk(bias, F32, 'bias')
+    N, H, W, Cc = x.shape
+    assert Cc == 16 and tuple(weight.shape) == (k, k, 16, 16)
+    fH, fW = (H - 1) * stride + k, (W - 1) * stride + k
+    oh0, ow0, OH, OW = window if window is not None else (0, 0, fH, fW)
+    if out is None:
+        out = torch.empty((N, OH, OW, 16), dtype=F32, device=x.device)
+    AH = AW = 0
+    if addend is not None:
+        _chk(addend, F32, 'addend')
+        AH, AW = addend.shape[1], addend.shape[2]
+    d = _lib.DeconvDesc(x=x.data_ptr(), N=N, H=H, W=W, weight=weight.data_ptr(), bias=bias.data_ptr(),
+                        k=k, stride=stride, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
+                        addend=addend.data_ptr() if addend is not None else None, AH=AH, AW=AW,
+                        ah0=addend_off[0], aw0=addend_off[1], out=out.data_ptr())
+    _lib.call('iiseg_deconv2d_fwd', C.byref(d), _stream())
+    return out
+
+
+# ---- softmax / update ---------------------------------------------------------
+def update_blocks(H, W):
+    return _lib.load().iiseg_update_blocks(H, W)
+
+
+def softmax_nchw(logits, C_, p_out, y_bf16=None):
+    _chk(logits, F32, 'logits')
+    N, H, W, c16 = logits.shape
+    assert c16 == 16
+    _chk(p_out, F32, 'p_out')
+    cpad = y_bf16.shape[3] if y_bf16 is not None else 0
+    _lib.call('iiseg_softmax_nchw', _ptr(logits), _ptr(p_out), _ptr(y_bf16), N, C_, H, W, cpad, _stream())
+    return p_out
+
+
+def softmax_update(logits, y, y_bf16, active, norm_partial, step, p_out=None):
+    _chk(logits, F32, 'logits')
+    _chk(y, F32, 'y')
+    N, C_, H, W = y.shape
+    assert tuple(logits.shape) == (N, H, W, 16)
+    cpad = y_bf16.shape[3] if y_bf16 is not None else 0
+    _lib.call('iiseg_softmax_update', _ptr(logits), _ptr(y), _ptr(y_bf16), _ptr(p_out), _ptr(active),
+              _ptr(norm_partial), N, C_, H, W, cpad, C.c_float(step), _stream())
+
+
+def softmax_grad(logits, y, grad):
+    _chk(logits, F32, 'logits')
+    _chk(y, F32, 'y')
+    _chk(grad, F32, 'grad')
+    N, C_, H, W = y.shape
+    _lib.call('iiseg_softmax_grad', _ptr(logits), _ptr(y), _ptr(grad), N, C_, H, W, _stream())
+    return grad
+
+
+def norm_finalize(norm_partial, norm, active, n_exec, H, W, eps):
+    N = norm.shape[0]
+    _lib.call('iiseg_norm_finalize', _ptr(norm_partial), _ptr(norm), _ptr(active), _ptr(n_exec), N, H, W,
+              C.c_float(eps), _stream())
+
+
+# ---- metrics ------------------------------------------------------------------
+def metrics_accumulate(y, cm, counts, sqerr, onehot=None, labels=None, active=None, void_label=-1):
+    _chk(y, F32, 'y')
+    N, C_, H, W = y.shape
+    if onehot is not None:
+        _chk(onehot, F32, 'onehot')
+        assert tuple(onehot.shape) == (N, C_ + 1, H, W), tuple(onehot.shape)
+    if labels is not None:
+        _chk(labels, torch.int32, 'labels')
+    _chk(cm, torch.int64, 'cm')
+    _chk(counts, torch.int64, 'counts')
+    _chk(sqerr, torch.float64, 'sqerr')
+    _lib.call('iiseg_metrics_accumulate', _ptr(y), _ptr(onehot), _ptr(labels), _ptr(active), _ptr(cm),
+              _ptr(counts), _ptr(sqerr), N, C_, H, W, void_label, _stream())

@@ -1,0 +1,103 @@
+"""ctypes binding of libiiseg.so (the C ABI declared in include/iiseg.h).
+
+There is no CPU fallback: if the library cannot be loaded, or a call fails, this
+module raises.  The library is built in-tree by csrc/build.py (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libiiseg.so')
+
+
+class IisegError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """struct iiseg_conv_desc (include/iiseg.h)."""
+    _fields_ = [
+        ('src0', C.c_void_p), ('src1', C.c_void_p),
+        ('N', C.c_int), ('H', C.c_int), ('W', C.c_int),
+        ('C0', C.c_int), ('C1', C.c_int),
+        ('weight', C.c_void_p), ('bias', C.c_void_p),
+        ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
+        ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
+        ('out', C.c_void_p), ('addend', C.c_void_p),
+        ('relu', C.c_int), ('out_f32', C.c_int),
+    ]
+
+
+class DeconvDesc(C.Structure):
+    """struct iiseg_deconv_desc (include/iiseg.h)."""
+    _fields_ = [
+        ('x', C.c_void_p), ('N', C.c_int), ('H', C.c_int), ('W', C.c_int),
+        ('weight', C.c_void_p), ('bias', C.c_void_p), ('k', C.c_int), ('stride', C.c_int),
+        ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
+        ('addend', C.c_void_p), ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int),
+        ('out', C.c_void_p),
+    ]
+
+
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/iiseg.h declares
+SIGNATURES = {
+    'iiseg_abi_version': (_i, []),
+    'iiseg_last_error': (C.c_char_p, []),
+    'iiseg_device_check': (_i, [_i]),
+    'iiseg_read_diag': (_i, [_vp, _i]),
+    'iiseg_launch_count': (C.c_int64, []),
+    'iiseg_pack_nchw_f32_to_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_unpack_nhwc_bf16_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_unpack_nhwc_f32_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_conv2d_fwd': (_i, [C.POINTER(ConvDesc), _vp]),
+    'iiseg_maxpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_unpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_deconv2d_fwd': (_i, [C.POINTER(DeconvDesc), _vp]),
+    'iiseg_update_blocks': (_i, [_i, _i]),
+    'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    'iiseg_softmax_grad': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libiiseg.so and bind every declared symbol.  Raises if missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IisegError('%s not found: build it with `python -m iterative_inference_segm_b200.csrc.build` '
+                             '(there is no CPU fallback)' % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if lib.iiseg_abi_version() != 1:
+            raise IisegError('libiiseg ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-status entry point; raise IisegError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise IisegError('%s failed (%d): %s' % (name, rc, lib.iiseg_last_error().decode()))
+
+
+def read_diag():
+    lib = load()
+    buf = (C.c_int32 * 8)()
+    n = lib.iiseg_read_diag(buf, 8)
+    return list(buf[:n])
+
+
+def launch_count():
+    return int(load().iiseg_launch_count())

@@ -1,0 +1,60 @@
+"""Repacks Lasagne-layout parameters into the kernels' layouts (done once at build
+time, on the device).
+
+Lasagne conv W is (out, in, kh, kw) (flip_filters=False -> cross-correlation);
+the GEMM B operand is bf16 [Cout_pad][kh*kw][Cin_pad] (K-major), where the input
+channels may be the concatenation of several sources, each padded to a multiple
+of 64 on its own.  Deconv W is (in, out, kh, kw).
+"""
+import numpy as np
+import torch
+
+from ._kernels import pad_channels
+
+
+def _as_f32(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.detach().to(device=device, dtype=torch.float32)
+    return torch.as_tensor(np.asarray(a, dtype=np.float32), device=device)
+
+
+def pack_conv(W, b, splits, cout_pad, device):
+    """W (Cout, sum(real), R, S), splits = [(real, padded), ...] per concatenated source.
+    Returns (bf16 [cout_pad, R*S*sum(padded)], fp32 bias [cout_pad])."""
+    W = _as_f32(W, device)
+    b = _as_f32(b, device)
+    Cout, Cin, R, S = W.shape
+    assert Cin == sum(r for r, _ in splits), (Cin, splits)
+    parts, c0 = [], 0
+    for real, padded in splits:
+        blk = torch.zeros((cout_pad, R, S, padded), dtype=torch.float32, device=device)
+        blk[:Cout, :, :, :real] = W[:, c0:c0 + real].permute(0, 2, 3, 1)
+        parts.append(blk)
+        c0 += real
+    Wk = torch.cat(parts, dim=3).reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
+    bk = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
+    bk[:Cout] = b
+    return Wk, bk
+
+
+def pack_deconv16(W, b, device, scale=1.0):
+    """Lasagne Deconv2DLayer W (in, out, k, k) -> Wt[a][b][ci][co] = W[ci, co, k-1-a, k-1-b]
+    (flip: the layer is the input-gradient of a true convolution), zero-padded to 16x16."""
+    W = _as_f32(W, device) * scale
+    b = _as_f32(b, device) * scale
+    Cin, Cout, k, _ = W.shape
+    assert Cin <= 16 and Cout <= 16
+    Wt = torch.zeros((k, k, 16, 16), dtype=torch.float32, device=device)
+    Wt[:, :, :Cin, :Cout] = W.flip(2, 3).permute(2, 3, 0, 1)
+    bk = torch.zeros((16,), dtype=torch.float32, device=device)
+    bk[:Cout] = b
+    return Wt.contiguous(), bk
+
+
+def load_npz_params(path):
+    """Positional checkpoint arr_0..arr_k (models/DAE_h.py:52-57, models/fcn8.py:177-180)."""
+    with np.load(path) as f:
+        return [f['arr_%d' % i] for i in range(len(f.files))]
+
+
+__all__ = ['pack_conv', 'pack_deconv16', 'load_npz_params', 'pad_channels']

@@ -64,7 +64,12 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     softmax_c(l, p, C);
     float* yb = y + (size_t)n * C * HW + pix;
     float out[kMaxC];
-    if (do_update) {
+    if (do_update == 2) {        // de_fn: grad = y - DAE(y, h), y untouched
+      float* gb = p_out + (size_t)n * C * HW + pix;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) if (c < C) gb[(size_t)c * HW] = yb[(size_t)c * HW] - p[c];
+      return;
+    } else if (do_update) {
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c) {
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     }
     if (y_bf16 != nullptr) store_row_bf16(y_bf16 + ((size_t)n * HW + pix) * Cpad, out, C, Cpad);
   }
+  if (do_update == 2) return;
   if (do_update) {
     __shared__ float red[kUpdBlock / 32];
 #pragma unroll
@@ -154,6 +160,18 @@ extern "C" int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, 1);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_softmax_grad(const float* logits, const float* y, float* grad, int N, int C, int H, int W,
+                                  void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(logits && y && grad, "softmax_grad: null tensor");
+  IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_grad: bad shape");
+  dim3 grid(iiseg_update_blocks(H, W), N);
+  softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 2);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,165 @@
+"""DAE_h (conditional denoising auto-encoder) on the sm_100a kernels: drop-in for
+models/DAE_h.py + models/fcn_down.py + models/fcn_up.py + layers/mylayers.py.
+
+One application DAE(y, h), benchmark configuration (kind='standard',
+unpool_type='trackind', conv_before_pool=1, skip=True, bn=0, dropout=0):
+
+  down, p = 1..P : conv3x3+ReLU (tcgen05 implicit GEMM; pad=`padding` on level 1,
+                   the (h, pool_n) concat of level n_pool+1 read by the loader from
+                   two tensor maps) -> 2x2 max-pool + tie-inclusive mask
+  up,   p = P..1 : mask unpool (DePool2D) -> conv3x3 linear with the skip-sum of
+                   pool_{p-1} fused in the epilogue; level 1 computes only the
+                   centre-crop window and emits fp32 logits
+  tail           : channel softmax (+ the y update) in one streaming kernel
+"""
+import torch
+
+from .. import _kernels as K
+from .._packing import pack_conv, load_npz_params
+from .fcn8 import LayerHandle
+
+
+def _levels(concat_h, additional_pool):
+    last = concat_h[-1]
+    n_pool = int(last[-1]) if 'pool' in last else 0   # models/DAE_h.py:36-39
+    return n_pool, n_pool + additional_pool
+
+
+class DAENet(object):
+    def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
+                 n_filters=64, additional_pool=2, device='cuda'):
+        K.require_device()
+        assert n_classes <= 16
+        self.n_classes = n_classes
+        self.nb_h = nb_features_to_concat
+        self.h_pad = K.pad_channels(nb_features_to_concat)
+        self.padding = padding
+        self.n_pool, self.total = _levels(concat_h, additional_pool)
+        assert self.n_pool >= 1, 'conditioning must be concatenated at a pool layer'
+        self.device = torch.device(device)
+        self.y_cpad = K.pad_channels(n_classes)           # channels of the bf16 copy of y
+        assert len(params) == 4 * self.total, 'expected %d arrays, got %d' % (4 * self.total, len(params))
+        # filters per level: n_filters * 2**p, p < 6 (models/fcn_down.py:96-99)
+        self.filters = []
+        f = n_filters
+        for p in range(self.total):
+            if p < 6:
+                f = n_filters * (2 ** p)
+            self.filters.append(f)
+        assert all(f % 64 == 0 for f in self.filters), 'n_filters must be a multiple of 64'
+        self.down, self.up = [], []
+        cin_real, cin_pad = n_classes, self.y_cpad
+        for p in range(self.total):
+            W, b = params[2 * p], params[2 * p + 1]
+            if p == self.n_pool:   # first conv after the concat: h channels come first
+                splits = [(self.nb_h, self.h_pad), (cin_real, cin_pad)]
+            else:
+                splits = [(cin_real, cin_pad)]
+            self.down.append(pack_conv(W, b, splits, self.filters[p], self.device))
+            cin_real = cin_pad = self.filters[p]
+        up_in = self.filters[-1]
+        for i, p in enumerate(range(self.total, 0, -1)):
+            W, b = params[2 * (self.total + i)], params[2 * (self.total + i) + 1]
+            n_cl = n_classes if p == 1 else self.filters[p - 2]   # models/fcn_up.py:29-34
+            cout_pad = 16 if p == 1 else n_cl
+            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device))
+            up_in = n_cl
+        self._ws = {}
+
+    # -- shapes -----------------------------------------------------------
+    def level_sizes(self, H, W):
+        """Pre-pool spatial size of every level (conv output), SURVEY.md App. B.1."""
+        sizes = []
+        pad = self.padding if self.padding > 0 else 1
+        h, w = H + 2 * pad - 2, W + 2 * pad - 2
+        for p in range(self.total):
+            sizes.append((h, w))
+            h, w = h // 2, w // 2
+        return sizes
+
+    def h_spatial(self, H, W):
+        s = self.level_sizes(H, W)[self.n_pool - 1]
+        return s[0] // 2, s[1] // 2
+
+    def workspace(self, B, H, W):
+        """Activation buffers for one application, allocated once per (B, H, W) and
+        kept resident (they are baked into the captured CUDA graph)."""
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, bf = self.device, torch.bfloat16
+        sizes = self.level_sizes(H, W)
+        ws = {'conv': [], 'pool': [], 'mask': [], 'unpool': [], 'upconv': []}
+        for p, (h, w) in enumerate(sizes):
+            f = self.filters[p]
+            ws['conv'].append(torch.empty((B, h, w, f), dtype=bf, device=dev))
+            ws['pool'].append(torch.empty((B, h // 2, w // 2, f), dtype=bf, device=dev))
+            ws['mask'].append(torch.empty((B, h // 2, w // 2, f // 8), dtype=torch.int32, device=dev))
+            ws['unpool'].append(torch.empty((B, h, w, f), dtype=bf, device=dev))
+        for p in range(self.total, 1, -1):   # up_conv_p output, p > 1: size of level p, channels of level p-1
+            h, w = sizes[p - 1]
+            assert (h, w) == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
+            ws['upconv'].append(torch.empty((B, h, w, self.filters[p - 2]), dtype=bf, device=dev))
+        ws['logits'] = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    # -- one application ----------------------------------------------------
+    def logits(self, h_bf16, y_bf16):
+        """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
+        Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16)."""
+        B, H, W, _ = y_bf16.shape
+        ws = self.workspace(B, H, W)
+        sizes = self.level_sizes(H, W)
+        assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.h_pad,), \
+            (tuple(h_bf16.shape), self.h_spatial(H, W), self.h_pad)
+        x = y_bf16
+        for p in range(self.total):
+            Wk, bk = self.down[p]
+            pad = self.padding if (p == 0 and self.padding > 0) else 1
+            if p == self.n_pool:
+                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, out=ws['conv'][p])
+            else:
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, out=ws['conv'][p])
+            K.maxpool2(ws['conv'][p], True, pooled=ws['pool'][p], mask=ws['mask'][p])
+            x = ws['pool'][p]
+        u = ws['pool'][-1]
+        for i, p in enumerate(range(self.total, 0, -1)):
+            h, w = sizes[p - 1]
+            K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p - 1])
+            Wk, bk = self.up[i]
+            if p > 1:
+                u = K.conv2d(ws['unpool'][p - 1], Wk, bk, 3, 3, 1, relu=False, addend=ws['pool'][p - 2],
+                             out=ws['upconv'][i])
+            else:   # centre crop (CroppingLayer, layers/mylayers.py:36-57): compute only that window
+                K.conv2d(ws['unpool'][0], Wk, bk, 3, 3, 1, relu=False, window=((h - H) // 2, (w - W) // 2, H, W),
+                         out=ws['logits'], out_f32=True)
+        return ws['logits']
+
+
+def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_concat,
+             padding, ae_h=False, void_labels=[], path_weights='/Tmp/romerosa/itinf/models/',
+             model_name='dae_model.npz', trainable=False, load_weights=False,
+             out_nonlin=None, concat_h=['input'], noise=0.1, n_filters=64,
+             conv_before_pool=1, additional_pool=0, dropout=0., skip=False,
+             unpool_type='standard', bn=0, params=None):
+    """Same arguments as the reference builder (models/DAE_h.py:12-17); returns the handle
+    of 'probs_dimshuffle'.  The symbolic inputs are ignored.  Built for the benchmark
+    configuration; other variants raise.  `noise` only matters for training and for the
+    reference's non-deterministic mask sub-graph (layers/mylayers.py:91-93); inference here
+    is the deterministic noise=0 graph."""
+    import os
+    if unpool_type != 'trackind' or not skip or conv_before_pool != 1 or bn or dropout > 0 or ae_h:
+        raise NotImplementedError('B200 DAE_h supports unpool_type=trackind, skip=True, conv_before_pool=1, '
+                                  'bn=0, dropout=0, ae_h=False')
+    concat_h = list(concat_h)
+    if len(concat_h) != 1 or 'pool' not in concat_h[-1]:
+        raise NotImplementedError('B200 DAE_h concatenates h at one pool layer (e.g. concat_h=[\'pool4\'])')
+    if params is None:
+        if not load_weights:
+            raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')
+        params = load_npz_params(os.path.join(path_weights, model_name))
+    net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
+                 n_filters=n_filters, additional_pool=additional_pool)
+    return LayerHandle(net, 'probs_dimshuffle', n_classes)

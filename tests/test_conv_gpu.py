@@ -1,0 +1,96 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv and the SIMT transposed conv against a plain
+PyTorch fp32 reference on the SAME bf16-rounded operands (so the only differences are the fp32
+accumulation order and the final bf16 rounding of the output: tolerance 2^-7 relative, stated
+below).  Shapes cover ragged tiles, the pad=100 first layer, the dual-source (concat) loader,
+the fused skip-sum, the cropped fp32 output window, 1x1 and 7x7 filters."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# N, H, W, C0, C1, Cout, R, pad, relu, addend, window, out_f32
+CASES = [
+    (1, 8, 16, 64, 0, 64, 1, 0, 0, 0, None, 0),
+    (1, 8, 16, 64, 0, 256, 1, 0, 1, 0, None, 0),
+    (2, 37, 45, 64, 0, 128, 3, 1, 1, 0, None, 0),
+    (2, 17, 21, 256, 0, 512, 3, 1, 1, 0, None, 0),
+    (2, 17, 21, 128, 64, 256, 3, 1, 1, 0, None, 0),
+    (2, 33, 29, 128, 0, 64, 3, 1, 0, 1, None, 0),
+    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),
+    (1, 40, 56, 64, 0, 16, 3, 1, 0, 0, (5, 7, 24, 32), 1),
+    (1, 17, 21, 128, 0, 256, 7, 0, 1, 0, None, 0),
+    (1, 11, 15, 256, 0, 16, 1, 0, 1, 0, None, 1),
+    (4, 139, 169, 64, 0, 128, 3, 1, 1, 0, None, 0),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[str(c) for c in CASES])
+def test_conv_matches_fp32_reference(cuda, case):
+    from iterative_inference_segm_b200 import _kernels as K
+    N, H, W, C0, C1, Cout, R, pad, relu, addend, window, out_f32 = case
+    torch.manual_seed(0)
+    Cin = C0 + C1
+    x = torch.randn(N, Cin, H, W, device=cuda).to(torch.bfloat16)
+    Wt = (torch.randn(Cout, Cin, R, R, device=cuda) / (Cin * R * R) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=cuda)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    src0 = xn[..., :C0].contiguous()
+    src1 = xn[..., C0:].contiguous() if C1 else None
+    Wk = Wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+    fOH, fOW = H + 2 * pad - R + 1, W + 2 * pad - R + 1
+    oh0, ow0, OH, OW = window if window else (0, 0, fOH, fOW)
+    add = torch.randn(N, OH, OW, Cout, device=cuda).to(torch.bfloat16) if addend else None
+    out = K.conv2d(src0, Wk, b, R, R, pad, relu, src1=src1, addend=add, window=window, out_f32=bool(out_f32))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), Wt.float(), b, padding=pad)[:, :, oh0:oh0 + OH, ow0:ow0 + OW]
+    if add is not None:
+        ref = ref + add.float().permute(0, 3, 1, 2)
+    if relu:
+        ref = torch.relu(ref)
+    got = out.float().permute(0, 3, 1, 2)
+    rel = 1e-4 if out_f32 else 2.0 ** -7      # fp32 out: accumulation order only; bf16 out: + output rounding
+    assert bool(((got - ref).abs() <= rel * ref.abs().clamp(min=1.0)).all()), float((got - ref).abs().max())
+
+
+def test_conv_constant_region_is_bit_constant(cuda):
+    """Spatially constant input -> every interior output pixel must be bit-identical (one uniform K
+    loop, zero padding by TMA fill), which the tie-inclusive pool mask relies on."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(1)
+    C, Cout, H, W = 64, 64, 40, 50
+    x = torch.randn(1, 1, 1, C, device=cuda).expand(1, H, W, C).to(torch.bfloat16).contiguous()
+    Wk = (torch.randn(Cout, 9 * C, device=cuda) / 24).to(torch.bfloat16)
+    out = K.conv2d(x, Wk, torch.zeros(Cout, device=cuda), 3, 3, 1, relu=False)
+    inner = out[0, 1:-1, 1:-1].reshape(-1, Cout)
+    assert bool((inner == inner[0]).all())
+
+
+@pytest.mark.parametrize('k,stride,H,W,window,addend', [
+    (4, 2, 11, 15, None, False), (4, 2, 11, 15, (0, 0, 24, 32), True), (16, 8, 7, 9, (24, 28, 20, 30), False)])
+def test_deconv_matches_conv_transpose(cuda, k, stride, H, W, window, addend):
+    """Deconv2DLayer(flip_filters=False) == conv_transpose2d with flipped kernels; fp32, tolerance 1e-4."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_deconv16
+    torch.manual_seed(2)
+    N, C = 2, 11
+    x = torch.randn(N, C, H, W, device=cuda)
+    Wd = torch.randn(C, C, k, k, device=cuda) / (C * (k / stride) ** 2) ** 0.5
+    b = torch.randn(C, device=cuda)
+    Wt, bk = pack_deconv16(Wd, b, cuda)
+    xn = torch.zeros(N, H, W, 16, device=cuda)
+    xn[..., :C] = x.permute(0, 2, 3, 1)
+    fH, fW = (H - 1) * stride + k, (W - 1) * stride + k
+    oh0, ow0, OH, OW = window if window else (0, 0, fH, fW)
+    add, off = None, (0, 0)
+    if addend:
+        add = torch.randn(N, OH + 10, OW + 10, 16, device=cuda)
+        add[..., C:] = 0
+        off = (5, 5)
+    out = K.deconv16(xn, Wt, bk, k, stride, window=window, addend=add, addend_off=off)
+    ref = F.conv_transpose2d(x, Wd.flip(2, 3), b, stride=stride)[:, :, oh0:oh0 + OH, ow0:ow0 + OW]
+    if add is not None:
+        ref = ref + add[:, 5:5 + OH, 5:5 + OW, :C].permute(0, 3, 1, 2)
+    got = out[..., :C].permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) < 1e-4
+    assert float(out[..., C:].abs().max()) == 0.0

@@ -1,0 +1,212 @@
+"""Pins the CPU oracle: the reference ships no tests or fixtures ("parity unpinned"), so the
+oracle is checked against what CAN be derived from the reference code by hand -- the shape
+tables, the Lasagne layer identities, hand-computed metric examples -- against an fp64 re-run
+of itself, and against the committed golden vectors (tests/golden/, made by make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import lasagne_semantics as L, loop, metrics as M, nets, weights
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+# ---- shapes (derived from models/fcn_down.py, fcn_up.py, fcn8.py) -------
+def test_dae_param_shapes_benchmark_config():
+    sh = nets.dae_param_shapes(11, 512, n_filters=64, concat_h=('pool4',), additional_pool=2)
+    names = [s[0] for s in sh]
+    assert names == ['conv%d_1' % i for i in range(1, 7)] + ['up_conv%d' % i for i in range(6, 0, -1)]
+    W = {s[0]: s[1] for s in sh}
+    assert W['conv1_1'] == (64, 11, 3, 3)
+    assert W['conv5_1'] == (1024, 1024, 3, 3)      # (512 h + 512) -> 1024
+    assert W['conv6_1'] == (2048, 1024, 3, 3)
+    assert W['up_conv6'] == (1024, 2048, 3, 3)
+    assert W['up_conv5'] == (512, 1024, 3, 3)      # skip-sum partner is the UN-concatenated pool4
+    assert W['up_conv1'] == (11, 64, 3, 3)
+    n_params = sum(int(np.prod(s[1])) + s[2][0] for s in sh)
+    assert abs(n_params - 55.0e6) < 0.1e6           # "DAE parameters: 55.0 M"
+
+
+def test_fcn8_param_shapes():
+    sh = nets.fcn8_param_shapes(3, 11)
+    assert len(sh) == 21                            # 42 arrays
+    assert sh[13][0] == 'fc6' and sh[13][1] == (4096, 512, 7, 7)
+    assert sh[-1][0] == 'upsample' and sh[-1][1] == (11, 11, 16, 16)
+
+
+def test_fcn8_shapes_small():
+    """pad=100 geometry: pool4 of a HxW image is ((H+198)//16, (W+198)//16); probs has the input size."""
+    X, _, _ = weights.synthetic_batch(1, 32, 48)
+    p = weights.synthetic_fcn8_params(3, 11)
+    h, y0, s2, s4, up = nets.fcn8_forward(p, X, 11, layer=('pool4', 'probs_dimshuffle', 'score2', 'score4', 'upsample'))
+    assert h.shape == (1, 512, (32 + 198) // 16, (48 + 198) // 16)
+    assert y0.shape == (1, 11, 32, 48)
+    assert torch.allclose(y0.sum(1), torch.ones(1, 32, 48), atol=1e-5)
+
+
+@pytest.mark.parametrize('H,W', [(360, 480), (224, 224)])
+def test_fcn8_geometry_table(H, W):
+    """SURVEY.md App. B.2 by arithmetic only (no forward pass)."""
+    s = [H + 198, W + 198]
+    sizes = []
+    for _ in range(5):
+        s = [s[0] // 2, s[1] // 2]
+        sizes.append(tuple(s))
+    if (H, W) == (360, 480):
+        assert sizes[3] == (34, 42) and sizes[4] == (17, 21)
+        fc6 = (sizes[4][0] - 6, sizes[4][1] - 6)
+        assert fc6 == (11, 15)
+        score2 = ((fc6[0] - 1) * 2 + 4, (fc6[1] - 1) * 2 + 4)
+        assert score2 == (24, 32) and (sizes[3][0] - 24) // 2 == 5
+        score4 = ((score2[0] - 1) * 2 + 4, (score2[1] - 1) * 2 + 4)
+        assert score4 == (50, 66) and (sizes[2][0] - 50) // 2 == 9
+        up = ((score4[0] - 1) * 8 + 16, (score4[1] - 1) * 8 + 16)
+        assert up == (408, 536) and ((up[0] - H) // 2, (up[1] - W) // 2) == (24, 28)
+    else:
+        assert sizes[3] == (26, 26)
+
+
+def test_dae_level_sizes_360x480():
+    s = (360 + 198, 480 + 198)
+    expect = [(558, 678), (279, 339), (139, 169), (69, 84), (34, 42), (17, 21)]
+    for e in expect:
+        assert s == e
+        s = (s[0] // 2, s[1] // 2)
+    assert s == (8, 10)
+    assert ((558 - 360) // 2, (678 - 480) // 2) == (99, 99)
+
+
+# ---- Lasagne identities ------------------------------------------------------------------
+def test_tie_inclusive_mask_and_depool():
+    x = torch.tensor([[[[1., 1., 0.], [0., 1., 5.], [2., 3., 4.]]]])      # 3x3: trailing row/col dropped
+    m = L.tie_mask(x)
+    assert m.tolist() == [[[[1., 1., 0.], [0., 1., 0.], [0., 0., 0.]]]]   # all three 1s tie
+    u = torch.tensor([[[[7.]]]])
+    assert L.depool2d(u, x).tolist() == [[[[7., 7., 0.], [0., 7., 0.], [0., 0., 0.]]]]
+    # torch's own unpool routes to ONE element only -> must not be used for the reference semantics
+    _, idx = F.max_pool2d(x, 2, 2, return_indices=True)
+    first_only = F.max_unpool2d(u, idx, 2, 2, output_size=(3, 3))
+    assert float(first_only.sum()) == 7.0
+
+
+def test_tie_mask_equals_theano_maxpoolgrad_rule():
+    """MaxPoolGrad on CPU: for each window element, gx += gz if x == max."""
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(2, 3, 7, 9)).round()            # many exact ties and zeros
+    m = L.tie_mask(x)
+    ref = torch.zeros_like(x)
+    for i in range(3):
+        for j in range(4):
+            win = x[:, :, 2 * i:2 * i + 2, 2 * j:2 * j + 2]
+            mx = win.amax((2, 3), keepdim=True)
+            ref[:, :, 2 * i:2 * i + 2, 2 * j:2 * j + 2] = (win == mx).float()
+    assert torch.equal(m, ref)
+
+
+def test_deconv_is_flipped_conv_transpose():
+    """Deconv2DLayer(flip_filters=False) = input-gradient of a TRUE convolution."""
+    torch.manual_seed(1)
+    x = torch.randn(1, 3, 5, 6)
+    W = torch.randn(3, 4, 4, 4)     # (in, out, k, k)
+    b = torch.randn(4)
+    y = L.deconv2d(x, W, b, 2)
+    # gradient of sum(conv_true(z, W') * x) wrt z, conv_true = correlation with flipped kernel
+    z = torch.zeros(1, 4, y.shape[2], y.shape[3], requires_grad=True)
+    out = F.conv2d(z, W.flip(2, 3), stride=2)       # true convolution of z with W (in=4 -> out=3)
+    (out * x).sum().backward()
+    assert torch.allclose(y - b.view(1, -1, 1, 1), z.grad, atol=1e-5)
+
+
+def test_center_crop_offsets():
+    a = torch.arange(7 * 9.).view(1, 1, 7, 9)
+    c = L.center_crop_to(a, 4, 4)
+    assert c[0, 0, 0, 0] == a[0, 0, 1, 2]       # offsets (7-4)//2 = 1, (9-4)//2 = 2
+
+
+# ---- metrics: hand-computed examples (metrics.py) ----------------------------------------------
+def _onehot(lab, C):
+    return np.eye(C, dtype=np.float32)[lab].transpose(0, 3, 1, 2)
+
+
+def test_metrics_hand_example():
+    # 1 image, 2x2 pixels, 3 classes + void(3).  truth: [[0,1],[2,void]]  pred: [[0,2],[2,1]]
+    lab = np.array([[[0, 1], [2, 3]]])
+    t = _onehot(lab, 4)
+    y = np.zeros((1, 3, 2, 2), np.float32)
+    for (i, j), c in {(0, 0): 0, (0, 1): 2, (1, 0): 2, (1, 1): 1}.items():
+        y[0, :, i, j] = 0.1
+        y[0, c, i, j] = 0.8
+    cm = M.confusion_matrix(y, t, 3)
+    assert cm.tolist() == [[1, 0, 0], [0, 0, 0], [0, 1, 1]]     # rows = prediction; void pixel dropped
+    jac = M.jaccard(y, t, 3)
+    assert jac.dtype == np.float32
+    assert jac.tolist() == [[1, 0, 1], [1, 1, 2]]               # [TP; TP+FP+FN]
+    assert M.accuracy(y, t, [3]) == np.float32(2. / 3.)
+    # squared error: mean over 3 channels, masked by non-void, over 3 non-void pixels
+    per_pix = [((0.8 - 1) ** 2 + 2 * 0.1 ** 2) / 3, (0.1 ** 2 + (0.1 - 1) ** 2 + 0.8 ** 2) / 3,
+               ((0.8 - 1) ** 2 + 2 * 0.1 ** 2) / 3]
+    assert abs(float(M.squared_error(y, t, 3)) - sum(per_pix) / 3) < 1e-6
+
+
+def test_argmax_tie_is_first_index():
+    y = np.full((1, 3, 1, 1), 1 / 3., np.float32)
+    t = _onehot(np.array([[[0]]]), 4)
+    assert M.confusion_matrix(y, t, 3)[0, 0] == 1
+
+
+# ---- the loop (iterative_inference.py:258-291) ---------------------------------------------------
+def _tiny_dae(seed=3):
+    """A 3-level DAE (concat at pool1, additional_pool=2) small enough for CPU unit tests."""
+    gen = torch.Generator().manual_seed(seed)
+    sh = nets.dae_param_shapes(4, 8, n_filters=8, concat_h=('pool1',), additional_pool=2)
+    params = []
+    for name, ws, bs in sh:
+        params += [weights.glorot_uniform(ws, gen), torch.zeros(bs)]
+    return params
+
+
+def test_loop_update_order_and_early_exit():
+    params = _tiny_dae()
+    torch.manual_seed(0)
+    y0 = torch.softmax(torch.randn(1, 4, 12, 14), 1)
+    h = torch.relu(torch.randn(1, 8, 6, 7))
+    kw = dict(concat_h=('pool1',), additional_pool=2)
+    y, n_exec, per_iter, tr = loop.iterate_image(params, h, y0, 0.5, 5, 0, eps=0.0, record=True, **kw)
+    assert n_exec == 5
+    p0 = nets.dae_forward(params, y0, h, 0, **kw)
+    y1 = torch.clamp(y0 - 0.5 * (y0 - p0), 0, 1)
+    assert torch.allclose(tr[0]['y'], y1)
+    # huge eps: exactly one update happens, then break BEFORE the metrics of that iteration
+    L_ = torch.zeros(1, 5, 12, 14); L_[:, 0] = 1
+    y, n_exec, per_iter, _ = loop.iterate_image(params, h, y0, 0.5, 5, 0, eps=1e9, t_im=L_.numpy(), n_classes=4,
+                                                void_labels=[4], **kw)
+    assert n_exec == 1 and per_iter == [] and torch.allclose(y, y1)
+
+
+def test_fp32_vs_fp64_single_application():
+    params = _tiny_dae()
+    torch.manual_seed(1)
+    y0 = torch.softmax(torch.randn(1, 4, 12, 14), 1)
+    h = torch.relu(torch.randn(1, 8, 6, 7))
+    kw = dict(concat_h=('pool1',), additional_pool=2)
+    p32 = nets.dae_forward(params, y0, h, 0, **kw)
+    p64 = nets.dae_forward([p.double() for p in params], y0.double(), h.double(), 0, **kw)
+    assert float((p32.double() - p64).abs().max()) < 1e-5
+
+
+# ---- golden vectors ----------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['dae_32x40', 'fcn8_32x40', 'loop_32x40'])
+def test_golden(name):
+    from tests.golden import make_golden
+    g = np.load(os.path.join(GOLD, name + '.npz'))
+    fresh = make_golden.CASES[name]()
+    for k in g.files:
+        a, b = g[k], fresh[k]
+        assert a.shape == b.shape, k
+        if a.dtype.kind in 'iu':
+            assert np.array_equal(a, b), k
+        else:
+            assert np.allclose(a, b, atol=5e-5, rtol=1e-4), (k, float(np.abs(a - b).max()))

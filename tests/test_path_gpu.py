@@ -1,0 +1,114 @@
+"""End-to-end GPU parity of the hot path against the CPU oracle on the same seeded inputs and
+weights: FCN8 forward, one DAE application (teacher-forced), the N-step loop with metrics.
+
+Arithmetic: bf16 operands, fp32 accumulation (dtype "bf16").  Tolerances are the bf16 variant's
+own: the pool mask is a discontinuous function of the conv outputs, so bf16
+rounding flips some tie decisions; bounds below are max-abs on probabilities and argmax
+agreement, measured with tools/parity_report.py and given ~2x headroom.  The integer reductions
+(confusion matrix, counts) are bit-exact GIVEN the labels, which is asserted separately by
+feeding the oracle the device's own y."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loop, metrics as M, nets, weights
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+NCLS = 11
+TOL_FCN_PROBS = 3e-2      # y0 max-abs, bf16 FCN8 (logit gain 10 amplifies bf16 rounding)
+TOL_DAE_P = 1e-2          # one DAE application, max-abs on p
+TOL_LOOP_Y = 1e-2         # y after the loop, max-abs
+MIN_ARGMAX = 0.99         # argmax agreement
+
+
+def _nets(cuda):
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf)
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=fcn[0].output_shape[1], padding=100,
+                   concat_h=['pool4'], noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2,
+                   skip=True, unpool_type='trackind', params=pd)
+    return pf, pd, fcn, dae
+
+
+@pytest.fixture(scope='module')
+def built(cuda):
+    return _nets(cuda)
+
+
+def test_fcn8_forward_vs_golden(cuda, built):
+    from iterative_inference_segm_b200.functions import function_pred_fcn
+    pf, pd, fcn, dae = built
+    g = np.load(os.path.join(GOLD, 'fcn8_32x40.npz'))
+    h, y0 = function_pred_fcn(fcn)(g['X'])
+    assert h.shape == g['pool4'].shape and y0.shape == g['probs'].shape and h.dtype == np.float32
+    scale = float(np.abs(g['pool4']).max())
+    assert float(np.abs(h - g['pool4']).max()) < 3e-2 * scale
+    assert float(np.abs(y0 - g['probs']).max()) < TOL_FCN_PROBS
+    assert float((y0.argmax(1) == g['probs'].argmax(1)).mean()) >= MIN_ARGMAX
+
+
+def test_dae_application_vs_golden(cuda, built):
+    """Teacher-forced: the oracle's own (h, y) in, compare p = DAE(y, h)."""
+    from iterative_inference_segm_b200.functions import function_pred_dae, function_de
+    pf, pd, fcn, dae = built
+    g = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    p = function_pred_dae(dae)(g['h'], g['y'])
+    assert p.shape == g['p'].shape
+    assert float(np.abs(p - g['p']).max()) < TOL_DAE_P
+    assert np.allclose(p.sum(1), 1.0, atol=1e-5)
+    de = function_de(dae)(g['h'], g['y'])
+    assert float(np.abs(de - (g['y'] - p)).max()) < 1e-6
+
+
+def test_loop_vs_oracle_and_exact_metrics(cuda, built):
+    from iterative_inference_segm_b200.functions import IterativeInference, jaccard_from_cm
+    pf, pd, fcn, dae = built
+    gd = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    gl = np.load(os.path.join(GOLD, 'loop_32x40.npz'))
+    ii = IterativeInference(dae, NCLS, [NCLS])
+    h = torch.from_numpy(gd['h']).to(cuda)
+    y0 = torch.from_numpy(gd['y']).to(cuda)
+    labels = torch.from_numpy(gl['labels']).to(cuda)
+    for use_graph in (False, True):
+        res = ii.run(h, y0, 0.05, 4, labels=labels, per_iter_metrics=True, use_graph=use_graph)
+        torch.cuda.synchronize()
+        y = res['y'].cpu().numpy()
+        assert res['n_exec'].cpu().tolist() == gl['n_exec'].tolist()
+        assert float(np.abs(y - gl['y_final']).max()) < TOL_LOOP_Y
+        assert float((y.argmax(1) == gl['y_final'].argmax(1)).mean()) >= MIN_ARGMAX
+        # integer reductions: bit-exact given identical labels -> oracle metrics of the DEVICE's y
+        onehot = np.eye(NCLS + 1, dtype=np.float32)[gl['labels']].transpose(0, 3, 1, 2)
+        cm = res['cm'].sum(0).cpu().numpy().reshape(NCLS, NCLS)
+        assert np.array_equal(cm, M.confusion_matrix(y, onehot, NCLS))
+        assert np.array_equal(jaccard_from_cm(cm), M.jaccard(y, onehot, NCLS))
+        c, v = M.accuracy_counts(y, onehot, [NCLS])
+        assert res['counts'].sum(0).cpu().tolist() == [c, v]
+        assert len(res['iter']) == 4
+    # graph replay is deterministic
+    y1 = ii.run(h, y0, 0.05, 4, labels=labels, per_iter_metrics=True)['y'].clone()
+    y2 = ii.run(h, y0, 0.05, 4, labels=labels, per_iter_metrics=True)['y'].clone()
+    assert torch.equal(y1, y2)
+
+
+def test_early_exit_semantics(cuda, built):
+    """eps huge: every image does exactly one update, then is frozen; no per-iteration metrics."""
+    from iterative_inference_segm_b200.functions import IterativeInference
+    pf, pd, fcn, dae = built
+    gd = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    gl = np.load(os.path.join(GOLD, 'loop_32x40.npz'))
+    ii = IterativeInference(dae, NCLS, [NCLS])
+    h = torch.from_numpy(gd['h']).to(cuda)
+    y0 = torch.from_numpy(gd['y']).to(cuda)
+    labels = torch.from_numpy(gl['labels']).to(cuda)
+    one = ii.run(h, y0, 0.05, 1, eps=0.0, labels=labels, use_graph=False)['y'].clone()
+    res = ii.run(h, y0, 0.05, 3, eps=1e9, labels=labels, per_iter_metrics=True, use_graph=False)
+    assert res['n_exec'].cpu().tolist() == [1]
+    assert torch.equal(res['y'], one)
+    assert all(int(a.cm.sum()) == 0 for a in res['iter'])
+    assert int(res['cm'].sum()) > 0          # the final batch-level val_fn still runs on the frozen y
