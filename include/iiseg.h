@@ -150,6 +150,11 @@ int iiseg_metrics_accumulate(const float* y, const float* onehot,
                              int64_t* cm, int64_t* counts, double* sqerr, int N,
                              int C, int H, int W, int void_label, void* stream);
 
+/* labels[n,h,w] = argmax_c onehot[n,c,h,w], first index on ties: the T.argmax(y_true, axis=1)
+ * of metrics.py:20-21,49-50 done once per batch.  onehot NCHW fp32 [N,C1,H,W]. */
+int iiseg_onehot_to_labels(const float* onehot, int32_t* labels, int N, int C1, int H,
+                           int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

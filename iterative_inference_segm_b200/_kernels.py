@@ -203,3 +203,12 @@ def metrics_accumulate(y, cm, counts, sqerr, onehot=None, labels=None, active=No
     _chk(sqerr, torch.float64, 'sqerr')
     _lib.call('iiseg_metrics_accumulate', _ptr(y), _ptr(onehot), _ptr(labels), _ptr(active), _ptr(cm),
               _ptr(counts), _ptr(sqerr), N, C_, H, W, void_label, _stream())
+
+
+def onehot_to_labels(onehot, labels=None):
+    _chk(onehot, F32, 'onehot')
+    N, C1, H, W = onehot.shape
+    if labels is None:
+        labels = torch.empty((N, H, W), dtype=torch.int32, device=onehot.device)
+    _lib.call('iiseg_onehot_to_labels', _ptr(onehot), _ptr(labels), N, C1, H, W, _stream())
+    return labels

@@ -60,6 +60,7 @@ SIGNATURES = {
     'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     'iiseg_softmax_grad': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

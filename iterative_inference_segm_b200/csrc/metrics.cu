@@ -102,7 +102,37 @@ __global__ void __launch_bounds__(kMetBlock) metrics_kernel(
   }
 }
 
+// labels[n,h,w] = argmax_c onehot[n,c,h,w] (first index on ties), as metrics.py does with one_hot=True
+__global__ void __launch_bounds__(256) onehot_to_labels_kernel(const float* __restrict__ onehot, int32_t* __restrict__ labels,
+                                                               int C1, int HW, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW;
+    const int pix = (int)(i - n * HW);
+    const float* tb = onehot + n * C1 * HW + pix;
+    float best = tb[0]; int arg = 0;
+    for (int c = 1; c < C1; ++c) {
+      const float v = tb[(size_t)c * HW];
+      if (v > best) { best = v; arg = c; }
+    }
+    labels[i] = arg;
+  }
+}
+
 }  // namespace iiseg
+
+extern "C" int iiseg_onehot_to_labels(const float* onehot, int32_t* labels, int N, int C1, int H, int W, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(onehot && labels, "onehot_to_labels: null tensor");
+  IISEG_CHECK(N > 0 && C1 >= 1 && H > 0 && W > 0, "onehot_to_labels: bad shape");
+  const long long total = (long long)N * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  onehot_to_labels_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      onehot, labels, C1, H * W, total);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int iiseg_metrics_accumulate(const float* y, const float* onehot, const int32_t* labels,
                                         const int32_t* active, int64_t* cm, int64_t* counts, double* sqerr, int N,

@@ -194,14 +194,16 @@ class IterativeInference(object):
             K.metrics_accumulate(st['y'], acc.cm, acc.counts, acc.sqerr, labels=st['labels'],
                                  void_label=self.void_label)
 
-    def run(self, h, y0, step, num_iter, eps=EPSILON, labels=None, per_iter_metrics=False, use_graph=True):
+    def run(self, h, y0, step, num_iter, eps=EPSILON, labels=None, onehot=None, per_iter_metrics=False,
+            use_graph=True):
         """h: NHWC bf16 (internal, from FCN8Net.forward) or NCHW fp32; y0: NCHW fp32;
-        labels: int (B,H,W) class indices with void = the void label, or None.
+        labels: int (B,H,W) class indices with void = the void label, or onehot: the reference's
+        (B,C+1,H,W) float32 target (argmax'd once on the device), or neither.
         Returns a dict of device tensors: y (B,C,H,W), n_exec, norm_hist, cm / counts /
         sqerr of the final batch-level val_fn, and the per-iteration accumulators."""
         B, Cc, H, W = y0.shape
         assert Cc == self.C
-        with_metrics = labels is not None
+        with_metrics = labels is not None or onehot is not None
         per_iter = bool(per_iter_metrics and with_metrics)
         st = self._buffers(B, H, W, num_iter, per_iter)
         if h.dtype == torch.bfloat16:
@@ -210,7 +212,9 @@ class IterativeInference(object):
             K.pack_nchw(h.contiguous(), self.net.h_pad, out=st['h'])
         st['y'].copy_(y0)
         K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'])
-        if with_metrics:
+        if onehot is not None:
+            K.onehot_to_labels(onehot.contiguous(), st['labels'])
+        elif labels is not None:
             st['labels'].copy_(labels)
         if use_graph:
             gkey = (float(step), float(eps), with_metrics)
