@@ -77,6 +77,18 @@ struct alignas(64) ConvParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One elected lane of a converged warp (elect.sync).  Unlike `lane == 0` this tells ptxas that
+// exactly one thread runs the guarded code, so the uniform-datapath instructions inside
+// (UTCHMMA, UTCBAR, UTMALDG) are emitted once instead of inside a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -256,19 +268,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_instr_desc<BN>();
-      int stage = 0; uint32_t phase = 0;
-      int iter = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
-        const int as = iter & 1;
-        const uint32_t aphase = (iter >> 1) & 1u;
-        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+    // The whole warp walks the pipeline (waits are warp-uniform); one elected lane issues.
+    constexpr uint32_t idesc = make_instr_desc<BN>();
+    int stage = 0; uint32_t phase = 0;
+    int iter = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase, p.diag, 3, stage);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.diag, 3, stage);
-          tcgen05_fence_after();
+        if (elect_one_sync()) {
           const uint64_t a_desc = make_smem_desc(smem_a + stage * kAStageBytes);
           const uint64_t b_desc = make_smem_desc(smem_b + stage * Cfg::kBStageBytes);
 #pragma unroll
@@ -278,15 +291,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
           }
           umma_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
           if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar(as));  // accumulator ready
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
     // ===================== Epilogue =====================
     const int q = warp - 4;                 // TMEM lane quadrant of this warp
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the box
-    const int epi_tid = threadIdx.x - 128;
     const int hl = m / p.TW, wl = m - hl * p.TW;
     int iter = 0;
     int store_buf = 0;
@@ -314,14 +327,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
               add[j] = valid ? ldg_nc_v4(p.addend + pix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
           }
           // the staging buffer we are about to overwrite must have been read by its TMA store
-          if (epi_tid == 0) tma_store_wait_read<1>();
+          if (q == 0 && elect_one_sync()) tma_store_wait_read<1>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
+          uint32_t vall[64];        // all 64 accumulator columns of this chunk in flight, one wait
+#pragma unroll
+          for (int half = 0; half < 4; ++half) tmem_ld_x16(taddr + chunk * 64 + half * 16, vall + half * 16);
+          tmem_ld_wait();
 #pragma unroll
           for (int half = 0; half < 4; ++half) {
-            uint32_t v[16];
-            tmem_ld_x16(taddr + chunk * 64 + half * 16, v);
-            tmem_ld_wait();
+            const uint32_t* v = vall + half * 16;
             uint32_t packed[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (epi_tid == 0) {
+          if (q == 0 && elect_one_sync()) {
             tma_store_4d(&p.tm_out, sbuf, cbase, tc.tw * p.TW, tc.th * p.TH, tc.n);
             tma_store_commit();
           }
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         }
       }
     }
-    if (Cfg::kTmaStore && epi_tid == 0) tma_store_wait_read<0>();
+    if (Cfg::kTmaStore && q == 0 && elect_one_sync()) tma_store_wait_read<0>();
   }
 
   tcgen05_fence_before();
