@@ -23,6 +23,8 @@
 //     swizzled smem -> TMA store, or direct fp32/bf16 stores for 16-channel
 //     outputs).  Persistent CTAs, one per SM, static round-robin tile schedule.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/iiseg.h"
@@ -32,16 +34,20 @@ namespace iiseg {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements: one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kAStageBytes = kBlockM * 128;  // 16 KiB
+constexpr int kAStageBytes = kBlockM * 128;  // 16 KiB per k-block
 constexpr int kStagingBytes = kBlockM * 128; // one 64-channel bf16 output chunk
-constexpr int kNumThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kNumThreads = 384;             // 4 pipeline warps + 8 epilogue warps
+constexpr int kEpilogueThreads = 256;
 constexpr long long kTimeoutCycles = 4000000000LL;  // ~2 s: a stuck pipeline traps instead of hanging
 
+// BN output channels per tile; G k-blocks (64 channels of one tap) per pipeline stage.  The
+// producer/MMA handshake costs ~350 cycles per stage whatever it carries (measured), so narrow
+// tiles, whose k-block is only 128-256 tensor cycles, carry several k-blocks per stage.
 template <int BN>
 struct ConvCfg {
-  static constexpr int kBStageBytes = BN * 128;
-  static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+  static constexpr int G = BN == 16 ? 3 : (BN == 256 ? 1 : 2);
+  static constexpr int kBBlockBytes = BN * 128;
+  static constexpr int kStageBytes = G * (kAStageBytes + kBBlockBytes);
   static constexpr bool kTmaStore = BN >= 64;
   static constexpr int kStagingTotal = kTmaStore ? 2 * kStagingBytes : 0;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStagingTotal;
@@ -50,7 +56,7 @@ struct ConvCfg {
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingTotal + 256;
-  static_assert(kStages >= 2, "pipeline too shallow");
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct alignas(64) ConvParams {
@@ -69,6 +75,8 @@ struct alignas(64) ConvParams {
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   int OH, OW, Cout;
   int relu, out_f32;
+  int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
+  int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue
 };
 
 // ---------------------------------------------------------------------------
@@ -183,6 +191,11 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------
@@ -201,11 +214,14 @@ template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int G = Cfg::G;
+  const int n_stages = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_a + kStages * kAStageBytes;
-  const uint32_t smem_stage_out = smem_b + kStages * Cfg::kBStageBytes;
+  // stage i: G A blocks (16 KiB each) then G B blocks (BN*128 B each)
+  auto stage_a = [&](int i, int g) { return smem_base + i * Cfg::kStageBytes + g * kAStageBytes; };
+  auto stage_b = [&](int i, int g) { return smem_base + i * Cfg::kStageBytes + G * kAStageBytes + g * Cfg::kBBlockBytes; };
+  const uint32_t smem_stage_out = smem_base + kStages * Cfg::kStageBytes;
   const uint32_t bars = smem_stage_out + Cfg::kStagingTotal;
   auto full_bar = [&](int i) { return bars + 8u * i; };
   auto empty_bar = [&](int i) { return bars + 8u * (kStages + i); };
@@ -239,30 +255,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 
   const int n_cblk = p.n_cblk0 + p.n_cblk1;
   const int num_k_blocks = p.R * p.S * n_cblk;
+  const int num_groups = (num_k_blocks + G - 1) / G;      // pipeline stages consumed per tile
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t a_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u;
+      const uint32_t kb_bytes = static_cast<uint32_t>(p.TH * p.TW) * 128u + Cfg::kBBlockBytes;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
         const int h_base = tc.th * p.TH + p.in_off_h;
         const int w_base = tc.tw * p.TW + p.in_off_w;
-        int kb = 0;
-        for (int r = 0; r < p.R; ++r) {
-          for (int s = 0; s < p.S; ++s) {
-            for (int cb = 0; cb < n_cblk; ++cb, ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u, p.diag, 1, stage);
-              mbar_arrive_expect_tx(full_bar(stage), a_bytes + Cfg::kBStageBytes);
-              if (cb < p.n_cblk0)
-                tma_load_4d(smem_a + stage * kAStageBytes, &p.tm_src0, full_bar(stage), cb * kBlockK, w_base + s, h_base + r, tc.n);
-              else
-                tma_load_4d(smem_a + stage * kAStageBytes, &p.tm_src1, full_bar(stage), (cb - p.n_cblk0) * kBlockK, w_base + s, h_base + r, tc.n);
-              tma_load_2d(smem_b + stage * Cfg::kBStageBytes, &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        int r = 0, s = 0, cb = 0, kb = 0;
+        for (int grp = 0; grp < num_groups; ++grp) {
+          const int g_n = (num_k_blocks - kb) < G ? (num_k_blocks - kb) : G;
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.diag, 1, stage);
+          if (p.dbg & 1) {
+            mbar_arrive(full_bar(stage));
+            kb += g_n;
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), kb_bytes * g_n);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (g < g_n) {
+                if (cb < p.n_cblk0)
+                  tma_load_4d(stage_a(stage, g), &p.tm_src0, full_bar(stage), cb * kBlockK, w_base + s, h_base + r, tc.n);
+                else
+                  tma_load_4d(stage_a(stage, g), &p.tm_src1, full_bar(stage), (cb - p.n_cblk0) * kBlockK, w_base + s, h_base + r, tc.n);
+                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN);
+                ++kb;
+                if (++cb == n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+              }
             }
           }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -278,29 +304,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
+      int kb = 0;
+      for (int grp = 0; grp < num_groups; ++grp) {
+        const int g_n = (num_k_blocks - kb) < G ? (num_k_blocks - kb) : G;
         mbar_wait(full_bar(stage), phase, p.diag, 3, stage);
         tcgen05_fence_after();
         if (elect_one_sync()) {
-          const uint64_t a_desc = make_smem_desc(smem_a + stage * kAStageBytes);
-          const uint64_t b_desc = make_smem_desc(smem_b + stage * Cfg::kBStageBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-            umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int g = 0; g < G; ++g) {
+            if (g < g_n && !(p.dbg & 2)) {
+              const uint64_t a_desc = make_smem_desc(stage_a(stage, g));
+              const uint64_t b_desc = make_smem_desc(stage_b(stage, g));
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb + g > 0 || k > 0) ? 1u : 0u);
+              }
+            }
           }
-          umma_commit(empty_bar(stage));                       // frees the smem slot when the MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar(as));  // accumulator ready
+          umma_commit(empty_bar(stage));                        // frees the smem slot when the MMAs retire
+          if (grp == num_groups - 1) umma_commit(tmem_full_bar(as));   // accumulator ready
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        kb += g_n;
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 4) {
-    // ===================== Epilogue =====================
-    const int q = warp - 4;                 // TMEM lane quadrant of this warp
+    // ===================== Epilogue (8 warps) =====================
+    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int m = q * 32 + lane;            // accumulator row = pixel index inside the box
     const int hl = m / p.TW, wl = m - hl * p.TW;
+    const bool issuer = (warp == 4);
     int iter = 0;
     int store_buf = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
@@ -318,102 +355,93 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       if constexpr (Cfg::kTmaStore) {
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 64; ++chunk) {
-          const int cbase = n0 + chunk * 64;
-          // skip-sum operand: this pixel's 64 channels = 128 contiguous bytes
-          uint4 add[8];
+          const int cbase = n0 + chunk * 64 + half * 32;     // this thread's 32 channels
+          // skip-sum operand: this pixel's 32 channels = 64 contiguous bytes
+          uint4 add[4];
           if (p.addend != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               add[j] = valid ? ldg_nc_v4(p.addend + pix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
           }
+          uint32_t v[32];
+          tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
+          tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
           // the staging buffer we are about to overwrite must have been read by its TMA store
-          if (q == 0 && elect_one_sync()) tma_store_wait_read<1>();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
-          uint32_t vall[64];        // all 64 accumulator columns of this chunk in flight, one wait
-#pragma unroll
-          for (int half = 0; half < 4; ++half) tmem_ld_x16(taddr + chunk * 64 + half * 16, vall + half * 16);
+          if (issuer && elect_one_sync()) tma_store_wait_read<1>();
           tmem_ld_wait();
-#pragma unroll
-          for (int half = 0; half < 4; ++half) {
-            const uint32_t* v = vall + half * 16;
-            uint32_t packed[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = half * 16 + 2 * j;
-              float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + c);
-              float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + c + 1);
-              if (p.addend != nullptr) {
-                const uint4& a4 = add[half * 2 + (j >> 2)];
-                const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
-                f0 += bf16_lo(aw); f1 += bf16_hi(aw);
-              }
-              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              packed[j] = pack_bf16x2(f0, f1);
-            }
-            // two 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const int chunk16 = half * 2 + cc;
-              const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
-              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
-                           "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
-            }
-          }
           if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
             tcgen05_fence_before();
             mbar_arrive(tmem_empty_bar(as));
           }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + 2 * j);
+            float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + 2 * j + 1);
+            if (p.addend != nullptr) {
+              const uint4& a4 = add[j >> 2];
+              const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
+              f0 += bf16_lo(aw); f1 += bf16_hi(aw);
+            }
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            packed[j] = pack_bf16x2(f0, f1);
+          }
+          // four 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int chunk16 = half * 4 + cc;
+            const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
+                         "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
+          }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (q == 0 && elect_one_sync()) {
-            tma_store_4d(&p.tm_out, sbuf, cbase, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (issuer && elect_one_sync()) {
+            tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
             tma_store_commit();
           }
           store_buf ^= 1;
         }
       } else {
-        // 16-channel outputs (score maps, logits): direct stores from registers
+        // 16-channel outputs (score maps, logits): direct stores from registers, 8 channels per thread
         static_assert(BN == 16 || Cfg::kTmaStore, "direct-store epilogue is written for BN == 16");
-        uint32_t v[16];
-        tmem_ld_x16(taddr, v);
+        uint32_t v[8];
+        tmem_ld_x8(taddr + half * 8, v);
         tmem_ld_wait();
         tcgen05_fence_before();
         mbar_arrive(tmem_empty_bar(as));
-        float f[16];
+        const int cbase = n0 + half * 8;
+        float f[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          f[j] = __uint_as_float(v[j]) + __ldg(p.bias + n0 + j);
-        }
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
         if (p.addend != nullptr && valid) {
-          const uint4 a0 = ldg_nc_v4(p.addend + pix * p.Cout + n0);
-          const uint4 a1 = ldg_nc_v4(p.addend + pix * p.Cout + n0 + 8);
-          const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const uint4 a0 = ldg_nc_v4(p.addend + pix * p.Cout + cbase);
+          const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
+          for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
         }
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (valid) {
           if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0;
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 2; ++j)
               stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
                                            __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              stg_v4(o + 8 * j, make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
+            stg_v4(o, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
           }
         }
       }
     }
-    if (Cfg::kTmaStore && q == 0 && elect_one_sync()) tma_store_wait_read<0>();
+    if (Cfg::kTmaStore && issuer && elect_one_sync()) tma_store_wait_read<0>();
   }
 
   tcgen05_fence_before();
@@ -495,7 +523,9 @@ static int launch_conv(const ConvParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  ConvParams q = p;
+  q.stages = (p.stages >= 2 && p.stages <= Cfg::kStages) ? p.stages : Cfg::kStages;
+  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(q);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -545,6 +575,11 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.num_tiles = d->N * p.tiles_h * p.tiles_w * p.n_ntiles;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.relu = d->relu; p.out_f32 = d->out_f32;
+  {
+    static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;
+    static const int env_stages = getenv("IISEG_CONV_STAGES") ? atoi(getenv("IISEG_CONV_STAGES")) : 0;
+    p.dbg = env_dbg; p.stages = env_stages;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (BN) {
     case 16: return launch_conv<16>(p, s);
