@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's iterative_inference.py (`inference`, `main`).
+
+Same entry point and arguments (`iterative_inference.py:56-59,329-394`): dataset,
+segmentation net, step, number of iterations, `dae_dict` (kind, concat_h, n_filters,
+additional_pool, unpool_type, noise, temperature, ...), which_set, save/load paths.  What
+changes is where the work happens: the per-image Python loop over `de_fn`/`val_fn`
+(`:258-282`) becomes one device-resident CUDA-graph replay per batch
+(`functions.IterativeInference`); `fused=False` runs the literal per-image loop over the four
+callables instead (kept for cross-checking the fused loop).
+
+Extra keyword arguments (not in the reference): `data_iter` (an iterator with the
+`dataset_loaders` attribute contract; default: synthetic CamVid-shaped data), `fcn_params` /
+`dae_params` (in-memory checkpoints instead of `.npz` paths), `verbose`.
+"""
+import argparse
+import os
+
+import numpy as np
+import torch
+
+from . import functions as F
+from .data_loader import load_data
+from .helpers import build_experiment_name, print_results, results_values
+from .models.DAE_h import buildDAE
+from .models.fcn8 import buildFCN8
+
+_EPSILON = 1e-3      # iterative_inference.py:53
+
+DAE_DICT_DEFAULTS = {'kind': 'fcn8', 'dropout': 0.0, 'skip': True, 'unpool_type': 'standard', 'n_filters': 64,
+                     'conv_before_pool': 1, 'additional_pool': 0, 'concat_h': ['input'], 'noise': 0.0,
+                     'from_gt': True, 'temperature': 1.0, 'layer': 'probs_dimshuffle', 'exp_name': '', 'bn': 0}
+
+
+def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path=None, loadpath=None,
+                   dataset='camvid', fcn_params=None, dae_params=None):
+    """The network-construction block of `inference` (iterative_inference.py:127-179)."""
+    if segm_net == 'fcn8':
+        fcn = buildFCN8(nb_in_channels, None, n_classes=n_classes, void_labels=void_labels,
+                        path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'),
+                        trainable=False, load_weights=True, layer=dae_dict['concat_h'] + [dae_dict['layer']],
+                        params=fcn_params)
+        padding = 100
+    elif segm_net == 'densenet':
+        raise NotImplementedError('FC-DenseNet103 conditioning is not built yet (DESIGN.md 7)')
+    elif segm_net == 'fcn_fcresnet':
+        raise NotImplementedError
+    else:
+        raise ValueError
+    if dae_dict['kind'] == 'standard':
+        dae = buildDAE([None] * len(dae_dict['concat_h']), None, n_classes,
+                       nb_features_to_concat=fcn[0].output_shape[1], padding=padding, trainable=True,
+                       void_labels=void_labels, load_weights=True, path_weights=loadpath or '',
+                       model_name='dae_model_best.npz', concat_h=dae_dict['concat_h'], noise=dae_dict['noise'],
+                       n_filters=dae_dict['n_filters'], conv_before_pool=dae_dict['conv_before_pool'],
+                       additional_pool=dae_dict['additional_pool'], dropout=dae_dict['dropout'],
+                       skip=dae_dict['skip'], unpool_type=dae_dict['unpool_type'], bn=dae_dict['bn'],
+                       params=dae_params)
+    elif dae_dict['kind'] in ('fcn8', 'contextmod'):
+        raise NotImplementedError('DAE kind %r is outside the B200 hot path (kind=standard)' % dae_dict['kind'])
+    else:
+        raise ValueError('Unknown dae kind')
+    return fcn, dae
+
+
+def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
+              data_augmentation=False, which_set='test', ae_h=False, full_im_ft=False, savepath=None,
+              loadpath=None, test_from_0_255=False, data_iter=None, fcn_params=None, dae_params=None,
+              weights_path=None, fused=True, verbose=True, save_batches=False):
+    dae_dict = dict(DAE_DICT_DEFAULTS)
+    dae_dict.update(dae_dict_updates)
+    exp_name = build_experiment_name(segm_net, data_aug=data_augmentation, ae_h=ae_h,
+                                     **dict(list(dae_dict.items()) + list(training_dict.items())))
+    if savepath is None:
+        raise ValueError('A saving directory must be specified')
+    savepath = os.path.join(savepath, dataset, exp_name, 'img_plots', which_set)
+    loadpath = os.path.join(loadpath or '', dataset, exp_name)
+    os.makedirs(savepath, exist_ok=True)
+
+    if data_iter is None:
+        data_iter = load_data(dataset, {}, one_hot=True, batch_size=[10, 5, 10], return_0_255=test_from_0_255,
+                              which_set=which_set)
+    n_batches_test = data_iter.nbatches
+    n_classes = data_iter.non_void_nclasses
+    void_labels = data_iter.void_labels
+    nb_in_channels = data_iter.data_shape[0]
+
+    fcn, dae = build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path, loadpath,
+                              dataset, fcn_params, dae_params)
+    pred_fcn_fn = F.function_pred_fcn(fcn)
+    pred_dae_fn = F.function_pred_dae(dae)
+    de_fn = F.function_de(dae)
+    val_fn = F.function_val(n_classes, void_labels)
+    loop = F.IterativeInference(dae, n_classes, void_labels)
+
+    tot = {k: 0 for k in ('rec', 'acc', 'jacc', 'rec_fcn', 'acc_fcn', 'jacc_fcn', 'rec_dae', 'acc_dae', 'jacc_dae')}
+    n_exec_all = []
+    cm_total = np.zeros((n_classes, n_classes), np.int64)
+    say = print if verbose else (lambda *a, **k: None)
+    say('Inference step: ' + str(learn_step) + ' num iter ' + str(num_iter))
+    for i in range(n_batches_test):
+        X, L = data_iter.next()
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+        Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
+        pred = pred_fcn_fn(Xd)
+        Y, H = pred[-1], pred[:-1]
+
+        acc_fcn, jacc_fcn, rec_fcn = val_fn(Y, Ld)                      # metrics before iterative inference
+        tot['acc_fcn'] += acc_fcn; tot['jacc_fcn'] = tot['jacc_fcn'] + jacc_fcn; tot['rec_fcn'] += rec_fcn
+        Y_dae = pred_dae_fn(*(H + [Y]))                                 # one plain DAE pass
+        acc_dae, jacc_dae, rec_dae = val_fn(Y_dae, Ld)
+        tot['acc_dae'] += acc_dae; tot['jacc_dae'] = tot['jacc_dae'] + jacc_dae; tot['rec_dae'] += rec_dae
+
+        if fused:
+            res = loop.run(H[0], Y, learn_step, num_iter, eps=_EPSILON, onehot=Ld)
+            Y_ii = res['y']
+            n_exec_all += res['n_exec'].cpu().tolist()
+            cm = res['cm'].sum(0).cpu().numpy().reshape(n_classes, n_classes)
+            cnt = res['counts'].sum(0).cpu().numpy()
+            se = res['sqerr'].sum(0).cpu().numpy()
+            acc, jacc, rec = (np.float32(np.float32(cnt[0]) / np.float32(cnt[1])), F.jaccard_from_cm(cm),
+                              np.float32(se[0] / se[1]))
+        else:
+            outs = []
+            for im in range(Xd.shape[0]):                               # iterative_inference.py:258-282
+                h_im = [el[im:im + 1] for el in H]
+                y_im = Y[im:im + 1]
+                n_exec = 0
+                for it in range(num_iter):
+                    grad = de_fn(*(h_im + [y_im]))
+                    y_im = torch.clamp(y_im - learn_step * grad, 0.0, 1.0)
+                    n_exec += 1
+                    norm = float(torch.linalg.vector_norm(grad, dim=1).mean())
+                    if norm < _EPSILON:
+                        break
+                outs.append(y_im)
+                n_exec_all.append(n_exec)
+            Y_ii = torch.cat(outs, dim=0)
+            acc, jacc, rec = val_fn(Y_ii, Ld)
+            cm = np.zeros_like(cm_total)
+        cm_total += cm
+        tot['acc'] += acc; tot['jacc'] = tot['jacc'] + jacc; tot['rec'] += rec
+        if verbose:
+            print_results('>>>>> FCN:', tot['rec_fcn'], tot['acc_fcn'], tot['jacc_fcn'], i + 1)
+            print_results('>>>>> FCN+DAE:', tot['rec_dae'], tot['acc_dae'], tot['jacc_dae'], i + 1)
+            print_results('>>>>> ITERATIVE INFERENCE:', tot['rec'], tot['acc'], tot['jacc'], i + 1)
+        if save_batches:                                                # iterative_inference.py:293
+            np.savez(os.path.join(savepath, 'batch' + str(i) + '.npz'), X=X, L=L, Y_ii=Y_ii.cpu().numpy(),
+                     Y_fcn=Y.cpu().numpy())
+    nb = n_batches_test
+    return {'fcn': results_values(tot['rec_fcn'], tot['acc_fcn'], tot['jacc_fcn'], nb),
+            'fcn_dae': results_values(tot['rec_dae'], tot['acc_dae'], tot['jacc_dae'], nb),
+            'iterative': results_values(tot['rec'], tot['acc'], tot['jacc'], nb),
+            'jacc_tot': tot['jacc'], 'jacc_tot_fcn': tot['jacc_fcn'], 'cm': cm_total, 'n_exec': n_exec_all,
+            'savepath': savepath}
+
+
+def main():
+    parser = argparse.ArgumentParser(description='Iterative inference.')
+    parser.add_argument('-dataset', type=str, default='camvid')
+    parser.add_argument('-segmentation_net', type=str, default='fcn8')
+    parser.add_argument('-step', type=float, default=1.0)
+    parser.add_argument('--num_iter', '-ne', type=int, default=1)
+    parser.add_argument('-which_set', type=str, default='test')
+    parser.add_argument('-savepath', type=str, default='./iiseg_out/')
+    parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
+    parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
+    args = parser.parse_args()
+    dae_dict = {'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0,
+                'concat_h': ['pool4'], 'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1, 'additional_pool': 2,
+                'path_weights': '', 'layer': 'probs_dimshuffle', 'exp_name': 'flip_final_', 'bn': 0}
+    training_dict = {'training_loss': ['crossentropy'], 'learning_rate': 0.0001, 'lr_anneal': 0.99,
+                     'weight_decay': 0.0001, 'optimizer': 'rmsprop'}
+    inference(args.dataset, args.segmentation_net, float(args.step), int(args.num_iter), which_set=args.which_set,
+              savepath=args.savepath, loadpath=args.loadpath, weights_path=args.weights_path,
+              dae_dict_updates=dae_dict, training_dict=training_dict, data_augmentation=True)
+
+
+if __name__ == '__main__':
+    main()

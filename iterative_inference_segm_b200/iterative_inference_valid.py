@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Drop-in for iterative_inference_valid.py: the step-size / iteration-count sweep.
+
+The reference rebuilds and recompiles both networks once per step value
+(`iterative_inference_valid.py:373-382`) and accumulates `valid_mat[:, :, it] += jacc_iter`
+from a host `val_fn` call per image per iteration (`:265-288`).  Here the networks are built
+once, `h` and `y0` of each batch are computed once and reused for all step values, and the
+per-iteration confusion matrices are accumulated on the device inside the captured loop
+(int64, exact); an image that early-exits at iteration `it` contributes nothing to
+`valid_mat[..., it:]`, exactly like the reference's `break` before `val_fn` (`:282-288`).
+"""
+import numpy as np
+import torch
+
+from . import functions as F
+from .data_loader import load_data
+from .iterative_inference import DAE_DICT_DEFAULTS, _EPSILON, build_networks
+
+STEPS = [.01, .02, .05, .08, .1, .5, 1.]      # iterative_inference_valid.py:373
+
+
+def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, which_set='val', data_iter=None,
+          fcn_params=None, dae_params=None, weights_path=None, loadpath=None, verbose=True):
+    """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter])."""
+    dae_dict = dict(DAE_DICT_DEFAULTS)
+    dae_dict.update(dae_dict_updates)
+    if data_iter is None:
+        data_iter = load_data(dataset, {}, one_hot=True, batch_size=[10, 10, 10], which_set=which_set)
+    n_classes, void_labels = data_iter.non_void_nclasses, data_iter.void_labels
+    fcn, dae = build_networks(segm_net, dae_dict, n_classes, data_iter.data_shape[0], void_labels, weights_path,
+                              loadpath, dataset, fcn_params, dae_params)
+    pred_fcn_fn = F.function_pred_fcn(fcn)
+    loop = F.IterativeInference(dae, n_classes, void_labels)
+    valid_mats = np.zeros((len(steps), 2, n_classes, num_iter))        # float64 like the reference (:231)
+    for _ in range(data_iter.nbatches):
+        X, L = data_iter.next()
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+        Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
+        pred = pred_fcn_fn(Xd)                                         # once per batch, shared by every step value
+        Y, H = pred[-1], pred[:-1]
+        for si, s in enumerate(steps):
+            res = loop.run(H[0], Y, s, num_iter, eps=_EPSILON, onehot=Ld, per_iter_metrics=True)
+            for it, acc in enumerate(res['iter']):
+                cms = acc.cm.cpu().numpy().reshape(-1, n_classes, n_classes)
+                for cm in cms:                                         # per image: val_fn(y_im, t_im) of the reference
+                    if cm.sum() > 0:
+                        valid_mats[si, :, :, it] += F.jaccard_from_cm(cm)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        all_results = np.nanmean(valid_mats[:, 0] / valid_mats[:, 1], axis=1)
+    if verbose:
+        best = all_results.max(1)
+        print('Best step: ' + str(steps[int(best.argmax())]))
+        print('Result: ' + str(best.max()))
+        print('Num iters: ' + str(int(all_results.argmax(1)[int(best.argmax())]) + 1))
+    return all_results, valid_mats
+
+
+def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
+              data_augmentation=False, which_set='val', ae_h=False, full_im_ft=False, savepath=None, loadpath=None,
+              test_from_0_255=False, **kw):
+    """Single-step form with the reference's signature (iterative_inference_valid.py:56-59): returns
+    `res = nanmean(valid_mat[0] / valid_mat[1], axis=0)` (`:297`)."""
+    res, _ = sweep(dataset, segm_net, [learn_step], num_iter, dae_dict_updates, which_set, loadpath=loadpath, **kw)
+    return res[0]

@@ -1,0 +1,29 @@
+"""Image sharding across GPUs and the one collective of the inference path.
+
+The reference is single-process.  Here images are partitioned into contiguous shards (rank r
+owns [r*n/G, (r+1)*n/G)), weights are replicated, and the only exchange is an all-reduce (SUM)
+of the integer confusion matrix / counts (and the fp64 squared-error sums).  Integer sums are
+order-independent, so any number of ranks gives bit-identical matrices.  Works on NCCL (CUDA
+tensors) and gloo (CPU tensors)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of `n_items` for `rank` of `world` (sizes differ by at most 1)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_metrics(cm, counts, sqerr=None):
+    """In-place SUM all-reduce of int64 `cm`, int64 `counts` and (optionally) fp64 `sqerr`."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return cm, counts, sqerr
+    packed = torch.cat([cm.reshape(-1), counts.reshape(-1)])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    cm.copy_(packed[:cm.numel()].view_as(cm))
+    counts.copy_(packed[cm.numel():].view_as(counts))
+    if sqerr is not None:
+        dist.all_reduce(sqerr, op=dist.ReduceOp.SUM)
+    return cm, counts, sqerr

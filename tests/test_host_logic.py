@@ -1,0 +1,87 @@
+"""CPU tests of the host-side logic: synthetic data iterator contract, experiment naming,
+print_results arithmetic, shard ranges, and the N>1 metric reduction with gloo (world_size 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_data_iterator_contract():
+    from iterative_inference_segm_b200.data_loader import load_data
+    it = load_data('camvid', {}, one_hot=True, batch_size=[10, 5, 10], which_set='test', n_images=12, height=8, width=10)
+    assert it.nbatches == 2 and it.non_void_nclasses == 11 and it.void_labels == [11] and it.data_shape == (3, 8, 10)
+    X, L = it.next()
+    assert X.shape == (10, 3, 8, 10) and X.dtype == np.float32 and 0 <= X.min() and X.max() < 1
+    assert L.shape == (10, 12, 8, 10) and np.array_equal(L.sum(1), np.ones((10, 8, 10), np.float32))
+    X2, _ = it.next()
+    assert X2.shape[0] == 2
+    assert len(it.mask_labels) == 12 and it.cmap.shape == (12, 3)
+
+
+def test_experiment_name_matches_reference_rules():
+    from iterative_inference_segm_b200.helpers import build_experiment_name
+    name = build_experiment_name('fcn8', kind='standard', concat_h=['pool4'], n_filters=64, conv_before_pool=1,
+                                 additional_pool=2, skip=True, unpool_type='trackind', dropout=0, noise=0.5,
+                                 from_gt=False, temperature=1.0, training_loss=['crossentropy', 'squared_error'],
+                                 learning_rate=0.001, lr_anneal=0.99, weight_decay=0.0001, optimizer='rmsprop',
+                                 data_aug=True, exp_name='flip_final_', layer='probs_dimshuffle', bn=0)
+    assert name == ('flip_final_fcn8_standard_pool4_f64c1p2_skip_trackind_crossentropy_squared_error_fromfcn8_z0.5'
+                    '_data_aug_T1.0_rmsprop_lr0.001_anneal0.99_decay0.0001_probs_dimshuffle')
+
+
+def test_results_values():
+    from iterative_inference_segm_b200.helpers import results_values
+    jacc = np.array([[1., 0., 2.], [2., 0., 4.]], np.float32)      # class 1 absent -> nan, ignored by nanmean
+    loss, acc, jm = results_values(3.0, 1.5, jacc, 3)
+    assert loss == 1.0 and acc == 0.5 and abs(jm - 0.5) < 1e-7
+
+
+def test_shard_range_partitions():
+    from iterative_inference_segm_b200.sharding import shard_range
+    for n in (1, 7, 10, 233):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from iterative_inference_segm_b200.sharding import shard_range, allreduce_metrics
+from oracle import metrics as M
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+rng = np.random.RandomState(0)
+N, C, H, W = 7, 11, 6, 8
+y = rng.rand(N, C, H, W).astype(np.float32)
+lab = rng.randint(0, C + 1, size=(N, H, W))
+onehot = np.eye(C + 1, dtype=np.float32)[lab].transpose(0, 3, 1, 2)
+lo, hi = shard_range(N, rank, world)
+cm = torch.from_numpy(M.confusion_matrix(y[lo:hi], onehot[lo:hi], C))
+c, v = M.accuracy_counts(y[lo:hi], onehot[lo:hi], [C])
+counts = torch.tensor([c, v], dtype=torch.int64)
+allreduce_metrics(cm, counts)
+full = M.confusion_matrix(y, onehot, C)
+cf, vf = M.accuracy_counts(y, onehot, [C])
+assert np.array_equal(cm.numpy(), full), 'confusion matrix differs after all-reduce'
+assert counts.tolist() == [cf, vf]
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_two_rank_metric_allreduce_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29543')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29543', str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('ok') == 2

@@ -112,3 +112,80 @@ def test_early_exit_semantics(cuda, built):
     assert torch.equal(res['y'], one)
     assert all(int(a.cm.sum()) == 0 for a in res['iter'])
     assert int(res['cm'].sum()) > 0          # the final batch-level val_fn still runs on the frozen y
+
+
+def _tiny_iter(n_images=3, batch=2):
+    from iterative_inference_segm_b200.data_loader import SyntheticSegmentationIterator
+    return SyntheticSegmentationIterator(n_images, batch, 32, 40, NCLS, seed=5)
+
+
+DAE_DICT = {'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0, 'concat_h': ['pool4'],
+            'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1, 'additional_pool': 2, 'path_weights': '',
+            'layer': 'probs_dimshuffle', 'exp_name': 'flip_final_', 'bn': 0}
+
+
+def test_inference_script_dropin(cuda, tmp_path):
+    """inference(...) with the reference's arguments: fused CUDA-graph loop == literal per-image loop over
+    the four callables, and both track the oracle's inference_batch."""
+    from iterative_inference_segm_b200.iterative_inference import inference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    kw = dict(dae_dict_updates=DAE_DICT, savepath=str(tmp_path), loadpath=str(tmp_path), fcn_params=pf, dae_params=pd,
+              verbose=False)
+    a = inference('camvid', 'fcn8', 0.05, 3, data_iter=_tiny_iter(), fused=True, save_batches=True, **kw)
+    b = inference('camvid', 'fcn8', 0.05, 3, data_iter=_tiny_iter(), fused=False, **kw)
+    assert a['n_exec'] == b['n_exec'] == [3, 3, 3]
+    assert np.array_equal(a['jacc_tot'], b['jacc_tot'])             # same kernels, same labels -> identical counts
+    assert abs(a['iterative'][0] - b['iterative'][0]) < 1e-6 and a['iterative'][1] == b['iterative'][1]
+    assert os.path.exists(os.path.join(a['savepath'], 'batch0.npz'))
+    # oracle: same data, same weights
+    it = _tiny_iter()
+    jacc_o = 0
+    agree, total = 0, 0
+    for i in range(it.nbatches):
+        X, L = it.next()
+        h, y0 = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+        Y, n_exec, bm, _ = loop.inference_batch(pd, h, y0, 0.05, 3, 100, L=L, n_classes=NCLS, void_labels=[NCLS])
+        jacc_o = jacc_o + bm[1]
+        saved = np.load(os.path.join(a['savepath'], 'batch%d.npz' % i))
+        agree += (saved['Y_ii'].argmax(1) == Y.numpy().argmax(1)).sum()
+        total += Y.numpy().argmax(1).size
+        assert float(np.abs(saved['Y_ii'] - Y.numpy()).max()) < 5e-2    # bf16 FCN8 (logit gain 10) + bf16 DAE
+    assert agree / total >= 0.98
+    # confusion-matrix totals: same pixel count, per-class counts within the argmax disagreement
+    assert a['jacc_tot'][1].sum() >= jacc_o[1].sum() * 0.9
+
+
+def test_valid_sweep_per_iteration_matrices(cuda):
+    """iterative_inference_valid: per-iteration Jaccard accumulators equal val_fn on the per-iteration y."""
+    from iterative_inference_segm_b200.iterative_inference_valid import sweep
+    from iterative_inference_segm_b200.functions import IterativeInference, function_pred_fcn, function_val
+    from iterative_inference_segm_b200.iterative_inference import build_networks, DAE_DICT_DEFAULTS
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    res, mats = sweep('camvid', 'fcn8', steps=[0.05, 0.5], num_iter=2, dae_dict_updates=DAE_DICT,
+                      data_iter=_tiny_iter(2, 2), fcn_params=pf, dae_params=pd, verbose=False)
+    assert res.shape == (2, 2) and mats.shape == (2, 2, NCLS, 2)
+    # recompute iteration 1 of step 0.05 by hand: one update, then val_fn per image
+    dd = dict(DAE_DICT_DEFAULTS); dd.update(DAE_DICT)
+    fcn, dae = build_networks('fcn8', dd, NCLS, 3, [NCLS], fcn_params=pf, dae_params=pd)
+    X, L = _tiny_iter(2, 2).next()
+    Xd, Ld = torch.from_numpy(X).cuda(), torch.from_numpy(L).cuda()
+    h, y0 = function_pred_fcn(fcn)(Xd)
+    y1 = IterativeInference(dae, NCLS, [NCLS]).run(h, y0, 0.05, 1, onehot=Ld, use_graph=False)['y']
+    val_fn = function_val(NCLS, [NCLS])
+    expect = sum(val_fn(y1[i:i + 1], Ld[i:i + 1])[1] for i in range(2))
+    assert np.array_equal(mats[0, :, :, 0], expect.astype(np.float64))
+
+
+def test_metrics_module_matches_oracle(cuda):
+    from iterative_inference_segm_b200 import metrics as GM
+    rng = np.random.RandomState(4)
+    y = rng.rand(2, NCLS, 9, 7).astype(np.float32)
+    lab = rng.randint(0, NCLS + 1, size=(2, 9, 7))
+    t = np.eye(NCLS + 1, dtype=np.float32)[lab].transpose(0, 3, 1, 2).copy()
+    y2d = y.transpose(0, 2, 3, 1).reshape(-1, NCLS)
+    t2d = t.transpose(0, 2, 3, 1).reshape(-1, NCLS + 1)
+    assert np.array_equal(GM.jaccard(y2d, t2d, NCLS, one_hot=True), M.jaccard(y, t, NCLS))
+    assert GM.accuracy(y2d, t2d, [NCLS], one_hot=True) == M.accuracy(y, t, [NCLS])
+    assert abs(float(GM.squared_error(y, t, NCLS)) - float(M.squared_error(y, t, NCLS))) < 1e-6
