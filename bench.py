@@ -146,22 +146,6 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- B200 arm
-def conv_flops_table():
-    """Executed algorithmic FLOPs (2*MAC, real channel counts) of the 12 conv launches of one DAE
-    application per image (up_conv1 only over the 360x480 crop window)."""
-    sizes = [(558, 678), (279, 339), (139, 169), (69, 84), (34, 42), (17, 21)]
-    down = [(11, 64), (64, 128), (128, 256), (256, 512), (1024, 1024), (1024, 2048)]
-    up = [(2048, 1024), (1024, 512), (512, 256), (256, 128), (128, 64), (64, 11)]
-    fl = []
-    for (h, w), (ci, co) in zip(sizes, down):
-        fl.append(2.0 * h * w * ci * co * 9)
-    for (h, w), (ci, co) in zip(sizes[::-1], up):
-        if co == 11:
-            h, w = H, W
-        fl.append(2.0 * h * w * ci * co * 9)
-    return fl
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -250,8 +234,7 @@ def run_b200(args):
     step_device(X_dev, L_dev)
     torch.cuda.synchronize()
     eager_per_step = _lib.launch_count() - l1
-    loop_nodes = (2 * dae.net.total + 2 * dae.net.total + 2) * N_ITER + 1   # conv+pool, unpool+conv, update+finalize; final metrics
-    launches_per_step = eager_per_step + loop_nodes
+    launches_per_step = eager_per_step + ii.graph_kernel_nodes     # eager FCN8/boundary launches + graph kernel nodes
 
     # ---- timed region: device-resident inputs
     with ClockSampler(local) as clk:
@@ -282,25 +265,22 @@ def run_b200(args):
         other = {}
         for (name, tag), v in summ.items():
             other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
-        flops = sum(conv_flops_table()) * BATCH
+        flops = sum(dae.net.executed_conv_flops(H, W)) * BATCH    # executed: cone windows on the expanding path
         achieved = flops / (conv_total_ms * 1e-3) / 1e12
         peak = peaks['bf16_tflops_sustained']
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (12 conv launches of one DAE application, batch 10)',
+        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (12 conv launches of one DAE application, batch 10; executed FLOPs, cone-restricted expanding path)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': conv_total_ms / 12.0,
                 'flops_per_application': flops}
-        pool_b, unpool_b = 0.0, 0.0
+        unpool_b = 0.0
         for (name, tag), v in summ.items():
-            if name == 'maxpool2':
-                n, h, w, c = tag
-                pool_b += n * h * w * c * 2 + n * (h // 2) * (w // 2) * c * 2.5
-            if name == 'unpool2':
-                n, h2, w2, c = tag
-                unpool_b += n * h2 * w2 * c * 2.5 + n * (2 * h2) * (2 * w2) * c * 2
+            if name == 'unpool2':       # algorithmic bytes: out written once, the touched u / mask windows read once
+                (n, uh, uw, c), (_, oh, ow, _) = tag
+                unpool_b += n * oh * ow * c * 2 + n * ((oh + 1) // 2 + 1) * ((ow + 1) // 2 + 1) * c * 2.5
         breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
-                     'pool_gbs': pool_b / (other.get('maxpool2', 1e9) * 1e-3) / 1e9,
                      'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
-                     'hbm_peak_gbs': peaks['hbm_gbs']}
+                     'hbm_peak_gbs': peaks['hbm_gbs'],
+                     'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues'}
         if world == 1:
             t_img, cores, parts = cpu_reference_sample()
             cpu_base = {'value': 1.0 / t_img, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

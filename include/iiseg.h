@@ -73,7 +73,15 @@ typedef struct iiseg_conv_desc {
    * layers/mylayers.py:36-57).                                             */
   int oh0, ow0, OH, OW;
   void* out;          /* NHWC [N,OH,OW,Cout], bf16 or fp32 per out_f32      */
-  const void* addend; /* NHWC bf16 [N,OH,OW,Cout] added before store, or NULL */
+  const void* addend; /* NHWC bf16 [N,AH,AW,Cout]; addend[oh+ah0, ow+aw0] is added
+                       * before the store (skip-sum with a cropped partner), or NULL */
+  int AH, AW, ah0, aw0;
+  /* Fused Pool2DLayer(2) (+ DePool2D mask): when `pooled` != NULL the conv output is max-pooled
+   * 2x2/stride 2 (floor) in the epilogue and only `pooled` [N,OH/2,OW/2,Cout] bf16 and, if
+   * non-NULL, `pool_mask` [N,OH/2,OW/2,Cout/8] (nibble layout of iiseg_maxpool2_mask_fwd) are
+   * written; `out` is not touched.  Needs Cout % 64 == 0.                                  */
+  void* pooled;
+  uint32_t* pool_mask;
   int relu;           /* 1: rectify (Lasagne default), 0: linear            */
   int out_f32;        /* 1: fp32 output (only Cout == 16)                   */
 } iiseg_conv_desc;
@@ -91,6 +99,13 @@ int iiseg_maxpool2_mask_fwd(const void* x, void* pooled, uint32_t* mask, int N,
  * the mask bit is set, else 0; trailing odd row/col of the HxW output = 0. */
 int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N,
                            int H, int W, int C, void* stream);
+/* Windowed form: only the output window [o_h0,o_h0+OH) x [o_w0,o_w0+OW) of the HxW map is
+ * produced (dense [N,OH,OW,C]); `u` is a dense [N,UH,UW,C] window of the pooled map whose
+ * element (0,0) is pooled position (u_h0,u_w0).  The expanding path only ever needs the
+ * dependency cone of the final centre crop (CroppingLayer, models/fcn_up.py:106-113). */
+int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask, void* out, int N,
+                                  int H, int W, int C, int UH, int UW, int u_h0, int u_w0,
+                                  int OH, int OW, int o_h0, int o_w0, void* stream);
 
 /* ---- transposed convolution: lasagne Deconv2DLayer ----------------------
  * models/fcn8.py:90-91,100-101,109-110 (crop='valid', flip_filters=False,

@@ -69,7 +69,7 @@ def conv_out_size(H, W, R, S, pad):
 
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
-           out_f32=False):
+           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all)."""
     _chk(src0, BF16, 'src0')
@@ -85,21 +85,34 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     assert weight.shape[1] == R * S * (C0 + C1), (tuple(weight.shape), R, S, C0, C1)
     fOH, fOW = conv_out_size(H, W, R, S, pad)
     oh0, ow0, OH, OW = window if window is not None else (0, 0, fOH, fOW)
-    if out is None:
+    if pooled is not None:     # fused 2x2 max-pool (+ mask): the full-resolution output is never written
+        _chk(pooled, BF16, 'pooled')
+        assert tuple(pooled.shape) == (N, OH // 2, OW // 2, Cout), (tuple(pooled.shape), (N, OH // 2, OW // 2, Cout))
+        if pool_mask is not None:
+            _chk(pool_mask, torch.int32, 'pool_mask')
+            assert tuple(pool_mask.shape) == (N, OH // 2, OW // 2, Cout // 8)
+        assert out is None
+    elif out is None:
         out = torch.empty((N, OH, OW, Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
     else:
         _chk(out, F32 if out_f32 else BF16, 'out')
         assert tuple(out.shape) == (N, OH, OW, Cout), (tuple(out.shape), (N, OH, OW, Cout))
     if addend is not None:
         _chk(addend, BF16, 'addend')
-        assert tuple(addend.shape) == (N, OH, OW, Cout)
+        assert addend.shape[0] == N and addend.shape[3] == Cout
+        assert addend_off[0] + OH <= addend.shape[1] and addend_off[1] + OW <= addend.shape[2]
     d = _lib.ConvDesc(src0=src0.data_ptr(), src1=src1.data_ptr() if src1 is not None else None,
                       N=N, H=H, W=W, C0=C0, C1=C1, weight=weight.data_ptr(), bias=bias.data_ptr(),
                       Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
-                      out=out.data_ptr(), addend=addend.data_ptr() if addend is not None else None,
+                      out=out.data_ptr() if out is not None else None,
+                      addend=addend.data_ptr() if addend is not None else None,
+                      pooled=pooled.data_ptr() if pooled is not None else None,
+                      pool_mask=pool_mask.data_ptr() if pool_mask is not None else None,
+                      AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
+                      ah0=addend_off[0], aw0=addend_off[1],
                       relu=int(bool(relu)), out_f32=int(bool(out_f32)))
     _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
-    return out
+    return out if pooled is None else pooled
 
 
 # ---- pool / unpool ----------------------------------------------------------
@@ -115,14 +128,19 @@ def maxpool2(x, with_mask, pooled=None, mask=None):
     return (pooled, mask) if with_mask else pooled
 
 
-def unpool2(u, mask, H, W, out=None):
+def unpool2(u, mask, H, W, out=None, u_origin=(0, 0), window=None):
+    """DePool2D into the HxW pre-pool map.  `u` is a dense window of the pooled map starting at pooled
+    position `u_origin`; `window` = (h0, w0, OH, OW) restricts the output (default: the whole map)."""
     _chk(u, BF16, 'u')
     _chk(mask, torch.int32, 'mask')
-    N, H2, W2, Cc = u.shape
-    assert (H2, W2) == (H // 2, W // 2)
+    N, UH, UW, Cc = u.shape
+    assert tuple(mask.shape) == (N, H // 2, W // 2, Cc // 8), (tuple(mask.shape), H, W, Cc)
+    h0, w0, OH, OW = window if window is not None else (0, 0, H, W)
     if out is None:
-        out = torch.empty((N, H, W, Cc), dtype=BF16, device=u.device)
-    _lib.call('iiseg_unpool2_mask_fwd', _ptr(u), _ptr(mask), _ptr(out), N, H, W, Cc, _stream())
+        out = torch.empty((N, OH, OW, Cc), dtype=BF16, device=u.device)
+    assert tuple(out.shape) == (N, OH, OW, Cc)
+    _lib.call('iiseg_unpool2_mask_window_fwd', _ptr(u), _ptr(mask), _ptr(out), N, H, W, Cc, UH, UW,
+              u_origin[0], u_origin[1], OH, OW, h0, w0, _stream())
     return out
 
 

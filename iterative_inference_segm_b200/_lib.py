@@ -24,6 +24,8 @@ class ConvDesc(C.Structure):
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('addend', C.c_void_p),
+        ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int),
+        ('pooled', C.c_void_p), ('pool_mask', C.c_void_p),
         ('relu', C.c_int), ('out_f32', C.c_int),
     ]
 
@@ -54,6 +56,7 @@ SIGNATURES = {
     'iiseg_conv2d_fwd': (_i, [C.POINTER(ConvDesc), _vp]),
     'iiseg_maxpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_unpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_unpool2_mask_window_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_deconv2d_fwd': (_i, [C.POINTER(DeconvDesc), _vp]),
     'iiseg_update_blocks': (_i, [_i, _i]),
     'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -74,6 +74,10 @@ struct alignas(64) ConvParams {
   int TH, TW;
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   int OH, OW, Cout;
+  int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
+  __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
+  uint32_t* pool_mask;       // tie-inclusive mask nibbles [N,PH,PW,Cout/8] or NULL
+  int PH, PW;
   int relu, out_f32;
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
       const bool valid = (hl < p.TH) && (oh < p.OH) && (ow < p.OW);
       const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+      const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
       mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
           if (p.addend != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              add[j] = valid ? ldg_nc_v4(p.addend + pix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
+              add[j] = valid ? ldg_nc_v4(p.addend + apix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
           }
           uint32_t v[32];
           tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
@@ -396,11 +401,51 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
                          "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
           }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (issuer && elect_one_sync()) {
-            tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
-            tma_store_commit();
+          if (p.pooled == nullptr) {
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (issuer && elect_one_sync()) {
+              tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
+              tma_store_commit();
+            }
+          } else {
+            // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
+            // staged tile never goes to HBM.  One thread per (pooled pixel, 8 channels): TH, TW and the
+            // tile origin are even, so every 2x2 window lies inside the box.
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int et = threadIdx.x - 128;
+            const int pp = et >> 3, cgp = et & 7;
+            const int tw2 = p.TW >> 1;
+            const int ph_l = pp / tw2, pw_l = pp - ph_l * tw2;
+            const int ph = ((tc.th * p.TH) >> 1) + ph_l, pw = ((tc.tw * p.TW) >> 1) + pw_l;
+            if (ph_l < (p.TH >> 1) && ph < p.PH && pw < p.PW) {
+              const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
+              uint32_t w[4][4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int mm = m00 + (e >> 1) * p.TW + (e & 1);
+                const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
+              }
+              uint32_t bits = 0, outw[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float lo[4], hi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { lo[e] = bf16_lo(w[e][k]); hi[e] = bf16_hi(w[e][k]); }
+                const float mlo = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
+                const float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+                uint32_t nlo = 0, nhi = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { nlo |= (lo[e] == mlo ? 1u : 0u) << e; nhi |= (hi[e] == mhi ? 1u : 0u) << e; }
+                bits |= (nlo << (8 * k)) | (nhi << (8 * k + 4));
+                outw[k] = pack_bf16x2(mlo, mhi);
+              }
+              const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
+              const int cch = n0 + chunk * 64 + cgp * 8;
+              stg_v4(p.pooled + ppix * p.Cout + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
+              if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+            }
           }
           store_buf ^= 1;
         }
@@ -417,7 +462,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
         if (p.addend != nullptr && valid) {
-          const uint4 a0 = ldg_nc_v4(p.addend + pix * p.Cout + cbase);
+          const uint4 a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
           const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
@@ -502,12 +547,14 @@ static int encode_weight(CUtensorMap* tm, const void* base, int Cout, int K, int
 }
 
 // Pick the TH x TW (<= 128 pixels) box that covers OH x OW with the fewest tiles; ties -> widest box.
-static void choose_box(int OH, int OW, int* TH, int* TW) {
-  long best = -1; int bh = 1, bw = 1;
-  const int wmax = OW < 128 ? OW : 128;
-  for (int tw = 1; tw <= wmax; ++tw) {
-    int th = 128 / tw; if (th > OH) th = OH;
-    if (th > 256) th = 256;
+static void choose_box(int OH, int OW, int* TH, int* TW, bool even) {
+  long best = -1; int bh = even ? 2 : 1, bw = even ? 2 : 1;
+  const int step = even ? 2 : 1;               // fused pool: even box, even origin (OH, OW are even then)
+  for (int tw = step; tw <= 128 && tw < OW + step; tw += step) {
+    int th = 128 / tw;
+    if (even) th &= ~1;
+    if (th > OH) th = OH;
+    if (th < step) continue;
     const long tiles = (long)ceil_div(OW, tw) * ceil_div(OH, th);
     if (best < 0 || tiles < best || (tiles == best && tw >= bw)) { best = tiles; bh = th; bw = tw; }
   }
@@ -535,7 +582,8 @@ static int launch_conv(const ConvParams& p, cudaStream_t stream) {
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
-  IISEG_CHECK(d->src0 != nullptr && d->weight != nullptr && d->bias != nullptr && d->out != nullptr, "conv: null tensor");
+  IISEG_CHECK(d->src0 != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr), "conv: null tensor");
+  IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
   IISEG_CHECK(d->C0 > 0 && d->C0 % 64 == 0, "conv: C0=%d must be a positive multiple of 64", d->C0);
   IISEG_CHECK(d->C1 >= 0 && d->C1 % 64 == 0 && (d->C1 == 0) == (d->src1 == nullptr), "conv: bad second source (C1=%d)", d->C1);
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
@@ -545,11 +593,17 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
   IISEG_CHECK(d->N >= 1, "conv: empty batch");
+  if (d->addend != nullptr)
+    IISEG_CHECK(d->ah0 >= 0 && d->aw0 >= 0 && d->ah0 + d->OH <= d->AH && d->aw0 + d->OW <= d->AW,
+                "conv: addend window [%d+%d, %d+%d] outside %dx%d", d->ah0, d->OH, d->aw0, d->OW, d->AH, d->AW);
 
   ConvParams p;
   memset(&p, 0, sizeof(p));
   const int BN = d->Cout == 16 ? 16 : (d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64));
-  choose_box(d->OH, d->OW, &p.TH, &p.TW);
+  const bool fuse_pool = d->pooled != nullptr;
+  // with the fused pool only the 2*floor(OH/2) x 2*floor(OW/2) outputs that have a pool window are computed
+  const int covH = fuse_pool ? (d->OH / 2) * 2 : d->OH, covW = fuse_pool ? (d->OW / 2) * 2 : d->OW;
+  choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
   if (encode_nhwc(&p.tm_src0, d->src0, d->N, d->H, d->W, d->C0, p.TH, p.TW)) return -1;
   if (d->src1 != nullptr) {
     if (encode_nhwc(&p.tm_src1, d->src1, d->N, d->H, d->W, d->C1, p.TH, p.TW)) return -1;
@@ -558,7 +612,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   }
   const int K = d->R * d->S * (d->C0 + d->C1);
   if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN)) return -1;
-  if (BN >= 64) {
+  if (BN >= 64 && !fuse_pool) {
     if (encode_nhwc(&p.tm_out, d->out, d->N, d->OH, d->OW, d->Cout, p.TH, p.TW)) return -1;
   } else {
     p.tm_out = p.tm_src0;
@@ -570,10 +624,12 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.n_cblk0 = d->C0 / 64; p.n_cblk1 = d->C1 / 64;
   p.R = d->R; p.S = d->S;
   p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
-  p.tiles_h = ceil_div(d->OH, p.TH); p.tiles_w = ceil_div(d->OW, p.TW);
+  p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);
+  p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask; p.PH = d->OH / 2; p.PW = d->OW / 2;
   p.n_ntiles = d->Cout / BN;
   p.num_tiles = d->N * p.tiles_h * p.tiles_w * p.n_ntiles;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
+  p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.relu = d->relu; p.out_f32 = d->out_f32;
   {
     static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;

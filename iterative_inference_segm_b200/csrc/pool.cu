@@ -6,7 +6,7 @@
 // streaming: NHWC bf16, one thread per (window, 8 channels), 16-byte vector
 // accesses, channel-fastest thread order so a warp touches contiguous bytes.
 //   pool  : reads 4 x 16 B, writes 16 B pooled + 4 B mask (8 nibbles)
-//   unpool: reads 16 B + 4 B, writes 4 x 16 B
+//   unpool: one thread per (output row, pooled column, 8 channels): reads 16 B + 4 B, writes 2 x 16 B
 #include "common.cuh"
 #include "../../include/iiseg.h"
 
@@ -48,40 +48,49 @@ __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restr
   }
 }
 
-// One thread per (ceil(H/2) x ceil(W/2) window, 8 channels): windows past the pooled extent
-// only zero-fill the trailing odd row / column.
-__global__ void __launch_bounds__(256) unpool2_mask_kernel(const uint4* __restrict__ u, const uint32_t* __restrict__ mask,
-                                                           uint4* __restrict__ out, int H, int W, int C8, int H2,
-                                                           int W2, int HC, int WC, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+// DePool2D restricted to an output window.  `u` is a dense
+// [N,UH,UW,C] tensor whose element (0,0) sits at pooled-grid position (u_h0,u_w0); `out` is a
+// dense [N,OH,OW,C] tensor whose element (0,0) is full-resolution pixel (o_h0,o_w0).  Output
+// pixels in the trailing odd row / column of the HxW map (no pool window) are zero.
+struct UnpoolParams {
+  const uint4* u; const uint32_t* mask; uint4* out;
+  int C8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN;
+  long long total;
+};
+
+__global__ void __launch_bounds__(256) unpool2_mask_kernel(const UnpoolParams p) {
+  // one thread per (output row, pooled column touched by the window, 8 channels): u and the mask
+  // word are read once for the (up to) two output pixels of that row they feed
+  const int pw_first = p.o_w0 >> 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.total;
        i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
-    const int cg = (int)(t % C8); t /= C8;
-    const int pw = (int)(t % WC); t /= WC;
-    const int ph = (int)(t % HC);
-    const long long n = t / HC;
+    const int cg = (int)(t % p.C8); t /= p.C8;
+    const int pc = (int)(t % p.PWN); t /= p.PWN;
+    const int oh = (int)(t % p.OH);
+    const long long n = t / p.OH;
+    const int fh = oh + p.o_h0;                           // full-resolution row
+    const int ph = fh >> 1, pw = pw_first + pc;
     uint4 val = make_uint4(0, 0, 0, 0);
     uint32_t bits = 0;
-    if (ph < H2 && pw < W2) {
-      const long long src = ((n * H2 + ph) * W2 + pw) * C8 + cg;
-      val = ldg_nc_v4(u + src);
-      bits = __ldg(mask + src);
+    if (ph < p.H2 && pw < p.W2) {
+      val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.C8 + cg);
+      bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.C8 + cg);
     }
-    // expand each channel's nibble bit to a 16-bit lane mask
     const uint32_t w[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
-    for (int pos = 0; pos < 4; ++pos) {
-      const int ih = 2 * ph + (pos >> 1), iw = 2 * pw + (pos & 1);
-      if (ih >= H || iw >= W) continue;
-      uint32_t o[4];
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ow = 2 * pw + dx - p.o_w0;
+      if (ow < 0 || ow >= p.OW) continue;
+      const int pos = ((fh & 1) << 1) | dx;
+      uint32_t r[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t lo = (bits >> (4 * (2 * k) + pos)) & 1u;
         const uint32_t hi = (bits >> (4 * (2 * k + 1) + pos)) & 1u;
-        const uint32_t sel = (lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
-        o[k] = w[k] & sel;
+        r[k] = w[k] & ((lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u));
       }
-      stg_v4(out + ((n * H + ih) * W + iw) * C8 + cg, make_uint4(o[0], o[1], o[2], o[3]));
+      stg_v4(p.out + ((n * p.OH + oh) * p.OW + ow) * p.C8 + cg, make_uint4(r[0], r[1], r[2], r[3]));
     }
   }
 }
@@ -107,15 +116,35 @@ extern "C" int iiseg_maxpool2_mask_fwd(const void* x, void* pooled, uint32_t* ma
   return 0;
 }
 
-extern "C" int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N, int H, int W, int C,
-                                      void* stream) {
+extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask, void* out, int N, int H, int W, int C,
+                                             int UH, int UW, int u_h0, int u_w0, int OH, int OW, int o_h0, int o_w0,
+                                             void* stream) {
   using namespace iiseg;
   IISEG_CHECK(u && mask && out, "unpool: null tensor");
   IISEG_CHECK(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, "unpool: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
-  const int H2 = H / 2, W2 = W / 2, HC = (H + 1) / 2, WC = (W + 1) / 2, C8 = C / 8;
-  const long long total = (long long)N * HC * WC * C8;
-  unpool2_mask_kernel<<<stream_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint4*>(u), mask, reinterpret_cast<uint4*>(out), H, W, C8, H2, W2, HC, WC, total);
+  const int H2 = H / 2, W2 = W / 2;
+  IISEG_CHECK(OH >= 1 && OW >= 1 && o_h0 >= 0 && o_w0 >= 0 && o_h0 + OH <= H && o_w0 + OW <= W,
+              "unpool: output window [%d+%d, %d+%d] outside %dx%d", o_h0, OH, o_w0, OW, H, W);
+  // every pool window the output touches must lie inside the u tensor
+  const int ph_lo = o_h0 / 2, pw_lo = o_w0 / 2;
+  int ph_hi = (o_h0 + OH - 1) / 2, pw_hi = (o_w0 + OW - 1) / 2;
+  if (ph_hi > H2 - 1) ph_hi = H2 - 1;
+  if (pw_hi > W2 - 1) pw_hi = W2 - 1;
+  IISEG_CHECK(u_h0 <= ph_lo && u_w0 <= pw_lo && ph_hi < u_h0 + UH && pw_hi < u_w0 + UW,
+              "unpool: u window [%d+%d, %d+%d] does not cover pooled rows %d..%d cols %d..%d", u_h0, UH, u_w0, UW,
+              ph_lo, ph_hi, pw_lo, pw_hi);
+  UnpoolParams p;
+  p.u = reinterpret_cast<const uint4*>(u); p.mask = mask; p.out = reinterpret_cast<uint4*>(out);
+  p.C8 = C / 8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
+  p.OH = OH; p.OW = OW; p.o_h0 = o_h0; p.o_w0 = o_w0;
+  p.PWN = (o_w0 + OW - 1) / 2 - o_w0 / 2 + 1;     // pooled columns the window touches (incl. a trailing odd one)
+  p.total = (long long)N * OH * p.PWN * p.C8;
+  unpool2_mask_kernel<<<stream_grid(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N, int H, int W, int C,
+                                      void* stream) {
+  return iiseg_unpool2_mask_window_fwd(u, mask, out, N, H, W, C, H / 2, W / 2, 0, 0, H, W, 0, 0, stream);
 }

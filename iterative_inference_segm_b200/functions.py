@@ -147,6 +147,7 @@ class IterativeInference(object):
         self.C = self.net.n_classes if n_classes is None else n_classes
         self.void_label = _void_label(self.C, list(void_labels))
         self._state = {}
+        self.graph_kernel_nodes = 0
 
     def _buffers(self, B, H, W, num_iter, per_iter):
         key = (B, H, W, num_iter, per_iter)
@@ -226,8 +227,11 @@ class IterativeInference(object):
                 st['y'].copy_(y0)
                 K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'])
                 g = torch.cuda.CUDAGraph()
+                from . import _lib
+                n0 = _lib.launch_count()
                 with torch.cuda.graph(g):
                     self._loop(st, step, num_iter, eps, with_metrics, per_iter)
+                self.graph_kernel_nodes = _lib.launch_count() - n0     # library kernels per replay
                 st['graph'][gkey] = g
             g.replay()
         else:

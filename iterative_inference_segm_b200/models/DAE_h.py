@@ -6,7 +6,8 @@ unpool_type='trackind', conv_before_pool=1, skip=True, bn=0, dropout=0):
 
   down, p = 1..P : conv3x3+ReLU (tcgen05 implicit GEMM; pad=`padding` on level 1,
                    the (h, pool_n) concat of level n_pool+1 read by the loader from
-                   two tensor maps) -> 2x2 max-pool + tie-inclusive mask
+                   two tensor maps) with the 2x2 max-pool + tie-inclusive mask fused
+                   in the epilogue (the pre-pool map never reaches HBM)
   up,   p = P..1 : mask unpool (DePool2D) -> conv3x3 linear with the skip-sum of
                    pool_{p-1} fused in the epilogue; level 1 computes only the
                    centre-crop window and emits fp32 logits
@@ -81,6 +82,47 @@ class DAENet(object):
         s = self.level_sizes(H, W)[self.n_pool - 1]
         return s[0] // 2, s[1] // 2
 
+    def cone_windows(self, H, W):
+        """Dependency cone of the final centre crop through the expanding path.
+
+        Only the H x W centre of `up_conv1` is kept (CroppingLayer, models/fcn_up.py:106-113), so each
+        upper layer is needed only where that crop can see it: conv window Wc[p] at level p needs the
+        unpooled map on Wu[p] = Wc[p] dilated by the 3x3 halo (clipped to the map), which needs the level
+        below on the pool windows it touches.  With pad=100 this is about half of every map.  Values outside
+        the cone never reach the output, so restricting the work is exact.  Returns {p: (h_lo, h_hi, w_lo,
+        w_hi)} for Wc and Wu, p = 1..P, in level-p (pre-pool) coordinates."""
+        sizes = self.level_sizes(H, W)
+        oh, ow = (sizes[0][0] - H) // 2, (sizes[0][1] - W) // 2
+        Wc, Wu = {1: (oh, oh + H, ow, ow + W)}, {}
+        for p in range(1, self.total + 1):
+            hl, hh, wl, wh = Wc[p]
+            Sh, Sw = sizes[p - 1]
+            Wu[p] = (max(hl - 1, 0), min(hh + 1, Sh), max(wl - 1, 0), min(wh + 1, Sw))
+            if p < self.total:
+                ul, uh, vl, vh = Wu[p]
+                S2h, S2w = sizes[p]
+                Wc[p + 1] = (ul // 2, min((uh - 1) // 2 + 1, S2h), vl // 2, min((vh - 1) // 2 + 1, S2w))
+        return Wc, Wu
+
+    def executed_conv_flops(self, H, W):
+        """Executed algorithmic FLOPs (2*MAC, real channel counts) of the 2P conv launches of one
+        application, per image: full maps on the contracting path, cone windows on the expanding path."""
+        sizes = self.level_sizes(H, W)
+        Wc, _ = self.cone_windows(H, W)
+        fl = []
+        cin = self.n_classes
+        for p in range(self.total):
+            c = cin + (self.nb_h if p == self.n_pool else 0)
+            fl.append(2.0 * sizes[p][0] * sizes[p][1] * c * self.filters[p] * 9)
+            cin = self.filters[p]
+        up_in = self.filters[-1]
+        for p in range(self.total, 0, -1):
+            n_cl = self.n_classes if p == 1 else self.filters[p - 2]
+            hl, hh, wl, wh = Wc[p]
+            fl.append(2.0 * (hh - hl) * (wh - wl) * up_in * n_cl * 9)
+            up_in = n_cl
+        return fl
+
     def workspace(self, B, H, W):
         """Activation buffers for one application, allocated once per (B, H, W) and
         kept resident (they are baked into the captured CUDA graph)."""
@@ -90,17 +132,19 @@ class DAENet(object):
             return ws
         dev, bf = self.device, torch.bfloat16
         sizes = self.level_sizes(H, W)
-        ws = {'conv': [], 'pool': [], 'mask': [], 'unpool': [], 'upconv': []}
+        Wc, Wu = self.cone_windows(H, W)
+        ws = {'pool': [], 'mask': [], 'unpool': {}, 'upconv': {}, 'Wc': Wc, 'Wu': Wu}
         for p, (h, w) in enumerate(sizes):
             f = self.filters[p]
-            ws['conv'].append(torch.empty((B, h, w, f), dtype=bf, device=dev))
             ws['pool'].append(torch.empty((B, h // 2, w // 2, f), dtype=bf, device=dev))
             ws['mask'].append(torch.empty((B, h // 2, w // 2, f // 8), dtype=torch.int32, device=dev))
-            ws['unpool'].append(torch.empty((B, h, w, f), dtype=bf, device=dev))
-        for p in range(self.total, 1, -1):   # up_conv_p output, p > 1: size of level p, channels of level p-1
-            h, w = sizes[p - 1]
-            assert (h, w) == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
-            ws['upconv'].append(torch.empty((B, h, w, self.filters[p - 2]), dtype=bf, device=dev))
+        for p in range(1, self.total + 1):
+            ul, uh, vl, vh = Wu[p]
+            ws['unpool'][p] = torch.empty((B, uh - ul, vh - vl, self.filters[p - 1]), dtype=bf, device=dev)
+            if p > 1:   # up_conv_p output: level-p window, channels of level p-1; skip partner pool_{p-1} has size S_p
+                hl, hh, wl, wh = Wc[p]
+                assert sizes[p - 1] == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
+                ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.filters[p - 2]), dtype=bf, device=dev)
         ws['logits'] = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
         self._ws[key] = ws
         return ws
@@ -112,29 +156,35 @@ class DAENet(object):
         B, H, W, _ = y_bf16.shape
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
+        Wc, Wu = ws['Wc'], ws['Wu']
         assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.h_pad,), \
             (tuple(h_bf16.shape), self.h_spatial(H, W), self.h_pad)
         x = y_bf16
         for p in range(self.total):
             Wk, bk = self.down[p]
             pad = self.padding if (p == 0 and self.padding > 0) else 1
+            # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
+            # pre-pool map is consumed on chip and never written (nothing else reads it)
             if p == self.n_pool:
-                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, out=ws['conv'][p])
+                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
             else:
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, out=ws['conv'][p])
-            K.maxpool2(ws['conv'][p], True, pooled=ws['pool'][p], mask=ws['mask'][p])
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
             x = ws['pool'][p]
-        u = ws['pool'][-1]
+        u, u_origin = ws['pool'][-1], (0, 0)
         for i, p in enumerate(range(self.total, 0, -1)):
             h, w = sizes[p - 1]
-            K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p - 1])
+            ul, uh, vl, vh = Wu[p]
+            hl, hh, wl, wh = Wc[p]
+            up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
+                           window=(ul, vl, uh - ul, vh - vl))
             Wk, bk = self.up[i]
-            if p > 1:
-                u = K.conv2d(ws['unpool'][p - 1], Wk, bk, 3, 3, 1, relu=False, addend=ws['pool'][p - 2],
-                             out=ws['upconv'][i])
-            else:   # centre crop (CroppingLayer, layers/mylayers.py:36-57): compute only that window
-                K.conv2d(ws['unpool'][0], Wk, bk, 3, 3, 1, relu=False, window=((h - H) // 2, (w - W) // 2, H, W),
-                         out=ws['logits'], out_f32=True)
+            win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
+            if p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
+                u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],
+                             addend_off=(hl, wl), out=ws['upconv'][p])
+                u_origin = (hl, wl)
+            else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
+                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True)
         return ws['logits']
 
 

@@ -71,10 +71,15 @@ class FCN8Net(object):
         out = {}
         x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin))
         for si, stage in enumerate(VGG_STAGES):
-            for name, _ in stage:
+            for ci, (name, cout) in enumerate(stage):
                 Wk, bk = self.w[name]
-                x = K.conv2d(x, Wk, bk, 3, 3, 100 if name == 'conv1_1' else 1, relu=True)
-            x = K.maxpool2(x, with_mask=False)
+                pad = 100 if name == 'conv1_1' else 1
+                if ci == len(stage) - 1:    # last conv of the stage: max-pool fused in the epilogue
+                    oh, ow = K.conv_out_size(x.shape[1], x.shape[2], 3, 3, pad)
+                    pooled = torch.empty((B, oh // 2, ow // 2, cout), dtype=torch.bfloat16, device=X.device)
+                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=pooled)
+                else:
+                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True)
             out['pool%d' % (si + 1)] = x
         x = K.conv2d(x, *self.w['fc6'], 7, 7, 0, relu=True)
         x = K.conv2d(x, *self.w['fc7'], 1, 1, 0, relu=True)

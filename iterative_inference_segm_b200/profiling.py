@@ -57,7 +57,10 @@ def _tag(name, args, kw):
         win = kw.get('window')
         c1 = kw['src1'].shape[3] if kw.get('src1') is not None else 0
         return (tuple(src0.shape), c1, weight.shape[0], R, S, tuple(win) if win else None,
-                tuple(out.shape) if out is not None else None)
-    if name in ('maxpool2', 'unpool2'):
+                tuple(out.shape) if out is not None else None, kw.get('pooled') is not None)
+    if name == 'unpool2':
+        out = kw.get('out')
+        return (tuple(args[0].shape), tuple(out.shape) if out is not None else None)
+    if name == 'maxpool2':
         return tuple(args[0].shape)
     return None

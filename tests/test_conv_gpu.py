@@ -53,6 +53,44 @@ def test_conv_matches_fp32_reference(cuda, case):
     assert bool(((got - ref).abs() <= rel * ref.abs().clamp(min=1.0)).all()), float((got - ref).abs().max())
 
 
+@pytest.mark.parametrize('N,H,W,C,Cout,pad', [(2, 37, 45, 64, 128, 1), (1, 17, 21, 128, 256, 1), (1, 20, 24, 64, 64, 100),
+                                               (3, 8, 10, 64, 512, 1)])
+def test_conv_fused_pool_equals_conv_then_pool(cuda, N, H, W, C, Cout, pad):
+    """The pool fused in the conv epilogue is bit-identical to conv (bf16 out) followed by the
+    stand-alone pool + tie-mask kernel, including the dropped odd row/col."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(4)
+    x = torch.randn(N, H, W, C, device=cuda).to(torch.bfloat16)
+    Wk = (torch.randn(Cout, 9 * C, device=cuda) / (9 * C) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=cuda)
+    full = K.conv2d(x, Wk, b, 3, 3, pad, relu=True)
+    ref_p, ref_m = K.maxpool2(full, with_mask=True)
+    OH, OW = full.shape[1], full.shape[2]
+    pooled = torch.zeros((N, OH // 2, OW // 2, Cout), dtype=torch.bfloat16, device=cuda)
+    mask = torch.zeros((N, OH // 2, OW // 2, Cout // 8), dtype=torch.int32, device=cuda)
+    K.conv2d(x, Wk, b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask)
+    assert torch.equal(pooled, ref_p)
+    assert torch.equal(mask, ref_m)
+
+
+def test_conv_addend_window_offset(cuda):
+    """Skip-sum partner read at an offset inside a larger tensor (cone-restricted expanding path)."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(3)
+    N, C, Cout, H, W = 2, 64, 64, 20, 26
+    x = torch.randn(N, H, W, C, device=cuda).to(torch.bfloat16)
+    Wt = (torch.randn(Cout, C, 3, 3, device=cuda) / 24).to(torch.bfloat16)
+    b = torch.randn(Cout, device=cuda)
+    big = torch.randn(N, 40, 50, Cout, device=cuda).to(torch.bfloat16)
+    win = (1, 1, 18, 24)
+    out = K.conv2d(x, Wt.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), b, 3, 3, 1, relu=False, window=win,
+                   addend=big, addend_off=(7, 9))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), Wt.float(), b, padding=1)[:, :, 1:19, 1:25]
+    ref = ref + big[:, 7:25, 9:33].float().permute(0, 3, 1, 2)
+    got = out.float().permute(0, 3, 1, 2)
+    assert bool(((got - ref).abs() <= 2.0 ** -7 * ref.abs().clamp(min=1.0)).all())
+
+
 def test_conv_constant_region_is_bit_constant(cuda):
     """Spatially constant input -> every interior output pixel must be bit-identical (one uniform K
     loop, zero padding by TMA fill), which the tie-inclusive pool mask relies on."""

@@ -44,6 +44,26 @@ def test_pool_mask_unpool_bit_exact(cuda, N, C, H, W):
     assert torch.equal(out.cpu().float().permute(0, 3, 1, 2), ref)      # includes the zero odd row/col
 
 
+def test_unpool_window_bit_exact(cuda):
+    """Windowed DePool2D: an odd-origin output window fed from a window of the pooled map equals the
+    same slice of the full unpool (incl. the zero trailing odd row/col)."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(5)
+    N, C, H, W = 2, 64, 23, 31
+    x = torch.relu(torch.randn(N, C, H, W)).mul(2).round().div(2).to(torch.bfloat16)
+    _, mask = K.maxpool2(_nhwc(x).to(cuda), with_mask=True)
+    u = torch.randn(N, C, H // 2, W // 2).to(torch.bfloat16)
+    full = L.depool2d(u.float(), x.float())
+    for (h0, w0, OH, OW) in [(3, 5, 17, 22), (0, 0, 23, 31), (7, 8, 16, 23), (22, 30, 1, 1)]:
+        ph0, pw0 = h0 // 2, w0 // 2
+        ph1, pw1 = min((h0 + OH - 1) // 2 + 1, H // 2), min((w0 + OW - 1) // 2 + 1, W // 2)
+        ph0, pw0 = min(ph0, H // 2 - 1), min(pw0, W // 2 - 1)      # trailing odd row/col: any non-empty u window
+        ph1, pw1 = max(ph1, ph0 + 1), max(pw1, pw0 + 1)
+        uw = _nhwc(u)[:, ph0:ph1, pw0:pw1].contiguous().to(cuda)
+        out = K.unpool2(uw, mask, H, W, u_origin=(ph0, pw0), window=(h0, w0, OH, OW))
+        assert torch.equal(out.cpu().float().permute(0, 3, 1, 2), full[:, :, h0:h0 + OH, w0:w0 + OW])
+
+
 def test_pool_without_mask(cuda):
     from iterative_inference_segm_b200 import _kernels as K
     x = torch.randn(2, 64, 10, 14).to(torch.bfloat16)
