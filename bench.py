@@ -256,19 +256,20 @@ def run_b200(args):
         st = ii._buffers(BATCH, H, W, N_ITER, False)
         timer = KernelTimer()
         reps = 3
+        dae.net.logits(st['h'], st['y_bf16'], full_down=True)          # fills the iteration-invariant borders
         with timer.recording():
             for _ in range(reps + 1):
-                dae.net.logits(st['h'], st['y_bf16'])
+                dae.net.logits(st['h'], st['y_bf16'], full_down=False)  # the steady-state application (49 of 50)
         summ = timer.summary()
-        conv_ms = [v for (name, tag), v in summ.items() if name == 'conv2d']
-        conv_total_ms = sum(sum(v[1:]) / len(v[1:]) for v in conv_ms)     # drop the first (cold) repetition
+        conv_lists = [v for (name, tag), v in summ.items() if name == 'conv2d']
+        conv_total_ms = sum(sum(v[1:]) / len(v[1:]) for v in conv_lists)     # drop the first (cold) repetition
         other = {}
         for (name, tag), v in summ.items():
             other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
-        flops = sum(dae.net.executed_conv_flops(H, W)) * BATCH    # executed: cone windows on the expanding path
+        flops = sum(dae.net.executed_conv_flops(H, W, steady_state=True)) * BATCH    # executed FLOPs only
         achieved = flops / (conv_total_ms * 1e-3) / 1e12
         peak = peaks['bf16_tflops_sustained']
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (12 conv launches of one DAE application, batch 10; executed FLOPs, cone-restricted expanding path)',
+        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (12 conv launches of one DAE application, batch 10; steady-state iteration: executed FLOPs on the y-dependent / crop-dependent windows)',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': conv_total_ms / 12.0,
                 'flops_per_application': flops}
@@ -277,7 +278,8 @@ def run_b200(args):
             if name == 'unpool2':       # algorithmic bytes: out written once, the touched u / mask windows read once
                 (n, uh, uw, c), (_, oh, ow, _) = tag
                 unpool_b += n * oh * ow * c * 2 + n * ((oh + 1) // 2 + 1) * ((ow + 1) // 2 + 1) * c * 2.5
-        breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
+        conv_ms = [round(sum(v[1:]) / len(v[1:]), 4) for (name, tag), v in summ.items() if name == 'conv2d']
+        breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()}, 'conv_ms_in_launch_order': conv_ms,
                      'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
                      'hbm_peak_gbs': peaks['hbm_gbs'],
                      'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues'}

@@ -82,6 +82,10 @@ typedef struct iiseg_conv_desc {
    * written; `out` is not touched.  Needs Cout % 64 == 0.                                  */
   void* pooled;
   uint32_t* pool_mask;
+  /* pool_H > 0: `pooled`/`pool_mask` are full [N,pool_H,pool_W,..] tensors and this launch writes
+   * only the pooled window of its (even-aligned) output window: rows [oh0/2, oh0/2 + OH/2).
+   * pool_H == 0: they are dense [N,OH/2,OW/2,..].                                            */
+  int pool_H, pool_W;
   int relu;           /* 1: rectify (Lasagne default), 0: linear            */
   int out_f32;        /* 1: fp32 output (only Cout == 16)                   */
 } iiseg_conv_desc;

@@ -87,10 +87,14 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     oh0, ow0, OH, OW = window if window is not None else (0, 0, fOH, fOW)
     if pooled is not None:     # fused 2x2 max-pool (+ mask): the full-resolution output is never written
         _chk(pooled, BF16, 'pooled')
-        assert tuple(pooled.shape) == (N, OH // 2, OW // 2, Cout), (tuple(pooled.shape), (N, OH // 2, OW // 2, Cout))
+        dense = tuple(pooled.shape) == (N, OH // 2, OW // 2, Cout)
+        if not dense:   # a window of a larger pooled tensor: even origin, pooled rows [oh0/2, oh0/2 + OH/2)
+            assert pooled.shape[0] == N and pooled.shape[3] == Cout and oh0 % 2 == 0 and ow0 % 2 == 0
+            assert oh0 // 2 + OH // 2 <= pooled.shape[1] and ow0 // 2 + OW // 2 <= pooled.shape[2]
+        pool_hw = (0, 0) if dense else (pooled.shape[1], pooled.shape[2])
         if pool_mask is not None:
             _chk(pool_mask, torch.int32, 'pool_mask')
-            assert tuple(pool_mask.shape) == (N, OH // 2, OW // 2, Cout // 8)
+            assert tuple(pool_mask.shape) == tuple(pooled.shape[:3]) + (Cout // 8,)
         assert out is None
     elif out is None:
         out = torch.empty((N, OH, OW, Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
@@ -108,6 +112,7 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       addend=addend.data_ptr() if addend is not None else None,
                       pooled=pooled.data_ptr() if pooled is not None else None,
                       pool_mask=pool_mask.data_ptr() if pool_mask is not None else None,
+                      pool_H=pool_hw[0] if pooled is not None else 0, pool_W=pool_hw[1] if pooled is not None else 0,
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1],
                       relu=int(bool(relu)), out_f32=int(bool(out_f32)))

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('addend', C.c_void_p),
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int),
-        ('pooled', C.c_void_p), ('pool_mask', C.c_void_p),
+        ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
         ('relu', C.c_int), ('out_f32', C.c_int),
     ]
 

@@ -77,7 +77,8 @@ struct alignas(64) ConvParams {
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
   uint32_t* pool_mask;       // tie-inclusive mask nibbles [N,PH,PW,Cout/8] or NULL
-  int PH, PW;
+  int PH, PW;                // pooled tensor extent
+  int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue
@@ -417,8 +418,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
             const int pp = et >> 3, cgp = et & 7;
             const int tw2 = p.TW >> 1;
             const int ph_l = pp / tw2, pw_l = pp - ph_l * tw2;
-            const int ph = ((tc.th * p.TH) >> 1) + ph_l, pw = ((tc.tw * p.TW) >> 1) + pw_l;
-            if (ph_l < (p.TH >> 1) && ph < p.PH && pw < p.PW) {
+            const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
+            const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
+            if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
               const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
               uint32_t w[4][4];
 #pragma unroll
@@ -593,6 +595,10 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
   IISEG_CHECK(d->N >= 1, "conv: empty batch");
+  if (d->pooled != nullptr && d->pool_H > 0)
+    IISEG_CHECK(d->oh0 % 2 == 0 && d->ow0 % 2 == 0 && d->oh0 / 2 + d->OH / 2 <= d->pool_H && d->ow0 / 2 + d->OW / 2 <= d->pool_W,
+                "conv: pooled window (origin %d,%d size %dx%d) must be even-aligned and inside the %dx%d pooled tensor",
+                d->oh0, d->ow0, d->OH, d->OW, d->pool_H, d->pool_W);
   if (d->addend != nullptr)
     IISEG_CHECK(d->ah0 >= 0 && d->aw0 >= 0 && d->ah0 + d->OH <= d->AH && d->aw0 + d->OW <= d->AW,
                 "conv: addend window [%d+%d, %d+%d] outside %dx%d", d->ah0, d->OH, d->aw0, d->OW, d->AH, d->AW);
@@ -625,7 +631,10 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.R = d->R; p.S = d->S;
   p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
   p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);
-  p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask; p.PH = d->OH / 2; p.PW = d->OW / 2;
+  p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask;
+  p.pwin_h = d->OH / 2; p.pwin_w = d->OW / 2;
+  if (d->pool_H > 0) { p.PH = d->pool_H; p.PW = d->pool_W; p.p_h0 = d->oh0 / 2; p.p_w0 = d->ow0 / 2; }
+  else { p.PH = p.pwin_h; p.PW = p.pwin_w; p.p_h0 = 0; p.p_w0 = 0; }
   p.n_ntiles = d->Cout / BN;
   p.num_tiles = d->N * p.tiles_h * p.tiles_w * p.n_ntiles;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;

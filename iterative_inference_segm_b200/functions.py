@@ -182,7 +182,9 @@ class IterativeInference(object):
             for acc in st['iter']:
                 acc.zero_()
         for it in range(num_iter):
-            logits = net.logits(st['h'], st['y_bf16'])
+            # the first iteration of a batch computes the whole contracting path (h is new); later ones only
+            # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
+            logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0))
             K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step)
             K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])

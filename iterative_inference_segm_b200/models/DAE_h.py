@@ -104,16 +104,35 @@ class DAENet(object):
                 Wc[p + 1] = (ul // 2, min((uh - 1) // 2 + 1, S2h), vl // 2, min((vh - 1) // 2 + 1, S2w))
         return Wc, Wu
 
-    def executed_conv_flops(self, H, W):
+    def down_windows(self, H, W):
+        """y-dependent window of every contracting-path conv output, even-aligned for the fused pool.
+
+        A level-p output pixel outside Wu[p] (the same cone, walked downwards from the image) sees only
+        the zero padding around y, constant borders of the levels above and -- from level n_pool+1 on -- h,
+        none of which change between iterations.  So after the first iteration of a batch, pool_p and
+        mask_p outside the window already hold the right values and only the window is recomputed."""
+        sizes = self.level_sizes(H, W)
+        _, Wu = self.cone_windows(H, W)
+        D = {}
+        for p in range(1, self.total + 1):
+            hl, hh, wl, wh = Wu[p]
+            Sh, Sw = sizes[p - 1]
+            D[p] = (hl & ~1, min((hh + 1) & ~1, (Sh // 2) * 2), wl & ~1, min((wh + 1) & ~1, (Sw // 2) * 2))
+        return D
+
+    def executed_conv_flops(self, H, W, steady_state=True):
         """Executed algorithmic FLOPs (2*MAC, real channel counts) of the 2P conv launches of one
-        application, per image: full maps on the contracting path, cone windows on the expanding path."""
+        application, per image: cone windows on the expanding path; on the contracting path the
+        y-dependent windows (`steady_state`, iterations 2..N) or the full maps (first iteration)."""
         sizes = self.level_sizes(H, W)
         Wc, _ = self.cone_windows(H, W)
+        D = self.down_windows(H, W)
         fl = []
         cin = self.n_classes
         for p in range(self.total):
             c = cin + (self.nb_h if p == self.n_pool else 0)
-            fl.append(2.0 * sizes[p][0] * sizes[p][1] * c * self.filters[p] * 9)
+            hl, hh, wl, wh = D[p + 1] if steady_state else (0, sizes[p][0], 0, sizes[p][1])
+            fl.append(2.0 * (hh - hl) * (wh - wl) * c * self.filters[p] * 9)
             cin = self.filters[p]
         up_in = self.filters[-1]
         for p in range(self.total, 0, -1):
@@ -150,9 +169,11 @@ class DAENet(object):
         return ws
 
     # -- one application ----------------------------------------------------
-    def logits(self, h_bf16, y_bf16):
+    def logits(self, h_bf16, y_bf16, full_down=True):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
-        Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16)."""
+        Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16).
+        `full_down=False` recomputes only the y-dependent windows of the contracting path; valid when
+        the workspace already holds a full pass for the same h (see `down_windows`)."""
         B, H, W, _ = y_bf16.shape
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
@@ -160,15 +181,21 @@ class DAENet(object):
         assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.h_pad,), \
             (tuple(h_bf16.shape), self.h_spatial(H, W), self.h_pad)
         x = y_bf16
+        D = None if full_down else self.down_windows(H, W)
         for p in range(self.total):
             Wk, bk = self.down[p]
             pad = self.padding if (p == 0 and self.padding > 0) else 1
+            win = None
+            if D is not None:
+                hl, hh, wl, wh = D[p + 1]
+                win = (hl, wl, hh - hl, wh - wl)
             # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
             # pre-pool map is consumed on chip and never written (nothing else reads it)
             if p == self.n_pool:
-                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
+                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, window=win, pooled=ws['pool'][p],
+                         pool_mask=ws['mask'][p])
             else:
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
             x = ws['pool'][p]
         u, u_origin = ws['pool'][-1], (0, 0)
         for i, p in enumerate(range(self.total, 0, -1)):

@@ -96,6 +96,22 @@ def test_loop_vs_oracle_and_exact_metrics(cuda, built):
     assert torch.equal(y1, y2)
 
 
+def test_windowed_down_path_is_exact(cuda, built):
+    """Recomputing only the y-dependent windows of the contracting path (iterations 2..N) gives
+    bit-identical logits to recomputing everything: the hoisted borders are iteration-invariant."""
+    pf, pd, fcn, dae = built
+    gd = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    from iterative_inference_segm_b200 import _kernels as K
+    net = dae.net
+    h = K.pack_nchw(torch.from_numpy(gd['h']).to(cuda), net.h_pad)
+    y_a = K.pack_nchw(torch.from_numpy(gd['y']).to(cuda), net.y_cpad)
+    y_b = K.pack_nchw(torch.softmax(torch.randn(1, NCLS, 32, 40, device=cuda), 1), net.y_cpad)
+    net.logits(h, y_a, full_down=True)                       # fills the borders for this h
+    win = net.logits(h, y_b, full_down=False).clone()        # different y, windows only
+    full = net.logits(h, y_b, full_down=True).clone()
+    assert torch.equal(win, full)
+
+
 def test_early_exit_semantics(cuda, built):
     """eps huge: every image does exactly one update, then is frozen; no per-iteration metrics."""
     from iterative_inference_segm_b200.functions import IterativeInference
