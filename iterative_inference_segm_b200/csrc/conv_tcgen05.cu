@@ -72,6 +72,10 @@ struct alignas(64) ConvParams {
   int R, S;
   int in_off_h, in_off_w;   // input row of tap r for local output row o: o + in_off_h + r
   int TH, TW;
+  int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
+  int a_blk_bytes, n_a, n_b, g_b;   // halo kernel: A buffer size / count, B stage count, taps per B stage
+  int b_resident;           // halo kernel: all R*S*n_cblk weight blocks stay in smem for the whole launch
+  int n_stage_buf;          // output staging buffers (2, or 1 when the resident filter bank needs the room)
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   int OH, OW, Cout;
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
@@ -215,6 +219,175 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   return c;
 }
 
+// ---------------------------------------------------------------------------
+// Epilogue (8 warps, shared by both main-loop kernels): TMEM -> registers -> bias / skip-sum / ReLU ->
+// bf16 -> swizzled smem staging -> TMA store, fused 2x2 max-pool + tie mask, or direct 16-channel stores.
+// TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
+// Accumulator row m is box pixel (m / pitch, m % pitch); rows with m % pitch >= TW are halo junk.
+// ---------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
+  using Cfg = ConvCfg<BN>;
+  auto tmem_full_bar = [&](int i) { return tmem_full_bar0 + 8u * i; };
+  auto tmem_empty_bar = [&](int i) { return tmem_empty_bar0 + 8u * i; };
+    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int macc = q * 32 + lane;         // accumulator row
+    const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+    const bool in_box = (hl < p.TH) && (wl < p.TW);
+    const int m = hl * p.TW + wl;           // dense pixel index inside the TH x TW box (staging row)
+    const bool issuer = (warp == 4);
+    int iter = 0;
+    int store_buf = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+      const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+      const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+      const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+      mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      const int n0 = tc.nt * BN;
+
+      if constexpr (Cfg::kTmaStore) {
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 64; ++chunk) {
+          const int cbase = n0 + chunk * 64 + half * 32;     // this thread's 32 channels
+          // skip-sum operand: this pixel's 32 channels = 64 contiguous bytes
+          uint4 add[4];
+          if (p.addend != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              add[j] = valid ? ldg_nc_v4(p.addend + apix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
+          }
+          uint32_t v[32];
+          tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
+          tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
+          // the staging buffer we are about to overwrite must have been read by its TMA store
+          if (issuer && elect_one_sync()) { if (p.n_stage_buf > 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          tmem_ld_wait();
+          if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
+            tcgen05_fence_before();
+            mbar_arrive(tmem_empty_bar(as));
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + 2 * j);
+            float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + 2 * j + 1);
+            if (p.addend != nullptr) {
+              const uint4& a4 = add[j >> 2];
+              const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
+              f0 += bf16_lo(aw); f1 += bf16_hi(aw);
+            }
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            packed[j] = pack_bf16x2(f0, f1);
+          }
+          // four 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (!in_box) break;
+            const int chunk16 = half * 4 + cc;
+            const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
+                         "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
+          }
+          if (p.pooled == nullptr) {
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (issuer && elect_one_sync()) {
+              tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
+              tma_store_commit();
+            }
+          } else {
+            // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
+            // staged tile never goes to HBM.  One thread per (pooled pixel, 8 channels): TH, TW and the
+            // tile origin are even, so every 2x2 window lies inside the box.
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int et = threadIdx.x - 128;
+            const int pp = et >> 3, cgp = et & 7;
+            const int tw2 = p.TW >> 1;
+            const int ph_l = pp / tw2, pw_l = pp - ph_l * tw2;
+            const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
+            const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
+            if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
+              const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
+              uint32_t w[4][4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int mm = m00 + (e >> 1) * p.TW + (e & 1);
+                const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
+              }
+              uint32_t bits = 0, outw[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float lo[4], hi[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { lo[e] = bf16_lo(w[e][k]); hi[e] = bf16_hi(w[e][k]); }
+                const float mlo = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
+                const float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
+                uint32_t nlo = 0, nhi = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { nlo |= (lo[e] == mlo ? 1u : 0u) << e; nhi |= (hi[e] == mhi ? 1u : 0u) << e; }
+                bits |= (nlo << (8 * k)) | (nhi << (8 * k + 4));
+                outw[k] = pack_bf16x2(mlo, mhi);
+              }
+              const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
+              const int cch = n0 + chunk * 64 + cgp * 8;
+              stg_v4(p.pooled + ppix * p.Cout + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
+              if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+            }
+          }
+          if (p.n_stage_buf > 1) store_buf ^= 1;
+        }
+      } else {
+        // 16-channel outputs (score maps, logits): direct stores from registers, 8 channels per thread
+        static_assert(BN == 16 || Cfg::kTmaStore, "direct-store epilogue is written for BN == 16");
+        uint32_t v[8];
+        tmem_ld_x8(taddr + half * 8, v);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar(as));
+        const int cbase = n0 + half * 8;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
+        if (p.addend != nullptr && valid) {
+          const uint4 a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
+          const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
+            stg_v4(o, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+          }
+        }
+      }
+    }
+    if (Cfg::kTmaStore && issuer && elect_one_sync()) tma_store_wait_read<0>();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -336,159 +509,198 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    // ===================== Epilogue (8 warps) =====================
-    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int m = q * 32 + lane;            // accumulator row = pixel index inside the box
-    const int hl = m / p.TW, wl = m - hl * p.TW;
-    const bool issuer = (warp == 4);
-    int iter = 0;
-    int store_buf = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
-      const TileCoord tc = decode_tile(p, t);
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1u;
-      const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
-      const bool valid = (hl < p.TH) && (oh < p.OH) && (ow < p.OW);
-      const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
-      const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
-      mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      const int n0 = tc.nt * BN;
+    conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+  }
 
-      if constexpr (Cfg::kTmaStore) {
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 64; ++chunk) {
-          const int cbase = n0 + chunk * 64 + half * 32;     // this thread's 32 channels
-          // skip-sum operand: this pixel's 32 channels = 64 contiguous bytes
-          uint4 add[4];
-          if (p.addend != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              add[j] = valid ? ldg_nc_v4(p.addend + apix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
-          }
-          uint32_t v[32];
-          tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
-          tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
-          // the staging buffer we are about to overwrite must have been read by its TMA store
-          if (issuer && elect_one_sync()) tma_store_wait_read<1>();
-          tmem_ld_wait();
-          if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
-            tcgen05_fence_before();
-            mbar_arrive(tmem_empty_bar(as));
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + 2 * j);
-            float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + 2 * j + 1);
-            if (p.addend != nullptr) {
-              const uint4& a4 = add[j >> 2];
-              const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
-              f0 += bf16_lo(aw); f1 += bf16_hi(aw);
-            }
-            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-            packed[j] = pack_bf16x2(f0, f1);
-          }
-          // four 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int chunk16 = half * 4 + cc;
-            const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
-                         "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
-          }
-          if (p.pooled == nullptr) {
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (issuer && elect_one_sync()) {
-              tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
-              tma_store_commit();
-            }
-          } else {
-            // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
-            // staged tile never goes to HBM.  One thread per (pooled pixel, 8 channels): TH, TW and the
-            // tile origin are even, so every 2x2 window lies inside the box.
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int et = threadIdx.x - 128;
-            const int pp = et >> 3, cgp = et & 7;
-            const int tw2 = p.TW >> 1;
-            const int ph_l = pp / tw2, pw_l = pp - ph_l * tw2;
-            const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
-            const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
-            if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
-              const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
-              uint32_t w[4][4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int mm = m00 + (e >> 1) * p.TW + (e & 1);
-                const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
-              }
-              uint32_t bits = 0, outw[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float lo[4], hi[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { lo[e] = bf16_lo(w[e][k]); hi[e] = bf16_hi(w[e][k]); }
-                const float mlo = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
-                const float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
-                uint32_t nlo = 0, nhi = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { nlo |= (lo[e] == mlo ? 1u : 0u) << e; nhi |= (hi[e] == mhi ? 1u : 0u) << e; }
-                bits |= (nlo << (8 * k)) | (nhi << (8 * k + 4));
-                outw[k] = pack_bf16x2(mlo, mhi);
-              }
-              const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
-              const int cch = n0 + chunk * 64 + cgp * 8;
-              stg_v4(p.pooled + ppix * p.Cout + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
-              if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
-            }
-          }
-          store_buf ^= 1;
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Halo-tile main loop (3x3 filters): ONE activation load per 64-channel block.
+//
+// The per-tap kernel above re-fetches the 128-pixel A box for each of the R*S taps, and every layer
+// whose k-block is short (Cout <= 128) ends up bound by L2->SM ingest (~64 B/clk/SM measured), not by
+// the tensor pipe.  Here the TMA box is the output tile plus its filter halo, (TH+R-1) x (TW+S-1)
+// pixels, loaded once per channel block; tap (r,s) is the SAME smem tile read through a UMMA
+// descriptor whose start address is advanced by (r*pitch + s) rows, pitch = TW+S-1.  A SWIZZLE_128B
+// descriptor may start at any row: the swizzle is a function of the absolute smem address and the
+// descriptor's base_offset stays 0 (tools/experiments/umma_shift_test.cu).  Accumulator row m is then
+// box pixel (m / pitch, m % pitch); the S-1 rows at the end of each line are junk and are dropped by
+// the epilogue.  Activations (ring of n_a halo tiles) and weights (ring of n_b stages of g_b taps)
+// flow through two independent mbarrier rings.
+// ---------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the plan uses the full 227 KB: the dynamic segment must start 1024-aligned (no round-up slack)
+  if ((smem_u32(smem_raw) & 1023u) != 0u) mbar_timeout(p.diag, 9, 0);
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.g_b) * Cfg::kBBlockBytes;
+  const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
+  const uint32_t b_bytes_total = p.b_resident ? static_cast<uint32_t>(p.R * p.S * (p.n_cblk0 + p.n_cblk1)) * Cfg::kBBlockBytes
+                                              : static_cast<uint32_t>(p.n_b) * b_stage_bytes;
+  const uint32_t smem_stage_out = b_ring + b_bytes_total;
+  const uint32_t bars = smem_stage_out + (Cfg::kTmaStore ? static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes : 0u);
+  auto a_full = [&](int i) { return bars + 8u * i; };
+  auto a_empty = [&](int i) { return bars + 8u * (4 + i); };
+  auto b_full = [&](int i) { return bars + 8u * (8 + i); };
+  auto b_empty = [&](int i) { return bars + 8u * (16 + i); };
+  auto tmem_full_bar = [&](int i) { return bars + 8u * (24 + i); };
+  auto tmem_empty_bar = [&](int i) { return bars + 8u * (26 + i); };
+  const uint32_t tmem_slot = bars + 8u * 28;
+  const uint32_t b_res_bar = bars + 8u * 29;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_src0);
+    prefetch_tmap(&p.tm_src1);
+    prefetch_tmap(&p.tm_w);
+    if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(b_res_bar, 1);
+    for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < p.n_b; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int n_cblk = p.n_cblk0 + p.n_cblk1;
+  const int taps = p.R * p.S;
+  const int n_groups = (taps + p.g_b - 1) / p.g_b;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one_sync()) {
+      int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
+      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + p.R - 1) * p.pitch) * 128u;
+      auto issue_a = [&](int t, int cb) {       // one halo tile: (TH+R-1) x pitch pixels of a 64-channel block
+        const TileCoord tc = decode_tile(p, t);
+        mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
+        mbar_arrive_expect_tx(a_full(ia), a_bytes);
+        const int h_base = tc.th * p.TH + p.in_off_h, w_base = tc.tw * p.TW + p.in_off_w;
+        if (cb < p.n_cblk0)
+          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src0, a_full(ia), cb * kBlockK, w_base, h_base, tc.n);
+        else
+          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src1, a_full(ia), (cb - p.n_cblk0) * kBlockK, w_base, h_base, tc.n);
+        if (++ia == p.n_a) { ia = 0; pa ^= 1u; }
+      };
+      if (p.b_resident) {
+        // Cout == BN and the whole filter bank fits: load it once, then only halo tiles stream (the
+        // A ring then holds several tiles, which hides the TMA latency of these short-K layers)
+        const int n_blocks = taps * n_cblk;
+        if (blockIdx.x < p.num_tiles) {
+          mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
+          for (int i = 0; i < n_blocks; ++i)
+            tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * kBlockK, 0);
         }
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
+          for (int cb = 0; cb < n_cblk; ++cb) issue_a(t, cb);
       } else {
-        // 16-channel outputs (score maps, logits): direct stores from registers, 8 channels per thread
-        static_assert(BN == 16 || Cfg::kTmaStore, "direct-store epilogue is written for BN == 16");
-        uint32_t v[8];
-        tmem_ld_x8(taddr + half * 8, v);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(tmem_empty_bar(as));
-        const int cbase = n0 + half * 8;
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
-        if (p.addend != nullptr && valid) {
-          const uint4 a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
-          const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (valid) {
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
-            stg_v4(o, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+        // streamed weights: the NEXT halo tile is requested before this step's weight stages, so its
+        // latency overlaps this step's MMAs
+        int t = blockIdx.x, cb = 0;
+        bool have = t < p.num_tiles;
+        if (have) issue_a(t, cb);
+        while (have) {
+          int t2 = t, cb2 = cb + 1;
+          if (cb2 == n_cblk) { cb2 = 0; t2 += gridDim.x; }
+          const bool have2 = t2 < p.num_tiles;
+          if (have2) issue_a(t2, cb2);
+          const int nt = decode_tile(p, t).nt;
+          for (int grp = 0; grp < n_groups; ++grp) {
+            const int tap0 = grp * p.g_b;
+            const int g_n = (taps - tap0) < p.g_b ? (taps - tap0) : p.g_b;
+            mbar_wait(b_empty(ib), pb ^ 1u, p.diag, 6, ib);
+            mbar_arrive_expect_tx(b_full(ib), static_cast<uint32_t>(g_n) * Cfg::kBBlockBytes);
+            for (int g = 0; g < g_n; ++g)
+              tma_load_2d(b_ring + ib * b_stage_bytes + g * Cfg::kBBlockBytes, &p.tm_w, b_full(ib),
+                          ((tap0 + g) * n_cblk + cb) * kBlockK, nt * BN);
+            if (++ib == p.n_b) { ib = 0; pb ^= 1u; }
           }
+          t = t2; cb = cb2; have = have2;
         }
       }
     }
-    if (Cfg::kTmaStore && issuer && elect_one_sync()) tma_store_wait_read<0>();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_instr_desc<BN>();
+    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
+    int iter = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int cb = 0; cb < n_cblk; ++cb) {
+        mbar_wait(a_full(ia), pa, p.diag, 7, ia);
+        const uint32_t a_tile = a_ring + ia * p.a_blk_bytes;
+        if (p.b_resident) {
+          if (iter == 0 && cb == 0) mbar_wait(b_res_bar, 0, p.diag, 10, 0);
+          tcgen05_fence_after();
+          if (elect_one_sync()) {
+            for (int tap = 0; tap < taps; ++tap) {
+              const int r = tap / p.S, s = tap - r * p.S;
+              const uint64_t a_desc = make_smem_desc(a_tile + static_cast<uint32_t>(r * p.pitch + s) * 128u);
+              const uint64_t b_desc = make_smem_desc(b_ring + static_cast<uint32_t>(tap * n_cblk + cb) * Cfg::kBBlockBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(a_empty(ia));
+            if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));
+          }
+          __syncwarp();
+        } else {
+          for (int grp = 0; grp < n_groups; ++grp) {
+            const int tap0 = grp * p.g_b;
+            const int g_n = (taps - tap0) < p.g_b ? (taps - tap0) : p.g_b;
+            mbar_wait(b_full(ib), pb, p.diag, 8, ib);
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
+              for (int g = 0; g < g_n; ++g) {
+                const int tap = tap0 + g;
+                const int r = tap / p.S, s = tap - r * p.S;
+                // tap (r,s): the same halo tile, start advanced by (r*pitch + s) rows of 128 bytes
+                const uint64_t a_desc = make_smem_desc(a_tile + static_cast<uint32_t>(r * p.pitch + s) * 128u);
+                const uint64_t b_desc = make_smem_desc(b_ring + ib * b_stage_bytes + g * Cfg::kBBlockBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(b_empty(ib));                                       // weights slot free when the MMAs retire
+              if (grp == n_groups - 1) {
+                umma_commit(a_empty(ia));                                     // all taps of this halo tile issued
+                if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));         // accumulator ready
+              }
+            }
+            __syncwarp();
+            if (++ib == p.n_b) { ib = 0; pb ^= 1u; }
+          }
+        }
+        if (++ia == p.n_a) { ia = 0; pa ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -563,6 +775,43 @@ static void choose_box(int OH, int OW, int* TH, int* TW, bool even) {
   *TH = bh; *TW = bw;
 }
 
+// Halo-tile box: TH x TW outputs with TH * (TW+S-1) <= 128 + S-1 accumulator rows and a
+// (TH+R-1) x (TW+S-1) TMA box of at most `max_rows` rows; fewest tiles first, then the smallest halo tile.
+static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_rows, int* TH, int* TW) {
+  long best = -1; long best_rows = 0; int bh = 0, bw = 0;
+  const int step = even ? 2 : 1;
+  for (int th = step; th <= 128 && th < OH + step; th += step) {
+    int tw = (128 + S - 1) / th - (S - 1);
+    if (tw > OW) tw = OW;
+    if (even) tw &= ~1;
+    if (tw < step) continue;
+    // try this width and a few narrower ones (a narrower box can tile OW with less waste)
+    for (int w = tw; w >= step && w > tw - 8; w -= step) {
+      const int pitch = w + S - 1;
+      const long rows = (long)(th + R - 1) * pitch;
+      if (pitch > 256 || th + R - 1 > 256 || rows > max_rows) continue;
+      const long tiles = (long)ceil_div(OW, w) * ceil_div(OH, th);
+      if (best < 0 || tiles < best || (tiles == best && rows < best_rows)) { best = tiles; best_rows = rows; bh = th; bw = w; }
+    }
+  }
+  if (best < 0) return false;
+  *TH = bh; *TW = bw;
+  return true;
+}
+
+template <int BN>
+static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_halo_kernel<BN><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BN>
 static int launch_conv(const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
@@ -609,10 +858,46 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   const bool fuse_pool = d->pooled != nullptr;
   // with the fused pool only the 2*floor(OH/2) x 2*floor(OW/2) outputs that have a pool window are computed
   const int covH = fuse_pool ? (d->OH / 2) * 2 : d->OH, covW = fuse_pool ? (d->OW / 2) * 2 : d->OW;
-  choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
-  if (encode_nhwc(&p.tm_src0, d->src0, d->N, d->H, d->W, d->C0, p.TH, p.TW)) return -1;
+  static const int env_halo = getenv("IISEG_CONV_HALO") ? atoi(getenv("IISEG_CONV_HALO")) : 1;
+  // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
+  // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
+  // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
+  const int n_cblk_all = (d->C0 + d->C1) / 64;
+  bool halo = env_halo && d->R == 3 && d->S == 3;
+  int box_h = 0, box_w = 0;       // TMA box extent in pixels
+  int smem_halo = 0;
+  if (halo) {
+    // shared-memory plan: n_a halo tiles + the resident filter bank + output staging (1 or 2 buffers)
+    const int b_blk = BN * 128;
+    const int b_all = d->R * d->S * n_cblk_all * b_blk;
+    halo = d->Cout == BN && choose_halo_box(covH, covW, d->R, d->S, fuse_pool, 256, &p.TH, &p.TW);
+    if (halo && env_halo != 2 && p.TH * p.TW < 100) halo = false;          // too many junk accumulator rows
+    if (halo) {
+      p.pitch = p.TW + d->S - 1;
+      const int rows_box = (p.TH + d->R - 1) * p.pitch;
+      const int rows_read = (d->R - 1) * p.pitch + d->S - 1 + kBlockM;     // last row the shifted descriptors touch
+      p.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * 128 + 1023) / 1024 * 1024;
+      const int total = 227 * 1024 - 256;
+      p.b_resident = 1; p.n_b = 0; p.g_b = 1;
+      p.n_stage_buf = BN >= 64 ? 2 : 0;
+      if (BN >= 64 && total - b_all - 2 * kStagingBytes < 3 * p.a_blk_bytes) p.n_stage_buf = 1;
+      const int staging = p.n_stage_buf * kStagingBytes;
+      p.n_a = (total - b_all - staging) / p.a_blk_bytes;
+      if (p.n_a > 4) p.n_a = 4;
+      if (p.n_a < 2) halo = false;      // filter bank too large to stay resident: per-tap kernel
+      box_h = p.TH + d->R - 1; box_w = p.pitch;
+      smem_halo = p.n_a * p.a_blk_bytes + b_all + staging + 256;
+    }
+  }
+  if (!halo) {
+    choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
+    p.pitch = p.TW;
+    p.n_stage_buf = 2;
+    box_h = p.TH; box_w = p.TW;
+  }
+  if (encode_nhwc(&p.tm_src0, d->src0, d->N, d->H, d->W, d->C0, box_h, box_w)) return -1;
   if (d->src1 != nullptr) {
-    if (encode_nhwc(&p.tm_src1, d->src1, d->N, d->H, d->W, d->C1, p.TH, p.TW)) return -1;
+    if (encode_nhwc(&p.tm_src1, d->src1, d->N, d->H, d->W, d->C1, box_h, box_w)) return -1;
   } else {
     p.tm_src1 = p.tm_src0;
   }
@@ -646,6 +931,14 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     p.dbg = env_dbg; p.stages = env_stages;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (halo) {
+    switch (BN) {
+      case 16: return launch_conv_halo<16>(p, smem_halo, s);
+      case 64: return launch_conv_halo<64>(p, smem_halo, s);
+      case 128: return launch_conv_halo<128>(p, smem_halo, s);
+      default: return launch_conv_halo<256>(p, smem_halo, s);
+    }
+  }
   switch (BN) {
     case 16: return launch_conv<16>(p, s);
     case 64: return launch_conv<64>(p, s);
