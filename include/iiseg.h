@@ -37,6 +37,9 @@ int iiseg_device_check(int dev);
 /* After a failed stream sync: copies the kernels' pinned-host diagnostic words
  * (which pipeline barrier timed out) into out[0..n). Returns words written. */
 int iiseg_read_diag(int32_t* out, int n);
+/* Tuning aid: with IISEG_CONV_DBG=4 block 0 of every conv launch stamps clock64() at fixed points
+ * of its first 32 tiles (16 slots each); returns the words copied. */
+int iiseg_debug_read_timeline(long long* out, int n);
 /* Number of kernel launches issued through this library since load. */
 int64_t iiseg_launch_count(void);
 
@@ -94,9 +97,10 @@ int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
 /* ---- pooling: lasagne Pool2DLayer(2) + DePool2D -------------------------
  * 2x2/stride-2 max, floor (models/fcn_down.py:122).  `mask` (may be NULL)
  * receives the tie-inclusive argmax mask DePool2D derives with
- * T.grad(pool, ones) (layers/mylayers.py:111-112): one 4-bit nibble per
- * (window, channel), bit (2*dy+dx) set iff x[2oh+dy, 2ow+dx] == window max;
- * eight channels per uint32, layout [N,H/2,W/2,C/8].  C multiple of 8. */
+ * T.grad(pool, ones) (layers/mylayers.py:111-112): four bits per (window,
+ * channel), one per window position pos = 2*dy+dx, set iff x[2oh+dy, 2ow+dx] ==
+ * window max; eight channels per uint32, layout [N,H/2,W/2,C/8]; inside a word
+ * channel j of the group sits at bit 16*(j&1) + 4*(j>>1) + pos.  C multiple of 8. */
 int iiseg_maxpool2_mask_fwd(const void* x, void* pooled, uint32_t* mask, int N,
                             int H, int W, int C, void* stream);
 /* DePool2D (layers/mylayers.py:88-115): out[2oh+dy,2ow+dx] = u[oh,ow] where

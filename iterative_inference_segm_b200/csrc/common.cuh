@@ -54,6 +54,28 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// ---- packed bf16x2 helpers for the pool / ReLU epilogues --------------------------------------
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// 0xFFFF in each 16-bit half whose values compare equal (IEEE ==: -0 == +0, NaN != NaN)
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+// Tie-mask word layout (8 channels x 4 window positions in one uint32): channel j = 2k + par
+// (k = 32-bit word of the 16-byte vector, par = half), window position pos = 2*dy + dx:
+//     bit = 16*par + 4*k + pos
+// so the equality mask of one packed compare lands on its two bits with a single AND.
+__device__ __forceinline__ uint32_t tie_bits(uint32_t eq_mask, int k, int pos) {
+  return eq_mask & ((1u << (4 * k + pos)) | (1u << (16 + 4 * k + pos)));
+}
+// expands the two mask bits of (word k, position pos) back to 16-bit lane masks
+__device__ __forceinline__ uint32_t tie_select(uint32_t bits, int k, int pos) {
+  const uint32_t lo = (bits >> (4 * k + pos)) & 1u, hi = (bits >> (16 + 4 * k + pos)) & 1u;
+  return (0u - lo) & 0x0000FFFFu | (0u - hi) & 0xFFFF0000u;
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

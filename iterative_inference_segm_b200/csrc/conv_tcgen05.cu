@@ -77,6 +77,7 @@ struct alignas(64) ConvParams {
   int b_resident;           // halo kernel: all R*S*n_cblk weight blocks stay in smem for the whole launch
   int n_stage_buf;          // output staging buffers (2, or 1 when the resident filter bank needs the room)
   int tiles_h, tiles_w, n_ntiles, num_tiles;
+  float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
   int OH, OW, Cout;
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
@@ -87,6 +88,10 @@ struct alignas(64) ConvParams {
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue
 };
+
+// Debug timeline (IISEG_CONV_DBG bit 2): block 0 stamps clock64() at fixed points of its first 32 tiles.
+__device__ long long g_timeline[32 * 16];
+#define IISEG_STAMP(tile, slot) do { if ((p.dbg & 4) && blockIdx.x == 0 && (tile) < 32) g_timeline[(tile) * 16 + (slot)] = clock64(); } while (0)
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -211,11 +216,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Kernel
 // ---------------------------------------------------------------------------
 struct TileCoord { int n, th, tw, nt; };
+// q = a / d, a = a % d for 0 <= a < 2^21 and launch-constant d, without the ~40-instruction integer
+// division: float reciprocal estimate plus one correction step in each direction (always exact).
+__device__ __forceinline__ int fast_divmod(int& a, int d, float inv_d) {
+  int q = __float2int_rz(__int2float_rn(a) * inv_d);
+  int r = a - q * d;
+  if (r >= d) { ++q; r -= d; }
+  if (r < 0) { --q; r += d; }
+  a = r;
+  return q;
+}
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
-  c.nt = t % p.n_ntiles; t /= p.n_ntiles;
-  c.tw = t % p.tiles_w;  t /= p.tiles_w;
-  c.th = t % p.tiles_h;  c.n = t / p.tiles_h;
+  int rest = fast_divmod(t, p.n_ntiles, p.inv_ntiles);  c.nt = t;    // t = nt + n_ntiles * rest
+  int rest2 = fast_divmod(rest, p.tiles_w, p.inv_tiles_w); c.tw = rest;
+  c.n = fast_divmod(rest2, p.tiles_h, p.inv_tiles_h);   c.th = rest2;
   return c;
 }
 
@@ -249,8 +264,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
       const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
       const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
       const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+      if (issuer && lane == 0) IISEG_STAMP(iter, 4);
       mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
       tcgen05_fence_after();
+      if (issuer && lane == 0) IISEG_STAMP(iter, 5);
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
       const int n0 = tc.nt * BN;
 
@@ -271,24 +288,32 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
           // the staging buffer we are about to overwrite must have been read by its TMA store
           if (issuer && elect_one_sync()) { if (p.n_stage_buf > 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           tmem_ld_wait();
+          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 6);
           if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
             tcgen05_fence_before();
             mbar_arrive(tmem_empty_bar(as));
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 7);
           const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
           uint32_t packed[16];
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + cbase + 2 * j);
-            float f1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + cbase + 2 * j + 1);
+          for (int j4 = 0; j4 < 8; ++j4) {      // 4 channels per step: one 16-byte bias load
+            const float4 b = __ldg(bias4 + j4);
+            float f0 = __uint_as_float(v[4 * j4]) + b.x, f1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
+            float f2 = __uint_as_float(v[4 * j4 + 2]) + b.z, f3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
             if (p.addend != nullptr) {
-              const uint4& a4 = add[j >> 2];
-              const uint32_t aw = (j & 3) == 0 ? a4.x : (j & 3) == 1 ? a4.y : (j & 3) == 2 ? a4.z : a4.w;
-              f0 += bf16_lo(aw); f1 += bf16_hi(aw);
+              const uint4& a4 = add[j4 >> 1];
+              const uint32_t aw0 = (j4 & 1) ? a4.z : a4.x, aw1 = (j4 & 1) ? a4.w : a4.y;
+              f0 += bf16_lo(aw0); f1 += bf16_hi(aw0); f2 += bf16_lo(aw1); f3 += bf16_hi(aw1);
             }
-            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-            packed[j] = pack_bf16x2(f0, f1);
+            packed[2 * j4] = pack_bf16x2(f0, f1);
+            packed[2 * j4 + 1] = pack_bf16x2(f2, f3);
+          }
+          if (p.relu) {     // rectify after rounding: max(x, 0) commutes with the bf16 rounding
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[j] = bf16x2_max(packed[j], 0u);
           }
           // four 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
 #pragma unroll
@@ -307,14 +332,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               tma_store_commit();
             }
           } else {
+            if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 8);
             // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
             // staged tile never goes to HBM.  One thread per (pooled pixel, 8 channels): TH, TW and the
             // tile origin are even, so every 2x2 window lies inside the box.
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 9);
             const int et = threadIdx.x - 128;
             const int pp = et >> 3, cgp = et & 7;
             const int tw2 = p.TW >> 1;
-            const int ph_l = pp / tw2, pw_l = pp - ph_l * tw2;
+            int pw_l = pp;
+            const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
             const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
             const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
             if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
@@ -329,16 +357,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               uint32_t bits = 0, outw[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                float lo[4], hi[4];
+                outw[k] = bf16x2_max(bf16x2_max(w[0][k], w[1][k]), bf16x2_max(w[2][k], w[3][k]));
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { lo[e] = bf16_lo(w[e][k]); hi[e] = bf16_hi(w[e][k]); }
-                const float mlo = fmaxf(fmaxf(lo[0], lo[1]), fmaxf(lo[2], lo[3]));
-                const float mhi = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3]));
-                uint32_t nlo = 0, nhi = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { nlo |= (lo[e] == mlo ? 1u : 0u) << e; nhi |= (hi[e] == mhi ? 1u : 0u) << e; }
-                bits |= (nlo << (8 * k)) | (nhi << (8 * k + 4));
-                outw[k] = pack_bf16x2(mlo, mhi);
+                for (int e = 0; e < 4; ++e) bits |= tie_bits(bf16x2_eq_mask(w[e][k], outw[k]), k, e);
               }
               const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
               const int cch = n0 + chunk * 64 + cgp * 8;
@@ -346,6 +367,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
             }
           }
+          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 10);
           if (p.n_stage_buf > 1) store_buf ^= 1;
         }
       } else {
@@ -358,8 +380,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         mbar_arrive(tmem_empty_bar(as));
         const int cbase = n0 + half * 8;
         float f[8];
+        {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + 1);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+        }
         if (p.addend != nullptr && valid) {
           const uint4 a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
           const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
@@ -531,8 +558,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 // descriptor may start at any row: the swizzle is a function of the absolute smem address and the
 // descriptor's base_offset stays 0 (tools/experiments/umma_shift_test.cu).  Accumulator row m is then
 // box pixel (m / pitch, m % pitch); the S-1 rows at the end of each line are junk and are dropped by
-// the epilogue.  Activations (ring of n_a halo tiles) and weights (ring of n_b stages of g_b taps)
-// flow through two independent mbarrier rings.
+// the epilogue.  The layer's whole filter bank (9 * n_cblk blocks, Cout == BN) is loaded once and stays
+// resident in smem; only halo tiles stream, through a ring of n_a buffers, so several tiles are in
+// flight and the TMA latency of these short-K layers is hidden.  Layers whose filter bank does not fit
+// (or whose maps are so small that the halo pitch wastes accumulator rows) use the per-tap kernel.
 // ---------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
@@ -542,16 +571,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if ((smem_u32(smem_raw) & 1023u) != 0u) mbar_timeout(p.diag, 9, 0);
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
-  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.g_b) * Cfg::kBBlockBytes;
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
-  const uint32_t b_bytes_total = p.b_resident ? static_cast<uint32_t>(p.R * p.S * (p.n_cblk0 + p.n_cblk1)) * Cfg::kBBlockBytes
-                                              : static_cast<uint32_t>(p.n_b) * b_stage_bytes;
+  const uint32_t b_bytes_total = static_cast<uint32_t>(9 * (p.n_cblk0 + p.n_cblk1)) * Cfg::kBBlockBytes;   // resident filter bank
   const uint32_t smem_stage_out = b_ring + b_bytes_total;
   const uint32_t bars = smem_stage_out + (Cfg::kTmaStore ? static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes : 0u);
   auto a_full = [&](int i) { return bars + 8u * i; };
   auto a_empty = [&](int i) { return bars + 8u * (4 + i); };
-  auto b_full = [&](int i) { return bars + 8u * (8 + i); };
-  auto b_empty = [&](int i) { return bars + 8u * (16 + i); };
   auto tmem_full_bar = [&](int i) { return bars + 8u * (24 + i); };
   auto tmem_empty_bar = [&](int i) { return bars + 8u * (26 + i); };
   const uint32_t tmem_slot = bars + 8u * 28;
@@ -569,7 +594,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < p.n_b; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }
     fence_barrier_init();
   }
@@ -583,120 +607,82 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int n_cblk = p.n_cblk0 + p.n_cblk1;
-  const int taps = p.R * p.S;
-  const int n_groups = (taps + p.g_b - 1) / p.g_b;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
-      int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
-      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + p.R - 1) * p.pitch) * 128u;
-      auto issue_a = [&](int t, int cb) {       // one halo tile: (TH+R-1) x pitch pixels of a 64-channel block
+      // the filter bank: loaded once, stays resident (Cout == BN, all 9 * n_cblk blocks fit)
+      const int n_blocks = 9 * n_cblk;
+      mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
+      for (int i = 0; i < n_blocks; ++i)
+        tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * kBlockK, 0);
+      // Halo tiles stream through two sub-rings of n_a/2 buffers: even tiles -> ring 0 (consumed by MMA
+      // warp 1), odd tiles -> ring 1 (warp 3), so every mbarrier has exactly one waiter walking its
+      // phases in order (parity waits cannot tell phase k from phase k+2).
+      const int n_half = p.n_a >> 1;
+      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.pitch) * 128u;
+      int iter = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
         const TileCoord tc = decode_tile(p, t);
-        mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
-        mbar_arrive_expect_tx(a_full(ia), a_bytes);
         const int h_base = tc.th * p.TH + p.in_off_h, w_base = tc.tw * p.TW + p.in_off_w;
-        if (cb < p.n_cblk0)
-          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src0, a_full(ia), cb * kBlockK, w_base, h_base, tc.n);
-        else
-          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src1, a_full(ia), (cb - p.n_cblk0) * kBlockK, w_base, h_base, tc.n);
-        if (++ia == p.n_a) { ia = 0; pa ^= 1u; }
-      };
-      if (p.b_resident) {
-        // Cout == BN and the whole filter bank fits: load it once, then only halo tiles stream (the
-        // A ring then holds several tiles, which hides the TMA latency of these short-K layers)
-        const int n_blocks = taps * n_cblk;
-        if (blockIdx.x < p.num_tiles) {
-          mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
-          for (int i = 0; i < n_blocks; ++i)
-            tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * kBlockK, 0);
-        }
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
-          for (int cb = 0; cb < n_cblk; ++cb) issue_a(t, cb);
-      } else {
-        // streamed weights: the NEXT halo tile is requested before this step's weight stages, so its
-        // latency overlaps this step's MMAs
-        int t = blockIdx.x, cb = 0;
-        bool have = t < p.num_tiles;
-        if (have) issue_a(t, cb);
-        while (have) {
-          int t2 = t, cb2 = cb + 1;
-          if (cb2 == n_cblk) { cb2 = 0; t2 += gridDim.x; }
-          const bool have2 = t2 < p.num_tiles;
-          if (have2) issue_a(t2, cb2);
-          const int nt = decode_tile(p, t).nt;
-          for (int grp = 0; grp < n_groups; ++grp) {
-            const int tap0 = grp * p.g_b;
-            const int g_n = (taps - tap0) < p.g_b ? (taps - tap0) : p.g_b;
-            mbar_wait(b_empty(ib), pb ^ 1u, p.diag, 6, ib);
-            mbar_arrive_expect_tx(b_full(ib), static_cast<uint32_t>(g_n) * Cfg::kBBlockBytes);
-            for (int g = 0; g < g_n; ++g)
-              tma_load_2d(b_ring + ib * b_stage_bytes + g * Cfg::kBBlockBytes, &p.tm_w, b_full(ib),
-                          ((tap0 + g) * n_cblk + cb) * kBlockK, nt * BN);
-            if (++ib == p.n_b) { ib = 0; pb ^= 1u; }
-          }
-          t = t2; cb = cb2; have = have2;
+        for (int cb = 0; cb < n_cblk; ++cb) {
+          const int lstep = (iter >> 1) * n_cblk + cb;
+          const int ia = (iter & 1) * n_half + lstep % n_half;
+          const uint32_t pa = (lstep / n_half) & 1u;
+          mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
+          mbar_arrive_expect_tx(a_full(ia), a_bytes);
+          if (cb < p.n_cblk0)
+            tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src0, a_full(ia), cb * kBlockK, w_base, h_base, tc.n);
+          else
+            tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src1, a_full(ia), (cb - p.n_cblk0) * kBlockK, w_base, h_base, tc.n);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (ping-pong) =====================
+    // Two warps alternate tiles: warp 1 owns accumulator stage 0 (even tiles), warp 3 stage 1 (odd
+    // tiles).  The barrier waits of one tile (~100+ cycles each even when already complete) then
+    // overlap the other warp's MMAs instead of idling the tensor pipe; the pipe executes both
+    // warps' MMAs in arrival order on independent accumulators.
     constexpr uint32_t idesc = make_instr_desc<BN>();
-    int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
-    int iter = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
-      const int as = iter & 1;
+    const int as = warp == 1 ? 0 : 1;
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+    const uint32_t pitch8 = static_cast<uint32_t>(p.pitch) * 8u;
+    const uint32_t b_tap = static_cast<uint32_t>(n_cblk) * (Cfg::kBBlockBytes >> 4);
+    const int n_half = p.n_a >> 1;
+    bool first = true;
+    for (int iter = as; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
       const uint32_t aphase = (iter >> 1) & 1u;
+      if (lane == 0) IISEG_STAMP(iter, 0);
       mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      if (lane == 0) IISEG_STAMP(iter, 1);
       for (int cb = 0; cb < n_cblk; ++cb) {
+        const int lstep = (iter >> 1) * n_cblk + cb;    // this warp's own sub-ring (see the producer)
+        const int ia = as * n_half + lstep % n_half;
+        const uint32_t pa = (lstep / n_half) & 1u;
         mbar_wait(a_full(ia), pa, p.diag, 7, ia);
-        const uint32_t a_tile = a_ring + ia * p.a_blk_bytes;
-        if (p.b_resident) {
-          if (iter == 0 && cb == 0) mbar_wait(b_res_bar, 0, p.diag, 10, 0);
-          tcgen05_fence_after();
-          if (elect_one_sync()) {
-            for (int tap = 0; tap < taps; ++tap) {
-              const int r = tap / p.S, s = tap - r * p.S;
-              const uint64_t a_desc = make_smem_desc(a_tile + static_cast<uint32_t>(r * p.pitch + s) * 128u);
-              const uint64_t b_desc = make_smem_desc(b_ring + static_cast<uint32_t>(tap * n_cblk + cb) * Cfg::kBBlockBytes);
+        if (first) { mbar_wait(b_res_bar, 0, p.diag, 10, 0); first = false; }
+        tcgen05_fence_after();
+        if (lane == 0 && cb == 0) IISEG_STAMP(iter, 2);
+        if (elect_one_sync()) {
+          // 3x3 taps fully unrolled: tap (r,s) = the halo tile advanced by (r*pitch + s) rows of 128 B,
+          // i.e. +8*(r*pitch + s) in the descriptor's (address >> 4) field.  A SWIZZLE_128B descriptor
+          // may start on any row (base_offset stays 0): the swizzle is a function of the smem address.
+          const uint64_t a0 = make_smem_desc(a_ring + ia * p.a_blk_bytes);
+          const uint64_t b0 = make_smem_desc(b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes);
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(a_empty(ia));
-            if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));
-          }
-          __syncwarp();
-        } else {
-          for (int grp = 0; grp < n_groups; ++grp) {
-            const int tap0 = grp * p.g_b;
-            const int g_n = (taps - tap0) < p.g_b ? (taps - tap0) : p.g_b;
-            mbar_wait(b_full(ib), pb, p.diag, 8, ib);
-            tcgen05_fence_after();
-            if (elect_one_sync()) {
-              for (int g = 0; g < g_n; ++g) {
-                const int tap = tap0 + g;
-                const int r = tap / p.S, s = tap - r * p.S;
-                // tap (r,s): the same halo tile, start advanced by (r*pitch + s) rows of 128 bytes
-                const uint64_t a_desc = make_smem_desc(a_tile + static_cast<uint32_t>(r * p.pitch + s) * 128u);
-                const uint64_t b_desc = make_smem_desc(b_ring + ib * b_stage_bytes + g * Cfg::kBBlockBytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t a_desc = a0 + (tap / 3) * pitch8 + (tap % 3) * 8u;
+            const uint64_t b_desc = b0 + tap * b_tap;
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                  umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              }
-              umma_commit(b_empty(ib));                                       // weights slot free when the MMAs retire
-              if (grp == n_groups - 1) {
-                umma_commit(a_empty(ia));                                     // all taps of this halo tile issued
-                if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));         // accumulator ready
-              }
-            }
-            __syncwarp();
-            if (++ib == p.n_b) { ib = 0; pb ^= 1u; }
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
           }
+          umma_commit(a_empty(ia));                                     // halo tile consumed
+          if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));         // accumulator ready
         }
-        if (++ia == p.n_a) { ia = 0; pa ^= 1u; }
+        __syncwarp();
+        if (lane == 0 && cb == n_cblk - 1) IISEG_STAMP(iter, 3);
       }
     }
   } else if (warp >= 4) {
@@ -830,6 +816,11 @@ static int launch_conv(const ConvParams& p, cudaStream_t stream) {
 
 }  // namespace iiseg
 
+extern "C" int iiseg_debug_read_timeline(long long* out, int n) {
+  if (n > 32 * 16) n = 32 * 16;
+  return cudaMemcpyFromSymbol(out, iiseg::g_timeline, n * sizeof(long long)) == cudaSuccess ? n : -1;
+}
+
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
@@ -883,7 +874,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       if (BN >= 64 && total - b_all - 2 * kStagingBytes < 3 * p.a_blk_bytes) p.n_stage_buf = 1;
       const int staging = p.n_stage_buf * kStagingBytes;
       p.n_a = (total - b_all - staging) / p.a_blk_bytes;
-      if (p.n_a > 4) p.n_a = 4;
+      p.n_a = p.n_a >= 4 ? 4 : (p.n_a >= 2 ? 2 : 0);      // two sub-rings (one per MMA warp)
       if (p.n_a < 2) halo = false;      // filter bank too large to stay resident: per-tap kernel
       box_h = p.TH + d->R - 1; box_w = p.pitch;
       smem_halo = p.n_a * p.a_blk_bytes + b_all + staging + 256;
@@ -922,6 +913,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   else { p.PH = p.pwin_h; p.PW = p.pwin_w; p.p_h0 = 0; p.p_w0 = 0; }
   p.n_ntiles = d->Cout / BN;
   p.num_tiles = d->N * p.tiles_h * p.tiles_w * p.n_ntiles;
+  IISEG_CHECK(p.num_tiles < (1 << 21), "conv: too many tiles (%d)", p.num_tiles);
+  p.inv_tw2 = p.TW >= 2 ? 1.0f / (p.TW >> 1) : 1.0f;
+  p.inv_ntiles = 1.0f / p.n_ntiles; p.inv_tiles_w = 1.0f / p.tiles_w; p.inv_tiles_h = 1.0f / p.tiles_h;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.relu = d->relu; p.out_f32 = d->out_f32;

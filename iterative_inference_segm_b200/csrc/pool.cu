@@ -12,11 +12,6 @@
 
 namespace iiseg {
 
-__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
-}
-
 __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restrict__ x, uint4* __restrict__ pooled,
                                                             uint32_t* __restrict__ mask, int H, int W, int C8,
                                                             int H2, int W2, long long total) {
@@ -31,19 +26,16 @@ __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restr
     const long long row1 = row0 + (long long)W * C8;
     const uint4 v00 = ldg_nc_v4(x + row0), v01 = ldg_nc_v4(x + row0 + C8);
     const uint4 v10 = ldg_nc_v4(x + row1), v11 = ldg_nc_v4(x + row1 + C8);
-    float a[8], b[8], c[8], d[8];
-    unpack8(v00, a); unpack8(v01, b); unpack8(v10, c); unpack8(v11, d);
-    float mx[8];
-    uint32_t bits = 0;
+    const uint32_t wa[4] = {v00.x, v00.y, v00.z, v00.w}, wb[4] = {v01.x, v01.y, v01.z, v01.w};
+    const uint32_t wc[4] = {v10.x, v10.y, v10.z, v10.w}, wd[4] = {v11.x, v11.y, v11.z, v11.w};
+    uint32_t mx[4], bits = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      mx[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
-      const uint32_t nib = (a[k] == mx[k] ? 1u : 0u) | (b[k] == mx[k] ? 2u : 0u) |
-                           (c[k] == mx[k] ? 4u : 0u) | (d[k] == mx[k] ? 8u : 0u);
-      bits |= nib << (4 * k);
+    for (int k = 0; k < 4; ++k) {
+      mx[k] = bf16x2_max(bf16x2_max(wa[k], wb[k]), bf16x2_max(wc[k], wd[k]));
+      bits |= tie_bits(bf16x2_eq_mask(wa[k], mx[k]), k, 0) | tie_bits(bf16x2_eq_mask(wb[k], mx[k]), k, 1) |
+              tie_bits(bf16x2_eq_mask(wc[k], mx[k]), k, 2) | tie_bits(bf16x2_eq_mask(wd[k], mx[k]), k, 3);
     }
-    stg_v4(pooled + i, make_uint4(pack_bf16x2(mx[0], mx[1]), pack_bf16x2(mx[2], mx[3]),
-                                  pack_bf16x2(mx[4], mx[5]), pack_bf16x2(mx[6], mx[7])));
+    stg_v4(pooled + i, make_uint4(mx[0], mx[1], mx[2], mx[3]));
     if (mask != nullptr) mask[i] = bits;
   }
 }
@@ -85,11 +77,7 @@ __global__ void __launch_bounds__(256) unpool2_mask_kernel(const UnpoolParams p)
       const int pos = ((fh & 1) << 1) | dx;
       uint32_t r[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t lo = (bits >> (4 * (2 * k) + pos)) & 1u;
-        const uint32_t hi = (bits >> (4 * (2 * k + 1) + pos)) & 1u;
-        r[k] = w[k] & ((lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u));
-      }
+      for (int k = 0; k < 4; ++k) r[k] = w[k] & tie_select(bits, k, pos);
       stg_v4(p.out + ((n * p.OH + oh) * p.OW + ow) * p.C8 + cg, make_uint4(r[0], r[1], r[2], r[3]));
     }
   }

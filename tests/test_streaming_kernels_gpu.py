@@ -14,15 +14,15 @@ def _nhwc(x):
 
 
 def _mask_to_dense(mask, C):
-    """[N,H2,W2,C/8] nibble words -> [N,C,2*H2,2*W2] 0/1 (bit 2*dy+dx)."""
+    """[N,H2,W2,C/8] tie-mask words -> [N,C,2*H2,2*W2] 0/1; channel j of a group, position pos = 2*dy+dx,
+    sits at bit 16*(j&1) + 4*(j>>1) + pos (include/iiseg.h)."""
     N, H2, W2, C8 = mask.shape
     m = mask.cpu().numpy().astype(np.uint32)
     out = np.zeros((N, C, 2 * H2, 2 * W2), np.float32)
-    for k in range(8):
-        nib = (m >> (4 * k)) & 0xF
+    for j in range(8):
         for pos in range(4):
-            bit = ((nib >> pos) & 1).astype(np.float32)     # [N,H2,W2,C8]
-            out[:, k::8, (pos >> 1)::2, (pos & 1)::2] = bit.transpose(0, 3, 1, 2)
+            bit = ((m >> (16 * (j & 1) + 4 * (j >> 1) + pos)) & 1).astype(np.float32)     # [N,H2,W2,C8]
+            out[:, j::8, (pos >> 1)::2, (pos & 1)::2] = bit.transpose(0, 3, 1, 2)
     return out
 
 

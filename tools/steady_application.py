@@ -1,0 +1,23 @@
+"""Profiling target: one full DAE application (fills borders) + 2 steady-state applications, eager."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import weights  # noqa: E402
+
+def main(B=10, H=360, W=480):
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200 import _kernels as K
+    pd = weights.synthetic_dae_params(11, 512, seed=1, out_gain=0.1)
+    dae = buildDAE([None], None, 11, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0,
+                   n_filters=64, additional_pool=2, skip=True, unpool_type='trackind', params=pd)
+    net = dae.net
+    hs = net.h_spatial(H, W)
+    h = torch.relu(torch.randn(B, hs[0], hs[1], 512, device='cuda')).to(torch.bfloat16)
+    y = K.pack_nchw(torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1), net.y_cpad)
+    net.logits(h, y, full_down=True)
+    for _ in range(2):
+        net.logits(h, y, full_down=False)
+    torch.cuda.synchronize()
+    print('ok')
+
+if __name__ == '__main__':
+    main()
