@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define IISEG_ABI_VERSION 1
+#define IISEG_ABI_VERSION 2
+#define IISEG_MAX_SRC 6
 
 /* ---- library ----------------------------------------------------------- */
 int iiseg_abi_version(void);
@@ -44,12 +45,16 @@ int iiseg_debug_read_timeline(long long* out, int n);
 int64_t iiseg_launch_count(void);
 
 /* ---- layout conversion at the boundary ---------------------------------- */
-/* NCHW fp32 [N,C,H,W] -> NHWC bf16 [N,H,W,Cpad], channels >= C zero-filled. */
+/* NCHW fp32 [N,C,H,W] -> NHWC bf16 [N,H,W,Cpad], channels >= C zero-filled.
+ * split = 1: dst is [N,H,W,2*Cpad], the (hi | lo) bf16 pair of each fp32 value
+ * (hi = bf16(x) in [0,Cpad), lo = bf16(x - hi) in [Cpad,2*Cpad)): the activation
+ * format of the fp32-accurate conv variant (iiseg_conv_desc.split). */
 int iiseg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C,
-                                     int H, int W, int Cpad, void* stream);
-/* NHWC bf16 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W] (first C channels). */
+                                     int H, int W, int Cpad, int split, void* stream);
+/* NHWC bf16 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W] (first C channels); split = 1:
+ * src is [N,H,W,2*Cpad] and dst = hi + lo. */
 int iiseg_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C,
-                                       int H, int W, int Cpad, void* stream);
+                                       int H, int W, int Cpad, int split, void* stream);
 /* NHWC fp32 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W]. */
 int iiseg_unpack_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C,
                                       int H, int W, int Cpad, void* stream);
@@ -63,11 +68,15 @@ int iiseg_unpack_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C
  * second source (ConcatLayer((h, pool4)), models/model_helpers.py:93-94) done
  * in the loader: the K loop walks src0's channels, then src1's. */
 typedef struct iiseg_conv_desc {
-  const void* src0;   /* NHWC bf16 [N,H,W,C0]; C0 multiple of 64            */
-  const void* src1;   /* NHWC bf16 [N,H,W,C1] or NULL; C1 multiple of 64    */
+  /* Up to IISEG_MAX_SRC activation sources concatenated along channels in the loader, in this order
+   * (source i supplies C[i] channels; unused entries are NULL / 0 and sources are packed from
+   * index 0).  Each is a view of an NHWC bf16 tensor [N,H,W,Cs[i]]: the first C[i] channels from
+   * the given pointer, Cs[i] channels per pixel in memory (0 = dense, Cs = C).  C[i] % 64 == 0. */
+  const void* src[IISEG_MAX_SRC];
+  int C[IISEG_MAX_SRC];
+  int Cs[IISEG_MAX_SRC];
   int N, H, W;        /* input extent                                       */
-  int C0, C1;
-  const void* weight; /* bf16 [Cout][R*S][C0+C1] (K-major GEMM B operand)   */
+  const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
   int Cout;           /* padded: 16, or a multiple of 64                    */
   int R, S, pad;      /* filter extent and symmetric zero padding           */
@@ -90,6 +99,11 @@ typedef struct iiseg_conv_desc {
    * pool_H == 0: they are dense [N,OH/2,OW/2,..].                                            */
   int pool_H, pool_W;
   int relu;           /* 1: rectify (Lasagne default), 0: linear            */
+  /* split = 1 (fp32-accurate variant): out / addend / pooled carry 2*Cout channels per pixel, the
+   * bf16 pair hi = bf16(x) in [0,Cout) and lo = bf16(x - hi) in [Cout,2*Cout) of the fp32 result;
+   * pool and tie mask compare hi+lo.  The caller feeds (hi | lo | hi) activation sources against
+   * (W_hi | W_hi | W_lo) weights, so the GEMM accumulates hi*hi + lo*hi + hi*lo in fp32.        */
+  int split;
   int out_f32;        /* 1: fp32 output (only Cout == 16)                   */
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
@@ -110,10 +124,12 @@ int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N
 /* Windowed form: only the output window [o_h0,o_h0+OH) x [o_w0,o_w0+OW) of the HxW map is
  * produced (dense [N,OH,OW,C]); `u` is a dense [N,UH,UW,C] window of the pooled map whose
  * element (0,0) is pooled position (u_h0,u_w0).  The expanding path only ever needs the
- * dependency cone of the final centre crop (CroppingLayer, models/fcn_up.py:106-113). */
+ * dependency cone of the final centre crop (CroppingLayer, models/fcn_up.py:106-113).
+ * split = 1: `u` and `out` carry the (hi | lo) bf16 pair of an fp32 map, 2*C channels per pixel
+ * (see iiseg_conv_desc.split); the mask still has C channels and gates both halves. */
 int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask, void* out, int N,
                                   int H, int W, int C, int UH, int UW, int u_h0, int u_w0,
-                                  int OH, int OW, int o_h0, int o_w0, void* stream);
+                                  int OH, int OW, int o_h0, int o_w0, int split, void* stream);
 
 /* ---- transposed convolution: lasagne Deconv2DLayer ----------------------
  * models/fcn8.py:90-91,100-101,109-110 (crop='valid', flip_filters=False,
@@ -144,14 +160,15 @@ int iiseg_deconv2d_fwd(const iiseg_deconv_desc* d, void* stream);
  *   (NCHW fp32) when p_out != NULL.
  * iiseg_norm_finalize: norm[n] = sum(partials)/(H*W) in fixed order;
  *   n_exec[n] += 1; if norm[n] < eps: active[n] = 0 (the `break`,
- *   iterative_inference.py:275-277).  Inactive images are untouched. */
+ *   iterative_inference.py:275-277).  Inactive images are untouched.
+ * split = 1: y_bf16 is [N,H,W,2*Cpad], the (hi | lo) bf16 pair of y (fp32-accurate variant). */
 int iiseg_update_blocks(int H, int W);
 int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, int N, int C,
-                       int H, int W, int Cpad, void* stream);
+                       int H, int W, int Cpad, int split, void* stream);
 int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
                          float* p_out, const int32_t* active,
                          float* norm_partial, int N, int C, int H, int W,
-                         int Cpad, float step, void* stream);
+                         int Cpad, float step, int split, void* stream);
 /* de_fn (iterative_inference.py:203-204): grad = y - softmax(logits), NCHW fp32. */
 int iiseg_softmax_grad(const float* logits, const float* y, float* grad, int N, int C,
                        int H, int W, void* stream);

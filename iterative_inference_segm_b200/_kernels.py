@@ -42,21 +42,26 @@ def pad_channels(c, conv_input=True):
 
 
 # ---- layout ---------------------------------------------------------------
-def pack_nchw(src, cpad, out=None):
+def pack_nchw(src, cpad, out=None, split=False):
+    """NCHW fp32 -> NHWC bf16 [N,H,W,cpad]; split: [N,H,W,2*cpad] = the (hi | lo) bf16 pair."""
     _chk(src, F32, 'src')
     N, Cc, H, W = src.shape
+    cs = 2 * cpad if split else cpad
     if out is None:
-        out = torch.empty((N, H, W, cpad), dtype=BF16, device=src.device)
-    _lib.call('iiseg_pack_nchw_f32_to_nhwc_bf16', _ptr(src), _ptr(out), N, Cc, H, W, cpad, _stream())
+        out = torch.empty((N, H, W, cs), dtype=BF16, device=src.device)
+    assert tuple(out.shape) == (N, H, W, cs)
+    _lib.call('iiseg_pack_nchw_f32_to_nhwc_bf16', _ptr(src), _ptr(out), N, Cc, H, W, cpad, int(split), _stream())
     return out
 
 
-def unpack_nhwc(src, c, out=None):
+def unpack_nhwc(src, c, out=None, split=False):
     N, H, W, cpad = src.shape
+    if split:
+        cpad //= 2
     if out is None:
         out = torch.empty((N, c, H, W), dtype=F32, device=src.device)
     if src.dtype == BF16:
-        _lib.call('iiseg_unpack_nhwc_bf16_to_nchw_f32', _ptr(src), _ptr(out), N, c, H, W, cpad, _stream())
+        _lib.call('iiseg_unpack_nhwc_bf16_to_nchw_f32', _ptr(src), _ptr(out), N, c, H, W, cpad, int(split), _stream())
     else:
         _chk(src, F32, 'src')
         _lib.call('iiseg_unpack_nhwc_f32_to_nchw_f32', _ptr(src), _ptr(out), N, c, H, W, cpad, _stream())
@@ -69,9 +74,15 @@ def conv_out_size(H, W, R, S, pad):
 
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
-           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None):
+           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
-    window = (oh0, ow0, OH, OW) selects the output window (default: all)."""
+    window = (oh0, ow0, OH, OW) selects the output window (default: all).
+
+    split=True is the fp32-accurate variant: every activation tensor (src0, src1, addend, out,
+    pooled) carries the (hi | lo) bf16 pair of an fp32 map, 2*C channels per pixel, and `weight` is
+    packed by _packing.pack_conv(split=True) as [Cout, R*S*3*(C0+C1)] = per tap (W_hi | W_hi | W_lo):
+    the loader walks (hi, lo, hi) views of the sources, so the unchanged bf16 tensor-core loop
+    accumulates hi*hi + lo*hi + hi*lo in fp32."""
     _chk(src0, BF16, 'src0')
     _chk(weight, BF16, 'weight')
     _chk(bias, F32, 'bias')
@@ -82,14 +93,20 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         assert src1.shape[:3] == src0.shape[:3]
         C1 = src1.shape[3]
     Cout = weight.shape[0]
-    assert weight.shape[1] == R * S * (C0 + C1), (tuple(weight.shape), R, S, C0, C1)
+    cm = 2 if (split and not out_f32) else 1     # channel multiplier of out / pooled / addend tensors
+    if split:
+        C0 //= 2
+        C1 //= 2
+        assert weight.shape[1] == R * S * 3 * (C0 + C1), (tuple(weight.shape), R, S, C0, C1)
+    else:
+        assert weight.shape[1] == R * S * (C0 + C1), (tuple(weight.shape), R, S, C0, C1)
     fOH, fOW = conv_out_size(H, W, R, S, pad)
     oh0, ow0, OH, OW = window if window is not None else (0, 0, fOH, fOW)
     if pooled is not None:     # fused 2x2 max-pool (+ mask): the full-resolution output is never written
         _chk(pooled, BF16, 'pooled')
-        dense = tuple(pooled.shape) == (N, OH // 2, OW // 2, Cout)
+        dense = tuple(pooled.shape) == (N, OH // 2, OW // 2, cm * Cout)
         if not dense:   # a window of a larger pooled tensor: even origin, pooled rows [oh0/2, oh0/2 + OH/2)
-            assert pooled.shape[0] == N and pooled.shape[3] == Cout and oh0 % 2 == 0 and ow0 % 2 == 0
+            assert pooled.shape[0] == N and pooled.shape[3] == cm * Cout and oh0 % 2 == 0 and ow0 % 2 == 0
             assert oh0 // 2 + OH // 2 <= pooled.shape[1] and ow0 // 2 + OW // 2 <= pooled.shape[2]
         pool_hw = (0, 0) if dense else (pooled.shape[1], pooled.shape[2])
         if pool_mask is not None:
@@ -97,16 +114,15 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
             assert tuple(pool_mask.shape) == tuple(pooled.shape[:3]) + (Cout // 8,)
         assert out is None
     elif out is None:
-        out = torch.empty((N, OH, OW, Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
+        out = torch.empty((N, OH, OW, cm * Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
     else:
         _chk(out, F32 if out_f32 else BF16, 'out')
-        assert tuple(out.shape) == (N, OH, OW, Cout), (tuple(out.shape), (N, OH, OW, Cout))
+        assert tuple(out.shape) == (N, OH, OW, cm * Cout), (tuple(out.shape), (N, OH, OW, cm * Cout))
     if addend is not None:
         _chk(addend, BF16, 'addend')
-        assert addend.shape[0] == N and addend.shape[3] == Cout
+        assert addend.shape[0] == N and addend.shape[3] == cm * Cout
         assert addend_off[0] + OH <= addend.shape[1] and addend_off[1] + OW <= addend.shape[2]
-    d = _lib.ConvDesc(src0=src0.data_ptr(), src1=src1.data_ptr() if src1 is not None else None,
-                      N=N, H=H, W=W, C0=C0, C1=C1, weight=weight.data_ptr(), bias=bias.data_ptr(),
+    d = _lib.ConvDesc(N=N, H=H, W=W, weight=weight.data_ptr(), bias=bias.data_ptr(),
                       Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
                       out=out.data_ptr() if out is not None else None,
                       addend=addend.data_ptr() if addend is not None else None,
@@ -115,7 +131,18 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       pool_H=pool_hw[0] if pooled is not None else 0, pool_W=pool_hw[1] if pooled is not None else 0,
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1],
-                      relu=int(bool(relu)), out_f32=int(bool(out_f32)))
+                      relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    # the channel-concatenated source views, in K order: (pointer, channels, channels per pixel in memory)
+    srcs = [(src0, C0)] + ([(src1, C1)] if src1 is not None else [])
+    views = []
+    if split:
+        for half in (0, 1, 0):        # hi, lo, hi  against  W_hi, W_hi, W_lo
+            views += [(t.data_ptr() + 2 * half * c, c, 2 * c) for t, c in srcs]
+    else:
+        views = [(t.data_ptr(), c, 0) for t, c in srcs]
+    assert len(views) <= _lib.MAX_SRC
+    for i, (ptr, c, cs) in enumerate(views):
+        d.src[i], d.C[i], d.Cs[i] = ptr, c, cs
     _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
     return out if pooled is None else pooled
 
@@ -133,19 +160,20 @@ def maxpool2(x, with_mask, pooled=None, mask=None):
     return (pooled, mask) if with_mask else pooled
 
 
-def unpool2(u, mask, H, W, out=None, u_origin=(0, 0), window=None):
+def unpool2(u, mask, H, W, out=None, u_origin=(0, 0), window=None, split=False):
     """DePool2D into the HxW pre-pool map.  `u` is a dense window of the pooled map starting at pooled
     position `u_origin`; `window` = (h0, w0, OH, OW) restricts the output (default: the whole map)."""
     _chk(u, BF16, 'u')
     _chk(mask, torch.int32, 'mask')
-    N, UH, UW, Cc = u.shape
+    N, UH, UW, Cu = u.shape
+    Cc = Cu // 2 if split else Cu          # split: u / out carry (hi | lo) pairs, the mask has Cc channels
     assert tuple(mask.shape) == (N, H // 2, W // 2, Cc // 8), (tuple(mask.shape), H, W, Cc)
     h0, w0, OH, OW = window if window is not None else (0, 0, H, W)
     if out is None:
-        out = torch.empty((N, OH, OW, Cc), dtype=BF16, device=u.device)
-    assert tuple(out.shape) == (N, OH, OW, Cc)
+        out = torch.empty((N, OH, OW, Cu), dtype=BF16, device=u.device)
+    assert tuple(out.shape) == (N, OH, OW, Cu)
     _lib.call('iiseg_unpool2_mask_window_fwd', _ptr(u), _ptr(mask), _ptr(out), N, H, W, Cc, UH, UW,
-              u_origin[0], u_origin[1], OH, OW, h0, w0, _stream())
+              u_origin[0], u_origin[1], OH, OW, h0, w0, int(split), _stream())
     return out
 
 
@@ -177,24 +205,24 @@ def update_blocks(H, W):
     return _lib.load().iiseg_update_blocks(H, W)
 
 
-def softmax_nchw(logits, C_, p_out, y_bf16=None):
+def softmax_nchw(logits, C_, p_out, y_bf16=None, split=False):
     _chk(logits, F32, 'logits')
     N, H, W, c16 = logits.shape
     assert c16 == 16
     _chk(p_out, F32, 'p_out')
-    cpad = y_bf16.shape[3] if y_bf16 is not None else 0
-    _lib.call('iiseg_softmax_nchw', _ptr(logits), _ptr(p_out), _ptr(y_bf16), N, C_, H, W, cpad, _stream())
+    cpad = y_bf16.shape[3] // (2 if split else 1) if y_bf16 is not None else 0
+    _lib.call('iiseg_softmax_nchw', _ptr(logits), _ptr(p_out), _ptr(y_bf16), N, C_, H, W, cpad, int(split), _stream())
     return p_out
 
 
-def softmax_update(logits, y, y_bf16, active, norm_partial, step, p_out=None):
+def softmax_update(logits, y, y_bf16, active, norm_partial, step, p_out=None, split=False):
     _chk(logits, F32, 'logits')
     _chk(y, F32, 'y')
     N, C_, H, W = y.shape
     assert tuple(logits.shape) == (N, H, W, 16)
-    cpad = y_bf16.shape[3] if y_bf16 is not None else 0
+    cpad = y_bf16.shape[3] // (2 if split else 1) if y_bf16 is not None else 0
     _lib.call('iiseg_softmax_update', _ptr(logits), _ptr(y), _ptr(y_bf16), _ptr(p_out), _ptr(active),
-              _ptr(norm_partial), N, C_, H, W, cpad, C.c_float(step), _stream())
+              _ptr(norm_partial), N, C_, H, W, cpad, C.c_float(step), int(split), _stream())
 
 
 def softmax_grad(logits, y, grad):

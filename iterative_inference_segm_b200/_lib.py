@@ -14,19 +14,22 @@ class IisegError(RuntimeError):
     pass
 
 
+ABI_VERSION = 2      # IISEG_ABI_VERSION
+MAX_SRC = 6          # IISEG_MAX_SRC
+
+
 class ConvDesc(C.Structure):
     """struct iiseg_conv_desc (include/iiseg.h)."""
     _fields_ = [
-        ('src0', C.c_void_p), ('src1', C.c_void_p),
+        ('src', C.c_void_p * MAX_SRC), ('C', C.c_int * MAX_SRC), ('Cs', C.c_int * MAX_SRC),
         ('N', C.c_int), ('H', C.c_int), ('W', C.c_int),
-        ('C0', C.c_int), ('C1', C.c_int),
         ('weight', C.c_void_p), ('bias', C.c_void_p),
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('addend', C.c_void_p),
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int),
         ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
-        ('relu', C.c_int), ('out_f32', C.c_int),
+        ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int),
     ]
 
 
@@ -51,17 +54,17 @@ SIGNATURES = {
     'iiseg_read_diag': (_i, [_vp, _i]),
     'iiseg_launch_count': (C.c_int64, []),
     'iiseg_debug_read_timeline': (_i, [_vp, _i]),
-    'iiseg_pack_nchw_f32_to_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'iiseg_unpack_nhwc_bf16_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_pack_nchw_f32_to_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_unpack_nhwc_bf16_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_unpack_nhwc_f32_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'iiseg_conv2d_fwd': (_i, [C.POINTER(ConvDesc), _vp]),
     'iiseg_maxpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_unpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'iiseg_unpool2_mask_window_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_unpool2_mask_window_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_deconv2d_fwd': (_i, [C.POINTER(DeconvDesc), _vp]),
     'iiseg_update_blocks': (_i, [_i, _i]),
-    'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     'iiseg_softmax_grad': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -83,7 +86,7 @@ def load():
             fn = getattr(lib, name)   # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.iiseg_abi_version() != 1:
+        if lib.iiseg_abi_version() != ABI_VERSION:
             raise IisegError('libiiseg ABI version mismatch')
         _lib = lib
     return _lib

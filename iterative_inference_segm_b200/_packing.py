@@ -18,9 +18,11 @@ def _as_f32(a, device):
     return torch.as_tensor(np.asarray(a, dtype=np.float32), device=device)
 
 
-def pack_conv(W, b, splits, cout_pad, device):
+def pack_conv(W, b, splits, cout_pad, device, split=False):
     """W (Cout, sum(real), R, S), splits = [(real, padded), ...] per concatenated source.
-    Returns (bf16 [cout_pad, R*S*sum(padded)], fp32 bias [cout_pad])."""
+    Returns (bf16 [cout_pad, R*S*sum(padded)], fp32 bias [cout_pad]).
+    split=True (fp32-accurate variant): K per tap is (W_hi | W_hi | W_lo) with W_hi = bf16(W),
+    W_lo = bf16(W - W_hi), matching the (hi | lo | hi) activation views of _kernels.conv2d."""
     W = _as_f32(W, device)
     b = _as_f32(b, device)
     Cout, Cin, R, S = W.shape
@@ -31,7 +33,13 @@ def pack_conv(W, b, splits, cout_pad, device):
         blk[:Cout, :, :, :real] = W[:, c0:c0 + real].permute(0, 2, 3, 1)
         parts.append(blk)
         c0 += real
-    Wk = torch.cat(parts, dim=3).reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
+    Wf = torch.cat(parts, dim=3)
+    if split:
+        hi = Wf.to(torch.bfloat16)
+        lo = (Wf - hi.float()).to(torch.bfloat16)
+        Wk = torch.cat([hi, hi, lo], dim=3).reshape(cout_pad, -1).contiguous()
+    else:
+        Wk = Wf.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()
     bk = torch.zeros((cout_pad,), dtype=torch.float32, device=device)
     bk[:Cout] = b
     return Wk, bk

@@ -60,15 +60,16 @@ struct ConvCfg {
 };
 
 struct alignas(64) ConvParams {
-  CUtensorMap tm_src0;
-  CUtensorMap tm_src1;
+  CUtensorMap tm_src[IISEG_MAX_SRC];     // channel-concatenated activation sources (views of NHWC tensors)
   CUtensorMap tm_w;
   CUtensorMap tm_out;
   const float* bias;
   const __nv_bfloat16* addend;
   void* out;
   int32_t* diag;
-  int n_cblk0, n_cblk1;     // 64-channel blocks of src0 / src1
+  int n_cblk_src[IISEG_MAX_SRC];        // 64-channel blocks of each source
+  int n_cblk;               // their sum
+  int split;                // split-precision output: channels [0,Cout) = hi, [Cout,2Cout) = lo (bf16 pair of the fp32 value)
   int R, S;
   int in_off_h, in_off_w;   // input row of tap r for local output row o: o + in_off_h + r
   int TH, TW;
@@ -415,6 +416,147 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
     if (Cfg::kTmaStore && issuer && elect_one_sync()) tma_store_wait_read<0>();
 }
 
+// ---------------------------------------------------------------------------
+// Split-precision epilogue (fp32-accurate variant).  Every activation tensor carries the bf16 pair
+// (hi, lo) of an fp32 value, hi = bf16(x), lo = bf16(x - hi), as channel halves [0,C) | [C,2C); the
+// host concatenates (hi, lo, hi) activations against (W_hi, W_hi, W_lo) weights along K, so the
+// unchanged bf16 main loops accumulate hi*hi + lo*hi + hi*lo in fp32 (relative error ~2^-16).
+// Here the fp32 accumulator gets bias / skip-sum / ReLU in fp32, is split into the pair, and both
+// halves are staged (buffer 0 = hi, buffer 1 = lo) for two TMA stores, or max-pooled: pool and
+// tie mask compare the reconstructed fp32 values, as the reference does on float32 activations.
+// ---------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                                    uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
+  auto tmem_full_bar = [&](int i) { return tmem_full_bar0 + 8u * i; };
+  auto tmem_empty_bar = [&](int i) { return tmem_empty_bar0 + 8u * i; };
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int macc = q * 32 + lane;
+  const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+  const bool in_box = (hl < p.TH) && (wl < p.TW);
+  const int m = hl * p.TW + wl;
+  const bool issuer = (warp == 4);
+  const int cpp = 2 * p.Cout;               // channels per pixel of out / addend / pooled tensors
+  const uint32_t sb_hi = smem_stage_out, sb_lo = smem_stage_out + kStagingBytes;
+  int iter = 0;
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+    const TileCoord tc = decode_tile(p, t);
+    const int as = iter & 1;
+    const uint32_t aphase = (iter >> 1) & 1u;
+    const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+    mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
+    const int n0 = tc.nt * BN;
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 64; ++chunk) {
+      const int cbase = n0 + chunk * 64 + half * 32;
+      uint32_t v[32];
+      tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
+      tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
+      if (issuer && elect_one_sync()) tma_store_wait_read<0>();      // both staging buffers are reused every chunk
+      tmem_ld_wait();
+      if (chunk == BN / 64 - 1) {
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar(as));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
+      if (p.addend != nullptr && valid) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 ah = ldg_nc_v4(p.addend + apix * cpp + cbase + j * 8);
+          const uint4 al = ldg_nc_v4(p.addend + apix * cpp + p.Cout + cbase + j * 8);
+          const uint32_t hw[4] = {ah.x, ah.y, ah.z, ah.w}, lw[4] = {al.x, al.y, al.z, al.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            f[8 * j + 2 * k] += bf16_lo(hw[k]) + bf16_lo(lw[k]);
+            f[8 * j + 2 * k + 1] += bf16_hi(hw[k]) + bf16_hi(lw[k]);
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (in_box) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a = f[8 * cc + 2 * k], b = f[8 * cc + 2 * k + 1];
+            hi[k] = pack_bf16x2(a, b);
+            lo[k] = pack_bf16x2(a - bf16_lo(hi[k]), b - bf16_hi(hi[k]));
+          }
+          const uint32_t off = m * 128 + (((half * 4 + cc) ^ (m & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sb_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sb_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+      }
+      if (p.pooled == nullptr) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (issuer && elect_one_sync()) {
+          tma_store_4d(&p.tm_out, sb_hi, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          tma_store_4d(&p.tm_out, sb_lo, p.Cout + n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
+          tma_store_commit();
+        }
+      } else {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int et = threadIdx.x - 128;
+        const int pp = et >> 3, cgp = et & 7;
+        const int tw2 = p.TW >> 1;
+        int pw_l = pp;
+        const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
+        const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;
+        const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;
+        if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
+          const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
+          uint32_t wh[4][4], wlo[4][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int mm = m00 + (e >> 1) * p.TW + (e & 1);
+            const uint32_t off = mm * 128 + ((cgp ^ (mm & 7)) << 4);
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wh[e][0]), "=r"(wh[e][1]), "=r"(wh[e][2]), "=r"(wh[e][3]) : "r"(sb_hi + off));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wlo[e][0]), "=r"(wlo[e][1]), "=r"(wlo[e][2]), "=r"(wlo[e][3]) : "r"(sb_lo + off));
+          }
+          uint32_t bits = 0, oh_w[4], ol_w[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {        // the two channels packed in word k
+              float fv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                fv[e] = par ? bf16_hi(wh[e][k]) + bf16_hi(wlo[e][k]) : bf16_lo(wh[e][k]) + bf16_lo(wlo[e][k]);
+              const float mx = fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3]));
+              int win = 3;
+#pragma unroll
+              for (int e = 3; e >= 0; --e)
+                if (fv[e] == mx) { bits |= 1u << (16 * par + 4 * k + e); win = e; }
+              const uint32_t sh = par ? 0xFFFF0000u : 0x0000FFFFu;
+              if (par == 0) { oh_w[k] = wh[win][k] & sh; ol_w[k] = wlo[win][k] & sh; }
+              else { oh_w[k] |= wh[win][k] & sh; ol_w[k] |= wlo[win][k] & sh; }
+            }
+          }
+          const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
+          const int cch = n0 + chunk * 64 + cgp * 8;
+          stg_v4(p.pooled + ppix * cpp + cch, make_uint4(oh_w[0], oh_w[1], oh_w[2], oh_w[3]));
+          stg_v4(p.pooled + ppix * cpp + p.Cout + cch, make_uint4(ol_w[0], ol_w[1], ol_w[2], ol_w[3]));
+          if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+        }
+      }
+    }
+  }
+  if (issuer && elect_one_sync()) tma_store_wait_read<0>();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -439,8 +581,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tm_src0);
-    prefetch_tmap(&p.tm_src1);
+    for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
     prefetch_tmap(&p.tm_w);
     if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
   }
@@ -458,7 +599,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int n_cblk = p.n_cblk0 + p.n_cblk1;
+  const int n_cblk = p.n_cblk;
   const int num_k_blocks = p.R * p.S * n_cblk;
   const int num_groups = (num_k_blocks + G - 1) / G;      // pipeline stages consumed per tile
 
@@ -483,10 +624,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               if (g < g_n) {
-                if (cb < p.n_cblk0)
-                  tma_load_4d(stage_a(stage, g), &p.tm_src0, full_bar(stage), cb * kBlockK, w_base + s, h_base + r, tc.n);
-                else
-                  tma_load_4d(stage_a(stage, g), &p.tm_src1, full_bar(stage), (cb - p.n_cblk0) * kBlockK, w_base + s, h_base + r, tc.n);
+                int src = 0, cbl = cb;      // which source this channel block belongs to (concat in the loader)
+                while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
+                tma_load_4d(stage_a(stage, g), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
                 tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN);
                 ++kb;
                 if (++cb == n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
@@ -536,7 +676,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (Cfg::kTmaStore && p.split) conv_epilogue_split<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -572,7 +713,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
-  const uint32_t b_bytes_total = static_cast<uint32_t>(9 * (p.n_cblk0 + p.n_cblk1)) * Cfg::kBBlockBytes;   // resident filter bank
+  const uint32_t b_bytes_total = static_cast<uint32_t>(9 * p.n_cblk) * Cfg::kBBlockBytes;   // resident filter bank
   const uint32_t smem_stage_out = b_ring + b_bytes_total;
   const uint32_t bars = smem_stage_out + (Cfg::kTmaStore ? static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes : 0u);
   auto a_full = [&](int i) { return bars + 8u * i; };
@@ -586,8 +727,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tm_src0);
-    prefetch_tmap(&p.tm_src1);
+    for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
     prefetch_tmap(&p.tm_w);
     if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
   }
@@ -606,7 +746,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int n_cblk = p.n_cblk0 + p.n_cblk1;
+  const int n_cblk = p.n_cblk;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -631,10 +771,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
           const uint32_t pa = (lstep / n_half) & 1u;
           mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
           mbar_arrive_expect_tx(a_full(ia), a_bytes);
-          if (cb < p.n_cblk0)
-            tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src0, a_full(ia), cb * kBlockK, w_base, h_base, tc.n);
-          else
-            tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src1, a_full(ia), (cb - p.n_cblk0) * kBlockK, w_base, h_base, tc.n);
+          int src = 0, cbl = cb;
+          while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
+          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src[src], a_full(ia), cbl * kBlockK, w_base, h_base, tc.n);
         }
       }
     }
@@ -686,7 +825,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (Cfg::kTmaStore && p.split) conv_epilogue_split<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -717,11 +857,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 tensor seen as (C, W, H, N); box (64, TW, TH, 1); 128B swizzle; OOB reads give zeros.
-static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW) {
+static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW, int Cs = 0) {
+  if (Cs == 0) Cs = C;        // channels per pixel in memory (the view may cover only C of them)
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -824,10 +965,17 @@ extern "C" int iiseg_debug_read_timeline(long long* out, int n) {
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
-  IISEG_CHECK(d->src0 != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr), "conv: null tensor");
+  IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr), "conv: null tensor");
   IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
-  IISEG_CHECK(d->C0 > 0 && d->C0 % 64 == 0, "conv: C0=%d must be a positive multiple of 64", d->C0);
-  IISEG_CHECK(d->C1 >= 0 && d->C1 % 64 == 0 && (d->C1 == 0) == (d->src1 == nullptr), "conv: bad second source (C1=%d)", d->C1);
+  IISEG_CHECK(d->C[0] > 0 && d->C[0] % 64 == 0, "conv: C0=%d must be a positive multiple of 64", d->C[0]);
+  int Cin = 0;
+  for (int i = 0; i < IISEG_MAX_SRC; ++i) {
+    IISEG_CHECK(d->C[i] >= 0 && d->C[i] % 64 == 0 && (d->C[i] == 0) == (d->src[i] == nullptr), "conv: bad source %d (C=%d)", i, d->C[i]);
+    IISEG_CHECK(d->Cs[i] == 0 || (d->Cs[i] >= d->C[i] && d->Cs[i] % 8 == 0), "conv: bad channel stride of source %d", i);
+    IISEG_CHECK(i == 0 || d->C[i] == 0 || d->C[i - 1] > 0, "conv: sources must be packed from index 0");
+    Cin += d->C[i];
+  }
+  IISEG_CHECK(d->split == 0 || (d->out_f32 == 0 && d->Cout % 64 == 0), "conv: split output needs a bf16 output with Cout %% 64 == 0");
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->out_f32 == 0 || d->Cout == 16, "conv: fp32 output only for Cout == 16");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
@@ -853,8 +1001,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
   // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
   // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
-  const int n_cblk_all = (d->C0 + d->C1) / 64;
-  bool halo = env_halo && d->R == 3 && d->S == 3;
+  const int n_cblk_all = Cin / 64;
+  bool halo = env_halo && d->R == 3 && d->S == 3 && !d->split;
   int box_h = 0, box_w = 0;       // TMA box extent in pixels
   int smem_halo = 0;
   if (halo) {
@@ -886,24 +1034,27 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     p.n_stage_buf = 2;
     box_h = p.TH; box_w = p.TW;
   }
-  if (encode_nhwc(&p.tm_src0, d->src0, d->N, d->H, d->W, d->C0, box_h, box_w)) return -1;
-  if (d->src1 != nullptr) {
-    if (encode_nhwc(&p.tm_src1, d->src1, d->N, d->H, d->W, d->C1, box_h, box_w)) return -1;
-  } else {
-    p.tm_src1 = p.tm_src0;
+  for (int i = 0; i < IISEG_MAX_SRC; ++i) {
+    if (d->src[i] != nullptr) {
+      if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i])) return -1;
+    } else {
+      p.tm_src[i] = p.tm_src[0];
+    }
+    p.n_cblk_src[i] = d->C[i] / 64;
   }
-  const int K = d->R * d->S * (d->C0 + d->C1);
+  p.n_cblk = n_cblk_all;
+  p.split = d->split;
+  const int K = d->R * d->S * Cin;
   if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN)) return -1;
   if (BN >= 64 && !fuse_pool) {
-    if (encode_nhwc(&p.tm_out, d->out, d->N, d->OH, d->OW, d->Cout, p.TH, p.TW)) return -1;
+    if (encode_nhwc(&p.tm_out, d->out, d->N, d->OH, d->OW, d->split ? 2 * d->Cout : d->Cout, p.TH, p.TW)) return -1;
   } else {
-    p.tm_out = p.tm_src0;
+    p.tm_out = p.tm_src[0];
   }
   p.bias = d->bias;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
   p.diag = diag_device_ptr();
-  p.n_cblk0 = d->C0 / 64; p.n_cblk1 = d->C1 / 64;
   p.R = d->R; p.S = d->S;
   p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
   p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);

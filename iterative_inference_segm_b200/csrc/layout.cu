@@ -8,7 +8,7 @@
 namespace iiseg {
 
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C, int HW,
-                                                   int C8, long long total) {
+                                                   int C8, long long total, int split) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
@@ -21,21 +21,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
       const int c = cg * 8 + k;
       v[k] = c < C ? src[(n * C + c) * HW + pix] : 0.f;
     }
-    stg_v4(dst + (n * HW + pix) * C8 + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    const uint32_t hi[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+    if (!split) {
+      stg_v4(dst + (n * HW + pix) * C8 + cg, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+    } else {        // (hi | lo) bf16 pair of the fp32 value: hi = bf16(x), lo = bf16(x - hi)
+      uint32_t lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo[k] = pack_bf16x2(v[2 * k] - bf16_lo(hi[k]), v[2 * k + 1] - bf16_hi(hi[k]));
+      stg_v4(dst + (n * HW + pix) * 2 * C8 + cg, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+      stg_v4(dst + (n * HW + pix) * 2 * C8 + C8 + cg, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW,
-                                                     int Cpad, long long total) {
+                                                     int Cpad, long long total, int split) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
     const int pix = (int)(t % HW); t /= HW;
     const int c = (int)(t % C);
     const long long n = t / C;
-    dst[i] = (float)src[(n * HW + pix) * Cpad + c];
+    if (!split) dst[i] = (float)src[(n * HW + pix) * Cpad + c];
+    else dst[i] = (float)src[(n * HW + pix) * 2 * Cpad + c] + (float)src[(n * HW + pix) * 2 * Cpad + Cpad + c];
   }
 }
 
@@ -48,25 +57,25 @@ static int grid_for(long long total) {
 }  // namespace iiseg
 
 extern "C" int iiseg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cpad,
-                                                void* stream) {
+                                                int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(src && dst, "pack: null tensor");
   IISEG_CHECK(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && Cpad % 8 == 0, "pack: bad shape C=%d Cpad=%d", C, Cpad);
   const long long total = (long long)N * (Cpad / 8) * H * W;
   pack_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<uint4*>(dst), C, H * W, Cpad / 8, total);
+      src, reinterpret_cast<uint4*>(dst), C, H * W, Cpad / 8, total, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int iiseg_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cpad,
-                                                  void* stream) {
+                                                  int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(src && dst, "unpack: null tensor");
   IISEG_CHECK(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "unpack: bad shape");
   const long long total = (long long)N * C * H * W;
   unpack_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), dst, C, H * W, Cpad, total);
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, C, H * W, Cpad, total, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -78,7 +87,7 @@ extern "C" int iiseg_unpack_nhwc_f32_to_nchw_f32(const float* src, float* dst, i
   IISEG_CHECK(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "unpack: bad shape");
   const long long total = (long long)N * C * H * W;
   unpack_kernel<float><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, C, H * W, Cpad,
-                                                                                            total);
+                                                                                            total, 0);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restr
 // pixels in the trailing odd row / column of the HxW map (no pool window) are zero.
 struct UnpoolParams {
   const uint4* u; const uint32_t* mask; uint4* out;
-  int C8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN;
+  int C8, MC8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN;   // MC8: channel groups of the mask (C8, or C8/2 for split pairs)
   long long total;
 };
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) unpool2_mask_kernel(const UnpoolParams p)
     uint32_t bits = 0;
     if (ph < p.H2 && pw < p.W2) {
       val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.C8 + cg);
-      bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.C8 + cg);
+      bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.MC8 + (cg >= p.MC8 ? cg - p.MC8 : cg));
     }
     const uint32_t w[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
@@ -106,7 +106,7 @@ extern "C" int iiseg_maxpool2_mask_fwd(const void* x, void* pooled, uint32_t* ma
 
 extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask, void* out, int N, int H, int W, int C,
                                              int UH, int UW, int u_h0, int u_w0, int OH, int OW, int o_h0, int o_w0,
-                                             void* stream) {
+                                             int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(u && mask && out, "unpool: null tensor");
   IISEG_CHECK(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0, "unpool: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
@@ -123,7 +123,7 @@ extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask
               ph_lo, ph_hi, pw_lo, pw_hi);
   UnpoolParams p;
   p.u = reinterpret_cast<const uint4*>(u); p.mask = mask; p.out = reinterpret_cast<uint4*>(out);
-  p.C8 = C / 8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
+  p.MC8 = C / 8; p.C8 = split ? 2 * p.MC8 : p.MC8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
   p.OH = OH; p.OW = OW; p.o_h0 = o_h0; p.o_w0 = o_w0;
   p.PWN = (o_w0 + OW - 1) / 2 - o_w0 / 2 + 1;     // pooled columns the window touches (incl. a trailing odd one)
   p.total = (long long)N * OH * p.PWN * p.C8;
@@ -134,5 +134,5 @@ extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask
 
 extern "C" int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N, int H, int W, int C,
                                       void* stream) {
-  return iiseg_unpool2_mask_window_fwd(u, mask, out, N, H, W, C, H / 2, W / 2, 0, 0, H, W, 0, 0, stream);
+  return iiseg_unpool2_mask_window_fwd(u, mask, out, N, H, W, C, H / 2, W / 2, 0, 0, H, W, 0, 0, 0, stream);
 }

@@ -27,14 +27,27 @@ __device__ __forceinline__ void load_logits16(const float* p, float* l) {
 }
 
 // writes C probabilities (rest zero) as one bf16 NHWC row of Cpad channels
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* row, const float* v, int C, int Cpad) {
+// split: the row is the (hi | lo) bf16 pair, 2*Cpad channels (fp32-accurate conv variant)
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* row, const float* v, int C, int Cpad, int split) {
   float t[kMaxC];
 #pragma unroll
   for (int c = 0; c < kMaxC; ++c) t[c] = c < C ? v[c] : 0.f;
+  uint32_t hi[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hi[k] = pack_bf16x2(t[2 * k], t[2 * k + 1]);
   uint4* o = reinterpret_cast<uint4*>(row);
-  stg_v4(o, make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7])));
-  stg_v4(o + 1, make_uint4(pack_bf16x2(t[8], t[9]), pack_bf16x2(t[10], t[11]), pack_bf16x2(t[12], t[13]), pack_bf16x2(t[14], t[15])));
+  stg_v4(o, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  stg_v4(o + 1, make_uint4(hi[4], hi[5], hi[6], hi[7]));
   for (int j = 2; j < Cpad / 8; ++j) stg_v4(o + j, make_uint4(0, 0, 0, 0));
+  if (split) {
+    uint32_t lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lo[k] = pack_bf16x2(t[2 * k] - bf16_lo(hi[k]), t[2 * k + 1] - bf16_hi(hi[k]));
+    o += Cpad / 8;
+    stg_v4(o, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+    stg_v4(o + 1, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+    for (int j = 2; j < Cpad / 8; ++j) stg_v4(o + j, make_uint4(0, 0, 0, 0));
+  }
 }
 
 __device__ __forceinline__ void softmax_c(const float* l, float* p, int C) {
@@ -53,7 +66,7 @@ __device__ __forceinline__ void softmax_c(const float* l, float* p, int C) {
 __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     const float* __restrict__ logits, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
     float* __restrict__ p_out, const int32_t* __restrict__ active, float* __restrict__ norm_partial,
-    int C, int HW, int Cpad, float step, int do_update) {
+    int C, int HW, int Cpad, float step, int do_update, int split) {
   const int n = blockIdx.y;
   if (do_update && active != nullptr && active[n] == 0) return;   // frozen image
   const int pix = blockIdx.x * kUpdBlock + threadIdx.x;
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
         if (c < C) yb[(size_t)c * HW] = p[c];
       }
     }
-    if (y_bf16 != nullptr) store_row_bf16(y_bf16 + ((size_t)n * HW + pix) * Cpad, out, C, Cpad);
+    if (y_bf16 != nullptr) store_row_bf16(y_bf16 + ((size_t)n * HW + pix) * (split ? 2 * Cpad : Cpad), out, C, Cpad, split);
   }
   if (do_update == 2) return;
   if (do_update) {
@@ -138,28 +151,28 @@ __global__ void norm_finalize_kernel(const float* __restrict__ norm_partial, flo
 extern "C" int iiseg_update_blocks(int H, int W) { return (H * W + iiseg::kUpdBlock - 1) / iiseg::kUpdBlock; }
 
 extern "C" int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, int N, int C, int H, int W, int Cpad,
-                                  void* stream) {
+                                  int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(logits && p, "softmax: null tensor");
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax: bad shape");
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, 0);
+      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, 0, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int iiseg_softmax_update(const float* logits, float* y, void* y_bf16, float* p_out, const int32_t* active,
                                     float* norm_partial, int N, int C, int H, int W, int Cpad, float step,
-                                    void* stream) {
+                                    int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(logits && y && norm_partial, "softmax_update: null tensor");
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_update: bad shape");
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax_update: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, 1);
+      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, 1, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -171,7 +184,7 @@ extern "C" int iiseg_softmax_grad(const float* logits, const float* y, float* gr
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_grad: bad shape");
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 2);
+      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 2, 0);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

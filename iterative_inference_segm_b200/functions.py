@@ -44,7 +44,7 @@ def function_pred_fcn(fcn):
         for hd in fcn:
             t = out[hd.name]
             if t.dtype == torch.bfloat16:     # poolK features leave as the reference's NCHW float32
-                t = K.unpack_nhwc(t, hd.output_shape[1])
+                t = K.unpack_nhwc(t, hd.output_shape[1], split=net.split)
             res.append(_ret(t, as_np))
         return res
     return pred_fcn_fn
@@ -61,8 +61,8 @@ class _DaeCallable(object):
         net = self.net
         hc, _ = _to_cuda(h)
         yc, as_np = _to_cuda(y)
-        h_bf16 = K.pack_nchw(hc, net.h_pad)
-        y_bf16 = K.pack_nchw(yc, net.y_cpad)
+        h_bf16 = K.pack_nchw(hc, net.h_pad, split=net.split)
+        y_bf16 = K.pack_nchw(yc, net.y_cpad, split=net.split)
         logits = net.logits(h_bf16, y_bf16)
         out = torch.empty_like(yc)
         if self.grad:
@@ -156,9 +156,9 @@ class IterativeInference(object):
             dev = self.net.device
             hs = self.net.h_spatial(H, W)
             st = {
-                'h': torch.zeros((B,) + hs + (self.net.h_pad,), dtype=torch.bfloat16, device=dev),
+                'h': torch.zeros((B,) + hs + (self.net.cm * self.net.h_pad,), dtype=torch.bfloat16, device=dev),
                 'y': torch.zeros((B, self.C, H, W), dtype=torch.float32, device=dev),
-                'y_bf16': torch.zeros((B, H, W, self.net.y_cpad), dtype=torch.bfloat16, device=dev),
+                'y_bf16': torch.zeros((B, H, W, self.net.cm * self.net.y_cpad), dtype=torch.bfloat16, device=dev),
                 'labels': torch.zeros((B, H, W), dtype=torch.int32, device=dev),
                 'active': torch.ones((B,), dtype=torch.int32, device=dev),
                 'n_exec': torch.zeros((B,), dtype=torch.int32, device=dev),
@@ -185,7 +185,7 @@ class IterativeInference(object):
             # the first iteration of a batch computes the whole contracting path (h is new); later ones only
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
             logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0))
-            K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step)
+            K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
             K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])
             if per_iter:
@@ -212,9 +212,9 @@ class IterativeInference(object):
         if h.dtype == torch.bfloat16:
             st['h'].copy_(h)
         else:
-            K.pack_nchw(h.contiguous(), self.net.h_pad, out=st['h'])
+            K.pack_nchw(h.contiguous(), self.net.h_pad, out=st['h'], split=self.net.split)
         st['y'].copy_(y0)
-        K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'])
+        K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'], split=self.net.split)
         if onehot is not None:
             K.onehot_to_labels(onehot.contiguous(), st['labels'])
         elif labels is not None:
@@ -227,7 +227,7 @@ class IterativeInference(object):
                 self._loop(st, step, 1, eps, with_metrics, False)
                 torch.cuda.synchronize()
                 st['y'].copy_(y0)
-                K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'])
+                K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'], split=self.net.split)
                 g = torch.cuda.CUDAGraph()
                 from . import _lib
                 n0 = _lib.launch_count()

@@ -33,13 +33,14 @@ DAE_DICT_DEFAULTS = {'kind': 'fcn8', 'dropout': 0.0, 'skip': True, 'unpool_type'
 
 
 def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path=None, loadpath=None,
-                   dataset='camvid', fcn_params=None, dae_params=None):
-    """The network-construction block of `inference` (iterative_inference.py:127-179)."""
+                   dataset='camvid', fcn_params=None, dae_params=None, precision='bf16'):
+    """The network-construction block of `inference` (iterative_inference.py:127-179).
+    `precision` ('bf16' | 'fp32x3') selects the arithmetic of both nets (see models/DAE_h.py)."""
     if segm_net == 'fcn8':
         fcn = buildFCN8(nb_in_channels, None, n_classes=n_classes, void_labels=void_labels,
                         path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'),
                         trainable=False, load_weights=True, layer=dae_dict['concat_h'] + [dae_dict['layer']],
-                        params=fcn_params)
+                        params=fcn_params, precision=precision)
         padding = 100
     elif segm_net == 'densenet':
         raise NotImplementedError('FC-DenseNet103 conditioning is not built yet (DESIGN.md 7)')
@@ -55,7 +56,7 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
                        n_filters=dae_dict['n_filters'], conv_before_pool=dae_dict['conv_before_pool'],
                        additional_pool=dae_dict['additional_pool'], dropout=dae_dict['dropout'],
                        skip=dae_dict['skip'], unpool_type=dae_dict['unpool_type'], bn=dae_dict['bn'],
-                       params=dae_params)
+                       params=dae_params, precision=precision)
     elif dae_dict['kind'] in ('fcn8', 'contextmod'):
         raise NotImplementedError('DAE kind %r is outside the B200 hot path (kind=standard)' % dae_dict['kind'])
     else:
@@ -66,7 +67,7 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
 def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
               data_augmentation=False, which_set='test', ae_h=False, full_im_ft=False, savepath=None,
               loadpath=None, test_from_0_255=False, data_iter=None, fcn_params=None, dae_params=None,
-              weights_path=None, fused=True, verbose=True, save_batches=False):
+              weights_path=None, fused=True, verbose=True, save_batches=False, precision='bf16'):
     dae_dict = dict(DAE_DICT_DEFAULTS)
     dae_dict.update(dae_dict_updates)
     exp_name = build_experiment_name(segm_net, data_aug=data_augmentation, ae_h=ae_h,
@@ -86,7 +87,7 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
     nb_in_channels = data_iter.data_shape[0]
 
     fcn, dae = build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path, loadpath,
-                              dataset, fcn_params, dae_params)
+                              dataset, fcn_params, dae_params, precision=precision)
     pred_fcn_fn = F.function_pred_fcn(fcn)
     pred_dae_fn = F.function_pred_dae(dae)
     de_fn = F.function_de(dae)

@@ -28,8 +28,15 @@ def _levels(concat_h, additional_pool):
 
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
-                 n_filters=64, additional_pool=2, device='cuda'):
+                 n_filters=64, additional_pool=2, device='cuda', precision='bf16'):
+        """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant) or 'fp32x3'
+        (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
+        hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work)."""
         K.require_device()
+        assert precision in ('bf16', 'fp32x3'), precision
+        self.precision = precision
+        self.split = precision == 'fp32x3'
+        self.cm = 2 if self.split else 1          # bf16 channels per logical channel in activation tensors
         assert n_classes <= 16
         self.n_classes = n_classes
         self.nb_h = nb_features_to_concat
@@ -56,14 +63,14 @@ class DAENet(object):
                 splits = [(self.nb_h, self.h_pad), (cin_real, cin_pad)]
             else:
                 splits = [(cin_real, cin_pad)]
-            self.down.append(pack_conv(W, b, splits, self.filters[p], self.device))
+            self.down.append(pack_conv(W, b, splits, self.filters[p], self.device, split=self.split))
             cin_real = cin_pad = self.filters[p]
         up_in = self.filters[-1]
         for i, p in enumerate(range(self.total, 0, -1)):
             W, b = params[2 * (self.total + i)], params[2 * (self.total + i) + 1]
             n_cl = n_classes if p == 1 else self.filters[p - 2]   # models/fcn_up.py:29-34
             cout_pad = 16 if p == 1 else n_cl
-            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device))
+            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split))
             up_in = n_cl
         self._ws = {}
 
@@ -155,15 +162,15 @@ class DAENet(object):
         ws = {'pool': [], 'mask': [], 'unpool': {}, 'upconv': {}, 'Wc': Wc, 'Wu': Wu}
         for p, (h, w) in enumerate(sizes):
             f = self.filters[p]
-            ws['pool'].append(torch.empty((B, h // 2, w // 2, f), dtype=bf, device=dev))
+            ws['pool'].append(torch.empty((B, h // 2, w // 2, self.cm * f), dtype=bf, device=dev))
             ws['mask'].append(torch.empty((B, h // 2, w // 2, f // 8), dtype=torch.int32, device=dev))
         for p in range(1, self.total + 1):
             ul, uh, vl, vh = Wu[p]
-            ws['unpool'][p] = torch.empty((B, uh - ul, vh - vl, self.filters[p - 1]), dtype=bf, device=dev)
+            ws['unpool'][p] = torch.empty((B, uh - ul, vh - vl, self.cm * self.filters[p - 1]), dtype=bf, device=dev)
             if p > 1:   # up_conv_p output: level-p window, channels of level p-1; skip partner pool_{p-1} has size S_p
                 hl, hh, wl, wh = Wc[p]
                 assert sizes[p - 1] == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
-                ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.filters[p - 2]), dtype=bf, device=dev)
+                ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.cm * self.filters[p - 2]), dtype=bf, device=dev)
         ws['logits'] = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
         self._ws[key] = ws
         return ws
@@ -178,8 +185,10 @@ class DAENet(object):
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
         Wc, Wu = ws['Wc'], ws['Wu']
-        assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.h_pad,), \
+        assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.cm * self.h_pad,), \
             (tuple(h_bf16.shape), self.h_spatial(H, W), self.h_pad)
+        assert y_bf16.shape[3] == self.cm * self.y_cpad
+        sp = self.split
         x = y_bf16
         D = None if full_down else self.down_windows(H, W)
         for p in range(self.total):
@@ -193,9 +202,10 @@ class DAENet(object):
             # pre-pool map is consumed on chip and never written (nothing else reads it)
             if p == self.n_pool:
                 K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, window=win, pooled=ws['pool'][p],
-                         pool_mask=ws['mask'][p])
+                         pool_mask=ws['mask'][p], split=sp)
             else:
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p])
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
+                         split=sp)
             x = ws['pool'][p]
         u, u_origin = ws['pool'][-1], (0, 0)
         for i, p in enumerate(range(self.total, 0, -1)):
@@ -203,15 +213,15 @@ class DAENet(object):
             ul, uh, vl, vh = Wu[p]
             hl, hh, wl, wh = Wc[p]
             up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
-                           window=(ul, vl, uh - ul, vh - vl))
+                           window=(ul, vl, uh - ul, vh - vl), split=sp)
             Wk, bk = self.up[i]
             win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
             if p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
                 u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],
-                             addend_off=(hl, wl), out=ws['upconv'][p])
+                             addend_off=(hl, wl), out=ws['upconv'][p], split=sp)
                 u_origin = (hl, wl)
             else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
-                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True)
+                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=sp)
         return ws['logits']
 
 
@@ -220,7 +230,7 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
              model_name='dae_model.npz', trainable=False, load_weights=False,
              out_nonlin=None, concat_h=['input'], noise=0.1, n_filters=64,
              conv_before_pool=1, additional_pool=0, dropout=0., skip=False,
-             unpool_type='standard', bn=0, params=None):
+             unpool_type='standard', bn=0, params=None, precision='bf16'):
     """Same arguments as the reference builder (models/DAE_h.py:12-17); returns the handle
     of 'probs_dimshuffle'.  The symbolic inputs are ignored.  Built for the benchmark
     configuration; other variants raise.  `noise` only matters for training and for the
@@ -238,5 +248,5 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
             raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
-                 n_filters=n_filters, additional_pool=additional_pool)
+                 n_filters=n_filters, additional_pool=additional_pool, precision=precision)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -38,8 +38,13 @@ class LayerHandle(object):
 
 
 class FCN8Net(object):
-    def __init__(self, nb_in_channels, n_classes, params, temperature=1.0, device='cuda'):
+    def __init__(self, nb_in_channels, n_classes, params, temperature=1.0, device='cuda', precision='bf16'):
+        """precision: 'bf16' or 'fp32x3' (see DAENet)."""
         K.require_device()
+        assert precision in ('bf16', 'fp32x3'), precision
+        self.precision = precision
+        self.split = sp = precision == 'fp32x3'
+        self.cm = 2 if sp else 1
         assert n_classes <= 16
         assert len(params) == 2 * len(PARAM_ORDER), 'expected %d arrays, got %d' % (2 * len(PARAM_ORDER), len(params))
         self.nb_in_channels = nb_in_channels
@@ -50,13 +55,13 @@ class FCN8Net(object):
         cin = nb_in_channels
         for stage in VGG_STAGES:
             for name, cout in stage:
-                self.w[name] = pack_conv(*P[name], [(cin, K.pad_channels(cin))], cout, self.device)
+                self.w[name] = pack_conv(*P[name], [(cin, K.pad_channels(cin))], cout, self.device, split=sp)
                 cin = cout
-        self.w['fc6'] = pack_conv(*P['fc6'], [(512, 512)], 4096, self.device)
-        self.w['fc7'] = pack_conv(*P['fc7'], [(4096, 4096)], 4096, self.device)
-        self.w['score_fr'] = pack_conv(*P['score_fr'], [(4096, 4096)], 16, self.device)
-        self.w['score_pool4'] = pack_conv(*P['score_pool4'], [(512, 512)], 16, self.device)
-        self.w['score_pool3'] = pack_conv(*P['score_pool3'], [(256, 256)], 16, self.device)
+        self.w['fc6'] = pack_conv(*P['fc6'], [(512, 512)], 4096, self.device, split=sp)
+        self.w['fc7'] = pack_conv(*P['fc7'], [(4096, 4096)], 4096, self.device, split=sp)
+        self.w['score_fr'] = pack_conv(*P['score_fr'], [(4096, 4096)], 16, self.device, split=sp)
+        self.w['score_pool4'] = pack_conv(*P['score_pool4'], [(512, 512)], 16, self.device, split=sp)
+        self.w['score_pool3'] = pack_conv(*P['score_pool3'], [(256, 256)], 16, self.device, split=sp)
         self.w['score2'] = pack_deconv16(*P['score2'], self.device)
         self.w['score4'] = pack_deconv16(*P['score4'], self.device)
         # temperature divides upsample.W and .b (models/fcn8.py:193-198)
@@ -69,25 +74,26 @@ class FCN8Net(object):
         B, Cin, H, W = X.shape
         assert Cin == self.nb_in_channels
         out = {}
-        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin))
+        sp, cm = self.split, self.cm
+        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin), split=sp)
         for si, stage in enumerate(VGG_STAGES):
             for ci, (name, cout) in enumerate(stage):
                 Wk, bk = self.w[name]
                 pad = 100 if name == 'conv1_1' else 1
                 if ci == len(stage) - 1:    # last conv of the stage: max-pool fused in the epilogue
                     oh, ow = K.conv_out_size(x.shape[1], x.shape[2], 3, 3, pad)
-                    pooled = torch.empty((B, oh // 2, ow // 2, cout), dtype=torch.bfloat16, device=X.device)
-                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=pooled)
+                    pooled = torch.empty((B, oh // 2, ow // 2, cm * cout), dtype=torch.bfloat16, device=X.device)
+                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=pooled, split=sp)
                 else:
-                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True)
+                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, split=sp)
             out['pool%d' % (si + 1)] = x
-        x = K.conv2d(x, *self.w['fc6'], 7, 7, 0, relu=True)
-        x = K.conv2d(x, *self.w['fc7'], 1, 1, 0, relu=True)
-        score_fr = K.conv2d(x, *self.w['score_fr'], 1, 1, 0, relu=True, out_f32=True)
+        x = K.conv2d(x, *self.w['fc6'], 7, 7, 0, relu=True, split=sp)
+        x = K.conv2d(x, *self.w['fc7'], 1, 1, 0, relu=True, split=sp)
+        score_fr = K.conv2d(x, *self.w['score_fr'], 1, 1, 0, relu=True, out_f32=True, split=sp)
         # score2 + centre-cropped score_pool4 (models/fcn8.py:90-97)
-        sp4 = K.conv2d(out['pool4'], *self.w['score_pool4'], 1, 1, 0, relu=True, out_f32=True)
+        sp4 = K.conv2d(out['pool4'], *self.w['score_pool4'], 1, 1, 0, relu=True, out_f32=True, split=sp)
         fused = self._deconv_sum(score_fr, 'score2', 4, 2, sp4)
-        sp3 = K.conv2d(out['pool3'], *self.w['score_pool3'], 1, 1, 0, relu=True, out_f32=True)
+        sp3 = K.conv2d(out['pool3'], *self.w['score_pool3'], 1, 1, 0, relu=True, out_f32=True, split=sp)
         final = self._deconv_sum(fused, 'score4', 4, 2, sp3)
         # upsample + centre crop to the input size (models/fcn8.py:109-118)
         fH, fW = (final.shape[1] - 1) * 8 + 16, (final.shape[2] - 1) * 8 + 16
@@ -96,8 +102,8 @@ class FCN8Net(object):
         probs = torch.empty((B, self.n_classes, H, W), dtype=torch.float32, device=X.device)
         y_bf16 = None
         if y_bf16_cpad:
-            y_bf16 = torch.empty((B, H, W, y_bf16_cpad), dtype=torch.bfloat16, device=X.device)
-        K.softmax_nchw(logits, self.n_classes, probs, y_bf16)
+            y_bf16 = torch.empty((B, H, W, cm * y_bf16_cpad), dtype=torch.bfloat16, device=X.device)
+        K.softmax_nchw(logits, self.n_classes, probs, y_bf16, split=sp)
         out['probs_dimshuffle'] = probs
         out['y_bf16'] = y_bf16
         return {k: v for k, v in out.items() if k in want or k == 'y_bf16'}
@@ -115,7 +121,7 @@ def buildFCN8(nb_in_channels, input_var=None,
               path_weights='/Tmp/romerosa/itinf/models/camvid/new_fcn8_model_best.npz',
               n_classes=21, load_weights=True, void_labels=[], trainable=False,
               layer=['probs_dimshuffle'], pascal=False, temperature=1.0, dropout=0.5,
-              params=None):
+              params=None, precision='bf16'):
     """Same arguments as the reference builder (models/fcn8.py:16-22).  `input_var` is a
     Theano symbol there and is ignored here; `params` (a 42-array list in checkpoint
     order) may be passed instead of `path_weights`.  Inference only: `trainable` and
@@ -128,7 +134,8 @@ def buildFCN8(nb_in_channels, input_var=None,
             raise ValueError('buildFCN8 needs weights: pass params= or load_weights=True with path_weights')
         params = load_npz_params(path_weights)
     # NB the reference applies `temperature` only when load_weights is set (models/fcn8.py:194)
-    net = FCN8Net(nb_in_channels, n_classes, params, temperature=temperature if load_weights else 1.0)
+    net = FCN8Net(nb_in_channels, n_classes, params, temperature=temperature if load_weights else 1.0,
+                  precision=precision)
     handles = []
     for el in layer:
         if el in _POOL_CHANNELS:

@@ -25,7 +25,7 @@ def test_binding_table_matches_header(lib):
 
 
 def test_abi_version_and_error_text(lib):
-    assert lib.iiseg_abi_version() == 1
+    assert lib.iiseg_abi_version() == 2
     assert isinstance(lib.iiseg_last_error(), bytes)
 
 
@@ -33,8 +33,9 @@ def test_bad_descriptor_is_rejected_without_gpu(lib):
     """Argument validation happens before any CUDA call, so it can be checked here."""
     import ctypes as C
     from iterative_inference_segm_b200 import _lib
-    d = _lib.ConvDesc(src0=16, weight=16, bias=16, out=16, N=1, H=8, W=8, C0=48, C1=0, Cout=64, R=3, S=3, pad=1,
+    d = _lib.ConvDesc(weight=16, bias=16, out=16, N=1, H=8, W=8, Cout=64, R=3, S=3, pad=1,
                       oh0=0, ow0=0, OH=8, OW=8)
+    d.src[0], d.C[0] = 16, 48
     assert lib.iiseg_conv2d_fwd(C.byref(d), None) != 0
     assert b'C0=48' in lib.iiseg_last_error()
 

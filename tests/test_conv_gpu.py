@@ -3,6 +3,7 @@ PyTorch fp32 reference on the SAME bf16-rounded operands (so the only difference
 accumulation order and the final bf16 rounding of the output: tolerance 2^-7 relative, stated
 below).  Shapes cover ragged tiles, the pad=100 first layer, the dual-source (concat) loader,
 the fused skip-sum, the cropped fp32 output window, 1x1 and 7x7 filters."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -132,3 +133,86 @@ def test_deconv_matches_conv_transpose(cuda, k, stride, H, W, window, addend):
     got = out[..., :C].permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) < 1e-4
     assert float(out[..., C:].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------
+# fp32-accurate variant ("fp32x3"): activations and weights are (hi | lo) bf16 pairs, the conv
+# accumulates hi*hi + lo*hi + hi*lo on the same tensor-core loop.  Compared against an fp64
+# convolution of the ORIGINAL fp32 operands; per-product error ~2^-16 plus the tensor core's fp32
+# accumulation over up to 392 MMAs (K = 6272): stated tolerance 1.5e-4 relative to max(|ref|, 1)
+# (measured worst case 7.9e-5 on the 7x7 layer, ~1e-5 on the 3x3 ones; the bf16 variant's is 2^-7).
+# ---------------------------------------------------------------------------
+def _recon(t):
+    """(hi | lo) NHWC bf16 pair tensor -> fp32 NCHW."""
+    c = t.shape[3] // 2
+    return (t[..., :c].float() + t[..., c:].float()).permute(0, 3, 1, 2)
+
+
+SPLIT_CASES = [
+    # N, H, W, C0, C1, Cout, R, pad, relu, addend, window, out_f32
+    (2, 37, 45, 64, 0, 128, 3, 1, 1, 0, None, 0),
+    (2, 17, 21, 128, 64, 256, 3, 1, 1, 0, None, 0),
+    (2, 33, 29, 128, 0, 64, 3, 1, 0, 1, None, 0),
+    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),
+    (1, 40, 56, 64, 0, 16, 3, 1, 0, 0, (5, 7, 24, 32), 1),
+    (1, 17, 21, 128, 0, 256, 7, 0, 1, 0, None, 0),
+    (1, 11, 15, 256, 0, 16, 1, 0, 1, 0, None, 1),
+]
+
+
+@pytest.mark.parametrize('case', SPLIT_CASES, ids=[str(c) for c in SPLIT_CASES])
+def test_conv_split_matches_fp64_reference(cuda, case):
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_conv
+    N, H, W, C0, C1, Cout, R, pad, relu, addend, window, out_f32 = case
+    torch.manual_seed(0)
+    Cin = C0 + C1
+    x = torch.randn(N, Cin, H, W, device=cuda)
+    Wt = torch.randn(Cout, Cin, R, R, device=cuda) / (Cin * R * R) ** 0.5
+    b = torch.randn(Cout, device=cuda)
+    src0 = K.pack_nchw(x[:, :C0].contiguous(), C0, split=True)
+    src1 = K.pack_nchw(x[:, C0:].contiguous(), C1, split=True) if C1 else None
+    Wk, bk = pack_conv(Wt, b, [(C0, C0)] + ([(C1, C1)] if C1 else []), Cout, cuda, split=True)
+    fOH, fOW = H + 2 * pad - R + 1, W + 2 * pad - R + 1
+    oh0, ow0, OH, OW = window if window else (0, 0, fOH, fOW)
+    add_f = torch.randn(N, Cout, OH, OW, device=cuda) if addend else None
+    add = K.pack_nchw(add_f, Cout, split=True) if addend else None
+    out = K.conv2d(src0, Wk, bk, R, R, pad, relu, src1=src1, addend=add, window=window, out_f32=bool(out_f32),
+                   split=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), Wt.double(), b.double(), padding=pad)[:, :, oh0:oh0 + OH, ow0:ow0 + OW]
+    if add_f is not None:
+        ref = ref + add_f.double()
+    if relu:
+        ref = torch.relu(ref)
+    got = (out.permute(0, 3, 1, 2) if out_f32 else _recon(out)).double()
+    err = ((got - ref).abs() / ref.abs().clamp(min=1.0)).max()
+    assert float(err) < 1.5e-4, float(err)
+
+
+@pytest.mark.parametrize('N,H,W,C,Cout,pad', [(2, 37, 45, 64, 128, 1), (1, 20, 24, 64, 64, 100), (3, 8, 10, 64, 512, 1)])
+def test_conv_split_fused_pool_mask_is_exact(cuda, N, H, W, C, Cout, pad):
+    """fp32x3 fused pool: pooled pair and tie mask are exactly the 2x2 max / tie-inclusive mask of the
+    reconstructed fp32 (hi+lo) conv output, and the windowed unpool gates both halves with it."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_conv
+    from oracle import lasagne_semantics as L
+    from tests.test_streaming_kernels_gpu import _mask_to_dense
+    torch.manual_seed(4)
+    x = torch.randn(N, C, H, W, device=cuda)
+    Wt = torch.randn(Cout, C, 3, 3, device=cuda) / (9 * C) ** 0.5
+    b = torch.randn(Cout, device=cuda)
+    xs = K.pack_nchw(x, C, split=True)
+    Wk, bk = pack_conv(Wt, b, [(C, C)], Cout, cuda, split=True)
+    full = _recon(K.conv2d(xs, Wk, bk, 3, 3, pad, relu=True, split=True)).cpu()
+    OH, OW = full.shape[2], full.shape[3]
+    pooled = torch.zeros((N, OH // 2, OW // 2, 2 * Cout), dtype=torch.bfloat16, device=cuda)
+    mask = torch.zeros((N, OH // 2, OW // 2, Cout // 8), dtype=torch.int32, device=cuda)
+    K.conv2d(xs, Wk, bk, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, split=True)
+    assert torch.equal(_recon(pooled).cpu(), L.maxpool2(full))
+    ref_mask = L.tie_mask(full)[:, :, :2 * (OH // 2), :2 * (OW // 2)]
+    assert np.array_equal(_mask_to_dense(mask, Cout), ref_mask.numpy())
+    u = torch.randn(N, Cout, OH // 2, OW // 2, device=cuda)
+    us = K.pack_nchw(u, Cout, split=True)
+    out = K.unpool2(us, mask, OH, OW, split=True)
+    assert torch.equal(_recon(out).cpu(), L.depool2d(_recon(us).cpu(), full))

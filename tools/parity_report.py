@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import nets, weights  # noqa: E402  (checker only)
 
 
-def main(H=64, W=80, N=10, step=0.05):
+def main(H=64, W=80, N=10, step=0.05, precision='bf16'):
     from iterative_inference_segm_b200.models.fcn8 import buildFCN8
     from iterative_inference_segm_b200.models.DAE_h import buildDAE
     from iterative_inference_segm_b200.functions import (function_pred_fcn, function_pred_dae, IterativeInference)
@@ -22,9 +22,10 @@ def main(H=64, W=80, N=10, step=0.05):
     X, L, lab = weights.synthetic_batch(2, H, W, NCLS)
     pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
     pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
-    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf, precision=precision)
     dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0,
-                   n_filters=64, additional_pool=2, skip=True, unpool_type='trackind', params=pd)
+                   n_filters=64, additional_pool=2, skip=True, unpool_type='trackind', params=pd, precision=precision)
+    print('precision', precision)
     t = time.time()
     h_o, y0_o = nets.fcn8_forward(pf, X, NCLS)
     print('oracle fcn8 %.1fs' % (time.time() - t))
@@ -55,5 +56,5 @@ def main(H=64, W=80, N=10, step=0.05):
 
 
 if __name__ == '__main__':
-    a = [int(v) for v in sys.argv[1:]]
-    main(*a)
+    a = [int(v) for v in sys.argv[1:4]]
+    main(*a, precision=sys.argv[4] if len(sys.argv) > 4 else 'bf16')
