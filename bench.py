@@ -156,7 +156,7 @@ def run_b200(args):
     from iterative_inference_segm_b200.models.DAE_h import buildDAE
     from iterative_inference_segm_b200.functions import IterativeInference, jaccard_from_cm
     from iterative_inference_segm_b200.profiling import KernelTimer
-    from oracle import weights     # synthetic weight / data recipe only (shared with the CPU arm)
+    from iterative_inference_segm_b200 import synthetic as weights     # synthetic weight / data recipe
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -283,7 +283,7 @@ def run_b200(args):
                      'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
                      'hbm_peak_gbs': peaks['hbm_gbs'],
                      'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues'}
-        if world == 1:
+        if world == 1 and not args.no_cpu_baseline:
             t_img, cores, parts = cpu_reference_sample()
             cpu_base = {'value': 1.0 / t_img, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                         'sample': CPU_SAMPLE_TEXT, 'parts_s': {k: round(v, 3) for k, v in parts.items()}}
@@ -319,6 +319,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='development runs: skip the CPU oracle timing')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -18,10 +18,11 @@
 //   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) M=128, N=BN, K=16, issued by
 //     one thread; accumulators live in TMEM, double-buffered (2 x BN columns) so
 //     the epilogue of tile i overlaps the main loop of tile i+1.
-//   * Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-//     allocator, warps 4-7 epilogue (tcgen05.ld -> bias/ReLU/skip-sum -> bf16 ->
-//     swizzled smem -> TMA store, or direct fp32/bf16 stores for 16-channel
-//     outputs).  Persistent CTAs, one per SM, static round-robin tile schedule.
+//   * Warp roles: warp 0 TMA producer, warp 1 (+3) MMA issuer(s), warp 2 TMEM
+//     allocator, warps 4-11 epilogue in two groups of four, one per accumulator
+//     stage (tcgen05.ld -> bias/ReLU/skip-sum -> bf16 -> global memory, or the fused
+//     2x2 max-pool + tie mask through a per-group smem tile, or fp32 16-channel
+//     rows).  Persistent CTAs, one per SM, static round-robin tile schedule.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,8 +49,8 @@ struct ConvCfg {
   static constexpr int G = BN == 16 ? 3 : (BN == 256 ? 1 : 2);
   static constexpr int kBBlockBytes = BN * 128;
   static constexpr int kStageBytes = G * (kAStageBytes + kBBlockBytes);
-  static constexpr bool kTmaStore = BN >= 64;
-  static constexpr int kStagingTotal = kTmaStore ? 2 * kStagingBytes : 0;
+  static constexpr bool kPoolStage = BN >= 64;                 // the fused pool stages tiles in smem, one buffer per epilogue group
+  static constexpr int kStagingTotal = kPoolStage ? 2 * kStagingBytes : 0;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - kStagingTotal;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -62,7 +63,6 @@ struct ConvCfg {
 struct alignas(64) ConvParams {
   CUtensorMap tm_src[IISEG_MAX_SRC];     // channel-concatenated activation sources (views of NHWC tensors)
   CUtensorMap tm_w;
-  CUtensorMap tm_out;
   const float* bias;
   const __nv_bfloat16* addend;
   void* out;
@@ -76,7 +76,7 @@ struct alignas(64) ConvParams {
   int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
   int a_blk_bytes, n_a, n_b, g_b;   // halo kernel: A buffer size / count, B stage count, taps per B stage
   int b_resident;           // halo kernel: all R*S*n_cblk weight blocks stay in smem for the whole launch
-  int n_stage_buf;          // output staging buffers (2, or 1 when the resident filter bank needs the room)
+  int n_stage_buf;          // halo kernel: pool staging buffers (2 = one per epilogue group with the fused pool, else 0)
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
   int OH, OW, Cout;
@@ -87,7 +87,7 @@ struct alignas(64) ConvParams {
   int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
-  int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue
+  int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores
 };
 
 // Debug timeline (IISEG_CONV_DBG bit 2): block 0 stamps clock64() at fixed points of its first 32 tiles.
@@ -168,14 +168,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 UMMA):
 // start address >> 4, LBO unused (one swizzle atom along K), SBO = 8 rows * 128 B,
@@ -236,325 +228,262 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
 }
 
 // ---------------------------------------------------------------------------
-// Epilogue (8 warps, shared by both main-loop kernels): TMEM -> registers -> bias / skip-sum / ReLU ->
-// bf16 -> swizzled smem staging -> TMA store, fused 2x2 max-pool + tie mask, or direct 16-channel stores.
-// TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
+// Epilogue (shared by both main-loop kernels): TMEM -> registers -> bias / skip-sum / ReLU -> bf16 ->
+// global memory, or the fused 2x2 max-pool + tie mask, or fp32 16-channel rows.
+//
+// The 8 epilogue warps form two groups of 4 (one warp per TMEM lane quadrant, q = warp % 4 by the
+// hardware rule).  Group g drains accumulator stage g, i.e. every other tile of this CTA, so two
+// tiles' epilogues are in flight at once and the latency-bound steps of one (skip-sum operand
+// fetched from L2/HBM, TMEM loads, global stores) overlap the other's.  Measured before this split:
+// with all 8 warps serialised on one tile the up_conv layers spent ~5000 cycles per tile waiting for
+// the addend, the pooled layers ~1900.  A warp owns 32 accumulator rows (pixels) and walks the BN
+// columns in 32-channel chunks; the skip-sum operand of the next chunk (and of the first chunk of the
+// tile, before the accumulator is even ready) is prefetched.  bf16 outputs go straight to global
+// memory (each thread writes 64 contiguous bytes = two full sectors), no smem staging, no barriers.
+// Only the fused pool stages 64 channels at a time in the group's own 16 KiB buffer (named barrier
+// 1 + g, 128 threads), because its 2x2 windows span accumulator rows owned by different warps.
 // Accumulator row m is box pixel (m / pitch, m % pitch); rows with m % pitch >= TW are halo junk.
 // ---------------------------------------------------------------------------
-template <int BN>
-__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
-                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
-  using Cfg = ConvCfg<BN>;
-  auto tmem_full_bar = [&](int i) { return tmem_full_bar0 + 8u * i; };
-  auto tmem_empty_bar = [&](int i) { return tmem_empty_bar0 + 8u * i; };
-    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the columns.
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int macc = q * 32 + lane;         // accumulator row
-    const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
-    const bool in_box = (hl < p.TH) && (wl < p.TW);
-    const int m = hl * p.TW + wl;           // dense pixel index inside the TH x TW box (staging row)
-    const bool issuer = (warp == 4);
-    int iter = 0;
-    int store_buf = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
-      const TileCoord tc = decode_tile(p, t);
-      const int as = iter & 1;
-      const uint32_t aphase = (iter >> 1) & 1u;
-      const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
-      const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
-      const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
-      const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
-      if (issuer && lane == 0) IISEG_STAMP(iter, 4);
-      mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
-      tcgen05_fence_after();
-      if (issuer && lane == 0) IISEG_STAMP(iter, 5);
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
-      const int n0 = tc.nt * BN;
-
-      if constexpr (Cfg::kTmaStore) {
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 64; ++chunk) {
-          const int cbase = n0 + chunk * 64 + half * 32;     // this thread's 32 channels
-          // skip-sum operand: this pixel's 32 channels = 64 contiguous bytes
-          uint4 add[4];
-          if (p.addend != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              add[j] = valid ? ldg_nc_v4(p.addend + apix * p.Cout + cbase + j * 8) : make_uint4(0, 0, 0, 0);
-          }
-          uint32_t v[32];
-          tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
-          tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
-          // the staging buffer we are about to overwrite must have been read by its TMA store
-          if (issuer && elect_one_sync()) { if (p.n_stage_buf > 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          tmem_ld_wait();
-          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 6);
-          if (chunk == BN / 64 - 1) {   // all TMEM reads of this accumulator are done
-            tcgen05_fence_before();
-            mbar_arrive(tmem_empty_bar(as));
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 7);
-          const uint32_t sbuf = smem_stage_out + store_buf * kStagingBytes;
-          uint32_t packed[16];
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {      // 4 channels per step: one 16-byte bias load
-            const float4 b = __ldg(bias4 + j4);
-            float f0 = __uint_as_float(v[4 * j4]) + b.x, f1 = __uint_as_float(v[4 * j4 + 1]) + b.y;
-            float f2 = __uint_as_float(v[4 * j4 + 2]) + b.z, f3 = __uint_as_float(v[4 * j4 + 3]) + b.w;
-            if (p.addend != nullptr) {
-              const uint4& a4 = add[j4 >> 1];
-              const uint32_t aw0 = (j4 & 1) ? a4.z : a4.x, aw1 = (j4 & 1) ? a4.w : a4.y;
-              f0 += bf16_lo(aw0); f1 += bf16_hi(aw0); f2 += bf16_lo(aw1); f3 += bf16_hi(aw1);
-            }
-            packed[2 * j4] = pack_bf16x2(f0, f1);
-            packed[2 * j4 + 1] = pack_bf16x2(f2, f3);
-          }
-          if (p.relu) {     // rectify after rounding: max(x, 0) commutes with the bf16 rounding
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[j] = bf16x2_max(packed[j], 0u);
-          }
-          // four 16-byte chunks (8 channels each) of this row, 128B-swizzled like the TMA box
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            if (!in_box) break;
-            const int chunk16 = half * 4 + cc;
-            const uint32_t addr = sbuf + m * 128 + ((chunk16 ^ (m & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(packed[cc * 4 + 0]),
-                         "r"(packed[cc * 4 + 1]), "r"(packed[cc * 4 + 2]), "r"(packed[cc * 4 + 3]) : "memory");
-          }
-          if (p.pooled == nullptr) {
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (issuer && elect_one_sync()) {
-              tma_store_4d(&p.tm_out, sbuf, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
-              tma_store_commit();
-            }
-          } else {
-            if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 8);
-            // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
-            // staged tile never goes to HBM.  One thread per (pooled pixel, 8 channels): TH, TW and the
-            // tile origin are even, so every 2x2 window lies inside the box.
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 9);
-            const int et = threadIdx.x - 128;
-            const int pp = et >> 3, cgp = et & 7;
-            const int tw2 = p.TW >> 1;
-            int pw_l = pp;
-            const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
-            const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
-            const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
-            if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
-              const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
-              uint32_t w[4][4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int mm = m00 + (e >> 1) * p.TW + (e & 1);
-                const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
-              }
-              uint32_t bits = 0, outw[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                outw[k] = bf16x2_max(bf16x2_max(w[0][k], w[1][k]), bf16x2_max(w[2][k], w[3][k]));
-#pragma unroll
-                for (int e = 0; e < 4; ++e) bits |= tie_bits(bf16x2_eq_mask(w[e][k], outw[k]), k, e);
-              }
-              const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
-              const int cch = n0 + chunk * 64 + cgp * 8;
-              stg_v4(p.pooled + ppix * p.Cout + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
-              if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
-            }
-          }
-          if (issuer && lane == 0 && chunk == 0) IISEG_STAMP(iter, 10);
-          if (p.n_stage_buf > 1) store_buf ^= 1;
-        }
-      } else {
-        // 16-channel outputs (score maps, logits): direct stores from registers, 8 channels per thread
-        static_assert(BN == 16 || Cfg::kTmaStore, "direct-store epilogue is written for BN == 16");
-        uint32_t v[8];
-        tmem_ld_x8(taddr + half * 8, v);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(tmem_empty_bar(as));
-        const int cbase = n0 + half * 8;
-        float f[8];
-        {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + 1);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
-        }
-        if (p.addend != nullptr && valid) {
-          const uint4 a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
-          const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (valid) {
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
-            stg_v4(o, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                 pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
-          }
-        }
-      }
-    }
-    if (Cfg::kTmaStore && issuer && elect_one_sync()) tma_store_wait_read<0>();
+__device__ __forceinline__ void epi_bar(int grp) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 }
 
-// ---------------------------------------------------------------------------
-// Split-precision epilogue (fp32-accurate variant).  Every activation tensor carries the bf16 pair
-// (hi, lo) of an fp32 value, hi = bf16(x), lo = bf16(x - hi), as channel halves [0,C) | [C,2C); the
-// host concatenates (hi, lo, hi) activations against (W_hi, W_hi, W_lo) weights along K, so the
-// unchanged bf16 main loops accumulate hi*hi + lo*hi + hi*lo in fp32 (relative error ~2^-16).
-// Here the fp32 accumulator gets bias / skip-sum / ReLU in fp32, is split into the pair, and both
-// halves are staged (buffer 0 = hi, buffer 1 = lo) for two TMA stores, or max-pooled: pool and
-// tie mask compare the reconstructed fp32 values, as the reference does on float32 activations.
-// ---------------------------------------------------------------------------
-template <int BN>
-__device__ __forceinline__ void conv_epilogue_split(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
-                                                    uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
-  auto tmem_full_bar = [&](int i) { return tmem_full_bar0 + 8u * i; };
-  auto tmem_empty_bar = [&](int i) { return tmem_empty_bar0 + 8u * i; };
+template <int BN, bool kSplit>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
   const int q = warp & 3;
-  const int half = (warp - 4) >> 2;
-  const int macc = q * 32 + lane;
+  const int grp = (warp - 4) >> 2;
+  const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * grp, tmem_empty_bar = tmem_empty_bar0 + 8u * grp;
+  const int macc = q * 32 + lane;         // accumulator row
   const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
   const bool in_box = (hl < p.TH) && (wl < p.TW);
-  const int m = hl * p.TW + wl;
-  const bool issuer = (warp == 4);
-  const int cpp = 2 * p.Cout;               // channels per pixel of out / addend / pooled tensors
-  const uint32_t sb_hi = smem_stage_out, sb_lo = smem_stage_out + kStagingBytes;
-  int iter = 0;
-  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
-    const TileCoord tc = decode_tile(p, t);
-    const int as = iter & 1;
+  const int m = hl * p.TW + wl;           // dense pixel index inside the TH x TW box (staging row)
+  const uint32_t sbuf = smem_stage_out + grp * kStagingBytes;
+  const int et = (warp & 3) * 32 + lane;  // thread index inside the group
+  const int cpp = kSplit ? 2 * p.Cout : p.Cout;      // channels per pixel of out / addend / pooled
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
     const uint32_t aphase = (iter >> 1) & 1u;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
     const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
-    mbar_wait(tmem_full_bar(as), aphase, p.diag, 4, as);
-    tcgen05_fence_after();
-    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
     const int n0 = tc.nt * BN;
-#pragma unroll 1
-    for (int chunk = 0; chunk < BN / 64; ++chunk) {
-      const int cbase = n0 + chunk * 64 + half * 32;
-      uint32_t v[32];
-      tmem_ld_x16(taddr + chunk * 64 + half * 32, v);
-      tmem_ld_x16(taddr + chunk * 64 + half * 32 + 16, v + 16);
-      if (issuer && elect_one_sync()) tma_store_wait_read<0>();      // both staging buffers are reused every chunk
-      tmem_ld_wait();
-      if (chunk == BN / 64 - 1) {
-        tcgen05_fence_before();
-        mbar_arrive(tmem_empty_bar(as));
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + cbase + j);
-      if (p.addend != nullptr && valid) {
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp * BN) + (static_cast<uint32_t>(q * 32) << 16);
+
+    if constexpr (BN >= 64) {
+      // skip-sum operand of the first chunk: requested before the accumulator is ready
+      const bool has_add = (p.addend != nullptr) && valid && !(p.dbg & 8);
+      const __nv_bfloat16* arow = p.addend + apix * cpp + n0;
+      uint4 add[kSplit ? 8 : 4];
+      if (has_add) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint4 ah = ldg_nc_v4(p.addend + apix * cpp + cbase + j * 8);
-          const uint4 al = ldg_nc_v4(p.addend + apix * cpp + p.Cout + cbase + j * 8);
-          const uint32_t hw[4] = {ah.x, ah.y, ah.z, ah.w}, lw[4] = {al.x, al.y, al.z, al.w};
+          add[j] = ldg_nc_v4(arow + j * 8);
+          if (kSplit) add[4 + j] = ldg_nc_v4(arow + p.Cout + j * 8);
+        }
+      }
+      if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 4);
+      mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
+      tcgen05_fence_after();
+      if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 5);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int cbase = n0 + chunk * 32;       // this chunk's 32 channels
+        uint32_t v[32];
+        tmem_ld_x16(taddr + chunk * 32, v);
+        tmem_ld_x16(taddr + chunk * 32 + 16, v + 16);
+        uint4 add_cur[kSplit ? 8 : 4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            f[8 * j + 2 * k] += bf16_lo(hw[k]) + bf16_lo(lw[k]);
-            f[8 * j + 2 * k + 1] += bf16_hi(hw[k]) + bf16_hi(lw[k]);
+        for (int j = 0; j < (kSplit ? 8 : 4); ++j) add_cur[j] = add[j];
+        if (has_add && chunk + 1 < BN / 32) {     // prefetch the next chunk's skip-sum operand
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            add[j] = ldg_nc_v4(arow + (chunk + 1) * 32 + j * 8);
+            if (kSplit) add[4 + j] = ldg_nc_v4(arow + p.Cout + (chunk + 1) * 32 + j * 8);
           }
+        }
+        tmem_ld_wait();
+        if (chunk == BN / 32 - 1) {   // all TMEM reads of this accumulator are done
+          tcgen05_fence_before();
+          mbar_arrive(tmem_empty_bar);
+        }
+        float f[32];
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {      // 4 channels per step: one 16-byte bias load
+          const float4 b = __ldg(bias4 + j4);
+          f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+          f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+        }
+        if (has_add) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t aw[4] = {add_cur[j].x, add_cur[j].y, add_cur[j].z, add_cur[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { f[8 * j + 2 * k] += bf16_lo(aw[k]); f[8 * j + 2 * k + 1] += bf16_hi(aw[k]); }
+            if (kSplit) {
+              const uint32_t lw[4] = {add_cur[4 + j].x, add_cur[4 + j].y, add_cur[4 + j].z, add_cur[4 + j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) { f[8 * j + 2 * k] += bf16_lo(lw[k]); f[8 * j + 2 * k + 1] += bf16_hi(lw[k]); }
+            }
+          }
+        }
+        // bf16 (pair) of the activation.  Plain variant: rectify after rounding (max(x,0) commutes with
+        // the rounding); split variant: rectify in fp32, then hi = bf16(x), lo = bf16(x - hi).
+        uint32_t hi[16], lo[kSplit ? 16 : 1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float a = f[2 * j], b = f[2 * j + 1];
+          if (kSplit && p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          hi[j] = pack_bf16x2(a, b);
+          if (kSplit) lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), b - bf16_hi(hi[j]));
+          else if (p.relu) hi[j] = bf16x2_max(hi[j], 0u);
+        }
+        if (p.pooled == nullptr) {
+          if (valid && !(p.dbg & 16)) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * cpp + cbase;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              stg_v4(o + j * 8, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+              if (kSplit) stg_v4(o + p.Cout + j * 8, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+            }
+          }
+        } else {
+          // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
+          // pre-pool tile never goes to HBM.  Staging row m holds 64 channels = 8 swizzled 16-byte
+          // chunks.  Plain: two 32-channel accumulator chunks fill a row, then the group pools 64
+          // channels.  Split: one accumulator chunk fills a row as (32 hi | 32 lo), pooled at once.
+          const int half = kSplit ? 0 : (chunk & 1);
+          if (in_box) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const uint32_t addr = sbuf + m * 128 + (((half * 4 + cc) ^ (m & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(hi[cc * 4 + 0]),
+                           "r"(hi[cc * 4 + 1]), "r"(hi[cc * 4 + 2]), "r"(hi[cc * 4 + 3]) : "memory");
+              if (kSplit) {
+                const uint32_t addr2 = sbuf + m * 128 + (((4 + cc) ^ (m & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr2), "r"(lo[cc * 4 + 0]),
+                             "r"(lo[cc * 4 + 1]), "r"(lo[cc * 4 + 2]), "r"(lo[cc * 4 + 3]) : "memory");
+              }
+            }
+          }
+          if (kSplit || half == 1) {
+            epi_bar(grp);
+            // TH, TW and the tile origin are even, so every 2x2 window lies inside the box.
+            const int tw2 = p.TW >> 1;
+            constexpr int kCg = kSplit ? 4 : 8;                 // 8-channel groups staged per row
+            constexpr int kItems = 32 * kCg / 128;              // work items per thread (32 pooled pixels max)
+#pragma unroll
+            for (int it = 0; it < kItems; ++it) {
+              const int item = et + it * 128;
+              const int cgp = item % kCg;
+              int pw_l = item / kCg;
+              const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
+              const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
+              const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
+              if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
+                const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
+                uint32_t w[4][4], wl_[kSplit ? 4 : 1][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int mm = m00 + (e >> 1) * p.TW + (e & 1);
+                  const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
+                  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
+                  if (kSplit) {
+                    const uint32_t addr2 = sbuf + mm * 128 + (((4 + cgp) ^ (mm & 7)) << 4);
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wl_[e][0]), "=r"(wl_[e][1]), "=r"(wl_[e][2]), "=r"(wl_[e][3]) : "r"(addr2));
+                  }
+                }
+                uint32_t bits = 0, outw[4], outl[kSplit ? 4 : 1] = {};
+                if constexpr (!kSplit) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    outw[k] = bf16x2_max(bf16x2_max(w[0][k], w[1][k]), bf16x2_max(w[2][k], w[3][k]));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) bits |= tie_bits(bf16x2_eq_mask(w[e][k], outw[k]), k, e);
+                  }
+                } else {      // pool and tie mask compare the reconstructed fp32 values hi + lo
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {        // the two channels packed in word k
+                      float fv[4];
+#pragma unroll
+                      for (int e = 0; e < 4; ++e)
+                        fv[e] = par ? bf16_hi(w[e][k]) + bf16_hi(wl_[e][k]) : bf16_lo(w[e][k]) + bf16_lo(wl_[e][k]);
+                      const float mx = fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3]));
+                      int win = 3;
+#pragma unroll
+                      for (int e = 3; e >= 0; --e)
+                        if (fv[e] == mx) { bits |= 1u << (16 * par + 4 * k + e); win = e; }
+                      const uint32_t sh = par ? 0xFFFF0000u : 0x0000FFFFu;
+                      if (par == 0) { outw[k] = w[win][k] & sh; outl[k] = wl_[win][k] & sh; }
+                      else { outw[k] |= w[win][k] & sh; outl[k] |= wl_[win][k] & sh; }
+                    }
+                  }
+                }
+                const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
+                const int cch = (kSplit ? cbase : cbase - 32) + cgp * 8;
+                stg_v4(p.pooled + ppix * cpp + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
+                if (kSplit) stg_v4(p.pooled + ppix * cpp + p.Cout + cch, make_uint4(outl[0], outl[1], outl[2], outl[3]));
+                if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+              }
+            }
+            epi_bar(grp);       // the staging rows are rewritten by the next channel chunk
+          }
+        }
+      }
+      if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 6);
+    } else {
+      // 16-channel outputs (score maps, logits): one 64-byte fp32 (or 32-byte bf16) row per thread
+      static_assert(BN == 16 || BN >= 64, "direct-store epilogue is written for BN == 16");
+      uint4 a01[2];
+      const bool has_add = (p.addend != nullptr) && valid;
+      if (has_add) { a01[0] = ldg_nc_v4(p.addend + apix * p.Cout); a01[1] = ldg_nc_v4(p.addend + apix * p.Cout + 8); }
+      mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
+      tcgen05_fence_after();
+      uint32_t v[16];
+      tmem_ld_x16(taddr, v);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty_bar);
+      float f[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+        f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+        f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+      }
+      if (has_add) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t aw[4] = {a01[j].x, a01[j].y, a01[j].z, a01[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { f[8 * j + 2 * k] += bf16_lo(aw[k]); f[8 * j + 2 * k + 1] += bf16_hi(aw[k]); }
         }
       }
       if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      if (in_box) {
+      if (valid) {
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t hi[4], lo[4];
+          for (int j = 0; j < 4; ++j)
+            stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float a = f[8 * cc + 2 * k], b = f[8 * cc + 2 * k + 1];
-            hi[k] = pack_bf16x2(a, b);
-            lo[k] = pack_bf16x2(a - bf16_lo(hi[k]), b - bf16_hi(hi[k]));
-          }
-          const uint32_t off = m * 128 + (((half * 4 + cc) ^ (m & 7)) << 4);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sb_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sb_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-        }
-      }
-      if (p.pooled == nullptr) {
-        fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (issuer && elect_one_sync()) {
-          tma_store_4d(&p.tm_out, sb_hi, n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
-          tma_store_4d(&p.tm_out, sb_lo, p.Cout + n0 + chunk * 64, tc.tw * p.TW, tc.th * p.TH, tc.n);
-          tma_store_commit();
-        }
-      } else {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int et = threadIdx.x - 128;
-        const int pp = et >> 3, cgp = et & 7;
-        const int tw2 = p.TW >> 1;
-        int pw_l = pp;
-        const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
-        const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;
-        const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;
-        if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
-          const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
-          uint32_t wh[4][4], wlo[4][4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int mm = m00 + (e >> 1) * p.TW + (e & 1);
-            const uint32_t off = mm * 128 + ((cgp ^ (mm & 7)) << 4);
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wh[e][0]), "=r"(wh[e][1]), "=r"(wh[e][2]), "=r"(wh[e][3]) : "r"(sb_hi + off));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wlo[e][0]), "=r"(wlo[e][1]), "=r"(wlo[e][2]), "=r"(wlo[e][3]) : "r"(sb_lo + off));
-          }
-          uint32_t bits = 0, oh_w[4], ol_w[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int par = 0; par < 2; ++par) {        // the two channels packed in word k
-              float fv[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                fv[e] = par ? bf16_hi(wh[e][k]) + bf16_hi(wlo[e][k]) : bf16_lo(wh[e][k]) + bf16_lo(wlo[e][k]);
-              const float mx = fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3]));
-              int win = 3;
-#pragma unroll
-              for (int e = 3; e >= 0; --e)
-                if (fv[e] == mx) { bits |= 1u << (16 * par + 4 * k + e); win = e; }
-              const uint32_t sh = par ? 0xFFFF0000u : 0x0000FFFFu;
-              if (par == 0) { oh_w[k] = wh[win][k] & sh; ol_w[k] = wlo[win][k] & sh; }
-              else { oh_w[k] |= wh[win][k] & sh; ol_w[k] |= wlo[win][k] & sh; }
-            }
-          }
-          const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + ph) * p.PW + pw;
-          const int cch = n0 + chunk * 64 + cgp * 8;
-          stg_v4(p.pooled + ppix * cpp + cch, make_uint4(oh_w[0], oh_w[1], oh_w[2], oh_w[3]));
-          stg_v4(p.pooled + ppix * cpp + p.Cout + cch, make_uint4(ol_w[0], ol_w[1], ol_w[2], ol_w[3]));
-          if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+          for (int j = 0; j < 2; ++j)
+            stg_v4(o + 8 * j, make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
         }
       }
     }
   }
-  if (issuer && elect_one_sync()) tma_store_wait_read<0>();
 }
 
 template <int BN>
@@ -583,11 +512,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
     prefetch_tmap(&p.tm_w);
-    if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -676,8 +604,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    if (Cfg::kTmaStore && p.split) conv_epilogue_split<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (BN >= 64 && p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -715,7 +643,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
   const uint32_t b_bytes_total = static_cast<uint32_t>(9 * p.n_cblk) * Cfg::kBBlockBytes;   // resident filter bank
   const uint32_t smem_stage_out = b_ring + b_bytes_total;
-  const uint32_t bars = smem_stage_out + (Cfg::kTmaStore ? static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes : 0u);
+  const uint32_t bars = smem_stage_out + static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes;
   auto a_full = [&](int i) { return bars + 8u * i; };
   auto a_empty = [&](int i) { return bars + 8u * (4 + i); };
   auto tmem_full_bar = [&](int i) { return bars + 8u * (24 + i); };
@@ -729,12 +657,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
     prefetch_tmap(&p.tm_w);
-    if (Cfg::kTmaStore) prefetch_tmap(&p.tm_out);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -770,6 +697,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
           const int ia = (iter & 1) * n_half + lstep % n_half;
           const uint32_t pa = (lstep / n_half) & 1u;
           mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
+          if (p.dbg & 1) { mbar_arrive(a_full(ia)); continue; }       // tuning: no activation loads
           mbar_arrive_expect_tx(a_full(ia), a_bytes);
           int src = 0, cbl = cb;
           while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
@@ -811,6 +739,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
           const uint64_t b0 = make_smem_desc(b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
+            if (p.dbg & 2) break;                                       // tuning: no MMAs
             const uint64_t a_desc = a0 + (tap / 3) * pitch8 + (tap % 3) * 8u;
             const uint64_t b_desc = b0 + tap * b_tap;
 #pragma unroll
@@ -825,8 +754,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    if (Cfg::kTmaStore && p.split) conv_epilogue_split<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (BN >= 64 && p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -1018,8 +947,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       p.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * 128 + 1023) / 1024 * 1024;
       const int total = 227 * 1024 - 256;
       p.b_resident = 1; p.n_b = 0; p.g_b = 1;
-      p.n_stage_buf = BN >= 64 ? 2 : 0;
-      if (BN >= 64 && total - b_all - 2 * kStagingBytes < 3 * p.a_blk_bytes) p.n_stage_buf = 1;
+      p.n_stage_buf = fuse_pool ? 2 : 0;
       const int staging = p.n_stage_buf * kStagingBytes;
       p.n_a = (total - b_all - staging) / p.a_blk_bytes;
       p.n_a = p.n_a >= 4 ? 4 : (p.n_a >= 2 ? 2 : 0);      // two sub-rings (one per MMA warp)
@@ -1046,11 +974,6 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.split = d->split;
   const int K = d->R * d->S * Cin;
   if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN)) return -1;
-  if (BN >= 64 && !fuse_pool) {
-    if (encode_nhwc(&p.tm_out, d->out, d->N, d->OH, d->OW, d->split ? 2 * d->Cout : d->Cout, p.TH, p.TW)) return -1;
-  } else {
-    p.tm_out = p.tm_src[0];
-  }
   p.bias = d->bias;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;

@@ -1,0 +1,88 @@
+"""Synthetic CamVid-shaped inputs and random-init weights (the benchmark recipe).
+
+There is no network for datasets or checkpoints, so bench.py and smoke runs use seeded synthetic
+data of the reference's shapes: images U[0,1) (B,3,H,W) (`return_0_255=False`,
+iterative_inference.py:117-118), one-hot float32 targets with a void channel (B,C+1,H,W)
+(`target_var[:, :void]`, iterative_inference.py:125), and weights drawn with Lasagne's initialisers
+in the positional checkpoint order of models/fcn8.py:177-180 / models/DAE_h.py:52-57.  The recipe
+(He-uniform FCN8 with the `upsample` kernel scaled so y0 is peaky, GlorotUniform zero-bias DAE with
+the last conv scaled so the iterated map is contractive) is part of the benchmark definition; the
+test oracle carries an independent copy (oracle/weights.py) and tests/test_host_logic.py checks
+that both produce identical tensors.
+"""
+import numpy as np
+import torch
+
+_VGG = [('conv1_1', 64), ('conv1_2', 64), ('conv2_1', 128), ('conv2_2', 128), ('conv3_1', 256), ('conv3_2', 256),
+        ('conv3_3', 256), ('conv4_1', 512), ('conv4_2', 512), ('conv4_3', 512), ('conv5_1', 512), ('conv5_2', 512),
+        ('conv5_3', 512)]
+
+
+def fcn8_shapes(nb_in_channels, n_classes):
+    """(name, W shape, b shape) of the 21 parameterised FCN8 layers (models/fcn8.py:33-110)."""
+    out, cin = [], nb_in_channels
+    for name, cout in _VGG:
+        out.append((name, (cout, cin, 3, 3), (cout,)))
+        cin = cout
+    c = n_classes
+    out += [('fc6', (4096, 512, 7, 7), (4096,)), ('fc7', (4096, 4096, 1, 1), (4096,)),
+            ('score_fr', (c, 4096, 1, 1), (c,)), ('score2', (c, c, 4, 4), (c,)),
+            ('score_pool4', (c, 512, 1, 1), (c,)), ('score4', (c, c, 4, 4), (c,)),
+            ('score_pool3', (c, 256, 1, 1), (c,)), ('upsample', (c, c, 16, 16), (c,))]
+    return out
+
+
+def dae_shapes(n_classes, nb_features_to_concat, n_filters=64, concat_h=('pool4',), additional_pool=2):
+    """(name, W shape, b shape) of DAE_h's convs: conv1_1..convP_1 (models/fcn_down.py:96-104) then
+    up_convP..up_conv1 (models/fcn_up.py:29-34,84-86)."""
+    last = concat_h[-1]
+    n_pool = int(last[-1]) if 'pool' in last else 0
+    total = n_pool + additional_pool
+    out, widths, cin = [], [], n_classes + (nb_features_to_concat if last == 'input' else 0)
+    f = n_filters
+    for p in range(total):
+        if p < 6:
+            f = n_filters * 2 ** p
+        out.append(('conv%d_1' % (p + 1), (f, cin, 3, 3), (f,)))
+        widths.append(f)
+        cin = f + (nb_features_to_concat if (p + 1 == n_pool and n_pool > 0) else 0)
+    up_in = widths[-1]
+    for p in range(total, 0, -1):
+        n_cl = n_classes if p == 1 else widths[p - 2]
+        out.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
+        up_in = n_cl
+    return out
+
+
+def _uniform(shape, a, gen):
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * a
+
+
+def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
+    """lasagne.init.HeUniform (a = sqrt(6 / fan_in)) W, zero b; `upsample` W x logit_gain."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, ws, bs in fcn8_shapes(nb_in_channels, n_classes):
+        W = _uniform(ws, np.sqrt(6.0 / int(np.prod(ws[1:]))), gen)
+        params += [W * logit_gain if name == 'upsample' else W, torch.zeros(bs)]
+    return params
+
+
+def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64, concat_h=('pool4',),
+                         additional_pool=2, out_gain=1.0):
+    """lasagne.init.GlorotUniform (a = sqrt(6 / ((n_out + n_in) * kh * kw))) W, zero b; `up_conv1` W x out_gain."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, ws, bs in dae_shapes(n_classes, nb_features_to_concat, n_filters, concat_h, additional_pool):
+        W = _uniform(ws, np.sqrt(6.0 / ((ws[0] + ws[1]) * int(np.prod(ws[2:])))), gen)
+        params += [W * out_gain if name == 'up_conv1' else W, torch.zeros(bs)]
+    return params
+
+
+def synthetic_batch(B, H, W, n_classes=11, seed=0):
+    """X (B,3,H,W) U[0,1); one-hot float32 targets (B, n_classes+1, H, W), label n_classes = void; labels."""
+    gen = torch.Generator().manual_seed(seed)
+    X = torch.rand((B, 3, H, W), generator=gen, dtype=torch.float32)
+    lab = torch.randint(0, n_classes + 1, (B, H, W), generator=gen)
+    L = torch.nn.functional.one_hot(lab, n_classes + 1).permute(0, 3, 1, 2).float()
+    return X, L.contiguous(), lab

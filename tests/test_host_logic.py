@@ -85,3 +85,17 @@ def test_two_rank_metric_allreduce_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('ok') == 2
+
+
+def test_synthetic_recipe_matches_oracle_copy():
+    """bench.py draws its synthetic weights / data from the product package; the oracle keeps an
+    independent copy.  Both must produce identical tensors or parity tests and the bench diverge."""
+    import torch
+    from oracle import weights as OW
+    from iterative_inference_segm_b200 import synthetic as S
+    for a, b in zip(S.synthetic_fcn8_params(3, 11, seed=0, logit_gain=10.0), OW.synthetic_fcn8_params(3, 11, seed=0, logit_gain=10.0)):
+        assert torch.equal(a, b)
+    for a, b in zip(S.synthetic_dae_params(11, 512, seed=1, out_gain=0.1), OW.synthetic_dae_params(11, 512, seed=1, out_gain=0.1)):
+        assert torch.equal(a, b)
+    for a, b in zip(S.synthetic_batch(2, 12, 16, 11, seed=7), OW.synthetic_batch(2, 12, 16, 11, seed=7)):
+        assert torch.equal(a, b)

@@ -44,9 +44,9 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int reps = 2048;
-  int Ns[4] = {16, 64, 128, 256}, shifts[5] = {0, 1, 2, 4, 8};
+  int Ns[4] = {16, 64, 128, 256}, shifts[8] = {0, 1, 2, 8, 64, 65, 66, 130};
   for (int ni = 0; ni < 4; ++ni)
-    for (int si = 0; si < 5; ++si) {
+    for (int si = 0; si < 8; ++si) {
       long long h = 0;
       for (int rep = 0; rep < 2; ++rep) { k<<<1, 128, 64 * 1024>>>(d, Ns[ni], shifts[si], reps); cudaDeviceSynchronize(); }
       cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
