@@ -248,6 +248,70 @@ __device__ __forceinline__ void epi_bar(int grp) {
   asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 }
 
+// 16-channel outputs (score maps, logits; BN == 16): the MMA main loop of such a tile is short, so all
+// 8 warps drain every tile together (TMEM lane quadrant q = warp % 4, the two warps of a quadrant take
+// 8 channels each) and stage = tile parity; tmem_empty expects all 256 epilogue threads.
+__device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                                uint32_t tmem_empty_bar0, int warp, int lane) {
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int macc = q * 32 + lane;
+  const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+  const bool in_box = (hl < p.TH) && (wl < p.TW);
+  int iter = 0;
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+    const TileCoord tc = decode_tile(p, t);
+    const int as = iter & 1;
+    const uint32_t aphase = (iter >> 1) & 1u;
+    const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+    const int cbase = half * 8;
+    uint4 a0 = make_uint4(0, 0, 0, 0);
+    const bool has_add = (p.addend != nullptr) && valid;
+    if (has_add) a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
+    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * 16) + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t v[8];
+    tmem_ld_x8(taddr + half * 8, v);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    mbar_arrive(tmem_empty_bar0 + 8u * as);
+    float f[8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + 1);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+    }
+    if (has_add) {
+      const uint32_t aw[4] = {a0.x, a0.y, a0.z, a0.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { f[2 * j] += bf16_lo(aw[j]); f[2 * j + 1] += bf16_hi(aw[j]); }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (valid) {
+      if (p.out_f32) {
+        float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                       __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
+        stg_v4(o, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                             pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
+      }
+    }
+  }
+}
+
 template <int BN, bool kSplit>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
                                               uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
@@ -436,52 +500,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
       }
       if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 6);
     } else {
-      // 16-channel outputs (score maps, logits): one 64-byte fp32 (or 32-byte bf16) row per thread
-      static_assert(BN == 16 || BN >= 64, "direct-store epilogue is written for BN == 16");
-      uint4 a01[2];
-      const bool has_add = (p.addend != nullptr) && valid;
-      if (has_add) { a01[0] = ldg_nc_v4(p.addend + apix * p.Cout); a01[1] = ldg_nc_v4(p.addend + apix * p.Cout + 8); }
-      mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
-      tcgen05_fence_after();
-      uint32_t v[16];
-      tmem_ld_x16(taddr, v);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(tmem_empty_bar);
-      float f[16];
-#pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-        f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-        f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
-      }
-      if (has_add) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t aw[4] = {a01[j].x, a01[j].y, a01[j].z, a01[j].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { f[8 * j + 2 * k] += bf16_lo(aw[k]); f[8 * j + 2 * k + 1] += bf16_hi(aw[k]); }
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (valid) {
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + n0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3])));
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + n0;
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            stg_v4(o + 8 * j, make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
-        }
-      }
+      // (BN == 16 is handled by conv_epilogue16 above)
     }
   }
 }
@@ -515,7 +534,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads / 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -604,7 +623,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    if (BN >= 64 && p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else if (p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
@@ -661,7 +681,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads / 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -754,7 +774,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    if (BN >= 64 && p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else if (p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 

@@ -6,7 +6,7 @@
 // streaming: NHWC bf16, one thread per (window, 8 channels), 16-byte vector
 // accesses, channel-fastest thread order so a warp touches contiguous bytes.
 //   pool  : reads 4 x 16 B, writes 16 B pooled + 4 B mask (8 nibbles)
-//   unpool: one thread per (output row, pooled column, 8 channels): reads 16 B + 4 B, writes 2 x 16 B
+//   unpool: one thread per (pooled pixel, 8 channels): reads 16 B + 4 B, writes 4 x 16 B
 #include "common.cuh"
 #include "../../include/iiseg.h"
 
@@ -46,35 +46,35 @@ __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restr
 // pixels in the trailing odd row / column of the HxW map (no pool window) are zero.
 struct UnpoolParams {
   const uint4* u; const uint32_t* mask; uint4* out;
-  int C8, MC8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN;   // MC8: channel groups of the mask (C8, or C8/2 for split pairs)
-  long long total;
+  int C8, MC8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN, PHN;   // MC8: channel groups of the mask (C8, or C8/2 for split pairs)
 };
 
+// One thread per (pooled pixel touched by the window, 8 channels): u and the mask word are read ONCE
+// and gate the (up to) 2x2 output pixels they feed.  grid = (ceil(PWN*C8/256), PHN, N): no 64-bit
+// index arithmetic, consecutive threads walk the channels of a pixel, so every load and store
+// instruction of a warp covers whole 128-byte lines.
 __global__ void __launch_bounds__(256) unpool2_mask_kernel(const UnpoolParams p) {
-  // one thread per (output row, pooled column touched by the window, 8 channels): u and the mask
-  // word are read once for the (up to) two output pixels of that row they feed
-  const int pw_first = p.o_w0 >> 1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int cg = (int)(t % p.C8); t /= p.C8;
-    const int pc = (int)(t % p.PWN); t /= p.PWN;
-    const int oh = (int)(t % p.OH);
-    const long long n = t / p.OH;
-    const int fh = oh + p.o_h0;                           // full-resolution row
-    const int ph = fh >> 1, pw = pw_first + pc;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    uint32_t bits = 0;
-    if (ph < p.H2 && pw < p.W2) {
-      val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.C8 + cg);
-      bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.MC8 + (cg >= p.MC8 ? cg - p.MC8 : cg));
-    }
-    const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.PWN * p.C8) return;
+  const int pc = idx / p.C8, cg = idx - pc * p.C8;
+  const int ph = (p.o_h0 >> 1) + blockIdx.y, pw = (p.o_w0 >> 1) + pc;
+  const size_t n = blockIdx.z;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  uint32_t bits = 0;
+  if (ph < p.H2 && pw < p.W2) {
+    val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.C8 + cg);
+    bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.MC8 + (cg >= p.MC8 ? cg - p.MC8 : cg));
+  }
+  const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int oh = 2 * ph + dy - p.o_h0;
+    if (oh < 0 || oh >= p.OH) continue;
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
       const int ow = 2 * pw + dx - p.o_w0;
       if (ow < 0 || ow >= p.OW) continue;
-      const int pos = ((fh & 1) << 1) | dx;
+      const int pos = (dy << 1) | dx;
       uint32_t r[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) r[k] = w[k] & tie_select(bits, k, pos);
@@ -125,9 +125,11 @@ extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask
   p.u = reinterpret_cast<const uint4*>(u); p.mask = mask; p.out = reinterpret_cast<uint4*>(out);
   p.MC8 = C / 8; p.C8 = split ? 2 * p.MC8 : p.MC8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
   p.OH = OH; p.OW = OW; p.o_h0 = o_h0; p.o_w0 = o_w0;
-  p.PWN = (o_w0 + OW - 1) / 2 - o_w0 / 2 + 1;     // pooled columns the window touches (incl. a trailing odd one)
-  p.total = (long long)N * OH * p.PWN * p.C8;
-  unpool2_mask_kernel<<<stream_grid(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  p.PWN = (o_w0 + OW - 1) / 2 - o_w0 / 2 + 1;     // pooled columns / rows the window touches (incl. a trailing odd one)
+  p.PHN = (o_h0 + OH - 1) / 2 - o_h0 / 2 + 1;
+  IISEG_CHECK(p.PHN <= 65535 && N <= 65535, "unpool: window too tall (%d pooled rows) or batch too large", p.PHN);
+  dim3 grid(ceil_div(p.PWN * p.C8, 256), p.PHN, N);
+  unpool2_mask_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
