@@ -88,6 +88,10 @@ typedef struct iiseg_conv_desc {
   const void* addend; /* NHWC bf16 [N,AH,AW,Cout]; addend[oh+ah0, ow+aw0] is added
                        * before the store (skip-sum with a cropped partner), or NULL */
   int AH, AW, ah0, aw0;
+  /* addend_f32 = 1: `addend` is fp32 [N,AH,AW,Cout] and is added before the ReLU in fp32 (Cout %
+   * 64 == 0).  Used to hoist the iteration-invariant half of a concat conv out of the loop:
+   * conv(concat(h, x)) = conv_h(h) + b (computed once, out_f32) + conv_x(x) (every iteration). */
+  int addend_f32;
   /* Fused Pool2DLayer(2) (+ DePool2D mask): when `pooled` != NULL the conv output is max-pooled
    * 2x2/stride 2 (floor) in the epilogue and only `pooled` [N,OH/2,OW/2,Cout] bf16 and, if
    * non-NULL, `pool_mask` [N,OH/2,OW/2,Cout/8] (nibble layout of iiseg_maxpool2_mask_fwd) are
@@ -104,7 +108,7 @@ typedef struct iiseg_conv_desc {
    * pool and tie mask compare hi+lo.  The caller feeds (hi | lo | hi) activation sources against
    * (W_hi | W_hi | W_lo) weights, so the GEMM accumulates hi*hi + lo*hi + hi*lo in fp32.        */
   int split;
-  int out_f32;        /* 1: fp32 output (only Cout == 16)                   */
+  int out_f32;        /* 1: fp32 output [N,OH,OW,Cout] (no pool, no split)      */
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
 

@@ -118,9 +118,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     else:
         _chk(out, F32 if out_f32 else BF16, 'out')
         assert tuple(out.shape) == (N, OH, OW, cm * Cout), (tuple(out.shape), (N, OH, OW, cm * Cout))
+    addend_f32 = addend is not None and addend.dtype == F32     # hoisted fp32 term (see iiseg_conv_desc.addend_f32)
     if addend is not None:
-        _chk(addend, BF16, 'addend')
-        assert addend.shape[0] == N and addend.shape[3] == cm * Cout
+        _chk(addend, F32 if addend_f32 else BF16, 'addend')
+        assert addend.shape[0] == N and addend.shape[3] == (Cout if addend_f32 else cm * Cout)
         assert addend_off[0] + OH <= addend.shape[1] and addend_off[1] + OW <= addend.shape[2]
     d = _lib.ConvDesc(N=N, H=H, W=W, weight=weight.data_ptr(), bias=bias.data_ptr(),
                       Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
@@ -130,7 +131,7 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       pool_mask=pool_mask.data_ptr() if pool_mask is not None else None,
                       pool_H=pool_hw[0] if pooled is not None else 0, pool_W=pool_hw[1] if pooled is not None else 0,
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
-                      ah0=addend_off[0], aw0=addend_off[1],
+                      ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
     # the channel-concatenated source views, in K order: (pointer, channels, channels per pixel in memory)
     srcs = [(src0, C0)] + ([(src1, C1)] if src1 is not None else [])

@@ -86,6 +86,7 @@ struct alignas(64) ConvParams {
   int PH, PW;                // pooled tensor extent
   int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
+  int addend_f32;           // the skip-sum / hoisted-term operand is fp32 [N,AH,AW,Cout] (BN >= 64 epilogue only)
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores
 };
@@ -337,7 +338,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
 
     if constexpr (BN >= 64) {
       // skip-sum operand of the first chunk: requested before the accumulator is ready
-      const bool has_add = (p.addend != nullptr) && valid && !(p.dbg & 8);
+      const bool has_add = (p.addend != nullptr) && !p.addend_f32 && valid && !(p.dbg & 8);
+      const bool has_add32 = (p.addend != nullptr) && p.addend_f32 && valid;
       const __nv_bfloat16* arow = p.addend + apix * cpp + n0;
       uint4 add[kSplit ? 8 : 4];
       if (has_add) {
@@ -380,6 +382,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
           f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
           f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
         }
+        if (has_add32) {      // fp32 operand (the hoisted iteration-invariant term of a concat conv): exact fp32 add
+          const float* a32 = reinterpret_cast<const float*>(p.addend) + apix * p.Cout + cbase;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 t = ldg_nc_v4(a32 + 4 * j);
+            f[4 * j] += __uint_as_float(t.x); f[4 * j + 1] += __uint_as_float(t.y);
+            f[4 * j + 2] += __uint_as_float(t.z); f[4 * j + 3] += __uint_as_float(t.w);
+          }
+        }
         if (has_add) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -404,7 +415,17 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
           if (kSplit) lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), b - bf16_hi(hi[j]));
           else if (p.relu) hi[j] = bf16x2_max(hi[j], 0u);
         }
-        if (p.pooled == nullptr) {
+        if (p.out_f32) {          // fp32 rows (the hoisted term itself): 128 contiguous bytes per thread
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = f[4 * j], b = f[4 * j + 1], c = f[4 * j + 2], d = f[4 * j + 3];
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); d = fmaxf(d, 0.f); }
+              stg_v4(o + 4 * j, make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d)));
+            }
+          }
+        } else if (p.pooled == nullptr) {
           if (valid && !(p.dbg & 16)) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * cpp + cbase;
 #pragma unroll
@@ -927,7 +948,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   }
   IISEG_CHECK(d->split == 0 || (d->out_f32 == 0 && d->Cout % 64 == 0), "conv: split output needs a bf16 output with Cout %% 64 == 0");
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
-  IISEG_CHECK(d->out_f32 == 0 || d->Cout == 16, "conv: fp32 output only for Cout == 16");
+  IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
   const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
@@ -1013,7 +1034,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.inv_ntiles = 1.0f / p.n_ntiles; p.inv_tiles_w = 1.0f / p.tiles_w; p.inv_tiles_h = 1.0f / p.tiles_h;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
-  p.relu = d->relu; p.out_f32 = d->out_f32;
+  p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
   {
     static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;
     static const int env_stages = getenv("IISEG_CONV_STAGES") ? atoi(getenv("IISEG_CONV_STAGES")) : 0;

@@ -56,14 +56,23 @@ class DAENet(object):
             self.filters.append(f)
         assert all(f % 64 == 0 for f in self.filters), 'n_filters must be a multiple of 64'
         self.down, self.up = [], []
+        self.hproj_w = None
         cin_real, cin_pad = n_classes, self.y_cpad
         for p in range(self.total):
             W, b = params[2 * p], params[2 * p + 1]
-            if p == self.n_pool:   # first conv after the concat: h channels come first
-                splits = [(self.nb_h, self.h_pad), (cin_real, cin_pad)]
+            if p == self.n_pool:
+                # First conv after ConcatLayer((h, pool_n)) (h channels first, models/model_helpers.py:93-94).
+                # conv(concat(h, x)) = [conv_h(h) + b] + conv_x(x): the bracket does not change between
+                # iterations, so it is computed once per batch in fp32 (`hproj`) and enters the per-iteration
+                # conv as an fp32 epilogue addend; the loop only runs the x half of the K range.
+                Wt = torch.as_tensor(W)
+                self.hproj_w = pack_conv(Wt[:, :self.nb_h], b, [(self.nb_h, self.h_pad)], self.filters[p], self.device,
+                                         split=self.split)
+                Wx, _ = pack_conv(Wt[:, self.nb_h:], b, [(cin_real, cin_pad)], self.filters[p], self.device,
+                                  split=self.split)
+                self.down.append((Wx, torch.zeros(self.filters[p], dtype=torch.float32, device=self.device)))
             else:
-                splits = [(cin_real, cin_pad)]
-            self.down.append(pack_conv(W, b, splits, self.filters[p], self.device, split=self.split))
+                self.down.append(pack_conv(W, b, [(cin_real, cin_pad)], self.filters[p], self.device, split=self.split))
             cin_real = cin_pad = self.filters[p]
         up_in = self.filters[-1]
         for i, p in enumerate(range(self.total, 0, -1)):
@@ -137,9 +146,11 @@ class DAENet(object):
         fl = []
         cin = self.n_classes
         for p in range(self.total):
-            c = cin + (self.nb_h if p == self.n_pool else 0)
             hl, hh, wl, wh = D[p + 1] if steady_state else (0, sizes[p][0], 0, sizes[p][1])
-            fl.append(2.0 * (hh - hl) * (wh - wl) * c * self.filters[p] * 9)
+            f = 2.0 * (hh - hl) * (wh - wl) * cin * self.filters[p] * 9
+            if p == self.n_pool and not steady_state:    # the hoisted h half runs once, with the first iteration
+                f += 2.0 * sizes[p][0] * sizes[p][1] * self.nb_h * self.filters[p] * 9
+            fl.append(f)
             cin = self.filters[p]
         up_in = self.filters[-1]
         for p in range(self.total, 0, -1):
@@ -171,6 +182,8 @@ class DAENet(object):
                 hl, hh, wl, wh = Wc[p]
                 assert sizes[p - 1] == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
                 ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.cm * self.filters[p - 2]), dtype=bf, device=dev)
+        hp = sizes[self.n_pool]
+        ws['hproj'] = torch.empty((B, hp[0], hp[1], self.filters[self.n_pool]), dtype=torch.float32, device=dev)
         ws['logits'] = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
         self._ws[key] = ws
         return ws
@@ -191,6 +204,9 @@ class DAENet(object):
         sp = self.split
         x = y_bf16
         D = None if full_down else self.down_windows(H, W)
+        if full_down:       # new h: the iteration-invariant half of the concat conv, once per batch, fp32
+            K.conv2d(h_bf16, self.hproj_w[0], self.hproj_w[1], 3, 3, 1, relu=False, out=ws['hproj'], out_f32=True,
+                     split=sp)
         for p in range(self.total):
             Wk, bk = self.down[p]
             pad = self.padding if (p == 0 and self.padding > 0) else 1
@@ -201,8 +217,8 @@ class DAENet(object):
             # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
             # pre-pool map is consumed on chip and never written (nothing else reads it)
             if p == self.n_pool:
-                K.conv2d(h_bf16, Wk, bk, 3, 3, pad, relu=True, src1=x, window=win, pooled=ws['pool'][p],
-                         pool_mask=ws['mask'][p], split=sp)
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
+                         addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0), split=sp)
             else:
                 K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
                          split=sp)

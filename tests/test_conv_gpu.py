@@ -216,3 +216,33 @@ def test_conv_split_fused_pool_mask_is_exact(cuda, N, H, W, C, Cout, pad):
     us = K.pack_nchw(u, Cout, split=True)
     out = K.unpool2(us, mask, OH, OW, split=True)
     assert torch.equal(_recon(out).cpu(), L.depool2d(_recon(us).cpu(), full))
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_conv_hoisted_concat_half(cuda, split):
+    """conv(concat(h, x)) == [conv_h(h) + b] (fp32 output, computed once) + conv_x(x) with the bracket as an
+    fp32 epilogue addend: the hoist of the iteration-invariant half of DAE conv5_1
+    (models/model_helpers.py:93-94).  Both forms against an fp64 convolution of the same operands."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_conv
+    torch.manual_seed(6)
+    N, H, W, Ch, Cx, Cout = 2, 18, 22, 128, 64, 256
+    q = (lambda t: t) if split else (lambda t: t.to(torch.bfloat16).float())     # bf16 variant: compare on rounded operands
+    h, x = q(torch.randn(N, Ch, H, W, device=cuda)), q(torch.randn(N, Cx, H, W, device=cuda))
+    Wt = q(torch.randn(Cout, Ch + Cx, 3, 3, device=cuda) / (9 * (Ch + Cx)) ** 0.5)
+    b = torch.randn(Cout, device=cuda)
+    hs, xs = K.pack_nchw(h, Ch, split=split), K.pack_nchw(x, Cx, split=split)
+    Wh, bh = pack_conv(Wt[:, :Ch], b, [(Ch, Ch)], Cout, cuda, split=split)
+    Wx, _ = pack_conv(Wt[:, Ch:], b, [(Cx, Cx)], Cout, cuda, split=split)
+    Wc, bc = pack_conv(Wt, b, [(Ch, Ch), (Cx, Cx)], Cout, cuda, split=split)
+    hproj = K.conv2d(hs, Wh, bh, 3, 3, 1, relu=False, out_f32=True, split=split)
+    assert hproj.dtype == torch.float32 and tuple(hproj.shape) == (N, H, W, Cout)
+    win = (2, 4, 12, 16)
+    hoisted = K.conv2d(xs, Wx, torch.zeros_like(b), 3, 3, 1, relu=True, window=win, addend=hproj, addend_off=(2, 4),
+                       split=split)
+    concat = K.conv2d(hs, Wc, bc, 3, 3, 1, relu=True, src1=xs, window=win, split=split)
+    ref = torch.relu(F.conv2d(torch.cat([h, x], 1).double(), Wt.double(), b.double(), padding=1))[:, :, 2:14, 4:20]
+    tol = 1.5e-4 if split else 2.0 ** -7
+    for got in (hoisted, concat):
+        g = (_recon(got) if split else got.float().permute(0, 3, 1, 2)).double()
+        assert float(((g - ref).abs() / ref.abs().clamp(min=1.0)).max()) < tol
