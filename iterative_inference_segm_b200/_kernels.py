@@ -33,10 +33,11 @@ def require_device():
     _lib.call('iiseg_device_check', torch.cuda.current_device())
 
 
-def pad_channels(c, conv_input=True):
-    """Channel padding rule of the kernels: conv inputs are multiples of 64
-    (one 128-byte TMA row); small outputs (score maps / logits) are 16."""
-    if not conv_input and c <= 16:
+def pad_channels(c, conv_input=True, narrow=False):
+    """Channel padding rule of the kernels: conv inputs are multiples of 64 (one 128-byte TMA row);
+    small outputs (score maps / logits) are 16.  `narrow`: a <=16-channel input of a 3x3 conv may be
+    padded to 16 instead (32-byte rows, one K=16 MMA per tap; the halo-tile kernel, bf16 variant)."""
+    if (not conv_input or narrow) and c <= 16:
         return 16
     return (c + 63) // 64 * 64
 

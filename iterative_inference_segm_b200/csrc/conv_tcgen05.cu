@@ -74,9 +74,8 @@ struct alignas(64) ConvParams {
   int in_off_h, in_off_w;   // input row of tap r for local output row o: o + in_off_h + r
   int TH, TW;
   int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
-  int a_blk_bytes, n_a, n_b, g_b;   // halo kernel: A buffer size / count, B stage count, taps per B stage
-  int b_resident;           // halo kernel: all R*S*n_cblk weight blocks stay in smem for the whole launch
-  int n_stage_buf;          // halo kernel: pool staging buffers (2 = one per epilogue group with the fused pool, else 0)
+  int a_blk_bytes, n_a;     // halo kernel: halo-block size and ring depth
+  int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
   int OH, OW, Cout;
@@ -262,8 +261,8 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
   int iter = 0;
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
     const TileCoord tc = decode_tile(p, t);
-    const int as = iter & 1;
-    const uint32_t aphase = (iter >> 1) & 1u;
+    const int as = iter & (p.acc_stages - 1);                                       // acc_stages is 2 or 4
+    const uint32_t aphase = static_cast<uint32_t>(iter >> (p.acc_stages >> 1)) & 1u;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
@@ -313,12 +312,11 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
   }
 }
 
-template <int BN, bool kSplit>
+template <int BN, bool kSplit, bool kShflPool>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
                                               uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
   const int q = warp & 3;
   const int grp = (warp - 4) >> 2;
-  const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * grp, tmem_empty_bar = tmem_empty_bar0 + 8u * grp;
   const int macc = q * 32 + lane;         // accumulator row
   const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
   const bool in_box = (hl < p.TH) && (wl < p.TW);
@@ -328,13 +326,15 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
   const int cpp = kSplit ? 2 * p.Cout : p.Cout;      // channels per pixel of out / addend / pooled
   for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
     const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
-    const uint32_t aphase = (iter >> 1) & 1u;
+    const int as = iter & (p.acc_stages - 1);            // 2 or 4 stages: a stage has the parity of its tiles, i.e. of the group
+    const uint32_t aphase = static_cast<uint32_t>(iter >> (p.acc_stages >> 1)) & 1u;
+    const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * as, tmem_empty_bar = tmem_empty_bar0 + 8u * as;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
     const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
     const int n0 = tc.nt * BN;
-    const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp * BN) + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
 
     if constexpr (BN >= 64) {
       // skip-sum operand of the first chunk: requested before the accumulator is ready
@@ -350,7 +350,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         }
       }
       if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 4);
-      mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
+      mbar_wait(tmem_full_bar, aphase, p.diag, 4, as);
       tcgen05_fence_after();
       if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 5);
 #pragma unroll 1
@@ -433,6 +433,38 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               stg_v4(o + j * 8, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
               if (kSplit) stg_v4(o + p.Cout + j * 8, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
             }
+          }
+        } else if constexpr (kShflPool) {
+          // Fused Pool2DLayer(2) + tie mask on registers (pitch == 16, plain bf16 variant): accumulator row
+          // m = 16*hl + wl, so this warp holds box lines 2q and 2q+1 and the 2x2 window of pooled pixel
+          // (q, wl/2) is lanes {l, l^1, l^16, l^17}.  Max and tie bits travel by warp shuffle; the lane
+          // at window position 0 writes the pooled 64 bytes and the four mask words of the chunk.
+          uint32_t mx[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t t = bf16x2_max(hi[j], __shfl_xor_sync(0xffffffffu, hi[j], 1));
+            mx[j] = bf16x2_max(t, __shfl_xor_sync(0xffffffffu, t, 16));
+          }
+          const int pos = ((lane >> 4) << 1) | (lane & 1);            // window position 2*dy + dx of this lane
+          const uint32_t posbits = (1u << pos) | (1u << (16 + pos));
+          uint32_t word[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t part = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) part |= bf16x2_eq_mask(hi[4 * g + k], mx[4 * g + k]) & (posbits << (4 * k));
+            part |= __shfl_xor_sync(0xffffffffu, part, 1);
+            part |= __shfl_xor_sync(0xffffffffu, part, 16);
+            word[g] = part;
+          }
+          const int phw = ((tc.th * p.TH) >> 1) + (hl >> 1), pww = ((tc.tw * p.TW) >> 1) + (wl >> 1);   // inside the window
+          if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w) {
+            const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + p.p_h0 + phw) * p.PW + p.p_w0 + pww;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              stg_v4(p.pooled + ppix * p.Cout + cbase + j * 8, make_uint4(mx[4 * j], mx[4 * j + 1], mx[4 * j + 2], mx[4 * j + 3]));
+            if (p.pool_mask != nullptr)
+              stg_v4(p.pool_mask + ppix * (p.Cout >> 3) + (cbase >> 3), make_uint4(word[0], word[1], word[2], word[3]));
           }
         } else {
           // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112): the
@@ -645,8 +677,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     }
   } else if (warp >= 4) {
     if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else if (p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -658,24 +690,46 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------
-// Halo-tile main loop (3x3 filters): ONE activation load per 64-channel block.
+// Halo-tile main loop (3x3 filters): ONE activation load per channel block.
 //
 // The per-tap kernel above re-fetches the 128-pixel A box for each of the R*S taps, and every layer
-// whose k-block is short (Cout <= 128) ends up bound by L2->SM ingest (~64 B/clk/SM measured), not by
-// the tensor pipe.  Here the TMA box is the output tile plus its filter halo, (TH+R-1) x (TW+S-1)
-// pixels, loaded once per channel block; tap (r,s) is the SAME smem tile read through a UMMA
-// descriptor whose start address is advanced by (r*pitch + s) rows, pitch = TW+S-1.  A SWIZZLE_128B
-// descriptor may start at any row: the swizzle is a function of the absolute smem address and the
-// descriptor's base_offset stays 0 (tools/experiments/umma_shift_test.cu).  Accumulator row m is then
-// box pixel (m / pitch, m % pitch); the S-1 rows at the end of each line are junk and are dropped by
-// the epilogue.  The layer's whole filter bank (9 * n_cblk blocks, Cout == BN) is loaded once and stays
-// resident in smem; only halo tiles stream, through a ring of n_a buffers, so several tiles are in
-// flight and the TMA latency of these short-K layers is hidden.  Layers whose filter bank does not fit
-// (or whose maps are so small that the halo pitch wastes accumulator rows) use the per-tap kernel.
+// whose k-block is short (Cout <= 128) ends up bound by L2->SM ingest, not by the tensor pipe.  Here
+// the TMA box is the output tile plus its filter halo, (TH+2) x pitch pixels (pitch >= TW+2), loaded
+// once per channel block; tap (r,s) is the SAME smem tile read through a UMMA descriptor whose start
+// address is advanced by (r*pitch + s) rows.  A swizzled K-major descriptor may start at any row: the
+// swizzle is a function of the absolute smem address and the descriptor's base_offset stays 0
+// (tools/experiments/umma_shift_test.cu for SWIZZLE_128B, umma_shift32_test.cu for SWIZZLE_32B).
+// Accumulator row m is box pixel (m / pitch, m % pitch); columns >= TW of each line are junk and are
+// dropped by the epilogue.  The layer's whole filter bank (9 * n_cblk blocks, Cout == BN) is loaded once
+// and stays resident in smem; only halo tiles stream, through a ring of n_a buffers.
+//
+// KB = channels per K block: 64 (128-byte rows, SWIZZLE_128B, four K=16 MMAs per tap) or 16 (32-byte
+// rows, SWIZZLE_32B, ONE MMA per tap).  KB = 16 serves the DAE's first layer, whose input y has 11
+// real channels: padded to 64 it spent 36 MMAs per tile on 83 % zeros, padded to 16 it spends 9.
+//
+// Two warps issue alternate tiles into a ring of kAccStages TMEM accumulators (4 for BN <= 128, two per
+// issuer), so an issuer starts its next tile while its previous accumulator is still being drained by
+// its epilogue group and the tensor pipe never waits for an epilogue.  With the fused pool the box is fixed at
+// 8 x 14 outputs with pitch 16: the four pixels of a 2x2 window then sit in lanes {l, l^1, l^16, l^17}
+// of one epilogue warp and the pool + tie mask are warp shuffles on registers (no smem staging).
 // ---------------------------------------------------------------------------
-template <int BN>
+template <int BN, int KB>
+struct HaloCfg {
+  static constexpr int kRowBytes = KB * 2;
+  static constexpr int kBBlockBytes = BN * kRowBytes;
+  static constexpr int kAccStages = BN <= 128 ? 4 : 2;         // TMEM room; the launch picks 2 or 4 (ConvParams::acc_stages)
+  static constexpr int kCols = kAccStages * BN;
+  static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
+  static constexpr int kMaxA = 8;
+  // K-major swizzled smem descriptor template: SBO = 8 rows, version 1, SWIZZLE_128B (2) or SWIZZLE_32B (6)
+  static constexpr uint64_t kDescHi = (static_cast<uint64_t>((8 * kRowBytes) >> 4) << 32) | (1ull << 46) |
+                                      (static_cast<uint64_t>(KB == 64 ? 2 : 6) << 61);
+};
+
+template <int BN, int KB>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = HaloCfg<BN, KB>;
+  const int S = p.acc_stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the plan uses the full 227 KB: the dynamic segment must start 1024-aligned (no round-up slack)
   if ((smem_u32(smem_raw) & 1023u) != 0u) mbar_timeout(p.diag, 9, 0);
@@ -683,14 +737,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const uint32_t a_ring = smem_base;
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
   const uint32_t b_bytes_total = static_cast<uint32_t>(9 * p.n_cblk) * Cfg::kBBlockBytes;   // resident filter bank
-  const uint32_t smem_stage_out = b_ring + b_bytes_total;
-  const uint32_t bars = smem_stage_out + static_cast<uint32_t>(p.n_stage_buf) * kStagingBytes;
+  const uint32_t bars = b_ring + b_bytes_total;
   auto a_full = [&](int i) { return bars + 8u * i; };
-  auto a_empty = [&](int i) { return bars + 8u * (4 + i); };
-  auto tmem_full_bar = [&](int i) { return bars + 8u * (24 + i); };
-  auto tmem_empty_bar = [&](int i) { return bars + 8u * (26 + i); };
-  const uint32_t tmem_slot = bars + 8u * 28;
-  const uint32_t b_res_bar = bars + 8u * 29;
+  auto a_empty = [&](int i) { return bars + 8u * (Cfg::kMaxA + i); };
+  auto tmem_full_bar = [&](int i) { return bars + 8u * (2 * Cfg::kMaxA + i); };
+  auto tmem_empty_bar = [&](int i) { return bars + 8u * (2 * Cfg::kMaxA + 4 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * Cfg::kMaxA + 8);
+  const uint32_t b_res_bar = bars + 8u * (2 * Cfg::kMaxA + 9);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5;
@@ -702,7 +755,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
+    for (int i = 0; i < S; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -723,71 +776,72 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       const int n_blocks = 9 * n_cblk;
       mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
       for (int i = 0; i < n_blocks; ++i)
-        tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * kBlockK, 0);
-      // Halo tiles stream through two sub-rings of n_a/2 buffers: even tiles -> ring 0 (consumed by MMA
+        tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * KB, 0);
+      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.pitch) * Cfg::kRowBytes;
+      // Halo blocks stream through two sub-rings of n_a/2 buffers: even tiles -> ring 0 (consumed by MMA
       // warp 1), odd tiles -> ring 1 (warp 3), so every mbarrier has exactly one waiter walking its
       // phases in order (parity waits cannot tell phase k from phase k+2).
       const int n_half = p.n_a >> 1;
-      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.pitch) * 128u;
       int iter = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
         const TileCoord tc = decode_tile(p, t);
         const int h_base = tc.th * p.TH + p.in_off_h, w_base = tc.tw * p.TW + p.in_off_w;
         for (int cb = 0; cb < n_cblk; ++cb) {
           const int lstep = (iter >> 1) * n_cblk + cb;
-          const int ia = (iter & 1) * n_half + lstep % n_half;
-          const uint32_t pa = (lstep / n_half) & 1u;
-          mbar_wait(a_empty(ia), pa ^ 1u, p.diag, 5, ia);
-          if (p.dbg & 1) { mbar_arrive(a_full(ia)); continue; }       // tuning: no activation loads
-          mbar_arrive_expect_tx(a_full(ia), a_bytes);
-          int src = 0, cbl = cb;
-          while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
-          tma_load_4d(a_ring + ia * p.a_blk_bytes, &p.tm_src[src], a_full(ia), cbl * kBlockK, w_base, h_base, tc.n);
+          const int slot = (iter & 1) * n_half + lstep % n_half;
+          const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
+          mbar_wait(a_empty(slot), phase ^ 1u, p.diag, 5, slot);
+          if (p.dbg & 1) {
+            mbar_arrive(a_full(slot));                                   // tuning: no activation loads
+          } else {
+            mbar_arrive_expect_tx(a_full(slot), a_bytes);
+            int src = 0, cbl = cb;
+            while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
+            tma_load_4d(a_ring + slot * p.a_blk_bytes, &p.tm_src[src], a_full(slot), cbl * KB, w_base, h_base, tc.n);
+          }
         }
       }
     }
   } else if (warp == 1 || warp == 3) {
-    // ===================== MMA issuers (ping-pong) =====================
-    // Two warps alternate tiles: warp 1 owns accumulator stage 0 (even tiles), warp 3 stage 1 (odd
-    // tiles).  The barrier waits of one tile (~100+ cycles each even when already complete) then
-    // overlap the other warp's MMAs instead of idling the tensor pipe; the pipe executes both
-    // warps' MMAs in arrival order on independent accumulators.
+    // ===================== MMA issuers =====================
+    // Two warps alternate tiles (warp 1 even, warp 3 odd), each with its own halo sub-ring and its own
+    // accumulator stages (stage = tile index % S has the parity of the tile).  One warp's barrier waits
+    // and descriptor set-up overlap the other's MMAs; with S = 4 a warp can issue its next tile while its
+    // previous accumulator is still being drained, so the tensor pipe never waits for an epilogue.
     constexpr uint32_t idesc = make_instr_desc<BN>();
-    const int as = warp == 1 ? 0 : 1;
-    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-    const uint32_t pitch8 = static_cast<uint32_t>(p.pitch) * 8u;
+    const int w = warp == 1 ? 0 : 1;
+    const uint32_t row16 = Cfg::kRowBytes >> 4;                           // descriptor address units per smem row
     const uint32_t b_tap = static_cast<uint32_t>(n_cblk) * (Cfg::kBBlockBytes >> 4);
     const int n_half = p.n_a >> 1;
-    bool first = true;
-    for (int iter = as; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
-      const uint32_t aphase = (iter >> 1) & 1u;
+    mbar_wait(b_res_bar, 0, p.diag, 10, 0);
+    for (int iter = w; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+      const int as = iter & (S - 1);
+      const uint32_t aphase = static_cast<uint32_t>(iter >> (S >> 1)) & 1u;
       if (lane == 0) IISEG_STAMP(iter, 0);
       mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
       if (lane == 0) IISEG_STAMP(iter, 1);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
       for (int cb = 0; cb < n_cblk; ++cb) {
-        const int lstep = (iter >> 1) * n_cblk + cb;    // this warp's own sub-ring (see the producer)
-        const int ia = as * n_half + lstep % n_half;
-        const uint32_t pa = (lstep / n_half) & 1u;
-        mbar_wait(a_full(ia), pa, p.diag, 7, ia);
-        if (first) { mbar_wait(b_res_bar, 0, p.diag, 10, 0); first = false; }
+        const int lstep = (iter >> 1) * n_cblk + cb;
+        const int slot = w * n_half + lstep % n_half;
+        const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
+        mbar_wait(a_full(slot), phase, p.diag, 7, slot);
         tcgen05_fence_after();
         if (lane == 0 && cb == 0) IISEG_STAMP(iter, 2);
         if (elect_one_sync()) {
-          // 3x3 taps fully unrolled: tap (r,s) = the halo tile advanced by (r*pitch + s) rows of 128 B,
-          // i.e. +8*(r*pitch + s) in the descriptor's (address >> 4) field.  A SWIZZLE_128B descriptor
-          // may start on any row (base_offset stays 0): the swizzle is a function of the smem address.
-          const uint64_t a0 = make_smem_desc(a_ring + ia * p.a_blk_bytes);
-          const uint64_t b0 = make_smem_desc(b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes);
+          // 3x3 taps fully unrolled: tap (r,s) = the halo tile advanced by (r*pitch + s) rows
+          const uint64_t a0 = Cfg::kDescHi | static_cast<uint64_t>(((a_ring + slot * p.a_blk_bytes) >> 4) & 0x3FFFu);
+          const uint64_t b0 = Cfg::kDescHi | static_cast<uint64_t>(((b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes) >> 4) & 0x3FFFu);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (p.dbg & 2) break;                                       // tuning: no MMAs
-            const uint64_t a_desc = a0 + (tap / 3) * pitch8 + (tap % 3) * 8u;
+            const uint64_t a_desc = a0 + static_cast<uint32_t>((tap / 3) * p.pitch + (tap % 3)) * row16;
             const uint64_t b_desc = b0 + tap * b_tap;
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            for (int k = 0; k < KB / kUmmaK; ++k)
               umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(a_empty(ia));                                     // halo tile consumed
+          umma_commit(a_empty(slot));                                   // halo block consumed
           if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));         // accumulator ready
         }
         __syncwarp();
@@ -796,8 +850,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
     }
   } else if (warp >= 4) {
     if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else if (p.split) conv_epilogue<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else if (p.pooled != nullptr) conv_epilogue<BN, false, true>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN, false, false>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -828,32 +882,32 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 tensor seen as (C, W, H, N); box (64, TW, TH, 1); 128B swizzle; OOB reads give zeros.
-static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW, int Cs = 0) {
+static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW, int Cs = 0, int KB = 64) {
   if (Cs == 0) Cs = C;        // channels per pixel in memory (the view may cover only C of them)
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc N=%d H=%d W=%d C=%d box %dx%d) failed: %d", N, H, W, C, TH, TW, (int)r);
   return 0;
 }
 
 // [Cout][K] bf16 weights seen as (K, Cout); box (64, BN).
-static int encode_weight(CUtensorMap* tm, const void* base, int Cout, int K, int BN) {
+static int encode_weight(CUtensorMap* tm, const void* base, int Cout, int K, int BN, int KB = 64) {
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight Cout=%d K=%d BN=%d) failed: %d", Cout, K, BN, (int)r);
   return 0;
 }
@@ -887,7 +941,8 @@ static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_row
     for (int w = tw; w >= step && w > tw - 8; w -= step) {
       const int pitch = w + S - 1;
       const long rows = (long)(th + R - 1) * pitch;
-      if (pitch > 256 || th + R - 1 > 256 || rows > max_rows) continue;
+      const long rows_read = (long)(R - 1) * pitch + S - 1 + 128;      // last row the shifted descriptors touch
+      if (pitch > 256 || th + R - 1 > 256 || rows > max_rows || rows_read > max_rows) continue;
       const long tiles = (long)ceil_div(OW, w) * ceil_div(OH, th);
       if (best < 0 || tiles < best || (tiles == best && rows < best_rows)) { best = tiles; best_rows = rows; bh = th; bw = w; }
     }
@@ -897,15 +952,15 @@ static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_row
   return true;
 }
 
-template <int BN>
+template <int BN, int KB>
 static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_halo_kernel<BN><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  conv_halo_kernel<BN, KB><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -938,10 +993,12 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
   IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr), "conv: null tensor");
   IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
-  IISEG_CHECK(d->C[0] > 0 && d->C[0] % 64 == 0, "conv: C0=%d must be a positive multiple of 64", d->C[0]);
+  // K blocks of 64 channels (128-byte rows), or -- one 16-channel source, 3x3 filter, halo-tile kernel only -- of 16
+  const int KB = (d->C[0] == 16 && d->src[1] == nullptr) ? 16 : 64;
+  IISEG_CHECK(d->C[0] > 0 && d->C[0] % KB == 0, "conv: C0=%d must be 16 or a positive multiple of 64", d->C[0]);
   int Cin = 0;
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
-    IISEG_CHECK(d->C[i] >= 0 && d->C[i] % 64 == 0 && (d->C[i] == 0) == (d->src[i] == nullptr), "conv: bad source %d (C=%d)", i, d->C[i]);
+    IISEG_CHECK(d->C[i] >= 0 && d->C[i] % KB == 0 && (d->C[i] == 0) == (d->src[i] == nullptr), "conv: bad source %d (C=%d)", i, d->C[i]);
     IISEG_CHECK(d->Cs[i] == 0 || (d->Cs[i] >= d->C[i] && d->Cs[i] % 8 == 0), "conv: bad channel stride of source %d", i);
     IISEG_CHECK(i == 0 || d->C[i] == 0 || d->C[i - 1] > 0, "conv: sources must be packed from index 0");
     Cin += d->C[i];
@@ -972,50 +1029,56 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
   // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
   // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
-  const int n_cblk_all = Cin / 64;
-  bool halo = env_halo && d->R == 3 && d->S == 3 && !d->split;
+  const int n_cblk_all = Cin / KB;
+  bool halo = env_halo && d->R == 3 && d->S == 3 && !d->split && d->Cout == BN && BN <= 128;
   int box_h = 0, box_w = 0;       // TMA box extent in pixels
   int smem_halo = 0;
   if (halo) {
-    // shared-memory plan: n_a halo tiles + the resident filter bank + output staging (1 or 2 buffers)
-    const int b_blk = BN * 128;
-    const int b_all = d->R * d->S * n_cblk_all * b_blk;
-    halo = d->Cout == BN && choose_halo_box(covH, covW, d->R, d->S, fuse_pool, 256, &p.TH, &p.TW);
-    if (halo && env_halo != 2 && p.TH * p.TW < 100) halo = false;          // too many junk accumulator rows
+    // shared-memory plan: the resident filter bank + a ring of n_a halo blocks holding at least two tiles
+    const int row_b = KB * 2;
+    const int b_all = 9 * n_cblk_all * BN * row_b;
+    const int total = 227 * 1024 - 256;
+    const int budget_rows = (total - b_all) / (2 * n_cblk_all) / 1024 * 1024 / row_b;     // rows one block may take
+    if (fuse_pool) {
+      // pool + tie mask by warp shuffle: 8 x 14 outputs on a pitch-16 box (see conv_epilogue, kShflPool)
+      p.TH = 8; p.TW = 14; p.pitch = 16;
+      halo = budget_rows >= 2 * 16 + 2 + kBlockM;
+    } else {
+      halo = budget_rows > 0 && choose_halo_box(covH, covW, 3, 3, false, budget_rows < 512 ? budget_rows : 512, &p.TH, &p.TW);
+      if (halo && env_halo != 2 && p.TH * p.TW < 100) halo = false;        // too many junk accumulator rows
+      p.pitch = p.TW + 2;
+    }
     if (halo) {
-      p.pitch = p.TW + d->S - 1;
-      const int rows_box = (p.TH + d->R - 1) * p.pitch;
-      const int rows_read = (d->R - 1) * p.pitch + d->S - 1 + kBlockM;     // last row the shifted descriptors touch
-      p.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * 128 + 1023) / 1024 * 1024;
-      const int total = 227 * 1024 - 256;
-      p.b_resident = 1; p.n_b = 0; p.g_b = 1;
-      p.n_stage_buf = fuse_pool ? 2 : 0;
-      const int staging = p.n_stage_buf * kStagingBytes;
-      p.n_a = (total - b_all - staging) / p.a_blk_bytes;
-      p.n_a = p.n_a >= 4 ? 4 : (p.n_a >= 2 ? 2 : 0);      // two sub-rings (one per MMA warp)
-      if (p.n_a < 2) halo = false;      // filter bank too large to stay resident: per-tap kernel
-      box_h = p.TH + d->R - 1; box_w = p.pitch;
-      smem_halo = p.n_a * p.a_blk_bytes + b_all + staging + 256;
+      const int rows_box = (p.TH + 2) * p.pitch;
+      const int rows_read = 2 * p.pitch + 2 + kBlockM;                       // last row the shifted descriptors touch
+      p.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * row_b + 1023) / 1024 * 1024;
+      p.n_a = (total - b_all) / p.a_blk_bytes;
+      if (p.n_a > 8) p.n_a = 8;
+      { static const int env_na = getenv("IISEG_HALO_NA") ? atoi(getenv("IISEG_HALO_NA")) : 0; if (env_na >= 2 && p.n_a > env_na) p.n_a = env_na; }
+      p.n_a &= ~1;                               // two sub-rings, one per MMA-issuer warp
+      if (p.n_a < 2) halo = false;
+      box_h = p.TH + 2; box_w = p.pitch;
+      smem_halo = p.n_a * p.a_blk_bytes + b_all + 256;
     }
   }
+  IISEG_CHECK(halo || KB == 64, "conv: a 16-channel source needs a 3x3 filter with Cout in {16,64,128} (halo-tile kernel)");
   if (!halo) {
     choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
     p.pitch = p.TW;
-    p.n_stage_buf = 2;
     box_h = p.TH; box_w = p.TW;
   }
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
     if (d->src[i] != nullptr) {
-      if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i])) return -1;
+      if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i], KB)) return -1;
     } else {
       p.tm_src[i] = p.tm_src[0];
     }
-    p.n_cblk_src[i] = d->C[i] / 64;
+    p.n_cblk_src[i] = d->C[i] / KB;
   }
   p.n_cblk = n_cblk_all;
   p.split = d->split;
   const int K = d->R * d->S * Cin;
-  if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN)) return -1;
+  if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN, KB)) return -1;
   p.bias = d->bias;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
@@ -1036,17 +1099,29 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
   {
+    // halo kernel, BN 64/128: 4 accumulator stages (an issuer runs a tile ahead of its epilogue group);
+    // 16-channel outputs measured faster with 2 (0.087 vs 0.107 ms on up_conv1)
+    static const int env_s = getenv("IISEG_HALO_S") ? atoi(getenv("IISEG_HALO_S")) : 4;
+    p.acc_stages = (halo && BN >= 64 && env_s == 4) ? 4 : 2;
+  }
+  {
     static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;
     static const int env_stages = getenv("IISEG_CONV_STAGES") ? atoi(getenv("IISEG_CONV_STAGES")) : 0;
     p.dbg = env_dbg; p.stages = env_stages;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (halo) {
+    if (KB == 16) {
+      switch (BN) {
+        case 16: return launch_conv_halo<16, 16>(p, smem_halo, s);
+        case 64: return launch_conv_halo<64, 16>(p, smem_halo, s);
+        default: return launch_conv_halo<128, 16>(p, smem_halo, s);
+      }
+    }
     switch (BN) {
-      case 16: return launch_conv_halo<16>(p, smem_halo, s);
-      case 64: return launch_conv_halo<64>(p, smem_halo, s);
-      case 128: return launch_conv_halo<128>(p, smem_halo, s);
-      default: return launch_conv_halo<256>(p, smem_halo, s);
+      case 16: return launch_conv_halo<16, 64>(p, smem_halo, s);
+      case 64: return launch_conv_halo<64, 64>(p, smem_halo, s);
+      default: return launch_conv_halo<128, 64>(p, smem_halo, s);
     }
   }
   switch (BN) {

@@ -45,7 +45,7 @@ class DAENet(object):
         self.n_pool, self.total = _levels(concat_h, additional_pool)
         assert self.n_pool >= 1, 'conditioning must be concatenated at a pool layer'
         self.device = torch.device(device)
-        self.y_cpad = K.pad_channels(n_classes)           # channels of the bf16 copy of y
+        self.y_cpad = K.pad_channels(n_classes, narrow=not self.split)    # channels of the bf16 copy of y
         assert len(params) == 4 * self.total, 'expected %d arrays, got %d' % (4 * self.total, len(params))
         # filters per level: n_filters * 2**p, p < 6 (models/fcn_down.py:96-99)
         self.filters = []

@@ -55,7 +55,8 @@ class FCN8Net(object):
         cin = nb_in_channels
         for stage in VGG_STAGES:
             for name, cout in stage:
-                self.w[name] = pack_conv(*P[name], [(cin, K.pad_channels(cin))], cout, self.device, split=sp)
+                cpad = K.pad_channels(cin, narrow=(name == 'conv1_1' and not sp))
+                self.w[name] = pack_conv(*P[name], [(cin, cpad)], cout, self.device, split=sp)
                 cin = cout
         self.w['fc6'] = pack_conv(*P['fc6'], [(512, 512)], 4096, self.device, split=sp)
         self.w['fc7'] = pack_conv(*P['fc7'], [(4096, 4096)], 4096, self.device, split=sp)
@@ -75,7 +76,7 @@ class FCN8Net(object):
         assert Cin == self.nb_in_channels
         out = {}
         sp, cm = self.split, self.cm
-        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin), split=sp)
+        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=not sp), split=sp)
         for si, stage in enumerate(VGG_STAGES):
             for ci, (name, cout) in enumerate(stage):
                 Wk, bk = self.w[name]

@@ -23,6 +23,10 @@ CASES = [
     (1, 17, 21, 128, 0, 256, 7, 0, 1, 0, None, 0),
     (1, 11, 15, 256, 0, 16, 1, 0, 1, 0, None, 1),
     (4, 139, 169, 64, 0, 128, 3, 1, 1, 0, None, 0),
+    # 16-channel source: 32-byte rows, SWIZZLE_32B, one K=16 MMA per tap (halo-tile kernel)
+    (2, 37, 45, 16, 0, 64, 3, 1, 1, 0, None, 0),
+    (1, 24, 32, 16, 0, 64, 3, 100, 1, 0, None, 0),
+    (2, 30, 41, 16, 0, 128, 3, 1, 0, 0, (3, 5, 20, 30), 0),
 ]
 
 
@@ -55,10 +59,14 @@ def test_conv_matches_fp32_reference(cuda, case):
 
 
 @pytest.mark.parametrize('N,H,W,C,Cout,pad', [(2, 37, 45, 64, 128, 1), (1, 17, 21, 128, 256, 1), (1, 20, 24, 64, 64, 100),
-                                               (3, 8, 10, 64, 512, 1)])
+                                               (3, 8, 10, 64, 512, 1), (2, 37, 45, 16, 64, 1), (1, 20, 24, 16, 64, 100),
+                                               (2, 61, 47, 256, 64, 1)])
 def test_conv_fused_pool_equals_conv_then_pool(cuda, N, H, W, C, Cout, pad):
     """The pool fused in the conv epilogue is bit-identical to conv (bf16 out) followed by the
-    stand-alone pool + tie-mask kernel, including the dropped odd row/col."""
+    stand-alone pool + tie-mask kernel, including the dropped odd row/col.  Shapes are chosen so that
+    the pooled and the plain launch run the same main loop (halo-tile or per-tap kernel: their fp32
+    accumulation orders differ): shuffle pool on 64- and 16-channel halo tiles, smem-staged pool of
+    the per-tap kernel for BN = 64 / 256."""
     from iterative_inference_segm_b200 import _kernels as K
     torch.manual_seed(4)
     x = torch.randn(N, H, W, C, device=cuda).to(torch.bfloat16)
