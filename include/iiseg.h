@@ -109,6 +109,19 @@ typedef struct iiseg_conv_desc {
    * (W_hi | W_hi | W_lo) weights, so the GEMM accumulates hi*hi + lo*hi + hi*lo in fp32.        */
   int split;
   int out_f32;        /* 1: fp32 output [N,OH,OW,Cout] (no pool, no split)      */
+  /* Fused softmax tail + iterative-inference update (Cout == 16, the DAE's last conv up_conv1):
+   * when upd_y != NULL the logits are not stored; for every image n with upd_active[n] != 0 (NULL =
+   * all) the epilogue does  p = softmax over the first upd_C channels;  g = y - p;
+   * y <- clip(y - upd_step*g, 0, 1)  on the fp32 NCHW master upd_y [N,upd_C,OH,OW] in place, writes
+   * the bf16 NHWC copy upd_y_bf16 [N,OH,OW,upd_cpad], and adds sum_pixels ||g||_2 of image n, in
+   * 2^-40 fixed point, to upd_norm_acc[n] (models/fcn_up.py:154-169, iterative_inference.py:267-277;
+   * same arithmetic as iiseg_softmax_update).  iiseg_norm_finalize_fixed consumes upd_norm_acc. */
+  float* upd_y;
+  void* upd_y_bf16;
+  const int32_t* upd_active;
+  uint64_t* upd_norm_acc;
+  float upd_step;
+  int upd_C, upd_cpad;
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
 
@@ -179,6 +192,11 @@ int iiseg_softmax_grad(const float* logits, const float* y, float* grad, int N, 
 int iiseg_norm_finalize(const float* norm_partial, float* norm, int32_t* active,
                         int32_t* n_exec, int N, int H, int W, float eps,
                         void* stream);
+/* Same decision from the fixed-point accumulator of the fused conv epilogue (iiseg_conv_desc.upd_*):
+ * norm[n] = norm_acc[n] * 2^-40 / (H*W) for active images; norm_acc[n] is reset to 0. */
+int iiseg_norm_finalize_fixed(uint64_t* norm_acc, float* norm, int32_t* active,
+                              int32_t* n_exec, int N, int H, int W, float eps,
+                              void* stream);
 
 /* ---- metrics: metrics.py jaccard / accuracy / squared_error --------------
  * One pass over y (NCHW fp32 [N,C,H,W]) and the target, per image n with

@@ -75,7 +75,7 @@ def conv_out_size(H, W, R, S, pad):
 
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
-           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False):
+           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -83,7 +83,11 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     pooled) carries the (hi | lo) bf16 pair of an fp32 map, 2*C channels per pixel, and `weight` is
     packed by _packing.pack_conv(split=True) as [Cout, R*S*3*(C0+C1)] = per tap (W_hi | W_hi | W_lo):
     the loader walks (hi, lo, hi) views of the sources, so the unchanged bf16 tensor-core loop
-    accumulates hi*hi + lo*hi + hi*lo in fp32."""
+    accumulates hi*hi + lo*hi + hi*lo in fp32.
+
+    update = dict(y, y_bf16, active, norm_acc, step, C): the 16-channel logits conv with the softmax
+    tail and the iterative-inference update fused in its epilogue (iiseg_conv_desc.upd_*); nothing is
+    returned, y / y_bf16 / norm_acc are updated in place."""
     _chk(src0, BF16, 'src0')
     _chk(weight, BF16, 'weight')
     _chk(bias, F32, 'bias')
@@ -114,6 +118,13 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
             _chk(pool_mask, torch.int32, 'pool_mask')
             assert tuple(pool_mask.shape) == tuple(pooled.shape[:3]) + (Cout // 8,)
         assert out is None
+    elif update is not None:
+        _chk(update['y'], F32, 'update.y')
+        _chk(update['y_bf16'], BF16, 'update.y_bf16')
+        _chk(update['norm_acc'], torch.int64, 'update.norm_acc')
+        assert Cout == 16 and out is None and addend is None and not split
+        assert tuple(update['y'].shape) == (N, update['C'], OH, OW) and tuple(update['y_bf16'].shape[:3]) == (N, OH, OW)
+        assert update['norm_acc'].numel() == N
     elif out is None:
         out = torch.empty((N, OH, OW, cm * Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
     else:
@@ -134,6 +145,11 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if update is not None:
+        d.upd_y, d.upd_y_bf16 = update['y'].data_ptr(), update['y_bf16'].data_ptr()
+        d.upd_active = update['active'].data_ptr() if update.get('active') is not None else None
+        d.upd_norm_acc = update['norm_acc'].data_ptr()
+        d.upd_step, d.upd_C, d.upd_cpad = float(update['step']), int(update['C']), int(update['y_bf16'].shape[3])
     # the channel-concatenated source views, in K order: (pointer, channels, channels per pixel in memory)
     srcs = [(src0, C0)] + ([(src1, C1)] if src1 is not None else [])
     views = []
@@ -234,6 +250,14 @@ def softmax_grad(logits, y, grad):
     N, C_, H, W = y.shape
     _lib.call('iiseg_softmax_grad', _ptr(logits), _ptr(y), _ptr(grad), N, C_, H, W, _stream())
     return grad
+
+
+def norm_finalize_fixed(norm_acc, norm, active, n_exec, H, W, eps):
+    """norm / active / n_exec step from the fixed-point accumulator of the fused conv epilogue."""
+    _chk(norm_acc, torch.int64, 'norm_acc')
+    N = norm.shape[0]
+    _lib.call('iiseg_norm_finalize_fixed', _ptr(norm_acc), _ptr(norm), _ptr(active), _ptr(n_exec), N, H, W,
+              C.c_float(eps), _stream())
 
 
 def norm_finalize(norm_partial, norm, active, n_exec, H, W, eps):

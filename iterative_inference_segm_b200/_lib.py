@@ -30,6 +30,8 @@ class ConvDesc(C.Structure):
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int),
         ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
         ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int),
+        ('upd_y', C.c_void_p), ('upd_y_bf16', C.c_void_p), ('upd_active', C.c_void_p), ('upd_norm_acc', C.c_void_p),
+        ('upd_step', C.c_float), ('upd_C', C.c_int), ('upd_cpad', C.c_int),
     ]
 
 
@@ -67,6 +69,7 @@ SIGNATURES = {
     'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     'iiseg_softmax_grad': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'iiseg_norm_finalize_fixed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

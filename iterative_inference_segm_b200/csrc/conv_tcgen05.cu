@@ -83,6 +83,9 @@ struct alignas(64) ConvParams {
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
   uint32_t* pool_mask;       // tie-inclusive mask nibbles [N,PH,PW,Cout/8] or NULL
   int PH, PW;                // pooled tensor extent
+  // fused softmax + iterative-inference update (16-channel logits conv): see iiseg_conv_desc.upd_*
+  float* upd_y; __nv_bfloat16* upd_y_bf16; const int32_t* upd_active; unsigned long long* upd_norm_acc;
+  float upd_step; int upd_C, upd_cpad;
   int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
   int addend_f32;           // the skip-sum / hoisted-term operand is fp32 [N,AH,AW,Cout] (BN >= 64 epilogue only)
@@ -309,6 +312,85 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])));
       }
     }
+  }
+}
+
+// Logits conv with the softmax tail and the iterative-inference update fused in (BN == 16, upd_y != NULL):
+//   p = softmax_c(logits);  g = y - p;  y <- clip(y - step*g, 0, 1);  ||g||_2 accumulated per image
+// (models/fcn_up.py:154-169 + iterative_inference.py:267-277), for the images still active.  The fp32
+// logits never reach HBM: a thread owns one pixel (accumulator row) with all 16 columns, reads / writes
+// the C planes of the fp32 NCHW master y (lanes = consecutive pixels of a box line) and the bf16 NHWC
+// row the first conv of the next iteration reads.  The arithmetic is the stand-alone kernel's
+// (update.cu), operation for operation, so fused and unfused loops give bit-identical y.  The norm is
+// summed in 2^-40 fixed point with integer atomics: order-independent, hence deterministic.
+// The two warps of a TMEM lane quadrant alternate tiles (group g = tile parity = accumulator stage).
+__device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                                       uint32_t tmem_empty_bar0, int warp, int lane) {
+  const int q = warp & 3;
+  const int grp = (warp - 4) >> 2;
+  const int macc = q * 32 + lane;
+  const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+  const bool in_box = (hl < p.TH) && (wl < p.TW);
+  const int C = p.upd_C;
+  const size_t HW = static_cast<size_t>(p.OH) * p.OW;
+  float bias[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + j4);
+    bias[4 * j4] = b.x; bias[4 * j4 + 1] = b.y; bias[4 * j4 + 2] = b.z; bias[4 * j4 + 3] = b.w;
+  }
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+    const uint32_t aphase = static_cast<uint32_t>(iter >> 1) & 1u;       // two stages: stage = tile parity = grp
+    const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const bool act = p.upd_active == nullptr || __ldg(p.upd_active + tc.n) != 0;    // frozen images are untouched
+    float* yb = p.upd_y + static_cast<size_t>(tc.n) * C * HW + static_cast<size_t>(oh) * p.OW + ow;
+    float yv[16];
+    if (valid && act) {      // requested before the accumulator is ready
+#pragma unroll
+      for (int c = 0; c < 16; ++c) if (c < C) yv[c] = yb[static_cast<size_t>(c) * HW];
+    }
+    mbar_wait(tmem_full_bar0 + 8u * grp, aphase, p.diag, 4, grp);
+    tcgen05_fence_after();
+    uint32_t v[16];
+    tmem_ld_x16(tmem_base + static_cast<uint32_t>(grp * 16) + (static_cast<uint32_t>(q * 32) << 16), v);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    mbar_arrive(tmem_empty_bar0 + 8u * grp);
+    float nrm = 0.f;
+    if (valid && act) {
+      float l[16], pr[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) l[c] = __uint_as_float(v[c]) + bias[c];
+      float mx = l[0];
+#pragma unroll
+      for (int c = 1; c < 16; ++c) if (c < C) mx = fmaxf(mx, l[c]);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { pr[c] = c < C ? expf(l[c] - mx) : 0.f; s += pr[c]; }
+      const float inv = 1.0f / s;
+      float ss = 0.f, outv[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c < C) {
+          const float g = __fsub_rn(yv[c], __fmul_rn(pr[c], inv));      // explicit roundings: same bits as update.cu
+          ss = __fmaf_rn(g, g, ss);
+          outv[c] = fminf(fmaxf(__fsub_rn(yv[c], __fmul_rn(p.upd_step, g)), 0.f), 1.f);
+          yb[static_cast<size_t>(c) * HW] = outv[c];
+        } else outv[c] = 0.f;
+      }
+      nrm = sqrtf(ss);
+      uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + (static_cast<size_t>(tc.n) * HW + static_cast<size_t>(oh) * p.OW + ow) * p.upd_cpad);
+      stg_v4(o, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]), pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
+      stg_v4(o + 1, make_uint4(pack_bf16x2(outv[8], outv[9]), pack_bf16x2(outv[10], outv[11]), pack_bf16x2(outv[12], outv[13]), pack_bf16x2(outv[14], outv[15])));
+      for (int j = 2; j < p.upd_cpad / 8; ++j) stg_v4(o + j, make_uint4(0, 0, 0, 0));
+    }
+    // per-image norm: 2^-40 fixed point, warp-reduced, one integer atomic per warp
+    unsigned long long fx = static_cast<unsigned long long>(static_cast<double>(nrm) * 1099511627776.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    if (lane == 0 && fx != 0ull) atomicAdd(p.upd_norm_acc + tc.n, fx);
   }
 }
 
@@ -587,7 +669,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), (BN == 16 && p.upd_y == nullptr) ? kEpilogueThreads : kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -676,8 +758,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if constexpr (BN == 16) {
+      if (p.upd_y != nullptr) conv_epilogue16_update(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
@@ -755,7 +839,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < S; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), BN == 16 ? kEpilogueThreads : kEpilogueThreads / 2); }
+    for (int i = 0; i < S; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), (BN == 16 && p.upd_y == nullptr) ? kEpilogueThreads : kEpilogueThreads / 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -849,8 +933,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    if constexpr (BN == 16) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else if (p.pooled != nullptr) conv_epilogue<BN, false, true>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if constexpr (BN == 16) {
+      if (p.upd_y != nullptr) conv_epilogue16_update(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else if (p.pooled != nullptr) conv_epilogue<BN, false, true>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else conv_epilogue<BN, false, false>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
@@ -991,7 +1077,11 @@ extern "C" int iiseg_debug_read_timeline(long long* out, int n) {
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
-  IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr), "conv: null tensor");
+  IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr || d->upd_y != nullptr), "conv: null tensor");
+  if (d->upd_y != nullptr)
+    IISEG_CHECK(d->Cout == 16 && d->upd_y_bf16 != nullptr && d->upd_norm_acc != nullptr && d->upd_C >= 1 && d->upd_C <= 16 &&
+                d->upd_cpad >= 16 && d->upd_cpad % 8 == 0 && d->addend == nullptr && d->pooled == nullptr && d->split == 0,
+                "conv: the fused softmax-update needs a 16-channel logits conv (no addend / pool / split), y_bf16 and norm_acc");
   IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
   // K blocks of 64 channels (128-byte rows), or -- one 16-channel source, 3x3 filter, halo-tile kernel only -- of 16
   const int KB = (d->C[0] == 16 && d->src[1] == nullptr) ? 16 : 64;
@@ -1087,6 +1177,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
   p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);
   p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask;
+  p.upd_y = d->upd_y; p.upd_y_bf16 = reinterpret_cast<__nv_bfloat16*>(d->upd_y_bf16); p.upd_active = d->upd_active;
+  p.upd_norm_acc = reinterpret_cast<unsigned long long*>(d->upd_norm_acc); p.upd_step = d->upd_step; p.upd_C = d->upd_C; p.upd_cpad = d->upd_cpad;
   p.pwin_h = d->OH / 2; p.pwin_w = d->OW / 2;
   if (d->pool_H > 0) { p.PH = d->pool_H; p.PW = d->pool_W; p.p_h0 = d->oh0 / 2; p.p_w0 = d->ow0 / 2; }
   else { p.PH = p.pwin_h; p.PW = p.pwin_w; p.p_h0 = 0; p.p_w0 = 0; }
@@ -1102,7 +1194,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     // halo kernel, BN 64/128: 4 accumulator stages (an issuer runs a tile ahead of its epilogue group);
     // 16-channel outputs measured faster with 2 (0.087 vs 0.107 ms on up_conv1)
     static const int env_s = getenv("IISEG_HALO_S") ? atoi(getenv("IISEG_HALO_S")) : 4;
-    p.acc_stages = (halo && BN >= 64 && env_s == 4) ? 4 : 2;
+    p.acc_stages = (halo && BN >= 64 && env_s == 4) ? 4 : 2;      // (the fused-update epilogue assumes 2)
   }
   {
     static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;

@@ -59,7 +59,8 @@ __device__ __forceinline__ void softmax_c(const float* l, float* p, int C) {
   for (int c = 0; c < kMaxC; ++c) { p[c] = c < C ? expf(l[c] - m) : 0.f; s += p[c]; }
   const float inv = 1.0f / s;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) p[c] = p[c] * inv;
+  for (int c = 0; c < kMaxC; ++c) p[c] = __fmul_rn(p[c], inv);      // explicit roundings (no FMA contraction): the fused
+                                                                      // conv epilogue (conv_epilogue16_update) must give the same bits
 }
 
 // grid = (nblk, N)
@@ -88,9 +89,9 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
       for (int c = 0; c < kMaxC; ++c) {
         if (c < C) {
           const float yc = yb[(size_t)c * HW];
-          const float g = yc - p[c];
-          ss += g * g;
-          out[c] = fminf(fmaxf(yc - step * g, 0.f), 1.f);
+          const float g = __fsub_rn(yc, p[c]);
+          ss = __fmaf_rn(g, g, ss);
+          out[c] = fminf(fmaxf(__fsub_rn(yc, __fmul_rn(step, g)), 0.f), 1.f);
           yb[(size_t)c * HW] = out[c];
         } else out[c] = 0.f;
       }
@@ -146,6 +147,21 @@ __global__ void norm_finalize_kernel(const float* __restrict__ norm_partial, flo
   }
 }
 
+// one thread per image: the fused conv epilogue already reduced ||g||_2 to one fixed-point word per image
+__global__ void norm_finalize_fixed_kernel(unsigned long long* __restrict__ norm_acc, float* __restrict__ norm,
+                                           int32_t* __restrict__ active, int32_t* __restrict__ n_exec, int N,
+                                           double inv_hw, float eps) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const unsigned long long acc = norm_acc[n];
+  norm_acc[n] = 0ull;
+  if (active[n] == 0) return;
+  const float nv = (float)((double)acc * (1.0 / 1099511627776.0) * inv_hw);
+  norm[n] = nv;
+  n_exec[n] += 1;
+  if (nv < eps) active[n] = 0;
+}
+
 }  // namespace iiseg
 
 extern "C" int iiseg_update_blocks(int H, int W) { return (H * W + iiseg::kUpdBlock - 1) / iiseg::kUpdBlock; }
@@ -195,6 +211,16 @@ extern "C" int iiseg_norm_finalize(const float* norm_partial, float* norm, int32
   IISEG_CHECK(norm_partial && norm && active && n_exec, "norm_finalize: null tensor");
   norm_finalize_kernel<<<N, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       norm_partial, norm, active, n_exec, iiseg_update_blocks(H, W), 1.0f / (float)(H * W), eps);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_norm_finalize_fixed(uint64_t* norm_acc, float* norm, int32_t* active, int32_t* n_exec, int N,
+                                         int H, int W, float eps, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(norm_acc && norm && active && n_exec, "norm_finalize_fixed: null tensor");
+  norm_finalize_fixed_kernel<<<(N + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long*>(norm_acc), norm, active, n_exec, N, 1.0 / ((double)H * (double)W), eps);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -142,8 +142,9 @@ class IterativeInference(object):
     (update first, then the test, then -- only if still active -- that iteration's
     metrics: iterative_inference.py:267-280).  Frozen images are predicated off."""
 
-    def __init__(self, dae, n_classes=None, void_labels=()):
+    def __init__(self, dae, n_classes=None, void_labels=(), fuse_update=True):
         self.net = dae.net
+        self.fuse_update = fuse_update      # False: stand-alone softmax_update kernel (same bits, one more pass over HBM)
         self.C = self.net.n_classes if n_classes is None else n_classes
         self.void_label = _void_label(self.C, list(void_labels))
         self._state = {}
@@ -165,6 +166,7 @@ class IterativeInference(object):
                 'norm': torch.zeros((B,), dtype=torch.float32, device=dev),
                 'norm_hist': torch.zeros((num_iter, B), dtype=torch.float32, device=dev),
                 'partial': torch.zeros((B, K.update_blocks(H, W)), dtype=torch.float32, device=dev),
+                'norm_acc': torch.zeros((B,), dtype=torch.int64, device=dev),
                 'final': MetricsAccumulator(B, self.C, dev),
                 'iter': [MetricsAccumulator(B, self.C, dev) for _ in range(num_iter)] if per_iter else None,
                 'graph': {},
@@ -177,6 +179,7 @@ class IterativeInference(object):
         H, W = st['y'].shape[2:]
         st['active'].fill_(1)
         st['n_exec'].zero_()
+        st['norm_acc'].zero_()
         st['final'].zero_()
         if per_iter:
             for acc in st['iter']:
@@ -184,9 +187,15 @@ class IterativeInference(object):
         for it in range(num_iter):
             # the first iteration of a batch computes the whole contracting path (h is new); later ones only
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
-            logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0))
-            K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
-            K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
+            if self.fuse_update and not net.split:
+                # softmax tail + update + norm in the epilogue of up_conv1: the logits never reach HBM
+                net.logits(st['h'], st['y_bf16'], full_down=(it == 0),
+                           update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))
+                K.norm_finalize_fixed(st['norm_acc'], st['norm'], st['active'], st['n_exec'], H, W, eps)
+            else:
+                logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0))
+                K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
+                K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])
             if per_iter:
                 acc = st['iter'][it]

@@ -189,11 +189,14 @@ class DAENet(object):
         return ws
 
     # -- one application ----------------------------------------------------
-    def logits(self, h_bf16, y_bf16, full_down=True):
+    def logits(self, h_bf16, y_bf16, full_down=True, update=None):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
         Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16).
         `full_down=False` recomputes only the y-dependent windows of the contracting path; valid when
-        the workspace already holds a full pass for the same h (see `down_windows`)."""
+        the workspace already holds a full pass for the same h (see `down_windows`).
+        `update` (bf16 variant): dict(y, active, norm_acc, step) -- the softmax tail and the
+        iterative-inference update run in the epilogue of the last conv (y and y_bf16 are updated in
+        place, the logits are never stored) and None is returned."""
         B, H, W, _ = y_bf16.shape
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
@@ -237,6 +240,10 @@ class DAENet(object):
                              addend_off=(hl, wl), out=ws['upconv'][p], split=sp)
                 u_origin = (hl, wl)
             else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
+                if update is not None:
+                    K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True,
+                             update=dict(update, y_bf16=y_bf16, C=self.n_classes))
+                    return None
                 K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=sp)
         return ws['logits']
 

@@ -265,3 +265,28 @@ def test_fp32x3_free_running_loop_vs_oracle_64x80(cuda, built_f32):
         y = ii.run(h_d, y, 0.05, 1, eps=0.0, use_graph=False)['y'].clone()
         assert float((y.cpu() - y_o).abs().max()) < TOL_F32, it
         assert float((y.cpu().argmax(1) == y_o.argmax(1)).float().mean()) >= MIN_ARGMAX_F32, it
+
+
+def test_fused_update_epilogue_equals_standalone_kernel(cuda, built):
+    """up_conv1 with the softmax tail + y update fused in its epilogue gives bit-identical y (and the same
+    executed-iteration counts) as logits -> iiseg_softmax_update; the per-iteration norms agree to
+    fp32 rounding (fixed-point integer sum vs ordered partial sums)."""
+    from iterative_inference_segm_b200.functions import IterativeInference
+    pf, pd, fcn, dae = built
+    gd = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    h = torch.from_numpy(gd['h']).to(cuda)
+    y0 = torch.from_numpy(np.concatenate([gd['y'], gd['y'][:, ::-1].copy()])).to(cuda)     # 2 images
+    h2 = torch.cat([h, h])
+    res = {}
+    for fuse in (True, False):
+        ii = IterativeInference(dae, NCLS, [NCLS], fuse_update=fuse)
+        r = ii.run(h2, y0, 0.05, 5, eps=0.0, use_graph=False)
+        res[fuse] = (r['y'].clone(), r['norm_hist'].clone(), r['n_exec'].clone())
+    assert torch.equal(res[True][0], res[False][0])
+    assert torch.equal(res[True][2], res[False][2])
+    assert torch.allclose(res[True][1], res[False][1], rtol=1e-5, atol=0)
+    # frozen images stay untouched in the fused path too
+    ii = IterativeInference(dae, NCLS, [NCLS], fuse_update=True)
+    one = ii.run(h2, y0, 0.05, 1, eps=0.0, use_graph=False)['y'].clone()
+    many = ii.run(h2, y0, 0.05, 3, eps=1e9, use_graph=False)
+    assert many['n_exec'].cpu().tolist() == [1, 1] and torch.equal(many['y'], one)

@@ -12,13 +12,13 @@ def run(name, fn):
     t = [[buf[i * 16 + s] for s in range(16)] for i in range(32)]
     base = t[2][0]
     print(name)
-    print(' tile | mma: wait_tmem_empty  got_it  a_full  issued | epi: wait_full got_full ld_done barA sts_done barB end')
-    for i in range(2, 14):
-        print(' %3d  | %s' % (i, ' '.join('%7d' % (t[i][s] - base) for s in range(11))))
+    print(' tile | mma: wait_tmem_empty  got_it  a_full  issued | epi(group 0): wait_full got_full end')
+    for i in range(2, 18):
+        print(' %3d  | %s' % (i, ' '.join('%7d' % (t[i][s] - base) if t[i][s] else '      -' for s in range(7))))
 
 B = 10
-y = torch.randn(B, 360, 480, 64, device='cuda').to(torch.bfloat16)
-W1 = (torch.randn(64, 9 * 64, device='cuda') * 0.02).to(torch.bfloat16)
+y = torch.randn(B, 360, 480, 16, device='cuda').to(torch.bfloat16)
+W1 = (torch.randn(64, 9 * 16, device='cuda') * 0.02).to(torch.bfloat16)
 b1 = torch.zeros(64, device='cuda')
 pooled = torch.empty(B, 279, 339, 64, dtype=torch.bfloat16, device='cuda')
 mask = torch.empty(B, 279, 339, 8, dtype=torch.int32, device='cuda')
