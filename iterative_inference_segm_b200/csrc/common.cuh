@@ -76,6 +76,10 @@ __device__ __forceinline__ uint32_t tie_select(uint32_t bits, int k, int pos) {
   return (0u - lo) & 0x0000FFFFu | (0u - hi) & 0xFFFF0000u;
 }
 
+// exp of a non-positive argument for the channel softmax: ex2.approx(x * log2 e), ~2^-21 relative error.
+// One definition shared by update.cu and the fused conv epilogue so both produce the same bits.
+__device__ __forceinline__ float softmax_exp(float x) { return __expf(x); }
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

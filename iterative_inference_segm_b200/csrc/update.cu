@@ -56,7 +56,7 @@ __device__ __forceinline__ void softmax_c(const float* l, float* p, int C) {
   for (int c = 1; c < kMaxC; ++c) if (c < C) m = fmaxf(m, l[c]);
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) { p[c] = c < C ? expf(l[c] - m) : 0.f; s += p[c]; }
+  for (int c = 0; c < kMaxC; ++c) { p[c] = c < C ? softmax_exp(l[c] - m) : 0.f; s += p[c]; }
   const float inv = 1.0f / s;
 #pragma unroll
   for (int c = 0; c < kMaxC; ++c) p[c] = __fmul_rn(p[c], inv);      // explicit roundings (no FMA contraction): the fused
