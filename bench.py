@@ -256,33 +256,48 @@ def run_b200(args):
         st = ii._buffers(BATCH, H, W, N_ITER, False)
         timer = KernelTimer()
         reps = 3
-        dae.net.logits(st['h'], st['y_bf16'], full_down=True)          # fills the iteration-invariant borders
+        upd = dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=STEP)   # as in the captured loop
+        st['active'].fill_(1)
+        dae.net.logits(st['h'], st['y_bf16'], full_down=True, update=upd)      # fills the iteration-invariant borders
         with timer.recording():
             for _ in range(reps + 1):
-                dae.net.logits(st['h'], st['y_bf16'], full_down=False)  # the steady-state application (49 of 50)
+                dae.net.logits(st['h'], st['y_bf16'], full_down=False, update=upd)  # the steady-state application (49 of 50)
         summ = timer.summary()
-        conv_lists = [v for (name, tag), v in summ.items() if name == 'conv2d']
-        conv_total_ms = sum(sum(v[1:]) / len(v[1:]) for v in conv_lists)     # drop the first (cold) repetition
+        fl = dae.net.executed_conv_flops(H, W, steady_state=True)               # executed FLOPs only, per image
+        convs = [(tag, sum(v[1:]) / len(v[1:])) for (name, tag), v in summ.items() if name == 'conv2d']   # launch order; drop the cold rep
+        assert len(convs) == len(fl)
+        conv_total_ms = sum(ms for _, ms in convs)
         other = {}
         for (name, tag), v in summ.items():
             other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
-        flops = sum(dae.net.executed_conv_flops(H, W, steady_state=True)) * BATCH    # executed FLOPs only
-        achieved = flops / (conv_total_ms * 1e-3) / 1e12
+        # dominant kernel: conv_igemm_kernel<256> (per-tap implicit GEMM, 256-channel tiles) = every launch with Cout % 256 == 0
+        dom = [(f, ms) for f, (tag, ms) in zip(fl, convs) if tag[2] % 256 == 0]
+        dom_flops, dom_ms = sum(f for f, _ in dom) * BATCH, sum(ms for _, ms in dom)
+        achieved = dom_flops / (dom_ms * 1e-3) / 1e12
         peak = peaks['bf16_tflops_sustained']
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (12 conv launches of one DAE application, batch 10; steady-state iteration: executed FLOPs on the y-dependent / crop-dependent windows)',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
-                'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': conv_total_ms / 12.0,
-                'flops_per_application': flops}
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get('conv_igemm_kernel<256>', {}).get('dram_bytes_per_launch')
+        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel<256> (tcgen05 implicit GEMM, %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1..conv6_1, up_conv6..up_conv4; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': dom_ms / len(dom),
+                'flops_per_launch': dom_flops / len(dom),
+                'all_12_conv_launches': {'achieved': sum(fl) * BATCH / (conv_total_ms * 1e-3) / 1e12, 'ms': conv_total_ms,
+                                         'flops_per_application': sum(fl) * BATCH,
+                                         'note': 'includes the 16-channel first layer, the fused 2x2 pool + tie mask epilogues and the fused softmax/update epilogue of up_conv1'}}
         unpool_b = 0.0
         for (name, tag), v in summ.items():
             if name == 'unpool2':       # algorithmic bytes: out written once, the touched u / mask windows read once
                 (n, uh, uw, c), (_, oh, ow, _) = tag
                 unpool_b += n * oh * ow * c * 2 + n * ((oh + 1) // 2 + 1) * ((ow + 1) // 2 + 1) * c * 2.5
-        conv_ms = [round(sum(v[1:]) / len(v[1:]), 4) for (name, tag), v in summ.items() if name == 'conv2d']
-        breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()}, 'conv_ms_in_launch_order': conv_ms,
+        breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
+                     'conv_ms_in_launch_order': [round(ms, 4) for _, ms in convs],
+                     'conv_tflops_in_launch_order': [round(f * BATCH / (ms * 1e-3) / 1e12, 1) for f, (_, ms) in zip(fl, convs)],
                      'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
                      'hbm_peak_gbs': peaks['hbm_gbs'],
-                     'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues'}
+                     'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues; softmax + y update + norm into up_conv1'}
         if world == 1 and not args.no_cpu_baseline:
             t_img, cores, parts = cpu_reference_sample()
             cpu_base = {'value': 1.0 / t_img, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

@@ -1,7 +1,7 @@
 """Profiling target: one full DAE application (fills borders) + 2 steady-state applications, eager."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import weights  # noqa: E402
+from iterative_inference_segm_b200 import synthetic as weights  # noqa: E402
 
 def main(B=10, H=360, W=480):
     from iterative_inference_segm_b200.models.DAE_h import buildDAE
@@ -12,10 +12,13 @@ def main(B=10, H=360, W=480):
     net = dae.net
     hs = net.h_spatial(H, W)
     h = torch.relu(torch.randn(B, hs[0], hs[1], 512, device='cuda')).to(torch.bfloat16)
-    y = K.pack_nchw(torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1), net.y_cpad)
-    net.logits(h, y, full_down=True)
+    yf = torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1)
+    y = K.pack_nchw(yf, net.y_cpad)
+    upd = dict(y=yf, active=torch.ones(B, dtype=torch.int32, device='cuda'),
+               norm_acc=torch.zeros(B, dtype=torch.int64, device='cuda'), step=0.05)      # as in the captured loop
+    net.logits(h, y, full_down=True, update=upd)
     for _ in range(2):
-        net.logits(h, y, full_down=False)
+        net.logits(h, y, full_down=False, update=upd)
     torch.cuda.synchronize()
     print('ok')
 
