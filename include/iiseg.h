@@ -109,6 +109,8 @@ typedef struct iiseg_conv_desc {
    * (W_hi | W_hi | W_lo) weights, so the GEMM accumulates hi*hi + lo*hi + hi*lo in fp32.        */
   int split;
   int out_f32;        /* 1: fp32 output [N,OH,OW,Cout] (no pool, no split)      */
+  int out_cs;         /* fp32 outputs: channels per pixel of the destination (0 = Cout): the conv writes
+                       * Cout channels at `out` inside a wider tensor (DenseNet stack, ConcatLayer-free) */
   /* Fused softmax tail + iterative-inference update (Cout == 16, the DAE's last conv up_conv1):
    * when upd_y != NULL the logits are not stored; for every image n with upd_active[n] != 0 (NULL =
    * all) the epilogue does  p = softmax over the first upd_C channels;  g = y - p;
@@ -216,6 +218,32 @@ int iiseg_metrics_accumulate(const float* y, const float* onehot,
  * of metrics.py:20-21,49-50 done once per batch.  onehot NCHW fp32 [N,C1,H,W]. */
 int iiseg_onehot_to_labels(const float* onehot, int32_t* labels, int N, int C1, int H,
                            int W, void* stream);
+
+/* ---- FC-DenseNet103 around the convs (models/FCDenseNet.py + FC_DenseNet.layers) ----------------
+ * The stack of a dense block is ONE fp32 NHWC tensor [N,H,W,Cs]; "the first C channels" is the stack a
+ * layer sees (ConcatLayer([stack, l]) without copies).
+ * iiseg_bn_relu_pack: BatchNormLayer with batch statistics (iterative_inference.py:187,
+ *   batch_norm_use_averages=False) + rectify + bf16 pack of channels [c0, c0+C):
+ *   out[.., c] = bf16(relu((x - mean[c]) * (gamma[c] * inv_std[c]) + beta[c])), zero for C <= c < Cpad;
+ *   mean == NULL: plain convert (TransitionUp's deconv input); relu = 0: no rectify.
+ * iiseg_channel_stats: mean and inv_std = 1/sqrt(var + eps) (biased variance over N,H,W) of channels
+ *   [c0, c0+C); deterministic two-level reduction; scratch = fp64 [iiseg_channel_stats_chunks(N,H,W)][C][2].
+ * iiseg_maxpool2_f32: Pool2DLayer(2,'max') of TransitionDown on fp32 maps, written as the first C
+ *   channels of the next stack (Cs_out channels per pixel).
+ * iiseg_deconv_interleave: assembles Deconv2DLayer(3, stride 2, crop 'valid') from its four
+ *   output-phase convolutions p[py][px] (dense fp32 [N,H+1,W+1,Cp]) with the centre crop of the
+ *   following ConcatLayer: out[oh,ow] = p[(oh+crop_h)&1][(ow+crop_w)&1][(oh+crop_h)>>1, (ow+crop_w)>>1]. */
+int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, int c0, int C, const float* mean,
+                       const float* inv_std, const float* gamma, const float* beta, int relu,
+                       void* out, int Cpad, void* stream);
+int iiseg_channel_stats_chunks(int N, int H, int W);
+int iiseg_channel_stats(const float* x, int N, int H, int W, int Cs, int c0, int C, float eps,
+                        double* scratch, float* mean, float* inv_std, void* stream);
+int iiseg_maxpool2_f32(const float* x, int N, int H, int W, int Cs_in, int C, float* out, int Cs_out,
+                       void* stream);
+int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10, const float* p11,
+                            int N, int H, int W, int Cp, int C, int crop_h, int crop_w, float* out,
+                            int OH, int OW, int Cs_out, void* stream);
 
 #ifdef __cplusplus
 }

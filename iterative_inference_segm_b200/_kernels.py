@@ -75,7 +75,8 @@ def conv_out_size(H, W, R, S, pad):
 
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
-           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None):
+           out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
+           out_slice=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -87,7 +88,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
 
     update = dict(y, y_bf16, active, norm_acc, step, C): the 16-channel logits conv with the softmax
     tail and the iterative-inference update fused in its epilogue (iiseg_conv_desc.upd_*); nothing is
-    returned, y / y_bf16 / norm_acc are updated in place."""
+    returned, y / y_bf16 / norm_acc are updated in place.
+
+    out_slice = (stack, c_off): fp32 output written as channels [c_off, c_off + Cout) of the wider fp32
+    NHWC tensor `stack` [N,OH,OW,Cs] (the DenseNet stack: ConcatLayer without a copy)."""
     _chk(src0, BF16, 'src0')
     _chk(weight, BF16, 'weight')
     _chk(bias, F32, 'bias')
@@ -125,6 +129,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         assert Cout == 16 and out is None and addend is None and not split
         assert tuple(update['y'].shape) == (N, update['C'], OH, OW) and tuple(update['y_bf16'].shape[:3]) == (N, OH, OW)
         assert update['norm_acc'].numel() == N
+    elif out_slice is not None:
+        stack, c_off = out_slice
+        _chk(stack, F32, 'out_slice.stack')
+        assert out_f32 and out is None and tuple(stack.shape[:3]) == (N, OH, OW) and c_off + Cout <= stack.shape[3] and c_off % 4 == 0
     elif out is None:
         out = torch.empty((N, OH, OW, cm * Cout), dtype=F32 if out_f32 else BF16, device=src0.device)
     else:
@@ -145,6 +153,8 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if out_slice is not None:
+        d.out, d.out_cs = out_slice[0].data_ptr() + 4 * out_slice[1], out_slice[0].shape[3]
     if update is not None:
         d.upd_y, d.upd_y_bf16 = update['y'].data_ptr(), update['y_bf16'].data_ptr()
         d.upd_active = update['active'].data_ptr() if update.get('active') is not None else None
@@ -264,6 +274,58 @@ def norm_finalize(norm_partial, norm, active, n_exec, H, W, eps):
     N = norm.shape[0]
     _lib.call('iiseg_norm_finalize', _ptr(norm_partial), _ptr(norm), _ptr(active), _ptr(n_exec), N, H, W,
               C.c_float(eps), _stream())
+
+
+# ---- FC-DenseNet103 streaming kernels -------------------------------------------
+def bn_relu_pack(stack, C, out, c0=0, stats=None, gamma=None, beta=None, relu=True):
+    """Channels [c0, c0+C) of the fp32 NHWC `stack` -> zero-padded bf16 NHWC `out`, through BatchNorm with the batch
+    statistics `stats` = (mean, inv_std) + gamma/beta and rectify; stats=None: plain convert."""
+    _chk(stack, F32, 'stack')
+    _chk(out, BF16, 'out')
+    N, H, W, Cs = stack.shape
+    assert tuple(out.shape[:3]) == (N, H, W) and out.shape[3] >= C
+    mean, inv_std = stats if stats is not None else (None, None)
+    _lib.call('iiseg_bn_relu_pack', _ptr(stack), N, H, W, Cs, c0, C, _ptr(mean), _ptr(inv_std), _ptr(gamma), _ptr(beta),
+              int(bool(relu)), _ptr(out), out.shape[3], _stream())
+    return out
+
+
+def channel_stats(stack, c0, nC, mean, inv_std, scratch, eps=1e-4):
+    """Batch statistics of channels [c0, c0+nC) of `stack` into mean[c0:c0+nC], inv_std[c0:c0+nC] (fp32 vectors)."""
+    _chk(stack, F32, 'stack')
+    N, H, W, Cs = stack.shape
+    need = _lib.load().iiseg_channel_stats_chunks(N, H, W) * nC * 2
+    assert scratch.dtype == torch.float64 and scratch.numel() >= need
+    _lib.call('iiseg_channel_stats', _ptr(stack), N, H, W, Cs, c0, nC, C.c_float(eps), _ptr(scratch), C_void(mean, c0),
+              C_void(inv_std, c0), _stream())
+
+
+def C_void(vec, off):
+    _chk(vec, F32, 'vector')
+    return C.c_void_p(vec.data_ptr() + 4 * off)
+
+
+def maxpool2_f32(x, C_, out):
+    _chk(x, F32, 'x')
+    _chk(out, F32, 'out')
+    N, H, W, Cs = x.shape
+    assert tuple(out.shape[:3]) == (N, H // 2, W // 2)
+    _lib.call('iiseg_maxpool2_f32', _ptr(x), N, H, W, Cs, C_, _ptr(out), out.shape[3], _stream())
+    return out
+
+
+def deconv_interleave(phases, C_, crop, out):
+    """phases[py][px]: dense fp32 [N,H+1,W+1,Cp]; out: fp32 [N,OH,OW,Cs], first C_ channels written."""
+    p00 = phases[0][0]
+    N, H1, W1, Cp = p00.shape
+    for row in phases:
+        for t in row:
+            _chk(t, F32, 'phase')
+            assert tuple(t.shape) == (N, H1, W1, Cp)
+    _chk(out, F32, 'out')
+    _lib.call('iiseg_deconv_interleave', _ptr(phases[0][0]), _ptr(phases[0][1]), _ptr(phases[1][0]), _ptr(phases[1][1]),
+              N, H1 - 1, W1 - 1, Cp, C_, crop[0], crop[1], _ptr(out), out.shape[1], out.shape[2], out.shape[3], _stream())
+    return out
 
 
 # ---- metrics ------------------------------------------------------------------

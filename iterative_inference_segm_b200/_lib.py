@@ -29,7 +29,7 @@ class ConvDesc(C.Structure):
         ('out', C.c_void_p), ('addend', C.c_void_p),
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int),
         ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
-        ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int),
+        ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int), ('out_cs', C.c_int),
         ('upd_y', C.c_void_p), ('upd_y_bf16', C.c_void_p), ('upd_active', C.c_void_p), ('upd_norm_acc', C.c_void_p),
         ('upd_step', C.c_float), ('upd_C', C.c_int), ('upd_cpad', C.c_int),
     ]
@@ -71,6 +71,11 @@ SIGNATURES = {
     'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'iiseg_norm_finalize_fixed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_bn_relu_pack': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    'iiseg_channel_stats_chunks': (_i, [_i, _i, _i]),
+    'iiseg_channel_stats': (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    'iiseg_maxpool2_f32': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    'iiseg_deconv_interleave': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

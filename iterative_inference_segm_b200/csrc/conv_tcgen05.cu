@@ -88,6 +88,7 @@ struct alignas(64) ConvParams {
   float upd_step; int upd_C, upd_cpad;
   int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
+  int out_cs;               // fp32 outputs: channels per pixel of the destination tensor (>= Cout: the conv writes a channel slice)
   int addend_f32;           // the skip-sum / hoisted-term operand is fp32 [N,AH,AW,Cout] (BN >= 64 epilogue only)
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores
@@ -301,7 +302,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
     }
     if (valid) {
       if (p.out_f32) {
-        float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
+        float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cs + cbase;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           stg_v4(o + 4 * j, make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
@@ -537,7 +538,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         }
         if (p.out_f32) {          // fp32 rows (the hoisted term itself): 128 contiguous bytes per thread
           if (valid) {
-            float* o = reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase;
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cs + cbase;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float a = f[4 * j], b = f[4 * j + 1], c = f[4 * j + 2], d = f[4 * j + 3];
@@ -1134,6 +1135,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->split == 0 || (d->out_f32 == 0 && d->Cout % 64 == 0), "conv: split output needs a bf16 output with Cout %% 64 == 0");
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
+  IISEG_CHECK(d->out_cs == 0 || (d->out_f32 && d->out_cs >= d->Cout && d->out_cs % 4 == 0), "conv: out_cs is for fp32 outputs (channel slice of a wider tensor)");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
   const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
@@ -1228,6 +1230,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
+  p.out_cs = d->out_cs > 0 ? d->out_cs : d->Cout;
   {
     // halo kernel, BN 64/128: 4 accumulator stages (an issuer runs a tile ahead of its epilogue group);
     // 16-channel outputs measured faster with 2 (0.087 vs 0.107 ms on up_conv1)

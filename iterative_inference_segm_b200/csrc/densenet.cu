@@ -1,0 +1,197 @@
+// Streaming kernels around the convs of FC-DenseNet103 (models/FCDenseNet.py + FC_DenseNet.layers).
+//
+// The "Tiramisu" stack (ConcatLayer([stack, l]), models/FCDenseNet.py:84-89) is ONE fp32 NHWC tensor
+// per dense block, allocated with its final channel count: a layer's 16 new feature maps are written
+// behind the channels that exist so far, so no concat ever copies the stack.  Every BN_ReLU_Conv reads
+// the first C channels through `bn_relu_pack` (BatchNormLayer with BATCH statistics,
+// iterative_inference.py:187 batch_norm_use_averages=False, then rectify) into the zero-padded bf16
+// NHWC tensor the tcgen05 conv kernel consumes.  Channel statistics are computed once per produced
+// feature map (they do not depend on the consuming layer) by a deterministic two-level reduction.
+// All kernels are bandwidth-bound: 16-byte accesses, channel-fastest thread order.
+#include "common.cuh"
+#include "../../include/iiseg.h"
+
+namespace iiseg {
+
+// ---- BatchNorm (batch statistics) + rectify + bf16 pack ---------------------------------------------
+// out[p, c] = bf16( relu( (x[p, c0+c] - mean[c]) * (gamma[c] * inv_std[c]) + beta[c] ) ), c < C; 0 for C <= c < Cpad.
+// mean == NULL: plain copy/convert of the channel range (the deconv input of TransitionUp is not normalised).
+__global__ void __launch_bounds__(256) bn_relu_pack_kernel(const float* __restrict__ x, long long P, int Cs, int c0, int C,
+                                                           const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int relu, uint4* __restrict__ out, int C8pad) {
+  const long long total = P * C8pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C8pad;
+    const int cg = (int)(i - pix * C8pad);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      float t = 0.f;
+      if (c < C) {
+        t = x[pix * Cs + c0 + c];
+        if (mean != nullptr) t = __fmaf_rn(__fsub_rn(t, __ldg(mean + c)), __fmul_rn(__ldg(gamma + c), __ldg(inv_std + c)), __ldg(beta + c));
+        if (relu) t = fmaxf(t, 0.f);
+      }
+      v[k] = t;
+    }
+    stg_v4(out + i, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+  }
+}
+
+// ---- per-channel batch statistics --------------------------------------------------------------------
+// Level 1: block (32 channels x 8 pixel lanes) sums x and x^2 over a chunk of kStatChunk pixels in fp32 per
+// thread, combines the 8 lanes in fp64 and writes one (sum, sumsq) pair per (chunk, channel).
+// Level 2: one thread per channel adds the chunks in index order (deterministic), biased variance,
+// inv_std = 1/sqrt(var + eps) (lasagne BatchNormLayer, epsilon = 1e-4).
+constexpr int kStatChunk = 2048;
+
+__global__ void __launch_bounds__(256) channel_stats_partial_kernel(const float* __restrict__ x, long long P, int Cs, int c0, int C,
+                                                                    double* __restrict__ partial) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long p0 = (long long)blockIdx.y * kStatChunk;
+  const long long p1 = p0 + kStatChunk < P ? p0 + kStatChunk : P;
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
+      const float v = x[p * Cs + c0 + c];
+      s += v;
+      q = __fmaf_rn(v, v, q);
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][threadIdx.y][threadIdx.x] = (double)s;
+  sh[1][threadIdx.y][threadIdx.x] = (double)q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double ds = 0.0, dq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ds += sh[0][k][threadIdx.x]; dq += sh[1][k][threadIdx.x]; }
+    partial[((size_t)blockIdx.y * C + c) * 2] = ds;
+    partial[((size_t)blockIdx.y * C + c) * 2 + 1] = dq;
+  }
+}
+
+__global__ void channel_stats_final_kernel(const double* __restrict__ partial, int n_chunks, int C, double inv_count, float eps,
+                                           float* __restrict__ mean, float* __restrict__ inv_std) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < n_chunks; ++k) { s += partial[((size_t)k * C + c) * 2]; q += partial[((size_t)k * C + c) * 2 + 1]; }
+  const double m = s * inv_count;
+  double var = q * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  inv_std[c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---- 2x2 max-pool on fp32 feature maps (TransitionDown), written into the next stack ------------------
+__global__ void __launch_bounds__(256) maxpool2_f32_kernel(const float4* __restrict__ x, int H, int W, int C4s_in, int C4,
+                                                           float4* __restrict__ out, int H2, int W2, int C4s_out, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int cg = (int)(t % C4); t /= C4;
+    const int ow = (int)(t % W2); t /= W2;
+    const int oh = (int)(t % H2);
+    const long long n = t / H2;
+    const long long r0 = ((n * H + 2 * oh) * W + 2 * ow) * C4s_in + cg, r1 = r0 + (long long)W * C4s_in;
+    const float4 a = x[r0], b = x[r0 + C4s_in], c = x[r1], d = x[r1 + C4s_in];
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)); m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)); m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+    out[((n * H2 + oh) * W2 + ow) * C4s_out + cg] = m;
+  }
+}
+
+// ---- TransitionUp: interleave the four output-phase maps of the stride-2 3x3 transposed conv ----------
+// out[n, oh, ow, c] = phase[(fh & 1) * 2 + (fw & 1)][n, fh >> 1, fw >> 1, c] with (fh, fw) = (oh + crop_h, ow + crop_w)
+// the position in the (2H+1) x (2W+1) deconv output; phase maps are dense [N, H+1, W+1, Cp] fp32.
+struct InterleaveParams { const float4* ph[4]; float4* out; int H1, W1, C4p, C4, OH, OW, crop_h, crop_w, C4s_out; long long total; };
+
+__global__ void __launch_bounds__(256) deconv_interleave_kernel(const InterleaveParams p) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int cg = (int)(t % p.C4); t /= p.C4;
+    const int ow = (int)(t % p.OW); t /= p.OW;
+    const int oh = (int)(t % p.OH);
+    const long long n = t / p.OH;
+    const int fh = oh + p.crop_h, fw = ow + p.crop_w;
+    const float4* src = p.ph[((fh & 1) << 1) | (fw & 1)];
+    p.out[((n * p.OH + oh) * p.OW + ow) * p.C4s_out + cg] = src[((n * p.H1 + (fh >> 1)) * p.W1 + (fw >> 1)) * p.C4p + cg];
+  }
+}
+
+static int sgrid(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace iiseg
+
+extern "C" int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, int c0, int C, const float* mean,
+                                  const float* inv_std, const float* gamma, const float* beta, int relu, void* out,
+                                  int Cpad, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(x && out, "bn_relu_pack: null tensor");
+  IISEG_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && Cpad >= C && Cpad % 8 == 0, "bn_relu_pack: bad shape C=%d Cs=%d Cpad=%d", C, Cs, Cpad);
+  IISEG_CHECK(mean == nullptr || (inv_std && gamma && beta), "bn_relu_pack: incomplete BN parameters");
+  const long long P = (long long)N * H * W;
+  bn_relu_pack_kernel<<<sgrid(P * (Cpad / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, P, Cs, c0, C, mean, inv_std, gamma, beta, relu, reinterpret_cast<uint4*>(out), Cpad / 8);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_channel_stats_chunks(int N, int H, int W) {
+  const long long P = (long long)N * H * W;
+  return (int)((P + iiseg::kStatChunk - 1) / iiseg::kStatChunk);
+}
+
+extern "C" int iiseg_channel_stats(const float* x, int N, int H, int W, int Cs, int c0, int C, float eps, double* scratch,
+                                   float* mean, float* inv_std, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(x && scratch && mean && inv_std, "channel_stats: null tensor");
+  IISEG_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs, "channel_stats: bad shape");
+  const long long P = (long long)N * H * W;
+  const int n_chunks = iiseg_channel_stats_chunks(N, H, W);
+  IISEG_CHECK(n_chunks <= 65535, "channel_stats: too many pixels");
+  dim3 grid((C + 31) / 32, n_chunks), block(32, 8);
+  channel_stats_partial_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, P, Cs, c0, C, scratch);
+  IISEG_LAUNCH_CHECK();
+  channel_stats_final_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scratch, n_chunks, C, 1.0 / (double)P, eps,
+                                                                                                  mean, inv_std);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_maxpool2_f32(const float* x, int N, int H, int W, int Cs_in, int C, float* out, int Cs_out, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(x && out, "maxpool2_f32: null tensor");
+  IISEG_CHECK(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0 && Cs_in % 4 == 0 && Cs_out % 4 == 0 && C <= Cs_in && C <= Cs_out, "maxpool2_f32: bad shape");
+  const int H2 = H / 2, W2 = W / 2;
+  const long long total = (long long)N * H2 * W2 * (C / 4);
+  maxpool2_f32_kernel<<<sgrid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), H, W, Cs_in / 4, C / 4, reinterpret_cast<float4*>(out), H2, W2, Cs_out / 4, total);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10, const float* p11, int N, int H,
+                                       int W, int Cp, int C, int crop_h, int crop_w, float* out, int OH, int OW, int Cs_out,
+                                       void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(p00 && p01 && p10 && p11 && out, "deconv_interleave: null tensor");
+  IISEG_CHECK(N > 0 && C > 0 && C % 4 == 0 && Cp % 4 == 0 && Cs_out % 4 == 0 && C <= Cp && C <= Cs_out, "deconv_interleave: bad channels");
+  IISEG_CHECK(crop_h >= 0 && crop_w >= 0 && crop_h + OH <= 2 * H + 1 && crop_w + OW <= 2 * W + 1, "deconv_interleave: crop outside the %dx%d deconv output", 2 * H + 1, 2 * W + 1);
+  InterleaveParams p;
+  p.ph[0] = reinterpret_cast<const float4*>(p00); p.ph[1] = reinterpret_cast<const float4*>(p01);
+  p.ph[2] = reinterpret_cast<const float4*>(p10); p.ph[3] = reinterpret_cast<const float4*>(p11);
+  p.out = reinterpret_cast<float4*>(out);
+  p.H1 = H + 1; p.W1 = W + 1; p.C4p = Cp / 4; p.C4 = C / 4; p.OH = OH; p.OW = OW; p.crop_h = crop_h; p.crop_w = crop_w; p.C4s_out = Cs_out / 4;
+  p.total = (long long)N * OH * OW * p.C4;
+  deconv_interleave_kernel<<<sgrid(p.total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}

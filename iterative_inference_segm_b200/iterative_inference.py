@@ -24,6 +24,7 @@ from .data_loader import load_data
 from .helpers import build_experiment_name, print_results, results_values
 from .models.DAE_h import buildDAE
 from .models.fcn8 import buildFCN8
+from .models.FCDenseNet import build_fcdensenet
 
 _EPSILON = 1e-3      # iterative_inference.py:53
 
@@ -43,7 +44,12 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
                         params=fcn_params, precision=precision)
         padding = 100
     elif segm_net == 'densenet':
-        raise NotImplementedError('FC-DenseNet103 conditioning is not built yet (DESIGN.md 7)')
+        if precision != 'bf16':
+            raise NotImplementedError('FC-DenseNet103 is built for precision=bf16 only')
+        fcn = build_fcdensenet(None, dae_dict['concat_h'], nb_in_channels, n_classes, output_d='4d', from_gt=False,
+                               weight_path=os.path.join(weights_path or '', dataset, 'DenseNet103', 'weights',
+                                                        'FC-DenseNet103_weights.npz'), params=fcn_params)
+        padding = 0
     elif segm_net == 'fcn_fcresnet':
         raise NotImplementedError
     else:

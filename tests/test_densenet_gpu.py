@@ -1,0 +1,115 @@
+"""FC-DenseNet103 conditioning net on the GPU vs the CPU oracle (oracle/densenet.py),
+same seeded inputs and weights: streaming kernels exactly / to fp32 rounding, the whole forward within
+the bf16 variant's stated tolerance (BN with batch statistics re-normalises every layer, so the error
+stays relative: 5e-2 of the feature scale on pool4; 0.15 max-abs on the peaky probabilities, >= 97 % argmax)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import densenet as OD, lasagne_semantics as L, nets, weights
+
+pytestmark = pytest.mark.gpu
+NCLS = 11
+TOL_H, TOL_P, MIN_AGREE = 5e-2, 0.15, 0.97     # bf16 operands through 103 conv layers + a peaky softmax (logit gain 4)
+
+
+def test_channel_stats_and_bn_pack(cuda):
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(0)
+    N, H, W, Cs, c0, C = 3, 37, 29, 112, 16, 80
+    x = (torch.randn(N, H, W, Cs) * 3 + 1.5).to(cuda)
+    mean = torch.zeros(Cs, device=cuda); inv = torch.ones(Cs, device=cuda)
+    scratch = torch.empty(K._lib.load().iiseg_channel_stats_chunks(N, H, W) * C * 2, dtype=torch.float64, device=cuda)
+    K.channel_stats(x, c0, C, mean, inv, scratch)
+    xs = x[..., c0:c0 + C].double()
+    m_ref = xs.mean((0, 1, 2)); v_ref = xs.var((0, 1, 2), unbiased=False)
+    assert torch.allclose(mean[c0:c0 + C].double(), m_ref, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(inv[c0:c0 + C].double(), 1 / torch.sqrt(v_ref + 1e-4), rtol=1e-6)
+    assert float(mean[:c0].abs().max()) == 0 and float((inv[c0 + C:] - 1).abs().max()) == 0     # untouched outside the range
+    gamma = torch.rand(C, device=cuda) + 0.5; beta = torch.randn(C, device=cuda)
+    out = torch.full((N, H, W, 128), 7.0, dtype=torch.bfloat16, device=cuda)
+    K.bn_relu_pack(x, C, out, c0=c0, stats=(mean[c0:c0 + C].contiguous(), inv[c0:c0 + C].contiguous()), gamma=gamma, beta=beta)
+    ref = torch.relu((x[..., c0:c0 + C] - mean[c0:c0 + C]) * (gamma * inv[c0:c0 + C]) + beta)
+    assert float((out[..., :C].float() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+    assert float(out[..., C:].abs().max()) == 0.0
+    raw = K.bn_relu_pack(x, C, torch.empty((N, H, W, 128), dtype=torch.bfloat16, device=cuda), c0=c0, relu=False)
+    assert torch.equal(raw[..., :C], x[..., c0:c0 + C].to(torch.bfloat16))
+
+
+def test_maxpool_f32_and_deconv_phases(cuda):
+    """TransitionDown's pool, and TransitionUp's Deconv2DLayer(3, stride 2) assembled from four phase
+    convolutions, against conv_transpose2d with the flipped kernel (oracle semantics)."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.models.FCDenseNet import DenseNetNet
+    torch.manual_seed(1)
+    N, H, W, C = 2, 11, 15, 48
+    x = torch.randn(N, C, H, W)
+    xs = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    out = torch.zeros((N, H // 2, W // 2, 64), device=cuda)
+    K.maxpool2_f32(xs, C, out)
+    assert torch.equal(out[..., :C].cpu().permute(0, 3, 1, 2), L.maxpool2(x))
+    keep = 80
+    Wd = torch.randn(C, keep, 3, 3) / (C * 2.25) ** 0.5
+    b = torch.randn(keep)
+    net = DenseNetNet.__new__(DenseNetNet)
+    net.device = cuda
+    tu = net._pack_deconv(Wd, b, C, keep)
+    xb = K.bn_relu_pack(xs, C, torch.empty((N, H, W, 64), dtype=torch.bfloat16, device=cuda), relu=False)
+    phases = [[K.conv2d(xb, tu['phases'][py][px][0], tu['phases'][py][px][1], tu['phases'][py][px][2], tu['phases'][py][px][3], 1,
+                        relu=False, out_f32=True, window=(1 if py else 0, 1 if px else 0, H + 1, W + 1)) for px in range(2)]
+              for py in range(2)]
+    skip_h, skip_w = 2 * H, 2 * W + 1
+    o = torch.zeros((N, skip_h, skip_w, 96), device=cuda)
+    K.deconv_interleave(phases, keep, ((2 * H + 1 - skip_h) // 2, 0), o)
+    ref = L.deconv2d(x.to(torch.bfloat16).float(), Wd.to(torch.bfloat16).float(), b, stride=2)
+    ref = ref[:, :, (2 * H + 1 - skip_h) // 2:(2 * H + 1 - skip_h) // 2 + skip_h, :skip_w]
+    got = o[..., :keep].cpu().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.fixture(scope='module')
+def dn(cuda):
+    from iterative_inference_segm_b200.models.FCDenseNet import build_fcdensenet
+    params = OD.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0)
+    fcn = build_fcdensenet(None, ['pool4'], 3, NCLS, params=params)
+    return params, fcn
+
+
+def test_densenet_forward_vs_oracle(cuda, dn):
+    from iterative_inference_segm_b200.functions import function_pred_fcn
+    params, fcn = dn
+    assert fcn[0].output_shape[1] == 464
+    X, _, _ = weights.synthetic_batch(2, 64, 96, NCLS, seed=9)
+    h_o, p_o = OD.densenet_forward(params, X, NCLS, layer=['pool4'])
+    h_d, p_d = function_pred_fcn(fcn)(X.numpy())
+    assert h_d.shape == tuple(h_o.shape) and p_d.shape == tuple(p_o.shape)
+    scale = float(h_o.abs().max())
+    eh, ep = float(np.abs(h_d - h_o.numpy()).max()) / scale, float(np.abs(p_d - p_o.numpy()).max())
+    agree = float((p_d.argmax(1) == p_o.numpy().argmax(1)).mean())
+    print('densenet parity: pool4 max-abs/scale %.3e  probs max-abs %.3e mean-abs %.3e  argmax agree %.4f' % (
+        eh, ep, float(np.abs(p_d - p_o.numpy()).mean()), agree))
+    assert eh < TOL_H and ep < TOL_P and agree >= MIN_AGREE
+    assert np.allclose(p_d.sum(1), 1.0, atol=1e-5)
+
+
+def test_densenet_plus_dae_loop_runs_and_tracks_oracle(cuda, dn):
+    """Config 3 wiring: DenseNet h (464 ch, padding 0) conditions DAE_h; 3 iterations vs the oracle loop."""
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import IterativeInference
+    params, fcn = dn
+    pd = weights.synthetic_dae_params(NCLS, 464, seed=1, out_gain=0.1)
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=fcn[0].output_shape[1], padding=0, concat_h=['pool4'],
+                   noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
+                   params=pd)
+    X, _, _ = weights.synthetic_batch(2, 64, 96, NCLS, seed=9)
+    out = fcn[0].net.forward(X.to(cuda), want=('pool4', 'probs_dimshuffle'))
+    res = IterativeInference(dae, NCLS, [NCLS]).run(out['pool4_bf16'], out['probs_dimshuffle'], 0.05, 3, eps=0.0)
+    h_o, y_o = OD.densenet_forward(params, X, NCLS, layer=['pool4'])
+    for _ in range(3):
+        y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, h_o, 0)), 0, 1)
+    y = res['y'].cpu()
+    assert res['n_exec'].cpu().tolist() == [3, 3]
+    print('densenet + dae loop: y max-abs %.3e  argmax agree %.4f' % (float((y - y_o).abs().max()),
+                                                                     float((y.argmax(1) == y_o.argmax(1)).float().mean())))
+    assert float((y - y_o).abs().max()) < TOL_P
+    assert float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= MIN_AGREE
