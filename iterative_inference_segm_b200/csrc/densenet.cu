@@ -16,60 +16,85 @@ namespace iiseg {
 // ---- BatchNorm (batch statistics) + rectify + bf16 pack ---------------------------------------------
 // out[p, c] = bf16( relu( (x[p, c0+c] - mean[c]) * (gamma[c] * inv_std[c]) + beta[c] ) ), c < C; 0 for C <= c < Cpad.
 // mean == NULL: plain copy/convert of the channel range (the deconv input of TransitionUp is not normalised).
+// Thread t owns the 8-channel group t % C8pad for the whole launch (the launch makes the thread count a
+// multiple of C8pad), keeps that group's BN coefficients in registers and walks pixels with 16-byte loads
+// (two float4 in, one uint4 out per pixel).
 __global__ void __launch_bounds__(256) bn_relu_pack_kernel(const float* __restrict__ x, long long P, int Cs, int c0, int C,
                                                            const float* __restrict__ mean, const float* __restrict__ inv_std,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int relu, uint4* __restrict__ out, int C8pad) {
-  const long long total = P * C8pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / C8pad;
-    const int cg = (int)(i - pix * C8pad);
-    float v[8];
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const int cg = (int)(tid % C8pad);
+  const long long pstep = nthr / C8pad;
+  const int cb = cg * 8;
+  const bool live = cb < C;                      // C is a multiple of 8 here: a group is all real or all padding
+  float mu[8], sc[8], be[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = cg * 8 + k;
-      float t = 0.f;
-      if (c < C) {
-        t = x[pix * Cs + c0 + c];
-        if (mean != nullptr) t = __fmaf_rn(__fsub_rn(t, __ldg(mean + c)), __fmul_rn(__ldg(gamma + c), __ldg(inv_std + c)), __ldg(beta + c));
-        if (relu) t = fmaxf(t, 0.f);
-      }
-      v[k] = t;
+  for (int k = 0; k < 8; ++k) {
+    mu[k] = 0.f; sc[k] = 1.f; be[k] = 0.f;
+    if (live && mean != nullptr) {
+      mu[k] = __ldg(mean + cb + k); sc[k] = __fmul_rn(__ldg(gamma + cb + k), __ldg(inv_std + cb + k)); be[k] = __ldg(beta + cb + k);
     }
-    stg_v4(out + i, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+  }
+  for (long long pix = tid / C8pad; pix < P; pix += pstep) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float4* src = reinterpret_cast<const float4*>(x + pix * Cs + c0 + cb);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      if (mean != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __fmaf_rn(__fsub_rn(v[k], mu[k]), sc[k], be[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+    }
+    stg_v4(out + pix * C8pad + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
   }
 }
 
 // ---- per-channel batch statistics --------------------------------------------------------------------
-// Level 1: block (32 channels x 8 pixel lanes) sums x and x^2 over a chunk of kStatChunk pixels in fp32 per
-// thread, combines the 8 lanes in fp64 and writes one (sum, sumsq) pair per (chunk, channel).
+// Level 1: a block sums x and x^2 over a chunk of kStatChunk pixels (fp32 per thread, 4 channels = one float4
+// per load), combines its pixel lanes in fp64 in a fixed order and writes one (sum, sumsq) pair per (chunk, channel).
 // Level 2: one thread per channel adds the chunks in index order (deterministic), biased variance,
 // inv_std = 1/sqrt(var + eps) (lasagne BatchNormLayer, epsilon = 1e-4).
 constexpr int kStatChunk = 2048;
 
+// block = (bx, 256 / bx): x walks groups of 4 channels (one float4), y walks pixels of the chunk
 __global__ void __launch_bounds__(256) channel_stats_partial_kernel(const float* __restrict__ x, long long P, int Cs, int c0, int C,
                                                                     double* __restrict__ partial) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index inside the channel range
+  const int c = c4 * 4;
   const long long p0 = (long long)blockIdx.y * kStatChunk;
   const long long p1 = p0 + kStatChunk < P ? p0 + kStatChunk : P;
-  float s = 0.f, q = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    for (long long p = p0 + threadIdx.y; p < p1; p += 8) {
-      const float v = x[p * Cs + c0 + c];
-      s += v;
-      q = __fmaf_rn(v, v, q);
+    for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * Cs + c0 + c));
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = __fmaf_rn(v.x, v.x, q[0]); q[1] = __fmaf_rn(v.y, v.y, q[1]); q[2] = __fmaf_rn(v.z, v.z, q[2]); q[3] = __fmaf_rn(v.w, v.w, q[3]);
     }
   }
-  __shared__ double sh[2][8][32];
-  sh[0][threadIdx.y][threadIdx.x] = (double)s;
-  sh[1][threadIdx.y][threadIdx.x] = (double)q;
+  __shared__ double sh[256][8];
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sh[t][k] = (double)s[k]; sh[t][4 + k] = (double)q[k]; }
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-    double ds = 0.0, dq = 0.0;
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    for (int yy = 0; yy < (int)blockDim.y; ++yy) {               // fixed order: deterministic
+      const int tt = yy * blockDim.x + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { ds += sh[0][k][threadIdx.x]; dq += sh[1][k][threadIdx.x]; }
-    partial[((size_t)blockIdx.y * C + c) * 2] = ds;
-    partial[((size_t)blockIdx.y * C + c) * 2 + 1] = dq;
+      for (int k = 0; k < 4; ++k) { ds[k] += sh[tt][k]; dq[k] += sh[tt][4 + k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      partial[((size_t)blockIdx.y * C + c + k) * 2] = ds[k];
+      partial[((size_t)blockIdx.y * C + c + k) * 2 + 1] = dq[k];
+    }
   }
 }
 
@@ -137,9 +162,18 @@ extern "C" int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, i
   IISEG_CHECK(x && out, "bn_relu_pack: null tensor");
   IISEG_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && Cpad >= C && Cpad % 8 == 0, "bn_relu_pack: bad shape C=%d Cs=%d Cpad=%d", C, Cs, Cpad);
   IISEG_CHECK(mean == nullptr || (inv_std && gamma && beta), "bn_relu_pack: incomplete BN parameters");
+  IISEG_CHECK(C % 8 == 0 && c0 % 4 == 0 && Cs % 4 == 0, "bn_relu_pack: C must be a multiple of 8, c0 / Cs of 4");
   const long long P = (long long)N * H * W;
-  bn_relu_pack_kernel<<<sgrid(P * (Cpad / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, P, Cs, c0, C, mean, inv_std, gamma, beta, relu, reinterpret_cast<uint4*>(out), Cpad / 8);
+  const int C8 = Cpad / 8;
+  int gcd = C8, r = 256;
+  while (r) { const int t = gcd % r; gcd = r; r = t; }
+  const int unit = C8 / gcd;                                  // grid must be a multiple of this: thread count % C8pad == 0
+  long long blocks = (P * C8 + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  blocks = (blocks + unit - 1) / unit * unit;
+  bn_relu_pack_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, P, Cs, c0, C, mean, inv_std, gamma, beta, relu, reinterpret_cast<uint4*>(out), C8);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -157,7 +191,9 @@ extern "C" int iiseg_channel_stats(const float* x, int N, int H, int W, int Cs, 
   const long long P = (long long)N * H * W;
   const int n_chunks = iiseg_channel_stats_chunks(N, H, W);
   IISEG_CHECK(n_chunks <= 65535, "channel_stats: too many pixels");
-  dim3 grid((C + 31) / 32, n_chunks), block(32, 8);
+  IISEG_CHECK(C % 4 == 0 && c0 % 4 == 0 && Cs % 4 == 0, "channel_stats: channel counts must be multiples of 4");
+  const int bx = (C / 4) >= 16 ? 16 : 4;
+  dim3 grid((C / 4 + bx - 1) / bx, n_chunks), block(bx, 256 / bx);
   channel_stats_partial_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, P, Cs, c0, C, scratch);
   IISEG_LAUNCH_CHECK();
   channel_stats_final_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scratch, n_chunks, C, 1.0 / (double)P, eps,

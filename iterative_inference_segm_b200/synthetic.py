@@ -79,6 +79,53 @@ def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
     return params
 
 
+N_LAYERS_103 = [4, 5, 7, 10, 12, 15, 12, 10, 7, 5, 4]
+
+
+def densenet_shapes(nb_in_channels=3, n_classes=11, n_first=48, n_pool=5, growth=16, n_layers=N_LAYERS_103):
+    """(name, kind, W shape) of FC-DenseNet103's 103 parameterised layers in creation order
+    (models/FCDenseNet.py:61-141): kind 'conv' -> W, b; 'bnconv' -> beta, gamma, mean, inv_std, W, b;
+    'deconv' -> W (in, out, 3, 3), b."""
+    out = [('first_conv', 'conv', (n_first, nb_in_channels, 3, 3))]
+    n, skips = n_first, []
+    for i in range(n_pool):
+        for j in range(n_layers[i]):
+            out.append(('down%d_l%d' % (i, j), 'bnconv', (growth, n, 3, 3)))
+            n += growth
+        skips.append(n)
+        out.append(('td%d' % i, 'bnconv', (n, n, 1, 1)))
+    skips = skips[::-1]
+    for j in range(n_layers[n_pool]):
+        out.append(('bottleneck_l%d' % j, 'bnconv', (growth, n, 3, 3)))
+        n += growth
+    up_ch = growth * n_layers[n_pool]
+    for i in range(n_pool):
+        keep = growth * n_layers[n_pool + i]
+        out.append(('tu%d' % i, 'deconv', (up_ch, keep, 3, 3)))
+        n = keep + skips[i]
+        for j in range(n_layers[n_pool + i + 1]):
+            out.append(('up%d_l%d' % (i, j), 'bnconv', (growth, n, 3, 3)))
+            n += growth
+        up_ch = growth * n_layers[n_pool + i + 1]
+    out.append(('softmax_conv', 'conv', (n_classes, n, 1, 1)))
+    return out
+
+
+def synthetic_densenet_params(nb_in_channels=3, n_classes=11, seed=2, logit_gain=1.0):
+    """HeUniform conv / deconv W, zero b, BatchNorm beta 0 / gamma 1 (lasagne defaults); the final 1x1 conv x logit_gain."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, kind, ws in densenet_shapes(nb_in_channels, n_classes):
+        W = _uniform(ws, (6.0 / (ws[1] * ws[2] * ws[3])) ** 0.5, gen)
+        if name == 'softmax_conv':
+            W = W * logit_gain
+        cin, cout = (ws[1], ws[0]) if kind != 'deconv' else (ws[0], ws[1])
+        if kind == 'bnconv':
+            params += [torch.zeros(cin), torch.ones(cin), torch.zeros(cin), torch.ones(cin)]
+        params += [W, torch.zeros(cout)]
+    return params
+
+
 def synthetic_batch(B, H, W, n_classes=11, seed=0):
     """X (B,3,H,W) U[0,1); one-hot float32 targets (B, n_classes+1, H, W), label n_classes = void; labels."""
     gen = torch.Generator().manual_seed(seed)

@@ -99,3 +99,8 @@ def test_synthetic_recipe_matches_oracle_copy():
         assert torch.equal(a, b)
     for a, b in zip(S.synthetic_batch(2, 12, 16, 11, seed=7), OW.synthetic_batch(2, 12, 16, 11, seed=7)):
         assert torch.equal(a, b)
+    from oracle import densenet as OD
+    pa, pb = S.synthetic_densenet_params(3, 11, seed=2, logit_gain=4.0), OD.synthetic_densenet_params(3, 11, seed=2, logit_gain=4.0)
+    assert len(pa) == len(pb) == 590
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)

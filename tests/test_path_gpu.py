@@ -290,3 +290,23 @@ def test_fused_update_epilogue_equals_standalone_kernel(cuda, built):
     one = ii.run(h2, y0, 0.05, 1, eps=0.0, use_graph=False)['y'].clone()
     many = ii.run(h2, y0, 0.05, 3, eps=1e9, use_graph=False)
     assert many['n_exec'].cpu().tolist() == [1, 1] and torch.equal(many['y'], one)
+
+
+def test_config1_224x224_one_image_10_steps(cuda, built, built_f32):
+    """BASELINE.json configs[0]: FCN8 + DAE_h, 1 synthetic 224x224 image, 11 classes, 10 steps, step 0.05 -- the
+    reference's own CPU-runnable case -- free-running against the oracle, both arithmetic variants."""
+    from iterative_inference_segm_b200.functions import function_pred_fcn, IterativeInference
+    X, L, lab = weights.synthetic_batch(1, 224, 224, NCLS, seed=11)
+    pf, pd = built[0], built[1]
+    h_o, y_o = nets.fcn8_forward(pf, X, NCLS)
+    for _ in range(10):
+        y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, h_o, 100)), 0, 1)
+    for (_, _, fcn, dae), tol, agree in ((built_f32, TOL_F32, MIN_ARGMAX_F32), (built, 5e-2, 0.98)):
+        h_d, y0_d = function_pred_fcn(fcn)(X.to(cuda))
+        res = IterativeInference(dae, NCLS, [NCLS]).run(h_d, y0_d, 0.05, 10, labels=lab.to(torch.int32).to(cuda))
+        y = res['y'].cpu()
+        assert res['n_exec'].cpu().tolist() == [10]
+        assert float((y - y_o).abs().max()) < tol, float((y - y_o).abs().max())
+        assert float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
+        onehot = np.eye(NCLS + 1, dtype=np.float32)[lab.numpy()].transpose(0, 3, 1, 2)
+        assert np.array_equal(res['cm'].sum(0).cpu().numpy().reshape(NCLS, NCLS), M.confusion_matrix(y.numpy(), onehot, NCLS))
