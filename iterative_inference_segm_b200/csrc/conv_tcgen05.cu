@@ -37,7 +37,8 @@ constexpr int kBlockK = 64;                 // bf16 elements: one 128-byte swizz
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * 128;  // 16 KiB per k-block
 constexpr int kStagingBytes = kBlockM * 128; // one 64-channel bf16 output chunk
-constexpr int kNumThreads = 384;             // 4 pipeline warps + 8 epilogue warps
+constexpr int kNumThreads = 384;             // per-tap kernel: 4 pipeline warps + 8 epilogue warps
+constexpr int kNumThreadsHalo = 640;         // halo-tile kernel: 4 pipeline warps + 16 epilogue warps
 constexpr int kEpilogueThreads = 256;
 constexpr long long kTimeoutCycles = 4000000000LL;  // ~2 s: a stuck pipeline traps instead of hanging
 
@@ -325,6 +326,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
 // (update.cu), operation for operation, so fused and unfused loops give bit-identical y.  The norm is
 // summed in 2^-40 fixed point with integer atomics: order-independent, hence deterministic.
 // The two warps of a TMEM lane quadrant alternate tiles (group g = tile parity = accumulator stage).
+template <int kGroups>
 __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
                                                        uint32_t tmem_empty_bar0, int warp, int lane) {
   const int q = warp & 3;
@@ -366,6 +368,7 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
   float yn[16];
   PixelRef nxt;
   nxt.go = false; nxt.yb = nullptr; nxt.n = 0; nxt.pixoff = 0;
+  static_assert(kGroups == 2 || kGroups == 4, "one group per accumulator stage parity / per stage");
   if (blockIdx.x + grp * gridDim.x < p.num_tiles) {
     nxt = locate(grp);
     if (nxt.go) {
@@ -373,7 +376,7 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
       for (int c = 0; c < 16; ++c) if (c < C) yn[c] = nxt.yb[static_cast<size_t>(c) * HW];
     }
   }
-  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += kGroups) {
     const PixelRef cur = nxt;
     if (cur.n != n_acc) { if (n_acc >= 0) flush(); n_acc = cur.n; }     // warp-uniform
     const int as = iter & (p.acc_stages - 1);                              // a stage has the parity of its tiles = grp
@@ -382,8 +385,8 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
     float yv[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) yv[c] = yn[c];
-    if (blockIdx.x + (iter + 2) * gridDim.x < p.num_tiles) {      // request this group's next tile before waiting
-      nxt = locate(iter + 2);
+    if (blockIdx.x + (iter + kGroups) * gridDim.x < p.num_tiles) {      // request this group's next tile before waiting
+      nxt = locate(iter + kGroups);
       if (nxt.go) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) if (c < C) yn[c] = nxt.yb[static_cast<size_t>(c) * HW];
@@ -798,7 +801,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     }
   } else if (warp >= 4) {
     if constexpr (BN == 16) {
-      if (p.upd_y != nullptr) conv_epilogue16_update(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      if (p.upd_y != nullptr) conv_epilogue16_update<2>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     } else if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
@@ -809,6 +812,124 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Epilogue of the halo-tile kernel (BN = 64 / 128): FOUR groups of four warps (warps 4-19), group g
+// drains accumulator stage g = tile index mod 4.  The high-resolution layers have short main loops
+// (9-72 MMAs per tile), so their epilogues -- latency-bound chains of TMEM load, convert, shuffle, store
+// -- set the pace; with four tiles in flight and 16 instead of 8 warps the chains overlap (measured with
+// two groups: conv1_1 105 us of 113 with neither loads nor MMAs).  16 accumulator columns per step keep
+// the kernel under the 102 registers per thread that 640 threads leave.  Same arithmetic as
+// conv_epilogue<.., kSplit = false>: + bias, + bf16 skip-sum operand (prefetched a step / a tile ahead),
+// bf16 rounding, ReLU, then either 32-byte global stores, fp32 rows, or the shuffle pool + tie mask on
+// pitch-16 boxes (lanes {l, l^1, l^16, l^17} hold a 2x2 window).
+// ---------------------------------------------------------------------------
+template <int BN, bool kPool>
+__device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                              uint32_t tmem_empty_bar0, int warp, int lane) {
+  const int q = warp & 3;
+  const int grp = (warp - 4) >> 2;          // 0..3 = accumulator stage
+  const int macc = q * 32 + lane;
+  const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+  const bool in_box = (hl < p.TH) && (wl < p.TW);
+  const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * grp, tmem_empty_bar = tmem_empty_bar0 + 8u * grp;
+  const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp * BN) + (static_cast<uint32_t>(q * 32) << 16);
+  const int pos = ((lane >> 4) << 1) | (lane & 1);            // pool: window position 2*dy + dx of this lane
+  const uint32_t posbits = (1u << pos) | (1u << (16 + pos));
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 4) {
+    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+    const uint32_t aphase = static_cast<uint32_t>(iter >> 2) & 1u;
+    const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+    const bool has_add = !kPool && (p.addend != nullptr) && valid;
+    const __nv_bfloat16* arow = p.addend + ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.Cout;
+    uint4 add[2];
+    if (has_add) { add[0] = ldg_nc_v4(arow); add[1] = ldg_nc_v4(arow + 8); }      // before the accumulator is ready
+    mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 16; ++chunk) {
+      const int cbase = chunk * 16;
+      uint32_t v[16];
+      tmem_ld_x16(taddr + cbase, v);
+      uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+      if (has_add) {
+        a0 = add[0]; a1 = add[1];
+        if (chunk + 1 < BN / 16) { add[0] = ldg_nc_v4(arow + cbase + 16); add[1] = ldg_nc_v4(arow + cbase + 24); }
+      }
+      tmem_ld_wait();
+      if (chunk == BN / 16 - 1) {   // all TMEM reads of this accumulator are done
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar);
+      }
+      float f[16];
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = __ldg(bias4 + j4);
+        f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+        f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+      }
+      if (has_add) {
+        const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(aw[k]); f[2 * k + 1] += bf16_hi(aw[k]); }
+      }
+      if (!kPool && p.out_f32) {          // fp32 rows (DenseNet's first conv): 64 contiguous bytes per thread
+        if (valid) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cs + cbase;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = f[4 * j], b = f[4 * j + 1], c = f[4 * j + 2], d = f[4 * j + 3];
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); d = fmaxf(d, 0.f); }
+            stg_v4(o + 4 * j, make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d)));
+          }
+        }
+        continue;
+      }
+      uint32_t hi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        if (p.relu) hi[j] = bf16x2_max(hi[j], 0u);      // max(x, 0) commutes with the bf16 rounding
+      }
+      if constexpr (!kPool) {
+        if (valid) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
+          stg_v4(o, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          stg_v4(o + 8, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+        }
+      } else {
+        // Fused Pool2DLayer(2) + tie mask (models/fcn_down.py:122, layers/mylayers.py:111-112) on registers
+        uint32_t mx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t t = bf16x2_max(hi[j], __shfl_xor_sync(0xffffffffu, hi[j], 1));
+          mx[j] = bf16x2_max(t, __shfl_xor_sync(0xffffffffu, t, 16));
+        }
+        uint32_t word[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t part = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) part |= bf16x2_eq_mask(hi[4 * g + k], mx[4 * g + k]) & (posbits << (4 * k));
+          part |= __shfl_xor_sync(0xffffffffu, part, 1);
+          part |= __shfl_xor_sync(0xffffffffu, part, 16);
+          word[g] = part;
+        }
+        const int phw = ((tc.th * p.TH) >> 1) + (hl >> 1), pww = ((tc.tw * p.TW) >> 1) + (wl >> 1);   // inside the window
+        if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w) {
+          const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + p.p_h0 + phw) * p.PW + p.p_w0 + pww;
+          stg_v4(p.pooled + ppix * p.Cout + cbase, make_uint4(mx[0], mx[1], mx[2], mx[3]));
+          stg_v4(p.pooled + ppix * p.Cout + cbase + 8, make_uint4(mx[4], mx[5], mx[6], mx[7]));
+          if (p.pool_mask != nullptr)
+            *reinterpret_cast<uint2*>(p.pool_mask + ppix * (p.Cout >> 3) + (cbase >> 3)) = make_uint2(word[0], word[1]);
+        }
+      }
+    }
   }
 }
 
@@ -850,7 +971,7 @@ struct HaloCfg {
 };
 
 template <int BN, int KB>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = HaloCfg<BN, KB>;
   const int S = p.acc_stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -973,10 +1094,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
     }
   } else if (warp >= 4) {
     if constexpr (BN == 16) {
-      if (p.upd_y != nullptr) conv_epilogue16_update(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-      else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    } else if (p.pooled != nullptr) conv_epilogue<BN, false, true>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN, false, false>(p, tmem_base, 0u, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      if (p.upd_y != nullptr) conv_epilogue16_update<4>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else if (warp < 12) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);      // 8 warps suffice
+    } else if (p.pooled != nullptr) halo_epilogue<BN, true>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else halo_epilogue<BN, false>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -1085,7 +1206,7 @@ static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t st
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_halo_kernel<BN, KB><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  conv_halo_kernel<BN, KB><<<grid, kNumThreadsHalo, smem_bytes, stream>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -1234,10 +1355,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   {
     // halo kernel, BN 64/128: 4 accumulator stages (an issuer runs a tile ahead of its epilogue group);
     // 16-channel outputs measured faster with 2 (0.087 vs 0.107 ms on up_conv1)
-    static const int env_s = getenv("IISEG_HALO_S") ? atoi(getenv("IISEG_HALO_S")) : 4;
-    static const int env_us = getenv("IISEG_UPD_S") ? atoi(getenv("IISEG_UPD_S")) : 4;
-    p.acc_stages = (halo && BN >= 64 && env_s == 4) ? 4 : 2;
-    if (halo && BN == 16 && d->upd_y != nullptr && env_us == 4) p.acc_stages = 4;     // two groups, each an issuer's two stages
+    p.acc_stages = (halo && (BN >= 64 || d->upd_y != nullptr)) ? 4 : 2;     // one stage per epilogue group
   }
   {
     static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0;
