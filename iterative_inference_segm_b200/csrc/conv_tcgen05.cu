@@ -19,8 +19,8 @@
 //     one thread; accumulators live in TMEM, double-buffered (2 x BN columns) so
 //     the epilogue of tile i overlaps the main loop of tile i+1.
 //   * Warp roles: warp 0 TMA producer, warp 1 (+3) MMA issuer(s), warp 2 TMEM
-//     allocator, warps 4-11 epilogue in two groups of four, one per accumulator
-//     stage (tcgen05.ld -> bias/ReLU/skip-sum -> bf16 -> global memory, or the fused
+//     allocator, warps 4-11 (per-tap kernel) / 4-19 (halo-tile kernel) epilogue in
+//     groups of four, one group per accumulator stage (tcgen05.ld -> bias/ReLU/skip-sum -> bf16 -> global memory, or the fused
 //     2x2 max-pool + tie mask through a per-group smem tile, or fp32 16-channel
 //     rows).  Persistent CTAs, one per SM, static round-robin tile schedule.
 #include <cuda.h>
@@ -1353,8 +1353,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
   p.out_cs = d->out_cs > 0 ? d->out_cs : d->Cout;
   {
-    // halo kernel, BN 64/128: 4 accumulator stages (an issuer runs a tile ahead of its epilogue group);
-    // 16-channel outputs measured faster with 2 (0.087 vs 0.107 ms on up_conv1)
+    // halo kernel, BN 64/128 and the fused-update logits conv: 4 accumulator stages, one per epilogue group (an
+    // issuer runs a tile ahead of the drains); plain 16-channel outputs measured faster with 2 stages drained
+    // by 8 warps together (0.087 vs 0.107 ms on up_conv1)
     p.acc_stages = (halo && (BN >= 64 || d->upd_y != nullptr)) ? 4 : 2;     // one stage per epilogue group
   }
   {
