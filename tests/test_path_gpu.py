@@ -310,3 +310,29 @@ def test_config1_224x224_one_image_10_steps(cuda, built, built_f32):
         assert float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
         onehot = np.eye(NCLS + 1, dtype=np.float32)[lab.numpy()].transpose(0, 3, 1, 2)
         assert np.array_equal(res['cm'].sum(0).cpu().numpy().reshape(NCLS, NCLS), M.confusion_matrix(y.numpy(), onehot, NCLS))
+
+
+def test_full_size_properties_360x480(cuda, built):
+    """BASELINE.json configs[1] size (360x480, 11 classes), checked through size-independent properties:
+    probabilities are a distribution, the confusion matrix counts exactly the non-void pixels, replays are
+    bit-identical, and images do not interact -- an image iterated inside a batch of 3 gives bit-identical
+    y to the same image iterated alone (no cross-image coupling, position-independent K order)."""
+    from iterative_inference_segm_b200.functions import IterativeInference
+    pf, pd, fcn, dae = built
+    X, L, lab = weights.synthetic_batch(3, 360, 480, NCLS, seed=21)
+    net = fcn[0].net
+    out = net.forward(X.to(cuda), want=('pool4', 'probs_dimshuffle'))
+    h, y0 = out['pool4'].clone(), out['probs_dimshuffle'].clone()
+    assert torch.allclose(y0.sum(1), torch.ones_like(y0[:, 0]), atol=1e-5) and float(y0.min()) >= 0.0
+    labels = lab.to(torch.int32).to(cuda)
+    ii = IterativeInference(dae, NCLS, [NCLS])
+    r1 = ii.run(h, y0, 0.05, 5, labels=labels)
+    y_a, cm_a = r1['y'].clone(), r1['cm'].clone()
+    r2 = ii.run(h, y0, 0.05, 5, labels=labels)
+    assert torch.equal(r2['y'], y_a) and torch.equal(r2['cm'], cm_a)                       # deterministic replay
+    assert float(y_a.min()) >= 0.0 and float(y_a.max()) <= 1.0
+    assert cm_a.sum(1).cpu().tolist() == [int((lab[i] != NCLS).sum()) for i in range(3)]     # every non-void pixel counted once
+    assert r1['counts'][:, 1].cpu().tolist() == [int((lab[i] != NCLS).sum()) for i in range(3)]
+    alone = IterativeInference(dae, NCLS, [NCLS]).run(h[1:2].contiguous(), y0[1:2].contiguous(), 0.05, 5,
+                                                      labels=labels[1:2].contiguous())
+    assert torch.equal(alone['y'][0], y_a[1]) and torch.equal(alone['cm'][0], cm_a[1])        # images do not interact
