@@ -76,6 +76,8 @@ struct alignas(64) ConvParams {
   int TH, TW;
   int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
   int a_blk_bytes, n_a;     // halo kernel: halo-block size and ring depth
+  int pair;                 // CTA-pair kernel (cta_group::2): work units are (N-tile, pair of M-tiles)
+  int num_units, m_tiles;   // pair kernel: n_ntiles * ceil(m_tiles / 2) units; m_tiles = N * tiles_h * tiles_w
   int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
@@ -228,6 +230,19 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
   TileCoord c;
   int rest = fast_divmod(t, p.n_ntiles, p.inv_ntiles);  c.nt = t;    // t = nt + n_ntiles * rest
   int rest2 = fast_divmod(rest, p.tiles_w, p.inv_tiles_w); c.tw = rest;
+  c.n = fast_divmod(rest2, p.tiles_h, p.inv_tiles_h);   c.th = rest2;
+  return c;
+}
+
+// CTA-pair kernel: unit u = (N-tile nt, pair of M-tiles mp); CTA `rank` of the pair owns M-tile 2*mp + rank.
+// An odd M-tile count leaves the last pair's peer a dummy: it recomputes the last real tile and stores nothing.
+__device__ __forceinline__ TileCoord decode_unit(const ConvParams& p, int u, int rank, bool* dummy) {
+  TileCoord c;
+  int mp = fast_divmod(u, p.n_ntiles, p.inv_ntiles);   c.nt = u;
+  int mt = 2 * mp + rank;
+  *dummy = mt >= p.m_tiles;
+  if (*dummy) mt = p.m_tiles - 1;
+  int rest2 = fast_divmod(mt, p.tiles_w, p.inv_tiles_w); c.tw = mt;
   c.n = fast_divmod(rest2, p.tiles_h, p.inv_tiles_h);   c.th = rest2;
   return c;
 }
@@ -448,13 +463,22 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
   const uint32_t sbuf = smem_stage_out + grp * kStagingBytes;
   const int et = (warp & 3) * 32 + lane;  // thread index inside the group
   const int cpp = kSplit ? 2 * p.Cout : p.Cout;      // channels per pixel of out / addend / pooled
-  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
-    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+  for (int iter = grp;; iter += 2) {
+    TileCoord tc;
+    bool dummy = false;
+    if (p.pair) {
+      const int u = (blockIdx.x >> 1) + iter * (gridDim.x >> 1);
+      if (u >= p.num_units) break;
+      tc = decode_unit(p, u, blockIdx.x & 1, &dummy);
+    } else {
+      if (blockIdx.x + iter * gridDim.x >= p.num_tiles) break;
+      tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+    }
     const int as = iter & (p.acc_stages - 1);            // 2 or 4 stages: a stage has the parity of its tiles, i.e. of the group
     const uint32_t aphase = static_cast<uint32_t>(iter >> (p.acc_stages >> 1)) & 1u;
     const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * as, tmem_empty_bar = tmem_empty_bar0 + 8u * as;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
-    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW) && !dummy;
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
     const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
     const int n0 = tc.nt * BN;
@@ -496,7 +520,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         tmem_ld_wait();
         if (chunk == BN / 32 - 1) {   // all TMEM reads of this accumulator are done
           tcgen05_fence_before();
-          mbar_arrive(tmem_empty_bar);
+          if (p.pair) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty_bar & 0xFEFFFFFFu) : "memory");   // the leader's
+          else mbar_arrive(tmem_empty_bar);
         }
         float f[32];
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
@@ -582,7 +607,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
             word[g] = part;
           }
           const int phw = ((tc.th * p.TH) >> 1) + (hl >> 1), pww = ((tc.tw * p.TW) >> 1) + (wl >> 1);   // inside the window
-          if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w) {
+          if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w && !dummy) {
             const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + p.p_h0 + phw) * p.PW + p.p_w0 + pww;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -623,7 +648,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               const int ph_l = fast_divmod(pw_l, tw2, p.inv_tw2);
               const int phw = ((tc.th * p.TH) >> 1) + ph_l, pww = ((tc.tw * p.TW) >> 1) + pw_l;   // inside the window
               const int ph = p.p_h0 + phw, pw = p.p_w0 + pww;                                      // inside the tensor
-              if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w) {
+              if (ph_l < (p.TH >> 1) && phw < p.pwin_h && pww < p.pwin_w && !dummy) {
                 const int m00 = (2 * ph_l) * p.TW + 2 * pw_l;
                 uint32_t w[4][4], wl_[kSplit ? 4 : 1][4];
 #pragma unroll
@@ -750,8 +775,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
               if (g < g_n) {
                 int src = 0, cbl = cb;      // which source this channel block belongs to (concat in the loader)
                 while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
-                tma_load_4d(stage_a(stage, g), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
-                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN);
+                // tuning: bit5 = every CTA fetches tile 0's A boxes, bit6 = every CTA fetches N-tile 0's B blocks
+                tma_load_4d(stage_a(stage, g), &p.tm_src[src], full_bar(stage), cbl * kBlockK, (p.dbg & 32) ? s : w_base + s,
+                            (p.dbg & 32) ? r : h_base + r, (p.dbg & 32) ? 0 : tc.n);
+                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK, (p.dbg & 64) ? 0 : tc.nt * BN);
                 ++kb;
                 if (++cb == n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
               }
@@ -812,6 +839,158 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant of the per-tap kernel (BN = 256): tcgen05.mma.cta_group::2, M = 256 over two SMs.
+//
+// Measured: the single-CTA kernel is bound by what one SM can ingest through TMA (~55-64 B/clk; the
+// time of a loads-only run does not change when every CTA fetches the SAME lines, so it is not L2
+// read bandwidth): a 128 x 256 tile needs 48 KB per 64-channel k-block for 512 tensor cycles.  A
+// cluster of two CTAs computes a 256 x 256 tile instead: each CTA loads its own 128-pixel A box and
+// only HALF of the filter block (128 of the 256 output channels); the leader's MMAs read A rows
+// 0-127 / B rows 0-127 from its own smem and rows 128-255 from the peer's at the same offsets and
+// write each CTA's 128 accumulator rows into that CTA's TMEM.  32 KB per SM per k-block.
+// Protocol: both CTAs' TMA loads complete_tx on the LEADER's full barrier (peer bit cleared in the
+// mbarrier address); the leader's MMA warp commits with .multicast::cluster to both CTAs' empty and
+// tmem_full barriers; both CTAs' epilogue threads arrive on the leader's tmem_empty barrier.
+// A work unit is (N-tile, pair of M-tiles); an odd M-tile count gives the last pair's peer a dummy
+// tile (it recomputes the leader's tile and stores nothing).
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even CTA
+constexpr int kPairStageBytes = kAStageBytes + 128 * 128;        // A box + half filter block
+constexpr int kPairStages = (227 * 1024 - 1024 - 256 - 2 * kStagingBytes) / kPairStageBytes;
+constexpr int kPairSmemBytes = 1024 + kPairStages * kPairStageBytes + 2 * kStagingBytes + 256;
+
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {       // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv_igemm_pair_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int BN = 256;
+  constexpr int kStages = kPairStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto stage_a = [&](int i) { return smem_base + i * kPairStageBytes; };
+  auto stage_b = [&](int i) { return smem_base + i * kPairStageBytes + kAStageBytes; };
+  const uint32_t smem_stage_out = smem_base + kStages * kPairStageBytes;
+  const uint32_t bars = smem_stage_out + 2 * kStagingBytes;
+  auto full_bar = [&](int i) { return bars + 8u * i; };
+  auto empty_bar = [&](int i) { return bars + 8u * (kStages + i); };
+  auto tmem_full_bar = [&](int i) { return bars + 8u * (2 * kStages + i); };
+  auto tmem_empty_bar = [&](int i) { return bars + 8u * (2 * kStages + 2 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = blockIdx.x & 1;                 // cluster dims (2,1,1): rank in the pair, 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
+    prefetch_tmap(&p.tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), kEpilogueThreads); }   // 128 threads of each CTA
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer's barriers exist before anything signals them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int num_k_blocks = p.R * p.S * p.n_cblk;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one_sync()) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t stage_bytes = (static_cast<uint32_t>(p.TH * p.TW) * 128u + 128u * 128u) * 2u;     // both CTAs' A box + filter half
+      for (int u = pair; u < p.num_units; u += n_pairs) {
+        bool dummy;
+        const TileCoord tc = decode_unit(p, u, rank, &dummy);
+        const int h_base = tc.th * p.TH + p.in_off_h;
+        const int w_base = tc.tw * p.TW + p.in_off_w;
+        int r = 0, s = 0, cb = 0;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.diag, 1, stage);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          int src = 0, cbl = cb;
+          while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
+          tma_load_4d_2sm(stage_a(stage), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
+          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN + rank * 128);
+          if (++cb == p.n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                               (static_cast<uint32_t>(256 >> 4) << 24);          // M = 256 over the pair
+    int stage = 0; uint32_t phase = 0;
+    int iter = 0;
+    for (int u = pair; u < p.num_units; u += n_pairs, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1u;
+      mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase, p.diag, 3, stage);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t a_desc = make_smem_desc(stage_a(stage));
+          const uint64_t b_desc = make_smem_desc(stage_b(stage));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(empty_bar(stage));                        // frees the smem slot in both CTAs
+          if (kb == num_k_blocks - 1) umma_commit_2sm(tmem_full_bar(as));    // both CTAs' accumulator halves ready
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // nobody leaves (or frees TMEM) while the pair still works
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -1364,6 +1543,25 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     p.dbg = env_dbg; p.stages = env_stages;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    static const int env_pair = getenv("IISEG_CONV_PAIR") ? atoi(getenv("IISEG_CONV_PAIR")) : 1;     // 0: single-CTA kernel (A/B comparison)
+    if (env_pair && !halo && BN == 256 && KB == 64) {
+      p.pair = 1;
+      p.m_tiles = d->N * p.tiles_h * p.tiles_w;
+      p.num_units = p.n_ntiles * ((p.m_tiles + 1) / 2);
+      if (encode_weight(&p.tm_w, d->weight, d->Cout, K, 128, KB)) return -1;       // each CTA loads half of a filter block
+      static bool configured = false;
+      if (!configured) {
+        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+        configured = true;
+      }
+      const int max_pairs = num_sms() / 2;
+      const int grid = 2 * (p.num_units < max_pairs ? p.num_units : max_pairs);
+      conv_igemm_pair_kernel<<<grid, kNumThreads, kPairSmemBytes, s>>>(p);
+      IISEG_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (halo) {
     if (KB == 16) {
       switch (BN) {
