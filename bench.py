@@ -279,8 +279,8 @@ def run_b200(args):
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get('conv_igemm_pair_kernel', {}).get('dram_bytes_per_launch')
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM, 256-channel tiles; %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1..conv6_1, up_conv6..up_conv4; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
+                traffic = json.load(fh).get('conv_igemm_pair_kernel<256>', {}).get('dram_bytes_per_launch')
+        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<256> (tcgen05 cta_group::2 implicit GEMM, 256 x 256 tiles over CTA pairs; %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1..conv6_1, up_conv6..up_conv4; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': dom_ms / len(dom),
                 'flops_per_launch': dom_flops / len(dom),

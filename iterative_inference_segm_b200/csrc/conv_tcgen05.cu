@@ -859,9 +859,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
 // tile (it recomputes the leader's tile and stores nothing).
 // ---------------------------------------------------------------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the pair's even CTA
-constexpr int kPairStageBytes = kAStageBytes + 128 * 128;        // A box + half filter block
-constexpr int kPairStages = (227 * 1024 - 1024 - 256 - 2 * kStagingBytes) / kPairStageBytes;
-constexpr int kPairSmemBytes = 1024 + kPairStages * kPairStageBytes + 2 * kStagingBytes + 256;
+template <int BN>
+struct PairCfg {
+  static constexpr int kStageBytes = kAStageBytes + (BN / 2) * 128;        // A box + half filter block
+  static constexpr int kStagesRaw = (227 * 1024 - 1024 - 256 - 2 * kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kStagingBytes + 256;
+  static constexpr int kTmemCols = 2 * BN;                                  // 512 or 256
+};
 
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -887,9 +892,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv_igemm_pair_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int BN = 256;
-  constexpr int kStages = kPairStages;
+  constexpr int kStages = PairCfg<BN>::kStages;
+  constexpr int kPairStageBytes = PairCfg<BN>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto stage_a = [&](int i) { return smem_base + i * kPairStageBytes; };
@@ -918,7 +924,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(PairCfg<BN>::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -933,7 +939,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
     // ===================== TMA producer (both CTAs) =====================
     if (elect_one_sync()) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t stage_bytes = (static_cast<uint32_t>(p.TH * p.TW) * 128u + 128u * 128u) * 2u;     // both CTAs' A box + filter half
+      const uint32_t stage_bytes = (static_cast<uint32_t>(p.TH * p.TW) * 128u + (BN / 2) * 128u) * 2u;     // both CTAs' A box + filter half
       for (int u = pair; u < p.num_units; u += n_pairs) {
         bool dummy;
         const TileCoord tc = decode_unit(p, u, rank, &dummy);
@@ -946,7 +952,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
           int src = 0, cbl = cb;
           while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
           tma_load_4d_2sm(stage_a(stage), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
-          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN + rank * 128);
+          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN + rank * (BN / 2));
           if (++cb == p.n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -990,7 +996,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
   cluster_sync_all();                               // nobody leaves (or frees TMEM) while the pair still works
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PairCfg<BN>::kTmemCols) : "memory");
   }
 }
 
@@ -1545,19 +1551,21 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {
     static const int env_pair = getenv("IISEG_CONV_PAIR") ? atoi(getenv("IISEG_CONV_PAIR")) : 1;     // 0: single-CTA kernel (A/B comparison)
-    if (env_pair && !halo && BN == 256 && KB == 64) {
+    if (env_pair && !halo && (BN == 256 || BN == 128) && KB == 64) {
       p.pair = 1;
       p.m_tiles = d->N * p.tiles_h * p.tiles_w;
       p.num_units = p.n_ntiles * ((p.m_tiles + 1) / 2);
-      if (encode_weight(&p.tm_w, d->weight, d->Cout, K, 128, KB)) return -1;       // each CTA loads half of a filter block
-      static bool configured = false;
-      if (!configured) {
-        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
-        configured = true;
-      }
+      if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN / 2, KB)) return -1;       // each CTA loads half of a filter block
       const int max_pairs = num_sms() / 2;
       const int grid = 2 * (p.num_units < max_pairs ? p.num_units : max_pairs);
-      conv_igemm_pair_kernel<<<grid, kNumThreads, kPairSmemBytes, s>>>(p);
+      static bool configured = false;
+      if (!configured) {
+        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::kSmemBytes));
+        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::kSmemBytes));
+        configured = true;
+      }
+      if (BN == 256) conv_igemm_pair_kernel<256><<<grid, kNumThreads, PairCfg<256>::kSmemBytes, s>>>(p);
+      else conv_igemm_pair_kernel<128><<<grid, kNumThreads, PairCfg<128>::kSmemBytes, s>>>(p);
       IISEG_LAUNCH_CHECK();
       return 0;
     }
