@@ -98,6 +98,9 @@ typedef struct iiseg_conv_desc {
    * written; `out` is not touched.  Needs Cout % 64 == 0.                                  */
   void* pooled;
   uint32_t* pool_mask;
+  /* training only (may be NULL): same layout as pool_mask, bit set iff the pre-rectifier value of that element is
+   * exactly 0 -- lasagne's rectify is 0.5*(x+|x|), whose gradient at 0 is 0.5 (iiseg_pool2_relu_bwd). */
+  uint32_t* pool_zmask;
   /* pool_H > 0: `pooled`/`pool_mask` are full [N,pool_H,pool_W,..] tensors and this launch writes
    * only the pooled window of its (even-aligned) output window: rows [oh0/2, oh0/2 + OH/2).
    * pool_H == 0: they are dense [N,OH/2,OW/2,..].                                            */
@@ -244,6 +247,45 @@ int iiseg_maxpool2_f32(const float* x, int N, int H, int W, int Cs_in, int C, fl
 int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10, const float* p11,
                             int N, int H, int W, int Cp, int C, int crop_h, int crop_w, float* out,
                             int OH, int OW, int Cs_out, void* stream);
+
+/* ---- DAE training step (train_dae.py:243-335) around the tensor-core GEMMs -------------------------
+ * iiseg_noise_pack: GaussianNoiseLayer (models/fcn_down.py:60-67) + layout change: dst = bf16 NHWC
+ *   [N,H,W,Cpad] of y + sigma*noise (y, noise NCHW fp32; noise == NULL: plain pack).
+ * iiseg_loss_grad: masked crossentropy (metrics.py:68-91, clip 1e-7, void label = C) + lmb * masked
+ *   squared_error (metrics.py:144-156) of softmax(logits) against the one-hot target (NCHW fp32,
+ *   C+1 channels).  sums (fp64[4]) = {sum mask*CE, sum mask, sum m2*mean_c (p-t)^2, sum m2}: the loss
+ *   is sums[0]/sums[1] + lmb*sums[2]/sums[3]; dlogits = bf16 NHWC16 gradient of that loss.
+ *   passes: bit 0 = accumulate sums (zeroing them first), bit 1 = write dlogits using sums[1], sums[3]
+ *   as the denominators (data-parallel ranks all-reduce `sums` between the two passes).
+ * iiseg_depool2_bwd: DePool2D backward, g_u[ph,pw] = sum over the 2x2 window of mask * g_v (g_v a
+ *   dense window [N,VH,VW,C] at full-resolution origin (v_h0,v_w0), zero outside; g_u dense
+ *   [N,UH,UW,C] at pooled origin (u_h0,u_w0); mask full [N,H/2,W/2,C/8]).
+ * iiseg_pool2_relu_bwd: Pool2DLayer(2) + rectify backward on full maps: every element that tied the
+ *   window max (Theano CPU MaxPoolGrad) gets g_pool where the pooled value is > 0; where it is 0 the
+ *   elements whose pre-rectifier value is exactly 0 (zmask, iiseg_conv_desc.pool_zmask) get g_pool / 2
+ *   (rectify = 0.5*(x+|x|)), the negative ones 0.
+ * iiseg_transpose_shift: out[(row0+c)*ldo + p] = x[n, h0+oh+dh, w0+ow+dw, c0+c] (0 outside the map),
+ *   p = (n*OH+oh)*OW+ow: the K-major operands g^T / tap-shifted x^T of the weight-gradient GEMM
+ *   dW[co][tap][ci] = sum_p g[p][co] x[p+tap][ci], which then runs on iiseg_conv2d_fwd (1x1, K = pixels).
+ * iiseg_rmsprop_pack: lasagne.updates.rmsprop (a <- rho a + (1-rho) g^2; w <- w - lr g / sqrt(a+eps))
+ *   on the fp32 master bank [Cout][taps][Cin_pad] and bias, reading g from the GEMM output [Cout][ldg]
+ *   (bias gradient in column bias_col); re-emits the bf16 forward bank wb and, if wt != NULL, the
+ *   flipped / transposed bank of the data-gradient conv wt[ci-ci0][taps-1-tap][co] ([Ci_t][taps][Co_pad]). */
+int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H,
+                     int W, int Cpad, void* stream);
+int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb,
+                    double* sums, void* dlogits, int passes, void* stream);
+int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,
+                      int VH, int VW, int v_h0, int v_w0, int UH, int UW, int u_h0, int u_w0,
+                      void* stream);
+int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const uint32_t* mask,
+                         const uint32_t* zmask, void* ga, int N, int H, int W, int C, void* stream);
+int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0,
+                          int OH, int OW, int dh, int dw, void* out, long long ldo, long long row0,
+                          void* stream);
+int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt,
+                       int Cout, int taps, int Cin_pad, int ldg, int bias_col, int ci0, int Ci_t,
+                       int Co_pad, float lr, float rho, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ def conv_out_size(H, W, R, S, pad):
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
-           out_slice=None):
+           out_slice=None, pool_zmask=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -149,6 +149,7 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       addend=addend.data_ptr() if addend is not None else None,
                       pooled=pooled.data_ptr() if pooled is not None else None,
                       pool_mask=pool_mask.data_ptr() if pool_mask is not None else None,
+                      pool_zmask=pool_zmask.data_ptr() if pool_zmask is not None else None,
                       pool_H=pool_hw[0] if pooled is not None else 0, pool_W=pool_hw[1] if pooled is not None else 0,
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
@@ -326,6 +327,79 @@ def deconv_interleave(phases, C_, crop, out):
     _lib.call('iiseg_deconv_interleave', _ptr(phases[0][0]), _ptr(phases[0][1]), _ptr(phases[1][0]), _ptr(phases[1][1]),
               N, H1 - 1, W1 - 1, Cp, C_, crop[0], crop[1], _ptr(out), out.shape[1], out.shape[2], out.shape[3], _stream())
     return out
+
+
+# ---- DAE training step kernels ------------------------------------------------------
+def noise_pack(y, noise, sigma, cpad, out=None):
+    """bf16 NHWC [N,H,W,cpad] of y + sigma*noise (NCHW fp32 inputs; noise=None: plain pack)."""
+    _chk(y, F32, 'y')
+    N, Cc, H, W = y.shape
+    if noise is not None:
+        _chk(noise, F32, 'noise')
+        assert noise.shape == y.shape
+    if out is None:
+        out = torch.empty((N, H, W, cpad), dtype=BF16, device=y.device)
+    _lib.call('iiseg_noise_pack', _ptr(y), _ptr(noise), C.c_float(sigma), _ptr(out), N, Cc, H, W, cpad, _stream())
+    return out
+
+
+def loss_grad(logits, target, n_classes, lmb, sums, dlogits=None, passes=3):
+    _chk(logits, F32, 'logits')
+    _chk(target, F32, 'target')
+    N, H, W, c16 = logits.shape
+    assert c16 == 16 and tuple(target.shape) == (N, n_classes + 1, H, W) and sums.dtype == torch.float64 and sums.numel() >= 4
+    if dlogits is None:
+        dlogits = torch.empty((N, H, W, 16), dtype=BF16, device=logits.device)
+    _lib.call('iiseg_loss_grad', _ptr(logits), _ptr(target), N, n_classes, H, W, C.c_float(lmb), _ptr(sums), _ptr(dlogits), passes,
+              _stream())
+    return dlogits
+
+
+def depool2_bwd(gv, mask, H, W, v_origin, u_origin, u_size):
+    """gv: [N,VH,VW,C] window of the unpooled-map gradient at full-resolution origin v_origin; returns the
+    pooled-map gradient over the window (u_origin, u_size)."""
+    _chk(gv, BF16, 'gv')
+    _chk(mask, torch.int32, 'mask')
+    N, VH, VW, Cc = gv.shape
+    assert tuple(mask.shape) == (N, H // 2, W // 2, Cc // 8)
+    gu = torch.empty((N, u_size[0], u_size[1], Cc), dtype=BF16, device=gv.device)
+    _lib.call('iiseg_depool2_bwd', _ptr(gv), _ptr(mask), _ptr(gu), N, H, W, Cc, VH, VW, v_origin[0], v_origin[1],
+              u_size[0], u_size[1], u_origin[0], u_origin[1], _stream())
+    return gu
+
+
+def pool2_relu_bwd(gpool, pooled, mask, H, W, zmask=None):
+    _chk(gpool, BF16, 'gpool')
+    _chk(pooled, BF16, 'pooled')
+    _chk(mask, torch.int32, 'mask')
+    N, H2, W2, Cc = pooled.shape
+    assert (H2, W2) == (H // 2, W // 2) and gpool.shape == pooled.shape and tuple(mask.shape) == (N, H2, W2, Cc // 8)
+    ga = torch.empty((N, H, W, Cc), dtype=BF16, device=gpool.device)
+    _lib.call('iiseg_pool2_relu_bwd', _ptr(gpool), _ptr(pooled), _ptr(mask), _ptr(zmask), _ptr(ga), N, H, W, Cc, _stream())
+    return ga
+
+
+def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0):
+    """out[row0 + c, p] = x[n, origin+o+shift, c0 + c] (zero outside the map), p = flat (n, oh, ow) over `size`."""
+    _chk(x, BF16, 'x')
+    _chk(out, BF16, 'out')
+    N, H, W, Cs = x.shape
+    assert out.dim() == 2 and row0 + C_ <= out.shape[0] and out.shape[1] >= N * size[0] * size[1]
+    _lib.call('iiseg_transpose_shift', _ptr(x), N, H, W, Cs, c0, C_, origin[0], origin[1], size[0], size[1], shift[0], shift[1],
+              _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), _stream())
+
+
+def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t, lr, rho, eps):
+    _chk(w, F32, 'w'); _chk(acc, F32, 'acc'); _chk(b, F32, 'b'); _chk(acc_b, F32, 'acc_b'); _chk(g, F32, 'g'); _chk(wb, BF16, 'wb')
+    Cout = w.shape[0]
+    assert w.numel() == Cout * taps * cin_pad == acc.numel() == wb.numel() and g.shape[0] == Cout
+    co_pad = 0
+    if wt is not None:
+        _chk(wt, BF16, 'wt')
+        assert wt.shape[0] == ci_t and wt.shape[1] % taps == 0
+        co_pad = wt.shape[1] // taps
+    _lib.call('iiseg_rmsprop_pack', _ptr(w), _ptr(acc), _ptr(b), _ptr(acc_b), _ptr(g), _ptr(wb), _ptr(wt), Cout, taps, cin_pad,
+              g.shape[1], bias_col, ci0, ci_t, co_pad, C.c_float(lr), C.c_float(rho), C.c_float(eps), _stream())
 
 
 # ---- metrics ------------------------------------------------------------------

@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('addend', C.c_void_p),
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int),
-        ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
+        ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_zmask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
         ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int), ('out_cs', C.c_int),
         ('upd_y', C.c_void_p), ('upd_y_bf16', C.c_void_p), ('upd_active', C.c_void_p), ('upd_norm_acc', C.c_void_p),
         ('upd_step', C.c_float), ('upd_C', C.c_int), ('upd_cpad', C.c_int),
@@ -76,6 +76,12 @@ SIGNATURES = {
     'iiseg_channel_stats': (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     'iiseg_maxpool2_f32': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     'iiseg_deconv_interleave': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    'iiseg_noise_pack': (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_loss_grad': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
+    'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _vp]),
+    'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

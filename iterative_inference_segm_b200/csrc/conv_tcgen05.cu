@@ -85,6 +85,7 @@ struct alignas(64) ConvParams {
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
   uint32_t* pool_mask;       // tie-inclusive mask nibbles [N,PH,PW,Cout/8] or NULL
+  uint32_t* pool_zmask;      // same layout: bit set iff the pre-rectifier value is exactly 0 (training: rectify'(0) = 0.5) or NULL
   int PH, PW;                // pooled tensor extent
   // fused softmax + iterative-inference update (16-channel logits conv): see iiseg_conv_desc.upd_*
   float* upd_y; __nv_bfloat16* upd_y_bf16; const int32_t* upd_active; unsigned long long* upd_norm_acc;
@@ -562,7 +563,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
           if (kSplit && p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
           hi[j] = pack_bf16x2(a, b);
           if (kSplit) lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), b - bf16_hi(hi[j]));
-          else if (p.relu) hi[j] = bf16x2_max(hi[j], 0u);
+          else if (p.relu && !(p.pooled != nullptr && p.pool_zmask != nullptr)) hi[j] = bf16x2_max(hi[j], 0u);   // (training: rectified at pool time)
         }
         if (p.out_f32) {          // fp32 rows (the hoisted term itself): 128 contiguous bytes per thread
           if (valid) {
@@ -661,8 +662,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wl_[e][0]), "=r"(wl_[e][1]), "=r"(wl_[e][2]), "=r"(wl_[e][3]) : "r"(addr2));
                   }
                 }
-                uint32_t bits = 0, outw[4], outl[kSplit ? 4 : 1] = {};
+                uint32_t bits = 0, zbits = 0, outw[4], outl[kSplit ? 4 : 1] = {};
                 if constexpr (!kSplit) {
+                  if (p.pool_zmask != nullptr) {       // training: the staged values are pre-rectifier; mark exact zeros, then rectify
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        zbits |= tie_bits(bf16x2_eq_mask(w[e][k], 0u), k, e);
+                        if (p.relu) w[e][k] = bf16x2_max(w[e][k], 0u);
+                      }
+                    }
+                  }
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     outw[k] = bf16x2_max(bf16x2_max(w[0][k], w[1][k]), bf16x2_max(w[2][k], w[3][k]));
@@ -694,6 +705,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
                 stg_v4(p.pooled + ppix * cpp + cch, make_uint4(outw[0], outw[1], outw[2], outw[3]));
                 if (kSplit) stg_v4(p.pooled + ppix * cpp + p.Cout + cch, make_uint4(outl[0], outl[1], outl[2], outl[3]));
                 if (p.pool_mask != nullptr) p.pool_mask[ppix * (p.Cout >> 3) + (cch >> 3)] = bits;
+                if (!kSplit && p.pool_zmask != nullptr) p.pool_zmask[ppix * (p.Cout >> 3) + (cch >> 3)] = zbits;
               }
             }
             epi_bar(grp);       // the staging rows are rewritten by the next channel chunk
@@ -1075,11 +1087,23 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         }
         continue;
       }
-      uint32_t hi[8];
+      uint32_t hi[8], zw[2] = {0u, 0u};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        if (p.relu) hi[j] = bf16x2_max(hi[j], 0u);      // max(x, 0) commutes with the bf16 rounding
+      for (int j = 0; j < 8; ++j) hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+      if (kPool && p.pool_zmask != nullptr) {          // training: which pre-rectifier values are exactly 0
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t part = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) part |= bf16x2_eq_mask(hi[4 * g + k], 0u) & (posbits << (4 * k));
+          part |= __shfl_xor_sync(0xffffffffu, part, 1);
+          part |= __shfl_xor_sync(0xffffffffu, part, 16);
+          zw[g] = part;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hi[j] = bf16x2_max(hi[j], 0u);      // max(x, 0) commutes with the bf16 rounding
       }
       if constexpr (!kPool) {
         if (valid) {
@@ -1112,6 +1136,8 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
           stg_v4(p.pooled + ppix * p.Cout + cbase + 8, make_uint4(mx[4], mx[5], mx[6], mx[7]));
           if (p.pool_mask != nullptr)
             *reinterpret_cast<uint2*>(p.pool_mask + ppix * (p.Cout >> 3) + (cbase >> 3)) = make_uint2(word[0], word[1]);
+          if (p.pool_zmask != nullptr)
+            *reinterpret_cast<uint2*>(p.pool_zmask + ppix * (p.Cout >> 3) + (cbase >> 3)) = make_uint2(zw[0], zw[1]);
         }
       }
     }
@@ -1441,6 +1467,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->split == 0 || (d->out_f32 == 0 && d->Cout % 64 == 0), "conv: split output needs a bf16 output with Cout %% 64 == 0");
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
+  IISEG_CHECK(d->pool_zmask == nullptr || (d->pooled != nullptr && d->split == 0), "conv: pool_zmask needs the fused pool (bf16 variant)");
   IISEG_CHECK(d->out_cs == 0 || (d->out_f32 && d->out_cs >= d->Cout && d->out_cs % 4 == 0), "conv: out_cs is for fp32 outputs (channel slice of a wider tensor)");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
   const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
@@ -1522,7 +1549,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.R = d->R; p.S = d->S;
   p.in_off_h = d->oh0 - d->pad; p.in_off_w = d->ow0 - d->pad;
   p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);
-  p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask;
+  p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask; p.pool_zmask = d->pool_zmask;
   p.upd_y = d->upd_y; p.upd_y_bf16 = reinterpret_cast<__nv_bfloat16*>(d->upd_y_bf16); p.upd_active = d->upd_active;
   p.upd_norm_acc = reinterpret_cast<unsigned long long*>(d->upd_norm_acc); p.upd_step = d->upd_step; p.upd_C = d->upd_C; p.upd_cpad = d->upd_cpad;
   p.pwin_h = d->OH / 2; p.pwin_w = d->OW / 2;

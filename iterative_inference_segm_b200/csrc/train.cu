@@ -1,0 +1,364 @@
+// Streaming kernels of the DAE training step (train_dae.py:243-335): everything between the tensor-core
+// GEMMs of the backward pass.
+//
+//   forward  : noise + pack, then the inference kernels (full maps, no iteration hoists)
+//   loss     : masked crossentropy + lmb * masked squared_error on softmax(logits) and its gradient
+//              w.r.t. the logits (metrics.py:68-91,144-156)
+//   backward : data gradients are the inference conv kernel on transposed / flipped filters (host side);
+//              DePool2D backward = masked 2x2 sum; Pool2DLayer + rectify backward = the gradient to EVERY
+//              tied maximum (Theano CPU MaxPoolGrad) where the pooled value is positive;
+//              weight gradients are plain K-major GEMMs  dW[co][tap][ci] = sum_p g[p][co] * x[p+tap][ci]
+//              on the same tensor-core kernel (a 1x1 "conv" whose channel axis is the pixel index), fed
+//              by `transpose_shift_kernel`, which writes g^T and the nine tap-shifted x^T as bf16
+//              [channels][pixels] matrices; a row of ones appended to x^T makes the bias gradient one
+//              more output column.
+//   update   : lasagne.updates.rmsprop on fp32 master weights kept in the GEMM layout, re-emitting the
+//              bf16 forward filter bank and the flipped / transposed bank of the data-gradient conv.
+#include "common.cuh"
+#include "../../include/iiseg.h"
+
+namespace iiseg {
+
+// ---- y + sigma * noise -> bf16 NHWC (GaussianNoiseLayer, models/fcn_down.py:60-67) -----------------
+__global__ void __launch_bounds__(256) noise_pack_kernel(const float* __restrict__ y, const float* __restrict__ noise, float sigma,
+                                                         uint4* __restrict__ dst, int C, int HW, int C8, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int pix = (int)(t % HW); t /= HW;
+    const int cg = (int)(t % C8);
+    const long long n = t / C8;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      v[k] = 0.f;
+      if (c < C) {
+        const long long j = (n * C + c) * HW + pix;
+        v[k] = noise != nullptr ? __fmaf_rn(sigma, noise[j], y[j]) : y[j];
+      }
+    }
+    stg_v4(dst + (n * HW + pix) * C8 + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+  }
+}
+
+// ---- loss and d loss / d logits ------------------------------------------------------------------------
+// sums[0] = sum_pix mask * CE, sums[1] = sum_pix mask, sums[2] = sum_pix m2 * mean_c (p-t)^2, sums[3] = sum_pix m2
+// (fp64 atomics; the loss is sums[0]/sums[1] + lmb*sums[2]/sums[3]).  Pass 0 accumulates the sums, pass 1 reads
+// the two denominators and writes dlogits (bf16 NHWC16):
+//   dL/dp_k = -[k == true] * mask / (p_true * N_ce)   (0 where p_true was clipped)  +  lmb * 2 (p_k - t_k) m2 / (C * N_mse)
+//   dL/dlogit_c = p_c * (dL/dp_c - sum_k dL/dp_k p_k)
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                        int C, int HW, float lmb, double* __restrict__ sums,
+                                                        __nv_bfloat16* __restrict__ dlogits, int pass) {
+  const int n = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  double ce_s = 0.0, mk_s = 0.0, se_s = 0.0, m2_s = 0.0;
+  if (pix < HW) {
+    float l[16], p[16], t[17];
+    const uint4* q = reinterpret_cast<const uint4*>(logits + ((size_t)n * HW + pix) * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 v = ldg_nc_v4(q + j);
+      l[4 * j] = __uint_as_float(v.x); l[4 * j + 1] = __uint_as_float(v.y); l[4 * j + 2] = __uint_as_float(v.z); l[4 * j + 3] = __uint_as_float(v.w);
+    }
+    float mx = l[0];
+#pragma unroll
+    for (int c = 1; c < 16; ++c) if (c < C) mx = fmaxf(mx, l[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { p[c] = c < C ? softmax_exp(l[c] - mx) : 0.f; s += p[c]; }
+    const float inv = 1.0f / s;
+    const float* tb = target + (size_t)n * (C + 1) * HW + pix;
+    int tru = 0; float tbest = tb[0];
+#pragma unroll
+    for (int c = 0; c < 17; ++c) {
+      if (c <= C) { t[c] = tb[(size_t)c * HW]; if (c > 0 && t[c] > tbest) { tbest = t[c]; tru = c; } }
+    }
+    const float mask = tru != C ? 1.f : 0.f;                  // void label = C (train_dae.py: void_labels of the iterator)
+    const int idx = tru != C ? tru : 0;
+    float m2 = 0.f, se = 0.f, ptrue = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c < C) {
+        p[c] *= inv;
+        m2 += t[c];
+        const float d = p[c] - t[c];
+        se += d * d;
+        if (c == idx) ptrue = p[c];
+      }
+    }
+    const bool clipped = ptrue < 1e-7f || ptrue > 1.0f - 1e-7f;
+    const float pc = fminf(fmaxf(ptrue, 1e-7f), 1.0f - 1e-7f);
+    if (pass == 0) {
+      ce_s = (double)(-logf(pc) * mask); mk_s = (double)mask; se_s = (double)(se / (float)C * m2); m2_s = (double)m2;
+    } else {
+      const float n_ce = (float)sums[1], n_mse = (float)sums[3];
+      float dp[16], dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        dp[c] = 0.f;
+        if (c < C) {
+          dp[c] = lmb * 2.f * (p[c] - t[c]) * m2 / ((float)C * n_mse);
+          if (c == idx && !clipped) dp[c] -= mask / (pc * n_ce);
+          dot += dp[c] * p[c];
+        }
+      }
+      float g[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) g[c] = c < C ? p[c] * (dp[c] - dot) : 0.f;
+      uint4* o = reinterpret_cast<uint4*>(dlogits + ((size_t)n * HW + pix) * 16);
+      stg_v4(o, make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7])));
+      stg_v4(o + 1, make_uint4(pack_bf16x2(g[8], g[9]), pack_bf16x2(g[10], g[11]), pack_bf16x2(g[12], g[13]), pack_bf16x2(g[14], g[15])));
+    }
+  }
+  if (pass == 0) {
+    __shared__ double red[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ce_s += __shfl_xor_sync(0xffffffffu, ce_s, o); mk_s += __shfl_xor_sync(0xffffffffu, mk_s, o);
+      se_s += __shfl_xor_sync(0xffffffffu, se_s, o); m2_s += __shfl_xor_sync(0xffffffffu, m2_s, o);
+    }
+    if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; red[0][w] = ce_s; red[1][w] = mk_s; red[2][w] = se_s; red[3][w] = m2_s; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      double a = 0.0;
+      for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+      atomicAdd(sums + threadIdx.x, a);
+    }
+  }
+}
+
+// ---- DePool2D backward: g_u[ph,pw,c] = sum over the 2x2 window of mask * g_v ----------------------------
+// g_v: dense window tensor [N,VH,VW,C] whose (0,0) is full-resolution pixel (v_h0,v_w0) (zero outside);
+// g_u: dense [N,UH,UW,C] whose (0,0) is pooled position (u_h0,u_w0); mask: full [N,H2,W2,C/8].
+struct DepoolBwdParams { const uint4* gv; const uint32_t* mask; uint4* gu; int C8, H2, W2, VH, VW, v_h0, v_w0, UH, UW, u_h0, u_w0; };
+
+__global__ void __launch_bounds__(256) depool_bwd_kernel(const DepoolBwdParams p) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= p.UW * p.C8) return;
+  const int uw = idx / p.C8, cg = idx - uw * p.C8;
+  const int uh = blockIdx.y;
+  const size_t n = blockIdx.z;
+  const int ph = p.u_h0 + uh, pw = p.u_w0 + uw;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ph < p.H2 && pw < p.W2) {
+    const uint32_t bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.C8 + cg);
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+      const int vh = 2 * ph + (pos >> 1) - p.v_h0, vw = 2 * pw + (pos & 1) - p.v_w0;
+      if (vh < 0 || vh >= p.VH || vw < 0 || vw >= p.VW) continue;
+      const uint4 v = ldg_nc_v4(p.gv + ((n * p.VH + vh) * p.VW + vw) * p.C8 + cg);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t m = w[k] & tie_select(bits, k, pos);
+        acc[2 * k] += bf16_lo(m); acc[2 * k + 1] += bf16_hi(m);
+      }
+    }
+  }
+  stg_v4(p.gu + ((n * p.UH + uh) * p.UW + uw) * p.C8 + cg, make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                      pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7])));
+}
+
+// ---- Pool2DLayer(2) + rectify backward -------------------------------------------------------------------
+// g_a[2ph+dy, 2pw+dx, c] = g_pool[ph,pw,c] if that element tied the window max (mask bit) and the max is > 0.
+// rectify = 0.5*(x+|x|) has gradient 0.5 at exactly 0: in a window whose max is 0 (every element ties) the elements
+// whose pre-rectifier value is exactly 0 (zmask bit) get g_pool/2, the negative ones 0 -- this is not a corner case:
+// with zero-initialised biases the whole zero-padded border of every level is exactly 0.  Trailing odd row / column: 0.
+__global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const uint4* __restrict__ gpool, const uint4* __restrict__ pooled,
+                                                            const uint32_t* __restrict__ mask, const uint32_t* __restrict__ zmask,
+                                                            uint4* __restrict__ ga, int H, int W, int C8, int PW2) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= PW2 * C8) return;
+  const int pw = idx / C8, cg = idx - pw * C8;            // pw in [0, ceil(W/2))
+  const int ph = blockIdx.y;                              // in [0, ceil(H/2))
+  const size_t n = blockIdx.z;
+  const int H2 = H / 2, W2 = W / 2;
+  uint32_t g[4] = {0, 0, 0, 0}, gh[4] = {0, 0, 0, 0}, bits = 0, zb = 0;
+  if (ph < H2 && pw < W2) {
+    const size_t pi = ((n * H2 + ph) * W2 + pw) * C8 + cg;
+    const uint4 gv = ldg_nc_v4(gpool + pi), pv = ldg_nc_v4(pooled + pi);
+    bits = __ldg(mask + pi);
+    if (zmask != nullptr) zb = __ldg(zmask + pi);
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, pwv[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = bf16_lo(pwv[k]) > 0.f ? 0x0000FFFFu : 0u, hi = bf16_hi(pwv[k]) > 0.f ? 0xFFFF0000u : 0u;
+      g[k] = gw[k] & (lo | hi);                                                        // windows with a positive max
+      gh[k] = pack_bf16x2(0.5f * bf16_lo(gw[k]), 0.5f * bf16_hi(gw[k])) & ~(lo | hi);  // windows whose max is 0: g/2 for exact zeros
+    }
+  }
+#pragma unroll
+  for (int pos = 0; pos < 4; ++pos) {
+    const int oh = 2 * ph + (pos >> 1), ow = 2 * pw + (pos & 1);
+    if (oh >= H || ow >= W) continue;
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = (g[k] & tie_select(bits, k, pos)) | (gh[k] & tie_select(zb, k, pos));
+    stg_v4(ga + ((n * H + oh) * W + ow) * C8 + cg, make_uint4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// ---- [pixels][channels] -> [channels][pixels] with a spatial shift (operands of the weight-gradient GEMM) ----
+// out[(row0 + c) * ldo + p] = x[n, h0 + oh + dh, w0 + ow + dw, c0 + c]  (0 outside the HxW map), p = (n*OH + oh)*OW + ow,
+// for c < C; columns p in [P, ldo) are written as zeros by the caller's memset.  64 pixels x 64 channels per block
+// through shared memory so that both sides move 128-byte rows.
+struct TransposeParams { const __nv_bfloat16* x; __nv_bfloat16* out; int N, H, W, Cs, c0, C, h0, w0, OH, OW, dh, dw; long long ldo, row0, P; };
+
+__global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposeParams p) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const long long p_base = (long long)blockIdx.x * 64;
+  const int c_base = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // 64 x 4
+  for (int i = ty; i < 64; i += 4) {                              // row i = pixel, tx = channel
+    const long long pp = p_base + i;
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (pp < p.P && c_base + tx < p.C) {
+      long long t = pp;
+      const int ow = (int)(t % p.OW); t /= p.OW;
+      const int oh = (int)(t % p.OH);
+      const long long n = t / p.OH;
+      const int ih = p.h0 + oh + p.dh, iw = p.w0 + ow + p.dw;
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[((n * p.H + ih) * p.W + iw) * p.Cs + p.c0 + c_base + tx];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {                              // row i = channel, tx = pixel
+    const long long pp = p_base + tx;
+    if (c_base + i < p.C && pp < p.ldo) p.out[(p.row0 + c_base + i) * p.ldo + pp] = pp < p.P ? tile[tx][i] : __float2bfloat16(0.f);
+  }
+}
+
+// ---- rmsprop + filter re-packing ---------------------------------------------------------------------------
+// lasagne.updates.rmsprop (rho, eps): a <- rho*a + (1-rho)*g^2 ; w <- w - lr * g / sqrt(a + eps), on the fp32 master
+// filter bank kept in the GEMM layout [Cout][taps][Cin_pad]; g is read from the weight-gradient GEMM output
+// [Cout][ldg] (taps*Cin_pad filter columns, then the bias column at `bias_col`).  Emits the bf16 forward bank
+// and, if wt != NULL, the bank of the data-gradient conv: wt[ci][R*S-1-tap][co] (flipped taps, transposed channels),
+// for the ci range [ci0, ci0 + Ci_t) only (the concat conv propagates to its own half), padded to Co_pad columns.
+struct RmspropParams {
+  float* w; float* acc; float* b; float* acc_b; const float* g; __nv_bfloat16* wb; __nv_bfloat16* wt;
+  int Cout, taps, Cin_pad, ldg, bias_col, ci0, Ci_t, Co_pad; float lr, rho, eps; long long total;
+};
+
+__global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.total; i += (long long)gridDim.x * blockDim.x) {
+    const int per = p.taps * p.Cin_pad;
+    const int co = (int)(i / per), rem = (int)(i - (long long)co * per);
+    const int tap = rem / p.Cin_pad, ci = rem - tap * p.Cin_pad;
+    const float g = p.g[(size_t)co * p.ldg + rem];
+    const float a = p.rho * p.acc[i] + (1.f - p.rho) * g * g;
+    p.acc[i] = a;
+    const float w = p.w[i] - p.lr * g / sqrtf(a + p.eps);
+    p.w[i] = w;
+    const __nv_bfloat16 wb = __float2bfloat16(w);
+    p.wb[i] = wb;
+    if (p.wt != nullptr && ci >= p.ci0 && ci < p.ci0 + p.Ci_t)
+      p.wt[((size_t)(ci - p.ci0) * p.taps + (p.taps - 1 - tap)) * p.Co_pad + co] = wb;
+    if (rem == 0) {       // one thread per output channel also updates the bias
+      const float gb = p.g[(size_t)co * p.ldg + p.bias_col];
+      const float ab = p.rho * p.acc_b[co] + (1.f - p.rho) * gb * gb;
+      p.acc_b[co] = ab;
+      p.b[co] -= p.lr * gb / sqrtf(ab + p.eps);
+    }
+  }
+}
+
+static int tgrid(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace iiseg
+
+extern "C" int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H, int W,
+                                int Cpad, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(y && dst, "noise_pack: null tensor");
+  IISEG_CHECK(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && Cpad % 8 == 0, "noise_pack: bad shape");
+  const long long total = (long long)N * (Cpad / 8) * H * W;
+  noise_pack_kernel<<<tgrid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, noise, sigma, reinterpret_cast<uint4*>(dst), C,
+                                                                                      H * W, Cpad / 8, total);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb, double* sums,
+                               void* dlogits, int passes, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(logits && target && sums && dlogits, "loss_grad: null tensor");
+  IISEG_CHECK(N > 0 && C >= 1 && C <= 16 && H > 0 && W > 0, "loss_grad: bad shape");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (passes & 1) IISEG_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), s));
+  dim3 grid((H * W + 255) / 256, N);
+  for (int pass = 0; pass < 2; ++pass) {
+    if (!(passes & (1 << pass))) continue;
+    loss_grad_kernel<<<grid, 256, 0, s>>>(logits, target, C, H * W, lmb, sums, reinterpret_cast<__nv_bfloat16*>(dlogits), pass);
+    IISEG_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C, int VH, int VW,
+                                 int v_h0, int v_w0, int UH, int UW, int u_h0, int u_w0, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(gv && mask && gu, "depool2_bwd: null tensor");
+  IISEG_CHECK(N > 0 && C > 0 && C % 8 == 0 && UH >= 1 && UW >= 1 && UH <= 65535 && N <= 65535, "depool2_bwd: bad shape");
+  DepoolBwdParams p;
+  p.gv = reinterpret_cast<const uint4*>(gv); p.mask = mask; p.gu = reinterpret_cast<uint4*>(gu);
+  p.C8 = C / 8; p.H2 = H / 2; p.W2 = W / 2; p.VH = VH; p.VW = VW; p.v_h0 = v_h0; p.v_w0 = v_w0;
+  p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
+  dim3 grid(ceil_div(UW * p.C8, 256), UH, N);
+  depool_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const uint32_t* mask, const uint32_t* zmask, void* ga,
+                                    int N, int H, int W, int C, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(gpool && pooled && mask && ga, "pool2_relu_bwd: null tensor");
+  IISEG_CHECK(N > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0 && (H + 1) / 2 <= 65535 && N <= 65535, "pool2_relu_bwd: bad shape");
+  const int PW2 = (W + 1) / 2;
+  dim3 grid(ceil_div(PW2 * (C / 8), 256), (H + 1) / 2, N);
+  pool_relu_bwd_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(gpool), reinterpret_cast<const uint4*>(pooled), mask, zmask, reinterpret_cast<uint4*>(ga), H, W, C / 8,
+      PW2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0, int OH, int OW,
+                                     int dh, int dw, void* out, long long ldo, long long row0, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(x && out, "transpose_shift: null tensor");
+  IISEG_CHECK(N > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && OH > 0 && OW > 0 && ldo >= (long long)N * OH * OW, "transpose_shift: bad shape");
+  TransposeParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.N = N; p.H = H; p.W = W; p.Cs = Cs; p.c0 = c0; p.C = C; p.h0 = h0; p.w0 = w0; p.OH = OH; p.OW = OW; p.dh = dh; p.dw = dw;
+  p.ldo = ldo; p.row0 = row0; p.P = (long long)N * OH * OW;
+  const long long pblocks = (ldo + 63) / 64;
+  IISEG_CHECK(pblocks < (1LL << 31) && (C + 63) / 64 <= 65535, "transpose_shift: too large");
+  dim3 grid((unsigned)pblocks, (C + 63) / 64);
+  transpose_shift_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt, int Cout,
+                                  int taps, int Cin_pad, int ldg, int bias_col, int ci0, int Ci_t, int Co_pad, float lr, float rho,
+                                  float eps, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(w && acc && b && acc_b && g && wb, "rmsprop_pack: null tensor");
+  IISEG_CHECK(Cout > 0 && taps > 0 && Cin_pad > 0 && ldg >= taps * Cin_pad && bias_col < ldg, "rmsprop_pack: bad shape");
+  IISEG_CHECK(wt == nullptr || (ci0 >= 0 && ci0 + Ci_t <= Cin_pad && Co_pad >= Cout), "rmsprop_pack: bad transposed-bank range");
+  RmspropParams p;
+  p.w = w; p.acc = acc; p.b = b; p.acc_b = acc_b; p.g = g; p.wb = reinterpret_cast<__nv_bfloat16*>(wb); p.wt = reinterpret_cast<__nv_bfloat16*>(wt);
+  p.Cout = Cout; p.taps = taps; p.Cin_pad = Cin_pad; p.ldg = ldg; p.bias_col = bias_col; p.ci0 = ci0; p.Ci_t = Ci_t; p.Co_pad = Co_pad;
+  p.lr = lr; p.rho = rho; p.eps = eps; p.total = (long long)Cout * taps * Cin_pad;
+  rmsprop_pack_kernel<<<tgrid(p.total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}

@@ -27,3 +27,17 @@ def allreduce_metrics(cm, counts, sqerr=None):
     if sqerr is not None:
         dist.all_reduce(sqerr, op=dist.ReduceOp.SUM)
     return cm, counts, sqerr
+
+
+class World(object):
+    """The collectives of the data-parallel DAE training step (train_dae.py step, config 4): SUM all-reduce of the
+    loss denominators and of the per-layer weight-gradient matrices.  NCCL for CUDA tensors, gloo for CPU."""
+
+    def __init__(self):
+        self.size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.size > 1 else 0
+
+    def allreduce_sum(self, t):
+        if self.size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t

@@ -1,0 +1,291 @@
+"""The DAE training step of train_dae.py on the sm_100a kernels.
+
+`DAETrainer.step(h, y, target, noise_main, noise_mask)` is one `train_fn(*H_pred, Y_pred, L)` call
+(train_dae.py:334-335, 378): GaussianNoiseLayer -> DAE forward (no `deterministic`) -> masked
+crossentropy + lmb * masked squared_error (train_dae.py:279-293, metrics.py:68-91,144-156) ->
+gradients of all 24 parameter arrays -> lasagne.updates.rmsprop (train_dae.py:326-327).  Benchmark
+configuration: kind='standard', unpool_type='trackind', skip=True, conv_before_pool=1, bn=0, dropout=0.
+
+Where the arithmetic runs:
+  * forward: the inference kernels on full maps (weights change every step, so none of the
+    iteration hoists of the inference loop apply); with noise > 0 the DePool2D masks come from a
+    SECOND stochastically noised pass of the contracting path, as in the reference
+    (layers/mylayers.py:91-93 calls get_output without `deterministic`);
+  * data gradients: the same tcgen05 conv kernel on the flipped / transposed filter bank;
+  * weight (+ bias) gradients: one K-major GEMM per layer on the same kernel (a 1x1 conv whose
+    channel axis is the pixel index): dW[co][tap][ci] = sum_p g[p][co] x[p + tap][ci], operands
+    written by `iiseg_transpose_shift`, a row of ones giving the bias gradient as one more column;
+  * pool / unpool / rectify / loss / rmsprop: streaming kernels of csrc/train.cu.
+Gradients travel as bf16 NHWC tensors (fp32 accumulation everywhere), master weights and rmsprop
+state are fp32 in the GEMM layout.  Data parallelism (`world` = sharding.World): the loss is a masked mean
+over the GLOBAL batch, so ranks all-reduce the two loss denominators between the loss pass and the
+gradient pass, then sum their weight-gradient matrices (NCCL) before the update: the step equals the
+single-device step on the concatenated batch up to fp32 summation order.
+"""
+import torch
+
+from . import _kernels as K
+from ._packing import _as_f32
+from .models.DAE_h import DAENet
+
+
+def _r64(c):
+    return (c + 63) // 64 * 64
+
+
+class _Layer(object):
+    """One conv of the DAE: fp32 master bank [Cout_pad][9][Cin_pad] + rmsprop state + bf16 banks."""
+
+    def __init__(self, W, b, splits, cout_pad, dev, dgrad_range):
+        W, b = _as_f32(W, dev), _as_f32(b, dev)
+        Cout, Cin = W.shape[0], W.shape[1]
+        assert Cin == sum(r for r, _ in splits)
+        parts, c0 = [], 0
+        for real, padded in splits:
+            blk = torch.zeros((cout_pad, 3, 3, padded), dtype=torch.float32, device=dev)
+            blk[:Cout, :, :, :real] = W[:, c0:c0 + real].permute(0, 2, 3, 1)
+            parts.append(blk)
+            c0 += real
+        self.cout, self.cout_pad = Cout, cout_pad
+        self.cin_pad = sum(pd for _, pd in splits)
+        self.w = torch.cat(parts, dim=3).reshape(cout_pad, 9, self.cin_pad).contiguous()
+        self.b = torch.zeros((cout_pad,), dtype=torch.float32, device=dev)
+        self.b[:Cout] = b
+        self.acc, self.acc_b = torch.zeros_like(self.w), torch.zeros_like(self.b)
+        self.wb = self.w.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()                 # forward bank
+        self.nb = _r64(9 * self.cin_pad + 1)                                                      # GEMM columns: filter + bias + pad
+        self.bias_col = 9 * self.cin_pad
+        # data-gradient bank over the input channels [ci0, ci0 + ci_t): wt[ci][8 - tap][co]
+        self.ci0, self.ci_t = dgrad_range if dgrad_range is not None else (0, 0)
+        self.wt = None
+        if dgrad_range is not None:
+            self.co_pad_t = cout_pad if cout_pad == 16 else _r64(cout_pad)
+            sub = self.w[:, :, self.ci0:self.ci0 + self.ci_t]                                   # [co, tap, ci]
+            wt = torch.zeros((self.ci_t, 9, self.co_pad_t), dtype=torch.float32, device=dev)
+            wt[:, :, :cout_pad] = sub.flip(1).permute(2, 1, 0)
+            self.wt = wt.reshape(self.ci_t, -1).to(torch.bfloat16).contiguous()
+        self.zero_bias_t = torch.zeros((max(self.ci_t, 16),), dtype=torch.float32, device=dev)
+        self.grad = None            # fp32 [Cout_pad][nb], the weight-gradient GEMM output of the last step
+
+    def lasagne_arrays(self, splits_real):
+        """(W (Cout, Cin, 3, 3), b (Cout,)) in the reference's checkpoint layout."""
+        w = self.w.reshape(self.cout_pad, 3, 3, self.cin_pad)
+        parts, c0 = [], 0
+        for real, padded in splits_real:
+            parts.append(w[:self.cout, :, :, c0:c0 + real])
+            c0 += padded
+        return torch.cat(parts, dim=3).permute(0, 3, 1, 2).contiguous(), self.b[:self.cout].clone()
+
+
+class DAETrainer(object):
+    def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
+                 additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda'):
+        K.require_device()
+        self.dev = dev = torch.device(device)
+        self.C, self.lr, self.sigma, self.lmb, self.rho, self.eps = n_classes, learning_rate, noise, lmb, rho, epsilon
+        geo = self.geo = DAENet.__new__(DAENet)          # geometry helpers only (level sizes, crop cone)
+        geo.n_classes, geo.nb_h, geo.h_pad, geo.padding = n_classes, nb_features_to_concat, _r64(nb_features_to_concat), padding
+        last = concat_h[-1]
+        geo.n_pool = int(last[-1])
+        geo.total = geo.n_pool + additional_pool
+        geo.filters = [n_filters * 2 ** min(p, 5) for p in range(geo.total)]
+        geo.split, geo.cm, geo.y_cpad = False, 1, 16
+        P, f = geo.total, geo.filters
+        assert len(params) == 4 * P
+        self.down, self.up, self._splits = [], [], []
+        cin = n_classes
+        for p in range(P):
+            if p == geo.n_pool:
+                splits = [(geo.nb_h, geo.h_pad), (cin, cin)]
+                rng = (geo.h_pad, cin)                     # the conv propagates to its own pool half only
+            else:
+                splits = [(cin, 16 if p == 0 else cin)]
+                rng = (0, cin) if p > 0 else None          # no gradient w.r.t. the network input
+            self.down.append(_Layer(params[2 * p], params[2 * p + 1], splits, f[p], dev, rng))
+            self._splits.append(splits)
+            cin = f[p]
+        up_in = f[-1]
+        for i, p in enumerate(range(P, 0, -1)):
+            n_cl = n_classes if p == 1 else f[p - 2]
+            self.up.append(_Layer(params[2 * (P + i)], params[2 * (P + i) + 1], [(up_in, up_in)], 16 if p == 1 else n_cl, dev,
+                                  (0, up_in)))
+            self._splits.append([(up_in, up_in)])
+            up_in = n_cl
+        self.sums = torch.zeros((4,), dtype=torch.float64, device=dev)
+        self.last_loss = None
+
+    def layers(self):
+        return self.down + self.up
+
+    def params(self):
+        """The 24 arrays in the reference's checkpoint order (np.savez(*get_all_param_values), train_dae.py:436-445)."""
+        out = []
+        for lay, splits in zip(self.layers(), self._splits):
+            out += list(lay.lasagne_arrays(splits))
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def _down(self, x0, h):
+        geo, sizes = self.geo, self._sizes
+        pools, masks, zmasks = [], [], []
+        x = x0
+        B = x0.shape[0]
+        for p, lay in enumerate(self.down):
+            hh, ww = sizes[p]
+            pooled = torch.empty((B, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
+            mask = torch.empty((B, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
+            zmask = torch.empty_like(mask)        # exact zeros before the rectifier (gradient 0.5 there)
+            pad = geo.padding if (p == 0 and geo.padding > 0) else 1
+            if p == geo.n_pool:
+                K.conv2d(h, lay.wb, lay.b, 3, 3, pad, relu=True, src1=x, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            else:
+                K.conv2d(x, lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            pools.append(pooled); masks.append(mask); zmasks.append(zmask)
+            x = pooled
+        return pools, masks, zmasks
+
+    def forward(self, h_bf16, y, noise_main=None, noise_mask=None):
+        """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits."""
+        geo = self.geo
+        B, _, H, W = y.shape
+        self._sizes = sizes = geo.level_sizes(H, W)
+        self.Wc, self.Wu = geo.cone_windows(H, W)
+        st = self.st = {'B': B, 'H': H, 'W': W, 'h': h_bf16}
+        st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
+        st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
+        if noise_mask is not None:     # the DePool2D mask sub-graph: a separately noised contracting path
+            _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
+        else:
+            st['masksB'] = st['masksA']
+        P = geo.total
+        st['v'] = {}
+        u, u_origin = st['pools'][-1], (0, 0)
+        for i, p in enumerate(range(P, 0, -1)):
+            hh, ww = sizes[p - 1]
+            ul, uh, vl, vh = self.Wu[p]
+            hl, hh2, wl, wh = self.Wc[p]
+            v = K.unpool2(u, st['masksB'][p - 1], hh, ww, u_origin=u_origin, window=(ul, vl, uh - ul, vh - vl))
+            st['v'][p] = v
+            lay = self.up[i]
+            win = (hl - ul, wl - vl, hh2 - hl, wh - wl)
+            if p > 1:
+                u = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win, addend=st['pools'][p - 2], addend_off=(hl, wl))
+                u_origin = (hl, wl)
+            else:
+                st['logits'] = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win, out_f32=True)
+        return st['logits']
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad(self, lay, g, x_srcs, g_origin_in_x, pad):
+        """dW (+ db) of `lay` = one GEMM.  g: [B,GH,GW,Cg] gradient w.r.t. the conv output over a window whose origin
+        sits at `g_origin_in_x` in the coordinates of the input tensors; x_srcs: [(tensor, real_channels_padded)]."""
+        B, GH, GW, Cg = g.shape
+        Pn = B * GH * GW
+        ldo = _r64(Pn)
+        A = torch.zeros((Cg, ldo), dtype=torch.bfloat16, device=self.dev)
+        K.transpose_shift(g, Cg, (0, 0), (GH, GW), (0, 0), A, 0)
+        Bm = torch.zeros((lay.nb, ldo), dtype=torch.bfloat16, device=self.dev)
+        for tap in range(9):
+            r, s = tap // 3, tap % 3
+            row = tap * lay.cin_pad
+            for x, c in x_srcs:
+                K.transpose_shift(x, c, g_origin_in_x, (GH, GW), (r - pad, s - pad), Bm, row)
+                row += c
+        Bm[lay.bias_col, :Pn] = 1.0                                    # the bias gradient is the column against ones
+        zero = torch.zeros((lay.nb,), dtype=torch.float32, device=self.dev)
+        G = K.conv2d(A.view(1, 1, Cg, ldo), Bm, zero, 1, 1, 0, relu=False, out_f32=True)
+        lay.grad = G.view(Cg, lay.nb)
+        return lay.grad
+
+    def _dgrad(self, lay, g, window, addend=None):
+        """Gradient w.r.t. the conv input over `window` = (j0h, j0w, OH, OW) of the pad-2 correlation of g with the
+        flipped / transposed bank (position q relative to g's origin is output index q + 1)."""
+        return K.conv2d(g, lay.wt, lay.zero_bias_t[:lay.ci_t].contiguous(), 3, 3, 2, relu=False, window=window, addend=addend)
+
+    def backward(self, target, world=None):
+        st, geo = self.st, self.geo
+        B, H, W = st['B'], st['H'], st['W']
+        sizes, Wc, Wu, P = self._sizes, self.Wc, self.Wu, geo.total
+        if world is None:
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums)      # dL/dlogits over Wc[1]
+        else:       # the loss is a masked mean over the GLOBAL batch (metrics.py:88-89,153-154): global denominators
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, passes=1)
+            world.allreduce_sum(self.sums)
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, dlogits=g_c, passes=2)
+        skip = {}                                                                      # level p -> (grad of pool_p from the skip-sum, its window)
+        g_u = None
+        for i, p in enumerate(range(1, P + 1)):          # expanding path, output towards the bottleneck
+            lay = self.up[P - p]
+            hl, hh, wl, wh = Wc[p]
+            ul, uh, vl, vh = Wu[p]
+            v = st['v'][p]
+            self._wgrad(lay, g_c, [(v, lay.cin_pad)], (hl - ul, wl - vl), 1)
+            g_v = self._dgrad(lay, g_c, (ul - hl + 1, vl - wl + 1, uh - ul, vh - vl))
+            # pooled positions under the unpooled window
+            S2h, S2w = sizes[p - 1][0] // 2, sizes[p - 1][1] // 2
+            pu = (ul // 2, min((uh - 1) // 2 + 1, S2h), vl // 2, min((vh - 1) // 2 + 1, S2w))
+            if p < P:
+                assert pu == tuple(Wc[p + 1]), (pu, Wc[p + 1])
+            g_u = K.depool2_bwd(g_v, st['masksB'][p - 1], sizes[p - 1][0], sizes[p - 1][1], (ul, vl), (pu[0], pu[2]),
+                                (pu[1] - pu[0], pu[3] - pu[2]))
+            skip[p] = (g_u, pu)          # u_p = c_{p+1} + pool_p (p < P) or pool_P itself: gradient of pool_p over window pu
+            g_c = g_u                    # ... and of c_{p+1}
+        # contracting path, bottleneck towards the input
+        g_in = None
+        for p in range(P, 0, -1):
+            lay = self.down[p - 1]
+            hp, wp = sizes[p - 1]
+            pooled = st['pools'][p - 1]
+            gs, pu = skip[p]
+            if g_in is None:             # level P: only the up path reaches pool_P
+                g_pool = torch.zeros_like(pooled)
+                g_pool[:, pu[0]:pu[1], pu[2]:pu[3]].copy_(gs)
+            else:
+                g_pool = g_in            # dgrad of conv_{p+1} already carries the skip part (epilogue addend)
+            g_a = K.pool2_relu_bwd(g_pool, pooled, st['masksA'][p - 1], hp, wp, zmask=st['zmasks'][p - 1])
+            pad = geo.padding if (p == 1 and geo.padding > 0) else 1
+            if p - 1 == geo.n_pool:
+                xs = [(st['h'], geo.h_pad), (st['pools'][p - 2], st['pools'][p - 2].shape[3])]
+            elif p == 1:
+                xs = [(st['x0'], 16)]
+            else:
+                xs = [(st['pools'][p - 2], st['pools'][p - 2].shape[3])]
+            self._wgrad(lay, g_a, xs, (0, 0), pad)
+            if p > 1:
+                gs_prev, pw = skip[p - 1]
+                buf = torch.zeros_like(st['pools'][p - 2])
+                buf[:, pw[0]:pw[1], pw[2]:pw[3]].copy_(gs_prev)       # data movement only: the skip gradient in place
+                g_in = self._dgrad(lay, g_a, (1, 1, hp, wp), addend=buf)
+        s = self.sums
+        self.last_loss = s     # device tensor; loss = s0/s1 + lmb*s2/s3
+        return [lay.grad for lay in self.layers()]
+
+    def loss_value(self):
+        s = self.sums.cpu()
+        return float(s[0] / s[1] + self.lmb * s[2] / s[3])
+
+    def update(self):
+        for lay in self.layers():
+            K.rmsprop_pack(lay.w, lay.acc, lay.b, lay.acc_b, lay.grad, lay.wb, lay.wt, 9, lay.cin_pad, lay.bias_col,
+                           lay.ci0, lay.ci_t, self.lr, self.rho, self.eps)
+
+    def step(self, h_bf16, y, target, noise_main=None, noise_mask=None, world=None):
+        self.forward(h_bf16, y, noise_main, noise_mask)
+        self.backward(target, world)
+        if world is not None:           # per-rank gradients already carry the global denominators: plain sum
+            for lay in self.layers():
+                world.allreduce_sum(lay.grad)
+        self.update()
+        return self.last_loss
+
+    def grads_lasagne(self):
+        """Gradients in the reference's parameter layout (for tests): [(dW (Cout,Cin,3,3), db (Cout,)), ...]."""
+        out = []
+        for lay, splits in zip(self.layers(), self._splits):
+            g = lay.grad[:, :9 * lay.cin_pad].reshape(lay.cout_pad, 3, 3, lay.cin_pad)
+            parts, c0 = [], 0
+            for real, padded in splits:
+                parts.append(g[:lay.cout, :, :, c0:c0 + real])
+                c0 += padded
+            out += [torch.cat(parts, dim=3).permute(0, 3, 1, 2).contiguous(), lay.grad[:lay.cout, lay.bias_col].clone()]
+        return out

@@ -1,0 +1,149 @@
+"""The DAE training step of train_dae.py restated on torch CPU with autograd (test oracle).
+
+Follows train_dae.py:243-335 (noise -> DAE forward without `deterministic`, masked crossentropy +
+lmb * masked squared_error, lasagne.updates.rmsprop) and metrics.py:68-91,144-156, for the benchmark
+configuration (kind='standard', unpool_type='trackind', skip=True, bn=0, dropout=0).  The parts of
+Theano/Lasagne semantics that autograd's defaults would get wrong are custom functions:
+
+  * Pool2DLayer backward = Theano CPU MaxPoolGrad: EVERY element equal to the window max receives
+    the upstream gradient (torch routes it to one element);
+  * DePool2D (layers/mylayers.py:88-115): out = repeat2(u) * mask, the mask being constant w.r.t.
+    the parameters (T.grad of the pool w.r.t. its input, all-ones upstream); with noise > 0 the mask
+    sub-graph is a SEPARATE stochastic forward of the contracting path (lasagne.layers.get_output is
+    called without `deterministic`, layers/mylayers.py:91-93), so masks come from a second noise draw;
+  * rectify = T.nnet.relu = 0.5 * (x + |x|): its gradient at exactly 0 is 0.5.
+
+Noise tensors are explicit inputs (Theano's MRG31k3p stream cannot be reproduced): `noise_main`
+for the path that produces values, `noise_mask` for the DePool2D mask sub-graph.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import lasagne_semantics as L
+from .nets import dae_levels
+
+EPS_CE = 1e-7          # metrics.py:8 _EPSILON
+
+
+class _Relu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.relu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * (0.5 * (1.0 + torch.sign(x)))       # d/dx 0.5*(x+|x|): 1, 0.5 at 0, 0
+
+
+class _MaxPool2TieAll(torch.autograd.Function):
+    """Pool2DLayer(2), ignore_border=True; backward to every tied maximum (Theano CPU MaxPoolGrad)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return F.max_pool2d(x, 2, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        mask = L.tie_mask(x)
+        up = torch.zeros_like(x)
+        r = g.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        up[:, :, :r.shape[2], :r.shape[3]] = r
+        return up * mask
+
+
+def _q_bf16(x):
+    """Round to bf16 with a straight-through gradient: emulates the storage format of the B200 path
+    (weights, activations) so that pool ties -- a discontinuous function of the values -- fall the same way."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
+def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=('pool4',), additional_pool=2,
+                      emulate_bf16=False):
+    """Differentiable DAE forward -> logits (before the softmax), cropped to the input size.
+    `mask_source_y`: input of the separate contracting-path forward the DePool2D masks are taken from
+    (None: the same forward).  Masks are constants (detached).  `emulate_bf16`: weights, inputs and every
+    stored activation are rounded to bf16 (straight-through), as on the B200 path; the arithmetic stays fp32."""
+    n_pool, total = dae_levels(concat_h, additional_pool)
+    q = _q_bf16 if emulate_bf16 else (lambda t: t)
+    Wd = [(q(params[2 * i]), params[2 * i + 1]) for i in range(total)]
+    Wu = [(q(params[2 * (total + i)]), params[2 * (total + i) + 1]) for i in range(total)]
+    y_noisy, h = q(y_noisy), q(h)
+    if mask_source_y is not None:
+        mask_source_y = q(mask_source_y)
+
+    def down(x, differentiable):
+        pre, pools = [], []
+        for p in range(total):
+            pad = padding if (p == 0 and padding > 0) else 1
+            a = q(F.conv2d(x, Wd[p][0], Wd[p][1], padding=pad))
+            r = _Relu.apply(a) if differentiable else torch.relu(a)
+            pre.append(r)
+            x = _MaxPool2TieAll.apply(r) if differentiable else F.max_pool2d(r, 2, 2)
+            pools.append(x)
+            if p + 1 == n_pool:
+                x = torch.cat([h, x], dim=1)
+        return pre, pools
+
+    pre, pools = down(y_noisy, True)
+    if mask_source_y is None:
+        masks = [L.tie_mask(r.detach()) for r in pre]
+    else:
+        with torch.no_grad():
+            pre_m, _ = down(mask_source_y, False)
+        masks = [L.tie_mask(r) for r in pre_m]
+    u = pools[-1]
+    for i, p in enumerate(range(total, 0, -1)):
+        m = masks[p - 1]
+        up = torch.zeros_like(m)
+        r = u.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+        up[:, :, :r.shape[2], :r.shape[3]] = r
+        v = up * m
+        c = F.conv2d(v, Wu[i][0], Wu[i][1], padding=1)
+        if p > 1:
+            a, b = L.center_crop_pair(c, pools[p - 2])
+            u = q(a + b)
+        else:
+            u = L.center_crop_to(c, y_noisy.shape[2], y_noisy.shape[3])
+    return u
+
+
+def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True):
+    """crossentropy (metrics.py:68-91, one_hot=True, void = n_classes) + lmb * squared_error
+    (metrics.py:144-156, void int) of softmax(logits) against the one-hot target (B, C+1, H, W)."""
+    p = torch.softmax(logits, dim=1)
+    true = target.argmax(dim=1)
+    mask = (true != n_classes).to(p.dtype)
+    loss = 0.0
+    if use_ce:
+        pc = torch.clamp(p, EPS_CE, 1.0 - EPS_CE)
+        idx = (true * mask.long()).unsqueeze(1)                       # void pixels point at class 0, then get masked
+        ce = -torch.log(pc.gather(1, idx)).squeeze(1)
+        loss = loss + (ce * mask).sum() / mask.sum()
+    if use_mse:
+        t = target[:, :n_classes]
+        se = ((p - t) ** 2).mean(dim=1)
+        m2 = t.sum(dim=1)
+        loss = loss + lmb * (se * m2).sum() / m2.sum()
+    return loss
+
+
+def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=None, noise_mask=None, lmb=1.0,
+               rho=0.9, eps=1e-6, emulate_bf16=False, **dae_kw):
+    """One train_fn call (train_dae.py:334-335): returns (loss, grads, new_params, new_accus).
+    lasagne.updates.rmsprop: a <- rho*a + (1-rho)*g^2 ; p <- p - lr * g / sqrt(a + eps)."""
+    ps = [p.clone().requires_grad_(True) for p in params]
+    y_main = y if noise_main is None else y + noise_main
+    y_mask = None if noise_mask is None else y + noise_mask
+    logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, **dae_kw)
+    loss = loss_fn(logits, target, n_classes, lmb=lmb)
+    grads = torch.autograd.grad(loss, ps)
+    new_p, new_a = [], []
+    for p, a, g in zip(params, accus, grads):
+        a2 = rho * a + (1 - rho) * g * g
+        new_a.append(a2)
+        new_p.append(p - lr * g / torch.sqrt(a2 + eps))
+    return float(loss.detach()), [g.detach() for g in grads], new_p, new_a

@@ -1,0 +1,95 @@
+"""The DAE training step (BASELINE config 4) on the GPU against the autograd oracle
+(oracle/train.py) with the same weights, inputs and explicit noise tensors.  bf16 operands / bf16 gradient
+tensors with fp32 accumulation: per-parameter gradients within 15 % relative L2 error (stated tolerance; measured
+2-7 %, largest on the first layer, whose gradient has crossed all twelve), the
+loss within 1e-3 relative, the rmsprop update applied to exactly those gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, train as OT, weights
+
+pytestmark = pytest.mark.gpu
+NCLS = 11
+TOL_GRAD = 0.15       # bf16 activations / gradients through 12 layers, incl. pool ties that flip under bf16 rounding
+
+
+def _setup(cuda, B=2, H=32, W=40, seed=3):
+    X, L, lab = weights.synthetic_batch(B, H, W, NCLS, seed=seed)
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    h, y0 = nets.fcn8_forward(pf, X, NCLS)
+    y = L[:, :NCLS].contiguous()                       # from_gt=True: the DAE denoises the ground truth (train_dae.py:371-372)
+    gen = torch.Generator().manual_seed(7)
+    nm = torch.randn(y.shape, generator=gen)
+    nk = torch.randn(y.shape, generator=gen)
+    return pd, h, y, L, nm, nk
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize('with_mask_noise', [False, True])
+def test_train_step_gradients_loss_and_update(cuda, with_mask_noise):
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    pd, h, y, L, nm, nk = _setup(cuda)
+    sigma, lr = 0.5, 1e-3
+    acc = [torch.zeros_like(p) for p in pd]
+    # the oracle rounds weights / stored activations to bf16 like the device path (straight-through), so that pool
+    # ties -- discontinuous in the values -- fall the same way; its arithmetic and its whole backward pass are fp32
+    loss_o, grads_o, newp_o, newa_o = OT.train_step(pd, acc, y, h, L, NCLS, 100, lr, noise_main=sigma * nm,
+                                                    noise_mask=sigma * nk if with_mask_noise else None, emulate_bf16=True)
+    loss_f32 = OT.train_step(pd, acc, y, h, L, NCLS, 100, lr, noise_main=sigma * nm,
+                             noise_mask=sigma * nk if with_mask_noise else None)[0]
+    assert abs(loss_o - loss_f32) < 2e-3 * abs(loss_f32)          # the bf16-storage oracle stays close to the fp32 one
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=sigma)
+    h_b = K.pack_nchw(h.to(cuda), 512)
+    tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda) if with_mask_noise else None)
+    tr.backward(L.to(cuda))
+    torch.cuda.synchronize()
+    assert abs(tr.loss_value() - loss_o) < 1e-3 * abs(loss_o) + 1e-4, (tr.loss_value(), loss_o)
+    errs = [_rel(g.cpu(), go) for g, go in zip(tr.grads_lasagne(), grads_o)]
+    print('relative L2 gradient errors (24 arrays, checkpoint order):', ' '.join('%.3f' % e for e in errs))
+    worst = max(errs)
+    assert worst < TOL_GRAD, errs
+    print('train step parity: loss %.6f vs %.6f, worst relative gradient error %.3e' % (tr.loss_value(), loss_o, worst))
+    before = [p.clone() for p in tr.params()]
+    grads = [g.clone() for g in tr.grads_lasagne()]
+    tr.update()
+    for p0, p1, g in zip(before, tr.params(), grads):     # lasagne.updates.rmsprop on the step's own gradients
+        a = 0.1 * g * g
+        assert torch.allclose(p1, p0 - lr * g / torch.sqrt(a + 1e-6), rtol=1e-5, atol=1e-7)
+    # the next forward uses the updated banks: loss after one step on the same batch does not increase much
+    tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda) if with_mask_noise else None)
+    K.loss_grad(tr.st['logits'], L.to(cuda), NCLS, 1.0, tr.sums)
+    assert tr.loss_value() < loss_o * 1.001
+
+
+def test_backward_kernels_against_definitions(cuda):
+    """depool2_bwd / pool2_relu_bwd / transpose_shift against direct torch restatements."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(0)
+    N, C, H, W = 2, 64, 11, 14
+    x = torch.relu(torch.randn(N, H, W, C)).mul(4).round().div(4).to(torch.bfloat16).to(cuda)       # many ties
+    pooled, mask = K.maxpool2(x, with_mask=True)
+    g_pool = torch.randn(N, H // 2, W // 2, C).to(torch.bfloat16).to(cuda)
+    zm = torch.zeros_like(mask)
+    ga = K.pool2_relu_bwd(g_pool, pooled, mask, H, W, zmask=zm)
+    xf = x.float()
+    up = pooled.float().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    tie = torch.zeros_like(xf); tie[:, :2 * (H // 2), :2 * (W // 2)] = (xf[:, :2 * (H // 2), :2 * (W // 2)] == up).float()
+    gup = torch.zeros_like(xf); gup[:, :2 * (H // 2), :2 * (W // 2)] = (g_pool.float() * (pooled.float() > 0)).repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert torch.equal(ga.float(), gup * tie)
+    gv = torch.randn(N, 7, 9, C).to(torch.bfloat16).to(cuda)            # window at origin (2, 3)
+    gu = K.depool2_bwd(gv, mask, H, W, (2, 3), (1, 1), (4, 5))
+    full = torch.zeros_like(xf); full[:, 2:9, 3:12] = gv.float()
+    ref = (full * tie)[:, :2 * (H // 2), :2 * (W // 2)].reshape(N, H // 2, 2, W // 2, 2, C).sum((2, 4))[:, 1:5, 1:6]
+    assert float((gu.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
+    out = torch.zeros((64, 256), dtype=torch.bfloat16, device=cuda)
+    K.transpose_shift(x, 32, (1, 2), (6, 8), (-2, 1), out, 16, c0=8)
+    P = N * 6 * 8
+    pad = torch.zeros(N, H + 8, W + 8, C, device=cuda); pad[:, 4:4 + H, 4:4 + W] = xf
+    ref = pad[:, 4 + 1 - 2:4 + 1 - 2 + 6, 4 + 2 + 1:4 + 2 + 1 + 8, 8:40].reshape(P, 32).t()
+    assert torch.equal(out[16:48, :P].float(), ref) and float(out[:16].abs().max()) == 0 and float(out[:, P:].abs().max()) == 0
