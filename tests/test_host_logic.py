@@ -104,3 +104,61 @@ def test_synthetic_recipe_matches_oracle_copy():
     assert len(pa) == len(pb) == 590
     for a, b in zip(pa, pb):
         assert torch.equal(a, b)
+
+
+_TRAIN_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from iterative_inference_segm_b200.sharding import World, shard_range
+from oracle import train as OT, weights
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+W_ = World()
+assert (W_.rank, W_.size) == (rank, world)
+torch.set_num_threads(2)
+NCLS, B, H, Wd = 11, 4, 8, 10
+pd = weights.synthetic_dae_params(NCLS, 8, seed=1, n_filters=8, out_gain=0.1)
+gen = torch.Generator().manual_seed(0)
+L = torch.nn.functional.one_hot(torch.randint(0, NCLS + 1, (B, H, Wd), generator=gen), NCLS + 1).permute(0, 3, 1, 2).float()
+y = L[:, :NCLS].contiguous()
+h = torch.rand((B, 8, 12, 13), generator=gen)          # pool4-sized conditioning for an 8x10 image with pad 100 (206x208 -> 12x13)
+noise = 0.5 * torch.randn(y.shape, generator=gen)
+# single-device step on the whole batch
+ps = [p.clone().requires_grad_(True) for p in pd]
+loss_full = OT.loss_fn(OT.dae_forward_train(ps, y + noise, h, 100), L, NCLS)
+g_full = torch.autograd.grad(loss_full, ps)
+# data-parallel: local numerators over GLOBAL denominators (two all-reduces), then SUM of the gradients
+lo, hi = shard_range(B, rank, world)
+ps = [p.clone().requires_grad_(True) for p in pd]
+logits = OT.dae_forward_train(ps, (y + noise)[lo:hi], h[lo:hi], 100)
+p = torch.softmax(logits, 1)
+t = L[lo:hi]
+true = t.argmax(1); mask = (true != NCLS).float()
+ce = -torch.log(torch.clamp(p, 1e-7, 1 - 1e-7).gather(1, (true * mask.long()).unsqueeze(1))).squeeze(1)
+m2 = t[:, :NCLS].sum(1)
+se = ((p - t[:, :NCLS]) ** 2).mean(1)
+den = torch.tensor([float(mask.sum()), float(m2.sum())], dtype=torch.float64)
+W_.allreduce_sum(den)                                   # the loss is a masked mean over the global batch
+loss_local = (ce * mask).sum() / den[0].float() + (se * m2).sum() / den[1].float()
+g = [x.clone() for x in torch.autograd.grad(loss_local, ps)]
+for x in g:
+    W_.allreduce_sum(x)
+for a, b in zip(g, g_full):
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-8), float((a - b).abs().max())
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_two_rank_train_step_allreduce_gloo(tmp_path):
+    """Data-parallel DAE train step protocol (config 4): global loss denominators + SUM of per-rank gradients equals
+    the single-device gradient on the concatenated batch (sharding.World over gloo, autograd oracle as the model)."""
+    script = tmp_path / 'train_worker.py'
+    script.write_text(_TRAIN_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29547')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29547', str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('ok') == 2
