@@ -76,6 +76,12 @@ typedef struct iiseg_conv_desc {
   int C[IISEG_MAX_SRC];
   int Cs[IISEG_MAX_SRC];
   int N, H, W;        /* input extent                                       */
+  /* Split-K GEMM views (1x1 launches, the weight-gradient GEMMs of the training step): image n of the batch is the
+   * n-th K slab of one row-major matrix.  src_image_stride = elements between consecutive images of the source (0 =
+   * dense H*W*Cs); weight_ld = elements per weight row (0 = R*S*sum C); the weight K coordinate of image n starts at
+   * n * w_koff.  Each image then yields its own partial product in `out` [N,..]. */
+  long long src_image_stride, weight_ld;
+  int w_koff;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
   int Cout;           /* padded: 16, or a multiple of 64                    */
@@ -283,6 +289,8 @@ int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const uint32_t* 
 int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0,
                           int OH, int OW, int dh, int dw, void* out, long long ldo, long long row0,
                           void* stream);
+/* out[i] = sum over the S slabs of in[s][i] (fp32, slab order): reduces a split-K GEMM (iiseg_conv_desc.w_koff). */
+int iiseg_sum_slabs(const float* in, float* out, int S, long long n, void* stream);
 int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt,
                        int Cout, int taps, int Cin_pad, int ldg, int bias_col, int ci0, int Ci_t,
                        int Co_pad, float lr, float rho, float eps, void* stream);

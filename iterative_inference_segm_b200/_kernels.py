@@ -389,6 +389,30 @@ def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0):
               _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), _stream())
 
 
+def gemm_nt_splitk(A, Bm, slabs):
+    """G[m][n] = sum_k A[m][k] * Bm[n][k] for row-major bf16 A [M, K], Bm [Nn, K] (K = slabs * slab, slab % 64 == 0),
+    fp32 result [M, Nn].  Runs on the tcgen05 conv kernel as a 1x1 conv whose batch images are the K slabs (split-K: each
+    slab yields a partial product, `iiseg_sum_slabs` adds them in order)."""
+    _chk(A, BF16, 'A')
+    _chk(Bm, BF16, 'Bm')
+    M, Kt = A.shape
+    Nn = Bm.shape[0]
+    assert Bm.shape[1] == Kt and Kt % (64 * slabs) == 0 and (Nn == 16 or Nn % 64 == 0)
+    slab = Kt // slabs
+    part = torch.empty((slabs, 1, M, Nn), dtype=F32, device=A.device)
+    zero = torch.zeros((Nn,), dtype=F32, device=A.device)
+    d = _lib.ConvDesc(N=slabs, H=1, W=M, weight=Bm.data_ptr(), bias=zero.data_ptr(), Cout=Nn, R=1, S=1, pad=0, oh0=0, ow0=0,
+                      OH=1, OW=M, out=part.data_ptr(), relu=0, out_f32=1,
+                      src_image_stride=slab if slabs > 1 else 0, weight_ld=Kt if slabs > 1 else 0, w_koff=slab if slabs > 1 else 0)
+    d.src[0], d.C[0], d.Cs[0] = A.data_ptr(), slab, Kt
+    _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
+    if slabs == 1:
+        return part.view(M, Nn)
+    out = torch.empty((M, Nn), dtype=F32, device=A.device)
+    _lib.call('iiseg_sum_slabs', _ptr(part), _ptr(out), slabs, C.c_longlong(M * Nn), _stream())
+    return out
+
+
 def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t, lr, rho, eps):
     _chk(w, F32, 'w'); _chk(acc, F32, 'acc'); _chk(b, F32, 'b'); _chk(acc_b, F32, 'acc_b'); _chk(g, F32, 'g'); _chk(wb, BF16, 'wb')
     Cout = w.shape[0]

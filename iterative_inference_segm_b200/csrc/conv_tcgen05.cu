@@ -76,6 +76,7 @@ struct alignas(64) ConvParams {
   int TH, TW;
   int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
   int a_blk_bytes, n_a;     // halo kernel: halo-block size and ring depth
+  int w_koff;               // weight K coordinate += image index * w_koff (split-K weight-gradient GEMMs: one K slab per image)
   int pair;                 // CTA-pair kernel (cta_group::2): work units are (N-tile, pair of M-tiles)
   int num_units, m_tiles;   // pair kernel: n_ntiles * ceil(m_tiles / 2) units; m_tiles = N * tiles_h * tiles_w
   int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
                 // tuning: bit5 = every CTA fetches tile 0's A boxes, bit6 = every CTA fetches N-tile 0's B blocks
                 tma_load_4d(stage_a(stage, g), &p.tm_src[src], full_bar(stage), cbl * kBlockK, (p.dbg & 32) ? s : w_base + s,
                             (p.dbg & 32) ? r : h_base + r, (p.dbg & 32) ? 0 : tc.n);
-                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK, (p.dbg & 64) ? 0 : tc.nt * BN);
+                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK + tc.n * p.w_koff, (p.dbg & 64) ? 0 : tc.nt * BN);
                 ++kb;
                 if (++cb == n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
               }
@@ -964,7 +965,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
           int src = 0, cbl = cb;
           while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
           tma_load_4d_2sm(stage_a(stage), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
-          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK, tc.nt * BN + rank * (BN / 2));
+          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK + tc.n * p.w_koff, tc.nt * BN + rank * (BN / 2));
           if (++cb == p.n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -1339,12 +1340,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 tensor seen as (C, W, H, N); box (64, TW, TH, 1); 128B swizzle; OOB reads give zeros.
-static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW, int Cs = 0, int KB = 64) {
+static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int TH, int TW, int Cs = 0, int KB = 64,
+                       long long image_stride = 0) {
   if (Cs == 0) Cs = C;        // channels per pixel in memory (the view may cover only C of them)
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2,
+                           image_stride > 0 ? (cuuint64_t)image_stride * 2 : (cuuint64_t)H * W * Cs * 2};
   cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -1355,17 +1358,17 @@ static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, i
 }
 
 // [Cout][K] bf16 weights seen as (K, Cout); box (64, BN).
-static int encode_weight(CUtensorMap* tm, const void* base, int Cout, int K, int BN, int KB = 64) {
+static int encode_weight(CUtensorMap* tm, const void* base, int Cout, long long K, int BN, int KB = 64, long long ld = 0) {
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : K) * 2};
   cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight Cout=%d K=%d BN=%d) failed: %d", Cout, K, BN, (int)r);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight Cout=%d K=%lld BN=%d) failed: %d", Cout, K, BN, (int)r);
   return 0;
 }
 
@@ -1468,6 +1471,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
   IISEG_CHECK(d->pool_zmask == nullptr || (d->pooled != nullptr && d->split == 0), "conv: pool_zmask needs the fused pool (bf16 variant)");
+  IISEG_CHECK((d->w_koff == 0 && d->weight_ld == 0 && d->src_image_stride == 0) || (d->R == 1 && d->S == 1 && d->w_koff % 64 == 0 && d->weight_ld % 8 == 0),
+              "conv: split-K views (w_koff / weight_ld / src_image_stride) are for 1x1 GEMM launches");
   IISEG_CHECK(d->out_cs == 0 || (d->out_f32 && d->out_cs >= d->Cout && d->out_cs % 4 == 0), "conv: out_cs is for fp32 outputs (channel slice of a wider tensor)");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
   const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
@@ -1532,7 +1537,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   }
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
     if (d->src[i] != nullptr) {
-      if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i], KB)) return -1;
+      if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i], KB, d->src_image_stride)) return -1;
     } else {
       p.tm_src[i] = p.tm_src[0];
     }
@@ -1541,7 +1546,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.n_cblk = n_cblk_all;
   p.split = d->split;
   const int K = d->R * d->S * Cin;
-  if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN, KB)) return -1;
+  const long long Kw = d->w_koff > 0 ? (long long)K + (long long)(d->N - 1) * d->w_koff : K;     // all K slabs of the weight matrix
+  p.w_koff = d->w_koff;
+  if (encode_weight(&p.tm_w, d->weight, d->Cout, Kw, BN, KB, d->weight_ld)) return -1;
   p.bias = d->bias;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
@@ -1578,11 +1585,13 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   {
     static const int env_pair = getenv("IISEG_CONV_PAIR") ? atoi(getenv("IISEG_CONV_PAIR")) : 1;     // 0: single-CTA kernel (A/B comparison)
-    if (env_pair && !halo && (BN == 256 || BN == 128) && KB == 64) {
+    // split-K views: both CTAs of a pair share one filter block, so a pair must not straddle two K slabs (images)
+    const bool pair_same_slab = d->w_koff == 0 || (p.tiles_h * p.tiles_w) % 2 == 0;
+    if (env_pair && !halo && (BN == 256 || BN == 128) && KB == 64 && pair_same_slab) {
       p.pair = 1;
       p.m_tiles = d->N * p.tiles_h * p.tiles_w;
       p.num_units = p.n_ntiles * ((p.m_tiles + 1) / 2);
-      if (encode_weight(&p.tm_w, d->weight, d->Cout, K, BN / 2, KB)) return -1;       // each CTA loads half of a filter block
+      if (encode_weight(&p.tm_w, d->weight, d->Cout, Kw, BN / 2, KB, d->weight_ld)) return -1;       // each CTA loads half of a filter block
       const int max_pairs = num_sms() / 2;
       const int grid = 2 * (p.num_units < max_pairs ? p.num_units : max_pairs);
       static bool configured = false;

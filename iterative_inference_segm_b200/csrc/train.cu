@@ -265,6 +265,18 @@ __global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p
   }
 }
 
+// out[i] = sum_s in[s][i]  (the K slabs of a split-K weight-gradient GEMM, summed in slab order: deterministic)
+__global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict__ in, float4* __restrict__ out, int S, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = in[i];
+    for (int s = 1; s < S; ++s) {
+      const float4 b = in[(long long)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
+  }
+}
+
 static int tgrid(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -359,6 +371,15 @@ extern "C" int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, 
   p.Cout = Cout; p.taps = taps; p.Cin_pad = Cin_pad; p.ldg = ldg; p.bias_col = bias_col; p.ci0 = ci0; p.Ci_t = Ci_t; p.Co_pad = Co_pad;
   p.lr = lr; p.rho = rho; p.eps = eps; p.total = (long long)Cout * taps * Cin_pad;
   rmsprop_pack_kernel<<<tgrid(p.total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_sum_slabs(const float* in, float* out, int S, long long n, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(in && out && S >= 1 && n > 0 && n % 4 == 0, "sum_slabs: bad arguments");
+  sum_slabs_kernel<<<tgrid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(in),
+                                                                                    reinterpret_cast<float4*>(out), S, n / 4);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

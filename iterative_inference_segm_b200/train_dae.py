@@ -181,7 +181,10 @@ class DAETrainer(object):
         sits at `g_origin_in_x` in the coordinates of the input tensors; x_srcs: [(tensor, real_channels_padded)]."""
         B, GH, GW, Cg = g.shape
         Pn = B * GH * GW
-        ldo = _r64(Pn)
+        # split K (the pixel axis) so that the GEMM has a few hundred tiles: the high-resolution layers have tiny M x N
+        tiles = max(1, (Cg + 127) // 128) * max(1, lay.nb // 256)
+        slabs = max(1, min(64, 296 // tiles, Pn // 4096))
+        ldo = (Pn + 64 * slabs - 1) // (64 * slabs) * (64 * slabs)
         A = torch.zeros((Cg, ldo), dtype=torch.bfloat16, device=self.dev)
         K.transpose_shift(g, Cg, (0, 0), (GH, GW), (0, 0), A, 0)
         Bm = torch.zeros((lay.nb, ldo), dtype=torch.bfloat16, device=self.dev)
@@ -192,9 +195,7 @@ class DAETrainer(object):
                 K.transpose_shift(x, c, g_origin_in_x, (GH, GW), (r - pad, s - pad), Bm, row)
                 row += c
         Bm[lay.bias_col, :Pn] = 1.0                                    # the bias gradient is the column against ones
-        zero = torch.zeros((lay.nb,), dtype=torch.float32, device=self.dev)
-        G = K.conv2d(A.view(1, 1, Cg, ldo), Bm, zero, 1, 1, 0, relu=False, out_f32=True)
-        lay.grad = G.view(Cg, lay.nb)
+        lay.grad = K.gemm_nt_splitk(A, Bm, slabs)
         return lay.grad
 
     def _dgrad(self, lay, g, window, addend=None):

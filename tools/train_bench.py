@@ -44,3 +44,7 @@ tot = {}
 for (name, tag), v in timer.summary().items():
     tot[name] = tot.get(name, 0.0) + sum(v)
 print('kernel sums per step (ms):', {k: round(v, 2) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])})
+
+convs = sorted(((sum(v), tag) for (name, tag), v in timer.summary().items() if name == 'conv2d'), reverse=True)[:14]
+for ms_, tag in convs:
+    print('  conv2d %.3f ms  src %s c1 %s Cout %s RxS %sx%s win %s' % (ms_, tag[0], tag[1], tag[2], tag[3], tag[4], tag[5]))
