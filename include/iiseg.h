@@ -29,6 +29,7 @@ extern "C" {
 
 #define IISEG_ABI_VERSION 2
 #define IISEG_MAX_SRC 6
+#define IISEG_MAX_WGROUPS 9
 
 /* ---- library ----------------------------------------------------------- */
 int iiseg_abi_version(void);
@@ -82,6 +83,15 @@ typedef struct iiseg_conv_desc {
    * n * w_koff.  Each image then yields its own partial product in `out` [N,..]. */
   long long src_image_stride, weight_ld;
   int w_koff;
+  /* Weight row groups (1x1 launches): `weight` holds w_rows_total rows; the Cout output channels are w_groups groups
+   * of Cout / w_groups channels, and group g reads rows [w_group_row[g], + Cout / w_groups) at K coordinate +
+   * w_group_koff[g] (a multiple of 8; reads outside the matrix give zero).  With K = pixel index on a zero-padded
+   * grid of pitch Gw (Gw % 8 == 0), the nine taps of a weight gradient
+   *   dW[co][r][s][ci] = sum_p g[co][p] * x[ci][p + r*Gw + s]
+   * are nine such views of three column-shifted copies of x^T (rows s*Cin.., K offset r*Gw): no 9-fold im2col. */
+  int w_groups, w_rows_total;
+  int w_group_koff[IISEG_MAX_WGROUPS];
+  int w_group_row[IISEG_MAX_WGROUPS];
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
   int Cout;           /* padded: 16, or a multiple of 64                    */
@@ -289,6 +299,9 @@ int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const uint32_t* 
 int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0,
                           int OH, int OW, int dh, int dw, void* out, long long ldo, long long row0,
                           void* stream);
+/* Bias gradient: out[c * ld] = sum over the P pixels of g[p][c] (bf16 NHWC rows of C channels, C % 8 == 0), fp32,
+ * deterministic two-stage sum (chunk partials in `scratch`, fp32 [chunks][C], chunks <= 1024, then in chunk order). */
+int iiseg_bias_grad(const void* g, long long P, int C, float* scratch, int chunks, float* out, int ld, void* stream);
 /* out[i] = sum over the S slabs of in[s][i] (fp32, slab order): reduces a split-K GEMM (iiseg_conv_desc.w_koff). */
 int iiseg_sum_slabs(const float* in, float* out, int S, long long n, void* stream);
 int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt,

@@ -389,6 +389,46 @@ def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0):
               _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), _stream())
 
 
+def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
+    """Weight gradient of a conv without a 9-fold im2col:
+        G[co][t*cin_pad + ci] = sum_k gT[co][k] * xT[row_t + ci][k + koff_t]      for (row_t, koff_t) = groups[t]
+    (columns beyond xT's width read as zero; koff_t % 8 == 0) -> fp32 [Cg, out_ld], first len(groups)*cin_pad columns written.
+    gT [Cg, K], xT [rows, K]: bf16, K = slabs * slab, slab % 64 == 0 -- the pixel axis of a zero-padded grid.
+    One launch of the tcgen05 conv kernel: a 1x1 conv whose batch images are the K slabs (split-K) and whose
+    output-channel groups are the taps (`w_groups`); `iiseg_sum_slabs` adds the slab partials in order."""
+    _chk(gT, BF16, 'gT')
+    _chk(xT, BF16, 'xT')
+    M, Kt = gT.shape
+    taps = len(groups)
+    assert xT.shape[1] == Kt and Kt % (64 * slabs) == 0 and out_ld >= taps * cin_pad and out_ld % 4 == 0
+    slab = Kt // slabs
+    part = torch.empty((slabs, M, out_ld), dtype=F32, device=gT.device)
+    zero = torch.zeros((taps * cin_pad,), dtype=F32, device=gT.device)
+    d = _lib.ConvDesc(N=slabs, H=1, W=M, weight=xT.data_ptr(), bias=zero.data_ptr(), Cout=taps * cin_pad, R=1, S=1, pad=0,
+                      oh0=0, ow0=0, OH=1, OW=M, out=part.data_ptr(), relu=0, out_f32=1, out_cs=out_ld,
+                      src_image_stride=slab, weight_ld=Kt, w_koff=slab, w_groups=taps, w_rows_total=xT.shape[0])
+    d.src[0], d.C[0], d.Cs[0] = gT.data_ptr(), slab, Kt
+    for t, (row, k) in enumerate(groups):
+        d.w_group_row[t], d.w_group_koff[t] = row, k
+    _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
+    if slabs == 1:
+        return part.view(M, out_ld)
+    out = torch.empty((M, out_ld), dtype=F32, device=gT.device)
+    _lib.call('iiseg_sum_slabs', _ptr(part), _ptr(out), slabs, C.c_longlong(M * out_ld), _stream())
+    return out
+
+
+def bias_grad(g, out, col, chunks=256):
+    """out[c][col] = sum over the pixels of the bf16 NHWC gradient g[..., c]  (out: fp32 [Cg, ld])."""
+    _chk(g, BF16, 'g')
+    _chk(out, F32, 'out')
+    Cg = g.shape[-1]
+    P = g.numel() // Cg
+    chunks = max(1, min(chunks, P // 64))
+    scratch = torch.empty((chunks, Cg), dtype=F32, device=g.device)
+    _lib.call('iiseg_bias_grad', _ptr(g), C.c_longlong(P), Cg, _ptr(scratch), chunks, out.data_ptr() + 4 * col, out.shape[1], _stream())
+
+
 def gemm_nt_splitk(A, Bm, slabs):
     """G[m][n] = sum_k A[m][k] * Bm[n][k] for row-major bf16 A [M, K], Bm [Nn, K] (K = slabs * slab, slab % 64 == 0),
     fp32 result [M, Nn].  Runs on the tcgen05 conv kernel as a 1x1 conv whose batch images are the K slabs (split-K: each

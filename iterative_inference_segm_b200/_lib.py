@@ -16,6 +16,7 @@ class IisegError(RuntimeError):
 
 ABI_VERSION = 2      # IISEG_ABI_VERSION
 MAX_SRC = 6          # IISEG_MAX_SRC
+MAX_WGROUPS = 9      # IISEG_MAX_WGROUPS
 
 
 class ConvDesc(C.Structure):
@@ -23,7 +24,8 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ('src', C.c_void_p * MAX_SRC), ('C', C.c_int * MAX_SRC), ('Cs', C.c_int * MAX_SRC),
         ('N', C.c_int), ('H', C.c_int), ('W', C.c_int),
-        ('src_image_stride', C.c_longlong), ('weight_ld', C.c_longlong), ('w_koff', C.c_int),
+        ('src_image_stride', C.c_longlong), ('weight_ld', C.c_longlong), ('w_koff', C.c_int), ('w_groups', C.c_int), ('w_rows_total', C.c_int), ('w_group_koff', C.c_int * MAX_WGROUPS),
+        ('w_group_row', C.c_int * MAX_WGROUPS),
         ('weight', C.c_void_p), ('bias', C.c_void_p),
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
@@ -82,6 +84,7 @@ SIGNATURES = {
     'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _vp]),
+    'iiseg_bias_grad': (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _i, _vp]),
     'iiseg_sum_slabs': (_i, [_vp, _vp, _i, C.c_longlong, _vp]),
     'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -77,6 +77,9 @@ struct alignas(64) ConvParams {
   int pitch;                // accumulator rows per box line: TW (per-tap loads) or TW+S-1 (halo tile)
   int a_blk_bytes, n_a;     // halo kernel: halo-block size and ring depth
   int w_koff;               // weight K coordinate += image index * w_koff (split-K weight-gradient GEMMs: one K slab per image)
+  int w_tpt;                // > 0: N tiles per weight row group (iiseg_conv_desc.w_groups): group g re-reads the same rows at K + w_group_koff[g]
+  int w_group_koff[IISEG_MAX_WGROUPS];
+  int w_group_row[IISEG_MAX_WGROUPS];
   int pair;                 // CTA-pair kernel (cta_group::2): work units are (N-tile, pair of M-tiles)
   int num_units, m_tiles;   // pair kernel: n_ntiles * ceil(m_tiles / 2) units; m_tiles = N * tiles_h * tiles_w
   int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
@@ -289,7 +292,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
     const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
-    const int cbase = half * 8;
+    const int cbase = tc.nt * 16 + half * 8;
     uint4 a0 = make_uint4(0, 0, 0, 0);
     const bool has_add = (p.addend != nullptr) && valid;
     if (has_add) a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
@@ -774,6 +777,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
         const TileCoord tc = decode_tile(p, t);
         const int h_base = tc.th * p.TH + p.in_off_h;
         const int w_base = tc.tw * p.TW + p.in_off_w;
+        int w_row = tc.nt * BN, w_k0 = tc.n * p.w_koff;          // filter block origin in the weight matrix
+        if (p.w_tpt > 0) { const int wg = tc.nt / p.w_tpt; w_row = p.w_group_row[wg] + (tc.nt - wg * p.w_tpt) * BN; w_k0 += p.w_group_koff[wg]; }
         int r = 0, s = 0, cb = 0, kb = 0;
         for (int grp = 0; grp < num_groups; ++grp) {
           const int g_n = (num_k_blocks - kb) < G ? (num_k_blocks - kb) : G;
@@ -791,7 +796,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
                 // tuning: bit5 = every CTA fetches tile 0's A boxes, bit6 = every CTA fetches N-tile 0's B blocks
                 tma_load_4d(stage_a(stage, g), &p.tm_src[src], full_bar(stage), cbl * kBlockK, (p.dbg & 32) ? s : w_base + s,
                             (p.dbg & 32) ? r : h_base + r, (p.dbg & 32) ? 0 : tc.n);
-                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK + tc.n * p.w_koff, (p.dbg & 64) ? 0 : tc.nt * BN);
+                tma_load_2d(stage_b(stage, g), &p.tm_w, full_bar(stage), kb * kBlockK + w_k0, (p.dbg & 64) ? 0 : w_row);
                 ++kb;
                 if (++cb == n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
               }
@@ -958,6 +963,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
         const TileCoord tc = decode_unit(p, u, rank, &dummy);
         const int h_base = tc.th * p.TH + p.in_off_h;
         const int w_base = tc.tw * p.TW + p.in_off_w;
+        int w_row = tc.nt * BN, w_k0 = tc.n * p.w_koff;
+        if (p.w_tpt > 0) { const int wg = tc.nt / p.w_tpt; w_row = p.w_group_row[wg] + (tc.nt - wg * p.w_tpt) * BN; w_k0 += p.w_group_koff[wg]; }
         int r = 0, s = 0, cb = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.diag, 1, stage);
@@ -965,7 +972,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
           int src = 0, cbl = cb;
           while (cbl >= p.n_cblk_src[src]) { cbl -= p.n_cblk_src[src]; ++src; }
           tma_load_4d_2sm(stage_a(stage), &p.tm_src[src], full_bar(stage), cbl * kBlockK, w_base + s, h_base + r, tc.n);
-          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK + tc.n * p.w_koff, tc.nt * BN + rank * (BN / 2));
+          tma_load_2d_2sm(stage_b(stage), &p.tm_w, full_bar(stage), kb * kBlockK + w_k0, w_row + rank * (BN / 2));
           if (++cb == p.n_cblk) { cb = 0; if (++s == p.S) { s = 0; ++r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -1468,7 +1475,13 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     Cin += d->C[i];
   }
   IISEG_CHECK(d->split == 0 || (d->out_f32 == 0 && d->Cout % 64 == 0), "conv: split output needs a bf16 output with Cout %% 64 == 0");
-  IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
+  const int wgroups = d->w_groups;
+  if (wgroups > 0)
+    IISEG_CHECK(d->R == 1 && d->S == 1 && wgroups <= IISEG_MAX_WGROUPS && d->Cout % wgroups == 0 &&
+                (d->Cout / wgroups == 16 || (d->Cout / wgroups) % 64 == 0) && d->addend == nullptr && d->pooled == nullptr && d->split == 0,
+                "conv: weight row groups are for plain 1x1 GEMM launches with Cout = w_groups * (16 or a multiple of 64) rows");
+  else
+    IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
   IISEG_CHECK(d->pool_zmask == nullptr || (d->pooled != nullptr && d->split == 0), "conv: pool_zmask needs the fused pool (bf16 variant)");
   IISEG_CHECK((d->w_koff == 0 && d->weight_ld == 0 && d->src_image_stride == 0) || (d->R == 1 && d->S == 1 && d->w_koff % 64 == 0 && d->weight_ld % 8 == 0),
@@ -1489,7 +1502,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
 
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  const int BN = d->Cout == 16 ? 16 : (d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64));
+  const int w_rows = wgroups > 0 ? d->Cout / wgroups : d->Cout;     // filter rows held by the weight matrix
+  const int BN = w_rows == 16 ? 16 : (w_rows % 256 == 0 ? 256 : (w_rows % 128 == 0 ? 128 : 64));
   const bool fuse_pool = d->pooled != nullptr;
   // with the fused pool only the 2*floor(OH/2) x 2*floor(OW/2) outputs that have a pool window are computed
   const int covH = fuse_pool ? (d->OH / 2) * 2 : d->OH, covW = fuse_pool ? (d->OW / 2) * 2 : d->OW;
@@ -1548,7 +1562,19 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   const int K = d->R * d->S * Cin;
   const long long Kw = d->w_koff > 0 ? (long long)K + (long long)(d->N - 1) * d->w_koff : K;     // all K slabs of the weight matrix
   p.w_koff = d->w_koff;
-  if (encode_weight(&p.tm_w, d->weight, d->Cout, Kw, BN, KB, d->weight_ld)) return -1;
+  if (wgroups > 0) {
+    p.w_tpt = w_rows / BN;
+    for (int g = 0; g < wgroups; ++g) {
+      // TMA needs 16-byte aligned coordinates along the contiguous (K) axis
+      IISEG_CHECK(d->w_group_koff[g] % 8 == 0 && d->w_group_row[g] >= 0 && d->w_group_row[g] % BN == 0 && d->w_group_row[g] + w_rows <= d->w_rows_total,
+                  "conv: weight row group %d (row %d, K offset %d) must start at a multiple of 8 along K and inside the %d weight rows", g,
+                  d->w_group_row[g], d->w_group_koff[g], d->w_rows_total);
+      p.w_group_koff[g] = d->w_group_koff[g];
+      p.w_group_row[g] = d->w_group_row[g];
+    }
+  }
+  const int w_rows_all = wgroups > 0 ? d->w_rows_total : d->Cout;
+  if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN, KB, d->weight_ld)) return -1;
   p.bias = d->bias;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
@@ -1591,7 +1617,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       p.pair = 1;
       p.m_tiles = d->N * p.tiles_h * p.tiles_w;
       p.num_units = p.n_ntiles * ((p.m_tiles + 1) / 2);
-      if (encode_weight(&p.tm_w, d->weight, d->Cout, Kw, BN / 2, KB, d->weight_ld)) return -1;       // each CTA loads half of a filter block
+      if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN / 2, KB, d->weight_ld)) return -1;       // each CTA loads half of a filter block
       const int max_pairs = num_sms() / 2;
       const int grid = 2 * (p.num_units < max_pairs ? p.num_units : max_pairs);
       static bool configured = false;

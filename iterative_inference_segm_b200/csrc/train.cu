@@ -277,6 +277,47 @@ __global__ void __launch_bounds__(256) sum_slabs_kernel(const float4* __restrict
   }
 }
 
+// ---- bias gradient: channel sums of a bf16 NHWC gradient, two deterministic stages ---------------------------------
+__global__ void __launch_bounds__(256) bias_grad_partial_kernel(const uint4* __restrict__ g, long long P, int C8, float* __restrict__ part) {
+  // block = 256 threads = (256 / C8l) pixel lanes x C8l channel groups, C8l = min(C8, 32) per pass
+  const int chunk = blockIdx.x, chunks = gridDim.x;
+  const long long per = (P + chunks - 1) / chunks;
+  const long long p0 = chunk * per, p1 = (p0 + per < P) ? p0 + per : P;
+  __shared__ float red[256][9];
+  for (int cg0 = 0; cg0 < C8; cg0 += 32) {
+    const int ncg = (C8 - cg0) < 32 ? (C8 - cg0) : 32;
+    const int lanes = 256 / ncg;
+    const int cg = threadIdx.x % ncg, pl = threadIdx.x / ncg;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (pl < lanes) {
+      for (long long q = p0 + pl; q < p1; q += lanes) {
+        const uint4 v = ldg_nc_v4(g + q * C8 + cg0 + cg);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[2 * j] += bf16_lo(w[j]); a[2 * j + 1] += bf16_hi(w[j]); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = a[j];
+    __syncthreads();
+    if (threadIdx.x < ncg * 8) {
+      const int c8 = threadIdx.x / 8, j = threadIdx.x % 8;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[l * ncg + c8][j];
+      part[(size_t)chunk * C8 * 8 + (cg0 + c8) * 8 + j] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_grad_final_kernel(const float* __restrict__ part, int chunks, int C, float* __restrict__ out, int ld) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[(size_t)k * C + c];
+  out[(size_t)c * ld] = s;
+}
+
 static int tgrid(long long total) {
   long long b = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -380,6 +421,17 @@ extern "C" int iiseg_sum_slabs(const float* in, float* out, int S, long long n, 
   IISEG_CHECK(in && out && S >= 1 && n > 0 && n % 4 == 0, "sum_slabs: bad arguments");
   sum_slabs_kernel<<<tgrid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(in),
                                                                                     reinterpret_cast<float4*>(out), S, n / 4);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_bias_grad(const void* g, long long P, int C, float* scratch, int chunks, float* out, int ld, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(g && scratch && out && P > 0 && C > 0 && C % 8 == 0 && chunks >= 1 && chunks <= 1024 && ld >= 1, "bias_grad: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  bias_grad_partial_kernel<<<chunks, 256, 0, s>>>(reinterpret_cast<const uint4*>(g), P, C / 8, scratch);
+  IISEG_LAUNCH_CHECK();
+  bias_grad_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(scratch, chunks, C, out, ld);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -10,7 +10,7 @@ import torch
 
 from . import _kernels as K
 
-_WRAPPED = ['conv2d', 'maxpool2', 'unpool2', 'softmax_update', 'softmax_nchw', 'norm_finalize',
+_WRAPPED = ['conv2d', 'wgrad_gemm', 'gemm_nt_splitk', 'bias_grad', 'maxpool2', 'unpool2', 'softmax_update', 'softmax_nchw', 'norm_finalize',
             'metrics_accumulate', 'deconv16', 'pack_nchw', 'norm_finalize_fixed', 'bn_relu_pack', 'channel_stats',
             'maxpool2_f32', 'deconv_interleave']
 

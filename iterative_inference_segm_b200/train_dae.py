@@ -180,22 +180,29 @@ class DAETrainer(object):
         """dW (+ db) of `lay` = one GEMM.  g: [B,GH,GW,Cg] gradient w.r.t. the conv output over a window whose origin
         sits at `g_origin_in_x` in the coordinates of the input tensors; x_srcs: [(tensor, real_channels_padded)]."""
         B, GH, GW, Cg = g.shape
-        Pn = B * GH * GW
+        # Both operands live on ONE zero-padded pixel grid of Gh x Gw per image (Gw a multiple of 8): g at the origin, x
+        # shifted by `pad`, so that output pixel k meets tap (r, s) at column k + r*Gw + s of x^T.  TMA wants 16-byte
+        # aligned K coordinates, so x^T is written three times (one copy per horizontal shift s) and tap (r, s) is copy s
+        # read at K + r*Gw (iiseg_conv_desc.w_groups): 3 transposed copies instead of 9.
+        Gh, Gw = GH + 2, (GW + 2 + 7) // 8 * 8
+        Pn = B * Gh * Gw
         # split K (the pixel axis) so that the GEMM has a few hundred tiles: the high-resolution layers have tiny M x N
-        tiles = max(1, (Cg + 127) // 128) * max(1, lay.nb // 256)
+        bn = min(lay.cin_pad, 256)
+        tiles = max(1, (Cg + 127) // 128) * (9 * lay.cin_pad // bn)
         slabs = max(1, min(64, 296 // tiles, Pn // 4096))
         ldo = (Pn + 64 * slabs - 1) // (64 * slabs) * (64 * slabs)
-        A = torch.zeros((Cg, ldo), dtype=torch.bfloat16, device=self.dev)
-        K.transpose_shift(g, Cg, (0, 0), (GH, GW), (0, 0), A, 0)
-        Bm = torch.zeros((lay.nb, ldo), dtype=torch.bfloat16, device=self.dev)
-        for tap in range(9):
-            r, s = tap // 3, tap % 3
-            row = tap * lay.cin_pad
+        gT = torch.empty((Cg, ldo), dtype=torch.bfloat16, device=self.dev)
+        K.transpose_shift(g, Cg, (0, 0), (Gh, Gw), (0, 0), gT, 0)
+        xT = torch.empty((3 * lay.cin_pad, ldo), dtype=torch.bfloat16, device=self.dev)
+        for s_ in range(3):
+            row = s_ * lay.cin_pad
             for x, c in x_srcs:
-                K.transpose_shift(x, c, g_origin_in_x, (GH, GW), (r - pad, s - pad), Bm, row)
+                K.transpose_shift(x, c, g_origin_in_x, (Gh, Gw), (-pad, s_ - pad), xT, row)
                 row += c
-        Bm[lay.bias_col, :Pn] = 1.0                                    # the bias gradient is the column against ones
-        lay.grad = K.gemm_nt_splitk(A, Bm, slabs)
+            assert row == (s_ + 1) * lay.cin_pad
+        groups = [(s_ * lay.cin_pad, r * Gw) for r in range(3) for s_ in range(3)]
+        lay.grad = K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb)
+        K.bias_grad(g, lay.grad, lay.bias_col)
         return lay.grad
 
     def _dgrad(self, lay, g, window, addend=None):

@@ -93,3 +93,38 @@ def test_backward_kernels_against_definitions(cuda):
     pad = torch.zeros(N, H + 8, W + 8, C, device=cuda); pad[:, 4:4 + H, 4:4 + W] = xf
     ref = pad[:, 4 + 1 - 2:4 + 1 - 2 + 6, 4 + 2 + 1:4 + 2 + 1 + 8, 8:40].reshape(P, 32).t()
     assert torch.equal(out[16:48, :P].float(), ref) and float(out[:16].abs().max()) == 0 and float(out[:, P:].abs().max()) == 0
+
+
+# (Cg, cin_pad, K, slabs, K offsets of the three tap rows): CTA-pair and single-CTA launches, 16-row groups, odd M
+WGRAD_CASES = [(16, 64, 4096, 1, (0, 72, 144)), (128, 256, 8192, 4, (0, 72, 144)), (64, 16, 8192, 2, (0, 32, 64)),
+               (256, 512, 4096, 2, (0, 32, 64)), (128, 128, 4096 * 3, 3, (0, 216, 432))]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES, ids=[str(c) for c in WGRAD_CASES])
+def test_wgrad_gemm_matches_matmul(cuda, case):
+    """The im2col-free weight-gradient GEMM (K slabs as images, taps as K-shifted weight row groups) against
+    fp32 matmuls of the same bf16 operands.  Tolerance: fp32 accumulation order only, 1e-5 of |a|.|b| summed."""
+    from iterative_inference_segm_b200 import _kernels as K
+    M, cin, Kt, slabs, koffs = case
+    torch.manual_seed(0)
+    gT = torch.randn(M, Kt, device=cuda).to(torch.bfloat16)
+    xT = torch.randn(3 * cin, Kt, device=cuda).to(torch.bfloat16)
+    groups = [(s * cin, k) for k in koffs for s in range(3)]
+    ld = (9 * cin + 1 + 63) // 64 * 64
+    G = K.wgrad_gemm(gT, xT, cin, groups, slabs, ld)
+    xp = torch.cat([xT.float(), torch.zeros(3 * cin, 512, device=cuda)], 1)
+    ref = torch.cat([gT.float() @ xp[r:r + cin, k:k + Kt].t() for (r, k) in groups], 1)
+    bound = torch.cat([gT.float().abs() @ xp[r:r + cin, k:k + Kt].abs().t() for (r, k) in groups], 1)
+    assert ((G[:, :9 * cin] - ref).abs() <= 1e-5 * bound + 1e-6).all()
+
+
+def test_bias_grad_matches_sum(cuda):
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(0)
+    for (P, Cg) in [((3, 17, 23), 16), ((2, 40, 33), 64), ((1, 9, 11), 512)]:
+        g = torch.randn(*P, Cg, device=cuda).to(torch.bfloat16)
+        out = torch.zeros(Cg, 8, device=cuda)
+        K.bias_grad(g, out, 5)
+        ref = g.float().sum(dim=(0, 1, 2))
+        assert torch.allclose(out[:, 5], ref, rtol=1e-5, atol=1e-4)
+        assert (out[:, :5] == 0).all() and (out[:, 6:] == 0).all()
