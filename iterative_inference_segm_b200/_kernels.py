@@ -418,7 +418,7 @@ def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
     return out
 
 
-def bias_grad(g, out, col, chunks=256):
+def bias_grad(g, out, col, chunks=592):
     """out[c][col] = sum over the pixels of the bf16 NHWC gradient g[..., c]  (out: fp32 [Cg, ld])."""
     _chk(g, BF16, 'g')
     _chk(out, F32, 'out')

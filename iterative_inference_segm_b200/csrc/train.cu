@@ -207,27 +207,43 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const uint4* __restr
 struct TransposeParams { const __nv_bfloat16* x; __nv_bfloat16* out; int N, H, W, Cs, c0, C, h0, w0, OH, OW, dh, dw; long long ldo, row0, P; };
 
 __global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposeParams p) {
-  __shared__ __nv_bfloat16 tile[64][66];
+  // 64 pixels x 64 channels per block.  33-word row pitch: the 4-byte stores of the load phase (lanes = 8 channel
+  // chunks x 4 pixels) and the 2-byte column reads of the store phase (lanes = 4 pixel groups x 8 channels) are
+  // both bank-conflict free; global loads move whole 128-byte pixel rows, global stores 64-byte row segments.
+  __shared__ uint32_t tile[64][33];
   const long long p_base = (long long)blockIdx.x * 64;
   const int c_base = blockIdx.y * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // 64 x 4
-  for (int i = ty; i < 64; i += 4) {                              // row i = pixel, tx = channel
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    const int chunk = idx & 7, i = idx >> 3;                        // pixel i, channels chunk*8 .. +7
     const long long pp = p_base + i;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (pp < p.P && c_base + tx < p.C) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pp < p.P && c_base + chunk * 8 < p.C) {
       long long t = pp;
       const int ow = (int)(t % p.OW); t /= p.OW;
       const int oh = (int)(t % p.OH);
       const long long n = t / p.OH;
       const int ih = p.h0 + oh + p.dh, iw = p.w0 + ow + p.dw;
-      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = p.x[((n * p.H + ih) * p.W + iw) * p.Cs + p.c0 + c_base + tx];
+      if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) v = ldg_nc_v4(p.x + ((n * p.H + ih) * p.W + iw) * p.Cs + p.c0 + c_base + chunk * 8);
     }
-    tile[i][tx] = v;
+    tile[i][chunk * 4 + 0] = v.x; tile[i][chunk * 4 + 1] = v.y; tile[i][chunk * 4 + 2] = v.z; tile[i][chunk * 4 + 3] = v.w;
   }
   __syncthreads();
-  for (int i = ty; i < 64; i += 4) {                              // row i = channel, tx = pixel
-    const long long pp = p_base + tx;
-    if (c_base + i < p.C && pp < p.ldo) p.out[(p.row0 + c_base + i) * p.ldo + pp] = pp < p.P ? tile[tx][i] : __float2bfloat16(0.f);
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(&tile[0][0]);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    const int pg = (idx & 3) + 4 * it, c = (idx >> 2) & 63;         // pixels pg*8 .. +7 of channel c
+    if (c_base + c < p.C) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t lo = t16[(pg * 8 + 2 * j) * 66 + c], hi = t16[(pg * 8 + 2 * j + 1) * 66 + c];
+        w[j] = lo | (hi << 16);
+      }
+      stg_v4(p.out + (p.row0 + c_base + c) * p.ldo + p_base + pg * 8, make_uint4(w[0], w[1], w[2], w[3]));
+    }
   }
 }
 
@@ -388,6 +404,7 @@ extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs,
   using namespace iiseg;
   IISEG_CHECK(x && out, "transpose_shift: null tensor");
   IISEG_CHECK(N > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && OH > 0 && OW > 0 && ldo >= (long long)N * OH * OW, "transpose_shift: bad shape");
+  IISEG_CHECK(C % 8 == 0 && c0 % 8 == 0 && Cs % 8 == 0 && ldo % 64 == 0, "transpose_shift: channels must come in groups of 8 and ldo in multiples of 64 (16-byte accesses)");
   TransposeParams p;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.N = N; p.H = H; p.W = W; p.Cs = Cs; p.c0 = c0; p.C = C; p.h0 = h0; p.w0 = w0; p.OH = OH; p.OW = OW; p.dh = dh; p.dw = dw;
