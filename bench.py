@@ -11,7 +11,8 @@ scaling); the only collective is the all-reduce of the int64 confusion matrix.
 
 `value`  : whole-job images/s with the batch already resident in HBM.
 `e2e`    : the same through the public callables with HOST (pinned) buffers: H2D of the images and
-           the one-hot targets and D2H of the metrics inside the timed region.
+           the one-hot targets and D2H of the metrics inside the timed region, every step (the copies
+           of step i+1 ride a copy stream under step i's kernels, as with a prefetching iterator).
 `roofline`: the tcgen05 conv kernel (all conv launches of one DAE application), CUDA-event timed.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the reference path (oracle/, PyTorch
            CPU fp32; Theano is not installable) on the host cores, on a bounded sample.
@@ -192,11 +193,37 @@ def run_b200(args):
             dist.all_reduce(cm_total)
         return res
 
-    def step_e2e():
-        Xd = X_host.to(dev, non_blocking=True)
-        Ld = L_host.to(dev, non_blocking=True)
-        res = step_device(Xd, Ld)
-        return cm_total.cpu(), res['n_exec'].cpu()
+    # End to end: every step copies its own inputs from pinned host memory and reads its result back.  The copies
+    # of step i+1 are issued on a copy stream before step i's kernels (two device buffers, like a prefetching data
+    # iterator), so only the first step's H2D is exposed; the D2H read of the result blocks the host every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    in_bufs = [(torch.empty_like(X_dev), torch.empty_like(L_dev)) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_h2d(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])
+            in_bufs[b][0].copy_(X_host, non_blocking=True)
+            in_bufs[b][1].copy_(L_host, non_blocking=True)
+            ev_ready[b].record(copy_stream)
+
+    def run_e2e(n):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            ev_free[b].record(cur)
+        issue_h2d(0)
+        out = None
+        for i in range(n):
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            b = i % 2
+            cur.wait_event(ev_ready[b])
+            res = step_device(*in_bufs[b])
+            ev_free[b].record(cur)
+            out = (cm_total.cpu(), res['n_exec'].cpu())
+        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,8 +268,8 @@ def run_b200(args):
         ms_dev, _ = timed(lambda: step_device(X_dev, L_dev), args.steps)
     clocks = clk.summary()
     # ---- timed region: end to end through host buffers (pinned), H2D + D2H inside
-    step_e2e()
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    run_e2e(2)
+    ms_e2e, wall_e2e = timed(lambda: run_e2e(args.steps), 1)
     ms_e2e = max(ms_e2e, wall_e2e)     # D2H reads block the host: wall clock covers them
 
     imgs = BATCH * world * args.steps
