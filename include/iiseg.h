@@ -281,11 +281,13 @@ int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10
  *   elements whose pre-rectifier value is exactly 0 (zmask, iiseg_conv_desc.pool_zmask) get g_pool / 2
  *   (rectify = 0.5*(x+|x|)), the negative ones 0.
  * iiseg_transpose_shift: out[(row0+c)*ldo + p] = x[n, h0+oh+dh, w0+ow+dw, c0+c] (0 outside the map),
- *   p = (n*OH+oh)*OW+ow: the K-major operands g^T / tap-shifted x^T of the weight-gradient GEMM
+ *   p = (n*OH+oh)*OW+ow; with nshift > 1 also the copies s = 1..nshift-1 at rows + s*shift_rows, copy s being
+ *   the same matrix read at flat pixel p + s (one read of x, nshift writes): the K-major operands g^T / x^T of the weight-gradient GEMM
  *   dW[co][tap][ci] = sum_p g[p][co] x[p+tap][ci], which then runs on iiseg_conv2d_fwd (1x1, K = pixels).
  * iiseg_rmsprop_pack: lasagne.updates.rmsprop (a <- rho a + (1-rho) g^2; w <- w - lr g / sqrt(a+eps))
  *   on the fp32 master bank [Cout][taps][Cin_pad] and bias, reading g from the GEMM output [Cout][ldg]
- *   (bias gradient in column bias_col); re-emits the bf16 forward bank wb and, if wt != NULL, the
+ *   (filter tap (r, s), channel ci in column r * g_rstride + s * Cin_pad + ci, g_rstride = 0 meaning
+ *   3 * Cin_pad; bias gradient in column bias_col); re-emits the bf16 forward bank wb and, if wt != NULL, the
  *   flipped / transposed bank of the data-gradient conv wt[ci-ci0][taps-1-tap][co] ([Ci_t][taps][Co_pad]). */
 int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H,
                      int W, int Cpad, void* stream);
@@ -298,15 +300,15 @@ int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const uint32_t* 
                          const uint32_t* zmask, void* ga, int N, int H, int W, int C, void* stream);
 int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0,
                           int OH, int OW, int dh, int dw, void* out, long long ldo, long long row0,
-                          void* stream);
+                          int nshift, long long shift_rows, void* stream);
 /* Bias gradient: out[c * ld] = sum over the P pixels of g[p][c] (bf16 NHWC rows of C channels, C % 8 == 0), fp32,
  * deterministic two-stage sum (chunk partials in `scratch`, fp32 [chunks][C], chunks <= 1024, then in chunk order). */
 int iiseg_bias_grad(const void* g, long long P, int C, float* scratch, int chunks, float* out, int ld, void* stream);
 /* out[i] = sum over the S slabs of in[s][i] (fp32, slab order): reduces a split-K GEMM (iiseg_conv_desc.w_koff). */
 int iiseg_sum_slabs(const float* in, float* out, int S, long long n, void* stream);
 int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt,
-                       int Cout, int taps, int Cin_pad, int ldg, int bias_col, int ci0, int Ci_t,
-                       int Co_pad, float lr, float rho, float eps, void* stream);
+                       int Cout, int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0,
+                       int Ci_t, int Co_pad, float lr, float rho, float eps, void* stream);
 
 #ifdef __cplusplus
 }

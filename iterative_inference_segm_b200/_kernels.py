@@ -379,14 +379,15 @@ def pool2_relu_bwd(gpool, pooled, mask, H, W, zmask=None):
     return ga
 
 
-def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0):
-    """out[row0 + c, p] = x[n, origin+o+shift, c0 + c] (zero outside the map), p = flat (n, oh, ow) over `size`."""
+def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0, nshift=1, shift_rows=0):
+    """out[row0 + c, p] = x[n, origin+o+shift, c0 + c] (zero outside the map), p = flat (n, oh, ow) over `size`;
+    nshift > 1 also writes the copies s at rows + s*shift_rows holding the same matrix at flat pixel p + s."""
     _chk(x, BF16, 'x')
     _chk(out, BF16, 'out')
     N, H, W, Cs = x.shape
-    assert out.dim() == 2 and row0 + C_ <= out.shape[0] and out.shape[1] >= N * size[0] * size[1]
+    assert out.dim() == 2 and row0 + (nshift - 1) * shift_rows + C_ <= out.shape[0] and out.shape[1] >= N * size[0] * size[1]
     _lib.call('iiseg_transpose_shift', _ptr(x), N, H, W, Cs, c0, C_, origin[0], origin[1], size[0], size[1], shift[0], shift[1],
-              _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), _stream())
+              _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), nshift, C.c_longlong(shift_rows), _stream())
 
 
 def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
@@ -453,7 +454,7 @@ def gemm_nt_splitk(A, Bm, slabs):
     return out
 
 
-def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t, lr, rho, eps):
+def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t, lr, rho, eps, g_rstride=0):
     _chk(w, F32, 'w'); _chk(acc, F32, 'acc'); _chk(b, F32, 'b'); _chk(acc_b, F32, 'acc_b'); _chk(g, F32, 'g'); _chk(wb, BF16, 'wb')
     Cout = w.shape[0]
     assert w.numel() == Cout * taps * cin_pad == acc.numel() == wb.numel() and g.shape[0] == Cout
@@ -463,7 +464,7 @@ def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t
         assert wt.shape[0] == ci_t and wt.shape[1] % taps == 0
         co_pad = wt.shape[1] // taps
     _lib.call('iiseg_rmsprop_pack', _ptr(w), _ptr(acc), _ptr(b), _ptr(acc_b), _ptr(g), _ptr(wb), _ptr(wt), Cout, taps, cin_pad,
-              g.shape[1], bias_col, ci0, ci_t, co_pad, C.c_float(lr), C.c_float(rho), C.c_float(eps), _stream())
+              g.shape[1], g_rstride, bias_col, ci0, ci_t, co_pad, C.c_float(lr), C.c_float(rho), C.c_float(eps), _stream())
 
 
 # ---- metrics ------------------------------------------------------------------

@@ -83,10 +83,10 @@ SIGNATURES = {
     'iiseg_loss_grad': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _vp]),
+    'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _i, C.c_longlong, _vp]),
     'iiseg_bias_grad': (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _i, _vp]),
     'iiseg_sum_slabs': (_i, [_vp, _vp, _i, C.c_longlong, _vp]),
-    'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
+    'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

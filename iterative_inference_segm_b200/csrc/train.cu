@@ -204,18 +204,19 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const uint4* __restr
 // out[(row0 + c) * ldo + p] = x[n, h0 + oh + dh, w0 + ow + dw, c0 + c]  (0 outside the HxW map), p = (n*OH + oh)*OW + ow,
 // for c < C; columns p in [P, ldo) are written as zeros by the caller's memset.  64 pixels x 64 channels per block
 // through shared memory so that both sides move 128-byte rows.
-struct TransposeParams { const __nv_bfloat16* x; __nv_bfloat16* out; int N, H, W, Cs, c0, C, h0, w0, OH, OW, dh, dw; long long ldo, row0, P; };
+struct TransposeParams { const __nv_bfloat16* x; __nv_bfloat16* out; int N, H, W, Cs, c0, C, h0, w0, OH, OW, dh, dw, nshift; long long ldo, row0, shift_rows, P; };
 
 __global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposeParams p) {
-  // 64 pixels x 64 channels per block.  33-word row pitch: the 4-byte stores of the load phase (lanes = 8 channel
+  // 64 (+8) pixels x 64 channels per block.  33-word row pitch: the 4-byte stores of the load phase (lanes = 8 channel
   // chunks x 4 pixels) and the 2-byte column reads of the store phase (lanes = 4 pixel groups x 8 channels) are
-  // both bank-conflict free; global loads move whole 128-byte pixel rows, global stores 64-byte row segments.
-  __shared__ uint32_t tile[64][33];
+  // bank-conflict free; global loads move whole 128-byte pixel rows, global stores 64-byte row segments.
+  // nshift > 1: copy s of the output (rows + s * shift_rows) is the same matrix shifted by s pixels along the flat
+  // pixel axis -- read once (8 extra pixels), written nshift times.
+  __shared__ uint32_t tile[72][33];
   const long long p_base = (long long)blockIdx.x * 64;
   const int c_base = blockIdx.y * 64;
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int idx = threadIdx.x + it * 256;
+  const int n_pix = p.nshift > 1 ? 72 : 64;
+  for (int idx = threadIdx.x; idx < n_pix * 8; idx += 256) {
     const int chunk = idx & 7, i = idx >> 3;                        // pixel i, channels chunk*8 .. +7
     const long long pp = p_base + i;
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -231,18 +232,20 @@ __global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposePar
   }
   __syncthreads();
   const unsigned short* t16 = reinterpret_cast<const unsigned short*>(&tile[0][0]);
+  for (int sh = 0; sh < p.nshift; ++sh) {
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int idx = threadIdx.x + it * 256;
-    const int pg = (idx & 3) + 4 * it, c = (idx >> 2) & 63;         // pixels pg*8 .. +7 of channel c
-    if (c_base + c < p.C) {
-      uint32_t w[4];
+    for (int it = 0; it < 2; ++it) {
+      const int idx = threadIdx.x + it * 256;
+      const int pg = (idx & 3) + 4 * it, c = (idx >> 2) & 63;         // pixels pg*8 .. +7 of channel c
+      if (c_base + c < p.C) {
+        uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t lo = t16[(pg * 8 + 2 * j) * 66 + c], hi = t16[(pg * 8 + 2 * j + 1) * 66 + c];
-        w[j] = lo | (hi << 16);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lo = t16[(pg * 8 + 2 * j + sh) * 66 + c], hi = t16[(pg * 8 + 2 * j + 1 + sh) * 66 + c];
+          w[j] = lo | (hi << 16);
+        }
+        stg_v4(p.out + (p.row0 + sh * p.shift_rows + c_base + c) * p.ldo + p_base + pg * 8, make_uint4(w[0], w[1], w[2], w[3]));
       }
-      stg_v4(p.out + (p.row0 + c_base + c) * p.ldo + p_base + pg * 8, make_uint4(w[0], w[1], w[2], w[3]));
     }
   }
 }
@@ -255,29 +258,53 @@ __global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposePar
 // for the ci range [ci0, ci0 + Ci_t) only (the concat conv propagates to its own half), padded to Co_pad columns.
 struct RmspropParams {
   float* w; float* acc; float* b; float* acc_b; const float* g; __nv_bfloat16* wb; __nv_bfloat16* wt;
-  int Cout, taps, Cin_pad, ldg, bias_col, ci0, Ci_t, Co_pad; float lr, rho, eps; long long total;
+  int Cout, taps, Cin_pad, ldg, bias_col, ci0, Ci_t, Co_pad, g_rstride; float lr, rho, eps; long long total;
 };
 
 __global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.total; i += (long long)gridDim.x * blockDim.x) {
-    const int per = p.taps * p.Cin_pad;
-    const int co = (int)(i / per), rem = (int)(i - (long long)co * per);
-    const int tap = rem / p.Cin_pad, ci = rem - tap * p.Cin_pad;
-    const float g = p.g[(size_t)co * p.ldg + rem];
-    const float a = p.rho * p.acc[i] + (1.f - p.rho) * g * g;
-    p.acc[i] = a;
-    const float w = p.w[i] - p.lr * g / sqrtf(a + p.eps);
-    p.w[i] = w;
-    const __nv_bfloat16 wb = __float2bfloat16(w);
-    p.wb[i] = wb;
-    if (p.wt != nullptr && ci >= p.ci0 && ci < p.ci0 + p.Ci_t)
-      p.wt[((size_t)(ci - p.ci0) * p.taps + (p.taps - 1 - tap)) * p.Co_pad + co] = wb;
+  // One block = 64 output channels x 16 input channels of one tap.  Thread (r, q) owns 4 consecutive input channels
+  // of output channel r: 16-byte accesses to w / acc / g, 8-byte stores of the forward bank.  The data-gradient
+  // bank wants the OUTPUT channel contiguous, so the bf16 tile goes through shared memory and thread (ci, cq) writes
+  // 4 consecutive output channels of input channel ci (8-byte stores, 128-byte runs per row).
+  __shared__ unsigned short tile[64][18];
+  const int n_cit = p.Cin_pad >> 4;
+  const int tap = blockIdx.x / n_cit, ci_base = (blockIdx.x - tap * n_cit) << 4;
+  const int co_base = blockIdx.y * 64;
+  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const int co = co_base + r;
+  uint32_t packed0 = 0, packed1 = 0;
+  if (co < p.Cout) {
+    const int rem = tap * p.Cin_pad + ci_base + 4 * q;
+    const size_t i = ((size_t)co * p.taps) * p.Cin_pad + rem;
+    const int fr = tap / 3;                                  // gradient column: filter row fr at stride g_rstride
+    const float4 g = *reinterpret_cast<const float4*>(p.g + (size_t)co * p.ldg + fr * p.g_rstride + (rem - fr * 3 * p.Cin_pad));
+    float4 a = *reinterpret_cast<const float4*>(p.acc + i);
+    float4 w = *reinterpret_cast<const float4*>(p.w + i);
+    a.x = p.rho * a.x + (1.f - p.rho) * g.x * g.x; w.x -= p.lr * g.x / sqrtf(a.x + p.eps);
+    a.y = p.rho * a.y + (1.f - p.rho) * g.y * g.y; w.y -= p.lr * g.y / sqrtf(a.y + p.eps);
+    a.z = p.rho * a.z + (1.f - p.rho) * g.z * g.z; w.z -= p.lr * g.z / sqrtf(a.z + p.eps);
+    a.w = p.rho * a.w + (1.f - p.rho) * g.w * g.w; w.w -= p.lr * g.w / sqrtf(a.w + p.eps);
+    *reinterpret_cast<float4*>(p.acc + i) = a;
+    *reinterpret_cast<float4*>(p.w + i) = w;
+    packed0 = pack_bf16x2(w.x, w.y); packed1 = pack_bf16x2(w.z, w.w);
+    *reinterpret_cast<uint2*>(p.wb + i) = make_uint2(packed0, packed1);
     if (rem == 0) {       // one thread per output channel also updates the bias
       const float gb = p.g[(size_t)co * p.ldg + p.bias_col];
       const float ab = p.rho * p.acc_b[co] + (1.f - p.rho) * gb * gb;
       p.acc_b[co] = ab;
       p.b[co] -= p.lr * gb / sqrtf(ab + p.eps);
     }
+  }
+  if (p.wt == nullptr || ci_base < p.ci0 || ci_base >= p.ci0 + p.Ci_t) return;      // block-uniform
+  tile[r][4 * q + 0] = (unsigned short)(packed0 & 0xFFFFu); tile[r][4 * q + 1] = (unsigned short)(packed0 >> 16);
+  tile[r][4 * q + 2] = (unsigned short)(packed1 & 0xFFFFu); tile[r][4 * q + 3] = (unsigned short)(packed1 >> 16);
+  __syncthreads();
+  const int ci = threadIdx.x >> 4, cq = threadIdx.x & 15;
+  const int co4 = co_base + 4 * cq;
+  if (co4 < p.Cout) {       // Cout % 4 == 0 (padded channel counts)
+    const uint32_t lo = (uint32_t)tile[4 * cq][ci] | ((uint32_t)tile[4 * cq + 1][ci] << 16);
+    const uint32_t hi = (uint32_t)tile[4 * cq + 2][ci] | ((uint32_t)tile[4 * cq + 3][ci] << 16);
+    *reinterpret_cast<uint2*>(p.wt + ((size_t)(ci_base + ci - p.ci0) * p.taps + (p.taps - 1 - tap)) * p.Co_pad + co4) = make_uint2(lo, hi);
   }
 }
 
@@ -327,11 +354,22 @@ __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const uint4* __r
 }
 
 __global__ void __launch_bounds__(256) bias_grad_final_kernel(const float* __restrict__ part, int chunks, int C, float* __restrict__ out, int ld) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= C) return;
+  // 32 channels per block; warp w adds chunks w, w+8, ... (coalesced 128-byte rows), then the 8 partial sums are
+  // added in warp order: a fixed summation tree, hence run-to-run identical results
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += part[(size_t)k * C + c];
-  out[(size_t)c * ld] = s;
+  if (c < C)
+    for (int k = w; k < chunks; k += 8) s += part[(size_t)k * C + c];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < C) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    out[(size_t)c * ld] = t;
+  }
 }
 
 static int tgrid(long long total) {
@@ -400,7 +438,8 @@ extern "C" int iiseg_pool2_relu_bwd(const void* gpool, const void* pooled, const
 }
 
 extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs, int c0, int C, int h0, int w0, int OH, int OW,
-                                     int dh, int dw, void* out, long long ldo, long long row0, void* stream) {
+                                     int dh, int dw, void* out, long long ldo, long long row0, int nshift, long long shift_rows,
+                                     void* stream) {
   using namespace iiseg;
   IISEG_CHECK(x && out, "transpose_shift: null tensor");
   IISEG_CHECK(N > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && OH > 0 && OW > 0 && ldo >= (long long)N * OH * OW, "transpose_shift: bad shape");
@@ -408,7 +447,8 @@ extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs,
   TransposeParams p;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.N = N; p.H = H; p.W = W; p.Cs = Cs; p.c0 = c0; p.C = C; p.h0 = h0; p.w0 = w0; p.OH = OH; p.OW = OW; p.dh = dh; p.dw = dw;
-  p.ldo = ldo; p.row0 = row0; p.P = (long long)N * OH * OW;
+  IISEG_CHECK(nshift >= 1 && nshift <= 8 && (nshift == 1 || shift_rows >= C), "transpose_shift: bad shift copies");
+  p.ldo = ldo; p.row0 = row0; p.P = (long long)N * OH * OW; p.nshift = nshift; p.shift_rows = shift_rows;
   const long long pblocks = (ldo + 63) / 64;
   IISEG_CHECK(pblocks < (1LL << 31) && (C + 63) / 64 <= 65535, "transpose_shift: too large");
   dim3 grid((unsigned)pblocks, (C + 63) / 64);
@@ -418,17 +458,23 @@ extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs,
 }
 
 extern "C" int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt, int Cout,
-                                  int taps, int Cin_pad, int ldg, int bias_col, int ci0, int Ci_t, int Co_pad, float lr, float rho,
-                                  float eps, void* stream) {
+                                  int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad, float lr,
+                                  float rho, float eps, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(w && acc && b && acc_b && g && wb, "rmsprop_pack: null tensor");
-  IISEG_CHECK(Cout > 0 && taps > 0 && Cin_pad > 0 && ldg >= taps * Cin_pad && bias_col < ldg, "rmsprop_pack: bad shape");
+  if (g_rstride == 0) g_rstride = 3 * Cin_pad;
+  IISEG_CHECK(Cout > 0 && taps > 0 && taps % 3 == 0 && Cin_pad > 0 && g_rstride >= 3 * Cin_pad && g_rstride % 4 == 0 &&
+              ldg >= (taps / 3) * g_rstride && bias_col < ldg, "rmsprop_pack: bad shape");
   IISEG_CHECK(wt == nullptr || (ci0 >= 0 && ci0 + Ci_t <= Cin_pad && Co_pad >= Cout), "rmsprop_pack: bad transposed-bank range");
   RmspropParams p;
   p.w = w; p.acc = acc; p.b = b; p.acc_b = acc_b; p.g = g; p.wb = reinterpret_cast<__nv_bfloat16*>(wb); p.wt = reinterpret_cast<__nv_bfloat16*>(wt);
-  p.Cout = Cout; p.taps = taps; p.Cin_pad = Cin_pad; p.ldg = ldg; p.bias_col = bias_col; p.ci0 = ci0; p.Ci_t = Ci_t; p.Co_pad = Co_pad;
+  p.Cout = Cout; p.taps = taps; p.Cin_pad = Cin_pad; p.ldg = ldg; p.bias_col = bias_col; p.ci0 = ci0; p.Ci_t = Ci_t; p.Co_pad = Co_pad; p.g_rstride = g_rstride;
   p.lr = lr; p.rho = rho; p.eps = eps; p.total = (long long)Cout * taps * Cin_pad;
-  rmsprop_pack_kernel<<<tgrid(p.total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  IISEG_CHECK(Cin_pad % 16 == 0 && Cout % 4 == 0 && ldg % 4 == 0 && (wt == nullptr || (ci0 % 16 == 0 && Ci_t % 16 == 0 && Co_pad % 4 == 0)),
+              "rmsprop_pack: channel counts must be padded (Cin %% 16, Cout %% 4, transposed range %% 16)");
+  IISEG_CHECK((Cout + 63) / 64 <= 65535, "rmsprop_pack: too many output channels");
+  dim3 grid(taps * (Cin_pad / 16), (Cout + 63) / 64);
+  rmsprop_pack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -448,7 +494,7 @@ extern "C" int iiseg_bias_grad(const void* g, long long P, int C, float* scratch
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   bias_grad_partial_kernel<<<chunks, 256, 0, s>>>(reinterpret_cast<const uint4*>(g), P, C / 8, scratch);
   IISEG_LAUNCH_CHECK();
-  bias_grad_final_kernel<<<(C + 255) / 256, 256, 0, s>>>(scratch, chunks, C, out, ld);
+  bias_grad_final_kernel<<<(C + 31) / 32, 256, 0, s>>>(scratch, chunks, C, out, ld);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

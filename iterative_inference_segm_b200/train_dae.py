@@ -53,8 +53,12 @@ class _Layer(object):
         self.b[:Cout] = b
         self.acc, self.acc_b = torch.zeros_like(self.w), torch.zeros_like(self.b)
         self.wb = self.w.reshape(cout_pad, -1).to(torch.bfloat16).contiguous()                 # forward bank
-        self.nb = _r64(9 * self.cin_pad + 1)                                                      # GEMM columns: filter + bias + pad
-        self.bias_col = 9 * self.cin_pad
+        # weight-gradient GEMM columns: filter row r at stride g_rstride, then (s, ci); bias column; pad to 64.
+        # A 16-channel input (the first layer) packs its three column shifts into ONE 64-row group per filter row
+        # (3 N tiles of 64 instead of 9 of 16: the g^T operand is streamed 3 times, not 9).
+        self.g_rstride = 64 if self.cin_pad == 16 else 3 * self.cin_pad
+        self.nb = _r64(3 * self.g_rstride + 1)
+        self.bias_col = 3 * self.g_rstride
         # data-gradient bank over the input channels [ci0, ci0 + ci_t): wt[ci][8 - tap][co]
         self.ci0, self.ci_t = dgrad_range if dgrad_range is not None else (0, 0)
         self.wt = None
@@ -182,26 +186,30 @@ class DAETrainer(object):
         B, GH, GW, Cg = g.shape
         # Both operands live on ONE zero-padded pixel grid of Gh x Gw per image (Gw a multiple of 8): g at the origin, x
         # shifted by `pad`, so that output pixel k meets tap (r, s) at column k + r*Gw + s of x^T.  TMA wants 16-byte
-        # aligned K coordinates, so x^T is written three times (one copy per horizontal shift s) and tap (r, s) is copy s
+        # aligned K coordinates, so x^T is written three times (one copy per horizontal shift s, a flat shift of the
+        # padded grid: where it wraps a row, g is zero) and tap (r, s) is copy s
         # read at K + r*Gw (iiseg_conv_desc.w_groups): 3 transposed copies instead of 9.
         Gh, Gw = GH + 2, (GW + 2 + 7) // 8 * 8
         Pn = B * Gh * Gw
         # split K (the pixel axis) so that the GEMM has a few hundred tiles: the high-resolution layers have tiny M x N
-        bn = min(lay.cin_pad, 256)
-        tiles = max(1, (Cg + 127) // 128) * (9 * lay.cin_pad // bn)
+        bn = 64 if lay.cin_pad == 16 else min(lay.cin_pad, 256)
+        tiles = max(1, (Cg + 127) // 128) * (3 * lay.g_rstride // bn)
         slabs = max(1, min(64, 296 // tiles, Pn // 4096))
         ldo = (Pn + 64 * slabs - 1) // (64 * slabs) * (64 * slabs)
         gT = torch.empty((Cg, ldo), dtype=torch.bfloat16, device=self.dev)
         K.transpose_shift(g, Cg, (0, 0), (Gh, Gw), (0, 0), gT, 0)
-        xT = torch.empty((3 * lay.cin_pad, ldo), dtype=torch.bfloat16, device=self.dev)
-        for s_ in range(3):
-            row = s_ * lay.cin_pad
-            for x, c in x_srcs:
-                K.transpose_shift(x, c, g_origin_in_x, (Gh, Gw), (-pad, s_ - pad), xT, row)
-                row += c
-            assert row == (s_ + 1) * lay.cin_pad
-        groups = [(s_ * lay.cin_pad, r * Gw) for r in range(3) for s_ in range(3)]
-        lay.grad = K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb)
+        merged = lay.g_rstride != 3 * lay.cin_pad
+        xT = (torch.zeros if merged else torch.empty)((lay.g_rstride, ldo), dtype=torch.bfloat16, device=self.dev)
+        row = 0
+        for x, c in x_srcs:        # one read of x, three writes: copy s is the same matrix one pixel further along the grid
+            K.transpose_shift(x, c, g_origin_in_x, (Gh, Gw), (-pad, -pad), xT, row, nshift=3, shift_rows=lay.cin_pad)
+            row += c
+        assert row == lay.cin_pad
+        if merged:
+            lay.grad = K.wgrad_gemm(gT, xT, lay.g_rstride, [(0, r * Gw) for r in range(3)], slabs, lay.nb)
+        else:
+            groups = [(s_ * lay.cin_pad, r * Gw) for r in range(3) for s_ in range(3)]
+            lay.grad = K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb)
         K.bias_grad(g, lay.grad, lay.bias_col)
         return lay.grad
 
@@ -275,7 +283,7 @@ class DAETrainer(object):
     def update(self):
         for lay in self.layers():
             K.rmsprop_pack(lay.w, lay.acc, lay.b, lay.acc_b, lay.grad, lay.wb, lay.wt, 9, lay.cin_pad, lay.bias_col,
-                           lay.ci0, lay.ci_t, self.lr, self.rho, self.eps)
+                           lay.ci0, lay.ci_t, self.lr, self.rho, self.eps, g_rstride=lay.g_rstride)
 
     def step(self, h_bf16, y, target, noise_main=None, noise_mask=None, world=None):
         self.forward(h_bf16, y, noise_main, noise_mask)
@@ -290,7 +298,8 @@ class DAETrainer(object):
         """Gradients in the reference's parameter layout (for tests): [(dW (Cout,Cin,3,3), db (Cout,)), ...]."""
         out = []
         for lay, splits in zip(self.layers(), self._splits):
-            g = lay.grad[:, :9 * lay.cin_pad].reshape(lay.cout_pad, 3, 3, lay.cin_pad)
+            g = lay.grad[:, :3 * lay.g_rstride].reshape(lay.cout_pad, 3, lay.g_rstride)[:, :, :3 * lay.cin_pad]
+            g = g.reshape(lay.cout_pad, 3, 3, lay.cin_pad)
             parts, c0 = [], 0
             for real, padded in splits:
                 parts.append(g[:lay.cout, :, :, c0:c0 + real])
