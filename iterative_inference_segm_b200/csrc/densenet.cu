@@ -37,22 +37,35 @@ __global__ void __launch_bounds__(256) bn_relu_pack_kernel(const float* __restri
       mu[k] = __ldg(mean + cb + k); sc[k] = __fmul_rn(__ldg(gamma + cb + k), __ldg(inv_std + cb + k)); be[k] = __ldg(beta + cb + k);
     }
   }
-  for (long long pix = tid / C8pad; pix < P; pix += pstep) {
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (live) {
-      const float4* src = reinterpret_cast<const float4*>(x + pix * Cs + c0 + cb);
-      const float4 a = __ldg(src), b = __ldg(src + 1);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      if (mean != nullptr) {
+  // four pixels per trip: eight independent 16-byte loads in flight per thread
+  for (long long pix0 = tid / C8pad; pix0 < P; pix0 += 4 * pstep) {
+    float4 a[4], b[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __fmaf_rn(__fsub_rn(v[k], mu[k]), sc[k], be[k]);
-      }
-      if (relu) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const long long pix = pix0 + u * pstep;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f); b[u] = a[u];
+      if (live && pix < P) {
+        const float4* src = reinterpret_cast<const float4*>(x + pix * Cs + c0 + cb);
+        a[u] = __ldg(src); b[u] = __ldg(src + 1);
       }
     }
-    stg_v4(out + pix * C8pad + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pix = pix0 + u * pstep;
+      if (pix >= P) break;
+      float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+      if (live) {
+        if (mean != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = __fmaf_rn(__fsub_rn(v[k], mu[k]), sc[k], be[k]);
+        }
+        if (relu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+      }
+      stg_v4(out + pix * C8pad + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    }
   }
 }
 
@@ -72,10 +85,20 @@ __global__ void __launch_bounds__(256) channel_stats_partial_kernel(const float*
   const long long p1 = p0 + kStatChunk < P ? p0 + kStatChunk : P;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    for (long long p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + p * Cs + c0 + c));
-      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-      q[0] = __fmaf_rn(v.x, v.x, q[0]); q[1] = __fmaf_rn(v.y, v.y, q[1]); q[2] = __fmaf_rn(v.z, v.z, q[2]); q[3] = __fmaf_rn(v.w, v.w, q[3]);
+    // four loads in flight per thread; the summation order (pixel order per thread) is unchanged
+    for (long long pb = p0 + threadIdx.y; pb < p1; pb += 4 * blockDim.y) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = pb + u * blockDim.y;
+        v[u] = p < p1 ? __ldg(reinterpret_cast<const float4*>(x + p * Cs + c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+        q[0] = __fmaf_rn(v[u].x, v[u].x, q[0]); q[1] = __fmaf_rn(v[u].y, v[u].y, q[1]);
+        q[2] = __fmaf_rn(v[u].z, v[u].z, q[2]); q[3] = __fmaf_rn(v[u].w, v[u].w, q[3]);
+      }
     }
   }
   __shared__ double sh[256][8];
@@ -98,12 +121,26 @@ __global__ void __launch_bounds__(256) channel_stats_partial_kernel(const float*
   }
 }
 
-__global__ void channel_stats_final_kernel(const double* __restrict__ partial, int n_chunks, int C, double inv_count, float eps,
-                                           float* __restrict__ mean, float* __restrict__ inv_std) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(512) channel_stats_final_kernel(const double* __restrict__ partial, int n_chunks, int C, double inv_count, float eps,
+                                                                  float* __restrict__ mean, float* __restrict__ inv_std) {
+  // 32 channels per block, 16 warps: warp w adds chunks w, w+16, ... (coalesced double2 rows), then the 16 partial
+  // sums are combined in warp order -- a fixed summation tree, so the statistics are run-to-run identical
+  __shared__ double sh[16][32][2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int k = 0; k < n_chunks; ++k) { s += partial[((size_t)k * C + c) * 2]; q += partial[((size_t)k * C + c) * 2 + 1]; }
+  if (c < C) {
+    for (int k = w; k < n_chunks; k += 16) {
+      const double2 v = *reinterpret_cast<const double2*>(partial + ((size_t)k * C + c) * 2);
+      s += v.x; q += v.y;
+    }
+  }
+  sh[w][lane][0] = s; sh[w][lane][1] = q;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  s = sh[0][lane][0]; q = sh[0][lane][1];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) { s += sh[i][lane][0]; q += sh[i][lane][1]; }
   const double m = s * inv_count;
   double var = q * inv_count - m * m;
   if (var < 0.0) var = 0.0;
@@ -196,7 +233,7 @@ extern "C" int iiseg_channel_stats(const float* x, int N, int H, int W, int Cs, 
   dim3 grid((C / 4 + bx - 1) / bx, n_chunks), block(bx, 256 / bx);
   channel_stats_partial_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, P, Cs, c0, C, scratch);
   IISEG_LAUNCH_CHECK();
-  channel_stats_final_kernel<<<(C + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scratch, n_chunks, C, 1.0 / (double)P, eps,
+  channel_stats_final_kernel<<<(C + 31) / 32, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scratch, n_chunks, C, 1.0 / (double)P, eps,
                                                                                                   mean, inv_std);
   IISEG_LAUNCH_CHECK();
   return 0;

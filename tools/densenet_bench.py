@@ -28,13 +28,17 @@ def step():
     return ii.run(out['pool4_bf16'], out['probs_dimshuffle'], 0.05, N, onehot=L)
 t_f = ev(lambda: net.forward(X, want=('pool4', 'probs_dimshuffle')))
 t_s = ev(step)
+out_ = net.forward(X, want=('pool4', 'probs_dimshuffle'), use_graph=False)
+t_l = ev(lambda: ii.run(out_['pool4_bf16'], out_['probs_dimshuffle'], 0.05, N, onehot=L))
+t_l0 = ev(lambda: ii.run(out_['pool4_bf16'], out_['probs_dimshuffle'], 0.05, N))
+print('loop alone %.2f ms with final metrics, %.2f ms without' % (t_l, t_l0))
 res = step(); torch.cuda.synchronize()
 print('densenet forward %.2f ms; full step %.2f ms -> %.1f images/s; n_exec %s; peak mem %.1f GB' % (
     t_f, t_s, B / t_s * 1e3, res['n_exec'].cpu().tolist(), torch.cuda.max_memory_allocated() / 2**30))
 timer = KernelTimer()
 import iterative_inference_segm_b200._kernels as K
 with timer.recording():
-    net.forward(X, want=('pool4', 'probs_dimshuffle'))
+    net.forward(X, want=('pool4', 'probs_dimshuffle'), use_graph=False)
 tot = {}
 for (name, tag), v in timer.summary().items():
     tot[name] = tot.get(name, 0.0) + sum(v)
