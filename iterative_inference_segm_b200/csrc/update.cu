@@ -63,32 +63,37 @@ __device__ __forceinline__ void softmax_c(const float* l, float* p, int C) {
                                                                       // conv epilogue (conv_epilogue16_update) must give the same bits
 }
 
-// grid = (nblk, N)
+// grid = (nblk, N); kMode 0: softmax only (y = p), 1: softmax + update + norm, 2: grad = y - p (de_fn)
+template <int kMode>
 __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     const float* __restrict__ logits, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
     float* __restrict__ p_out, const int32_t* __restrict__ active, float* __restrict__ norm_partial,
-    int C, int HW, int Cpad, float step, int do_update, int split) {
+    int C, int HW, int Cpad, float step, int split) {
   const int n = blockIdx.y;
-  if (do_update && active != nullptr && active[n] == 0) return;   // frozen image
+  if (kMode != 0 && active != nullptr && active[n] == 0) return;   // frozen image
   const int pix = blockIdx.x * kUpdBlock + threadIdx.x;
   float nrm = 0.f;
   if (pix < HW) {
-    float l[kMaxC], p[kMaxC];
-    load_logits16(logits + ((size_t)n * HW + pix) * 16, l);
-    softmax_c(l, p, C);
+    float l[kMaxC], p[kMaxC], yv[kMaxC];
     float* yb = y + (size_t)n * C * HW + pix;
+    load_logits16(logits + ((size_t)n * HW + pix) * 16, l);
+    if (kMode != 0) {            // the C plane reads of y go out together with the logits row: one memory latency, not two
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) yv[c] = c < C ? yb[(size_t)c * HW] : 0.f;
+    }
+    softmax_c(l, p, C);
     float out[kMaxC];
-    if (do_update == 2) {        // de_fn: grad = y - DAE(y, h), y untouched
+    if (kMode == 2) {        // de_fn: grad = y - DAE(y, h), y untouched
       float* gb = p_out + (size_t)n * C * HW + pix;
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) if (c < C) gb[(size_t)c * HW] = yb[(size_t)c * HW] - p[c];
+      for (int c = 0; c < kMaxC; ++c) if (c < C) gb[(size_t)c * HW] = yv[c] - p[c];
       return;
-    } else if (do_update) {
+    } else if (kMode != 0) {
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c) {
         if (c < C) {
-          const float yc = yb[(size_t)c * HW];
+          const float yc = yv[c];
           const float g = __fsub_rn(yc, p[c]);
           ss = __fmaf_rn(g, g, ss);
           out[c] = fminf(fmaxf(__fsub_rn(yc, __fmul_rn(step, g)), 0.f), 1.f);
@@ -110,8 +115,8 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     }
     if (y_bf16 != nullptr) store_row_bf16(y_bf16 + ((size_t)n * HW + pix) * (split ? 2 * Cpad : Cpad), out, C, Cpad, split);
   }
-  if (do_update == 2) return;
-  if (do_update) {
+  if (kMode == 2) return;
+  if (kMode != 0) {
     __shared__ float red[kUpdBlock / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
@@ -173,8 +178,8 @@ extern "C" int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, i
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax: bad shape");
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
-  softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, 0, split);
+  softmax_update_kernel<0><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -187,8 +192,8 @@ extern "C" int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_update: bad shape");
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax_update: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
-  softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, 1, split);
+  softmax_update_kernel<1><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -199,8 +204,8 @@ extern "C" int iiseg_softmax_grad(const float* logits, const float* y, float* gr
   IISEG_CHECK(logits && y && grad, "softmax_grad: null tensor");
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_grad: bad shape");
   dim3 grid(iiseg_update_blocks(H, W), N);
-  softmax_update_kernel<<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 2, 0);
+  softmax_update_kernel<2><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 0);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
