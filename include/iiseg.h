@@ -92,6 +92,13 @@ typedef struct iiseg_conv_desc {
   int w_groups, w_rows_total;
   int w_group_koff[IISEG_MAX_WGROUPS];
   int w_group_row[IISEG_MAX_WGROUPS];
+  /* Fused DePool2D loader (layers/mylayers.py:88-115; 3x3 convs with Cout in {16,64,128} on the halo-tile kernel):
+   * depool_mask != NULL makes the conv input the VIRTUAL map v [N,H,W,C] = DePool2D(u, mask), never written to
+   * memory.  src[0] is then the pooled tensor u, dense [N,depool_UH,depool_UW,C[0]], whose element (0,0) sits at
+   * pooled-grid position (depool_h0, depool_w0); depool_mask is the tie mask [N,H/2,W/2,C[0]/8] of
+   * iiseg_maxpool2_mask_fwd; pooled positions outside u read as zero. */
+  const uint32_t* depool_mask;
+  int depool_UH, depool_UW, depool_h0, depool_w0;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
   int Cout;           /* padded: 16, or a multiple of 64                    */

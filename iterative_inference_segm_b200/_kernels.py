@@ -76,7 +76,7 @@ def conv_out_size(H, W, R, S, pad):
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
-           out_slice=None, pool_zmask=None):
+           out_slice=None, pool_zmask=None, depool=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -90,12 +90,20 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     tail and the iterative-inference update fused in its epilogue (iiseg_conv_desc.upd_*); nothing is
     returned, y / y_bf16 / norm_acc are updated in place.
 
+    depool = (mask, H, W, u_origin): `src0` is the POOLED tensor u (a dense window whose element (0,0) sits at pooled
+    position u_origin) and the conv runs on the virtual map DePool2D(u, mask) of size HxW, expanded inside the
+    kernel's loader (iiseg_conv_desc.depool_mask) -- same result as unpool2(...) followed by conv2d(...).
+
     out_slice = (stack, c_off): fp32 output written as channels [c_off, c_off + Cout) of the wider fp32
     NHWC tensor `stack` [N,OH,OW,Cs] (the DenseNet stack: ConcatLayer without a copy)."""
     _chk(src0, BF16, 'src0')
     _chk(weight, BF16, 'weight')
     _chk(bias, F32, 'bias')
     N, H, W, C0 = src0.shape
+    if depool is not None:
+        dp_mask, H, W, dp_origin = depool
+        _chk(dp_mask, torch.int32, 'depool.mask')
+        assert src1 is None and not split and tuple(dp_mask.shape) == (N, H // 2, W // 2, C0 // 8), (tuple(dp_mask.shape), H, W, C0)
     C1 = 0
     if src1 is not None:
         _chk(src1, BF16, 'src1')
@@ -154,6 +162,9 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if depool is not None:
+        d.depool_mask = dp_mask.data_ptr()
+        d.depool_UH, d.depool_UW, d.depool_h0, d.depool_w0 = src0.shape[1], src0.shape[2], dp_origin[0], dp_origin[1]
     if out_slice is not None:
         d.out, d.out_cs = out_slice[0].data_ptr() + 4 * out_slice[1], out_slice[0].shape[3]
     if update is not None:

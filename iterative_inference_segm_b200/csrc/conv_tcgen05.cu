@@ -64,6 +64,7 @@ struct ConvCfg {
 struct alignas(64) ConvParams {
   CUtensorMap tm_src[IISEG_MAX_SRC];     // channel-concatenated activation sources (views of NHWC tensors)
   CUtensorMap tm_w;
+  CUtensorMap tm_mask;                   // fused DePool2D loader: the tie-mask words [N,H/2,W/2,C/8] (uint32)
   const float* bias;
   const __nv_bfloat16* addend;
   void* out;
@@ -80,6 +81,12 @@ struct alignas(64) ConvParams {
   int w_tpt;                // > 0: N tiles per weight row group (iiseg_conv_desc.w_groups): group g re-reads the same rows at K + w_group_koff[g]
   int w_group_koff[IISEG_MAX_WGROUPS];
   int w_group_row[IISEG_MAX_WGROUPS];
+  // fused DePool2D loader (halo kernel): src 0 is the POOLED tensor u; boxes of u and of the mask are staged by TMA
+  // and two warps expand them into the halo block the MMAs read (see conv_halo_kernel)
+  int depool;
+  int dp_phb, dp_pwb;       // staged box: pooled rows x pooled columns
+  int dp_u_h0, dp_u_w0;     // pooled-grid position of u's element (0,0)
+  uint32_t dp_stage_bytes, dp_mask_off, dp_stage_tx;
   int pair;                 // CTA-pair kernel (cta_group::2): work units are (N-tile, pair of M-tiles)
   int num_units, m_tiles;   // pair kernel: n_ntiles * ceil(m_tiles / 2) units; m_tiles = N * tiles_h * tiles_w
   int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
@@ -99,7 +106,8 @@ struct alignas(64) ConvParams {
   int out_cs;               // fp32 outputs: channels per pixel of the destination tensor (>= Cout: the conv writes a channel slice)
   int addend_f32;           // the skip-sum / hoisted-term operand is fp32 [N,AH,AW,Cout] (BN >= 64 epilogue only)
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
-  int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores
+  int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores,
+                            // bit8 = DePool2D loader without the expansion loop, bit9 = without its proxy fence (timing only)
 };
 
 // Debug timeline (IISEG_CONV_DBG bit 2): block 0 stamps clock64() at fixed points of its first 32 tiles.
@@ -161,6 +169,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1176,6 +1197,9 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
 // 8 x 14 outputs with pitch 16: the four pixels of a 2x2 window then sit in lanes {l, l^1, l^16, l^17}
 // of one epilogue warp and the pool + tie mask are warp shuffles on registers (no smem staging).
 // ---------------------------------------------------------------------------
+constexpr int kDpStages = 6;          // depool loader: staged (u, mask) boxes in flight (five tiles of look-ahead cover the DRAM latency)
+constexpr int kDpReserve = 72 * 1024; // shared memory set aside for that staging ring
+
 template <int BN, int KB>
 struct HaloCfg {
   static constexpr int kRowBytes = KB * 2;
@@ -1189,8 +1213,11 @@ struct HaloCfg {
                                       (static_cast<uint64_t>(KB == 64 ? 2 : 6) << 61);
 };
 
-template <int BN, int KB>
-__global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+constexpr int kDpBuilders = 8;        // ... expanded by warps 0, 2 and the six extra warps 20-25 of the depool instantiation
+constexpr int kDpExtraThreads = (kDpBuilders - 2) * 32;
+
+template <int BN, int KB, bool kDepool = false>
+__global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads : 0), 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = HaloCfg<BN, KB>;
   const int S = p.acc_stages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1207,6 +1234,9 @@ __global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __g
   auto tmem_empty_bar = [&](int i) { return bars + 8u * (2 * Cfg::kMaxA + 4 + i); };
   const uint32_t tmem_slot = bars + 8u * (2 * Cfg::kMaxA + 8);
   const uint32_t b_res_bar = bars + 8u * (2 * Cfg::kMaxA + 9);
+  auto st_full = [&](int i) { return bars + 8u * (2 * Cfg::kMaxA + 10 + i); };                 // depool staging ring
+  auto st_empty = [&](int i) { return bars + 8u * (2 * Cfg::kMaxA + 10 + kDpStages + i); };
+  const uint32_t st_ring = bars + 512u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5;
@@ -1214,11 +1244,13 @@ __global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < IISEG_MAX_SRC; ++i) if (p.n_cblk_src[i] > 0) prefetch_tmap(&p.tm_src[i]);
     prefetch_tmap(&p.tm_w);
+    if (kDepool) prefetch_tmap(&p.tm_mask);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
-    for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), kDepool ? kDpBuilders : 1); mbar_init(a_empty(i), 1); }     // depool: one arrival per builder warp
     for (int i = 0; i < S; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), (BN == 16 && p.upd_y == nullptr) ? kEpilogueThreads : kEpilogueThreads / 2); }
+    for (int i = 0; i < kDpStages; ++i) { mbar_init(st_full(i), 1); mbar_init(st_empty(i), kDpBuilders); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -1232,7 +1264,99 @@ __global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __g
 
   const int n_cblk = p.n_cblk;
 
-  if (warp == 0) {
+  if (kDepool && (warp == 0 || warp == 2 || warp >= 20)) {
+    // ===================== DePool2D loader (warps 0, 2, 20..25) =====================
+    // The conv input v = DePool2D(u) is never materialised (layers/mylayers.py:88-115):
+    //   v[h][w][c] = u[h>>1][w>>1][c] if bit (h&1)*2 + (w&1) of the tie mask of (h>>1, w>>1, c) is set, else 0.
+    // Warp 0's elected lane streams, kDpStages - 1 items ahead, the boxes of u (dp_phb x dp_pwb pooled pixels x 64
+    // channels) and of the mask words under the halo tile into a staging ring; the builder warps then expand them into
+    // the 128-byte-swizzled halo block the MMAs read (what TMA would have written from a materialised v): box row
+    // i, column j -> block row i*pitch + j, 16-byte chunk q at ((q ^ (row & 7)) << 4).  Positions outside the
+    // map get zero mask words from TMA's out-of-bounds fill, hence zeros: the conv's padding.
+    const int bw = warp == 0 ? 0 : (warp == 2 ? 1 : warp - 18);            // builder index: box rows i = bw (mod kDpBuilders)
+    if (warp == 0 && elect_one_sync()) {
+      const int n_blocks = 9 * n_cblk;
+      mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
+      for (int i = 0; i < n_blocks; ++i)
+        tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * KB, 0);
+    }
+    __syncwarp();
+    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_items = my_tiles * n_cblk;
+    const int n_half = p.n_a >> 1;
+    auto issue = [&](int item) {
+      const int it = item / n_cblk, cb = item - it * n_cblk;
+      const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+      const int ph0 = (tc.th * p.TH + p.in_off_h) >> 1, pw0 = (tc.tw * p.TW + p.in_off_w) >> 1;     // arithmetic shifts: -1 -> -1
+      const int st = item % kDpStages;
+      mbar_wait(st_empty(st), (static_cast<uint32_t>(item / kDpStages) & 1u) ^ 1u, p.diag, 11, st);
+      mbar_arrive_expect_tx(st_full(st), p.dp_stage_tx);
+      const uint32_t dst = st_ring + static_cast<uint32_t>(st) * p.dp_stage_bytes;
+      tma_load_4d(dst, &p.tm_src[0], st_full(st), cb * KB, pw0 - p.dp_u_w0, ph0 - p.dp_u_h0, tc.n);
+      tma_load_4d(dst + p.dp_mask_off, &p.tm_mask, st_full(st), cb * (KB / 8), pw0, ph0, tc.n);
+    };
+    if (warp == 0) {
+      if (elect_one_sync())
+        for (int item = 0; item < kDpStages - 1 && item < n_items; ++item) issue(item);
+      __syncwarp();
+    }
+    for (int item = 0; item < n_items; ++item) {
+      if (warp == 0) {
+        if (elect_one_sync() && item + kDpStages - 1 < n_items) issue(item + kDpStages - 1);
+        __syncwarp();
+      }
+      const int it = item / n_cblk, cb = item - it * n_cblk;
+      const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+      const int h_base = tc.th * p.TH + p.in_off_h, w_base = tc.tw * p.TW + p.in_off_w;
+      const int ph0 = h_base >> 1, pw0 = w_base >> 1;
+      const int lstep = (it >> 1) * n_cblk + cb;
+      const int slot = (it & 1) * n_half + lstep % n_half;
+      const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
+      const int st = item % kDpStages;
+      mbar_wait(st_full(st), static_cast<uint32_t>(item / kDpStages) & 1u, p.diag, 12, st);
+      mbar_wait(a_empty(slot), phase ^ 1u, p.diag, 5, slot);
+      const uint32_t u_st = st_ring + static_cast<uint32_t>(st) * p.dp_stage_bytes, m_st = u_st + p.dp_mask_off;
+      const uint32_t a_blk = a_ring + static_cast<uint32_t>(slot) * p.a_blk_bytes;
+      const int q = lane & 7, jq = lane >> 3;
+      for (int i = bw; i < p.TH + 2 && !(p.dbg & 256); i += kDpBuilders) {      // tuning bit 8: no expansion
+        const int ih = h_base + i;
+        const int dy2 = (ih & 1) << 1;
+        const int prow = ((ih >> 1) - ph0) * p.dp_pwb - pw0;
+        const uint32_t urow = u_st + static_cast<uint32_t>(q) * 16u, mrow = m_st + static_cast<uint32_t>(q) * 4u;
+        const int rowbase = i * p.pitch;
+        // four pixels per trip, all eight shared-memory loads issued before the first store (the stores' memory
+        // clobber would otherwise serialise load -> mask -> store chains: measured 1800 extra cycles per tile)
+        for (int j0 = jq; j0 < p.pitch; j0 += 16) {
+          uint4 val[4]; uint32_t b[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = j0 + 4 * t;
+            if (j < p.pitch) {
+              const int iw = w_base + j;
+              const uint32_t cell = static_cast<uint32_t>(prow + (iw >> 1));
+              val[t] = lds_v4(urow + cell * 128u);
+              b[t] = lds_u32(mrow + cell * 32u) >> (dy2 | (iw & 1));
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = j0 + 4 * t;
+            if (j < p.pitch) {
+              // nibble k bit 0 -> low half of word k, nibble 4+k bit 0 -> high half (tie_bits): 0x0001 / 0x00010000 -> 16 ones
+              const uint32_t m0 = (b[t] & 0x00010001u) * 0xFFFFu, m1 = ((b[t] >> 4) & 0x00010001u) * 0xFFFFu;
+              const uint32_t m2 = ((b[t] >> 8) & 0x00010001u) * 0xFFFFu, m3 = ((b[t] >> 12) & 0x00010001u) * 0xFFFFu;
+              const int row = rowbase + j;
+              sts_v4(a_blk + static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((q ^ (row & 7)) << 4),
+                     make_uint4(val[t].x & m0, val[t].y & m1, val[t].z & m2, val[t].w & m3));
+            }
+          }
+        }
+      }
+      if (!(p.dbg & 512)) fence_proxy_async_smem();             // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(a_full(slot)); mbar_arrive(st_empty(st)); }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
       // the filter bank: loaded once, stays resident (Cout == BN, all 9 * n_cblk blocks fit)
@@ -1311,7 +1435,7 @@ __global__ void __launch_bounds__(kNumThreadsHalo, 1) conv_halo_kernel(const __g
         if (lane == 0 && cb == n_cblk - 1) IISEG_STAMP(iter, 3);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 20) {
     if constexpr (BN == 16) {
       if (p.upd_y != nullptr) conv_epilogue16_update<4>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else if (warp < 12) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);      // 8 warps suffice
@@ -1364,6 +1488,21 @@ static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, i
   return 0;
 }
 
+// Un-swizzled 4-D box (dense in shared memory): the staged u / mask boxes of the fused DePool2D loader.
+static int encode_dense4d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base, int d0, int d1, int d2, int d3,
+                          int b0, int b1, int b2) {
+  EncodeTiledFn fn = get_encode_fn();
+  IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)d3};
+  cuuint64_t strides[3] = {(cuuint64_t)d0 * elem_bytes, (cuuint64_t)d1 * d0 * elem_bytes, (cuuint64_t)d2 * d1 * d0 * elem_bytes};
+  cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dense %dx%dx%dx%d box %dx%dx%d) failed: %d", d0, d1, d2, d3, b0, b1, b2, (int)r);
+  return 0;
+}
+
 // [Cout][K] bf16 weights seen as (K, Cout); box (64, BN).
 static int encode_weight(CUtensorMap* tm, const void* base, int Cout, long long K, int BN, int KB = 64, long long ld = 0) {
   EncodeTiledFn fn = get_encode_fn();
@@ -1396,7 +1535,7 @@ static void choose_box(int OH, int OW, int* TH, int* TW, bool even) {
 
 // Halo-tile box: TH x TW outputs with TH * (TW+S-1) <= 128 + S-1 accumulator rows and a
 // (TH+R-1) x (TW+S-1) TMA box of at most `max_rows` rows; fewest tiles first, then the smallest halo tile.
-static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_rows, int* TH, int* TW) {
+static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_rows, int* TH, int* TW, int max_dp_cells = 0) {
   long best = -1; long best_rows = 0; int bh = 0, bw = 0;
   const int step = even ? 2 : 1;
   for (int th = step; th <= 128 && th < OH + step; th += step) {
@@ -1410,6 +1549,7 @@ static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_row
       const long rows = (long)(th + R - 1) * pitch;
       const long rows_read = (long)(R - 1) * pitch + S - 1 + 128;      // last row the shifted descriptors touch
       if (pitch > 256 || th + R - 1 > 256 || rows > max_rows || rows_read > max_rows) continue;
+      if (max_dp_cells > 0 && ((th + 3) / 2 + 1) * ((pitch + 1) / 2 + 1) > max_dp_cells) continue;     // staged pooled box of the DePool2D loader
       const long tiles = (long)ceil_div(OW, w) * ceil_div(OH, th);
       if (best < 0 || tiles < best || (tiles == best && rows < best_rows)) { best = tiles; best_rows = rows; bh = th; bw = w; }
     }
@@ -1428,6 +1568,19 @@ static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t st
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   conv_halo_kernel<BN, KB><<<grid, kNumThreadsHalo, smem_bytes, stream>>>(p);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int launch_conv_halo_depool(const ConvParams& p, int smem_bytes, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_halo_kernel<BN, 64, true><<<grid, kNumThreadsHalo + kDpExtraThreads, smem_bytes, stream>>>(p);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -1488,6 +1641,12 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
               "conv: split-K views (w_koff / weight_ld / src_image_stride) are for 1x1 GEMM launches");
   IISEG_CHECK(d->out_cs == 0 || (d->out_f32 && d->out_cs >= d->Cout && d->out_cs % 4 == 0), "conv: out_cs is for fp32 outputs (channel slice of a wider tensor)");
   IISEG_CHECK(d->R >= 1 && d->S >= 1 && d->pad >= 0, "conv: bad filter");
+  const bool depool = d->depool_mask != nullptr;
+  if (depool)
+    IISEG_CHECK(d->R == 3 && d->S == 3 && d->src[1] == nullptr && d->C[0] % 64 == 0 && (d->Cs[0] == 0 || d->Cs[0] == d->C[0]) && d->split == 0 &&
+                d->H >= 2 && d->W >= 2 && d->depool_UH >= 1 && d->depool_UW >= 1 && d->depool_h0 >= 0 && d->depool_w0 >= 0 &&
+                d->depool_h0 + d->depool_UH <= d->H / 2 && d->depool_w0 + d->depool_UW <= d->W / 2 && (d->Cout == 16 || d->Cout == 64 || d->Cout == 128),
+                "conv: the fused DePool2D loader needs a 3x3 conv of one dense 64k-channel pooled source, Cout in {16,64,128}, u window inside the pooled map");
   const int fullOH = d->H + 2 * d->pad - d->R + 1, fullOW = d->W + 2 * d->pad - d->S + 1;
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
@@ -1519,16 +1678,28 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     // shared-memory plan: the resident filter bank + a ring of n_a halo blocks holding at least two tiles
     const int row_b = KB * 2;
     const int b_all = 9 * n_cblk_all * BN * row_b;
-    const int total = 227 * 1024 - 256;
+    const int total = 227 * 1024 - 512 - (depool ? kDpReserve : 0);      // depool: room for the staging ring (checked below)
     const int budget_rows = (total - b_all) / (2 * n_cblk_all) / 1024 * 1024 / row_b;     // rows one block may take
     if (fuse_pool) {
       // pool + tie mask by warp shuffle: 8 x 14 outputs on a pitch-16 box (see conv_epilogue, kShflPool)
       p.TH = 8; p.TW = 14; p.pitch = 16;
       halo = budget_rows >= 2 * 16 + 2 + kBlockM;
     } else {
-      halo = budget_rows > 0 && choose_halo_box(covH, covW, 3, 3, false, budget_rows < 512 ? budget_rows : 512, &p.TH, &p.TW);
+      halo = budget_rows > 0 && choose_halo_box(covH, covW, 3, 3, false, budget_rows < 512 ? budget_rows : 512, &p.TH, &p.TW,
+                                                depool ? kDpReserve / (kDpStages * 160) - 2 : 0);
       if (halo && env_halo != 2 && p.TH * p.TW < 100) halo = false;        // too many junk accumulator rows
       p.pitch = p.TW + 2;
+    }
+    int dp_total = 0;
+    if (halo && depool) {
+      p.depool = 1;
+      p.dp_phb = (p.TH + 3) / 2 + 1; p.dp_pwb = (p.pitch + 1) / 2 + 1;
+      const int cells = p.dp_phb * p.dp_pwb;
+      const int u_bytes = (cells * 128 + 127) / 128 * 128, m_bytes = (cells * 32 + 127) / 128 * 128;
+      p.dp_mask_off = u_bytes; p.dp_stage_bytes = u_bytes + m_bytes; p.dp_stage_tx = cells * 160;
+      p.dp_u_h0 = d->depool_h0; p.dp_u_w0 = d->depool_w0;
+      dp_total = kDpStages * (int)p.dp_stage_bytes;
+      IISEG_CHECK(dp_total <= kDpReserve && p.dp_phb <= 256 && p.dp_pwb <= 256, "conv: DePool2D staging ring too large (%d bytes)", dp_total);
     }
     if (halo) {
       const int rows_box = (p.TH + 2) * p.pitch;
@@ -1540,17 +1711,21 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       p.n_a &= ~1;                               // two sub-rings, one per MMA-issuer warp
       if (p.n_a < 2) halo = false;
       box_h = p.TH + 2; box_w = p.pitch;
-      smem_halo = p.n_a * p.a_blk_bytes + b_all + 256;
+      smem_halo = p.n_a * p.a_blk_bytes + b_all + 512 + dp_total;
     }
   }
   IISEG_CHECK(halo || KB == 64, "conv: a 16-channel source needs a 3x3 filter with Cout in {16,64,128} (halo-tile kernel)");
+  IISEG_CHECK(halo || !depool, "conv: no halo-tile plan for this DePool2D-fused conv (window %dx%d, %d channels)", d->OH, d->OW, d->C[0]);
   if (!halo) {
     choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
     p.pitch = p.TW;
     box_h = p.TH; box_w = p.TW;
   }
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
-    if (d->src[i] != nullptr) {
+    if (d->src[i] != nullptr && depool) {
+      if (encode_dense4d(&p.tm_src[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->src[0], d->C[0], d->depool_UW, d->depool_UH, d->N, 64, p.dp_pwb, p.dp_phb)) return -1;
+      if (encode_dense4d(&p.tm_mask, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d->depool_mask, d->C[0] / 8, d->W / 2, d->H / 2, d->N, 8, p.dp_pwb, p.dp_phb)) return -1;
+    } else if (d->src[i] != nullptr) {
       if (encode_nhwc(&p.tm_src[i], d->src[i], d->N, d->H, d->W, d->C[i], box_h, box_w, d->Cs[i], KB, d->src_image_stride)) return -1;
     } else {
       p.tm_src[i] = p.tm_src[0];
@@ -1638,6 +1813,13 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
         case 16: return launch_conv_halo<16, 16>(p, smem_halo, s);
         case 64: return launch_conv_halo<64, 16>(p, smem_halo, s);
         default: return launch_conv_halo<128, 16>(p, smem_halo, s);
+      }
+    }
+    if (p.depool) {
+      switch (BN) {
+        case 16: return launch_conv_halo_depool<16>(p, smem_halo, s);
+        case 64: return launch_conv_halo_depool<64>(p, smem_halo, s);
+        default: return launch_conv_halo_depool<128>(p, smem_halo, s);
       }
     }
     switch (BN) {

@@ -13,6 +13,8 @@ unpool_type='trackind', conv_before_pool=1, skip=True, bn=0, dropout=0):
                    centre-crop window and emits fp32 logits
   tail           : channel softmax (+ the y update) in one streaming kernel
 """
+import os
+
 import torch
 
 from .. import _kernels as K
@@ -36,6 +38,9 @@ class DAENet(object):
         assert precision in ('bf16', 'fp32x3'), precision
         self.precision = precision
         self.split = precision == 'fp32x3'
+        # IISEG_FUSE_DEPOOL=1: last DePool2D expanded inside the loader of up_conv1 (bf16 variant; bit-identical results).
+        # Off by default: measured 0.179 ms against 0.050 (unpool) + 0.112 (conv) -- see DESIGN.md 3.7
+        self.fuse_depool = os.environ.get('IISEG_FUSE_DEPOOL', '0') == '1'
         self.cm = 2 if self.split else 1          # bf16 channels per logical channel in activation tensors
         assert n_classes <= 16
         self.n_classes = n_classes
@@ -231,9 +236,19 @@ class DAENet(object):
             h, w = sizes[p - 1]
             ul, uh, vl, vh = Wu[p]
             hl, hh, wl, wh = Wc[p]
+            Wk, bk = self.up[i]
+            if p == 1 and self.fuse_depool and not sp:
+                # DePool2D expanded inside the conv's loader: the 64-channel full-resolution map (221 MB per batch of
+                # 10) is neither written nor read; the conv runs on the virtual map in full-map coordinates
+                dp = dict(window=(hl, wl, hh - hl, wh - wl), depool=(ws['mask'][0], h, w, u_origin))
+                if update is not None:
+                    K.conv2d(u, Wk, bk, 3, 3, 1, relu=False, out_f32=True,
+                             update=dict(update, y_bf16=y_bf16, C=self.n_classes), **dp)
+                    return None
+                K.conv2d(u, Wk, bk, 3, 3, 1, relu=False, out=ws['logits'], out_f32=True, **dp)
+                break
             up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
                            window=(ul, vl, uh - ul, vh - vl), split=sp)
-            Wk, bk = self.up[i]
             win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
             if p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
                 u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],

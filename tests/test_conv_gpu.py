@@ -254,3 +254,42 @@ def test_conv_hoisted_concat_half(cuda, split):
     for got in (hoisted, concat):
         g = (_recon(got) if split else got.float().permute(0, 3, 1, 2)).double()
         assert float(((g - ref).abs() / ref.abs().clamp(min=1.0)).max()) < tol
+
+
+# N, H, W (pre-pool map), C, Cout, u window (ph0, pw0, UH, UW), conv window (oh0, ow0, OH, OW), addend, relu
+DEPOOL_CASES = [
+    (2, 40, 56, 64, 16, (0, 0, 20, 28), (0, 0, 40, 56), 0, 0),          # whole map
+    (2, 41, 57, 64, 16, (0, 0, 20, 28), (0, 0, 41, 57), 0, 0),          # odd map: the last row / column has no pool window
+    (2, 90, 122, 64, 64, (3, 5, 40, 52), (9, 13, 70, 96), 1, 0),        # cone window, skip-sum
+    (1, 64, 80, 64, 64, (2, 2, 28, 36), (5, 7, 50, 60), 0, 1),          # odd window origin
+    (3, 120, 160, 64, 16, (10, 12, 45, 60), (21, 25, 86, 116), 0, 0),   # many tiles per CTA ring
+]
+
+
+@pytest.mark.parametrize('case', DEPOOL_CASES, ids=[str(c) for c in DEPOOL_CASES])
+def test_conv_with_fused_depool_equals_unpool_then_conv(cuda, case):
+    """The DePool2D loader (iiseg_conv_desc.depool_mask) against the materialised path: same operands, same
+    accumulation order -> bit-identical outputs."""
+    from iterative_inference_segm_b200 import _kernels as K
+    N, H, W, C, Cout, (ph0, pw0, UH, UW), (oh0, ow0, OH, OW), addend, relu = case
+    torch.manual_seed(1)
+    x = torch.randn(N, H, W, C, device=cuda).to(torch.bfloat16)
+    x[:, 0:H - 1:2, :, :8] = x[:, 1:H:2, :, :8]                          # ties inside pool windows -> multi-bit masks
+    _, mask = K.maxpool2(x, True)
+    u_full = torch.randn(N, H // 2, W // 2, C, device=cuda).to(torch.bfloat16)
+    u = u_full[:, ph0:ph0 + UH, pw0:pw0 + UW].contiguous()
+    Wt = (torch.randn(Cout, 9 * C, device=cuda) / (9 * C) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=cuda)
+    add = torch.randn(N, OH, OW, Cout, device=cuda).to(torch.bfloat16) if addend else None
+    # materialised reference: unpool the window the conv needs (one pixel of halo), then the plain conv
+    vh0, vw0 = max(oh0 - 1, 0), max(ow0 - 1, 0)
+    vh1, vw1 = min(oh0 + OH + 1, H), min(ow0 + OW + 1, W)
+    full = K.unpool2(u, mask, H, W, u_origin=(ph0, pw0), window=(2 * ph0, 2 * pw0, min(2 * UH, H - 2 * ph0), min(2 * UW, W - 2 * pw0)))
+    v = torch.zeros(N, H, W, C, dtype=torch.bfloat16, device=cuda)
+    v[:, 2 * ph0:2 * ph0 + full.shape[1], 2 * pw0:2 * pw0 + full.shape[2]] = full
+    ref = K.conv2d(v, Wt, b, 3, 3, 1, relu=bool(relu), window=(oh0, ow0, OH, OW), addend=add, out_f32=(Cout == 16))
+    got = K.conv2d(u, Wt, b, 3, 3, 1, relu=bool(relu), window=(oh0, ow0, OH, OW), addend=add, out_f32=(Cout == 16),
+                   depool=(mask, H, W, (ph0, pw0)))
+    torch.cuda.synchronize()
+    assert vh0 >= 2 * ph0 and vw0 >= 2 * pw0 and vh1 <= min(2 * (ph0 + UH), H) + (H % 2) and vw1 <= min(2 * (pw0 + UW), W) + (W % 2)
+    assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
