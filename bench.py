@@ -174,10 +174,10 @@ def run_b200(args):
 
     pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN)
     pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=OUT_GAIN)
-    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf, precision=args.precision)
     dae = buildDAE([None], None, NCLS, nb_features_to_concat=fcn[0].output_shape[1], padding=100, concat_h=['pool4'],
                    noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
-                   params=pd)
+                   params=pd, precision=args.precision)
     del pf, pd
     ii = IterativeInference(dae, NCLS, [NCLS])
     fnet = fcn[0].net
@@ -283,7 +283,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: every conv launch of one DAE application, event-timed eagerly
     roof, breakdown = None, None
     cpu_base = None
-    if rank == 0:
+    if rank == 0 and args.precision == 'bf16':
         st = ii._buffers(BATCH, H, W, N_ITER, False)
         timer = KernelTimer()
         reps = 3
@@ -341,7 +341,7 @@ def run_b200(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'fp32 operands as bf16 hi/lo pairs, 3 tensor-core products, fp32 accumulate', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'per_gpu_batch': BATCH, 'global_batch': BATCH * world,
                        'parallelism': 'image shards, dp%d' % world,
                        'weights': 'random init (He-uniform FCN8 x logit gain 10, Glorot DAE x out gain 0.1)',
@@ -367,6 +367,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true', help='development runs: skip the CPU oracle timing')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32x3'],
+                    help="fp32x3: the parity-grade variant (fp32 operands as bf16 hi/lo pairs, three tensor-core products); no roofline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
