@@ -162,3 +162,27 @@ def test_two_rank_train_step_allreduce_gloo(tmp_path):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count('ok') == 2
+
+
+def test_error_behaviour_matches_reference():
+    """The reference raises ValueError for an unknown segmentation net / DAE kind and for a missing save directory
+    (iterative_inference.py:51,147,179); the drop-in raises the same exceptions before touching the device."""
+    import pytest
+    from iterative_inference_segm_b200.iterative_inference import build_networks, inference, DAE_DICT_DEFAULTS
+    with pytest.raises(ValueError):
+        build_networks('resnet', dict(DAE_DICT_DEFAULTS), 11, 3, [11])
+    with pytest.raises(ValueError):
+        inference('camvid', 'fcn8', 0.05, 3, savepath=None)
+    from iterative_inference_segm_b200.data_loader import load_data
+    with pytest.raises(NotImplementedError):
+        load_data('camvid', {}, one_hot=False)
+
+
+def test_product_path_has_no_cpu_fallback():
+    """Kernel wrappers refuse CPU tensors: there is no silent host path behind the C ABI."""
+    import pytest
+    import torch
+    from iterative_inference_segm_b200 import _kernels as K
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16)
+    with pytest.raises((AssertionError, RuntimeError, ValueError, TypeError)):
+        K.maxpool2(x, True)

@@ -336,3 +336,25 @@ def test_full_size_properties_360x480(cuda, built):
     alone = IterativeInference(dae, NCLS, [NCLS]).run(h[1:2].contiguous(), y0[1:2].contiguous(), 0.05, 5,
                                                       labels=labels[1:2].contiguous())
     assert torch.equal(alone['y'][0], y_a[1]) and torch.equal(alone['cm'][0], cm_a[1])        # images do not interact
+
+
+def test_batch_composition_does_not_change_results(cuda, built):
+    """Images are independent (no cross-image coupling, fixed accumulation order per output): three images run as
+    one batch of 3 or as batches of 2 + 1 give bit-identical y and identical int64 confusion matrices -- the property
+    image sharding across GPUs relies on."""
+    from iterative_inference_segm_b200.functions import IterativeInference
+    _, _, fcn, dae = built
+    X, L, _ = weights.synthetic_batch(3, 32, 40, NCLS, seed=9)
+    X, L = X.to(cuda), L.to(cuda)
+    ii = IterativeInference(dae, NCLS, [NCLS])
+    net = fcn[0].net
+
+    def run(sl):
+        out = net.forward(X[sl].contiguous(), want=('pool4', 'probs_dimshuffle'))
+        r = ii.run(out['pool4'], out['probs_dimshuffle'], 0.05, 4, onehot=L[sl].contiguous())
+        return r['y'].clone(), r['cm'].clone()
+    y_all, cm_all = run(slice(0, 3))
+    y_a, cm_a = run(slice(0, 2))
+    y_b, cm_b = run(slice(2, 3))
+    assert torch.equal(y_all[:2], y_a) and torch.equal(y_all[2:], y_b)
+    assert torch.equal(cm_all.sum(0), cm_a.sum(0) + cm_b.sum(0))

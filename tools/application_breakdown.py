@@ -7,15 +7,16 @@ from iterative_inference_segm_b200.profiling import KernelTimer
 
 pad = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 nbh = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+prec = sys.argv[3] if len(sys.argv) > 3 else 'bf16'
 B, H, W = 10, 360, 480
 dae = buildDAE([None], None, 11, nb_features_to_concat=nbh, padding=pad, concat_h=['pool4'], noise=0.0, n_filters=64,
-               additional_pool=2, skip=True, unpool_type='trackind', params=weights.synthetic_dae_params(11, nbh, seed=1, out_gain=0.1))
+               additional_pool=2, skip=True, unpool_type='trackind', params=weights.synthetic_dae_params(11, nbh, seed=1, out_gain=0.1), precision=prec)
 net = dae.net
 hs = net.h_spatial(H, W)
-h = torch.zeros(B, hs[0], hs[1], net.cm * net.h_pad, device="cuda", dtype=torch.bfloat16); h[..., :nbh] = torch.relu(torch.randn(B, hs[0], hs[1], nbh, device="cuda")).to(torch.bfloat16)
+h = K.pack_nchw(torch.relu(torch.randn(B, nbh, hs[0], hs[1], device='cuda')), net.h_pad, split=net.split)
 yf = torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1)
-y = K.pack_nchw(yf, net.y_cpad)
-upd = dict(y=yf, active=torch.ones(B, dtype=torch.int32, device='cuda'), norm_acc=torch.zeros(B, dtype=torch.int64, device='cuda'), step=0.05)
+y = K.pack_nchw(yf, net.y_cpad, split=net.split)
+upd = dict(y=yf, active=torch.ones(B, dtype=torch.int32, device='cuda'), norm_acc=torch.zeros(B, dtype=torch.int64, device='cuda'), step=0.05) if not net.split else None
 net.logits(h, y, full_down=True, update=upd)
 for _ in range(2):
     net.logits(h, y, full_down=False, update=upd)
