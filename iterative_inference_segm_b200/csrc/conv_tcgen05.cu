@@ -1074,8 +1074,10 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
     const __nv_bfloat16* arow = p.addend + ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.Cout;
     uint4 add[2];
     if (has_add) { add[0] = ldg_nc_v4(arow); add[1] = ldg_nc_v4(arow + 8); }      // before the accumulator is ready
+    if (q == 0 && lane == 0) IISEG_STAMP(iter, 4);
     mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
     tcgen05_fence_after();
+    if (q == 0 && lane == 0) IISEG_STAMP(iter, 5);
 #pragma unroll 1
     for (int chunk = 0; chunk < BN / 16; ++chunk) {
       const int cbase = chunk * 16;
@@ -1170,6 +1172,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         }
       }
     }
+    if (q == 0 && lane == 0) IISEG_STAMP(iter, 6);
   }
 }
 
@@ -1208,9 +1211,9 @@ struct HaloCfg {
   static constexpr int kCols = kAccStages * BN;
   static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
   static constexpr int kMaxA = 8;
-  // K-major swizzled smem descriptor template: SBO = 8 rows, version 1, SWIZZLE_128B (2) or SWIZZLE_32B (6)
+  // K-major swizzled smem descriptor template: SBO = 8 rows, version 1, SWIZZLE_128B (2), SWIZZLE_64B (4) or SWIZZLE_32B (6)
   static constexpr uint64_t kDescHi = (static_cast<uint64_t>((8 * kRowBytes) >> 4) << 32) | (1ull << 46) |
-                                      (static_cast<uint64_t>(KB == 64 ? 2 : 6) << 61);
+                                      (static_cast<uint64_t>(KB == 64 ? 2 : (KB == 32 ? 4 : 6)) << 61);
 };
 
 constexpr int kDpBuilders = 8;        // ... expanded by warps 0, 2 and the six extra warps 20-25 of the depool instantiation
@@ -1482,7 +1485,7 @@ static int encode_nhwc(CUtensorMap* tm, const void* base, int N, int H, int W, i
   cuuint32_t box[4] = {(cuuint32_t)KB, (cuuint32_t)TW, (cuuint32_t)TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc N=%d H=%d W=%d C=%d box %dx%d) failed: %d", N, H, W, C, TH, TW, (int)r);
   return 0;
@@ -1512,7 +1515,7 @@ static int encode_weight(CUtensorMap* tm, const void* base, int Cout, long long 
   cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight Cout=%d K=%lld BN=%d) failed: %d", Cout, K, BN, (int)r);
   return 0;
@@ -1618,7 +1621,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
                 "conv: the fused softmax-update needs a 16-channel logits conv (no addend / pool / split), y_bf16 and norm_acc");
   IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
   // K blocks of 64 channels (128-byte rows), or -- one 16-channel source, 3x3 filter, halo-tile kernel only -- of 16
-  const int KB = (d->C[0] == 16 && d->src[1] == nullptr) ? 16 : 64;
+  int KB = (d->C[0] == 16 && d->src[1] == nullptr) ? 16 : 64;
   IISEG_CHECK(d->C[0] > 0 && d->C[0] % KB == 0, "conv: C0=%d must be 16 or a positive multiple of 64", d->C[0]);
   int Cin = 0;
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
@@ -1670,8 +1673,17 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
   // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
   // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
-  const int n_cblk_all = Cin / KB;
   bool halo = env_halo && d->R == 3 && d->S == 3 && !d->split && d->Cout == BN && BN <= 128;
+  {
+    // IISEG_HALO_KB32=1 (experiment, off): 32-channel K blocks (64-byte rows, SWIZZLE_64B) for the layers whose resident
+    // 144 KB filter bank (64 -> 128, 128 -> 64 channels) leaves room for only two 128-byte-row halo blocks; the ring
+    // gets six half-size blocks.  Parity-green, but not faster (conv2_1 0.064 vs 0.062 ms, up_conv2 0.107 vs 0.106):
+    // the per-tile timeline shows these layers bound by the issue rate of small-N MMAs (72 x M128 N64 K16 at ~66
+    // cycles with both issuer warps active), not by reload latency.
+    static const int env_kb32 = getenv("IISEG_HALO_KB32") ? atoi(getenv("IISEG_HALO_KB32")) : 0;
+    if (halo && env_kb32 && KB == 64 && !depool && 9 * Cin * BN * 2 >= 128 * 1024) KB = 32;
+  }
+  int n_cblk_all = Cin / KB;
   int box_h = 0, box_w = 0;       // TMA box extent in pixels
   int smem_halo = 0;
   if (halo) {
@@ -1714,6 +1726,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       smem_halo = p.n_a * p.a_blk_bytes + b_all + 512 + dp_total;
     }
   }
+  if (!halo && KB == 32) { KB = 64; n_cblk_all = Cin / KB; }      // no halo plan: the per-tap kernels use 64-channel blocks
   IISEG_CHECK(halo || KB == 64, "conv: a 16-channel source needs a 3x3 filter with Cout in {16,64,128} (halo-tile kernel)");
   IISEG_CHECK(halo || !depool, "conv: no halo-tile plan for this DePool2D-fused conv (window %dx%d, %d channels)", d->OH, d->OW, d->C[0]);
   if (!halo) {
@@ -1808,6 +1821,12 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     }
   }
   if (halo) {
+    if (KB == 32) {
+      switch (BN) {
+        case 64: return launch_conv_halo<64, 32>(p, smem_halo, s);
+        default: return launch_conv_halo<128, 32>(p, smem_halo, s);
+      }
+    }
     if (KB == 16) {
       switch (BN) {
         case 16: return launch_conv_halo<16, 16>(p, smem_halo, s);

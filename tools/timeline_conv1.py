@@ -13,7 +13,7 @@ def run(name, fn):
     base = t[2][0]
     print(name)
     print(' tile | mma: wait_tmem_empty  got_it  a_full  issued | epi(group 0): wait_full got_full end')
-    for i in range(2, 18):
+    for i in range(2, 26):
         print(' %3d  | %s' % (i, ' '.join('%7d' % (t[i][s] - base) if t[i][s] else '      -' for s in range(7))))
 
 B = 10
@@ -28,3 +28,9 @@ W2 = (torch.randn(16, 9 * 64, device='cuda') * 0.02).to(torch.bfloat16)
 b2 = torch.zeros(16, device='cuda')
 out = torch.empty(B, 360, 480, 16, dtype=torch.float32, device='cuda')
 run('up_conv1', lambda: K.conv2d(up, W2, b2, 3, 3, 1, relu=False, window=(1, 1, 360, 480), out=out, out_f32=True))
+v2 = torch.randn(B, 183, 243, 128, device='cuda').to(torch.bfloat16)
+W3 = (torch.randn(64, 9 * 128, device='cuda') * 0.02).to(torch.bfloat16)
+b3 = torch.zeros(64, device='cuda')
+add = torch.randn(B, 279, 339, 64, device='cuda').to(torch.bfloat16)
+out3 = torch.empty(B, 181, 241, 64, dtype=torch.bfloat16, device='cuda')
+run('up_conv2', lambda: K.conv2d(v2, W3, b3, 3, 3, 1, relu=False, window=(1, 1, 181, 241), out=out3, addend=add, addend_off=(49, 49)))
