@@ -99,6 +99,16 @@ typedef struct iiseg_conv_desc {
    * iiseg_maxpool2_mask_fwd; pooled positions outside u read as zero. */
   const uint32_t* depool_mask;
   int depool_UH, depool_UW, depool_h0, depool_w0;
+  /* DePool2D fused into the PRODUCER's epilogue: instead of its output u (bf16, Cout % 64 == 0, after bias / skip-sum)
+   * the conv writes v = DePool2D(u, depool_out_mask) restricted to a window.  The launch's output pixel (0,0) sits at
+   * (depool_out_ph0, depool_out_pw0) of the pooled grid depool_out_H2 x depool_out_W2, over which depool_out_mask is
+   * the tie mask [N,H2,W2,Cout/8]; depool_out is dense [N,depool_out_VH,depool_out_VW,Cout], its element (0,0) being
+   * full-resolution pixel (depool_out_h0, depool_out_w0).  Every window position under an output pixel is written
+   * (zeros where the mask is clear); positions of a trailing odd row / column are never written and must be zero. */
+  void* depool_out;
+  const uint32_t* depool_out_mask;
+  int depool_out_VH, depool_out_VW, depool_out_h0, depool_out_w0;
+  int depool_out_H2, depool_out_W2, depool_out_ph0, depool_out_pw0;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
   int Cout;           /* padded: 16, or a multiple of 64                    */

@@ -76,7 +76,7 @@ def conv_out_size(H, W, R, S, pad):
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
-           out_slice=None, pool_zmask=None, depool=None):
+           out_slice=None, pool_zmask=None, depool=None, depool_out=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -93,6 +93,11 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     depool = (mask, H, W, u_origin): `src0` is the POOLED tensor u (a dense window whose element (0,0) sits at pooled
     position u_origin) and the conv runs on the virtual map DePool2D(u, mask) of size HxW, expanded inside the
     kernel's loader (iiseg_conv_desc.depool_mask) -- same result as unpool2(...) followed by conv2d(...).
+
+    depool_out = (v, mask, (h0, w0), (ph0, pw0)): the conv's output u is not stored; its epilogue writes
+    v = DePool2D(u, mask) restricted to the window tensor `v` [N,VH,VW,Cout] whose element (0,0) is full-resolution
+    pixel (h0, w0); `mask` [N,H2,W2,Cout/8] is the tie mask over the pooled grid, on which this launch's output pixel
+    (0,0) sits at (ph0, pw0).  Returns v.
 
     out_slice = (stack, c_off): fp32 output written as channels [c_off, c_off + Cout) of the wider fp32
     NHWC tensor `stack` [N,OH,OW,Cs] (the DenseNet stack: ConcatLayer without a copy)."""
@@ -137,6 +142,13 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         assert Cout == 16 and out is None and addend is None and not split
         assert tuple(update['y'].shape) == (N, update['C'], OH, OW) and tuple(update['y_bf16'].shape[:3]) == (N, OH, OW)
         assert update['norm_acc'].numel() == N
+    elif depool_out is not None:
+        dpo_v, dpo_mask, dpo_org, dpo_porg = depool_out
+        _chk(dpo_v, BF16, 'depool_out.v')
+        _chk(dpo_mask, torch.int32, 'depool_out.mask')
+        assert out is None and not split and not out_f32 and Cout % 64 == 0
+        assert dpo_v.shape[0] == N and dpo_v.shape[3] == Cout and dpo_mask.shape[0] == N and dpo_mask.shape[3] == Cout // 8
+        assert dpo_porg[0] + OH <= dpo_mask.shape[1] and dpo_porg[1] + OW <= dpo_mask.shape[2]
     elif out_slice is not None:
         stack, c_off = out_slice
         _chk(stack, F32, 'out_slice.stack')
@@ -162,6 +174,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if depool_out is not None:
+        d.depool_out, d.depool_out_mask = dpo_v.data_ptr(), dpo_mask.data_ptr()
+        d.depool_out_VH, d.depool_out_VW, d.depool_out_h0, d.depool_out_w0 = dpo_v.shape[1], dpo_v.shape[2], dpo_org[0], dpo_org[1]
+        d.depool_out_H2, d.depool_out_W2, d.depool_out_ph0, d.depool_out_pw0 = dpo_mask.shape[1], dpo_mask.shape[2], dpo_porg[0], dpo_porg[1]
     if depool is not None:
         d.depool_mask = dp_mask.data_ptr()
         d.depool_UH, d.depool_UW, d.depool_h0, d.depool_w0 = src0.shape[1], src0.shape[2], dp_origin[0], dp_origin[1]
@@ -184,6 +200,8 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     for i, (ptr, c, cs) in enumerate(views):
         d.src[i], d.C[i], d.Cs[i] = ptr, c, cs
     _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
+    if depool_out is not None:
+        return dpo_v
     return out if pooled is None else pooled
 
 

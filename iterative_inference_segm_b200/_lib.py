@@ -27,6 +27,9 @@ class ConvDesc(C.Structure):
         ('src_image_stride', C.c_longlong), ('weight_ld', C.c_longlong), ('w_koff', C.c_int), ('w_groups', C.c_int), ('w_rows_total', C.c_int), ('w_group_koff', C.c_int * MAX_WGROUPS),
         ('w_group_row', C.c_int * MAX_WGROUPS),
         ('depool_mask', C.c_void_p), ('depool_UH', C.c_int), ('depool_UW', C.c_int), ('depool_h0', C.c_int), ('depool_w0', C.c_int),
+        ('depool_out', C.c_void_p), ('depool_out_mask', C.c_void_p), ('depool_out_VH', C.c_int), ('depool_out_VW', C.c_int),
+        ('depool_out_h0', C.c_int), ('depool_out_w0', C.c_int),
+        ('depool_out_H2', C.c_int), ('depool_out_W2', C.c_int), ('depool_out_ph0', C.c_int), ('depool_out_pw0', C.c_int),
         ('weight', C.c_void_p), ('bias', C.c_void_p),
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),

@@ -87,6 +87,12 @@ struct alignas(64) ConvParams {
   int dp_phb, dp_pwb;       // staged box: pooled rows x pooled columns
   int dp_u_h0, dp_u_w0;     // pooled-grid position of u's element (0,0)
   uint32_t dp_stage_bytes, dp_mask_off, dp_stage_tx;
+  // DePool2D fused into the PRODUCER's epilogue (iiseg_conv_desc.depool_out): the conv output u is written as the masked
+  // 2x2 blocks of v = DePool2D(u) that fall inside the v window; u itself is not stored
+  __nv_bfloat16* dpo_out; const uint32_t* dpo_mask;
+  int dpo_H2, dpo_W2;       // pooled grid = this conv's full output map
+  int dpo_ph0, dpo_pw0;     // pooled-grid position of this launch's output pixel (0,0)
+  int dpo_vh0, dpo_vw0, dpo_VH, dpo_VW;   // v window: origin in full-resolution coordinates, extent
   int pair;                 // CTA-pair kernel (cta_group::2): work units are (N-tile, pair of M-tiles)
   int num_units, m_tiles;   // pair kernel: n_ntiles * ceil(m_tiles / 2) units; m_tiles = N * tiles_h * tiles_w
   int acc_stages;           // TMEM accumulator stages in use (2, or 4 in the halo kernel when BN allows)
@@ -109,6 +115,24 @@ struct alignas(64) ConvParams {
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores,
                             // bit8 = DePool2D loader without the expansion loop, bit9 = without its proxy fence (timing only)
 };
+
+// Store 8*kWords channels of output pixel (n, ph, pw) as the masked 2x2 block of v = DePool2D(u) (layers/mylayers.py:88-115):
+// mask word g covers channels 8g..8g+7 (nibble k bit pos -> low half of packed word k, nibble 4+k -> high half, see tie_bits).
+template <int kWords>
+__device__ __forceinline__ void depool_store(const ConvParams& p, int n, int ph, int pw, int cbase, const uint32_t* hi, const uint32_t* bits) {
+#pragma unroll
+  for (int pos = 0; pos < 4; ++pos) {
+    const int vh = 2 * ph + (pos >> 1) - p.dpo_vh0, vw = 2 * pw + (pos & 1) - p.dpo_vw0;
+    if (vh < 0 || vh >= p.dpo_VH || vw < 0 || vw >= p.dpo_VW) continue;
+    __nv_bfloat16* o = p.dpo_out + ((static_cast<size_t>(n) * p.dpo_VH + vh) * p.dpo_VW + vw) * p.Cout + cbase;
+#pragma unroll
+    for (int g = 0; g < kWords; ++g) {
+      const uint32_t b = bits[g] >> pos;
+      stg_v4(o + 8 * g, make_uint4(hi[4 * g] & ((b & 0x00010001u) * 0xFFFFu), hi[4 * g + 1] & (((b >> 4) & 0x00010001u) * 0xFFFFu),
+                                   hi[4 * g + 2] & (((b >> 8) & 0x00010001u) * 0xFFFFu), hi[4 * g + 3] & (((b >> 12) & 0x00010001u) * 0xFFFFu)));
+    }
+  }
+}
 
 // Debug timeline (IISEG_CONV_DBG bit 2): block 0 stamps clock64() at fixed points of its first 32 tiles.
 __device__ long long g_timeline[32 * 16];
@@ -599,6 +623,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); c = fmaxf(c, 0.f); d = fmaxf(d, 0.f); }
               stg_v4(o + 4 * j, make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d)));
             }
+          }
+        } else if (!kSplit && p.dpo_out != nullptr) {
+          if (valid) {
+            const int ph = p.dpo_ph0 + oh, pw = p.dpo_pw0 + ow;
+            const uint4 mw = ldg_nc_v4(p.dpo_mask + ((static_cast<size_t>(tc.n) * p.dpo_H2 + ph) * p.dpo_W2 + pw) * (p.Cout >> 3) + (cbase >> 3));
+            const uint32_t bits[4] = {mw.x, mw.y, mw.z, mw.w};
+            depool_store<4>(p, tc.n, ph, pw, cbase, hi, bits);
           }
         } else if (p.pooled == nullptr) {
           if (valid && !(p.dbg & 16)) {
@@ -1137,7 +1168,12 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         for (int j = 0; j < 8; ++j) hi[j] = bf16x2_max(hi[j], 0u);      // max(x, 0) commutes with the bf16 rounding
       }
       if constexpr (!kPool) {
-        if (valid) {
+        if (valid && p.dpo_out != nullptr) {
+          const int ph = p.dpo_ph0 + oh, pw = p.dpo_pw0 + ow;
+          const uint2 mw = *reinterpret_cast<const uint2*>(p.dpo_mask + ((static_cast<size_t>(tc.n) * p.dpo_H2 + ph) * p.dpo_W2 + pw) * (p.Cout >> 3) + (cbase >> 3));
+          const uint32_t bits[2] = {mw.x, mw.y};
+          depool_store<2>(p, tc.n, ph, pw, cbase, hi, bits);
+        } else if (valid) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase;
           stg_v4(o, make_uint4(hi[0], hi[1], hi[2], hi[3]));
           stg_v4(o + 8, make_uint4(hi[4], hi[5], hi[6], hi[7]));
@@ -1614,7 +1650,13 @@ extern "C" int iiseg_debug_read_timeline(long long* out, int n) {
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
-  IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr && (d->out != nullptr || d->pooled != nullptr || d->upd_y != nullptr), "conv: null tensor");
+  IISEG_CHECK(d->src[0] != nullptr && d->weight != nullptr && d->bias != nullptr &&
+              (d->out != nullptr || d->pooled != nullptr || d->upd_y != nullptr || d->depool_out != nullptr), "conv: null tensor");
+  if (d->depool_out != nullptr)
+    IISEG_CHECK(d->depool_out_mask != nullptr && d->out == nullptr && d->pooled == nullptr && d->upd_y == nullptr && d->split == 0 && d->out_f32 == 0 &&
+                d->Cout % 64 == 0 && d->depool_out_VH >= 1 && d->depool_out_VW >= 1 && d->depool_out_ph0 >= 0 && d->depool_out_pw0 >= 0 &&
+                d->depool_out_ph0 + d->OH <= d->depool_out_H2 && d->depool_out_pw0 + d->OW <= d->depool_out_W2,
+                "conv: depool_out needs its mask, a plain bf16 conv with Cout %% 64 == 0 and no other output");
   if (d->upd_y != nullptr)
     IISEG_CHECK(d->Cout == 16 && d->upd_y_bf16 != nullptr && d->upd_norm_acc != nullptr && d->upd_C >= 1 && d->upd_C <= 16 &&
                 d->upd_cpad >= 16 && d->upd_cpad % 8 == 0 && d->addend == nullptr && d->pooled == nullptr && d->split == 0,
@@ -1784,6 +1826,11 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
+  if (d->depool_out != nullptr) {
+    p.dpo_out = reinterpret_cast<__nv_bfloat16*>(d->depool_out); p.dpo_mask = d->depool_out_mask;
+    p.dpo_H2 = d->depool_out_H2; p.dpo_W2 = d->depool_out_W2; p.dpo_ph0 = d->depool_out_ph0; p.dpo_pw0 = d->depool_out_pw0;
+    p.dpo_vh0 = d->depool_out_h0; p.dpo_vw0 = d->depool_out_w0; p.dpo_VH = d->depool_out_VH; p.dpo_VW = d->depool_out_VW;
+  }
   p.out_cs = d->out_cs > 0 ? d->out_cs : d->Cout;
   {
     // halo kernel, BN 64/128 and the fused-update logits conv: 4 accumulator stages, one per epilogue group (an

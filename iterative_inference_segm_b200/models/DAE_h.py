@@ -41,6 +41,9 @@ class DAENet(object):
         # IISEG_FUSE_DEPOOL=1: last DePool2D expanded inside the loader of up_conv1 (bf16 variant; bit-identical results).
         # Off by default: measured 0.179 ms against 0.050 (unpool) + 0.112 (conv) -- see DESIGN.md 3.7
         self.fuse_depool = os.environ.get('IISEG_FUSE_DEPOOL', '0') == '1'
+        # IISEG_DEPOOL_EPILOGUE=1: DePool2D of level p-1 written by the epilogue of up_conv_p (bf16 variant, bit-identical).
+        # Off by default: measured 163 vs 165 images/s -- the 4x larger epilogue stores cost what the unpool launch did
+        self.fuse_depool_out = os.environ.get('IISEG_DEPOOL_EPILOGUE', '0') == '1'
         self.cm = 2 if self.split else 1          # bf16 channels per logical channel in activation tensors
         assert n_classes <= 16
         self.n_classes = n_classes
@@ -182,7 +185,8 @@ class DAENet(object):
             ws['mask'].append(torch.empty((B, h // 2, w // 2, f // 8), dtype=torch.int32, device=dev))
         for p in range(1, self.total + 1):
             ul, uh, vl, vh = Wu[p]
-            ws['unpool'][p] = torch.empty((B, uh - ul, vh - vl, self.cm * self.filters[p - 1]), dtype=bf, device=dev)
+            # zeros: with the DePool2D-in-the-producer path the trailing odd row / column of a level is never written
+            ws['unpool'][p] = torch.zeros((B, uh - ul, vh - vl, self.cm * self.filters[p - 1]), dtype=bf, device=dev)
             if p > 1:   # up_conv_p output: level-p window, channels of level p-1; skip partner pool_{p-1} has size S_p
                 hl, hh, wl, wh = Wc[p]
                 assert sizes[p - 1] == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
@@ -232,6 +236,7 @@ class DAENet(object):
                          split=sp)
             x = ws['pool'][p]
         u, u_origin = ws['pool'][-1], (0, 0)
+        prefilled = False
         for i, p in enumerate(range(self.total, 0, -1)):
             h, w = sizes[p - 1]
             ul, uh, vl, vh = Wu[p]
@@ -247,10 +252,21 @@ class DAENet(object):
                     return None
                 K.conv2d(u, Wk, bk, 3, 3, 1, relu=False, out=ws['logits'], out_f32=True, **dp)
                 break
-            up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
-                           window=(ul, vl, uh - ul, vh - vl), split=sp)
+            if prefilled:        # the previous conv's epilogue already wrote DePool2D(u) into this level's window
+                up = ws['unpool'][p]
+            else:
+                up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
+                               window=(ul, vl, uh - ul, vh - vl), split=sp)
             win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
-            if p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
+            if p > 1 and self.fuse_depool_out and not sp and not (p == 2 and self.fuse_depool):
+                # skip-sum, then DePool2D for the next level written straight from this conv's epilogue (u itself is
+                # never stored): one launch and one round trip of u through HBM less per level
+                nul, _, nvl, _ = Wu[p - 1]
+                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2], addend_off=(hl, wl),
+                         depool_out=(ws['unpool'][p - 1], ws['mask'][p - 2], (nul, nvl), (hl, wl)))
+                prefilled = True
+            elif p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
+                prefilled = False
                 u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],
                              addend_off=(hl, wl), out=ws['upconv'][p], split=sp)
                 u_origin = (hl, wl)

@@ -293,3 +293,37 @@ def test_conv_with_fused_depool_equals_unpool_then_conv(cuda, case):
     torch.cuda.synchronize()
     assert vh0 >= 2 * ph0 and vw0 >= 2 * pw0 and vh1 <= min(2 * (ph0 + UH), H) + (H % 2) and vw1 <= min(2 * (pw0 + UW), W) + (W % 2)
     assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
+
+
+# N, conv input map H x W, Cin, Cout, conv window (oh0, ow0, OH, OW), v window in the 2x map (vh0, vw0, VH, VW), odd (2H+1 x 2W+1 map)
+DEPOOL_OUT_CASES = [
+    (2, 17, 21, 128, 256, (0, 0, 17, 21), (0, 0, 34, 42), 0),            # CTA-pair kernel, whole maps
+    (2, 17, 21, 128, 256, (0, 0, 17, 21), (0, 0, 35, 43), 1),            # odd unpooled map: trailing row / column stay zero
+    (2, 27, 35, 256, 128, (1, 1, 25, 33), (2, 3, 50, 64), 0),            # cone windows (up_conv3-like), pair<128>
+    (3, 46, 60, 128, 64, (3, 2, 40, 55), (7, 5, 78, 108), 0),            # halo-tile kernel (up_conv2-like), skip-sum
+    (1, 30, 40, 64, 64, (2, 4, 26, 30), (4, 8, 52, 59), 1),
+]
+
+
+@pytest.mark.parametrize('case', DEPOOL_OUT_CASES, ids=[str(c) for c in DEPOOL_OUT_CASES])
+def test_conv_with_depool_epilogue_equals_conv_then_unpool(cuda, case):
+    """iiseg_conv_desc.depool_out: DePool2D written by the producing conv's epilogue == conv followed by the unpool kernel,
+    bit for bit (same accumulation, same mask selection)."""
+    from iterative_inference_segm_b200 import _kernels as K
+    N, H, W, Cin, Cout, (oh0, ow0, OH, OW), (vh0, vw0, VH, VW), odd = case
+    torch.manual_seed(2)
+    FH, FW = 2 * H + odd, 2 * W + odd                                   # the unpooled (pre-pool) map
+    xfull = torch.randn(N, FH, FW, Cout, device=cuda).to(torch.bfloat16)
+    xfull[:, 0:2 * H:2, :, :16] = xfull[:, 1:2 * H:2, :, :16]           # ties -> multi-bit masks
+    _, mask = K.maxpool2(xfull, True)                                    # [N, H, W, Cout/8]
+    x = torch.randn(N, H, W, Cin, device=cuda).to(torch.bfloat16)
+    Wt = (torch.randn(Cout, 9 * Cin, device=cuda) / (9 * Cin) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=cuda)
+    add = torch.randn(N, H, W, Cout, device=cuda).to(torch.bfloat16)
+    u = K.conv2d(x, Wt, b, 3, 3, 1, relu=False, window=(oh0, ow0, OH, OW), addend=add, addend_off=(oh0, ow0))
+    ref = K.unpool2(u, mask, FH, FW, u_origin=(oh0, ow0), window=(vh0, vw0, VH, VW))
+    v = torch.zeros(N, VH, VW, Cout, dtype=torch.bfloat16, device=cuda)
+    got = K.conv2d(x, Wt, b, 3, 3, 1, relu=False, window=(oh0, ow0, OH, OW), addend=add, addend_off=(oh0, ow0),
+                   depool_out=(v, mask, (vh0, vw0), (oh0, ow0)))
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
