@@ -113,7 +113,8 @@ struct alignas(64) ConvParams {
   int addend_f32;           // the skip-sum / hoisted-term operand is fp32 [N,AH,AW,Cout] (BN >= 64 epilogue only)
   int stages;               // pipeline depth actually used (<= ConvCfg::kStages)
   int dbg;                  // tuning experiments: bit0 = skip TMA loads, bit1 = skip MMA issue, bit3 = skip addend loads, bit4 = skip bf16 stores,
-                            // bit8 = DePool2D loader without the expansion loop, bit9 = without its proxy fence (timing only)
+                            // bit8 = DePool2D loader without the expansion loop, bit9 = without its proxy fence (timing only),
+                            // bit10 = epilogue accumulator waits spin without the 64 ns back-off (default: back off; +0.5 % end to end, the GPU runs power-capped)
 };
 
 // Store 8*kWords channels of output pixel (n, ph, pw) as the masked 2x2 block of v = DePool2D(u) (layers/mylayers.py:88-115):
@@ -184,10 +185,11 @@ __device__ __noinline__ void mbar_timeout(int32_t* diag, int code, int aux) {
   }
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* diag, int code, int aux) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* diag, int code, int aux, bool backoff = false) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (backoff) __nanosleep(64);           // epilogue warps waiting for an accumulator: leave the issue slots (and power) to the others
     if (clock64() - t0 > kTimeoutCycles) mbar_timeout(diag, code, aux);
   }
 }
@@ -341,7 +343,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
     uint4 a0 = make_uint4(0, 0, 0, 0);
     const bool has_add = (p.addend != nullptr) && valid;
     if (has_add) a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
-    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as);
+    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * 16) + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t v[8];
@@ -457,7 +459,7 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
         for (int c = 0; c < 16; ++c) if (c < C) yn[c] = nxt.yb[static_cast<size_t>(c) * HW];
       }
     }
-    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as);
+    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
     tcgen05_fence_after();
     uint32_t v[16];
     tmem_ld_x16(tmem_base + static_cast<uint32_t>(as * 16) + (static_cast<uint32_t>(q * 32) << 16), v);
@@ -548,7 +550,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         }
       }
       if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 4);
-      mbar_wait(tmem_full_bar, aphase, p.diag, 4, as);
+      mbar_wait(tmem_full_bar, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
       tcgen05_fence_after();
       if (grp == 0 && q == 0 && lane == 0) IISEG_STAMP(iter, 5);
 #pragma unroll 1
@@ -1106,7 +1108,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
     uint4 add[2];
     if (has_add) { add[0] = ldg_nc_v4(arow); add[1] = ldg_nc_v4(arow + 8); }      // before the accumulator is ready
     if (q == 0 && lane == 0) IISEG_STAMP(iter, 4);
-    mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp);
+    mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp, (p.dbg & 1024) == 0);
     tcgen05_fence_after();
     if (q == 0 && lane == 0) IISEG_STAMP(iter, 5);
 #pragma unroll 1
