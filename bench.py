@@ -301,8 +301,9 @@ def run_b200(args):
         other = {}
         for (name, tag), v in summ.items():
             other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
-        # dominant kernel: conv_igemm_pair_kernel (per-tap implicit GEMM, 256-channel tiles, cta_group::2 CTA pairs) = every launch with Cout % 256 == 0
-        dom = [(f, ms) for f, (tag, ms) in zip(fl, convs) if tag[2] % 256 == 0]
+        # dominant kernel: conv_igemm_pair_kernel<256> (per-tap implicit GEMM, 256 x 256 tiles over CTA pairs): the launches the
+        # library reports as kernel 1 (CTA pair) with BN = 256 (tag[-1] = iiseg_last_conv_plan of that launch)
+        dom = [(f, ms) for f, (tag, ms) in zip(fl, convs) if tag[-1][0] == 1 and tag[-1][1] == 256]
         dom_flops, dom_ms = sum(f for f, _ in dom) * BATCH, sum(ms for _, ms in dom)
         achieved = dom_flops / (dom_ms * 1e-3) / 1e12
         peak = peaks['bf16_tflops_sustained']
@@ -311,7 +312,7 @@ def run_b200(args):
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get('conv_igemm_pair_kernel<256>', {}).get('dram_bytes_per_launch')
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<256> (tcgen05 cta_group::2 implicit GEMM, 256 x 256 tiles over CTA pairs; %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1..conv6_1, up_conv6..up_conv4; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
+        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<256> (tcgen05 cta_group::2 implicit GEMM, 256 x 256 tiles over CTA pairs; %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1, conv4_1, conv6_1, up_conv6..up_conv4 -- conv5_1 runs the same kernel with 128-wide tiles; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': dom_ms / len(dom),
                 'flops_per_launch': dom_flops / len(dom),

@@ -162,6 +162,9 @@ typedef struct iiseg_conv_desc {
   int upd_C, upd_cpad;
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
+/* Which kernel the calling thread's last iiseg_conv2d_fwd launched: *kernel = 0 per-tap, 1 CTA pair (cta_group::2),
+ * 2 halo tile; *bn = N tile, *kb = channels per K block.  Measurement tooling (bench.py groups launches by kernel). */
+int iiseg_last_conv_plan(int* kernel, int* bn, int* kb);
 
 /* ---- pooling: lasagne Pool2DLayer(2) + DePool2D -------------------------
  * 2x2/stride-2 max, floor (models/fcn_down.py:122).  `mask` (may be NULL)

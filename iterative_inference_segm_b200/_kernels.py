@@ -459,6 +459,13 @@ def bias_grad(g, out, col, chunks=592):
     _lib.call('iiseg_bias_grad', _ptr(g), C.c_longlong(P), Cg, _ptr(scratch), chunks, out.data_ptr() + 4 * col, out.shape[1], _stream())
 
 
+def last_conv_plan():
+    """(kernel, BN, KB) of this thread's last conv launch: kernel 0 per-tap, 1 CTA pair, 2 halo tile."""
+    k, bn, kb = C.c_int(-1), C.c_int(0), C.c_int(0)
+    _lib.load().iiseg_last_conv_plan(C.byref(k), C.byref(bn), C.byref(kb))
+    return k.value, bn.value, kb.value
+
+
 def gemm_nt_splitk(A, Bm, slabs):
     """G[m][n] = sum_k A[m][k] * Bm[n][k] for row-major bf16 A [M, K], Bm [Nn, K] (K = slabs * slab, slab % 64 == 0),
     fp32 result [M, Nn].  Runs on the tcgen05 conv kernel as a 1x1 conv whose batch images are the K slabs (split-K: each

@@ -88,6 +88,7 @@ SIGNATURES = {
     'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _i, C.c_longlong, _vp]),
+    'iiseg_last_conv_plan': (_i, [_vp, _vp, _vp]),
     'iiseg_bias_grad': (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _i, _vp]),
     'iiseg_sum_slabs': (_i, [_vp, _vp, _i, C.c_longlong, _vp]),
     'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),

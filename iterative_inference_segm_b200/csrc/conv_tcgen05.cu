@@ -1649,6 +1649,15 @@ extern "C" int iiseg_debug_read_timeline(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, iiseg::g_timeline, n * sizeof(long long)) == cudaSuccess ? n : -1;
 }
 
+static thread_local int g_last_plan[3] = {-1, 0, 0};      // kernel (0 per-tap, 1 CTA pair, 2 halo tile), BN, KB of this thread's last conv launch
+
+extern "C" int iiseg_last_conv_plan(int* kernel, int* bn, int* kb) {
+  if (kernel) *kernel = g_last_plan[0];
+  if (bn) *bn = g_last_plan[1];
+  if (kb) *kb = g_last_plan[2];
+  return g_last_plan[0] >= 0 ? 0 : -1;
+}
+
 extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(d != nullptr, "conv: null descriptor");
@@ -1709,7 +1718,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   ConvParams p;
   memset(&p, 0, sizeof(p));
   const int w_rows = wgroups > 0 ? d->Cout / wgroups : d->Cout;     // filter rows held by the weight matrix
-  const int BN = w_rows == 16 ? 16 : (w_rows % 256 == 0 ? 256 : (w_rows % 128 == 0 ? 128 : 64));
+  static const int env_bnmax = getenv("IISEG_CONV_BNMAX") ? atoi(getenv("IISEG_CONV_BNMAX")) : 256;      // tuning: cap the N tile
+  int BN = w_rows == 16 ? 16 : ((w_rows % 256 == 0 && env_bnmax >= 256) ? 256 : (w_rows % 128 == 0 ? 128 : 64));
   const bool fuse_pool = d->pooled != nullptr;
   // with the fused pool only the 2*floor(OH/2) x 2*floor(OW/2) outputs that have a pool window are computed
   const int covH = fuse_pool ? (d->OH / 2) * 2 : d->OH, covW = fuse_pool ? (d->OW / 2) * 2 : d->OW;
@@ -1777,6 +1787,17 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
     p.pitch = p.TW;
     box_h = p.TH; box_w = p.TW;
+    // CTA-pair kernel: units run in whole rounds over the SM pairs.  256-wide N tiles are ~15 % more efficient per
+    // FLOP than 128-wide ones (measured on conv3_1 .. up_conv4), but when the last round of 256-wide units is mostly
+    // empty, twice as many half-size units waste less: conv5_1 has 180 units on 74 pairs = 3 rounds, or 360 halves =
+    // 5 half-rounds (0.105 -> 0.091 ms).
+    static const int env_bnauto = getenv("IISEG_CONV_BNAUTO") ? atoi(getenv("IISEG_CONV_BNAUTO")) : 1;
+    if (env_bnauto && BN == 256 && KB == 64) {
+      const int pairs = num_sms() / 2;
+      const long units = (long)(d->Cout / 256) * ((d->N * ceil_div(covH, p.TH) * ceil_div(covW, p.TW) + 1) / 2);
+      const long r256 = (units + pairs - 1) / pairs, r128 = (2 * units + pairs - 1) / pairs;
+      if (0.5 * 1.15 * (double)r128 < (double)r256) BN = 128;
+    }
   }
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
     if (d->src[i] != nullptr && depool) {
@@ -1850,8 +1871,10 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     static const int env_pair = getenv("IISEG_CONV_PAIR") ? atoi(getenv("IISEG_CONV_PAIR")) : 1;     // 0: single-CTA kernel (A/B comparison)
     // split-K views: both CTAs of a pair share one filter block, so a pair must not straddle two K slabs (images)
     const bool pair_same_slab = d->w_koff == 0 || (p.tiles_h * p.tiles_w) % 2 == 0;
+    g_last_plan[0] = halo ? 2 : 0; g_last_plan[1] = BN; g_last_plan[2] = KB;
     if (env_pair && !halo && (BN == 256 || BN == 128) && KB == 64 && pair_same_slab) {
       p.pair = 1;
+      g_last_plan[0] = 1;
       p.m_tiles = d->N * p.tiles_h * p.tiles_w;
       p.num_units = p.n_ntiles * ((p.m_tiles + 1) / 2);
       if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN / 2, KB, d->weight_ld)) return -1;       // each CTA loads half of a filter block

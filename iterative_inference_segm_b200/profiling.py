@@ -30,7 +30,10 @@ class KernelTimer(object):
                 s.record()
                 out = fn(*args, **kw)
                 e.record()
-                self.records.append((name, _tag(name, args, kw), s, e))
+                tag = _tag(name, args, kw)
+                if name == 'conv2d':
+                    tag = tag + (K.last_conv_plan(),)       # (kernel, BN, KB): which kernel ran
+                self.records.append((name, tag, s, e))
                 return out
             return timed
         for n, fn in saved.items():
