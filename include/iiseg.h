@@ -27,12 +27,16 @@
 extern "C" {
 #endif
 
-#define IISEG_ABI_VERSION 2
+#define IISEG_ABI_VERSION 3
 #define IISEG_MAX_SRC 6
 #define IISEG_MAX_WGROUPS 9
 
 /* ---- library ----------------------------------------------------------- */
 int iiseg_abi_version(void);
+/* sizeof(iiseg_conv_desc) and offsetof(iiseg_conv_desc, upd_cpad) (its last field): lets a binding check its mirror of the
+ * struct without a GPU. */
+int iiseg_conv_desc_size(void);
+int iiseg_conv_desc_last_offset(void);
 const char* iiseg_last_error(void);
 /* 0 if device `dev` is compute capability 10.x; negative otherwise. */
 int iiseg_device_check(int dev);

@@ -14,7 +14,7 @@ class IisegError(RuntimeError):
     pass
 
 
-ABI_VERSION = 2      # IISEG_ABI_VERSION
+ABI_VERSION = 3      # IISEG_ABI_VERSION
 MAX_SRC = 6          # IISEG_MAX_SRC
 MAX_WGROUPS = 9      # IISEG_MAX_WGROUPS
 
@@ -58,6 +58,8 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 # name -> (restype, argtypes); must list every symbol include/iiseg.h declares
 SIGNATURES = {
     'iiseg_abi_version': (_i, []),
+    'iiseg_conv_desc_size': (_i, []),
+    'iiseg_conv_desc_last_offset': (_i, []),
     'iiseg_last_error': (C.c_char_p, []),
     'iiseg_device_check': (_i, [_i]),
     'iiseg_read_diag': (_i, [_vp, _i]),

@@ -3,6 +3,7 @@
 #include <mutex>
 #include <string.h>
 
+#include <cstddef>
 #include "common.cuh"
 #include "../../include/iiseg.h"
 
@@ -53,6 +54,8 @@ int32_t* diag_device_ptr() {
 }  // namespace iiseg
 
 extern "C" int iiseg_abi_version(void) { return IISEG_ABI_VERSION; }
+extern "C" int iiseg_conv_desc_size(void) { return (int)sizeof(iiseg_conv_desc); }
+extern "C" int iiseg_conv_desc_last_offset(void) { return (int)offsetof(iiseg_conv_desc, upd_cpad); }
 
 extern "C" const char* iiseg_last_error(void) { return iiseg::g_err; }
 

@@ -25,8 +25,17 @@ def test_binding_table_matches_header(lib):
 
 
 def test_abi_version_and_error_text(lib):
-    assert lib.iiseg_abi_version() == 2
+    assert lib.iiseg_abi_version() == 3
     assert isinstance(lib.iiseg_last_error(), bytes)
+
+
+def test_conv_desc_mirror_has_the_c_layout(lib):
+    """The ctypes mirror of struct iiseg_conv_desc: same size, same offset of the last field."""
+    import ctypes as C
+    from iterative_inference_segm_b200 import _lib
+    assert C.sizeof(_lib.ConvDesc) == lib.iiseg_conv_desc_size()
+    assert _lib.ConvDesc.upd_cpad.offset == lib.iiseg_conv_desc_last_offset()
+    assert _lib.ConvDesc._fields_[-1][0] == 'upd_cpad'
 
 
 def test_bad_descriptor_is_rejected_without_gpu(lib):
