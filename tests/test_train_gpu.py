@@ -128,3 +128,22 @@ def test_bias_grad_matches_sum(cuda):
         ref = g.float().sum(dim=(0, 1, 2))
         assert torch.allclose(out[:, 5], ref, rtol=1e-5, atol=1e-4)
         assert (out[:, :5] == 0).all() and (out[:, 6:] == 0).all()
+
+
+def test_graphed_step_equals_eager_step(cuda):
+    """DAETrainer.step_graphed (eager, then capture + replay, then replay) == DAETrainer.step, bit for bit, over four steps."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    pd, h, y, L, nm, nk = _setup(cuda)
+    trs = [DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=0.5) for _ in range(2)]
+    h_b = K.pack_nchw(h.to(cuda), 512)
+    y, L = y.to(cuda), L.to(cuda)
+    gen = torch.Generator(device=cuda).manual_seed(11)
+    for k in range(4):
+        n1 = torch.randn(y.shape, device=cuda, generator=gen)
+        n2 = torch.randn(y.shape, device=cuda, generator=gen)
+        trs[0].step(h_b, y, L, n1, n2)
+        trs[1].step_graphed(h_b, y, L, n1, n2)
+        assert trs[0].loss_value() == trs[1].loss_value(), k
+    for a, b in zip(trs[0].params(), trs[1].params()):
+        assert torch.equal(a, b)

@@ -33,6 +33,20 @@ for _ in range(n):
 e.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(e) / n
 losses.append(tr.loss_value())
+def step_g():
+    nm = torch.randn(y.shape, device='cuda', generator=gen)
+    nk = torch.randn(y.shape, device='cuda', generator=gen)
+    tr.step_graphed(h, y, L, nm, nk)
+
+for _ in range(3):
+    step_g()
+torch.cuda.synchronize()
+s.record()
+for _ in range(n):
+    step_g()
+e.record(); torch.cuda.synchronize()
+ms_g = s.elapsed_time(e) / n
+print('graphed train step: %.2f ms / step = %.1f images/s' % (ms_g, B / ms_g * 1e3))
 print('train step: %.2f ms / step (batch %d at %dx%d) = %.1f images/s; loss over steps %s; peak mem %.1f GB' % (
     ms, B, H, W, B / ms * 1e3, ['%.4f' % l for l in losses], torch.cuda.max_memory_allocated() / 2**30))
 timer = KernelTimer()
