@@ -162,25 +162,51 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
             'savepath': savepath}
 
 
+def _flag(v):
+    """argparse `type=bool` treats every non-empty string as True (the reference's flags do); this one parses it."""
+    return str(v).strip().lower() in ('1', 'true', 'yes', 'y', 'on')
+
+
+def _literal_dict(v):
+    import ast
+    d = ast.literal_eval(v) if isinstance(v, str) else v
+    if not isinstance(d, dict):
+        raise argparse.ArgumentTypeError('expected a dict literal, e.g. "{\'noise\': 0}"')
+    return d
+
+
 def main():
+    """Same flags as the reference's CLI (iterative_inference.py:329-394).  `-dae_dict` / `-training_dict` take a Python
+    dict literal; the defaults are the benchmark's DAE (kind=standard, concat_h=[pool4]) -- the reference's default
+    kind, contextmod on the input, is outside the B200 hot path and raises NotImplementedError."""
     parser = argparse.ArgumentParser(description='Iterative inference.')
-    parser.add_argument('-dataset', type=str, default='camvid')
-    parser.add_argument('-segmentation_net', type=str, default='fcn8')
-    parser.add_argument('-step', type=float, default=1.0)
-    parser.add_argument('--num_iter', '-ne', type=int, default=1)
-    parser.add_argument('-which_set', type=str, default='test')
+    parser.add_argument('-dataset', type=str, default='camvid', help='Dataset.')
+    parser.add_argument('-segmentation_net', type=str, default='fcn8', help='Segmentation network: fcn8 | densenet')
+    parser.add_argument('-step', type=float, default=1.0, help='step')
+    parser.add_argument('--num_iter', '-ne', type=int, default=1, help='Max number of iterations')
+    parser.add_argument('-which_set', type=str, default='test', help='Inference set')
+    parser.add_argument('-dae_dict', type=_literal_dict,
+                        default={'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0,
+                                 'concat_h': ['pool4'], 'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1,
+                                 'additional_pool': 2, 'path_weights': '', 'layer': 'probs_dimshuffle',
+                                 'exp_name': 'flip_final_', 'bn': 0}, help='DAE kind and parameters')
+    parser.add_argument('-training_dict', type=_literal_dict,
+                        default={'training_loss': ['crossentropy'], 'learning_rate': 0.0001, 'lr_anneal': 0.99,
+                                 'weight_decay': 0.0001, 'optimizer': 'rmsprop'}, help='Training parameters')
+    parser.add_argument('-full_im_ft', type=_flag, default=False, help='Whether to finetune at full image resolution')
+    parser.add_argument('-ae_h', type=_flag, default=False, help='Whether to reconstruct intermediate h')
+    parser.add_argument('-data_augmentation', type=_flag, default=True, help='Data augmentation tag of the experiment name')
+    parser.add_argument('-test_from_0_255', type=_flag, default=False, help='Whether images are within the 0-255 range')
     parser.add_argument('-savepath', type=str, default='./iiseg_out/')
     parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
     parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
+    parser.add_argument('-precision', type=str, default='bf16', choices=['bf16', 'fp32x3'])
     args = parser.parse_args()
-    dae_dict = {'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0,
-                'concat_h': ['pool4'], 'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1, 'additional_pool': 2,
-                'path_weights': '', 'layer': 'probs_dimshuffle', 'exp_name': 'flip_final_', 'bn': 0}
-    training_dict = {'training_loss': ['crossentropy'], 'learning_rate': 0.0001, 'lr_anneal': 0.99,
-                     'weight_decay': 0.0001, 'optimizer': 'rmsprop'}
     inference(args.dataset, args.segmentation_net, float(args.step), int(args.num_iter), which_set=args.which_set,
               savepath=args.savepath, loadpath=args.loadpath, weights_path=args.weights_path,
-              dae_dict_updates=dae_dict, training_dict=training_dict, data_augmentation=True)
+              full_im_ft=args.full_im_ft, test_from_0_255=args.test_from_0_255, ae_h=args.ae_h,
+              dae_dict_updates=args.dae_dict, data_augmentation=args.data_augmentation,
+              training_dict=args.training_dict, precision=args.precision)
 
 
 if __name__ == '__main__':

@@ -14,14 +14,17 @@ import torch
 
 from . import functions as F
 from .data_loader import load_data
-from .iterative_inference import DAE_DICT_DEFAULTS, _EPSILON, build_networks
+import argparse
+import os
+
+from .iterative_inference import DAE_DICT_DEFAULTS, _EPSILON, _flag, _literal_dict, build_networks
 
 STEPS = [.01, .02, .05, .08, .1, .5, 1.]      # iterative_inference_valid.py:373
 
 
 def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, which_set='val', data_iter=None,
           fcn_params=None, dae_params=None, weights_path=None, loadpath=None, verbose=True,
-          precision='bf16'):
+          precision='bf16', savepath=None):
     """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter])."""
     dae_dict = dict(DAE_DICT_DEFAULTS)
     dae_dict.update(dae_dict_updates)
@@ -46,6 +49,10 @@ def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, whic
                 for cm in cms:                                         # per image: val_fn(y_im, t_im) of the reference
                     if cm.sum() > 0:
                         valid_mats[si, :, :, it] += F.jaccard_from_cm(cm)
+    if savepath is not None:                       # the reference writes one `iterations<step>.npz` per step value (:303)
+        os.makedirs(savepath, exist_ok=True)
+        for si, s in enumerate(steps):
+            np.savez(os.path.join(savepath, 'iterations' + str(s) + '.npz'), valid_mats[si])
     with np.errstate(divide='ignore', invalid='ignore'):
         all_results = np.nanmean(valid_mats[:, 0] / valid_mats[:, 1], axis=1)
     if verbose:
@@ -63,3 +70,36 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
     `res = nanmean(valid_mat[0] / valid_mat[1], axis=0)` (`:297`)."""
     res, _ = sweep(dataset, segm_net, [learn_step], num_iter, dae_dict_updates, which_set, loadpath=loadpath, **kw)
     return res[0]
+
+
+def main():
+    """The reference's CLI (iterative_inference_valid.py:312-394): same flags and defaults; the seven step values are swept in
+    ONE job (networks built once, h / y0 of a batch shared by all steps) instead of seven rebuilds."""
+    parser = argparse.ArgumentParser(description='Iterative inference.')
+    parser.add_argument('-dataset', type=str, default='camvid', help='Dataset.')
+    parser.add_argument('-segmentation_net', type=str, default='fcn8', help='Segmentation network.')
+    parser.add_argument('-step', type=float, default=0.05, help='step (ignored: the sweep covers STEPS, like the reference)')
+    parser.add_argument('--num_iter', '-ne', type=int, default=50, help='Max number of iterations')
+    parser.add_argument('-which_set', type=str, default='val', help='Inference set')
+    parser.add_argument('-dae_dict', type=_literal_dict,
+                        default={'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0.5,
+                                 'concat_h': ['pool4'], 'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1,
+                                 'additional_pool': 2, 'path_weights': '', 'layer': 'probs_dimshuffle',
+                                 'exp_name': 'flip_final_', 'bn': 0}, help='DAE kind and parameters')
+    parser.add_argument('-training_dict', type=_literal_dict,
+                        default={'training_loss': ['crossentropy', 'squared_error'], 'learning_rate': 0.001, 'lr_anneal': 0.99,
+                                 'weight_decay': 0.0001, 'optimizer': 'rmsprop'}, help='Training parameters')
+    parser.add_argument('-full_im_ft', type=_flag, default=False)
+    parser.add_argument('-ae_h', type=_flag, default=False)
+    parser.add_argument('-data_augmentation', type=_flag, default=True)
+    parser.add_argument('-test_from_0_255', type=_flag, default=False)
+    parser.add_argument('-savepath', type=str, default='./iiseg_out/')
+    parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
+    parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
+    args = parser.parse_args()
+    sweep(args.dataset, args.segmentation_net, STEPS, int(args.num_iter), args.dae_dict, args.which_set,
+          weights_path=args.weights_path, loadpath=args.loadpath, savepath=args.savepath)
+
+
+if __name__ == '__main__':
+    main()

@@ -186,3 +186,19 @@ def test_product_path_has_no_cpu_fallback():
     x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16)
     with pytest.raises((AssertionError, RuntimeError, ValueError, TypeError)):
         K.maxpool2(x, True)
+
+
+def test_cli_accepts_the_reference_flags(monkeypatch):
+    """Every flag of the reference's CLI (iterative_inference.py:329-394) parses and reaches inference()."""
+    import sys
+    from iterative_inference_segm_b200 import iterative_inference as II
+    seen = {}
+    monkeypatch.setattr(II, 'inference', lambda *a, **k: seen.update(args=a, kw=k))
+    monkeypatch.setattr(sys, 'argv', ['iterative_inference.py', '-dataset', 'camvid', '-segmentation_net', 'fcn8', '-step', '0.05',
+                                      '-ne', '50', '-which_set', 'val', '-dae_dict', "{'kind': 'standard', 'noise': 0}",
+                                      '-training_dict', "{'optimizer': 'rmsprop'}", '-full_im_ft', 'False', '-ae_h', 'False',
+                                      '-data_augmentation', 'True', '-test_from_0_255', 'False'])
+    II.main()
+    assert seen['args'] == ('camvid', 'fcn8', 0.05, 50)
+    assert seen['kw']['which_set'] == 'val' and seen['kw']['dae_dict_updates'] == {'kind': 'standard', 'noise': 0}
+    assert seen['kw']['full_im_ft'] is False and seen['kw']['data_augmentation'] is True
