@@ -70,6 +70,40 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
     return fcn, dae
 
 
+class _BatchStager(object):
+    """Host -> device staging of (X, L) batches: two pinned buffers per tensor and a copy stream, so that the next batch
+    is fetched from the iterator and copied while the current batch's loop runs on the device (the reference's iterator
+    prefetches with threads, data_loader.py:58)."""
+
+    def __init__(self, data_iter, n_batches, device):
+        self.it, self.n, self.dev = data_iter, n_batches, device
+        self.stream = torch.cuda.Stream(device=device)
+        self.pinned = [{}, {}]
+        self.k = 0
+
+    def _stage(self, slot, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        buf = self.pinned[slot].get(name)
+        if buf is None or tuple(buf.shape) != arr.shape:
+            buf = self.pinned[slot][name] = torch.empty(arr.shape, dtype=torch.float32).pin_memory()
+        buf.copy_(torch.from_numpy(arr))
+        with torch.cuda.stream(self.stream):
+            return buf.to(self.dev, non_blocking=True)
+
+    def fetch(self):
+        """Next (X, L, Xd, Ld, ready_event) or None; the device tensors are valid after `ready_event`."""
+        if self.k >= self.n:
+            return None
+        slot = self.k % 2
+        self.k += 1
+        X, L = self.it.next()
+        self.stream.synchronize()                 # the pinned buffers of this slot were last used two fetches ago
+        Xd, Ld = self._stage(slot, 'X', X), self._stage(slot, 'L', L)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return X, L, Xd, Ld, ev
+
+
 def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
               data_augmentation=False, which_set='test', ae_h=False, full_im_ft=False, savepath=None,
               loadpath=None, test_from_0_255=False, data_iter=None, fcn_params=None, dae_params=None,
@@ -105,10 +139,13 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
     cm_total = np.zeros((n_classes, n_classes), np.int64)
     say = print if verbose else (lambda *a, **k: None)
     say('Inference step: ' + str(learn_step) + ' num iter ' + str(num_iter))
+    stager = _BatchStager(data_iter, n_batches_test, torch.device('cuda', torch.cuda.current_device()))
+    nxt = stager.fetch()
     for i in range(n_batches_test):
-        X, L = data_iter.next()
-        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
-        Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
+        X, L, Xd, Ld, ready = nxt
+        torch.cuda.current_stream().wait_event(ready)
+        Xd.record_stream(torch.cuda.current_stream()); Ld.record_stream(torch.cuda.current_stream())
+        nxt = None
         pred = pred_fcn_fn(Xd)
         Y, H = pred[-1], pred[:-1]
 
@@ -120,6 +157,7 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
 
         if fused:
             res = loop.run(H[0], Y, learn_step, num_iter, eps=_EPSILON, onehot=Ld)
+            nxt = stager.fetch()                  # the loop is queued: fetch + copy the next batch under it
             Y_ii = res['y']
             n_exec_all += res['n_exec'].cpu().tolist()
             cm = res['cm'].sum(0).cpu().numpy().reshape(n_classes, n_classes)
@@ -145,6 +183,8 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
             Y_ii = torch.cat(outs, dim=0)
             acc, jacc, rec = val_fn(Y_ii, Ld)
             cm = np.zeros_like(cm_total)
+        if nxt is None:
+            nxt = stager.fetch()
         cm_total += cm
         tot['acc'] += acc; tot['jacc'] = tot['jacc'] + jacc; tot['rec'] += rec
         if verbose:
