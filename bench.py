@@ -112,7 +112,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,enforced.power.limit')
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw.instant,enforced.power.limit')
 
     def __init__(self, index):
         self.index = index
@@ -148,10 +148,11 @@ class ClockSampler(object):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
         out = {'sm_mhz': mhz[len(mhz) // 2] if mhz else None, 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
                'reasons': reasons, 'samples': len(self.samples)}
-        try:        # board power under load against its enforced limit (explains sw_power_cap)
+        try:        # instantaneous board power under load against its enforced limit (explains sw_power_cap)
             watts = sorted(float(s[6]) for s in self.samples if len(s) >= 8)
             if watts:
                 out['power_w'] = watts[len(watts) // 2]
+                out['power_max_w'] = watts[-1]
                 out['power_limit_w'] = float(self.samples[0][7])
         except ValueError:
             pass
