@@ -120,12 +120,19 @@ class ClockSampler(object):
         self._stop = threading.Event()
         self._thr = threading.Thread(target=self._run, daemon=True)
 
+    def _query(self, fields):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + fields,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        return [p.strip() for p in out.strip().split(',')]
+
     def _run(self):
+        fields = self.QUERY
         while not self._stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
+                parts = self._query(fields)
+                if len(parts) < 8 and fields is self.QUERY:      # a driver without the power fields: clocks and reasons only
+                    fields = ','.join(self.QUERY.split(',')[:6])
+                    parts = self._query(fields)
                 if len(parts) >= 6:
                     self.samples.append(parts)
             except Exception:
