@@ -202,3 +202,20 @@ def test_cli_accepts_the_reference_flags(monkeypatch):
     assert seen['args'] == ('camvid', 'fcn8', 0.05, 50)
     assert seen['kw']['which_set'] == 'val' and seen['kw']['dae_dict_updates'] == {'kind': 'standard', 'noise': 0}
     assert seen['kw']['full_im_ft'] is False and seen['kw']['data_augmentation'] is True
+
+
+def test_bench_clock_sampler_summary():
+    """bench.ClockSampler: median SM clock, throttle reasons, instantaneous power (when the driver reports it)."""
+    import bench
+    cs = bench.ClockSampler(0)
+    cs.samples = [['1710', '1965', 'Not Active', 'Not Active', 'Not Active', 'Active', '995.1', '1000.00'],
+                  ['1725', '1965', 'Not Active', 'Not Active', 'Not Active', 'Active', '988.0', '1000.00'],
+                  ['1717', '1965', 'Not Active', 'Not Active', 'Not Active', 'Not Active', '640.2', '1000.00']]
+    out = cs.summary()
+    assert out['sm_mhz'] == 1717 and out['sm_max_mhz'] == 1965 and out['reasons'] == ['sw_power_cap'] and out['samples'] == 3
+    assert out['power_w'] == 988.0 and out['power_max_w'] == 995.1 and out['power_limit_w'] == 1000.0
+    cs.samples = [['1965', '1965', 'Not Active', 'Not Active', 'Not Active', 'Not Active']]      # driver without power fields
+    out = cs.summary()
+    assert out['sm_mhz'] == 1965 and out['reasons'] == [] and 'power_w' not in out
+    cs.samples = []
+    assert cs.summary()['reasons'] == ['unsampled']
