@@ -26,22 +26,41 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu into one shared library; skipped when sources are unchanged."""
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _fresh(dig):
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
-            if fh.read().strip() == dig:
+            return fh.read().strip() == dig
+    return False
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu into one shared library; skipped when sources are unchanged.  Safe under `torchrun`: the ranks
+    of a node serialise on a file lock, the first one compiles (into a temporary file, renamed atomically), the others
+    find the fresh stamp."""
+    import fcntl
+    dig = _digest()
+    if not force and _fresh(dig):
+        return LIB
+    with open(os.path.join(HERE, '.libiiseg.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _fresh(dig):
                 return LIB
-    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB] + [os.path.join(HERE, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed (exit %d)' % res.returncode)
-    with open(STAMP, 'w') as fh:
-        fh.write(dig)
+            nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+            tmp = LIB + '.tmp.%d' % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ['-o', tmp] + [os.path.join(HERE, s) for s in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed (exit %d)' % res.returncode)
+            os.replace(tmp, LIB)
+            with open(STAMP, 'w') as fh:
+                fh.write(dig)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
