@@ -8,14 +8,25 @@ confusion-matrix / Jaccard reduction.  Every rank processes its own batch (image
 scaling); the only collective is the all-reduce of the int64 confusion matrix.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config 2|3|4] [--precision mixed|bf16|fp32x3] [--scaling weak|strong] [--sections a,b,..]
+
+The headline (`value`, `e2e`, `roofline`) is the PARITY-GRADE arithmetic, precision='mixed': fp32-accurate convs
+(bf16 hi/lo operand pairs, three tensor-core products) in FCN8 and on the DAE's contracting path, bf16 on the
+expanding path -- the variant the -m gpu tests hold to BASELINE.json's fp32 bar (2e-3 max-abs per iteration,
+>= 99.9 % argmax agreement, confusion matrix bit-exact given the labels).  The all-bf16 throughput variant, with
+its own stated tolerance, is measured in the same run and reported as `bf16_variant`.
 
 `value`  : whole-job images/s with the batch already resident in HBM.
 `e2e`    : the same through the public callables with HOST (pinned) buffers: H2D of the images and
            the one-hot targets and D2H of the metrics inside the timed region, every step (the copies
            of step i+1 ride a copy stream under step i's kernels, as with a prefetching iterator).
-`roofline`: the tcgen05 conv kernel (all conv launches of one DAE application), CUDA-event timed.
+`roofline`: the dominant kernel, conv_igemm_pair_kernel (tcgen05 cta_group::2), CUDA-event timed.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the reference path (oracle/, PyTorch
            CPU fp32; Theano is not installable) on the host cores, on a bounded sample.
+Other BASELINE.json configs ride the same line as sub-records measured in the same run:
+`config3` (FC-DenseNet103 + DAE_h), `config4` (train_dae.py step, data-parallel over the N ranks with the
+gradient all-reduce), `steps_sweep` (config 5: iterations 1..100); `--config 3|4` makes one of them the headline.
+`--scaling strong`: a fixed set of 80 images (8 batches) is sharded over the ranks (sharding.shard_range).
 """
 import argparse
 import json
@@ -29,9 +40,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NCLS, H, W, BATCH, N_ITER, STEP = 11, 360, 480, 10, 50, 0.05
+TH, TW = 224, 224                    # config 4: train_dae.py crop
 LOGIT_GAIN, OUT_GAIN = 10.0, 0.1
+STRONG_SET = 80                      # --scaling strong: images in the fixed set
 METRIC = 'images/sec, N-step FCN8+DAE iterative inference 360x480'
 WORKLOAD = 'FCN8 + DAE_h (n_filters=64, concat_h=pool4, trackind unpool), batch 10 x 360x480, 11 classes, 50 steps, step 0.05, metrics.py Jaccard'
+WORKLOAD3 = 'FC-DenseNet103 + DAE_h (concat_h=pool4, padding 0), batch 10 x 360x480, 11 classes, 50 steps, step 0.05, metrics.py Jaccard'
+WORKLOAD4 = 'train_dae.py DAE step (rmsprop lr 1e-3, crossentropy + squared_error, noise 0.5, both noise passes), batch 10 x 224x224 per GPU, data-parallel gradient all-reduce'
+WEIGHTS = 'random init (He-uniform FCN8 x logit gain 10, Glorot DAE x out gain 0.1)'
+DTYPES = {'bf16': 'bf16',
+          'fp32x3': 'fp32 operands as bf16 hi/lo pairs, 3 tensor-core products, fp32 accumulate',
+          'mixed': 'fp32-accurate (bf16 hi/lo pairs x 3 tensor-core products, fp32 accumulate) in FCN8 and the DAE contracting path; bf16 operands / fp32 accumulate on the DAE expanding path'}
+PARITY = {'mixed': 'tests/test_path_gpu.py: per-iteration y within 2e-3 max-abs, argmax agreement >= 99.9 %, vs the CPU oracle (full size: test_full_size_end_to_end_vs_oracle); confusion matrix bit-exact given the labels',
+          'fp32x3': 'tests/test_path_gpu.py: per-iteration y within 2e-3 max-abs, argmax agreement >= 99.9 %, vs the CPU oracle; confusion matrix bit-exact given the labels',
+          'bf16': 'own tolerance (tests/test_path_gpu.py::test_full_size_end_to_end_vs_oracle): bf16 rounding flips pool-mask ties, so per-iteration y is only within the stated bf16 bound of the oracle; confusion matrix bit-exact given the labels'}
 
 
 def load_peaks():
@@ -80,33 +102,90 @@ def cpu_reference_sample(n_dae_iters=CPU_SAMPLE_ITERS):
 
 
 cpu_reference_sample.state = None
+
+
 def cpu_sample_text(n):
     return ('1 image 360x480: FCN8 forward + %d of the 50 DAE iterations + metrics timed with the PyTorch-CPU '
             'oracle (port of the Theano path), per-image time extrapolated linearly to 50 iterations' % n)
+
+
+def cpu_reference_sample_config3(n_dae_iters=5):
+    """config 3 on the host cores: FC-DenseNet103 forward on one batch-2 sample is avoided (batch-stat BN couples the
+    batch): 1 image 360x480 through the oracle DenseNet + n of the 50 DAE iterations (padding 0)."""
+    import torch
+    from oracle import nets, weights, densenet, metrics as M
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    X, L, _ = weights.synthetic_batch(1, H, W, NCLS, seed=0)
+    pn = densenet.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0)
+    pd = weights.synthetic_dae_params(NCLS, 464, seed=1, out_gain=OUT_GAIN)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        h, y = densenet.densenet_forward(pn, X, NCLS, layer=('pool4',))
+        t1 = time.perf_counter()
+        for _ in range(n_dae_iters):
+            p = nets.dae_forward(pd, y, h, 0)
+            y = torch.clamp(y - STEP * (y - p), 0.0, 1.0)
+        t2 = time.perf_counter()
+        M.val_fn(y.numpy(), L.numpy(), NCLS, [NCLS])
+        t3 = time.perf_counter()
+    return (t1 - t0) + (t2 - t1) / n_dae_iters * N_ITER + (t3 - t2), cores
+
+
+def cpu_reference_sample_config4(n_images=2):
+    """config 4 on the host cores: one oracle train step (autograd, rmsprop) on `n_images` 224x224 crops; returns s / image."""
+    import torch
+    from oracle import weights, train as OT
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    X, L, _ = weights.synthetic_batch(n_images, TH, TW, NCLS, seed=5)
+    pd = [p.clone() for p in weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=OUT_GAIN)]
+    accus = [torch.zeros_like(p) for p in pd]
+    y = L[:, :NCLS].contiguous()
+    hs = (((TH + 198) // 2 // 2 // 2) // 2, ((TW + 198) // 2 // 2 // 2) // 2)
+    gen = torch.Generator().manual_seed(3)
+    h = torch.relu(torch.randn((n_images, 512) + hs, generator=gen))
+    nm, nk = torch.randn(y.shape, generator=gen) * 0.5, torch.randn(y.shape, generator=gen) * 0.5
+    t0 = time.perf_counter()
+    OT.train_step(pd, accus, y, h, L, NCLS, 100, 1e-3, noise_main=nm, noise_mask=nk)
+    return (time.perf_counter() - t0) / n_images, cores
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if args.config == 3:
+        sample = lambda: cpu_reference_sample_config3()[0]           # noqa: E731
+        text, workload, batch = ('1 image 360x480: oracle FC-DenseNet103 forward + 5 of the 50 DAE iterations + metrics, '
+                                 'extrapolated linearly to 50 iterations'), WORKLOAD3, BATCH
+    elif args.config == 4:
+        sample = lambda: cpu_reference_sample_config4()[0]           # noqa: E731
+        text, workload, batch = '2 images 224x224: one oracle train step (autograd + rmsprop), time per image', WORKLOAD4, BATCH
+    else:
+        sample = lambda: cpu_reference_sample()[0]                   # noqa: E731
+        text, workload, batch = cpu_sample_text(CPU_SAMPLE_ITERS), WORKLOAD, BATCH
     for _ in range(args.warmup):
-        cpu_reference_sample()
-    times = []
-    for _ in range(args.steps):
-        t_img, cores, parts = cpu_reference_sample()
-        times.append(t_img)
+        sample()
+    times = [sample() for _ in range(args.steps)]
+    cores = len(os.sched_getaffinity(0))
     t = sum(times) / len(times)
     val = 1.0 / t
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * BATCH * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'weights': 'random init (He-uniform FCN8 x logit gain 10, Glorot DAE x out gain 0.1)'},
-        'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': cpu_sample_text(CPU_SAMPLE_ITERS)},
+        'impl': 'reference', 'metric': METRIC if args.config == 2 else metric_name(args.config), 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * batch * 1e3, 'higher_is_better': True,
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload, 'weights': WEIGHTS},
+        'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': text},
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def metric_name(config):
+    return {2: METRIC, 3: 'images/sec, N-step FC-DenseNet103+DAE iterative inference 360x480',
+            4: 'images/sec, train_dae.py DAE train step 224x224 (data-parallel)'}[config]
 
 
 # --------------------------------------------------------------------------- clocks
@@ -167,210 +246,375 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- B200 arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from iterative_inference_segm_b200.csrc.build import build
-    build()
-    from iterative_inference_segm_b200 import _lib
-    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
-    from iterative_inference_segm_b200.models.DAE_h import buildDAE
-    from iterative_inference_segm_b200.functions import IterativeInference, jaccard_from_cm
-    from iterative_inference_segm_b200.profiling import KernelTimer
-    from iterative_inference_segm_b200 import synthetic as weights     # synthetic weight / data recipe
+class Ctx(object):
+    """Process-wide state of the B200 arm: rank / world, device, timing helpers."""
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    peaks = load_peaks()
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.peaks = load_peaks()
 
-    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN)
-    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=OUT_GAIN)
-    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf, precision=args.precision)
-    dae = buildDAE([None], None, NCLS, nb_features_to_concat=fcn[0].output_shape[1], padding=100, concat_h=['pool4'],
-                   noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
-                   params=pd, precision=args.precision)
-    del pf, pd
-    ii = IterativeInference(dae, NCLS, [NCLS])
-    fnet = fcn[0].net
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    # rank r holds images [r*BATCH, (r+1)*BATCH) of the synthetic set
-    X, L, lab = weights.synthetic_batch(BATCH, H, W, NCLS, seed=100 + rank)
-    X_host, L_host = X.pin_memory(), L.pin_memory()
-    X_dev, L_dev = X_host.to(dev), L_host.to(dev)
-    cm_total = torch.zeros(NCLS * NCLS + 2, dtype=torch.int64, device=dev)
-
-    def step_device(Xd, Ld):
-        out = fnet.forward(Xd, want=('pool4', 'probs_dimshuffle'))
-        res = ii.run(out['pool4'], out['probs_dimshuffle'], STEP, N_ITER, onehot=Ld)
-        cm_total[:NCLS * NCLS] = res['cm'].sum(0)
-        cm_total[NCLS * NCLS:] = res['counts'].sum(0)
-        if world > 1:
-            dist.all_reduce(cm_total)
-        return res
-
-    # End to end: every step copies its own inputs from pinned host memory and reads its result back.  The copies
-    # of step i+1 are issued on a copy stream before step i's kernels (two device buffers, like a prefetching data
-    # iterator), so only the first step's H2D is exposed; the D2H read of the result blocks the host every step.
-    copy_stream = torch.cuda.Stream(device=dev)
-    in_bufs = [(torch.empty_like(X_dev), torch.empty_like(L_dev)) for _ in range(2)]
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-
-    def issue_h2d(i):
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[b])
-            in_bufs[b][0].copy_(X_host, non_blocking=True)
-            in_bufs[b][1].copy_(L_host, non_blocking=True)
-            ev_ready[b].record(copy_stream)
-
-    def run_e2e(n):
-        cur = torch.cuda.current_stream()
-        for b in range(2):
-            ev_free[b].record(cur)
-        issue_h2d(0)
-        out = None
-        for i in range(n):
-            if i + 1 < n:
-                issue_h2d(i + 1)
-            b = i % 2
-            cur.wait_event(ev_ready[b])
-            res = step_device(*in_bufs[b])
-            ev_free[b].record(cur)
-            out = (cm_total.cpu(), res['n_exec'].cpu())
-        return out
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, n):
-        barrier()
+    def timed(self, fn, n):
+        """Barrier + synchronize on both sides, CUDA events on the launching stream, MAX over ranks -> (ms, wall ms)."""
+        torch = self.torch
+        self.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         s.record()
         for _ in range(n):
             fn()
         e.record()
-        barrier()
+        self.barrier()
         wall = time.perf_counter() - t0
-        ms = torch.tensor([s.elapsed_time(e), wall * 1e3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = torch.tensor([s.elapsed_time(e), wall * 1e3], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms[0]), float(ms[1])
+
+
+def build_inference(ctx, precision, segm='fcn8'):
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.models.FCDenseNet import build_fcdensenet
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import IterativeInference
+    from iterative_inference_segm_b200 import synthetic as weights
+    if segm == 'fcn8':
+        fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'],
+                        params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
+        nb_h, padding = fcn[0].output_shape[1], 100
+    else:
+        fcn = build_fcdensenet(None, ['pool4'], 3, NCLS, params=weights.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0))
+        nb_h, padding = 464, 0
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=nb_h, padding=padding, concat_h=['pool4'],
+                   noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
+                   params=weights.synthetic_dae_params(NCLS, nb_h, seed=1, out_gain=OUT_GAIN), precision=precision)
+    return fcn, dae, IterativeInference(dae, NCLS, [NCLS])
+
+
+def measure_inference(ctx, precision, segm='fcn8', n_iter=N_ITER, with_e2e=True, clocks=False, strong=False):
+    """Times the step (FCN forward + n_iter loop iterations + metrics + the confusion-matrix all-reduce) on this rank's
+    batches.  Returns (record, objects for the roofline leg)."""
+    torch, dist, args = ctx.torch, ctx.dist, ctx.args
+    from iterative_inference_segm_b200 import _lib
+    from iterative_inference_segm_b200 import synthetic as weights
+    from iterative_inference_segm_b200.sharding import shard_range, allreduce_metrics
+    fcn, dae, ii = build_inference(ctx, precision, segm)
+    fnet = fcn[0].net
+    hkey = 'pool4' if segm == 'fcn8' else 'pool4_bf16'
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    if strong:       # a fixed set of STRONG_SET images = batches of 10; rank r owns batches [lo, hi)
+        lo, hi = shard_range(STRONG_SET // BATCH, rank, world)
+        my_batches = list(range(lo, hi))
+    else:            # rank r holds images [r*BATCH, (r+1)*BATCH) of the synthetic set
+        my_batches = [rank]
+    hosts = []
+    for b in my_batches:
+        X, L, _ = weights.synthetic_batch(BATCH, H, W, NCLS, seed=100 + b)
+        hosts.append((X.pin_memory(), L.pin_memory()))
+    devs = [(X.to(dev), L.to(dev)) for X, L in hosts]
+    cm_total = torch.zeros(NCLS * NCLS, dtype=torch.int64, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def batch_device(Xd, Ld):
+        out = fnet.forward(Xd, want=('pool4', 'probs_dimshuffle'))
+        res = ii.run(out[hkey], out['probs_dimshuffle'], STEP, n_iter, onehot=Ld)
+        cm_total.add_(res['cm'].sum(0))
+        counts.add_(res['counts'].sum(0))
+        return res
+
+    def step_device():
+        cm_total.zero_(); counts.zero_()
+        res = None
+        for Xd, Ld in devs:
+            res = batch_device(Xd, Ld)
+        allreduce_metrics(cm_total, counts)          # the one collective of the inference path (sharding.py)
+        return res
+
+    # End to end: every step copies its own inputs from pinned host memory and reads its result back.  The copies
+    # of batch i+1 are issued on a copy stream before batch i's kernels (two device buffers, like a prefetching data
+    # iterator), so only the first batch's H2D is exposed; the D2H read of the result blocks the host every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    in_bufs = [(torch.empty_like(devs[0][0]), torch.empty_like(devs[0][1])) for _ in range(2)]
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_h2d(i):
+        b = i % 2
+        Xh, Lh = hosts[i % len(hosts)]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])
+            in_bufs[b][0].copy_(Xh, non_blocking=True)
+            in_bufs[b][1].copy_(Lh, non_blocking=True)
+            ev_ready[b].record(copy_stream)
+
+    def run_e2e(n_steps):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            ev_free[b].record(cur)
+        n = n_steps * len(hosts)
+        issue_h2d(0)
+        out = None
+        for i in range(n):
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            b = i % 2
+            if i % len(hosts) == 0:
+                cm_total.zero_(); counts.zero_()
+            cur.wait_event(ev_ready[b])
+            res = batch_device(*in_bufs[b])
+            ev_free[b].record(cur)
+            if (i + 1) % len(hosts) == 0:
+                allreduce_metrics(cm_total, counts)
+                out = (cm_total.cpu(), counts.cpu(), res['n_exec'].cpu())      # the step's result leaves the device
+        return out
 
     # ---- warm-up (also captures the CUDA graph) + launch census
     l0 = _lib.launch_count()
-    res = step_device(X_dev, L_dev)
+    res = step_device()
     torch.cuda.synchronize()
     census_first = _lib.launch_count() - l0
     for _ in range(max(args.warmup - 1, 0)):
-        res = step_device(X_dev, L_dev)
+        res = step_device()
     torch.cuda.synchronize()
     n_exec = res['n_exec'].cpu().tolist()
-    assert all(n == N_ITER for n in n_exec), 'early exit in the benchmark: %s' % n_exec
-    # launches per step: eager FCN8 + boundary launches are counted live; the loop is a graph replay
+    assert all(n == n_iter for n in n_exec), 'early exit in the benchmark: %s' % n_exec
     l1 = _lib.launch_count()
-    step_device(X_dev, L_dev)
+    step_device()
     torch.cuda.synchronize()
     eager_per_step = _lib.launch_count() - l1
-    launches_per_step = eager_per_step + ii.graph_kernel_nodes     # eager FCN8/boundary launches + graph kernel nodes
+    # eager FCN / boundary launches are counted live; the loop is a graph replay of graph_kernel_nodes library kernels
+    launches_per_step = eager_per_step + ii.graph_kernel_nodes * len(devs)
 
-    # ---- timed region: device-resident inputs
-    with ClockSampler(local) as clk:
-        ms_dev, _ = timed(lambda: step_device(X_dev, L_dev), args.steps)
-    clocks = clk.summary()
-    # ---- timed region: end to end through host buffers (pinned), H2D + D2H inside
-    run_e2e(2)
-    ms_e2e, wall_e2e = timed(lambda: run_e2e(args.steps), 1)
-    ms_e2e = max(ms_e2e, wall_e2e)     # D2H reads block the host: wall clock covers them
+    clk = None
+    if clocks:
+        with ClockSampler(ctx.local) as cs:
+            ms_dev, _ = ctx.timed(step_device, args.steps)
+        clk = cs.summary()
+    else:
+        ms_dev, _ = ctx.timed(step_device, args.steps)
+    imgs = BATCH * (STRONG_SET // BATCH if strong else world) * args.steps
+    rec = {'precision': precision, 'value': imgs / (ms_dev * 1e-3), 'ms_per_step': ms_dev / args.steps,
+           'executed_iterations': n_exec[0], 'launches_per_step': int(launches_per_step), 'census_first': int(census_first),
+           'clocks': clk, 'batches_per_rank_step': len(devs)}
+    if with_e2e:
+        run_e2e(1)
+        ms_e2e, wall_e2e = ctx.timed(lambda: run_e2e(args.steps), 1)
+        ms_e2e = max(ms_e2e, wall_e2e)     # D2H reads block the host: wall clock covers them
+        Xh, Lh = hosts[0]
+        rec['e2e'] = {'value': imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
+                      'h2d_bytes_per_step': int((Xh.numel() + Lh.numel()) * 4 * len(hosts)),
+                      'd2h_bytes_per_step': int(cm_total.numel() * 8 + counts.numel() * 8 + BATCH * 4), 'ms_per_step': ms_e2e / args.steps}
+    rec['cm'] = cm_total.cpu().numpy()
+    return rec, (fcn, dae, ii)
 
-    imgs = BATCH * world * args.steps
-    value = imgs / (ms_dev * 1e-3)
-    e2e_value = imgs / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel: every conv launch of one DAE application, event-timed eagerly
-    roof, breakdown = None, None
-    cpu_base = None
-    if rank == 0 and args.precision == 'bf16':
-        st = ii._buffers(BATCH, H, W, N_ITER, False)
-        timer = KernelTimer()
-        reps = 3
-        upd = dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=STEP)   # as in the captured loop
-        st['active'].fill_(1)
-        dae.net.logits(st['h'], st['y_bf16'], full_down=True, update=upd)      # fills the iteration-invariant borders
-        with timer.recording():
-            for _ in range(reps + 1):
-                dae.net.logits(st['h'], st['y_bf16'], full_down=False, update=upd)  # the steady-state application (49 of 50)
-        summ = timer.summary()
-        fl = dae.net.executed_conv_flops(H, W, steady_state=True)               # executed FLOPs only, per image
-        convs = [(tag, sum(v[1:]) / len(v[1:])) for (name, tag), v in summ.items() if name == 'conv2d']   # launch order; drop the cold rep
-        assert len(convs) == len(fl)
-        conv_total_ms = sum(ms for _, ms in convs)
-        other = {}
-        for (name, tag), v in summ.items():
-            other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
-        # dominant kernel: conv_igemm_pair_kernel<256> (per-tap implicit GEMM, 256 x 256 tiles over CTA pairs): the launches the
-        # library reports as kernel 1 (CTA pair) with BN = 256 (tag[-1] = iiseg_last_conv_plan of that launch)
-        dom = [(f, ms) for f, (tag, ms) in zip(fl, convs) if tag[-1][0] == 1 and tag[-1][1] == 256]
-        dom_flops, dom_ms = sum(f for f, _ in dom) * BATCH, sum(ms for _, ms in dom)
-        achieved = dom_flops / (dom_ms * 1e-3) / 1e12
-        peak = peaks['bf16_tflops_sustained']
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get('conv_igemm_pair_kernel<256>', {}).get('dram_bytes_per_launch')
-        roof = {'bound': 'tensor', 'kernel': 'conv_igemm_pair_kernel<256> (tcgen05 cta_group::2 implicit GEMM, 256 x 256 tiles over CTA pairs; %d of the 12 conv launches of one steady-state DAE application, batch 10: conv3_1, conv4_1, conv6_1, up_conv6..up_conv4 -- conv5_1 runs the same kernel with 128-wide tiles; executed FLOPs on the y-dependent / crop-dependent windows)' % len(dom),
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
-                'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': dom_ms / len(dom),
-                'flops_per_launch': dom_flops / len(dom),
-                'all_12_conv_launches': {'achieved': sum(fl) * BATCH / (conv_total_ms * 1e-3) / 1e12, 'ms': conv_total_ms,
-                                         'flops_per_application': sum(fl) * BATCH,
-                                         'note': 'includes the 16-channel first layer, the fused 2x2 pool + tie mask epilogues and the fused softmax/update epilogue of up_conv1'}}
-        unpool_b = 0.0
-        for (name, tag), v in summ.items():
-            if name == 'unpool2':       # algorithmic bytes: out written once, the touched u / mask windows read once
-                (n, uh, uw, c), (_, oh, ow, _) = tag
-                unpool_b += n * oh * ow * c * 2 + n * ((oh + 1) // 2 + 1) * ((ow + 1) // 2 + 1) * c * 2.5
-        breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
-                     'conv_ms_in_launch_order': [round(ms, 4) for _, ms in convs],
-                     'conv_tflops_in_launch_order': [round(f * BATCH / (ms * 1e-3) / 1e12, 1) for f, (_, ms) in zip(fl, convs)],
-                     'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
-                     'hbm_peak_gbs': peaks['hbm_gbs'],
-                     'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues; softmax + y update + norm into up_conv1'}
-        if world == 1 and not args.no_cpu_baseline:
+def roofline_leg(ctx, dae, ii, precision):
+    """Every conv launch of one steady-state DAE application (the 49 of 50), event-timed eagerly on the launching
+    stream; the dominant kernel is the CTA-pair implicit GEMM."""
+    torch = ctx.torch
+    from iterative_inference_segm_b200.profiling import KernelTimer
+    peaks = ctx.peaks
+    st = ii._buffers(BATCH, H, W, N_ITER, False)
+    timer = KernelTimer()
+    reps = 3
+    upd = None if dae.net.split_up else dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=STEP)   # as in the captured loop
+    st['active'].fill_(1)
+    dae.net.logits(st['h'], st['y_bf16'], full_down=True, update=upd)      # fills the iteration-invariant borders
+    with timer.recording():
+        for _ in range(reps + 1):
+            dae.net.logits(st['h'], st['y_bf16'], full_down=False, update=upd)  # the steady-state application
+    summ = timer.summary()
+    fl = dae.net.executed_conv_flops(H, W, steady_state=True)               # fp32-conv (algorithmic) FLOPs, per image
+    flt = dae.net.executed_conv_flops(H, W, steady_state=True, tensor=True)  # FLOPs the tensor cores execute
+    convs = [(tag, sum(v[1:]) / len(v[1:])) for (name, tag), v in summ.items() if name == 'conv2d']   # launch order; drop the cold rep
+    assert len(convs) == len(fl)
+    conv_total_ms = sum(ms for _, ms in convs)
+    other = {}
+    for (name, tag), v in summ.items():
+        other[name] = other.get(name, 0.0) + sum(v[1:]) / len(v[1:])
+    # dominant kernel: the launches the library reports as kernel 1 (CTA pair) (tag[-1] = iiseg_last_conv_plan)
+    dom = [(f, ft, ms) for f, ft, (tag, ms) in zip(fl, flt, convs) if tag[-1][0] == 1]
+    dom_alg, dom_tensor, dom_ms = sum(d[0] for d in dom) * BATCH, sum(d[1] for d in dom) * BATCH, sum(d[2] for d in dom)
+    achieved = dom_tensor / (dom_ms * 1e-3) / 1e12
+    peak = peaks['bf16_tflops_sustained']
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic = tj.get('conv_igemm_pair_kernel/' + precision, tj.get('conv_igemm_pair_kernel<256>', {})).get('dram_bytes_per_launch')
+    roof = {'bound': 'tensor',
+            'kernel': 'conv_igemm_pair_kernel<256|128> (tcgen05 cta_group::2 implicit GEMM over CTA pairs): %d of the 12 conv launches of one '
+                      'steady-state DAE application, batch 10 (conv2_1..conv6_1, up_conv6..up_conv3 as the plan selects); executed FLOPs on the '
+                      'y-dependent / crop-dependent windows; precision %s' % (len(dom), precision),
+            'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+            'peak_source': peaks['source'] + ' bf16_tflops_sustained', 'launch_ms': dom_ms / len(dom),
+            'flops_per_launch': dom_tensor / len(dom),
+            'flops_note': 'tensor-core FLOPs executed: an fp32-accurate MAC is three bf16 products (hi*hi + lo*hi + hi*lo); '
+                          'fp32-conv (algorithmic) FLOPs of the same launches: %.4g per launch = %.1f TFLOP/s' % (
+                              dom_alg / len(dom), dom_alg / (dom_ms * 1e-3) / 1e12),
+            'all_12_conv_launches': {'achieved': sum(flt) * BATCH / (conv_total_ms * 1e-3) / 1e12, 'ms': conv_total_ms,
+                                     'tensor_flops_per_application': sum(flt) * BATCH, 'fp32_conv_flops_per_application': sum(fl) * BATCH,
+                                     'frac': sum(flt) * BATCH / (conv_total_ms * 1e-3) / 1e12 / peak,
+                                     'note': 'includes the 16-channel first layer, the fused 2x2 pool + tie mask epilogues and the fused softmax/update epilogue of up_conv1'}}
+    unpool_b = 0.0
+    for (name, tag), v in summ.items():
+        if name == 'unpool2':       # algorithmic bytes: out written once, the touched u / mask windows read once
+            (n, uh, uw, c), (_, oh, ow, co) = tag
+            unpool_b += n * oh * ow * co * 2 + n * ((oh + 1) // 2 + 1) * ((ow + 1) // 2 + 1) * co * 2.5
+    breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
+                 'conv_ms_in_launch_order': [round(ms, 4) for _, ms in convs],
+                 'conv_tensor_tflops_in_launch_order': [round(f * BATCH / (ms * 1e-3) / 1e12, 1) for f, (_, ms) in zip(flt, convs)],
+                 'conv_kernel_in_launch_order': ['%s<%d>' % (('per_tap', 'pair', 'halo')[tag[-1][0]], tag[-1][1]) for tag, _ in convs],
+                 'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
+                 'unpool_frac_of_hbm': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                 'hbm_peak_gbs': peaks['hbm_gbs'],
+                 'note': 'max-pool + tie mask are fused into the contracting-path conv epilogues; softmax + y update + norm into up_conv1'}
+    return roof, breakdown
+
+
+def config4_leg(ctx):
+    """train_dae.py step (config 4): rank r trains on its own batch of 10 crops; global loss denominators and the 24
+    gradient matrices are all-reduced over NCCL (sharding.World)."""
+    torch, args = ctx.torch, ctx.args
+    from iterative_inference_segm_b200 import synthetic as S, _kernels as K, _lib
+    from iterative_inference_segm_b200.sharding import World
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    tr = DAETrainer(NCLS, 512, 100, S.synthetic_dae_params(NCLS, 512, seed=1, out_gain=OUT_GAIN), learning_rate=1e-3, noise=0.5)
+    X, L, _ = S.synthetic_batch(BATCH, TH, TW, NCLS, seed=5 + ctx.rank)
+    L = L.to(ctx.dev)
+    y = L[:, :NCLS].contiguous()
+    gen = torch.Generator(device=ctx.dev).manual_seed(3 + ctx.rank)
+    hs = (((TH + 198) // 2 // 2 // 2) // 2, ((TW + 198) // 2 // 2 // 2) // 2)
+    h = K.pack_nchw(torch.relu(torch.randn((BATCH, 512) + hs, device=ctx.dev, generator=gen)), 512)
+    nm = torch.randn(y.shape, device=ctx.dev, generator=gen)
+    nk = torch.randn(y.shape, device=ctx.dev, generator=gen)
+    world = World() if ctx.world > 1 else None
+
+    def step():
+        if world is None:
+            tr.step_graphed(h, y, L, nm, nk)
+        else:
+            tr.step_dp(h, y, L, nm, nk, world)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    tr.step(h, y, L, nm, nk, world=world)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    loss0 = tr.loss_value()
+    n = max(args.steps, 5)
+    ms, _ = ctx.timed(step, n)
+    rec = {'workload': WORKLOAD4, 'value': BATCH * ctx.world * n / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms / n,
+           'steps': n, 'dtype': 'bf16 operands, fp32 accumulate, fp32 master weights', 'launches_per_step': int(launches),
+           'loss': loss0, 'allreduce': None if world is None else tr.dp_info()}
+    return rec
+
+
+def run_b200(args):
+    import numpy as np
+    from iterative_inference_segm_b200.csrc.build import build
+    build()
+    ctx = Ctx(args)
+    torch, dist = ctx.torch, ctx.dist
+    from iterative_inference_segm_b200.functions import jaccard_from_cm
+    rank, world = ctx.rank, ctx.world
+    sections = set(args.sections.split(',')) if args.sections else {'headline', 'bf16', 'roofline', 'cpu', 'config3', 'config4', 'sweep'}
+    strong = args.scaling == 'strong'
+    line = None
+
+    if args.config == 2:
+        rec, (fcn, dae, ii) = measure_inference(ctx, args.precision, clocks=True, strong=strong)
+        jac = jaccard_from_cm(rec['cm'])
+        roof = breakdown = cpu_base = None
+        if rank == 0 and 'roofline' in sections:
+            roof, breakdown = roofline_leg(ctx, dae, ii, args.precision)
+        ctx.barrier()
+        line = {
+            'metric': METRIC, 'value': rec['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': rec['ms_per_step'], 'higher_is_better': True, 'scaling': args.scaling,
+            'vs_baseline': None, 'dtype': DTYPES[args.precision], 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'per_gpu_batch': BATCH, 'global_batch': STRONG_SET if strong else BATCH * world,
+                       'parallelism': ('a fixed set of %d images sharded over %d rank(s) in whole batches of 10' % (STRONG_SET, world)) if strong
+                       else 'image shards, dp%d' % world,
+                       'precision': args.precision, 'parity': PARITY[args.precision], 'weights': WEIGHTS,
+                       'l2': 'working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush',
+                       'executed_iterations': rec['executed_iterations']},
+            'e2e': rec['e2e'], 'gpu_launches': int(rec['launches_per_step'] * args.steps),
+            'clocks': rec['clocks'], 'roofline': roof, 'cpu_baseline': None, 'breakdown': breakdown,
+            'result': {'mean_jaccard': float(np.nanmean(jac[0] / jac[1])), 'first_step_launch_census': rec['census_first']},
+        }
+        del fcn, dae, ii
+        torch.cuda.empty_cache()
+        if 'bf16' in sections and args.precision != 'bf16':
+            rb, (fcn, dae, ii) = measure_inference(ctx, 'bf16', strong=strong)
+            rfb = None
+            if rank == 0 and 'roofline' in sections:
+                rfb, bdb = roofline_leg(ctx, dae, ii, 'bf16')
+                rfb = {'achieved': rfb['achieved'], 'frac': rfb['frac'], 'launch_ms': rfb['launch_ms'], 'all_12_conv_launches': rfb['all_12_conv_launches'],
+                       'conv_ms_in_launch_order': bdb['conv_ms_in_launch_order'], 'conv_tensor_tflops_in_launch_order': bdb['conv_tensor_tflops_in_launch_order'],
+                       'unpool_gbs': bdb['unpool_gbs']}
+            ctx.barrier()
+            line['bf16_variant'] = {'value': rb['value'], 'unit': 'images/s', 'ms_per_step': rb['ms_per_step'], 'e2e': rb['e2e'],
+                                    'dtype': DTYPES['bf16'], 'parity': PARITY['bf16'], 'roofline': rfb,
+                                    'note': 'throughput variant: same kernels, all-bf16 operands'}
+            del fcn, dae, ii
+            torch.cuda.empty_cache()
+        if 'sweep' in sections:          # config 5: iterations 1..100 (each its own captured graph), same batch
+            sweep = {}
+            for n_it in (1, 10, 50, 100):
+                rs, objs = measure_inference(ctx, args.precision, n_iter=n_it, with_e2e=False, strong=strong)
+                sweep[str(n_it)] = {'value': rs['value'], 'ms_per_step': rs['ms_per_step']}
+                del objs
+                torch.cuda.empty_cache()
+            line['steps_sweep'] = {'unit': 'images/s', 'precision': args.precision, 'by_iterations': sweep}
+        if 'config3' in sections:
+            r3, objs = measure_inference(ctx, 'bf16', segm='densenet', strong=strong)
+            line['config3'] = {'workload': WORKLOAD3, 'value': r3['value'], 'unit': 'images/s', 'ms_per_step': r3['ms_per_step'], 'e2e': r3['e2e'],
+                               'dtype': 'bf16 operands, fp32 stacks and accumulation', 'executed_iterations': r3['executed_iterations']}
+            del objs
+            torch.cuda.empty_cache()
+        if 'config4' in sections:
+            line['config4'] = config4_leg(ctx)
+        if rank == 0 and world == 1 and 'cpu' in sections and not args.no_cpu_baseline:
             cpu_reference_sample(2)                                   # warm-up: thread pool, oneDNN primitive caches
             t_img, cores, parts = cpu_reference_sample(25)            # ~7 s of host work
-            cpu_base = {'value': 1.0 / t_img, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                        'sample': cpu_sample_text(25), 'parts_s': {k: round(v, 3) for k, v in parts.items()}}
-
+            line['cpu_baseline'] = {'value': 1.0 / t_img, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                    'sample': cpu_sample_text(25), 'parts_s': {k: round(v, 3) for k, v in parts.items()}}
+    elif args.config == 3:
+        with ClockSampler(ctx.local) as cs:
+            r3, objs = measure_inference(ctx, 'bf16', segm='densenet', strong=strong)
+        jac = jaccard_from_cm(r3['cm'])
+        line = {'metric': metric_name(3), 'value': r3['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': r3['ms_per_step'], 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+                'dtype': 'bf16 operands, fp32 stacks and accumulation', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD3, 'per_gpu_batch': BATCH, 'parallelism': 'image shards in whole batches (batch-stat BN), dp%d' % world,
+                           'executed_iterations': r3['executed_iterations']},
+                'e2e': r3['e2e'], 'gpu_launches': int(r3['launches_per_step'] * args.steps), 'clocks': cs.summary(),
+                'result': {'mean_jaccard': float(np.nanmean(jac[0] / jac[1]))}}
+    else:
+        with ClockSampler(ctx.local) as cs:
+            r4 = config4_leg(ctx)
+        line = {'metric': metric_name(4), 'value': r4['value'], 'unit': 'images/s', 'n_gpus': world, 'steps': r4['steps'], 'warmup': 3,
+                'ms_per_step': r4['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': r4['dtype'],
+                'data': 'synthetic', 'config': {'workload': WORKLOAD4, 'per_gpu_batch': BATCH, 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world},
+                'gpu_launches': int(r4['launches_per_step'] * r4['steps']), 'clocks': cs.summary(), 'allreduce': r4['allreduce'], 'loss': r4['loss']}
     if rank == 0:
-        cm = cm_total[:NCLS * NCLS].cpu().numpy()
-        jac = jaccard_from_cm(cm)
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'fp32 operands as bf16 hi/lo pairs, 3 tensor-core products, fp32 accumulate', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'per_gpu_batch': BATCH, 'global_batch': BATCH * world,
-                       'parallelism': 'image shards, dp%d' % world,
-                       'weights': 'random init (He-uniform FCN8 x logit gain 10, Glorot DAE x out gain 0.1)',
-                       'l2': 'working set per step (>2 GB of activations) exceeds the 126 MB L2; no explicit flush',
-                       'executed_iterations': n_exec[0]},
-            'e2e': {'value': e2e_value, 'unit': 'images/s',
-                    'h2d_bytes_per_step': int(X_host.numel() * 4 + L_host.numel() * 4),
-                    'd2h_bytes_per_step': int(cm_total.numel() * 8 + BATCH * 4), 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': int(launches_per_step * args.steps),
-            'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_base, 'breakdown': breakdown,
-            'result': {'mean_jaccard': float(__import__('numpy').nanmean(jac[0] / jac[1])), 'first_step_launch_census': int(census_first)},
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -383,9 +627,14 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', type=int, default=2, choices=[2, 3, 4],
+                    help='BASELINE.json config that is the headline of the line: 2 FCN8+DAE (default), 3 FC-DenseNet103+DAE, 4 train step')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='strong: a fixed set of 80 images is sharded over the ranks in whole batches')
+    ap.add_argument('--sections', default='', help='development runs: comma list of headline,bf16,roofline,cpu,config3,config4,sweep')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='development runs: skip the CPU oracle timing')
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32x3'],
-                    help="fp32x3: the parity-grade variant (fp32 operands as bf16 hi/lo pairs, three tensor-core products); no roofline leg")
+    ap.add_argument('--precision', default='mixed', choices=['mixed', 'bf16', 'fp32x3'],
+                    help="arithmetic of the headline: mixed (parity-grade, default), bf16 (throughput variant), fp32x3 (every conv fp32-accurate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

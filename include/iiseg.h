@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IISEG_ABI_VERSION 3
+#define IISEG_ABI_VERSION 4
 #define IISEG_MAX_SRC 6
 #define IISEG_MAX_WGROUPS 9
 
@@ -37,6 +37,7 @@ int iiseg_abi_version(void);
  * struct without a GPU. */
 int iiseg_conv_desc_size(void);
 int iiseg_conv_desc_last_offset(void);
+int iiseg_deconv_desc_size(void);      /* sizeof(iiseg_deconv_desc) */
 const char* iiseg_last_error(void);
 /* 0 if device `dev` is compute capability 10.x; negative otherwise. */
 int iiseg_device_check(int dev);
@@ -129,6 +130,10 @@ typedef struct iiseg_conv_desc {
    * 64 == 0).  Used to hoist the iteration-invariant half of a concat conv out of the loop:
    * conv(concat(h, x)) = conv_h(h) + b (computed once, out_f32) + conv_x(x) (every iteration). */
   int addend_f32;
+  /* addend_cs > 0: channels per pixel of the `addend` tensor in memory (default: Cout, or 2*Cout with split); the
+   * first Cout channels from the given pointer are added.  The mixed-precision DAE (fp32-accurate contracting path,
+   * bf16 expanding path) adds the hi halves of the contracting path's (hi | lo) pool tensors this way. */
+  int addend_cs;
   /* Fused Pool2DLayer(2) (+ DePool2D mask): when `pooled` != NULL the conv output is max-pooled
    * 2x2/stride 2 (floor) in the epilogue and only `pooled` [N,OH/2,OW/2,Cout] bf16 and, if
    * non-NULL, `pool_mask` [N,OH/2,OW/2,Cout/8] (nibble layout of iiseg_maxpool2_mask_fwd) are
@@ -163,7 +168,12 @@ typedef struct iiseg_conv_desc {
   const int32_t* upd_active;
   uint64_t* upd_norm_acc;
   float upd_step;
-  int upd_C, upd_cpad;
+  /* upd_step_dev != NULL: the step is read from device memory at run time instead (one captured CUDA graph then
+   * serves every step value of the iterative_inference_valid.py sweep). */
+  const float* upd_step_dev;
+  /* upd_split = 1: upd_y_bf16 is [N,OH,OW,2*upd_cpad], the (hi | lo) bf16 pair of the updated y (the first conv of
+   * the next iteration is an fp32-accurate `split` conv). */
+  int upd_C, upd_split, upd_cpad;
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
 /* Which kernel the calling thread's last iiseg_conv2d_fwd launched: *kernel = 0 per-tap, 1 CTA pair (cta_group::2),
@@ -188,7 +198,9 @@ int iiseg_unpool2_mask_fwd(const void* u, const uint32_t* mask, void* out, int N
  * element (0,0) is pooled position (u_h0,u_w0).  The expanding path only ever needs the
  * dependency cone of the final centre crop (CroppingLayer, models/fcn_up.py:106-113).
  * split = 1: `u` and `out` carry the (hi | lo) bf16 pair of an fp32 map, 2*C channels per pixel
- * (see iiseg_conv_desc.split); the mask still has C channels and gates both halves. */
+ * (see iiseg_conv_desc.split); the mask still has C channels and gates both halves.
+ * split = 2: `u` is such a pair tensor (2*C channels per pixel) but `out` is plain bf16 [N,OH,OW,C]: the hi halves
+ * gated by the mask (mixed precision: fp32-accurate contracting path, bf16 expanding path). */
 int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask, void* out, int N,
                                   int H, int W, int C, int UH, int UW, int u_h0, int u_w0,
                                   int OH, int OW, int o_h0, int o_w0, int split, void* stream);
@@ -223,24 +235,26 @@ int iiseg_deconv2d_fwd(const iiseg_deconv_desc* d, void* stream);
  * iiseg_norm_finalize: norm[n] = sum(partials)/(H*W) in fixed order;
  *   n_exec[n] += 1; if norm[n] < eps: active[n] = 0 (the `break`,
  *   iterative_inference.py:275-277).  Inactive images are untouched.
- * split = 1: y_bf16 is [N,H,W,2*Cpad], the (hi | lo) bf16 pair of y (fp32-accurate variant). */
+ * split = 1: y_bf16 is [N,H,W,2*Cpad], the (hi | lo) bf16 pair of y (fp32-accurate variant).
+ * step_dev / eps_dev != NULL: step / eps are read from device memory when the kernel runs (the by-value
+ * arguments are then ignored), so a captured CUDA graph is not tied to one step size or threshold. */
 int iiseg_update_blocks(int H, int W);
 int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, int N, int C,
                        int H, int W, int Cpad, int split, void* stream);
 int iiseg_softmax_update(const float* logits, float* y, void* y_bf16,
                          float* p_out, const int32_t* active,
                          float* norm_partial, int N, int C, int H, int W,
-                         int Cpad, float step, int split, void* stream);
+                         int Cpad, float step, const float* step_dev, int split, void* stream);
 /* de_fn (iterative_inference.py:203-204): grad = y - softmax(logits), NCHW fp32. */
 int iiseg_softmax_grad(const float* logits, const float* y, float* grad, int N, int C,
                        int H, int W, void* stream);
 int iiseg_norm_finalize(const float* norm_partial, float* norm, int32_t* active,
-                        int32_t* n_exec, int N, int H, int W, float eps,
+                        int32_t* n_exec, int N, int H, int W, float eps, const float* eps_dev,
                         void* stream);
 /* Same decision from the fixed-point accumulator of the fused conv epilogue (iiseg_conv_desc.upd_*):
  * norm[n] = norm_acc[n] * 2^-40 / (H*W) for active images; norm_acc[n] is reset to 0. */
 int iiseg_norm_finalize_fixed(uint64_t* norm_acc, float* norm, int32_t* active,
-                              int32_t* n_exec, int N, int H, int W, float eps,
+                              int32_t* n_exec, int N, int H, int W, float eps, const float* eps_dev,
                               void* stream);
 
 /* ---- metrics: metrics.py jaccard / accuracy / squared_error --------------

@@ -76,7 +76,7 @@ def conv_out_size(H, W, R, S, pad):
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
-           out_slice=None, pool_zmask=None, depool=None, depool_out=None):
+           out_slice=None, pool_zmask=None, depool=None, depool_out=None, addend_pair_hi=False):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -86,9 +86,12 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     the loader walks (hi, lo, hi) views of the sources, so the unchanged bf16 tensor-core loop
     accumulates hi*hi + lo*hi + hi*lo in fp32.
 
-    update = dict(y, y_bf16, active, norm_acc, step, C): the 16-channel logits conv with the softmax
+    update = dict(y, y_bf16, active, norm_acc, step, C[, y_split]): the 16-channel logits conv with the softmax
     tail and the iterative-inference update fused in its epilogue (iiseg_conv_desc.upd_*); nothing is
-    returned, y / y_bf16 / norm_acc are updated in place.
+    returned, y / y_bf16 / norm_acc are updated in place.  y_split: y_bf16 carries the (hi | lo) pair of y.
+
+    addend_pair_hi: the (bf16, non-split) conv adds the hi halves of a (hi | lo) pair tensor `addend`
+    [N,AH,AW,2*Cout] (iiseg_conv_desc.addend_cs): the skip-sum of the mixed-precision expanding path.
 
     depool = (mask, H, W, u_origin): `src0` is the POOLED tensor u (a dense window whose element (0,0) sits at pooled
     position u_origin) and the conv runs on the virtual map DePool2D(u, mask) of size HxW, expanded inside the
@@ -159,9 +162,13 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         _chk(out, F32 if out_f32 else BF16, 'out')
         assert tuple(out.shape) == (N, OH, OW, cm * Cout), (tuple(out.shape), (N, OH, OW, cm * Cout))
     addend_f32 = addend is not None and addend.dtype == F32     # hoisted fp32 term (see iiseg_conv_desc.addend_f32)
+    addend_cs = 0
     if addend is not None:
         _chk(addend, F32 if addend_f32 else BF16, 'addend')
-        assert addend.shape[0] == N and addend.shape[3] == (Cout if addend_f32 else cm * Cout)
+        if addend_pair_hi:
+            assert not split and not addend_f32 and addend.shape[3] == 2 * Cout
+            addend_cs = 2 * Cout
+        assert addend.shape[0] == N and addend.shape[3] == (Cout if addend_f32 else (2 * Cout if addend_pair_hi else cm * Cout))
         assert addend_off[0] + OH <= addend.shape[1] and addend_off[1] + OW <= addend.shape[2]
     d = _lib.ConvDesc(N=N, H=H, W=W, weight=weight.data_ptr(), bias=bias.data_ptr(),
                       Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
@@ -172,7 +179,7 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       pool_zmask=pool_zmask.data_ptr() if pool_zmask is not None else None,
                       pool_H=pool_hw[0] if pooled is not None else 0, pool_W=pool_hw[1] if pooled is not None else 0,
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
-                      ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32),
+                      ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32), addend_cs=addend_cs,
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
     if depool_out is not None:
         d.depool_out, d.depool_out_mask = dpo_v.data_ptr(), dpo_mask.data_ptr()
@@ -187,7 +194,15 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         d.upd_y, d.upd_y_bf16 = update['y'].data_ptr(), update['y_bf16'].data_ptr()
         d.upd_active = update['active'].data_ptr() if update.get('active') is not None else None
         d.upd_norm_acc = update['norm_acc'].data_ptr()
-        d.upd_step, d.upd_C, d.upd_cpad = float(update['step']), int(update['C']), int(update['y_bf16'].shape[3])
+        ysp = bool(update.get('y_split'))
+        stp = update['step']          # a python float, or a 1-element fp32 CUDA tensor read by the kernel at run time
+        if isinstance(stp, torch.Tensor):
+            _chk(stp, F32, 'update.step')
+            d.upd_step, d.upd_step_dev = 0.0, stp.data_ptr()
+        else:
+            d.upd_step = float(stp)
+        d.upd_C, d.upd_split = int(update['C']), int(ysp)
+        d.upd_cpad = int(update['y_bf16'].shape[3]) // (2 if ysp else 1)
     # the channel-concatenated source views, in K order: (pointer, channels, channels per pixel in memory)
     srcs = [(src0, C0)] + ([(src1, C1)] if src1 is not None else [])
     views = []
@@ -220,16 +235,18 @@ def maxpool2(x, with_mask, pooled=None, mask=None):
 
 def unpool2(u, mask, H, W, out=None, u_origin=(0, 0), window=None, split=False):
     """DePool2D into the HxW pre-pool map.  `u` is a dense window of the pooled map starting at pooled
-    position `u_origin`; `window` = (h0, w0, OH, OW) restricts the output (default: the whole map)."""
+    position `u_origin`; `window` = (h0, w0, OH, OW) restricts the output (default: the whole map).
+    split=True: u and out carry (hi | lo) pairs; split=2: u is a pair tensor, out its gated hi halves (plain bf16)."""
     _chk(u, BF16, 'u')
     _chk(mask, torch.int32, 'mask')
     N, UH, UW, Cu = u.shape
     Cc = Cu // 2 if split else Cu          # split: u / out carry (hi | lo) pairs, the mask has Cc channels
     assert tuple(mask.shape) == (N, H // 2, W // 2, Cc // 8), (tuple(mask.shape), H, W, Cc)
     h0, w0, OH, OW = window if window is not None else (0, 0, H, W)
+    Co = Cc if split == 2 else Cu
     if out is None:
-        out = torch.empty((N, OH, OW, Cu), dtype=BF16, device=u.device)
-    assert tuple(out.shape) == (N, OH, OW, Cu)
+        out = torch.empty((N, OH, OW, Co), dtype=BF16, device=u.device)
+    assert tuple(out.shape) == (N, OH, OW, Co)
     _lib.call('iiseg_unpool2_mask_window_fwd', _ptr(u), _ptr(mask), _ptr(out), N, H, W, Cc, UH, UW,
               u_origin[0], u_origin[1], OH, OW, h0, w0, int(split), _stream())
     return out
@@ -259,6 +276,15 @@ def deconv16(x, weight, bias, k, stride, window=None, addend=None, addend_off=(0
 
 
 # ---- softmax / update ---------------------------------------------------------
+def _scalar(v):
+    """(by-value float, device pointer) of a kernel scalar: python floats go by value; a 1-element fp32 CUDA tensor is
+    read by the kernel when it runs (so a captured graph is not tied to the value)."""
+    if isinstance(v, torch.Tensor):
+        _chk(v, F32, 'scalar')
+        return C.c_float(0.0), C.c_void_p(v.data_ptr())
+    return C.c_float(float(v)), C.c_void_p(0)
+
+
 def update_blocks(H, W):
     return _lib.load().iiseg_update_blocks(H, W)
 
@@ -279,8 +305,9 @@ def softmax_update(logits, y, y_bf16, active, norm_partial, step, p_out=None, sp
     N, C_, H, W = y.shape
     assert tuple(logits.shape) == (N, H, W, 16)
     cpad = y_bf16.shape[3] // (2 if split else 1) if y_bf16 is not None else 0
+    sv, sd = _scalar(step)
     _lib.call('iiseg_softmax_update', _ptr(logits), _ptr(y), _ptr(y_bf16), _ptr(p_out), _ptr(active),
-              _ptr(norm_partial), N, C_, H, W, cpad, C.c_float(step), int(split), _stream())
+              _ptr(norm_partial), N, C_, H, W, cpad, sv, sd, int(split), _stream())
 
 
 def softmax_grad(logits, y, grad):
@@ -296,14 +323,16 @@ def norm_finalize_fixed(norm_acc, norm, active, n_exec, H, W, eps):
     """norm / active / n_exec step from the fixed-point accumulator of the fused conv epilogue."""
     _chk(norm_acc, torch.int64, 'norm_acc')
     N = norm.shape[0]
+    ev, ed = _scalar(eps)
     _lib.call('iiseg_norm_finalize_fixed', _ptr(norm_acc), _ptr(norm), _ptr(active), _ptr(n_exec), N, H, W,
-              C.c_float(eps), _stream())
+              ev, ed, _stream())
 
 
 def norm_finalize(norm_partial, norm, active, n_exec, H, W, eps):
     N = norm.shape[0]
+    ev, ed = _scalar(eps)
     _lib.call('iiseg_norm_finalize', _ptr(norm_partial), _ptr(norm), _ptr(active), _ptr(n_exec), N, H, W,
-              C.c_float(eps), _stream())
+              ev, ed, _stream())
 
 
 # ---- FC-DenseNet103 streaming kernels -------------------------------------------
@@ -419,7 +448,7 @@ def transpose_shift(x, C_, origin, size, shift, out, row0, c0=0, nshift=1, shift
               _ptr(out), C.c_longlong(out.shape[1]), C.c_longlong(row0), nshift, C.c_longlong(shift_rows), _stream())
 
 
-def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
+def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld, out=None):
     """Weight gradient of a conv without a 9-fold im2col:
         G[co][t*cin_pad + ci] = sum_k gT[co][k] * xT[row_t + ci][k + koff_t]      for (row_t, koff_t) = groups[t]
     (columns beyond xT's width read as zero; koff_t % 8 == 0) -> fp32 [Cg, out_ld], first len(groups)*cin_pad columns written.
@@ -432,7 +461,10 @@ def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
     taps = len(groups)
     assert xT.shape[1] == Kt and Kt % (64 * slabs) == 0 and out_ld >= taps * cin_pad and out_ld % 4 == 0
     slab = Kt // slabs
-    part = torch.empty((slabs, M, out_ld), dtype=F32, device=gT.device)
+    if out is not None:           # a persistent destination (a view of the trainer's flat gradient buffer)
+        _chk(out, F32, 'out')
+        assert tuple(out.shape) == (M, out_ld)
+    part = out.view(1, M, out_ld) if (out is not None and slabs == 1) else torch.empty((slabs, M, out_ld), dtype=F32, device=gT.device)
     zero = torch.zeros((taps * cin_pad,), dtype=F32, device=gT.device)
     d = _lib.ConvDesc(N=slabs, H=1, W=M, weight=xT.data_ptr(), bias=zero.data_ptr(), Cout=taps * cin_pad, R=1, S=1, pad=0,
                       oh0=0, ow0=0, OH=1, OW=M, out=part.data_ptr(), relu=0, out_f32=1, out_cs=out_ld,
@@ -443,7 +475,8 @@ def wgrad_gemm(gT, xT, cin_pad, groups, slabs, out_ld):
     _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
     if slabs == 1:
         return part.view(M, out_ld)
-    out = torch.empty((M, out_ld), dtype=F32, device=gT.device)
+    if out is None:
+        out = torch.empty((M, out_ld), dtype=F32, device=gT.device)
     _lib.call('iiseg_sum_slabs', _ptr(part), _ptr(out), slabs, C.c_longlong(M * out_ld), _stream())
     return out
 

@@ -14,7 +14,7 @@ class IisegError(RuntimeError):
     pass
 
 
-ABI_VERSION = 3      # IISEG_ABI_VERSION
+ABI_VERSION = 4      # IISEG_ABI_VERSION
 MAX_SRC = 6          # IISEG_MAX_SRC
 MAX_WGROUPS = 9      # IISEG_MAX_WGROUPS
 
@@ -34,11 +34,11 @@ class ConvDesc(C.Structure):
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('addend', C.c_void_p),
-        ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int),
+        ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int), ('addend_cs', C.c_int),
         ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_zmask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
         ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int), ('out_cs', C.c_int),
         ('upd_y', C.c_void_p), ('upd_y_bf16', C.c_void_p), ('upd_active', C.c_void_p), ('upd_norm_acc', C.c_void_p),
-        ('upd_step', C.c_float), ('upd_C', C.c_int), ('upd_cpad', C.c_int),
+        ('upd_step', C.c_float), ('upd_step_dev', C.c_void_p), ('upd_C', C.c_int), ('upd_split', C.c_int), ('upd_cpad', C.c_int),
     ]
 
 
@@ -60,6 +60,7 @@ SIGNATURES = {
     'iiseg_abi_version': (_i, []),
     'iiseg_conv_desc_size': (_i, []),
     'iiseg_conv_desc_last_offset': (_i, []),
+    'iiseg_deconv_desc_size': (_i, []),
     'iiseg_last_error': (C.c_char_p, []),
     'iiseg_device_check': (_i, [_i]),
     'iiseg_read_diag': (_i, [_vp, _i]),
@@ -75,10 +76,10 @@ SIGNATURES = {
     'iiseg_deconv2d_fwd': (_i, [C.POINTER(DeconvDesc), _vp]),
     'iiseg_update_blocks': (_i, [_i, _i]),
     'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
     'iiseg_softmax_grad': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
-    'iiseg_norm_finalize_fixed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    'iiseg_norm_finalize_fixed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_bn_relu_pack': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     'iiseg_channel_stats_chunks': (_i, [_i, _i, _i]),
@@ -113,7 +114,16 @@ def load():
             fn.restype = res
             fn.argtypes = args
         if lib.iiseg_abi_version() != ABI_VERSION:
-            raise IisegError('libiiseg ABI version mismatch')
+            raise IisegError('libiiseg ABI version mismatch (library %d, binding %d): rebuild with '
+                             '`python -m iterative_inference_segm_b200.csrc.build --force`' % (lib.iiseg_abi_version(), ABI_VERSION))
+        # the hand-mirrored descriptor structs must have the C layout: a stale library or an edited struct would otherwise
+        # hand misaligned descriptors to the kernels
+        if (C.sizeof(ConvDesc) != lib.iiseg_conv_desc_size() or ConvDesc.upd_cpad.offset != lib.iiseg_conv_desc_last_offset()
+                or C.sizeof(DeconvDesc) != lib.iiseg_deconv_desc_size()):
+            raise IisegError('ctypes mirror of iiseg_conv_desc / iiseg_deconv_desc does not match libiiseg.so '
+                             '(conv %d vs %d bytes, last field at %d vs %d, deconv %d vs %d bytes): rebuild the library'
+                             % (C.sizeof(ConvDesc), lib.iiseg_conv_desc_size(), ConvDesc.upd_cpad.offset,
+                                lib.iiseg_conv_desc_last_offset(), C.sizeof(DeconvDesc), lib.iiseg_deconv_desc_size()))
         _lib = lib
     return _lib
 

@@ -24,14 +24,21 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
+int num_sms() {           // per device ordinal: a process may drive several GPUs
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 // 64 pinned, device-mapped words.  A kernel whose mbarrier wait times out writes
@@ -56,6 +63,7 @@ int32_t* diag_device_ptr() {
 extern "C" int iiseg_abi_version(void) { return IISEG_ABI_VERSION; }
 extern "C" int iiseg_conv_desc_size(void) { return (int)sizeof(iiseg_conv_desc); }
 extern "C" int iiseg_conv_desc_last_offset(void) { return (int)offsetof(iiseg_conv_desc, upd_cpad); }
+extern "C" int iiseg_deconv_desc_size(void) { return (int)sizeof(iiseg_deconv_desc); }
 
 extern "C" const char* iiseg_last_error(void) { return iiseg::g_err; }
 

@@ -44,7 +44,19 @@ void count_launch(int n = 1);
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-int num_sms();
+constexpr int kMaxDevices = 64;
+int current_device();         // ordinal of the calling thread's device, clamped to [0, kMaxDevices)
+int num_sms();                // SM count of that device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: opt a kernel in once per device ordinal
+#define IISEG_SMEM_OPT_IN(kernel, bytes)                                                            \
+  do {                                                                                              \
+    static bool configured_[::iiseg::kMaxDevices] = {false};                                        \
+    const int dev_ = ::iiseg::current_device();                                                     \
+    if (!configured_[dev_]) {                                                                       \
+      IISEG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      configured_[dev_] = true;                                                                     \
+    }                                                                                               \
+  } while (0)
 
 // ---- device helpers --------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

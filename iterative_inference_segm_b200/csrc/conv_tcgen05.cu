@@ -72,6 +72,9 @@ struct alignas(64) ConvParams {
   int n_cblk_src[IISEG_MAX_SRC];        // 64-channel blocks of each source
   int n_cblk;               // their sum
   int split;                // split-precision output: channels [0,Cout) = hi, [Cout,2Cout) = lo (bf16 pair of the fp32 value)
+  int hsplit;               // halo kernel, split precision: A blocks are (hi x n, lo x n); the resident bank holds W_hi and W_lo; a hi
+                            // block is multiplied with both, a lo block with W_hi only (hi*W_hi + hi*W_lo + lo*W_hi)
+  int n_bblk;               // halo kernel: filter blocks per tap in the resident bank (n_cblk, or 2n with hsplit)
   int R, S;
   int in_off_h, in_off_w;   // input row of tap r for local output row o: o + in_off_h + r
   int TH, TW;
@@ -100,13 +103,14 @@ struct alignas(64) ConvParams {
   float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
   int OH, OW, Cout;
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
+  int addend_cs;             // channels per pixel of the addend tensor in memory
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
   uint32_t* pool_mask;       // tie-inclusive mask nibbles [N,PH,PW,Cout/8] or NULL
   uint32_t* pool_zmask;      // same layout: bit set iff the pre-rectifier value is exactly 0 (training: rectify'(0) = 0.5) or NULL
   int PH, PW;                // pooled tensor extent
   // fused softmax + iterative-inference update (16-channel logits conv): see iiseg_conv_desc.upd_*
   float* upd_y; __nv_bfloat16* upd_y_bf16; const int32_t* upd_active; unsigned long long* upd_norm_acc;
-  float upd_step; int upd_C, upd_cpad;
+  float upd_step; const float* upd_step_dev; int upd_C, upd_cpad, upd_split;
   int p_h0, p_w0, pwin_h, pwin_w;   // pooled-grid origin and extent of this launch's output window
   int relu, out_f32;
   int out_cs;               // fp32 outputs: channels per pixel of the destination tensor (>= Cout: the conv writes a channel slice)
@@ -342,7 +346,7 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
     const int cbase = tc.nt * 16 + half * 8;
     uint4 a0 = make_uint4(0, 0, 0, 0);
     const bool has_add = (p.addend != nullptr) && valid;
-    if (has_add) a0 = ldg_nc_v4(p.addend + apix * p.Cout + cbase);
+    if (has_add) a0 = ldg_nc_v4(p.addend + apix * p.addend_cs + cbase);
     mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * 16) + (static_cast<uint32_t>(q * 32) << 16);
@@ -403,6 +407,7 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
   const bool in_box = (hl < p.TH) && (wl < p.TW);
   const int C = p.upd_C;
   const size_t HW = static_cast<size_t>(p.OH) * p.OW;
+  const float upd_step = p.upd_step_dev != nullptr ? __ldg(p.upd_step_dev) : p.upd_step;      // device scalar: one graph, any step
   float bias[16];
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
@@ -484,15 +489,31 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
         if (c < C) {
           const float g = __fsub_rn(yv[c], __fmul_rn(pr[c], inv));      // explicit roundings: same bits as update.cu
           ss = __fmaf_rn(g, g, ss);
-          outv[c] = fminf(fmaxf(__fsub_rn(yv[c], __fmul_rn(p.upd_step, g)), 0.f), 1.f);
+          outv[c] = fminf(fmaxf(__fsub_rn(yv[c], __fmul_rn(upd_step, g)), 0.f), 1.f);
           yb[static_cast<size_t>(c) * HW] = outv[c];
         } else outv[c] = 0.f;
       }
       nrm = sqrtf(ss);
-      uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + (static_cast<size_t>(cur.n) * HW + cur.pixoff) * p.upd_cpad);
-      stg_v4(o, make_uint4(pack_bf16x2(outv[0], outv[1]), pack_bf16x2(outv[2], outv[3]), pack_bf16x2(outv[4], outv[5]), pack_bf16x2(outv[6], outv[7])));
-      stg_v4(o + 1, make_uint4(pack_bf16x2(outv[8], outv[9]), pack_bf16x2(outv[10], outv[11]), pack_bf16x2(outv[12], outv[13]), pack_bf16x2(outv[14], outv[15])));
-      for (int j = 2; j < p.upd_cpad / 8; ++j) stg_v4(o + j, make_uint4(0, 0, 0, 0));
+      uint32_t hw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hw[j] = pack_bf16x2(outv[2 * j], outv[2 * j + 1]);
+      if (!p.upd_split) {
+        uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + (static_cast<size_t>(cur.n) * HW + cur.pixoff) * p.upd_cpad);
+        stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+        for (int j = 2; j < p.upd_cpad / 8; ++j) stg_v4(o + j, make_uint4(0, 0, 0, 0));
+      } else {      // (hi | lo) pair of y for an fp32-accurate first conv: hi = bf16(y), lo = bf16(y - hi)
+        uint32_t lw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lw[j] = pack_bf16x2(outv[2 * j] - bf16_lo(hw[j]), outv[2 * j + 1] - bf16_hi(hw[j]));
+        uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + (static_cast<size_t>(cur.n) * HW + cur.pixoff) * (2 * p.upd_cpad));
+        const int half = p.upd_cpad / 8;
+        stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+        stg_v4(o + half, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        stg_v4(o + half + 1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+        for (int j = 2; j < half; ++j) { stg_v4(o + j, make_uint4(0, 0, 0, 0)); stg_v4(o + half + j, make_uint4(0, 0, 0, 0)); }
+      }
     }
     // per-image norm in 2^-40 fixed point (integer sums are order-independent): nrm <= sqrt(C) < 2^11, so
     // nrm * 2^20 < 2^31 splits exactly into an integer part and a fraction, each converted in fp32
@@ -540,7 +561,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
       // skip-sum operand of the first chunk: requested before the accumulator is ready
       const bool has_add = (p.addend != nullptr) && !p.addend_f32 && valid && !(p.dbg & 8);
       const bool has_add32 = (p.addend != nullptr) && p.addend_f32 && valid;
-      const __nv_bfloat16* arow = p.addend + apix * cpp + n0;
+      const __nv_bfloat16* arow = p.addend + apix * p.addend_cs + n0;
       uint4 add[kSplit ? 8 : 4];
       if (has_add) {
 #pragma unroll
@@ -584,7 +605,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
           f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
         }
         if (has_add32) {      // fp32 operand (the hoisted iteration-invariant term of a concat conv): exact fp32 add
-          const float* a32 = reinterpret_cast<const float*>(p.addend) + apix * p.Cout + cbase;
+          const float* a32 = reinterpret_cast<const float*>(p.addend) + apix * p.addend_cs + cbase;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 t = ldg_nc_v4(a32 + 4 * j);
@@ -1104,7 +1125,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
     const bool has_add = !kPool && (p.addend != nullptr) && valid;
-    const __nv_bfloat16* arow = p.addend + ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.Cout;
+    const __nv_bfloat16* arow = p.addend + ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.addend_cs;
     uint4 add[2];
     if (has_add) { add[0] = ldg_nc_v4(arow); add[1] = ldg_nc_v4(arow + 8); }      // before the accumulator is ready
     if (q == 0 && lane == 0) IISEG_STAMP(iter, 4);
@@ -1215,6 +1236,113 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
 }
 
 // ---------------------------------------------------------------------------
+// Split-precision ("fp32x3") epilogue of the halo-tile kernel: the accumulator is the fp32-accurate sum
+// hi*W_hi + hi*W_lo + lo*W_hi; bias and ReLU are applied in fp32 and the result leaves as the bf16 pair
+// hi = bf16(x), lo = bf16(x - hi) (channels [0,Cout) and [Cout,2*Cout) of the output pixel).  With the fused
+// Pool2DLayer(2) the 2x2 max and the tie-inclusive mask compare the reconstructed values r = hi + lo (the
+// numbers the next layer actually sees; same rule as conv_epilogue<.., kSplit = true>) with warp shuffles on the
+// pitch-16 box (lanes {l, l^1, l^16, l^17} hold a window), and the pooled pixel is written as the pair of the
+// window maximum.  No skip-sum operand: the contracting path and FCN8's first stage have none.
+// ---------------------------------------------------------------------------
+template <int BN, bool kPool>
+__device__ __forceinline__ void halo_epilogue_split(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                                    uint32_t tmem_empty_bar0, int warp, int lane) {
+  const int q = warp & 3;
+  const int grp = (warp - 4) >> 2;          // 0..3 = accumulator stage
+  const int macc = q * 32 + lane;
+  const int hl = macc / p.pitch, wl = macc - hl * p.pitch;
+  const bool in_box = (hl < p.TH) && (wl < p.TW);
+  const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * grp, tmem_empty_bar = tmem_empty_bar0 + 8u * grp;
+  const uint32_t taddr = tmem_base + static_cast<uint32_t>(grp * BN) + (static_cast<uint32_t>(q * 32) << 16);
+  const int pos = ((lane >> 4) << 1) | (lane & 1);            // pool: window position 2*dy + dx of this lane
+  const int cpp = 2 * p.Cout;
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 4) {
+    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+    const uint32_t aphase = static_cast<uint32_t>(iter >> 2) & 1u;
+    const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
+    const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
+    mbar_wait(tmem_full_bar, aphase, p.diag, 4, grp, (p.dbg & 1024) == 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 16; ++chunk) {
+      const int cbase = chunk * 16;
+      uint32_t v[16];
+      tmem_ld_x16(taddr + cbase, v);
+      tmem_ld_wait();
+      if (chunk == BN / 16 - 1) {   // all TMEM reads of this accumulator are done
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar);
+      }
+      float f[16];
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = __ldg(bias4 + j4);
+        f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+        f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        lo[j] = pack_bf16x2(f[2 * j] - bf16_lo(hi[j]), f[2 * j + 1] - bf16_hi(hi[j]));
+      }
+      if constexpr (!kPool) {
+        if (valid) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * cpp + cbase;
+          stg_v4(o, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          stg_v4(o + 8, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+          stg_v4(o + p.Cout, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          stg_v4(o + p.Cout + 8, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+        }
+      } else {
+        // r = hi + lo, window max and tie bits over the four lanes of the window
+        uint32_t word[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
+          f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float m = fmaxf(f[c], __shfl_xor_sync(0xffffffffu, f[c], 1));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+          // channel c of the chunk = channel (c & 7) of mask word c >> 3: bit 16*(c & 1) + 4*((c >> 1) & 3) + pos
+          if (f[c] == m) word[c >> 3] |= 1u << (16 * (c & 1) + 4 * ((c >> 1) & 3) + pos);
+          f[c] = m;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          word[g] |= __shfl_xor_sync(0xffffffffu, word[g], 1);
+          word[g] |= __shfl_xor_sync(0xffffffffu, word[g], 16);
+        }
+        const int phw = ((tc.th * p.TH) >> 1) + (hl >> 1), pww = ((tc.tw * p.TW) >> 1) + (wl >> 1);   // inside the window
+        if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {       // pair of the window maximum (hi + lo reproduces it exactly)
+            hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            lo[j] = pack_bf16x2(f[2 * j] - bf16_lo(hi[j]), f[2 * j + 1] - bf16_hi(hi[j]));
+          }
+          const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + p.p_h0 + phw) * p.PW + p.p_w0 + pww;
+          __nv_bfloat16* o = p.pooled + ppix * cpp + cbase;
+          stg_v4(o, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          stg_v4(o + 8, make_uint4(hi[4], hi[5], hi[6], hi[7]));
+          stg_v4(o + p.Cout, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          stg_v4(o + p.Cout + 8, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+          if (p.pool_mask != nullptr)
+            *reinterpret_cast<uint2*>(p.pool_mask + ppix * (p.Cout >> 3) + (cbase >> 3)) = make_uint2(word[0], word[1]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Halo-tile main loop (3x3 filters): ONE activation load per channel block.
 //
 // The per-tap kernel above re-fetches the 128-pixel A box for each of the R*S taps, and every layer
@@ -1267,7 +1395,7 @@ __global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads :
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
-  const uint32_t b_bytes_total = static_cast<uint32_t>(9 * p.n_cblk) * Cfg::kBBlockBytes;   // resident filter bank
+  const uint32_t b_bytes_total = static_cast<uint32_t>(9 * p.n_bblk) * Cfg::kBBlockBytes;   // resident filter bank
   const uint32_t bars = b_ring + b_bytes_total;
   auto a_full = [&](int i) { return bars + 8u * i; };
   auto a_empty = [&](int i) { return bars + 8u * (Cfg::kMaxA + i); };
@@ -1316,7 +1444,7 @@ __global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads :
     // map get zero mask words from TMA's out-of-bounds fill, hence zeros: the conv's padding.
     const int bw = warp == 0 ? 0 : (warp == 2 ? 1 : warp - 18);            // builder index: box rows i = bw (mod kDpBuilders)
     if (warp == 0 && elect_one_sync()) {
-      const int n_blocks = 9 * n_cblk;
+      const int n_blocks = 9 * p.n_bblk;
       mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
       for (int i = 0; i < n_blocks; ++i)
         tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * KB, 0);
@@ -1400,11 +1528,22 @@ __global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads :
   } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
-      // the filter bank: loaded once, stays resident (Cout == BN, all 9 * n_cblk blocks fit)
-      const int n_blocks = 9 * n_cblk;
+      // the filter bank: loaded once, stays resident (Cout == BN, all 9 * n_bblk blocks fit)
+      const int n_blocks = 9 * p.n_bblk;
       mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(n_blocks) * Cfg::kBBlockBytes);
-      for (int i = 0; i < n_blocks; ++i)
-        tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * KB, 0);
+      if (!p.hsplit) {
+        for (int i = 0; i < n_blocks; ++i)
+          tma_load_2d(b_ring + i * Cfg::kBBlockBytes, &p.tm_w, b_res_bar, i * KB, 0);
+      } else {
+        // split precision: the packed K axis of a tap is (W_hi | W_hi | W_lo), n blocks each; the bank keeps
+        // [W_hi: 9 taps x n blocks][W_lo: 9 taps x n blocks]
+        const int n = p.n_bblk >> 1;
+        for (int half = 0; half < 2; ++half)
+          for (int tap = 0; tap < 9; ++tap)
+            for (int cb = 0; cb < n; ++cb)
+              tma_load_2d(b_ring + ((half * 9 + tap) * n + cb) * Cfg::kBBlockBytes, &p.tm_w, b_res_bar,
+                          (tap * 3 * n + half * 2 * n + cb) * KB, 0);
+      }
       const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * p.pitch) * Cfg::kRowBytes;
       // Halo blocks stream through two sub-rings of n_a/2 buffers: even tiles -> ring 0 (consumed by MMA
       // warp 1), odd tiles -> ring 1 (warp 3), so every mbarrier has exactly one waiter walking its
@@ -1459,15 +1598,34 @@ __global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads :
         if (elect_one_sync()) {
           // 3x3 taps fully unrolled: tap (r,s) = the halo tile advanced by (r*pitch + s) rows
           const uint64_t a0 = Cfg::kDescHi | static_cast<uint64_t>(((a_ring + slot * p.a_blk_bytes) >> 4) & 0x3FFFu);
-          const uint64_t b0 = Cfg::kDescHi | static_cast<uint64_t>(((b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes) >> 4) & 0x3FFFu);
+          if (!p.hsplit) {
+            const uint64_t b0 = Cfg::kDescHi | static_cast<uint64_t>(((b_ring + static_cast<uint32_t>(cb) * Cfg::kBBlockBytes) >> 4) & 0x3FFFu);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            if (p.dbg & 2) break;                                       // tuning: no MMAs
-            const uint64_t a_desc = a0 + static_cast<uint32_t>((tap / 3) * p.pitch + (tap % 3)) * row16;
-            const uint64_t b_desc = b0 + tap * b_tap;
+            for (int tap = 0; tap < 9; ++tap) {
+              if (p.dbg & 2) break;                                       // tuning: no MMAs
+              const uint64_t a_desc = a0 + static_cast<uint32_t>((tap / 3) * p.pitch + (tap % 3)) * row16;
+              const uint64_t b_desc = b0 + tap * b_tap;
 #pragma unroll
-            for (int k = 0; k < KB / kUmmaK; ++k)
-              umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < KB / kUmmaK; ++k)
+                umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            // split precision: block cb < n is a hi block (x W_hi, then x W_lo), block cb >= n the lo block n - cb (x W_hi)
+            const int n = n_cblk >> 1;
+            const int cbw = cb < n ? cb : cb - n;
+            const int halves = cb < n ? 2 : 1;
+            for (int half = 0; half < halves; ++half) {
+              const uint64_t b0 = Cfg::kDescHi | static_cast<uint64_t>(((b_ring + static_cast<uint32_t>(half * 9 * n + cbw) * Cfg::kBBlockBytes) >> 4) & 0x3FFFu);
+              const uint32_t b_tap_s = static_cast<uint32_t>(n) * (Cfg::kBBlockBytes >> 4);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t a_desc = a0 + static_cast<uint32_t>((tap / 3) * p.pitch + (tap % 3)) * row16;
+                const uint64_t b_desc = b0 + tap * b_tap_s;
+#pragma unroll
+                for (int k = 0; k < KB / kUmmaK; ++k)
+                  umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (cb > 0 || half > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
           }
           umma_commit(a_empty(slot));                                   // halo block consumed
           if (cb == n_cblk - 1) umma_commit(tmem_full_bar(as));         // accumulator ready
@@ -1480,6 +1638,9 @@ __global__ void __launch_bounds__(kNumThreadsHalo + (kDepool ? kDpExtraThreads :
     if constexpr (BN == 16) {
       if (p.upd_y != nullptr) conv_epilogue16_update<4>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else if (warp < 12) conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);      // 8 warps suffice
+    } else if (!kDepool && p.hsplit) {
+      if (p.pooled != nullptr) halo_epilogue_split<BN, true>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else halo_epilogue_split<BN, false>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     } else if (p.pooled != nullptr) halo_epilogue<BN, true>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     else halo_epilogue<BN, false>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
@@ -1602,11 +1763,7 @@ static bool choose_halo_box(int OH, int OW, int R, int S, bool even, int max_row
 
 template <int BN, int KB>
 static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  IISEG_SMEM_OPT_IN((conv_halo_kernel<BN, KB>), 227 * 1024);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   conv_halo_kernel<BN, KB><<<grid, kNumThreadsHalo, smem_bytes, stream>>>(p);
   IISEG_LAUNCH_CHECK();
@@ -1615,11 +1772,7 @@ static int launch_conv_halo(const ConvParams& p, int smem_bytes, cudaStream_t st
 
 template <int BN>
 static int launch_conv_halo_depool(const ConvParams& p, int smem_bytes, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    IISEG_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  IISEG_SMEM_OPT_IN((conv_halo_kernel<BN, 64, true>), 227 * 1024);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   conv_halo_kernel<BN, 64, true><<<grid, kNumThreadsHalo + kDpExtraThreads, smem_bytes, stream>>>(p);
   IISEG_LAUNCH_CHECK();
@@ -1629,11 +1782,7 @@ static int launch_conv_halo_depool(const ConvParams& p, int smem_bytes, cudaStre
 template <int BN>
 static int launch_conv(const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  IISEG_SMEM_OPT_IN(conv_igemm_kernel<BN>, Cfg::kSmemBytes);
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   ConvParams q = p;
   q.stages = (p.stages >= 2 && p.stages <= Cfg::kStages) ? p.stages : Cfg::kStages;
@@ -1673,8 +1822,14 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
                 d->upd_cpad >= 16 && d->upd_cpad % 8 == 0 && d->addend == nullptr && d->pooled == nullptr && d->split == 0,
                 "conv: the fused softmax-update needs a 16-channel logits conv (no addend / pool / split), y_bf16 and norm_acc");
   IISEG_CHECK(d->pooled == nullptr || (d->Cout % 64 == 0 && d->OH >= 2 && d->OW >= 2 && d->out_f32 == 0), "conv: fused pool needs Cout %% 64 == 0 and a bf16 output");
+  // Split precision on the halo-tile kernel: ONE logical source given as the (hi | lo | hi) views of a pair tensor, split
+  // output, no skip-sum / training mask / DePool2D fusion.  The kernel loads the hi and lo blocks once each and keeps
+  // W_hi and W_lo resident (hi*W_hi + hi*W_lo + lo*W_hi).
+  const bool hsplit_ok = d->split && d->src[2] != nullptr && d->src[3] == nullptr && d->src[2] == d->src[0] && d->C[0] == d->C[1] &&
+                         d->C[0] == d->C[2] && d->Cs[0] == d->Cs[2] && d->addend == nullptr && d->pool_zmask == nullptr &&
+                         d->depool_mask == nullptr && d->depool_out == nullptr && d->w_groups == 0;
   // K blocks of 64 channels (128-byte rows), or -- one 16-channel source, 3x3 filter, halo-tile kernel only -- of 16
-  int KB = (d->C[0] == 16 && d->src[1] == nullptr) ? 16 : 64;
+  int KB = (d->C[0] == 16 && (d->src[1] == nullptr || hsplit_ok)) ? 16 : 64;
   IISEG_CHECK(d->C[0] > 0 && d->C[0] % KB == 0, "conv: C0=%d must be 16 or a positive multiple of 64", d->C[0]);
   int Cin = 0;
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
@@ -1692,6 +1847,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   else
     IISEG_CHECK(d->Cout == 16 || d->Cout % 64 == 0, "conv: Cout=%d must be 16 or a multiple of 64", d->Cout);
   IISEG_CHECK(d->addend_f32 == 0 || (d->addend != nullptr && d->Cout % 64 == 0), "conv: fp32 addend needs Cout %% 64 == 0");
+  IISEG_CHECK(d->addend_cs == 0 || (d->addend != nullptr && d->addend_cs >= d->Cout && d->addend_cs % 8 == 0),
+              "conv: addend_cs=%d must be a multiple of 8 >= Cout", d->addend_cs);
   IISEG_CHECK(d->pool_zmask == nullptr || (d->pooled != nullptr && d->split == 0), "conv: pool_zmask needs the fused pool (bf16 variant)");
   IISEG_CHECK((d->w_koff == 0 && d->weight_ld == 0 && d->src_image_stride == 0) || (d->R == 1 && d->S == 1 && d->w_koff % 64 == 0 && d->weight_ld % 8 == 0),
               "conv: split-K views (w_koff / weight_ld / src_image_stride) are for 1x1 GEMM launches");
@@ -1727,7 +1884,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
   // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
   // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
-  bool halo = env_halo && d->R == 3 && d->S == 3 && !d->split && d->Cout == BN && BN <= 128;
+  bool halo = env_halo && d->R == 3 && d->S == 3 && (!d->split || hsplit_ok) && d->Cout == BN && BN <= 128;
+  const bool hsplit = halo && d->split;
   {
     // IISEG_HALO_KB32=1 (experiment, off): 32-channel K blocks (64-byte rows, SWIZZLE_64B) for the layers whose resident
     // 144 KB filter bank (64 -> 128, 128 -> 64 channels) leaves room for only two 128-byte-row halo blocks; the ring
@@ -1735,9 +1893,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     // the per-tile timeline shows these layers bound by the issue rate of small-N MMAs (72 x M128 N64 K16 at ~66
     // cycles with both issuer warps active), not by reload latency.
     static const int env_kb32 = getenv("IISEG_HALO_KB32") ? atoi(getenv("IISEG_HALO_KB32")) : 0;
-    if (halo && env_kb32 && KB == 64 && !depool && 9 * Cin * BN * 2 >= 128 * 1024) KB = 32;
+    if (halo && !hsplit && env_kb32 && KB == 64 && !depool && 9 * Cin * BN * 2 >= 128 * 1024) KB = 32;
   }
-  int n_cblk_all = Cin / KB;
+  int n_cblk_all = hsplit ? 2 * (d->C[0] / KB) : Cin / KB;      // A blocks per tile (hsplit: hi blocks, then lo blocks)
   int box_h = 0, box_w = 0;       // TMA box extent in pixels
   int smem_halo = 0;
   if (halo) {
@@ -1745,7 +1903,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     const int row_b = KB * 2;
     const int b_all = 9 * n_cblk_all * BN * row_b;
     const int total = 227 * 1024 - 512 - (depool ? kDpReserve : 0);      // depool: room for the staging ring (checked below)
-    const int budget_rows = (total - b_all) / (2 * n_cblk_all) / 1024 * 1024 / row_b;     // rows one block may take
+    // rows one block may take: room for two tiles' blocks (split precision, whose bank is twice as large: at least the
+    // two-slot ring, one slot per issuer warp)
+    const int budget_rows = (total - b_all) / (hsplit ? 2 : 2 * n_cblk_all) / 1024 * 1024 / row_b;
     if (fuse_pool) {
       // pool + tie mask by warp shuffle: 8 x 14 outputs on a pitch-16 box (see conv_epilogue, kShflPool)
       p.TH = 8; p.TW = 14; p.pitch = 16;
@@ -1780,8 +1940,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       smem_halo = p.n_a * p.a_blk_bytes + b_all + 512 + dp_total;
     }
   }
-  if (!halo && KB == 32) { KB = 64; n_cblk_all = Cin / KB; }      // no halo plan: the per-tap kernels use 64-channel blocks
-  IISEG_CHECK(halo || KB == 64, "conv: a 16-channel source needs a 3x3 filter with Cout in {16,64,128} (halo-tile kernel)");
+  if (!halo && KB == 32) KB = 64;                                 // no halo plan: the per-tap kernels use 64-channel blocks
+  if (!halo) n_cblk_all = Cin / KB;
+  IISEG_CHECK(halo || KB == 64, "conv: a 16-channel source needs a 3x3 filter with Cout in {16,64,128} and an output window the halo-tile kernel can tile");
   IISEG_CHECK(halo || !depool, "conv: no halo-tile plan for this DePool2D-fused conv (window %dx%d, %d channels)", d->OH, d->OW, d->C[0]);
   if (!halo) {
     choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
@@ -1799,7 +1960,13 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       if (0.5 * 1.15 * (double)r128 < (double)r256) BN = 128;
     }
   }
+  const bool hs = halo && hsplit;
   for (int i = 0; i < IISEG_MAX_SRC; ++i) {
+    if (hs && i >= 2) {           // the third view repeats the hi block: the kernel reuses the one it loaded
+      p.tm_src[i] = p.tm_src[0];
+      p.n_cblk_src[i] = 0;
+      continue;
+    }
     if (d->src[i] != nullptr && depool) {
       if (encode_dense4d(&p.tm_src[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->src[0], d->C[0], d->depool_UW, d->depool_UH, d->N, 64, p.dp_pwb, p.dp_phb)) return -1;
       if (encode_dense4d(&p.tm_mask, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d->depool_mask, d->C[0] / 8, d->W / 2, d->H / 2, d->N, 8, p.dp_pwb, p.dp_phb)) return -1;
@@ -1811,6 +1978,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
     p.n_cblk_src[i] = d->C[i] / KB;
   }
   p.n_cblk = n_cblk_all;
+  p.n_bblk = n_cblk_all;
+  p.hsplit = hs ? 1 : 0;
   p.split = d->split;
   const int K = d->R * d->S * Cin;
   const long long Kw = d->w_koff > 0 ? (long long)K + (long long)(d->N - 1) * d->w_koff : K;     // all K slabs of the weight matrix
@@ -1837,7 +2006,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.tiles_h = ceil_div(covH, p.TH); p.tiles_w = ceil_div(covW, p.TW);
   p.pooled = reinterpret_cast<__nv_bfloat16*>(d->pooled); p.pool_mask = d->pool_mask; p.pool_zmask = d->pool_zmask;
   p.upd_y = d->upd_y; p.upd_y_bf16 = reinterpret_cast<__nv_bfloat16*>(d->upd_y_bf16); p.upd_active = d->upd_active;
-  p.upd_norm_acc = reinterpret_cast<unsigned long long*>(d->upd_norm_acc); p.upd_step = d->upd_step; p.upd_C = d->upd_C; p.upd_cpad = d->upd_cpad;
+  p.upd_norm_acc = reinterpret_cast<unsigned long long*>(d->upd_norm_acc); p.upd_step = d->upd_step; p.upd_step_dev = d->upd_step_dev; p.upd_C = d->upd_C; p.upd_cpad = d->upd_cpad; p.upd_split = d->upd_split;
   p.pwin_h = d->OH / 2; p.pwin_w = d->OW / 2;
   if (d->pool_H > 0) { p.PH = d->pool_H; p.PW = d->pool_W; p.p_h0 = d->oh0 / 2; p.p_w0 = d->ow0 / 2; }
   else { p.PH = p.pwin_h; p.PW = p.pwin_w; p.p_h0 = 0; p.p_w0 = 0; }
@@ -1848,6 +2017,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.inv_ntiles = 1.0f / p.n_ntiles; p.inv_tiles_w = 1.0f / p.tiles_w; p.inv_tiles_h = 1.0f / p.tiles_h;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
+  p.addend_cs = d->addend_cs > 0 ? d->addend_cs : ((d->split && !d->addend_f32) ? 2 * d->Cout : d->Cout);
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;
   if (d->depool_out != nullptr) {
     p.dpo_out = reinterpret_cast<__nv_bfloat16*>(d->depool_out); p.dpo_mask = d->depool_out_mask;
@@ -1880,12 +2050,8 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN / 2, KB, d->weight_ld)) return -1;       // each CTA loads half of a filter block
       const int max_pairs = num_sms() / 2;
       const int grid = 2 * (p.num_units < max_pairs ? p.num_units : max_pairs);
-      static bool configured = false;
-      if (!configured) {
-        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::kSmemBytes));
-        IISEG_CUDA(cudaFuncSetAttribute(conv_igemm_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<128>::kSmemBytes));
-        configured = true;
-      }
+      IISEG_SMEM_OPT_IN(conv_igemm_pair_kernel<256>, PairCfg<256>::kSmemBytes);
+      IISEG_SMEM_OPT_IN(conv_igemm_pair_kernel<128>, PairCfg<128>::kSmemBytes);
       if (BN == 256) conv_igemm_pair_kernel<256><<<grid, kNumThreads, PairCfg<256>::kSmemBytes, s>>>(p);
       else conv_igemm_pair_kernel<128><<<grid, kNumThreads, PairCfg<128>::kSmemBytes, s>>>(p);
       IISEG_LAUNCH_CHECK();

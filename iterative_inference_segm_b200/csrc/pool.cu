@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) maxpool2_mask_kernel(const uint4* __restr
 // pixels in the trailing odd row / column of the HxW map (no pool window) are zero.
 struct UnpoolParams {
   const uint4* u; const uint32_t* mask; uint4* out;
-  int C8, MC8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN, PHN;   // MC8: channel groups of the mask (C8, or C8/2 for split pairs)
+  int C8, UC8, MC8, H2, W2, UH, UW, u_h0, u_w0, OH, OW, o_h0, o_w0, PWN, PHN;   // MC8: channel groups of the mask (C8, or C8/2 for split pairs);
+                                                                                // UC8: channel groups per pixel of u (C8, or 2*C8 when only the hi halves of a pair tensor are read)
 };
 
 // One thread per (pooled pixel touched by the window, 8 channels): u and the mask word are read ONCE
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) unpool2_mask_kernel(const UnpoolParams p)
   uint4 val = make_uint4(0, 0, 0, 0);
   uint32_t bits = 0;
   if (ph < p.H2 && pw < p.W2) {
-    val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.C8 + cg);
+    val = ldg_nc_v4(p.u + ((n * p.UH + (ph - p.u_h0)) * p.UW + (pw - p.u_w0)) * p.UC8 + cg);
     bits = __ldg(p.mask + ((n * p.H2 + ph) * p.W2 + pw) * p.MC8 + (cg >= p.MC8 ? cg - p.MC8 : cg));
   }
   const uint32_t w[4] = {val.x, val.y, val.z, val.w};
@@ -123,7 +124,8 @@ extern "C" int iiseg_unpool2_mask_window_fwd(const void* u, const uint32_t* mask
               ph_lo, ph_hi, pw_lo, pw_hi);
   UnpoolParams p;
   p.u = reinterpret_cast<const uint4*>(u); p.mask = mask; p.out = reinterpret_cast<uint4*>(out);
-  p.MC8 = C / 8; p.C8 = split ? 2 * p.MC8 : p.MC8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
+  IISEG_CHECK(split >= 0 && split <= 2, "unpool: split must be 0, 1 or 2");
+  p.MC8 = C / 8; p.C8 = split == 1 ? 2 * p.MC8 : p.MC8; p.UC8 = split ? 2 * p.MC8 : p.MC8; p.H2 = H2; p.W2 = W2; p.UH = UH; p.UW = UW; p.u_h0 = u_h0; p.u_w0 = u_w0;
   p.OH = OH; p.OW = OW; p.o_h0 = o_h0; p.o_w0 = o_w0;
   p.PWN = (o_w0 + OW - 1) / 2 - o_w0 / 2 + 1;     // pooled columns / rows the window touches (incl. a trailing odd one)
   p.PHN = (o_h0 + OH - 1) / 2 - o_h0 / 2 + 1;

@@ -68,8 +68,9 @@ template <int kMode>
 __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
     const float* __restrict__ logits, float* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
     float* __restrict__ p_out, const int32_t* __restrict__ active, float* __restrict__ norm_partial,
-    int C, int HW, int Cpad, float step, int split) {
+    int C, int HW, int Cpad, float step, const float* __restrict__ step_dev, int split) {
   const int n = blockIdx.y;
+  if (kMode == 1 && step_dev != nullptr) step = __ldg(step_dev);
   if (kMode != 0 && active != nullptr && active[n] == 0) return;   // frozen image
   const int pix = blockIdx.x * kUpdBlock + threadIdx.x;
   float nrm = 0.f;
@@ -132,9 +133,10 @@ __global__ void __launch_bounds__(kUpdBlock) softmax_update_kernel(
 
 __global__ void norm_finalize_kernel(const float* __restrict__ norm_partial, float* __restrict__ norm,
                                      int32_t* __restrict__ active, int32_t* __restrict__ n_exec, int nblk,
-                                     float inv_hw, float eps) {
+                                     float inv_hw, float eps, const float* __restrict__ eps_dev) {
   const int n = blockIdx.x;
   if (active[n] == 0) return;
+  if (eps_dev != nullptr) eps = __ldg(eps_dev);
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nblk; i += blockDim.x) s += (double)norm_partial[(size_t)n * nblk + i];
@@ -155,9 +157,10 @@ __global__ void norm_finalize_kernel(const float* __restrict__ norm_partial, flo
 // one thread per image: the fused conv epilogue already reduced ||g||_2 to one fixed-point word per image
 __global__ void norm_finalize_fixed_kernel(unsigned long long* __restrict__ norm_acc, float* __restrict__ norm,
                                            int32_t* __restrict__ active, int32_t* __restrict__ n_exec, int N,
-                                           double inv_hw, float eps) {
+                                           double inv_hw, float eps, const float* __restrict__ eps_dev) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  if (eps_dev != nullptr) eps = __ldg(eps_dev);
   const unsigned long long acc = norm_acc[n];
   norm_acc[n] = 0ull;
   if (active[n] == 0) return;
@@ -179,21 +182,21 @@ extern "C" int iiseg_softmax_nchw(const float* logits, float* p, void* y_bf16, i
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<0><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, split);
+      logits, p, reinterpret_cast<__nv_bfloat16*>(y_bf16), nullptr, nullptr, nullptr, C, H * W, Cpad, 0.f, nullptr, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int iiseg_softmax_update(const float* logits, float* y, void* y_bf16, float* p_out, const int32_t* active,
                                     float* norm_partial, int N, int C, int H, int W, int Cpad, float step,
-                                    int split, void* stream) {
+                                    const float* step_dev, int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(logits && y && norm_partial, "softmax_update: null tensor");
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_update: bad shape");
   IISEG_CHECK(y_bf16 == nullptr || (Cpad >= 16 && Cpad % 8 == 0), "softmax_update: Cpad=%d", Cpad);
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<1><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, split);
+      logits, y, reinterpret_cast<__nv_bfloat16*>(y_bf16), p_out, active, norm_partial, C, H * W, Cpad, step, step_dev, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -205,27 +208,27 @@ extern "C" int iiseg_softmax_grad(const float* logits, const float* y, float* gr
   IISEG_CHECK(N > 0 && C >= 1 && C <= kMaxC && H > 0 && W > 0, "softmax_grad: bad shape");
   dim3 grid(iiseg_update_blocks(H, W), N);
   softmax_update_kernel<2><<<grid, kUpdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, 0);
+      logits, const_cast<float*>(y), nullptr, grad, nullptr, nullptr, C, H * W, 0, 0.f, nullptr, 0);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int iiseg_norm_finalize(const float* norm_partial, float* norm, int32_t* active, int32_t* n_exec, int N,
-                                   int H, int W, float eps, void* stream) {
+                                   int H, int W, float eps, const float* eps_dev, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(norm_partial && norm && active && n_exec, "norm_finalize: null tensor");
   norm_finalize_kernel<<<N, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      norm_partial, norm, active, n_exec, iiseg_update_blocks(H, W), 1.0f / (float)(H * W), eps);
+      norm_partial, norm, active, n_exec, iiseg_update_blocks(H, W), 1.0f / (float)(H * W), eps, eps_dev);
   IISEG_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int iiseg_norm_finalize_fixed(uint64_t* norm_acc, float* norm, int32_t* active, int32_t* n_exec, int N,
-                                         int H, int W, float eps, void* stream) {
+                                         int H, int W, float eps, const float* eps_dev, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(norm_acc && norm && active && n_exec, "norm_finalize_fixed: null tensor");
   norm_finalize_fixed_kernel<<<(N + 63) / 64, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<unsigned long long*>(norm_acc), norm, active, n_exec, N, 1.0 / ((double)H * (double)W), eps);
+      reinterpret_cast<unsigned long long*>(norm_acc), norm, active, n_exec, N, 1.0 / ((double)H * (double)W), eps, eps_dev);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

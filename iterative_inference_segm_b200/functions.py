@@ -149,9 +149,10 @@ class IterativeInference(object):
         self.void_label = _void_label(self.C, list(void_labels))
         self._state = {}
         self.graph_kernel_nodes = 0
+        self.graph_captures = 0
 
-    def _buffers(self, B, H, W, num_iter, per_iter):
-        key = (B, H, W, num_iter, per_iter)
+    def _buffers(self, B, H, W, num_iter, per_iter, record_y=False):
+        key = (B, H, W, num_iter, per_iter, record_y)
         st = self._state.get(key)
         if st is None:
             dev = self.net.device
@@ -167,8 +168,11 @@ class IterativeInference(object):
                 'norm_hist': torch.zeros((num_iter, B), dtype=torch.float32, device=dev),
                 'partial': torch.zeros((B, K.update_blocks(H, W)), dtype=torch.float32, device=dev),
                 'norm_acc': torch.zeros((B,), dtype=torch.int64, device=dev),
+                'step': torch.zeros((1,), dtype=torch.float32, device=dev),      # device scalars: one captured graph
+                'eps': torch.zeros((1,), dtype=torch.float32, device=dev),       # serves every (step, eps)
                 'final': MetricsAccumulator(B, self.C, dev),
                 'iter': [MetricsAccumulator(B, self.C, dev) for _ in range(num_iter)] if per_iter else None,
+                'y_hist': torch.zeros((num_iter, B, self.C, H, W), dtype=torch.float32, device=dev) if record_y else None,
                 'graph': {},
             }
             self._state[key] = st
@@ -187,7 +191,7 @@ class IterativeInference(object):
         for it in range(num_iter):
             # the first iteration of a batch computes the whole contracting path (h is new); later ones only
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
-            if self.fuse_update and not net.split:
+            if self.fuse_update and not net.split_up:
                 # softmax tail + update + norm in the epilogue of up_conv1: the logits never reach HBM
                 net.logits(st['h'], st['y_bf16'], full_down=(it == 0),
                            update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))
@@ -197,6 +201,8 @@ class IterativeInference(object):
                 K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
                 K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])
+            if st['y_hist'] is not None:
+                st['y_hist'][it].copy_(st['y'])
             if per_iter:
                 acc = st['iter'][it]
                 K.metrics_accumulate(st['y'], acc.cm, acc.counts, acc.sqerr, labels=st['labels'],
@@ -207,17 +213,18 @@ class IterativeInference(object):
                                  void_label=self.void_label)
 
     def run(self, h, y0, step, num_iter, eps=EPSILON, labels=None, onehot=None, per_iter_metrics=False,
-            use_graph=True):
+            use_graph=True, record_y=False):
         """h: NHWC bf16 (internal, from FCN8Net.forward) or NCHW fp32; y0: NCHW fp32;
         labels: int (B,H,W) class indices with void = the void label, or onehot: the reference's
         (B,C+1,H,W) float32 target (argmax'd once on the device), or neither.
         Returns a dict of device tensors: y (B,C,H,W), n_exec, norm_hist, cm / counts /
-        sqerr of the final batch-level val_fn, and the per-iteration accumulators."""
+        sqerr of the final batch-level val_fn, and the per-iteration accumulators.  `record_y` (parity tooling):
+        also keeps y after every iteration in 'y_hist' (num_iter, B, C, H, W)."""
         B, Cc, H, W = y0.shape
         assert Cc == self.C
         with_metrics = labels is not None or onehot is not None
         per_iter = bool(per_iter_metrics and with_metrics)
-        st = self._buffers(B, H, W, num_iter, per_iter)
+        st = self._buffers(B, H, W, num_iter, per_iter, bool(record_y))
         if h.dtype == torch.bfloat16:
             st['h'].copy_(h)
         else:
@@ -229,11 +236,17 @@ class IterativeInference(object):
         elif labels is not None:
             st['labels'].copy_(labels)
         if use_graph:
-            gkey = (float(step), float(eps), with_metrics)
+            # step and eps are device scalars read by the kernels at run time: the graph is captured once per shape and
+            # replayed for any step size / threshold (the seven step values of the valid sweep share it)
+            st['step'].fill_(float(step))
+            st['eps'].fill_(float(eps))
+            step, eps = st['step'], st['eps']
+            gkey = (with_metrics,)
             g = st['graph'].get(gkey)
             if g is None:
-                # warm-up outside capture (lazy module loading, smem attribute calls), then capture
-                self._loop(st, step, 1, eps, with_metrics, False)
+                # warm-up outside capture (lazy module loading, smem attribute calls) with every launch shape of the
+                # captured loop: the full first iteration, a windowed one and the per-iteration metrics; then capture
+                self._loop(st, step, min(num_iter, 2), eps, with_metrics, per_iter)
                 torch.cuda.synchronize()
                 st['y'].copy_(y0)
                 K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'], split=self.net.split)
@@ -243,10 +256,11 @@ class IterativeInference(object):
                 with torch.cuda.graph(g):
                     self._loop(st, step, num_iter, eps, with_metrics, per_iter)
                 self.graph_kernel_nodes = _lib.launch_count() - n0     # library kernels per replay
+                self.graph_captures += 1
                 st['graph'][gkey] = g
             g.replay()
         else:
             self._loop(st, step, num_iter, eps, with_metrics, per_iter)
         return {'y': st['y'], 'n_exec': st['n_exec'], 'norm_hist': st['norm_hist'],
                 'cm': st['final'].cm, 'counts': st['final'].counts, 'sqerr': st['final'].sqerr,
-                'iter': st['iter']}
+                'iter': st['iter'], 'y_hist': st['y_hist']}

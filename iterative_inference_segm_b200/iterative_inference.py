@@ -36,7 +36,7 @@ DAE_DICT_DEFAULTS = {'kind': 'fcn8', 'dropout': 0.0, 'skip': True, 'unpool_type'
 def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path=None, loadpath=None,
                    dataset='camvid', fcn_params=None, dae_params=None, precision='bf16'):
     """The network-construction block of `inference` (iterative_inference.py:127-179).
-    `precision` ('bf16' | 'fp32x3') selects the arithmetic of both nets (see models/DAE_h.py)."""
+    `precision` ('bf16' | 'fp32x3' | 'mixed') selects the arithmetic of both nets (see models/DAE_h.py)."""
     if segm_net == 'fcn8':
         fcn = buildFCN8(nb_in_channels, None, n_classes=n_classes, void_labels=void_labels,
                         path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'),
@@ -75,11 +75,13 @@ class _BatchStager(object):
     is fetched from the iterator and copied while the current batch's loop runs on the device (the reference's iterator
     prefetches with threads, data_loader.py:58)."""
 
-    def __init__(self, data_iter, n_batches, device):
+    def __init__(self, data_iter, n_batches, device, shard=None):
         self.it, self.n, self.dev = data_iter, n_batches, device
         self.stream = torch.cuda.Stream(device=device)
         self.pinned = [{}, {}]
         self.k = 0
+        self.lo, self.hi = shard if shard is not None else (0, n_batches)      # this rank's batches [lo, hi)
+        self.taken = 0
 
     def _stage(self, slot, name, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float32)
@@ -92,10 +94,14 @@ class _BatchStager(object):
 
     def fetch(self):
         """Next (X, L, Xd, Ld, ready_event) or None; the device tensors are valid after `ready_event`."""
+        while self.k < self.n and not (self.lo <= self.k < self.hi):
+            self.it.next()              # another rank's batch: advance the shared iterator order past it
+            self.k += 1
         if self.k >= self.n:
             return None
-        slot = self.k % 2
+        slot = self.taken % 2
         self.k += 1
+        self.taken += 1
         X, L = self.it.next()
         self.stream.synchronize()                 # the pinned buffers of this slot were last used two fetches ago
         Xd, Ld = self._stage(slot, 'X', X), self._stage(slot, 'L', L)
@@ -139,9 +145,15 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
     cm_total = np.zeros((n_classes, n_classes), np.int64)
     say = print if verbose else (lambda *a, **k: None)
     say('Inference step: ' + str(learn_step) + ' num iter ' + str(num_iter))
-    stager = _BatchStager(data_iter, n_batches_test, torch.device('cuda', torch.cuda.current_device()))
+    # Multi-GPU (torch.distributed initialised, one process per GPU): the batches are sharded contiguously over the
+    # ranks (sharding.shard_range; whole batches, so per-batch means and DenseNet's batch statistics are those of the
+    # single-process run), weights are replicated and the only exchange is the final SUM all-reduce of the totals.
+    from .sharding import World, shard_range
+    world = World()
+    b_lo, b_hi = shard_range(n_batches_test, world.rank, world.size)
+    stager = _BatchStager(data_iter, n_batches_test, torch.device('cuda', torch.cuda.current_device()), (b_lo, b_hi))
     nxt = stager.fetch()
-    for i in range(n_batches_test):
+    for i in range(b_lo, b_hi):
         X, L, Xd, Ld, ready = nxt
         torch.cuda.current_stream().wait_event(ready)
         Xd.record_stream(torch.cuda.current_stream()); Ld.record_stream(torch.cuda.current_stream())
@@ -188,12 +200,29 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
         cm_total += cm
         tot['acc'] += acc; tot['jacc'] = tot['jacc'] + jacc; tot['rec'] += rec
         if verbose:
-            print_results('>>>>> FCN:', tot['rec_fcn'], tot['acc_fcn'], tot['jacc_fcn'], i + 1)
-            print_results('>>>>> FCN+DAE:', tot['rec_dae'], tot['acc_dae'], tot['jacc_dae'], i + 1)
-            print_results('>>>>> ITERATIVE INFERENCE:', tot['rec'], tot['acc'], tot['jacc'], i + 1)
+            print_results('>>>>> FCN:', tot['rec_fcn'], tot['acc_fcn'], tot['jacc_fcn'], i - b_lo + 1)
+            print_results('>>>>> FCN+DAE:', tot['rec_dae'], tot['acc_dae'], tot['jacc_dae'], i - b_lo + 1)
+            print_results('>>>>> ITERATIVE INFERENCE:', tot['rec'], tot['acc'], tot['jacc'], i - b_lo + 1)
         if save_batches:                                                # iterative_inference.py:293
             np.savez(os.path.join(savepath, 'batch' + str(i) + '.npz'), X=X, L=L, Y_ii=Y_ii.cpu().numpy(),
                      Y_fcn=Y.cpu().numpy())
+    if world.size > 1:          # totals over all shards: integer counts (exact in float64 / int64) and per-batch means
+        dev = torch.device('cuda', torch.cuda.current_device())
+        keys = sorted(tot)
+        parts = [np.broadcast_to(np.asarray(tot[k], dtype=np.float64), (2, n_classes) if 'jacc' in k else ()).reshape(-1) for k in keys]
+        flat = torch.tensor(np.concatenate(parts), dtype=torch.float64, device=dev)
+        world.allreduce_sum(flat)
+        cm_dev = torch.from_numpy(cm_total).to(dev)
+        world.allreduce_sum(cm_dev)
+        cm_total = cm_dev.cpu().numpy()
+        flat, off = flat.cpu().numpy(), 0
+        for k, part in zip(keys, parts):
+            v = flat[off:off + part.size]
+            tot[k] = v.reshape(2, n_classes).astype(np.float32) if 'jacc' in k else np.float32(v[0])
+            off += part.size
+        gathered = [None] * world.size
+        torch.distributed.all_gather_object(gathered, n_exec_all)
+        n_exec_all = [n for g in gathered for n in g]
     nb = n_batches_test
     return {'fcn': results_values(tot['rec_fcn'], tot['acc_fcn'], tot['jacc_fcn'], nb),
             'fcn_dae': results_values(tot['rec_dae'], tot['acc_dae'], tot['jacc_dae'], nb),
@@ -240,7 +269,7 @@ def main():
     parser.add_argument('-savepath', type=str, default='./iiseg_out/')
     parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
     parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
-    parser.add_argument('-precision', type=str, default='bf16', choices=['bf16', 'fp32x3'])
+    parser.add_argument('-precision', type=str, default='bf16', choices=['bf16', 'fp32x3', 'mixed'])
     args = parser.parse_args()
     inference(args.dataset, args.segmentation_net, float(args.step), int(args.num_iter), which_set=args.which_set,
               savepath=args.savepath, loadpath=args.loadpath, weights_path=args.weights_path,

@@ -24,8 +24,9 @@ STEPS = [.01, .02, .05, .08, .1, .5, 1.]      # iterative_inference_valid.py:373
 
 def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, which_set='val', data_iter=None,
           fcn_params=None, dae_params=None, weights_path=None, loadpath=None, verbose=True,
-          precision='bf16', savepath=None):
-    """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter])."""
+          precision='bf16', savepath=None, eps=_EPSILON):
+    """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter]).  `eps` is the convergence
+    threshold of the loop (the reference's _EPSILON = 1e-3, iterative_inference_valid.py:53)."""
     dae_dict = dict(DAE_DICT_DEFAULTS)
     dae_dict.update(dae_dict_updates)
     if data_iter is None:
@@ -36,25 +37,37 @@ def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, whic
     pred_fcn_fn = F.function_pred_fcn(fcn)
     loop = F.IterativeInference(dae, n_classes, void_labels)
     valid_mats = np.zeros((len(steps), 2, n_classes, num_iter))        # float64 like the reference (:231)
-    for _ in range(data_iter.nbatches):
+    # multi-GPU: contiguous batch shards per rank, one SUM all-reduce of valid_mats at the end (integer counts held in
+    # float64: exact, order-free)
+    from .sharding import World, shard_range
+    world = World()
+    b_lo, b_hi = shard_range(data_iter.nbatches, world.rank, world.size)
+    for b in range(data_iter.nbatches):
         X, L = data_iter.next()
+        if not (b_lo <= b < b_hi):
+            continue
         Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
         Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).cuda()
         pred = pred_fcn_fn(Xd)                                         # once per batch, shared by every step value
         Y, H = pred[-1], pred[:-1]
         for si, s in enumerate(steps):
-            res = loop.run(H[0], Y, s, num_iter, eps=_EPSILON, onehot=Ld, per_iter_metrics=True)
+            res = loop.run(H[0], Y, s, num_iter, eps=eps, onehot=Ld, per_iter_metrics=True)
             for it, acc in enumerate(res['iter']):
                 cms = acc.cm.cpu().numpy().reshape(-1, n_classes, n_classes)
                 for cm in cms:                                         # per image: val_fn(y_im, t_im) of the reference
                     if cm.sum() > 0:
                         valid_mats[si, :, :, it] += F.jaccard_from_cm(cm)
-    if savepath is not None:                       # the reference writes one `iterations<step>.npz` per step value (:303)
+    if world.size > 1:
+        vm = torch.from_numpy(valid_mats).cuda()
+        world.allreduce_sum(vm)
+        valid_mats = vm.cpu().numpy()
+    if savepath is not None and world.rank == 0:   # the reference writes one `iterations<step>.npz` per step value (:303)
         os.makedirs(savepath, exist_ok=True)
         for si, s in enumerate(steps):
             np.savez(os.path.join(savepath, 'iterations' + str(s) + '.npz'), valid_mats[si])
     with np.errstate(divide='ignore', invalid='ignore'):
         all_results = np.nanmean(valid_mats[:, 0] / valid_mats[:, 1], axis=1)
+    sweep.last_graph_captures = loop.graph_captures         # one captured graph serves every step value
     if verbose:
         best = all_results.max(1)
         print('Best step: ' + str(steps[int(best.argmax())]))
@@ -68,7 +81,8 @@ def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_update
               test_from_0_255=False, **kw):
     """Single-step form with the reference's signature (iterative_inference_valid.py:56-59): returns
     `res = nanmean(valid_mat[0] / valid_mat[1], axis=0)` (`:297`)."""
-    res, _ = sweep(dataset, segm_net, [learn_step], num_iter, dae_dict_updates, which_set, loadpath=loadpath, **kw)
+    res, _ = sweep(dataset, segm_net, [learn_step], num_iter, dae_dict_updates, which_set, loadpath=loadpath,
+                   savepath=savepath, **kw)
     return res[0]
 
 

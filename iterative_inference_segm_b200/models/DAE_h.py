@@ -31,20 +31,25 @@ def _levels(concat_h, additional_pool):
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
                  n_filters=64, additional_pool=2, device='cuda', precision='bf16'):
-        """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant) or 'fp32x3'
+        """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
-        hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work)."""
+        hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
+        'mixed': fp32x3 on the contracting path -- whose conv outputs decide the pool tie masks, the one
+        discontinuous function on the path -- and bf16 on the expanding path, which only carries smooth
+        errors (oracle/precision_mix.py: same parity numbers as 'fp32x3' on every iteration)."""
         K.require_device()
-        assert precision in ('bf16', 'fp32x3'), precision
+        assert precision in ('bf16', 'fp32x3', 'mixed'), precision
         self.precision = precision
-        self.split = precision == 'fp32x3'
+        self.split = precision != 'bf16'          # contracting path (and the h / y input format)
+        self.split_up = precision == 'fp32x3'     # expanding path
         # IISEG_FUSE_DEPOOL=1: last DePool2D expanded inside the loader of up_conv1 (bf16 variant; bit-identical results).
         # Off by default: measured 0.179 ms against 0.050 (unpool) + 0.112 (conv) -- see DESIGN.md 3.7
         self.fuse_depool = os.environ.get('IISEG_FUSE_DEPOOL', '0') == '1'
         # IISEG_DEPOOL_EPILOGUE=1: DePool2D of level p-1 written by the epilogue of up_conv_p (bf16 variant, bit-identical).
         # Off by default: measured 163 vs 165 images/s -- the 4x larger epilogue stores cost what the unpool launch did
         self.fuse_depool_out = os.environ.get('IISEG_DEPOOL_EPILOGUE', '0') == '1'
-        self.cm = 2 if self.split else 1          # bf16 channels per logical channel in activation tensors
+        self.cm = 2 if self.split else 1          # bf16 channels per logical channel in activation tensors (contracting path)
+        self.cm_up = 2 if self.split_up else 1
         assert n_classes <= 16
         self.n_classes = n_classes
         self.nb_h = nb_features_to_concat
@@ -53,7 +58,7 @@ class DAENet(object):
         self.n_pool, self.total = _levels(concat_h, additional_pool)
         assert self.n_pool >= 1, 'conditioning must be concatenated at a pool layer'
         self.device = torch.device(device)
-        self.y_cpad = K.pad_channels(n_classes, narrow=not self.split)    # channels of the bf16 copy of y
+        self.y_cpad = K.pad_channels(n_classes, narrow=True)    # channels of the bf16 copy of y (16: 32-byte K blocks)
         assert len(params) == 4 * self.total, 'expected %d arrays, got %d' % (4 * self.total, len(params))
         # filters per level: n_filters * 2**p, p < 6 (models/fcn_down.py:96-99)
         self.filters = []
@@ -87,7 +92,7 @@ class DAENet(object):
             W, b = params[2 * (self.total + i)], params[2 * (self.total + i) + 1]
             n_cl = n_classes if p == 1 else self.filters[p - 2]   # models/fcn_up.py:29-34
             cout_pad = 16 if p == 1 else n_cl
-            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split))
+            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split_up))
             up_in = n_cl
         self._ws = {}
 
@@ -144,10 +149,12 @@ class DAENet(object):
             D[p] = (hl & ~1, min((hh + 1) & ~1, (Sh // 2) * 2), wl & ~1, min((wh + 1) & ~1, (Sw // 2) * 2))
         return D
 
-    def executed_conv_flops(self, H, W, steady_state=True):
+    def executed_conv_flops(self, H, W, steady_state=True, tensor=False):
         """Executed algorithmic FLOPs (2*MAC, real channel counts) of the 2P conv launches of one
         application, per image: cone windows on the expanding path; on the contracting path the
-        y-dependent windows (`steady_state`, iterations 2..N) or the full maps (first iteration)."""
+        y-dependent windows (`steady_state`, iterations 2..N) or the full maps (first iteration).
+        `tensor`: the FLOPs the tensor cores execute -- three bf16 products per fp32-accurate MAC on the
+        layers that run split precision ('fp32x3', 'mixed')."""
         sizes = self.level_sizes(H, W)
         Wc, _ = self.cone_windows(H, W)
         D = self.down_windows(H, W)
@@ -158,13 +165,13 @@ class DAENet(object):
             f = 2.0 * (hh - hl) * (wh - wl) * cin * self.filters[p] * 9
             if p == self.n_pool and not steady_state:    # the hoisted h half runs once, with the first iteration
                 f += 2.0 * sizes[p][0] * sizes[p][1] * self.nb_h * self.filters[p] * 9
-            fl.append(f)
+            fl.append(f * (3.0 if (tensor and self.split) else 1.0))
             cin = self.filters[p]
         up_in = self.filters[-1]
         for p in range(self.total, 0, -1):
             n_cl = self.n_classes if p == 1 else self.filters[p - 2]
             hl, hh, wl, wh = Wc[p]
-            fl.append(2.0 * (hh - hl) * (wh - wl) * up_in * n_cl * 9)
+            fl.append(2.0 * (hh - hl) * (wh - wl) * up_in * n_cl * 9 * (3.0 if (tensor and self.split_up) else 1.0))
             up_in = n_cl
         return fl
 
@@ -186,11 +193,11 @@ class DAENet(object):
         for p in range(1, self.total + 1):
             ul, uh, vl, vh = Wu[p]
             # zeros: with the DePool2D-in-the-producer path the trailing odd row / column of a level is never written
-            ws['unpool'][p] = torch.zeros((B, uh - ul, vh - vl, self.cm * self.filters[p - 1]), dtype=bf, device=dev)
+            ws['unpool'][p] = torch.zeros((B, uh - ul, vh - vl, self.cm_up * self.filters[p - 1]), dtype=bf, device=dev)
             if p > 1:   # up_conv_p output: level-p window, channels of level p-1; skip partner pool_{p-1} has size S_p
                 hl, hh, wl, wh = Wc[p]
                 assert sizes[p - 1] == tuple(ws['pool'][p - 2].shape[1:3]), 'skip-sum needs equal sizes'
-                ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.cm * self.filters[p - 2]), dtype=bf, device=dev)
+                ws['upconv'][p] = torch.empty((B, hh - hl, wh - wl, self.cm_up * self.filters[p - 2]), dtype=bf, device=dev)
         hp = sizes[self.n_pool]
         ws['hproj'] = torch.empty((B, hp[0], hp[1], self.filters[self.n_pool]), dtype=torch.float32, device=dev)
         ws['logits'] = torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)
@@ -203,7 +210,7 @@ class DAENet(object):
         Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16).
         `full_down=False` recomputes only the y-dependent windows of the contracting path; valid when
         the workspace already holds a full pass for the same h (see `down_windows`).
-        `update` (bf16 variant): dict(y, active, norm_acc, step) -- the softmax tail and the
+        `update` (bf16 expanding path: 'bf16' and 'mixed'): dict(y, active, norm_acc, step) -- the softmax tail and the
         iterative-inference update run in the epilogue of the last conv (y and y_bf16 are updated in
         place, the logits are never stored) and None is returned."""
         B, H, W, _ = y_bf16.shape
@@ -213,7 +220,8 @@ class DAENet(object):
         assert tuple(h_bf16.shape) == (B,) + self.h_spatial(H, W) + (self.cm * self.h_pad,), \
             (tuple(h_bf16.shape), self.h_spatial(H, W), self.h_pad)
         assert y_bf16.shape[3] == self.cm * self.y_cpad
-        sp = self.split
+        sp, spu = self.split, self.split_up
+        mixed = sp and not spu       # pair tensors on the way down, plain bf16 on the way up
         x = y_bf16
         D = None if full_down else self.down_windows(H, W)
         if full_down:       # new h: the iteration-invariant half of the concat conv, once per batch, fp32
@@ -255,8 +263,9 @@ class DAENet(object):
             if prefilled:        # the previous conv's epilogue already wrote DePool2D(u) into this level's window
                 up = ws['unpool'][p]
             else:
+                # mixed: the first unpool reads the hi halves of the contracting path's pool pair
                 up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
-                               window=(ul, vl, uh - ul, vh - vl), split=sp)
+                               window=(ul, vl, uh - ul, vh - vl), split=(2 if (mixed and i == 0) else spu))
             win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
             if p > 1 and self.fuse_depool_out and not sp and not (p == 2 and self.fuse_depool):
                 # skip-sum, then DePool2D for the next level written straight from this conv's epilogue (u itself is
@@ -268,14 +277,14 @@ class DAENet(object):
             elif p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
                 prefilled = False
                 u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],
-                             addend_off=(hl, wl), out=ws['upconv'][p], split=sp)
+                             addend_off=(hl, wl), out=ws['upconv'][p], split=spu, addend_pair_hi=mixed)
                 u_origin = (hl, wl)
             else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
                 if update is not None:
                     K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True,
-                             update=dict(update, y_bf16=y_bf16, C=self.n_classes))
+                             update=dict(update, y_bf16=y_bf16, C=self.n_classes, y_split=sp))
                     return None
-                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=sp)
+                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=spu)
         return ws['logits']
 
 

@@ -39,11 +39,12 @@ class LayerHandle(object):
 
 class FCN8Net(object):
     def __init__(self, nb_in_channels, n_classes, params, temperature=1.0, device='cuda', precision='bf16'):
-        """precision: 'bf16' or 'fp32x3' (see DAENet)."""
+        """precision: 'bf16', or 'fp32x3' / 'mixed' (see DAENet; FCN8 has no expanding path of its own and its output
+        y0 enters y directly, so both run every layer fp32-accurate)."""
         K.require_device()
-        assert precision in ('bf16', 'fp32x3'), precision
+        assert precision in ('bf16', 'fp32x3', 'mixed'), precision
         self.precision = precision
-        self.split = sp = precision == 'fp32x3'
+        self.split = sp = precision != 'bf16'
         self.cm = 2 if sp else 1
         assert n_classes <= 16
         assert len(params) == 2 * len(PARAM_ORDER), 'expected %d arrays, got %d' % (2 * len(PARAM_ORDER), len(params))
@@ -55,7 +56,7 @@ class FCN8Net(object):
         cin = nb_in_channels
         for stage in VGG_STAGES:
             for name, cout in stage:
-                cpad = K.pad_channels(cin, narrow=(name == 'conv1_1' and not sp))
+                cpad = K.pad_channels(cin, narrow=(name == 'conv1_1'))
                 self.w[name] = pack_conv(*P[name], [(cin, cpad)], cout, self.device, split=sp)
                 cin = cout
         self.w['fc6'] = pack_conv(*P['fc6'], [(512, 512)], 4096, self.device, split=sp)
@@ -76,7 +77,7 @@ class FCN8Net(object):
         assert Cin == self.nb_in_channels
         out = {}
         sp, cm = self.split, self.cm
-        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=not sp), split=sp)
+        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=True), split=sp)
         for si, stage in enumerate(VGG_STAGES):
             for ci, (name, cout) in enumerate(stage):
                 Wk, bk = self.w[name]

@@ -41,3 +41,15 @@ class World(object):
         if self.size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t
+
+    def allreduce_sum_async(self, t):
+        """Starts the SUM all-reduce of `t` (ordered after the kernels already queued on the current stream) and returns
+        a handle with `.wait()`; the reduction runs on the backend's own stream, under whatever is launched next."""
+        if self.size > 1:
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+        return _Done()
+
+
+class _Done(object):
+    def wait(self):
+        return True

@@ -82,6 +82,8 @@ class _Layer(object):
 
 
 class DAETrainer(object):
+    BUCKET_BYTES = 32 << 20        # gradient all-reduce bucket size (NVSwitch: sized for launch latency / overlap, not link count)
+
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
                  additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda'):
         K.require_device()
@@ -118,6 +120,23 @@ class DAETrainer(object):
         self.sums = torch.zeros((4,), dtype=torch.float64, device=dev)
         self._graphs = {}
         self.last_loss = None
+        # One flat fp32 buffer holds the 24 weight-gradient matrices in the order backward produces them (expanding path
+        # from the output, then the contracting path from the bottleneck): the data-parallel step all-reduces it in a
+        # few large buckets, each launched as soon as its last layer's gradient is written, under the rest of backward.
+        order = [self.up[P - p] for p in range(1, P + 1)] + [self.down[p - 1] for p in range(P, 0, -1)]
+        self._grad_flat = torch.zeros((sum(l.cout_pad * l.nb for l in order),), dtype=torch.float32, device=dev)
+        off = 0
+        for l in order:
+            l.grad = self._grad_flat[off:off + l.cout_pad * l.nb].view(l.cout_pad, l.nb)
+            l.grad_off = off
+            off += l.cout_pad * l.nb
+        self._buckets, start, last = [], 0, None            # [(lo, hi, id of the layer that completes the bucket)]
+        for l in order:
+            end = l.grad_off + l.cout_pad * l.nb
+            if (end - start) * 4 >= self.BUCKET_BYTES or l is order[-1]:
+                self._buckets.append((start, end, id(l)))
+                start = end
+        self._works = []
 
     def layers(self):
         return self.down + self.up
@@ -207,11 +226,15 @@ class DAETrainer(object):
             row += c
         assert row == lay.cin_pad
         if merged:
-            lay.grad = K.wgrad_gemm(gT, xT, lay.g_rstride, [(0, r * Gw) for r in range(3)], slabs, lay.nb)
+            K.wgrad_gemm(gT, xT, lay.g_rstride, [(0, r * Gw) for r in range(3)], slabs, lay.nb, out=lay.grad)
         else:
             groups = [(s_ * lay.cin_pad, r * Gw) for r in range(3) for s_ in range(3)]
-            lay.grad = K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb)
+            K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb, out=lay.grad)
         K.bias_grad(g, lay.grad, lay.bias_col)
+        if self._dp_world is not None:           # data parallel: this layer may complete a bucket -> all-reduce it now
+            for lo, hi, last in self._buckets:
+                if last == id(lay):
+                    self._works.append(self._dp_world.allreduce_sum_async(self._grad_flat[lo:hi]))
         return lay.grad
 
     def _dgrad(self, lay, g, window, addend=None):
@@ -219,7 +242,13 @@ class DAETrainer(object):
         flipped / transposed bank (position q relative to g's origin is output index q + 1)."""
         return K.conv2d(g, lay.wt, lay.zero_bias_t[:lay.ci_t].contiguous(), 3, 3, 2, relu=False, window=window, addend=addend)
 
-    def backward(self, target, world=None):
+    _dp_world = None
+
+    def backward(self, target, world=None, overlap=False):
+        """`overlap` (data parallel): gradient buckets are all-reduced asynchronously as backward completes them; the
+        caller waits on `self._works` before the update."""
+        self._dp_world = world if (world is not None and overlap) else None
+        self._works = []
         st, geo = self.st, self.geo
         B, H, W = st['B'], st['H'], st['W']
         sizes, Wc, Wu, P = self._sizes, self.Wc, self.Wu, geo.total
@@ -290,10 +319,25 @@ class DAETrainer(object):
         self.forward(h_bf16, y, noise_main, noise_mask)
         self.backward(target, world)
         if world is not None:           # per-rank gradients already carry the global denominators: plain sum
-            for lay in self.layers():
-                world.allreduce_sum(lay.grad)
+            world.allreduce_sum(self._grad_flat)
         self.update()
         return self.last_loss
+
+    def step_dp(self, h_bf16, y, target, noise_main=None, noise_mask=None, world=None):
+        """Data-parallel step with the gradient all-reduce bucketed (BUCKET_BYTES) and launched under backward: bucket k
+        is reduced on NCCL's stream while the layers of bucket k+1.. are still being differentiated; the update waits
+        for the last bucket only.  Same result as `step(..., world=world)` (same sums, same order inside NCCL)."""
+        self.forward(h_bf16, y, noise_main, noise_mask)
+        self.backward(target, world, overlap=True)
+        for w in self._works:
+            w.wait()                   # stream-level wait: the update kernels queue behind the reductions
+        self._works, self._dp_world = [], None
+        self.update()
+        return self.last_loss
+
+    def dp_info(self):
+        return {'buckets': len(self._buckets), 'bucket_bytes': [int((hi - lo) * 4) for lo, hi, _ in self._buckets],
+                'gradient_bytes': int(self._grad_flat.numel() * 4), 'overlap': 'buckets all-reduced asynchronously under backward'}
 
     def step_graphed(self, h_bf16, y, target, noise_main=None, noise_mask=None):
         """Single-device `step` as one CUDA graph replay (~170 launches per step otherwise go through the host one by
@@ -302,7 +346,13 @@ class DAETrainer(object):
         exactly one training step."""
         ins = [h_bf16, y, target, noise_main, noise_mask]
         key = tuple((tuple(t.shape), t.dtype) if t is not None else None for t in ins)
+        # lr / sigma / lmb / rho / eps are kernel arguments passed by value, i.e. frozen into a captured graph: they are
+        # part of the graph's identity, and a change (the reference anneals lr every epoch, train_dae.py:424) drops the
+        # stale graph and captures a new one on the next call
+        hp = (float(self.lr), float(self.sigma), float(self.lmb), float(self.rho), float(self.eps))
         ent = self._graphs.get(key)
+        if ent is not None and ent != 'warm' and ent[2] != hp:
+            ent = self._graphs[key] = 'warm'
         if ent is None:
             self._graphs[key] = 'warm'
             return self.step(*ins)
@@ -312,8 +362,8 @@ class DAETrainer(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):             # capture executes nothing
                 self.step(*bufs)
-            ent = self._graphs[key] = (g, bufs)
-        g, bufs = ent
+            ent = self._graphs[key] = (g, bufs, hp)
+        g, bufs, _ = ent
         for b_, t in zip(bufs, ins):
             if t is not None:
                 b_.copy_(t)
@@ -332,3 +382,172 @@ class DAETrainer(object):
                 c0 += padded
             out += [torch.cat(parts, dim=3).permute(0, 3, 1, 2).contiguous(), lay.grad[:lay.cout, lay.bias_col].clone()]
         return out
+
+
+# ---------------------------------------------------------------------------
+# The host loop of the reference's train() (train_dae.py:351-457): epochs, validation, learning-rate annealing,
+# patience, best / last checkpoints in the reference's positional .npz layout.
+# ---------------------------------------------------------------------------
+def validate(trainer, h_bf16, y, target):
+    """`val_fn` of train_dae.py:338: [test_loss, test_jacc (2, C) float32, test_mse_loss] with the deterministic DAE
+    (no noise; with noise == 0 at build time the mask sub-graph is deterministic too, layers/mylayers.py:91-93)."""
+    from .functions import MetricsAccumulator, jaccard_from_cm
+    logits = trainer.forward(h_bf16, y, None, None)
+    K.loss_grad(logits, target, trainer.C, trainer.lmb, trainer.sums, passes=1)          # loss sums only
+    s = trainer.sums.cpu()
+    loss = float(s[0] / s[1] + trainer.lmb * s[2] / s[3])
+    B, _, H, W = y.shape
+    p = torch.empty((B, trainer.C, H, W), dtype=torch.float32, device=y.device)
+    K.softmax_nchw(logits, trainer.C, p)
+    acc = MetricsAccumulator(B, trainer.C, y.device)
+    K.metrics_accumulate(p, acc.cm, acc.counts, acc.sqerr, onehot=target, void_label=trainer.C)
+    se = acc.sqerr.sum(0).cpu().numpy()
+    return loss, jaccard_from_cm(acc.cm.sum(0).cpu().numpy()), float(se[0] / se[1])
+
+
+def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e-4, num_epochs=500, max_patience=100,
+          optimizer='rmsprop', training_loss=['squared_error'], batch_size=[10, 1, 1], ae_h=False, dae_dict_updates={},
+          data_augmentation={}, savepath=None, loadpath=None, resume=False, train_from_0_255=False, lmb=1,
+          full_im_ft=False, train_iter=None, val_iter=None, fcn_params=None, dae_params=None, weights_path=None,
+          seed=0, verbose=True):
+    """Same signature as the reference's train() (train_dae.py:54-60) plus in-memory iterators / checkpoints.  Built for
+    the benchmark configuration (kind='standard', trackind unpool, rmsprop, crossentropy + squared_error).  As in the
+    reference, `weight_decay` only enters the experiment name (train_dae.py:15,55,91)."""
+    import os
+    import time
+    import numpy as np
+    from .data_loader import load_data
+    from .helpers import build_experiment_name
+    from .iterative_inference import DAE_DICT_DEFAULTS
+    from .models.fcn8 import buildFCN8
+    from ._packing import load_npz_params
+    dae_dict = dict(DAE_DICT_DEFAULTS)
+    dae_dict['path_weights'] = ''
+    dae_dict.update(dae_dict_updates)
+    if optimizer != 'rmsprop':
+        raise NotImplementedError('B200 train step implements lasagne.updates.rmsprop (the benchmark optimiser)')
+    if dae_dict['kind'] != 'standard' or dae_dict['unpool_type'] != 'trackind' or segm_net != 'fcn8':
+        raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net=fcn8')
+    if sorted(training_loss) != ['crossentropy', 'squared_error']:
+        raise NotImplementedError('B200 train step: training_loss = [crossentropy, squared_error]')
+    exp_name = build_experiment_name(segm_net, training_loss=training_loss, data_aug=bool(data_augmentation),
+                                     learning_rate=learning_rate, lr_anneal=lr_anneal, weight_decay=weight_decay,
+                                     optimizer=optimizer, ae_h=ae_h, **dae_dict)
+    if savepath is None:
+        raise ValueError('A saving directory must be specified')
+    exp_name += '_ft' if full_im_ft else ''
+    savepath = os.path.join(savepath, dataset, exp_name)
+    os.makedirs(savepath, exist_ok=True)
+    if train_iter is None or val_iter is None:
+        train_iter = load_data(dataset, data_augmentation, one_hot=True, batch_size=batch_size, which_set='train')
+        val_iter = load_data(dataset, {}, one_hot=True, batch_size=batch_size, which_set='val')
+    n_classes = train_iter.non_void_nclasses
+    fcn = buildFCN8(train_iter.data_shape[0], None, n_classes=n_classes, layer=dae_dict['concat_h'] + [dae_dict['layer']],
+                    path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'), params=fcn_params)
+    fnet = fcn[0].net
+    if dae_params is None:
+        if resume:
+            dae_params = load_npz_params(os.path.join(loadpath or savepath, 'dae_model_best.npz'))
+        else:
+            from . import synthetic
+            dae_params = synthetic.synthetic_dae_params(n_classes, fcn[0].output_shape[1], seed=seed, n_filters=dae_dict['n_filters'],
+                                                        concat_h=tuple(dae_dict['concat_h']), additional_pool=dae_dict['additional_pool'])
+    tr = DAETrainer(n_classes, fcn[0].output_shape[1], 100, dae_params, concat_h=tuple(dae_dict['concat_h']),
+                    n_filters=dae_dict['n_filters'], additional_pool=dae_dict['additional_pool'],
+                    learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb)
+    gen = torch.Generator(device=tr.dev).manual_seed(seed)
+    say = print if verbose else (lambda *a, **k: None)
+
+    def batch(it):
+        X, L = it.next()
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(tr.dev)
+        Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).to(tr.dev)
+        out = fnet.forward(Xd, want=('pool4', 'probs_dimshuffle'))
+        y = Ld[:, :n_classes].contiguous() if dae_dict['from_gt'] else out['probs_dimshuffle']
+        return out['pool4'], y, Ld
+
+    err_train, err_valid, jacc_val_arr, mse_val_arr = [], [], [], []
+    patience, best_err_val = 0, None
+    for epoch in range(num_epochs):
+        t0 = time.time()
+        cost = 0.0
+        for _ in range(train_iter.nbatches):
+            h, y, Ld = batch(train_iter)
+            nm = nk = None
+            if tr.sigma > 0:
+                nm = torch.randn(y.shape, device=tr.dev, generator=gen)
+                nk = torch.randn(y.shape, device=tr.dev, generator=gen)
+            tr.step_graphed(h, y, Ld, nm, nk)
+            cost += tr.loss_value()
+        err_train.append(cost / train_iter.nbatches)
+        cv, jv, mv = 0.0, 0, 0.0
+        for _ in range(val_iter.nbatches):
+            h, y, Ld = batch(val_iter)
+            c, j, m = validate(tr, h, y, Ld)
+            cv += c; jv = jv + j; mv += m
+        err_valid.append(cv / val_iter.nbatches)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            jacc_val_arr.append(float(np.mean(jv[0, :] / jv[1, :])))
+        mse_val_arr.append(mv / val_iter.nbatches)
+        out_str = 'EPOCH %i: Avg epoch training cost train %f, cost val %f, jacc val %f, mse val % f took %f s' % (
+            epoch, err_train[epoch], err_valid[epoch], jacc_val_arr[epoch], mse_val_arr[epoch], time.time() - t0)
+        say(out_str)
+        with open(os.path.join(savepath, 'output.log'), 'a') as f:
+            f.write(out_str + '\n')
+        tr.lr = float(tr.lr * lr_anneal)                 # lr.set_value(lr * lr_anneal), train_dae.py:424
+        arrays = [np.asarray(a.cpu()) for a in tr.params()]
+        if epoch == 0:
+            best_err_val = err_valid[epoch]
+        elif err_valid[epoch] < best_err_val:
+            best_err_val = err_valid[epoch]
+            patience = 0
+            np.savez(os.path.join(savepath, 'dae_model_best.npz'), *arrays)
+            np.savez(os.path.join(savepath, 'dae_errors_best.npz'), err_train, err_valid, jacc_val_arr, mse_val_arr)
+        else:
+            patience += 1
+            np.savez(os.path.join(savepath, 'dae_model_last.npz'), *arrays)
+            np.savez(os.path.join(savepath, 'dae_errors_last.npz'), err_train, err_valid, jacc_val_arr, mse_val_arr)
+        if patience == max_patience or epoch == num_epochs - 1:
+            if loadpath is not None:
+                import shutil
+                dst = os.path.join(loadpath, dataset, exp_name)
+                if os.path.abspath(dst) != os.path.abspath(savepath):
+                    shutil.copytree(savepath, dst, dirs_exist_ok=True)
+            say(' Training Done !')
+            break
+    return {'err_train': err_train, 'err_valid': err_valid, 'jacc_val': jacc_val_arr, 'mse_val': mse_val_arr,
+            'savepath': savepath, 'trainer': tr}
+
+
+def main():
+    """The reference's CLI (train_dae.py:460-505); `-train_dict` / `-dae_dict` / `-data_augmentation` take dict literals."""
+    import argparse
+    from .iterative_inference import _flag, _literal_dict
+    parser = argparse.ArgumentParser(description='DAE training')
+    parser.add_argument('-dataset', type=str, default='camvid', help='Dataset.')
+    parser.add_argument('-segmentation_net', type=str, default='fcn8', help='Segmentation network.')
+    parser.add_argument('-train_dict', type=_literal_dict,
+                        default={'learning_rate': 0.001, 'lr_anneal': 0.99, 'weight_decay': 0.0001, 'num_epochs': 500,
+                                 'max_patience': 100, 'optimizer': 'rmsprop', 'batch_size': [10, 10, 10],
+                                 'training_loss': ['crossentropy', 'squared_error'], 'lmb': 1, 'full_im_ft': False},
+                        help='Training configuration')
+    parser.add_argument('-dae_dict', type=_literal_dict,
+                        default={'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0.5,
+                                 'concat_h': ['pool4'], 'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1,
+                                 'additional_pool': 2, 'temperature': 1.0, 'path_weights': '', 'layer': 'probs_dimshuffle',
+                                 'exp_name': 'flip_final_', 'bn': 0}, help='DAE kind and parameters')
+    parser.add_argument('-data_augmentation', type=_literal_dict,
+                        default={'crop_size': (224, 224), 'horizontal_flip': 0.5, 'fill_mode': 'constant'},
+                        help='Dictionary of data augmentation to be used')
+    parser.add_argument('-train_from_0_255', type=_flag, default=False)
+    parser.add_argument('-savepath', type=str, default='./iiseg_out/')
+    parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
+    parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
+    args = parser.parse_args()
+    train(dataset=args.dataset, segm_net=args.segmentation_net, dae_dict_updates=args.dae_dict,
+          data_augmentation=args.data_augmentation, train_from_0_255=args.train_from_0_255, resume=False,
+          savepath=args.savepath, loadpath=args.loadpath, weights_path=args.weights_path, **args.train_dict)
+
+
+if __name__ == '__main__':
+    main()

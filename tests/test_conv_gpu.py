@@ -18,7 +18,9 @@ CASES = [
     (2, 17, 21, 256, 0, 512, 3, 1, 1, 0, None, 0),
     (2, 17, 21, 128, 64, 256, 3, 1, 1, 0, None, 0),
     (2, 33, 29, 128, 0, 64, 3, 1, 0, 1, None, 0),
-    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),
+    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),            # halo-tile kernel, split precision, 64-channel K blocks
+    (2, 30, 40, 16, 0, 64, 3, 100, 1, 0, None, 0),            # ... 16-channel K blocks (y / RGB inputs)
+    (2, 41, 37, 16, 0, 64, 3, 1, 0, 0, (3, 5, 30, 28), 0),    # ... linear, windowed
     (1, 40, 56, 64, 0, 16, 3, 1, 0, 0, (5, 7, 24, 32), 1),
     (1, 17, 21, 128, 0, 256, 7, 0, 1, 0, None, 0),
     (1, 11, 15, 256, 0, 16, 1, 0, 1, 0, None, 1),
@@ -161,7 +163,9 @@ SPLIT_CASES = [
     (2, 37, 45, 64, 0, 128, 3, 1, 1, 0, None, 0),
     (2, 17, 21, 128, 64, 256, 3, 1, 1, 0, None, 0),
     (2, 33, 29, 128, 0, 64, 3, 1, 0, 1, None, 0),
-    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),
+    (1, 24, 32, 64, 0, 64, 3, 100, 1, 0, None, 0),            # halo-tile kernel, split precision, 64-channel K blocks
+    (2, 30, 40, 16, 0, 64, 3, 100, 1, 0, None, 0),            # ... 16-channel K blocks (y / RGB inputs)
+    (2, 41, 37, 16, 0, 64, 3, 1, 0, 0, (3, 5, 30, 28), 0),    # ... linear, windowed
     (1, 40, 56, 64, 0, 16, 3, 1, 0, 0, (5, 7, 24, 32), 1),
     (1, 17, 21, 128, 0, 256, 7, 0, 1, 0, None, 0),
     (1, 11, 15, 256, 0, 16, 1, 0, 1, 0, None, 1),
@@ -198,7 +202,8 @@ def test_conv_split_matches_fp64_reference(cuda, case):
     assert float(err) < 1.5e-4, float(err)
 
 
-@pytest.mark.parametrize('N,H,W,C,Cout,pad', [(2, 37, 45, 64, 128, 1), (1, 20, 24, 64, 64, 100), (3, 8, 10, 64, 512, 1)])
+@pytest.mark.parametrize('N,H,W,C,Cout,pad', [(2, 37, 45, 64, 128, 1), (1, 20, 24, 64, 64, 100), (3, 8, 10, 64, 512, 1),
+                                              (2, 30, 40, 16, 64, 100), (3, 33, 47, 16, 64, 1)])
 def test_conv_split_fused_pool_mask_is_exact(cuda, N, H, W, C, Cout, pad):
     """fp32x3 fused pool: pooled pair and tie mask are exactly the 2x2 max / tie-inclusive mask of the
     reconstructed fp32 (hi+lo) conv output, and the windowed unpool gates both halves with it."""
@@ -327,3 +332,42 @@ def test_conv_with_depool_epilogue_equals_conv_then_unpool(cuda, case):
                    depool_out=(v, mask, (vh0, vw0), (oh0, ow0)))
     torch.cuda.synchronize()
     assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
+
+
+def test_split_halo_kernel_is_selected(cuda):
+    """The split-precision 3x3 convs with Cout <= 128 run on the halo-tile kernel (kernel id 2): DAE conv1_1 / FCN8 conv1_1
+    (16-channel K blocks) and FCN8 conv1_2 (64 -> 64)."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_conv
+    for C in (16, 64):
+        x = K.pack_nchw(torch.randn(1, C, 40, 48, device=cuda), C, split=True)
+        Wk, bk = pack_conv(torch.randn(64, C, 3, 3, device=cuda), torch.zeros(64, device=cuda), [(C, C)], 64, cuda, split=True)
+        pooled = torch.empty((1, 20, 24, 128), dtype=torch.bfloat16, device=cuda)
+        K.conv2d(x, Wk, bk, 3, 3, 1, relu=True, pooled=pooled, split=True)
+        assert K.last_conv_plan() == (2, 64, C), K.last_conv_plan()
+
+
+def test_mixed_precision_plumbing(cuda):
+    """The three kernel-level pieces of precision='mixed': (1) unpool split=2 reads the hi halves of a pair tensor,
+    (2) addend_pair_hi adds the hi halves of a pair tensor in a bf16 conv, (3) nothing else changes -- each equals
+    the plain-bf16 call on the extracted hi tensor bit for bit."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(3)
+    N, H, W, C = 2, 20, 26, 64
+    x = torch.randn(N, H, W, C, device=cuda).to(torch.bfloat16)
+    _, mask = K.maxpool2(x, True)
+    u_pair = K.pack_nchw(torch.randn(N, C, H // 2, W // 2, device=cuda), C, split=True)      # [N,h,w,2C]
+    u_hi = u_pair[..., :C].contiguous()
+    win = (3, 2, 14, 21)
+    assert torch.equal(K.unpool2(u_pair, mask, H, W, window=win, split=2), K.unpool2(u_hi, mask, H, W, window=win))
+    Wt = (torch.randn(128, 9 * C, device=cuda) / (9 * C) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(128, device=cuda)
+    add_pair = K.pack_nchw(torch.randn(N, 128, H + 4, W + 4, device=cuda), 128, split=True)
+    add_hi = add_pair[..., :128].contiguous()
+    for cout in (128, 64):                                   # CTA-pair kernel and halo-tile kernel epilogues
+        got = K.conv2d(x, Wt[:cout].contiguous(), b[:cout].contiguous(), 3, 3, 1, relu=False,
+                       addend=add_pair[..., :2 * cout].contiguous() if cout == 128 else torch.cat([add_pair[..., :64], add_pair[..., 128:192]], 3).contiguous(),
+                       addend_off=(2, 1), addend_pair_hi=True)
+        ref = K.conv2d(x, Wt[:cout].contiguous(), b[:cout].contiguous(), 3, 3, 1, relu=False,
+                       addend=add_hi[..., :cout].contiguous(), addend_off=(2, 1))
+        assert torch.equal(got, ref)

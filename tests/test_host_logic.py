@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -219,3 +220,58 @@ def test_bench_clock_sampler_summary():
     assert out['sm_mhz'] == 1965 and out['reasons'] == [] and 'power_w' not in out
     cs.samples = []
     assert cs.summary()['reasons'] == ['unsampled']
+
+
+def test_camvid_directory_reader(tmp_path):
+    """The on-disk CamVid reader (layout of dataset_loaders' CamvidDataset: <set>/NAME.png + <set>annot/NAME.png) keeps the
+    iterator contract the scripts rely on (iterative_inference.py:117-125, 233-234) and shards whole batches."""
+    from PIL import Image
+    from iterative_inference_segm_b200.data_loader import load_data, CamvidDirectoryIterator
+    rng = np.random.RandomState(0)
+    root = tmp_path / 'camvid'
+    imgs, labs = [], []
+    for s, n in (('test', 5), ('train', 3)):
+        os.makedirs(root / s); os.makedirs(root / (s + 'annot'))
+        for i in range(n):
+            img = rng.randint(0, 256, size=(12, 16, 3)).astype(np.uint8)
+            lab = rng.randint(0, 12, size=(12, 16)).astype(np.uint8)
+            Image.fromarray(img).save(str(root / s / ('f%02d.png' % i)))
+            Image.fromarray(lab).save(str(root / (s + 'annot') / ('f%02d.png' % i)))
+            if s == 'test':
+                imgs.append(img); labs.append(lab)
+    it = load_data('camvid', {}, one_hot=True, batch_size=[10, 5, 2], which_set='test', path=str(root))
+    assert it.nbatches == 3 and it.non_void_nclasses == 11 and it.void_labels == [11] and it.data_shape == (3, 12, 16)
+    assert len(it.cmap) == 12 and len(it.mask_labels) == 12
+    X, L = it.next()
+    assert X.shape == (2, 3, 12, 16) and X.dtype == np.float32 and L.shape == (2, 12, 12, 16) and L.dtype == np.float32
+    assert np.array_equal(X[0], imgs[0].transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))
+    assert np.array_equal(L[1].argmax(0), labs[1]) and np.all(L.sum(1) == 1)
+    it.next()
+    X3, _ = it.next()
+    assert X3.shape[0] == 1                                  # the last, short batch
+    X4, _ = it.next()
+    assert np.array_equal(X4, X)                             # next epoch starts over in the same order
+    it255 = load_data('camvid', {}, one_hot=True, batch_size=[10, 5, 2], which_set='test', path=str(root), return_0_255=True)
+    assert float(it255.next()[0].max()) > 1.0
+    # training-time augmentation: random crop + flip, labels stay aligned with the pixels
+    tr = load_data('camvid', {'crop_size': (8, 10), 'horizontal_flip': 0.5}, one_hot=True, batch_size=[3, 1, 1], which_set='train',
+                   path=str(root), seed=3)
+    Xc, Lc = tr.next()
+    assert Xc.shape == (3, 3, 8, 10) and Lc.shape == (3, 12, 8, 10) and tr.data_shape == (3, 8, 10)
+    # shards: two ranks see disjoint batches that together are the whole set, in order
+    a = CamvidDirectoryIterator(str(root), 'test', 2, shard=(0, 2), use_threads=False)
+    b = CamvidDirectoryIterator(str(root), 'test', 2, shard=(1, 2), use_threads=False)
+    assert a.nbatches + b.nbatches == 3
+    got = [a.next()[0] for _ in range(a.nbatches)] + [b.next()[0] for _ in range(b.nbatches)]
+    assert np.array_equal(np.concatenate(got), np.stack([im.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0) for im in imgs]))
+    with pytest.raises(IOError):
+        load_data('camvid', {}, one_hot=True, which_set='val', path=str(root))
+
+
+def test_trainer_graph_identity_includes_hyperparameters():
+    """lr / sigma / lmb / rho / eps are baked into a captured graph, so they are part of its identity."""
+    import inspect
+    from iterative_inference_segm_b200 import train_dae
+    src = inspect.getsource(train_dae.DAETrainer.step_graphed)
+    assert 'self.lr' in src and 'self.sigma' in src and 'ent[2] != hp' in src
+    assert hasattr(train_dae, 'train') and hasattr(train_dae, 'main') and hasattr(train_dae.DAETrainer, 'step_dp')

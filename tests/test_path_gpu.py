@@ -4,7 +4,7 @@ weights: FCN8 forward, one DAE application (teacher-forced), the N-step loop wit
 Arithmetic: bf16 operands, fp32 accumulation (dtype "bf16").  Tolerances are the bf16 variant's
 own: the pool mask is a discontinuous function of the conv outputs, so bf16
 rounding flips some tie decisions; bounds below are max-abs on probabilities and argmax
-agreement, measured with tools/parity_report.py and given ~2x headroom.  The integer reductions
+agreement, measured with tests/parity_report.py and given ~2x headroom.  The integer reductions
 (confusion matrix, counts) are bit-exact GIVEN the labels, which is asserted separately by
 feeding the oracle the device's own y."""
 import os
@@ -173,7 +173,8 @@ def test_inference_script_dropin(cuda, tmp_path):
 
 
 def test_valid_sweep_per_iteration_matrices(cuda):
-    """iterative_inference_valid: per-iteration Jaccard accumulators equal val_fn on the per-iteration y."""
+    """iterative_inference_valid, internal consistency: the per-iteration Jaccard accumulators of the captured loop equal
+    val_fn on the per-iteration y (the comparison with the ORACLE's valid_mat is test_valid_sweep_matches_oracle_valid_mat)."""
     from iterative_inference_segm_b200.iterative_inference_valid import sweep
     from iterative_inference_segm_b200.functions import IterativeInference, function_pred_fcn, function_val
     from iterative_inference_segm_b200.iterative_inference import build_networks, DAE_DICT_DEFAULTS
@@ -215,9 +216,11 @@ TOL_F32 = 2e-3
 MIN_ARGMAX_F32 = 0.999
 
 
-@pytest.fixture(scope='module')
-def built_f32(cuda):
-    return _nets(cuda, 'fp32x3')
+@pytest.fixture(scope='module', params=['fp32x3', 'mixed'])
+def built_f32(cuda, request):
+    """Both fp32-grade variants are held to the same bar: 'fp32x3' (every conv fp32-accurate) and 'mixed'
+    (fp32-accurate FCN8 + contracting path, bf16 expanding path with the fused softmax/update epilogue)."""
+    return _nets(cuda, request.param)
 
 
 def test_fp32x3_fcn8_forward_vs_golden(cuda, built_f32):
@@ -267,12 +270,14 @@ def test_fp32x3_free_running_loop_vs_oracle_64x80(cuda, built_f32):
         assert float((y.cpu().argmax(1) == y_o.argmax(1)).float().mean()) >= MIN_ARGMAX_F32, it
 
 
-def test_fused_update_epilogue_equals_standalone_kernel(cuda, built):
+@pytest.mark.parametrize('precision', ['bf16', 'mixed'])
+def test_fused_update_epilogue_equals_standalone_kernel(cuda, built, precision):
     """up_conv1 with the softmax tail + y update fused in its epilogue gives bit-identical y (and the same
     executed-iteration counts) as logits -> iiseg_softmax_update; the per-iteration norms agree to
-    fp32 rounding (fixed-point integer sum vs ordered partial sums)."""
+    fp32 rounding (fixed-point integer sum vs ordered partial sums).  'mixed': the epilogue writes the
+    (hi | lo) pair of y that the fp32-accurate first conv reads."""
     from iterative_inference_segm_b200.functions import IterativeInference
-    pf, pd, fcn, dae = built
+    pf, pd, fcn, dae = built if precision == 'bf16' else _nets(cuda, precision)
     gd = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
     h = torch.from_numpy(gd['h']).to(cuda)
     y0 = torch.from_numpy(np.concatenate([gd['y'], gd['y'][:, ::-1].copy()])).to(cuda)     # 2 images
@@ -358,3 +363,116 @@ def test_batch_composition_does_not_change_results(cuda, built):
     y_b, cm_b = run(slice(2, 3))
     assert torch.equal(y_all[:2], y_a) and torch.equal(y_all[2:], y_b)
     assert torch.equal(cm_all.sum(0), cm_a.sum(0) + cm_b.sum(0))
+
+
+# ---------------------------------------------------------------------------
+# Full BASELINE size, end to end, against the live oracle
+# ---------------------------------------------------------------------------
+# bf16 variant's own tolerance at 360x480 x 50 iterations, true pipeline (device FCN8 -> device loop): measured with
+# tests/parity_report.py on a B200 (profiles/r02_parity_360x480_50it_bf16.txt) and asserted with ~25 % headroom.
+BF16_FULL = {'fcn_y0': 3.2e-2, 'true_y': 3.2e-2, 'true_argmax': 0.990, 'tf_p': 8e-3, 'loop_y': 4e-3, 'loop_argmax': 0.9915}
+
+
+@pytest.mark.parametrize('precision', ['mixed', 'bf16'])
+def test_full_size_end_to_end_vs_oracle(cuda, precision):
+    """BASELINE.json configs[1] size: one 360x480 image, 50 iterations, step 0.05.  The TRUE pipeline -- device FCN8 ->
+    device loop as one CUDA-graph replay, y recorded after every iteration -- against oracle FCN8 -> oracle loop run
+    live on the host (~15 s), every iteration compared; plus the teacher-forced application (oracle y_k in) and the
+    loop alone from the oracle's h / y0.  'mixed' is held to north_star's fp32 bar on every iteration; 'bf16' to its
+    own measured tolerance."""
+    from tests.parity_report import measure
+    r = measure(360, 480, 50, 0.05, precision, n_images=1, verbose=False)
+    if precision == 'mixed':
+        assert r['fcn_y0_maxabs'] < TOL_F32 and r['fcn_argmax'] >= MIN_ARGMAX_F32, r
+        assert r['true_y'] < TOL_F32 and r['true_argmax'] >= MIN_ARGMAX_F32, r       # every iteration, end to end
+        assert r['tf_p'] < TOL_F32, r                                                 # every teacher-forced application
+        assert r['loop_y'] < TOL_F32 and r['loop_argmax'] >= MIN_ARGMAX_F32, r
+    else:
+        assert r['fcn_y0_maxabs'] < BF16_FULL['fcn_y0'], r
+        assert r['true_y'] < BF16_FULL['true_y'] and r['true_argmax'] >= BF16_FULL['true_argmax'], r
+        assert r['tf_p'] < BF16_FULL['tf_p'], r
+        assert r['loop_y'] < BF16_FULL['loop_y'] and r['loop_argmax'] >= BF16_FULL['loop_argmax'], r
+
+
+def test_valid_sweep_matches_oracle_valid_mat(cuda):
+    """iterative_inference_valid.py's accumulator against the ORACLE's (oracle.loop.inference_batch, restating
+    iterative_inference_valid.py:231,286-297): same data, same weights, two step values, three iterations, an eps
+    chosen so that some images leave the loop early.  Executed-iteration pattern identical; per-iteration [TP; union]
+    counts equal up to the few pixels whose argmax differs (fp32-grade arithmetic: <= 0.1 % of the pixels)."""
+    from iterative_inference_segm_b200.iterative_inference_valid import sweep
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    steps, n_it = [0.05, 0.5], 3
+    it = _tiny_iter(3, 2)
+    batches = [it.next() for _ in range(it.nbatches)]
+    # first-iteration norms of every image in the oracle -> an eps that freezes about half of them after iteration 1
+    norms = []
+    for X, L in batches:
+        h, y0 = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+        for im in range(X.shape[0]):
+            g = y0[im:im + 1] - nets.dae_forward(pd, y0[im:im + 1], h[im:im + 1], 100)
+            norms.append(float(torch.linalg.vector_norm(g, dim=1).mean()))
+    ns = sorted(norms)
+    eps = 0.5 * (ns[0] + ns[1])               # between two images' norms: no decision sits on the threshold
+    assert ns[0] < eps < ns[1]
+    want = np.zeros((len(steps), 2, NCLS, n_it))
+    n_exec_o = []
+    for X, L in batches:
+        h, y0 = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+        for si, s in enumerate(steps):
+            _, n_exec, _, vm = loop.inference_batch(pd, h, y0, s, n_it, 100, L=L, n_classes=NCLS, void_labels=[NCLS], eps=eps)
+            want[si] += vm
+            n_exec_o.append(n_exec)
+    res, mats = sweep('camvid', 'fcn8', steps=steps, num_iter=n_it, dae_dict_updates=DAE_DICT, data_iter=_tiny_iter(3, 2),
+                      fcn_params=pf, dae_params=pd, verbose=False, precision='mixed', eps=eps)
+    assert sweep.last_graph_captures <= 2            # one graph per batch shape (2 and 1 images), NOT one per step value
+    assert any(n < n_it for ne in n_exec_o for n in ne), 'eps did not trigger an early exit: the test would not cover it'
+    # an image that left the loop contributes nothing afterwards: the zero pattern of the denominators is the oracle's
+    assert np.array_equal(mats[:, 1].sum(1) == 0, want[:, 1].sum(1) == 0)
+    npix = 32 * 40
+    assert float(np.abs(mats - want).max()) <= max(2.0, 1e-3 * npix * 3), float(np.abs(mats - want).max())
+    assert np.array_equal(mats[:, 1].sum(1) > 0, want[:, 1].sum(1) > 0)
+
+
+def test_temperature_divides_the_upsample_layer(cuda):
+    """models/fcn8.py:193-198: temperature T divides upsample.W and .b, i.e. y0 = softmax(logits / T).  T = 2.5 against
+    the oracle's fcn8_forward(temperature=2.5), fp32-grade arithmetic; T is only applied with load_weights (as in the
+    reference)."""
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.functions import function_pred_fcn
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    X, _, _ = weights.synthetic_batch(2, 32, 40, NCLS, seed=7)
+    _, y_T = nets.fcn8_forward(pf, X, NCLS, temperature=2.5)
+    _, y_1 = nets.fcn8_forward(pf, X, NCLS)
+    assert float((y_T - y_1).abs().max()) > 0.05                       # the temperature matters on this input
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf, load_weights=True,
+                    temperature=2.5, precision='mixed')
+    _, y_d = function_pred_fcn(fcn)(X.to(cuda))
+    assert float((y_d.cpu() - y_T).abs().max()) < TOL_F32
+    fcn1 = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'], params=pf, load_weights=False,
+                     temperature=2.5, precision='mixed')                # reference: T ignored without load_weights
+    _, y_d1 = function_pred_fcn(fcn1)(X.to(cuda))
+    assert float((y_d1.cpu() - y_1).abs().max()) < TOL_F32
+
+
+def test_checkpoints_load_from_disk_in_the_reference_layout(cuda, tmp_path):
+    """Positional .npz checkpoints (np.savez(path, *get_all_param_values(net)): arr_0..arr_k; models/fcn8.py:177-180,
+    models/DAE_h.py:52-57) written where the reference's scripts look for them -- <weights_path>/<dataset>/fcn8_model.npz and
+    <loadpath>/<dataset>/<experiment name>/dae_model_best.npz (iterative_inference.py:136,157) -- give bit-identical results
+    to passing the same arrays in memory."""
+    from iterative_inference_segm_b200.iterative_inference import inference
+    from iterative_inference_segm_b200.helpers import build_experiment_name
+    from iterative_inference_segm_b200.iterative_inference import DAE_DICT_DEFAULTS
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    dd = dict(DAE_DICT_DEFAULTS); dd.update(DAE_DICT)
+    exp = build_experiment_name('fcn8', data_aug=False, ae_h=False, **dd)
+    wdir, ldir = tmp_path / 'w', tmp_path / 'l'
+    os.makedirs(wdir / 'camvid'); os.makedirs(ldir / 'camvid' / exp)
+    weights.save_npz(str(wdir / 'camvid' / 'fcn8_model.npz'), pf)
+    weights.save_npz(str(ldir / 'camvid' / exp / 'dae_model_best.npz'), pd)
+    kw = dict(dae_dict_updates=DAE_DICT, savepath=str(tmp_path / 'out'), verbose=False)
+    a = inference('camvid', 'fcn8', 0.05, 2, data_iter=_tiny_iter(2, 2), weights_path=str(wdir), loadpath=str(ldir), **kw)
+    b = inference('camvid', 'fcn8', 0.05, 2, data_iter=_tiny_iter(2, 2), fcn_params=pf, dae_params=pd, loadpath=str(ldir), **kw)
+    assert np.array_equal(a['cm'], b['cm']) and np.array_equal(a['jacc_tot'], b['jacc_tot']) and a['iterative'] == b['iterative']
+    assert a['n_exec'] == b['n_exec'] == [2, 2]

@@ -21,7 +21,7 @@ def main(B=10, H=360, W=480, precision='bf16'):
     h = K.pack_nchw(torch.relu(torch.randn(B, 512, hs[0], hs[1], device='cuda')), net.h_pad, split=net.split)
     y = K.pack_nchw(torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1), net.y_cpad, split=net.split)
     yf = torch.softmax(torch.randn(B, 11, H, W, device='cuda'), 1)
-    upd = None if (net.split or os.environ.get('UNFUSED')) else dict(y=yf, active=torch.ones(B, dtype=torch.int32, device='cuda'),
+    upd = None if (net.split_up or os.environ.get('UNFUSED')) else dict(y=yf, active=torch.ones(B, dtype=torch.int32, device='cuda'),
                                      norm_acc=torch.zeros(B, dtype=torch.int64, device='cuda'), step=0.05)
     net.logits(h, y, full_down=True)
     timer = KernelTimer()
