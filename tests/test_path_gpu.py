@@ -370,7 +370,10 @@ def test_batch_composition_does_not_change_results(cuda, built):
 # ---------------------------------------------------------------------------
 # bf16 variant's own tolerance at 360x480 x 50 iterations, true pipeline (device FCN8 -> device loop): measured with
 # tests/parity_report.py on a B200 (profiles/r02_parity_360x480_50it_bf16.txt) and asserted with ~25 % headroom.
-BF16_FULL = {'fcn_y0': 3.2e-2, 'true_y': 3.2e-2, 'true_argmax': 0.990, 'tf_p': 8e-3, 'loop_y': 4e-3, 'loop_argmax': 0.9915}
+# Measured (1 image, seed 0): FCN8 y0 max-abs 2.40e-2 / argmax 99.43 %; true pipeline worst y 2.28e-2 (iteration 1: FCN8's y0
+# error, decaying under the iteration) / worst argmax 98.93 % (iteration 50); teacher-forced p worst 6.2e-3; loop alone
+# (oracle h, y0 in) worst y 2.4e-3 / argmax 99.33 %.
+BF16_FULL = {'fcn_y0': 3.0e-2, 'true_y': 2.9e-2, 'true_argmax': 0.986, 'tf_p': 7.8e-3, 'loop_y': 3.0e-3, 'loop_argmax': 0.9915}
 
 
 @pytest.mark.parametrize('precision', ['mixed', 'bf16'])
