@@ -1957,7 +1957,11 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
       const int pairs = num_sms() / 2;
       const long units = (long)(d->Cout / 256) * ((d->N * ceil_div(covH, p.TH) * ceil_div(covW, p.TW) + 1) / 2);
       const long r256 = (units + pairs - 1) / pairs, r128 = (2 * units + pairs - 1) / pairs;
-      if (0.5 * 1.15 * (double)r128 < (double)r256) BN = 128;
+      // a long K loop (the split-precision layers walk three times the blocks) amortises the per-unit overheads and
+      // leaves the 128-wide unit bound by what an SM can ingest: measured on conv5_1, 254 us (128) vs 231 us (256) with
+      // 216 k-blocks per unit, against 92 vs 105 us with 72
+      const double penalty = d->R * d->S * n_cblk_all >= 150 ? 1.35 : 1.15;
+      if (0.5 * penalty * (double)r128 < (double)r256) BN = 128;
     }
   }
   const bool hs = halo && hsplit;

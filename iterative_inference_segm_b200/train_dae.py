@@ -168,8 +168,11 @@ class DAETrainer(object):
             x = pooled
         return pools, masks, zmasks
 
-    def forward(self, h_bf16, y, noise_main=None, noise_mask=None):
-        """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits."""
+    def forward(self, h_bf16, y, noise_main=None, noise_mask=None, forced=None):
+        """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits.
+        `forced` (parity tooling): dict(masksA, zmasks, masksB) of per-level mask tensors in the kernels' nibble layout
+        that REPLACE the ones this pass computes -- the discrete decisions (which window elements are maxima, which
+        pre-rectifier values are exactly zero) are then someone else's, and only the arithmetic is this path's."""
         geo = self.geo
         B, _, H, W = y.shape
         self._sizes = sizes = geo.level_sizes(H, W)
@@ -181,6 +184,12 @@ class DAETrainer(object):
             _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
         else:
             st['masksB'] = st['masksA']
+        if forced is not None:
+            if st['masksB'] is st['masksA']:
+                st['masksB'] = [m.clone() for m in st['masksA']]
+            for key, mine in (('masksA', st['masksA']), ('zmasks', st['zmasks']), ('masksB', st['masksB'])):
+                for m, f in zip(mine, forced[key]):
+                    m.copy_(f)
         P = geo.total
         st['v'] = {}
         u, u_origin = st['pools'][-1], (0, 0)

@@ -62,11 +62,14 @@ def _q_bf16(x):
 
 
 def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=('pool4',), additional_pool=2,
-                      emulate_bf16=False):
+                      emulate_bf16=False, tap=None):
     """Differentiable DAE forward -> logits (before the softmax), cropped to the input size.
     `mask_source_y`: input of the separate contracting-path forward the DePool2D masks are taken from
     (None: the same forward).  Masks are constants (detached).  `emulate_bf16`: weights, inputs and every
-    stored activation are rounded to bf16 (straight-through), as on the B200 path; the arithmetic stays fp32."""
+    stored activation are rounded to bf16 (straight-through), as on the B200 path; the arithmetic stays fp32.
+    `tap` (dict): receives the discrete decisions of this pass -- 'masksA' (tie masks of the main pass: the pool
+    backward routing), 'zero' (pre-rectifier value exactly 0: rectify'(0) = 0.5) and 'masksB' (the DePool2D masks) --
+    so that a test can teacher-force them into the CUDA path and compare the arithmetic alone."""
     n_pool, total = dae_levels(concat_h, additional_pool)
     q = _q_bf16 if emulate_bf16 else (lambda t: t)
     Wd = [(q(params[2 * i]), params[2 * i + 1]) for i in range(total)]
@@ -75,11 +78,15 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
     if mask_source_y is not None:
         mask_source_y = q(mask_source_y)
 
+    zero = []
+
     def down(x, differentiable):
         pre, pools = [], []
         for p in range(total):
             pad = padding if (p == 0 and padding > 0) else 1
             a = q(F.conv2d(x, Wd[p][0], Wd[p][1], padding=pad))
+            if differentiable:
+                zero.append((a.detach() == 0).to(a.dtype))
             r = _Relu.apply(a) if differentiable else torch.relu(a)
             pre.append(r)
             x = _MaxPool2TieAll.apply(r) if differentiable else F.max_pool2d(r, 2, 2)
@@ -95,6 +102,10 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
         with torch.no_grad():
             pre_m, _ = down(mask_source_y, False)
         masks = [L.tie_mask(r) for r in pre_m]
+    if tap is not None:
+        tap['masksA'] = [L.tie_mask(r.detach()) for r in pre]
+        tap['zero'] = zero
+        tap['masksB'] = masks
     u = pools[-1]
     for i, p in enumerate(range(total, 0, -1)):
         m = masks[p - 1]
@@ -132,13 +143,13 @@ def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True):
 
 
 def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=None, noise_mask=None, lmb=1.0,
-               rho=0.9, eps=1e-6, emulate_bf16=False, **dae_kw):
+               rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, **dae_kw):
     """One train_fn call (train_dae.py:334-335): returns (loss, grads, new_params, new_accus).
     lasagne.updates.rmsprop: a <- rho*a + (1-rho)*g^2 ; p <- p - lr * g / sqrt(a + eps)."""
     ps = [p.clone().requires_grad_(True) for p in params]
     y_main = y if noise_main is None else y + noise_main
     y_mask = None if noise_mask is None else y + noise_mask
-    logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, **dae_kw)
+    logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, tap=tap, **dae_kw)
     loss = loss_fn(logits, target, n_classes, lmb=lmb)
     grads = torch.autograd.grad(loss, ps)
     new_p, new_a = [], []

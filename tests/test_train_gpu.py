@@ -147,3 +147,49 @@ def test_graphed_step_equals_eager_step(cuda):
         assert trs[0].loss_value() == trs[1].loss_value(), k
     for a, b in zip(trs[0].params(), trs[1].params()):
         assert torch.equal(a, b)
+
+
+def _dense_to_mask(dense, cuda):
+    """[N,C,H,W] 0/1 (H, W even or odd: the trailing odd row / column has no window) -> the kernels' tie-mask words
+    [N,H/2,W/2,C/8] (int32): channel j of a group of 8, window position pos = 2*dy+dx at bit 16*(j&1) + 4*(j>>1) + pos."""
+    N, C, H, W = dense.shape
+    H2, W2 = H // 2, W // 2
+    d = dense[:, :, :2 * H2, :2 * W2].numpy().astype(np.uint32)
+    words = np.zeros((N, H2, W2, C // 8), np.uint32)
+    for j in range(8):
+        for pos in range(4):
+            bit = d[:, j::8, (pos >> 1)::2, (pos & 1)::2].transpose(0, 2, 3, 1)           # [N,H2,W2,C/8]
+            words |= bit << np.uint32(16 * (j & 1) + 4 * (j >> 1) + pos)
+    return torch.from_numpy(words.view(np.int32)).to(cuda)
+
+
+TOL_GRAD_FORCED = 1.2e-2     # teacher-forced masks: bf16 arithmetic alone (measured <= 9e-3, see the printed errors)
+
+
+@pytest.mark.parametrize('with_mask_noise', [False, True])
+def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
+    """Separates the two sources of gradient error.  The step's only discontinuous decisions are
+    which window elements are maxima (pool backward routing, DePool2D masks) and which pre-rectifier values are exactly
+    zero.  Here the PURE fp32 oracle's decisions are forced into the CUDA path (DAETrainer.forward(forced=...)), so what is
+    left is the arithmetic -- bf16 operands and bf16 gradient tensors with fp32 accumulation -- and every one of the 24
+    gradient arrays must agree with the fp32 autograd oracle to ~1 % relative L2."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    pd, h, y, L, nm, nk = _setup(cuda)
+    sigma, lr = 0.5, 1e-3
+    acc = [torch.zeros_like(p) for p in pd]
+    tap = {}
+    loss_o, grads_o, _, _ = OT.train_step(pd, acc, y, h, L, NCLS, 100, lr, noise_main=sigma * nm,
+                                          noise_mask=sigma * nk if with_mask_noise else None, tap=tap)     # fp32, no emulation
+    forced = {'masksA': [_dense_to_mask(m, cuda) for m in tap['masksA']],
+              'zmasks': [_dense_to_mask(z, cuda) for z in tap['zero']],
+              'masksB': [_dense_to_mask(m, cuda) for m in tap['masksB']]}
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=sigma)
+    h_b = K.pack_nchw(h.to(cuda), 512)
+    tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda) if with_mask_noise else None, forced=forced)
+    tr.backward(L.to(cuda))
+    torch.cuda.synchronize()
+    assert abs(tr.loss_value() - loss_o) < 1e-3 * abs(loss_o) + 1e-4, (tr.loss_value(), loss_o)
+    errs = [_rel(g.cpu(), go) for g, go in zip(tr.grads_lasagne(), grads_o)]
+    print('teacher-forced masks, relative L2 gradient errors vs the fp32 oracle:', ' '.join('%.4f' % e for e in errs))
+    assert max(errs) < TOL_GRAD_FORCED, errs
