@@ -170,9 +170,11 @@ class DAETrainer(object):
 
     def forward(self, h_bf16, y, noise_main=None, noise_mask=None, forced=None):
         """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits.
-        `forced` (parity tooling): dict(masksA, zmasks, masksB) of per-level mask tensors in the kernels' nibble layout
-        that REPLACE the ones this pass computes -- the discrete decisions (which window elements are maxima, which
-        pre-rectifier values are exactly zero) are then someone else's, and only the arithmetic is this path's."""
+        `forced` (parity tooling): dict(masksA, zmasks, masksB[, positive]) of per-level tensors that REPLACE the discrete
+        decisions this pass takes -- which window elements are maxima (tie masks, nibble layout), which pre-rectifier
+        values are exactly zero, and (`positive`: bool [B,h/2,w/2,C] per level) whether a window's maximum is positive, i.e.
+        whether the rectifier passes the gradient -- so that only the arithmetic is this path's.  The pooled values of
+        windows whose forced sign differs (all within rounding of zero) are nudged to the forced side of zero."""
         geo = self.geo
         B, _, H, W = y.shape
         self._sizes = sizes = geo.level_sizes(H, W)
@@ -190,6 +192,9 @@ class DAETrainer(object):
             for key, mine in (('masksA', st['masksA']), ('zmasks', st['zmasks']), ('masksB', st['masksB'])):
                 for m, f in zip(mine, forced[key]):
                     m.copy_(f)
+            for pooled, pos in zip(st['pools'], forced.get('positive', [])):
+                tiny = torch.full_like(pooled, 2.0 ** -100)
+                pooled.copy_(torch.where(pos, torch.maximum(pooled, tiny), torch.zeros_like(pooled)))
         P = geo.total
         st['v'] = {}
         u, u_origin = st['pools'][-1], (0, 0)
@@ -252,6 +257,7 @@ class DAETrainer(object):
         return K.conv2d(g, lay.wt, lay.zero_bias_t[:lay.ci_t].contiguous(), 3, 3, 2, relu=False, window=window, addend=addend)
 
     _dp_world = None
+    keep_grads = None
 
     def backward(self, target, world=None, overlap=False):
         """`overlap` (data parallel): gradient buckets are all-reduced asynchronously as backward completes them; the
@@ -298,6 +304,8 @@ class DAETrainer(object):
             else:
                 g_pool = g_in            # dgrad of conv_{p+1} already carries the skip part (epilogue addend)
             g_a = K.pool2_relu_bwd(g_pool, pooled, st['masksA'][p - 1], hp, wp, zmask=st['zmasks'][p - 1])
+            if self.keep_grads is not None:          # parity tooling: gradient w.r.t. the pre-rectifier output of conv_p
+                self.keep_grads[p] = (g_pool, g_a)
             pad = geo.padding if (p == 1 and geo.padding > 0) else 1
             if p - 1 == geo.n_pool:
                 xs = [(st['h'], geo.h_pad), (st['pools'][p - 2], st['pools'][p - 2].shape[3])]

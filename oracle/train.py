@@ -87,6 +87,9 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
             a = q(F.conv2d(x, Wd[p][0], Wd[p][1], padding=pad))
             if differentiable:
                 zero.append((a.detach() == 0).to(a.dtype))
+                if tap is not None and a.requires_grad:
+                    a.retain_grad()
+                    tap.setdefault('pre_act', []).append(a)
             r = _Relu.apply(a) if differentiable else torch.relu(a)
             pre.append(r)
             x = _MaxPool2TieAll.apply(r) if differentiable else F.max_pool2d(r, 2, 2)

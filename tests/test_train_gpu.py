@@ -14,8 +14,18 @@ NCLS = 11
 TOL_GRAD = 0.15       # bf16 activations / gradients through 12 layers, incl. pool ties that flip under bf16 rounding
 
 
-def _setup(cuda, B=2, H=32, W=40, seed=3):
+def _setup(cuda, B=2, H=32, W=40, seed=3, structured=False):
+    """structured: label maps made of 4x4 blocks with skewed class frequencies instead of per-pixel uniform labels.  With
+    uniform per-pixel labels the true gradients are small differences of large sums (sum_pixels (p_c - t_c) ~ 0 when every
+    class has frequency 1/11 ~ p_c), so a RELATIVE error mostly measures that cancellation; structured labels give
+    gradients of the size a real segmentation batch gives."""
     X, L, lab = weights.synthetic_batch(B, H, W, NCLS, seed=seed)
+    if structured:
+        gen = torch.Generator().manual_seed(seed + 100)
+        probs = torch.tensor([2.0 ** (-0.5 * c) for c in range(NCLS + 1)])
+        blocks = torch.multinomial(probs, B * ((H + 3) // 4) * ((W + 3) // 4), replacement=True, generator=gen)
+        lab = blocks.view(B, (H + 3) // 4, (W + 3) // 4).repeat_interleave(4, 1).repeat_interleave(4, 2)[:, :H, :W]
+        L = torch.nn.functional.one_hot(lab, NCLS + 1).permute(0, 3, 1, 2).float().contiguous()
     pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
     pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
     h, y0 = nets.fcn8_forward(pf, X, NCLS)
@@ -163,19 +173,24 @@ def _dense_to_mask(dense, cuda):
     return torch.from_numpy(words.view(np.int32)).to(cuda)
 
 
-TOL_GRAD_FORCED = 1.2e-2     # teacher-forced masks: bf16 arithmetic alone (measured <= 9e-3, see the printed errors)
+TOL_GRAD_FORCED = 8e-3       # teacher-forced discrete decisions: bf16 arithmetic alone (a CPU emulation of bf16 storage of
+                             # activations and gradients with the same decisions forced gives 2e-3 .. 5e-3 per array; measured on the B200: <= 5.4e-3)
 
 
 @pytest.mark.parametrize('with_mask_noise', [False, True])
 def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
-    """Separates the two sources of gradient error.  The step's only discontinuous decisions are
-    which window elements are maxima (pool backward routing, DePool2D masks) and which pre-rectifier values are exactly
-    zero.  Here the PURE fp32 oracle's decisions are forced into the CUDA path (DAETrainer.forward(forced=...)), so what is
-    left is the arithmetic -- bf16 operands and bf16 gradient tensors with fp32 accumulation -- and every one of the 24
-    gradient arrays must agree with the fp32 autograd oracle to ~1 % relative L2."""
+    """Separates the two sources of gradient error.  The step's discontinuous decisions are: which
+    window elements are maxima (pool backward routing, DePool2D masks), which pre-rectifier values are exactly zero
+    (rectify'(0) = 0.5) and whether a window's maximum is positive (the rectifier gate).  A window that falls on the other
+    side of one of them under bf16 rounding changes its gradient contribution by O(1) -- an all-negative window whose
+    bf16 maximum rounds above zero sends the FULL gradient to all four tied positions where the oracle sends none -- and
+    ~1e-3 of the windows doing so is what the 5-15 % of test_train_step_gradients_loss_and_update consists of.  Here the PURE
+    fp32 oracle's decisions are forced into the CUDA path (DAETrainer.forward(forced=...)), so what is left is the
+    arithmetic -- bf16 operands and bf16 gradient tensors with fp32 accumulation -- and every one of the 24 gradient arrays
+    must agree with the fp32 autograd oracle to 1 % relative L2."""
     from iterative_inference_segm_b200 import _kernels as K
     from iterative_inference_segm_b200.train_dae import DAETrainer
-    pd, h, y, L, nm, nk = _setup(cuda)
+    pd, h, y, L, nm, nk = _setup(cuda, structured=True)
     sigma, lr = 0.5, 1e-3
     acc = [torch.zeros_like(p) for p in pd]
     tap = {}
@@ -183,7 +198,8 @@ def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
                                           noise_mask=sigma * nk if with_mask_noise else None, tap=tap)     # fp32, no emulation
     forced = {'masksA': [_dense_to_mask(m, cuda) for m in tap['masksA']],
               'zmasks': [_dense_to_mask(z, cuda) for z in tap['zero']],
-              'masksB': [_dense_to_mask(m, cuda) for m in tap['masksB']]}
+              'masksB': [_dense_to_mask(m, cuda) for m in tap['masksB']],
+              'positive': [(torch.nn.functional.max_pool2d(a.detach(), 2, 2) > 0).permute(0, 2, 3, 1).contiguous().to(cuda) for a in tap['pre_act']]}
     tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=sigma)
     h_b = K.pack_nchw(h.to(cuda), 512)
     tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda) if with_mask_noise else None, forced=forced)
