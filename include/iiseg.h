@@ -123,6 +123,12 @@ typedef struct iiseg_conv_desc {
    * layers/mylayers.py:36-57).                                             */
   int oh0, ow0, OH, OW;
   void* out;          /* NHWC [N,OH,OW,Cout], bf16 or fp32 per out_f32      */
+  /* out_stride > 1 (the output phases of a transposed convolution, lasagne Deconv2DLayer(4, stride=2) of the DAE's
+   * unpool_type='standard', models/fcn_up.py:37-63, run as four 2x2 convolutions): output pixel (oh, ow) of this launch is
+   * stored at pixel (oh*out_stride + out_h0, ow*out_stride + out_w0) of the tensor `out` [N,out_H,out_W,Cout]; the skip-sum
+   * operand is read with the same stride: addend[oh*out_stride + ah0, ow*out_stride + aw0].  Plain stores only (no
+   * pool / update fusion); per-tap and CTA-pair kernels. */
+  int out_stride, out_H, out_W, out_h0, out_w0;
   const void* addend; /* NHWC bf16 [N,AH,AW,Cout]; addend[oh+ah0, ow+aw0] is added
                        * before the store (skip-sum with a cropped partner), or NULL */
   int AH, AW, ah0, aw0;

@@ -76,7 +76,8 @@ def conv_out_size(H, W, R, S, pad):
 
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
-           out_slice=None, pool_zmask=None, depool=None, depool_out=None, addend_pair_hi=False):
+           out_slice=None, pool_zmask=None, depool=None, depool_out=None, addend_pair_hi=False, out_strided=None,
+           src_pair_hi=False):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -89,6 +90,12 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     update = dict(y, y_bf16, active, norm_acc, step, C[, y_split]): the 16-channel logits conv with the softmax
     tail and the iterative-inference update fused in its epilogue (iiseg_conv_desc.upd_*); nothing is
     returned, y / y_bf16 / norm_acc are updated in place.  y_split: y_bf16 carries the (hi | lo) pair of y.
+
+    out_strided = (dest, stride, (h0, w0)): output pixel (oh, ow) goes to dest[n, oh*stride + h0, ow*stride + w0]
+    (dest: [N,DH,DW,cm*Cout], bf16 or fp32 per out_f32) and the addend, if any, is read at the same stride from
+    `addend_off` -- one output phase of a transposed convolution (iiseg_conv_desc.out_stride).  Returns dest.
+
+    src_pair_hi: src0 is a (hi | lo) pair tensor [N,H,W,2*C0] of which a plain bf16 conv reads the hi halves.
 
     addend_pair_hi: the (bf16, non-split) conv adds the hi halves of a (hi | lo) pair tensor `addend`
     [N,AH,AW,2*Cout] (iiseg_conv_desc.addend_cs): the skip-sum of the mixed-precision expanding path.
@@ -119,6 +126,9 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         C1 = src1.shape[3]
     Cout = weight.shape[0]
     cm = 2 if (split and not out_f32) else 1     # channel multiplier of out / pooled / addend tensors
+    if src_pair_hi:
+        assert not split and src1 is None
+        C0 //= 2
     if split:
         C0 //= 2
         C1 //= 2
@@ -152,6 +162,11 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         assert out is None and not split and not out_f32 and Cout % 64 == 0
         assert dpo_v.shape[0] == N and dpo_v.shape[3] == Cout and dpo_mask.shape[0] == N and dpo_mask.shape[3] == Cout // 8
         assert dpo_porg[0] + OH <= dpo_mask.shape[1] and dpo_porg[1] + OW <= dpo_mask.shape[2]
+    elif out_strided is not None:
+        dest, ostride, (oh_0, ow_0) = out_strided
+        _chk(dest, F32 if out_f32 else BF16, 'out_strided.dest')
+        assert out is None and dest.shape[0] == N and dest.shape[3] == cm * Cout and ostride >= 2
+        assert oh_0 + (OH - 1) * ostride < dest.shape[1] and ow_0 + (OW - 1) * ostride < dest.shape[2]
     elif out_slice is not None:
         stack, c_off = out_slice
         _chk(stack, F32, 'out_slice.stack')
@@ -169,7 +184,8 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
             assert not split and not addend_f32 and addend.shape[3] == 2 * Cout
             addend_cs = 2 * Cout
         assert addend.shape[0] == N and addend.shape[3] == (Cout if addend_f32 else (2 * Cout if addend_pair_hi else cm * Cout))
-        assert addend_off[0] + OH <= addend.shape[1] and addend_off[1] + OW <= addend.shape[2]
+        ast = out_strided[1] if out_strided is not None else 1
+        assert addend_off[0] + (OH - 1) * ast < addend.shape[1] and addend_off[1] + (OW - 1) * ast < addend.shape[2]
     d = _lib.ConvDesc(N=N, H=H, W=W, weight=weight.data_ptr(), bias=bias.data_ptr(),
                       Cout=Cout, R=R, S=S, pad=pad, oh0=oh0, ow0=ow0, OH=OH, OW=OW,
                       out=out.data_ptr() if out is not None else None,
@@ -181,6 +197,8 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32), addend_cs=addend_cs,
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if out_strided is not None:
+        d.out, d.out_stride, d.out_H, d.out_W, d.out_h0, d.out_w0 = dest.data_ptr(), ostride, dest.shape[1], dest.shape[2], oh_0, ow_0
     if depool_out is not None:
         d.depool_out, d.depool_out_mask = dpo_v.data_ptr(), dpo_mask.data_ptr()
         d.depool_out_VH, d.depool_out_VW, d.depool_out_h0, d.depool_out_w0 = dpo_v.shape[1], dpo_v.shape[2], dpo_org[0], dpo_org[1]
@@ -210,13 +228,15 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         for half in (0, 1, 0):        # hi, lo, hi  against  W_hi, W_hi, W_lo
             views += [(t.data_ptr() + 2 * half * c, c, 2 * c) for t, c in srcs]
     else:
-        views = [(t.data_ptr(), c, 0) for t, c in srcs]
+        views = [(t.data_ptr(), c, 2 * c if src_pair_hi else 0) for t, c in srcs]
     assert len(views) <= _lib.MAX_SRC
     for i, (ptr, c, cs) in enumerate(views):
         d.src[i], d.C[i], d.Cs[i] = ptr, c, cs
     _lib.call('iiseg_conv2d_fwd', C.byref(d), _stream())
     if depool_out is not None:
         return dpo_v
+    if out_strided is not None:
+        return dest
     return out if pooled is None else pooled
 
 

@@ -33,7 +33,8 @@ class ConvDesc(C.Structure):
         ('weight', C.c_void_p), ('bias', C.c_void_p),
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
-        ('out', C.c_void_p), ('addend', C.c_void_p),
+        ('out', C.c_void_p), ('out_stride', C.c_int), ('out_H', C.c_int), ('out_W', C.c_int), ('out_h0', C.c_int), ('out_w0', C.c_int),
+        ('addend', C.c_void_p),
         ('AH', C.c_int), ('AW', C.c_int), ('ah0', C.c_int), ('aw0', C.c_int), ('addend_f32', C.c_int), ('addend_cs', C.c_int),
         ('pooled', C.c_void_p), ('pool_mask', C.c_void_p), ('pool_zmask', C.c_void_p), ('pool_H', C.c_int), ('pool_W', C.c_int),
         ('relu', C.c_int), ('split', C.c_int), ('out_f32', C.c_int), ('out_cs', C.c_int),

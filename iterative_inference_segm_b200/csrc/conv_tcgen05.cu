@@ -102,6 +102,7 @@ struct alignas(64) ConvParams {
   int tiles_h, tiles_w, n_ntiles, num_tiles;
   float inv_ntiles, inv_tiles_w, inv_tiles_h, inv_tw2;   // reciprocals for fast_divmod
   int OH, OW, Cout;
+  int OHs, OWs, o_s, o_h0, o_w0;   // destination tensor extent, pixel stride and origin (dense: OH, OW, 1, 0, 0)
   int AH, AW, ah0, aw0;      // addend tensor extent and the offset of out pixel (0,0) inside it
   int addend_cs;             // channels per pixel of the addend tensor in memory
   __nv_bfloat16* pooled;     // fused 2x2 max-pool: pooled output [N,PH,PW,Cout] (NULL = plain conv)
@@ -341,8 +342,10 @@ __device__ __forceinline__ void conv_epilogue16(const ConvParams& p, uint32_t tm
     const uint32_t aphase = static_cast<uint32_t>(iter >> (p.acc_stages >> 1)) & 1u;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
-    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
-    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+    // destination pixel: dense [N,OH,OW,..], or (out_stride > 1: the phase convolutions of a transposed conv) pixel
+    // (oh*s + o_h0, ow*s + o_w0) of a [N,OHs,OWs,..] tensor; the skip-sum operand follows the same stride
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OHs + oh * p.o_s + p.o_h0) * p.OWs + ow * p.o_s + p.o_w0;
+    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh * p.o_s + p.ah0) * p.AW + ow * p.o_s + p.aw0;
     const int cbase = tc.nt * 16 + half * 8;
     uint4 a0 = make_uint4(0, 0, 0, 0);
     const bool has_add = (p.addend != nullptr) && valid;
@@ -552,8 +555,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
     const uint32_t tmem_full_bar = tmem_full_bar0 + 8u * as, tmem_empty_bar = tmem_empty_bar0 + 8u * as;
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW) && !dummy;
-    const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
-    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
+    // destination pixel: dense [N,OH,OW,..], or (out_stride > 1: the phase convolutions of a transposed conv) pixel
+    // (oh*s + o_h0, ow*s + o_w0) of a [N,OHs,OWs,..] tensor; the skip-sum operand follows the same stride
+    const size_t pix = (static_cast<size_t>(tc.n) * p.OHs + oh * p.o_s + p.o_h0) * p.OWs + ow * p.o_s + p.o_w0;
+    const size_t apix = (static_cast<size_t>(tc.n) * p.AH + oh * p.o_s + p.ah0) * p.AW + ow * p.o_s + p.aw0;
     const int n0 = tc.nt * BN;
     const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * BN) + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -662,6 +667,47 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
               stg_v4(o + j * 8, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
               if (kSplit) stg_v4(o + p.Cout + j * 8, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
             }
+          }
+        } else if constexpr (kShflPool && kSplit) {
+          // Fused Pool2DLayer(2) + tie mask on registers, split precision (8 x 16 box, pitch 16: this warp holds box lines
+          // 2q and 2q+1, the window of pooled pixel (q, wl/2) is lanes {l, l^1, l^16, l^17}).  The window maximum and the
+          // tie bits compare the reconstructed values r = hi + lo (as the staged variant below does); no shared-memory
+          // staging, no named barriers.  The lane at window position 0 writes the pair of the maximum and the mask words.
+          const int pos = ((lane >> 4) << 1) | (lane & 1);
+          uint32_t word[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
+            f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float mxv = fmaxf(f[c], __shfl_xor_sync(0xffffffffu, f[c], 1));
+            mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, 16));
+            if (f[c] == mxv) word[c >> 3] |= 1u << (16 * (c & 1) + 4 * ((c >> 1) & 3) + pos);
+            f[c] = mxv;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            word[g] |= __shfl_xor_sync(0xffffffffu, word[g], 1);
+            word[g] |= __shfl_xor_sync(0xffffffffu, word[g], 16);
+          }
+          const int phw = ((tc.th * p.TH) >> 1) + (hl >> 1), pww = ((tc.tw * p.TW) >> 1) + (wl >> 1);   // inside the window
+          if (pos == 0 && wl < p.TW && hl < p.TH && phw < p.pwin_h && pww < p.pwin_w && !dummy) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {      // pair of the window maximum (hi + lo reproduces it exactly)
+              hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              lo[j] = pack_bf16x2(f[2 * j] - bf16_lo(hi[j]), f[2 * j + 1] - bf16_hi(hi[j]));
+            }
+            const size_t ppix = (static_cast<size_t>(tc.n) * p.PH + p.p_h0 + phw) * p.PW + p.p_w0 + pww;
+            __nv_bfloat16* o = p.pooled + ppix * cpp + cbase;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              stg_v4(o + j * 8, make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+              stg_v4(o + p.Cout + j * 8, make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+            }
+            if (p.pool_mask != nullptr)
+              stg_v4(p.pool_mask + ppix * (p.Cout >> 3) + (cbase >> 3), make_uint4(word[0], word[1], word[2], word[3]));
           }
         } else if constexpr (kShflPool) {
           // Fused Pool2DLayer(2) + tie mask on registers (pitch == 16, plain bf16 variant): accumulator row
@@ -923,8 +969,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     if constexpr (BN == 16) {
       if (p.upd_y != nullptr) conv_epilogue16_update<2>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    } else if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else if (p.split) {
+      if (p.pooled != nullptr && p.pitch == 16 && p.TH == 8) conv_epilogue<BN, true, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -1082,8 +1130,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
       }
     }
   } else if (warp >= 4) {
-    if (p.split) conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (p.split) {
+      if (p.pooled != nullptr && p.pitch == 16 && p.TH == 8) conv_epilogue<BN, true, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
 
   tcgen05_fence_before();
@@ -1864,11 +1914,21 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
   IISEG_CHECK(d->N >= 1, "conv: empty batch");
+  if (d->out_stride > 1) {
+    IISEG_CHECK(d->out != nullptr && d->pooled == nullptr && d->upd_y == nullptr && d->depool_out == nullptr && d->out_cs == 0 &&
+                d->out_h0 >= 0 && d->out_w0 >= 0 && d->out_h0 + (d->OH - 1) * d->out_stride < d->out_H &&
+                d->out_w0 + (d->OW - 1) * d->out_stride < d->out_W,
+                "conv: strided output (stride %d, origin %d,%d, window %dx%d) must fit the %dx%d destination and be a plain store",
+                d->out_stride, d->out_h0, d->out_w0, d->OH, d->OW, d->out_H, d->out_W);
+    if (d->addend != nullptr)
+      IISEG_CHECK(d->ah0 + (d->OH - 1) * d->out_stride < d->AH && d->aw0 + (d->OW - 1) * d->out_stride < d->AW,
+                  "conv: strided addend window outside %dx%d", d->AH, d->AW);
+  }
   if (d->pooled != nullptr && d->pool_H > 0)
     IISEG_CHECK(d->oh0 % 2 == 0 && d->ow0 % 2 == 0 && d->oh0 / 2 + d->OH / 2 <= d->pool_H && d->ow0 / 2 + d->OW / 2 <= d->pool_W,
                 "conv: pooled window (origin %d,%d size %dx%d) must be even-aligned and inside the %dx%d pooled tensor",
                 d->oh0, d->ow0, d->OH, d->OW, d->pool_H, d->pool_W);
-  if (d->addend != nullptr)
+  if (d->addend != nullptr && d->out_stride <= 1)
     IISEG_CHECK(d->ah0 >= 0 && d->aw0 >= 0 && d->ah0 + d->OH <= d->AH && d->aw0 + d->OW <= d->AW,
                 "conv: addend window [%d+%d, %d+%d] outside %dx%d", d->ah0, d->OH, d->aw0, d->OW, d->AH, d->AW);
 
@@ -1884,7 +1944,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // The halo-tile kernel pays off where the per-tap kernel is bound by re-fetching activations: few
   // channel blocks and narrow tiles (the high-resolution layers).  Big-K layers keep per-tap loads
   // (they already run at the tensor roofline, and small maps lose M rows to the halo pitch).
-  bool halo = env_halo && d->R == 3 && d->S == 3 && (!d->split || hsplit_ok) && d->Cout == BN && BN <= 128;
+  bool halo = env_halo && d->R == 3 && d->S == 3 && (!d->split || hsplit_ok) && d->Cout == BN && BN <= 128 && d->out_stride <= 1;
   const bool hsplit = halo && d->split;
   {
     // IISEG_HALO_KB32=1 (experiment, off): 32-channel K blocks (64-byte rows, SWIZZLE_64B) for the layers whose resident
@@ -1946,6 +2006,14 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(halo || !depool, "conv: no halo-tile plan for this DePool2D-fused conv (window %dx%d, %d channels)", d->OH, d->OW, d->C[0]);
   if (!halo) {
     choose_box(covH, covW, &p.TH, &p.TW, fuse_pool);
+    if (fuse_pool && d->split && BN >= 64) {
+      // split precision + fused pool: an 8 x 16 box puts the four pixels of a pool window in one epilogue warp (lanes l, l^1,
+      // l^16, l^17), so the pool + tie mask run on registers instead of through the staged shared-memory tile.  Taken when
+      // it needs at most 5 % more tiles than the best box (the high-resolution layers, whose epilogue sets the pace).
+      const long best = (long)ceil_div(covH, p.TH) * ceil_div(covW, p.TW), shfl = (long)ceil_div(covH, 8) * ceil_div(covW, 16);
+      static const int env_shfl = getenv("IISEG_SPLIT_SHFL_POOL") ? atoi(getenv("IISEG_SPLIT_SHFL_POOL")) : 1;
+      if (env_shfl && covH >= 8 && covW >= 16 && shfl * 100 <= best * 105) { p.TH = 8; p.TW = 16; }
+    }
     p.pitch = p.TW;
     box_h = p.TH; box_w = p.TW;
     // CTA-pair kernel: units run in whole rounds over the SM pairs.  256-wide N tiles are ~15 % more efficient per
@@ -2020,6 +2088,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   p.inv_tw2 = p.TW >= 2 ? 1.0f / (p.TW >> 1) : 1.0f;
   p.inv_ntiles = 1.0f / p.n_ntiles; p.inv_tiles_w = 1.0f / p.tiles_w; p.inv_tiles_h = 1.0f / p.tiles_h;
   p.OH = d->OH; p.OW = d->OW; p.Cout = d->Cout;
+  p.o_s = d->out_stride > 1 ? d->out_stride : 1;
+  if (p.o_s > 1) { p.OHs = d->out_H; p.OWs = d->out_W; p.o_h0 = d->out_h0; p.o_w0 = d->out_w0; }
+  else { p.OHs = d->OH; p.OWs = d->OW; p.o_h0 = 0; p.o_w0 = 0; }
   p.AH = d->AH; p.AW = d->AW; p.ah0 = d->ah0; p.aw0 = d->aw0;
   p.addend_cs = d->addend_cs > 0 ? d->addend_cs : ((d->split && !d->addend_f32) ? 2 * d->Cout : d->Cout);
   p.relu = d->relu; p.out_f32 = d->out_f32; p.addend_f32 = d->addend_f32;

@@ -191,7 +191,7 @@ class IterativeInference(object):
         for it in range(num_iter):
             # the first iteration of a batch computes the whole contracting path (h is new); later ones only
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
-            if self.fuse_update and not net.split_up:
+            if self.fuse_update and net.fusable_update:
                 # softmax tail + update + norm in the epilogue of up_conv1: the logits never reach HBM
                 net.logits(st['h'], st['y_bf16'], full_down=(it == 0),
                            update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))

@@ -30,7 +30,7 @@ def _levels(concat_h, additional_pool):
 
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
-                 n_filters=64, additional_pool=2, device='cuda', precision='bf16'):
+                 n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind'):
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
         hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
@@ -39,6 +39,11 @@ class DAENet(object):
         errors (oracle/precision_mix.py: same parity numbers as 'fp32x3' on every iteration)."""
         K.require_device()
         assert precision in ('bf16', 'fp32x3', 'mixed'), precision
+        # 'inverse' (lasagne InverseLayer of the pool, models/fcn_up.py:76-79) IS DePool2D's repeat * tie-mask under Theano's
+        # CPU MaxPoolGrad (the gradient of a max-pool w.r.t. its input goes to every tied maximum); 'standard'
+        # (models/fcn_up.py:37-63) replaces unpool + conv by Deconv2DLayer(4, stride=2), run as four 2x2 phase convs
+        assert unpool_type in ('trackind', 'inverse', 'standard'), unpool_type
+        self.unpool_type = unpool_type
         self.precision = precision
         self.split = precision != 'bf16'          # contracting path (and the h / y input format)
         self.split_up = precision == 'fp32x3'     # expanding path
@@ -92,8 +97,25 @@ class DAENet(object):
             W, b = params[2 * (self.total + i)], params[2 * (self.total + i) + 1]
             n_cl = n_classes if p == 1 else self.filters[p - 2]   # models/fcn_up.py:29-34
             cout_pad = 16 if p == 1 else n_cl
-            self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split_up))
+            if unpool_type == 'standard':
+                # Deconv2DLayer W (in, out, 4, 4), flip_filters=False = conv_transpose2d with the flipped kernel Wf:
+                #   out[2m + py] = x[m - 1] * Wf[py + 2] + x[m] * Wf[py]
+                # i.e. output phase (py, px) is a 2x2 cross-correlation with pad 1 whose taps are (Wf[q + 2], Wf[q])
+                Wf = torch.as_tensor(W).flip(2, 3)
+                assert tuple(Wf.shape) == (up_in, n_cl, 4, 4), tuple(Wf.shape)
+                phases = []
+                for py in range(2):
+                    row = []
+                    for px in range(2):
+                        Wc = Wf[:, :, [py + 2, py]][:, :, :, [px + 2, px]].permute(1, 0, 2, 3).contiguous()      # (out, in, 2, 2)
+                        row.append(pack_conv(Wc, b, [(up_in, up_in)], cout_pad, self.device, split=self.split_up))
+                    phases.append(row)
+                self.up.append(phases)
+            else:
+                self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split_up))
             up_in = n_cl
+        # the softmax tail + update can run in the epilogue of the last conv when that conv is a bf16 3x3 conv
+        self.fusable_update = unpool_type != 'standard' and not self.split_up
         self._ws = {}
 
     # -- shapes -----------------------------------------------------------
@@ -214,6 +236,8 @@ class DAENet(object):
         iterative-inference update run in the epilogue of the last conv (y and y_bf16 are updated in
         place, the logits are never stored) and None is returned."""
         B, H, W, _ = y_bf16.shape
+        if self.unpool_type == 'standard':
+            full_down = True          # (no crop cone / y-dependent windows for this variant: every level is computed in full)
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
         Wc, Wu = ws['Wc'], ws['Wu']
@@ -243,6 +267,8 @@ class DAENet(object):
                 K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
                          split=sp)
             x = ws['pool'][p]
+        if self.unpool_type == 'standard':
+            return self._up_standard(ws, sizes, B, H, W)
         u, u_origin = ws['pool'][-1], (0, 0)
         prefilled = False
         for i, p in enumerate(range(self.total, 0, -1)):
@@ -288,6 +314,48 @@ class DAENet(object):
         return ws['logits']
 
 
+def _phase_range(size_in, size_out, crop, q):
+    """Phase q of a stride-2, 4-tap transposed conv of a length-`size_in` axis produces out[2m + q], m = 0..size_in; after
+    a centre crop by `crop` to `size_out` the kept m are [lo, hi] and out index 2*lo + q - crop is the first written."""
+    lo = max(0, (crop - q + 1) // 2)
+    hi = min(size_in, (size_out - 1 + crop - q) // 2)
+    return lo, hi - lo + 1, 2 * lo + q - crop
+
+
+def _up_standard(self, ws, sizes, B, H, W):
+    """Expanding path of unpool_type='standard' (models/fcn_up.py:37-63): per level Deconv2DLayer(4, stride 2, 'valid',
+    linear) as four 2x2 phase convolutions whose epilogues store with pixel stride 2 straight into the centre-cropped
+    map and add the skip partner pool_{p-1} read at the same stride (ElemwiseSumLayer, cropping=center)."""
+    spu, mixed = self.split_up, self.split and not self.split_up
+    prev, prev_pair_hi = ws['pool'][-1], mixed
+    for i, p in enumerate(range(self.total, 0, -1)):
+        hp, wp = prev.shape[1], prev.shape[2]
+        dh, dw = 2 * hp + 2, 2 * wp + 2
+        Sh, Sw = sizes[p - 1] if p > 1 else (H, W)
+        assert dh >= Sh and dw >= Sw
+        ch, cw = (dh - Sh) // 2, (dw - Sw) // 2
+        key = ('std', p)
+        dest = ws.get(key)
+        if dest is None:
+            c = 16 if p == 1 else self.cm_up * self.filters[p - 2]
+            dest = ws[key] = torch.empty((B, Sh, Sw, c), dtype=torch.float32 if p == 1 else torch.bfloat16, device=self.device)
+        for py in range(2):
+            m0, mh, o_h0 = _phase_range(hp, Sh, ch, py)
+            for px in range(2):
+                n0, nw, o_w0 = _phase_range(wp, Sw, cw, px)
+                Wk, bk = self.up[i][py][px]
+                kw = {}
+                if p > 1:       # skip partner, same size as the cropped map (pool_{p-1} never is the larger one)
+                    kw = dict(addend=ws['pool'][p - 2], addend_off=(o_h0, o_w0), addend_pair_hi=mixed)
+                K.conv2d(prev, Wk, bk, 2, 2, 1, relu=False, window=(m0, n0, mh, nw), out_f32=(p == 1), split=spu,
+                         out_strided=(dest, 2, (o_h0, o_w0)), src_pair_hi=prev_pair_hi, **kw)
+        prev, prev_pair_hi = dest, False
+    return prev
+
+
+DAENet._up_standard = _up_standard
+
+
 def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_concat,
              padding, ae_h=False, void_labels=[], path_weights='/Tmp/romerosa/itinf/models/',
              model_name='dae_model.npz', trainable=False, load_weights=False,
@@ -300,9 +368,19 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     reference's non-deterministic mask sub-graph (layers/mylayers.py:91-93); inference here
     is the deterministic noise=0 graph."""
     import os
-    if unpool_type != 'trackind' or not skip or conv_before_pool != 1 or bn or dropout > 0 or ae_h:
-        raise NotImplementedError('B200 DAE_h supports unpool_type=trackind, skip=True, conv_before_pool=1, '
-                                  'bn=0, dropout=0, ae_h=False')
+    import warnings
+    if unpool_type not in ('trackind', 'inverse', 'standard'):
+        raise ValueError('Unkown unpool type')                       # models/fcn_up.py:115
+    if not skip or conv_before_pool != 1 or bn or ae_h:
+        raise NotImplementedError('B200 DAE_h supports unpool_type in (trackind, inverse, standard), skip=True, '
+                                  'conv_before_pool=1, bn=0, ae_h=False')
+    # dropout: DropoutLayer is the identity under deterministic=True (iterative_inference.py:189-190), so it does not
+    # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
+    # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
+    # build is the deterministic graph; warn so that a caller comparing against such a reference run knows.
+    if unpool_type == 'trackind' and (noise > 0 or dropout > 0):
+        warnings.warn('buildDAE: noise=%s dropout=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
+                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks' % (noise, dropout), stacklevel=2)
     concat_h = list(concat_h)
     if len(concat_h) != 1 or 'pool' not in concat_h[-1]:
         raise NotImplementedError('B200 DAE_h concatenates h at one pool layer (e.g. concat_h=[\'pool4\'])')
@@ -311,5 +389,5 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
             raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
-                 n_filters=n_filters, additional_pool=additional_pool, precision=precision)
+                 n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -32,7 +32,7 @@ def fcn8_shapes(nb_in_channels, n_classes):
     return out
 
 
-def dae_shapes(n_classes, nb_features_to_concat, n_filters=64, concat_h=('pool4',), additional_pool=2):
+def dae_shapes(n_classes, nb_features_to_concat, n_filters=64, concat_h=('pool4',), additional_pool=2, unpool_type='trackind'):
     """(name, W shape, b shape) of DAE_h's convs: conv1_1..convP_1 (models/fcn_down.py:96-104) then
     up_convP..up_conv1 (models/fcn_up.py:29-34,84-86)."""
     last = concat_h[-1]
@@ -49,7 +49,10 @@ def dae_shapes(n_classes, nb_features_to_concat, n_filters=64, concat_h=('pool4'
     up_in = widths[-1]
     for p in range(total, 0, -1):
         n_cl = n_classes if p == 1 else widths[p - 2]
-        out.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
+        if unpool_type == 'standard':      # Deconv2DLayer(n_cl, 4, stride=2): W (in, out, 4, 4), models/fcn_up.py:41-45
+            out.append(('up%d' % p, (up_in, n_cl, 4, 4), (n_cl,)))
+        else:
+            out.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
         up_in = n_cl
     return out
 
@@ -69,13 +72,13 @@ def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
 
 
 def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64, concat_h=('pool4',),
-                         additional_pool=2, out_gain=1.0):
+                         additional_pool=2, out_gain=1.0, unpool_type='trackind'):
     """lasagne.init.GlorotUniform (a = sqrt(6 / ((n_out + n_in) * kh * kw))) W, zero b; `up_conv1` W x out_gain."""
     gen = torch.Generator().manual_seed(seed)
     params = []
-    for name, ws, bs in dae_shapes(n_classes, nb_features_to_concat, n_filters, concat_h, additional_pool):
+    for name, ws, bs in dae_shapes(n_classes, nb_features_to_concat, n_filters, concat_h, additional_pool, unpool_type):
         W = _uniform(ws, np.sqrt(6.0 / ((ws[0] + ws[1]) * int(np.prod(ws[2:])))), gen)
-        params += [W * out_gain if name == 'up_conv1' else W, torch.zeros(bs)]
+        params += [W * out_gain if name in ('up_conv1', 'up1') else W, torch.zeros(bs)]
     return params
 
 

@@ -98,7 +98,7 @@ def dae_levels(concat_h=('pool4',), additional_pool=2):
 
 
 def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
-                     concat_h=('pool4',), additional_pool=2):
+                     concat_h=('pool4',), additional_pool=2, unpool_type='trackind'):
     """[(name, W shape, b shape)] in checkpoint order: conv1_1..convP_1 then
     up_convP..up_conv1.  Filter counts: n_filters*2**p for p<6
     (models/fcn_down.py:96-99); up_conv_p outputs the channel count of
@@ -122,13 +122,16 @@ def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
     for p in range(total, 0, -1):
         # pool_{p-1}.input_shape[1]: the (un-concatenated) conv output of level p-1
         n_cl = n_classes if p == 1 else conv_out[p - 2]
-        shapes.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
+        if unpool_type == 'standard':   # Deconv2DLayer(n_cl, 4, stride=2): W (in, out, 4, 4)  (models/fcn_up.py:41-45)
+            shapes.append(('up%d' % p, (up_in, n_cl, 4, 4), (n_cl,)))
+        else:
+            shapes.append(('up_conv%d' % p, (n_cl, up_in, 3, 3), (n_cl,)))
         up_in = n_cl
     return shapes
 
 
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
-                return_logits=False):
+                return_logits=False, unpool_type='trackind'):
     """One application DAE(y, h) -> probabilities, same size as y.
 
     Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
@@ -138,6 +141,11 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
     Up (models/fcn_up.py:65-113): DePool2D with the tie mask of level p's
     pre-pool map, conv3x3 'same' linear, skip-sum with the un-concatenated
     pool_{p-1} (p>1) or centre crop to the input size (p==1); channel softmax.
+    unpool_type='inverse' (models/fcn_up.py:76-79): lasagne InverseLayer(prev, pool_p) = the gradient of
+    the max-pool w.r.t. its input with `prev` as the upstream gradient; with Theano's CPU MaxPoolGrad
+    (every tied maximum receives it) that is exactly DePool2D's repeat * tie-mask, so it shares the code.
+    unpool_type='standard' (models/fcn_up.py:37-63): up_p = Deconv2DLayer(prev, n_cl, 4, stride=2,
+    crop='valid', linear) and NO convolution; skip-sum / crop as above (centre crop of the larger map).
     """
     n_pool, total = dae_levels(concat_h, additional_pool)
     Wd = [(params[2 * i], params[2 * i + 1]) for i in range(total)]
@@ -157,8 +165,13 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
             x = torch.cat([h, x], dim=1)
     u = pools[-1]
     for i, p in enumerate(range(total, 0, -1)):
-        u = L.depool2d(u, pre[p - 1])
-        u = L.conv2d(u, *Wu[i], pad='same', relu=False)
+        if unpool_type == 'standard':
+            u = L.deconv2d(u, *Wu[i], stride=2)
+        elif unpool_type in ('trackind', 'inverse'):
+            u = L.depool2d(u, pre[p - 1])
+            u = L.conv2d(u, *Wu[i], pad='same', relu=False)
+        else:
+            raise ValueError('Unkown unpool type')
         if p > 1:
             a, b = L.center_crop_pair(u, pools[p - 2])
             u = a + b

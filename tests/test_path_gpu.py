@@ -479,3 +479,62 @@ def test_checkpoints_load_from_disk_in_the_reference_layout(cuda, tmp_path):
     b = inference('camvid', 'fcn8', 0.05, 2, data_iter=_tiny_iter(2, 2), fcn_params=pf, dae_params=pd, loadpath=str(ldir), **kw)
     assert np.array_equal(a['cm'], b['cm']) and np.array_equal(a['jacc_tot'], b['jacc_tot']) and a['iterative'] == b['iterative']
     assert a['n_exec'] == b['n_exec'] == [2, 2]
+
+
+# ---------------------------------------------------------------------------
+# SURVEY 8(f4), first slice: the other unpool types of models/fcn_up.py
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['mixed', 'bf16'])
+def test_unpool_type_standard_deconv_vs_oracle(cuda, precision):
+    """unpool_type='standard' (models/fcn_up.py:37-63): Deconv2DLayer(4, stride=2, crop='valid') per level + centre-cropped
+    skip-sum, no convolution on the way up.  One application and a 3-step loop against the oracle, odd and even sizes."""
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import function_pred_dae, IterativeInference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=4, out_gain=0.1, unpool_type='standard')
+    assert tuple(pd[12].shape) == (2048, 1024, 4, 4) and tuple(pd[22].shape) == (64, NCLS, 4, 4)
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0, n_filters=64,
+                   conv_before_pool=1, additional_pool=2, skip=True, unpool_type='standard', params=pd, precision=precision)
+    tol, agree = (TOL_F32, MIN_ARGMAX_F32) if precision == 'mixed' else (TOL_DAE_P, MIN_ARGMAX)
+    for (H, W) in ((32, 40), (37, 45)):
+        X, L, lab = weights.synthetic_batch(2, H, W, NCLS, seed=13)
+        h, y0 = nets.fcn8_forward(pf, X, NCLS)
+        p_o = nets.dae_forward(pd, y0, h, 100, unpool_type='standard')
+        p_d = function_pred_dae(dae)(h.numpy(), y0.numpy())
+        assert p_d.shape == tuple(p_o.shape)
+        assert float(np.abs(p_d - p_o.numpy()).max()) < tol, float(np.abs(p_d - p_o.numpy()).max())
+        y_o = y0.clone()
+        for _ in range(3):
+            y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, h, 100, unpool_type='standard')), 0, 1)
+        res = IterativeInference(dae, NCLS, [NCLS]).run(h.to(cuda), y0.to(cuda), 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))
+        y = res['y'].cpu()
+        assert float((y - y_o).abs().max()) < tol and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
+        onehot = np.eye(NCLS + 1, dtype=np.float32)[lab.numpy()].transpose(0, 3, 1, 2)
+        assert np.array_equal(res['cm'].sum(0).cpu().numpy().reshape(NCLS, NCLS), M.confusion_matrix(y.numpy(), onehot, NCLS))
+
+
+def test_unpool_type_inverse_is_the_tie_mask_unpool(cuda, built):
+    """unpool_type='inverse' (models/fcn_up.py:76-79): lasagne's InverseLayer of the max-pool = the pool's input-gradient with
+    the incoming map as upstream gradient; Theano's CPU MaxPoolGrad sends it to EVERY tied maximum, which is DePool2D's
+    repeat * tie-mask.  Checked in the oracle with autograd-free arithmetic (the gradient rule written out), and on the device
+    as bit-identical results of the two unpool types."""
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import function_pred_dae
+    from oracle import lasagne_semantics as LS
+    torch.manual_seed(0)
+    x = torch.relu(torch.randn(2, 8, 9, 11)).mul(2).round().div(2)          # many ties
+    u = torch.randn(2, 8, 4, 5)
+    # MaxPoolGrad written out: gx[i, j] += gz[i // 2, j // 2] if x[i, j] == max of its window
+    gx = torch.zeros_like(x)
+    pooled = LS.maxpool2(x)
+    for i in range(8):
+        for j in range(10):
+            gx[:, :, i, j] = torch.where(x[:, :, i, j] == pooled[:, :, i // 2, j // 2], u[:, :, i // 2, j // 2], torch.zeros(()))
+    assert torch.equal(gx, LS.depool2d(u, x))
+    pf, pd, fcn, dae = built
+    dae_inv = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0, n_filters=64,
+                       conv_before_pool=1, additional_pool=2, skip=True, unpool_type='inverse', params=pd)
+    g = np.load(os.path.join(GOLD, 'dae_32x40.npz'))
+    assert np.array_equal(function_pred_dae(dae_inv)(g['h'], g['y']), function_pred_dae(dae)(g['h'], g['y']))
+    assert float(np.abs(function_pred_dae(dae_inv)(g['h'], g['y']) - nets.dae_forward(pd, torch.from_numpy(g['y']), torch.from_numpy(g['h']), 100,
+                                                                                       unpool_type='inverse').numpy()).max()) < TOL_DAE_P
