@@ -520,9 +520,16 @@ def config4_leg(ctx):
     loss0 = tr.loss_value()
     n = max(args.steps, 5)
     ms, _ = ctx.timed(step, n)
+    ar = None
+    if world is not None:        # what the gradient exchange costs: the same eager step without it, and with one blocking all-reduce
+        ms_local, _ = ctx.timed(lambda: tr.step(h, y, L, nm, nk), n)
+        ms_block, _ = ctx.timed(lambda: tr.step(h, y, L, nm, nk, world=world), n)
+        ar = dict(tr.dp_info(), ms_per_step_without_exchange=ms_local / n, ms_per_step_blocking_allreduce=ms_block / n,
+                  exposed_ms_per_step=(ms - ms_local) / n,
+                  note='the data-parallel step runs eagerly (NCCL work is not captured); the single-GPU number is a CUDA-graph replay')
     rec = {'workload': WORKLOAD4, 'value': BATCH * ctx.world * n / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms / n,
            'steps': n, 'dtype': 'bf16 operands, fp32 accumulate, fp32 master weights', 'launches_per_step': int(launches),
-           'loss': loss0, 'allreduce': None if world is None else tr.dp_info()}
+           'loss': loss0, 'allreduce': ar}
     return rec
 
 
