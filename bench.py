@@ -297,7 +297,8 @@ def build_inference(ctx, precision, segm='fcn8'):
                         params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
         nb_h, padding = fcn[0].output_shape[1], 100
     else:
-        fcn = build_fcdensenet(None, ['pool4'], 3, NCLS, params=weights.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0))
+        fcn = build_fcdensenet(None, ['pool4'], 3, NCLS, params=weights.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0),
+                               precision=precision)
         nb_h, padding = 464, 0
     dae = buildDAE([None], None, NCLS, nb_features_to_concat=nb_h, padding=padding, concat_h=['pool4'],
                    noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
@@ -594,6 +595,12 @@ def run_b200(args):
             r3, objs = measure_inference(ctx, 'bf16', segm='densenet', strong=strong)
             line['config3'] = {'workload': WORKLOAD3, 'value': r3['value'], 'unit': 'images/s', 'ms_per_step': r3['ms_per_step'], 'e2e': r3['e2e'],
                                'dtype': 'bf16 operands, fp32 stacks and accumulation', 'executed_iterations': r3['executed_iterations']}
+            del objs
+            torch.cuda.empty_cache()
+            r3p, objs = measure_inference(ctx, 'mixed', segm='densenet', with_e2e=False, strong=strong)
+            line['config3']['parity_grade'] = {'value': r3p['value'], 'unit': 'images/s', 'ms_per_step': r3p['ms_per_step'],
+                                               'dtype': 'fp32-accurate FC-DenseNet103 (bf16 hi/lo pairs x 3 products) + ' + DTYPES['mixed'],
+                                               'parity': 'tests/test_densenet_gpu.py::test_densenet_fp32_accurate_variant_vs_oracle: probabilities within 2e-3, argmax >= 99.9 %'}
             del objs
             torch.cuda.empty_cache()
         if 'config4' in sections:

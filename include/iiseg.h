@@ -288,7 +288,8 @@ int iiseg_onehot_to_labels(const float* onehot, int32_t* labels, int N, int C1, 
  * iiseg_bn_relu_pack: BatchNormLayer with batch statistics (iterative_inference.py:187,
  *   batch_norm_use_averages=False) + rectify + bf16 pack of channels [c0, c0+C):
  *   out[.., c] = bf16(relu((x - mean[c]) * (gamma[c] * inv_std[c]) + beta[c])), zero for C <= c < Cpad;
- *   mean == NULL: plain convert (TransitionUp's deconv input); relu = 0: no rectify.
+ *   mean == NULL: plain convert (TransitionUp's deconv input); relu = 0: no rectify;
+ *   split = 1: out is [.., 2*Cpad], the (hi | lo) bf16 pair of the fp32 value (fp32-accurate variant).
  * iiseg_channel_stats: mean and inv_std = 1/sqrt(var + eps) (biased variance over N,H,W) of channels
  *   [c0, c0+C); deterministic two-level reduction; scratch = fp64 [iiseg_channel_stats_chunks(N,H,W)][C][2].
  * iiseg_maxpool2_f32: Pool2DLayer(2,'max') of TransitionDown on fp32 maps, written as the first C
@@ -298,7 +299,7 @@ int iiseg_onehot_to_labels(const float* onehot, int32_t* labels, int N, int C1, 
  *   following ConcatLayer: out[oh,ow] = p[(oh+crop_h)&1][(ow+crop_w)&1][(oh+crop_h)>>1, (ow+crop_w)>>1]. */
 int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, int c0, int C, const float* mean,
                        const float* inv_std, const float* gamma, const float* beta, int relu,
-                       void* out, int Cpad, void* stream);
+                       void* out, int Cpad, int split, void* stream);
 int iiseg_channel_stats_chunks(int N, int H, int W);
 int iiseg_channel_stats(const float* x, int N, int H, int W, int Cs, int c0, int C, float eps,
                         double* scratch, float* mean, float* inv_std, void* stream);

@@ -356,16 +356,18 @@ def norm_finalize(norm_partial, norm, active, n_exec, H, W, eps):
 
 
 # ---- FC-DenseNet103 streaming kernels -------------------------------------------
-def bn_relu_pack(stack, C, out, c0=0, stats=None, gamma=None, beta=None, relu=True):
+def bn_relu_pack(stack, C, out, c0=0, stats=None, gamma=None, beta=None, relu=True, split=False):
     """Channels [c0, c0+C) of the fp32 NHWC `stack` -> zero-padded bf16 NHWC `out`, through BatchNorm with the batch
-    statistics `stats` = (mean, inv_std) + gamma/beta and rectify; stats=None: plain convert."""
+    statistics `stats` = (mean, inv_std) + gamma/beta and rectify; stats=None: plain convert.
+    split: out is [N,H,W,2*Cpad], the (hi | lo) bf16 pair of each fp32 value."""
     _chk(stack, F32, 'stack')
     _chk(out, BF16, 'out')
     N, H, W, Cs = stack.shape
-    assert tuple(out.shape[:3]) == (N, H, W) and out.shape[3] >= C
+    cpad = out.shape[3] // (2 if split else 1)
+    assert tuple(out.shape[:3]) == (N, H, W) and cpad >= C
     mean, inv_std = stats if stats is not None else (None, None)
     _lib.call('iiseg_bn_relu_pack', _ptr(stack), N, H, W, Cs, c0, C, _ptr(mean), _ptr(inv_std), _ptr(gamma), _ptr(beta),
-              int(bool(relu)), _ptr(out), out.shape[3], _stream())
+              int(bool(relu)), _ptr(out), cpad, int(bool(split)), _stream())
     return out
 
 

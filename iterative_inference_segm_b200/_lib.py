@@ -82,7 +82,7 @@ SIGNATURES = {
     'iiseg_norm_finalize': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     'iiseg_norm_finalize_fixed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     'iiseg_onehot_to_labels': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    'iiseg_bn_relu_pack': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    'iiseg_bn_relu_pack': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     'iiseg_channel_stats_chunks': (_i, [_i, _i, _i]),
     'iiseg_channel_stats': (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     'iiseg_maxpool2_f32': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -22,7 +22,7 @@ namespace iiseg {
 __global__ void __launch_bounds__(256) bn_relu_pack_kernel(const float* __restrict__ x, long long P, int Cs, int c0, int C,
                                                            const float* __restrict__ mean, const float* __restrict__ inv_std,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int relu, uint4* __restrict__ out, int C8pad) {
+                                                           int relu, uint4* __restrict__ out, int C8pad, int split) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long nthr = (long long)gridDim.x * blockDim.x;
   const int cg = (int)(tid % C8pad);
@@ -64,7 +64,15 @@ __global__ void __launch_bounds__(256) bn_relu_pack_kernel(const float* __restri
           for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
         }
       }
-      stg_v4(out + pix * C8pad + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+      const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]), h2 = pack_bf16x2(v[4], v[5]), h3 = pack_bf16x2(v[6], v[7]);
+      if (!split) {
+        stg_v4(out + pix * C8pad + cg, make_uint4(h0, h1, h2, h3));
+      } else {        // (hi | lo) pair of the fp32 value: the operand format of the fp32-accurate convs (iiseg_conv_desc.split)
+        stg_v4(out + pix * (2 * C8pad) + cg, make_uint4(h0, h1, h2, h3));
+        stg_v4(out + pix * (2 * C8pad) + C8pad + cg,
+               make_uint4(pack_bf16x2(v[0] - bf16_lo(h0), v[1] - bf16_hi(h0)), pack_bf16x2(v[2] - bf16_lo(h1), v[3] - bf16_hi(h1)),
+                          pack_bf16x2(v[4] - bf16_lo(h2), v[5] - bf16_hi(h2)), pack_bf16x2(v[6] - bf16_lo(h3), v[7] - bf16_hi(h3))));
+      }
     }
   }
 }
@@ -194,7 +202,7 @@ static int sgrid(long long total) {
 
 extern "C" int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, int c0, int C, const float* mean,
                                   const float* inv_std, const float* gamma, const float* beta, int relu, void* out,
-                                  int Cpad, void* stream) {
+                                  int Cpad, int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(x && out, "bn_relu_pack: null tensor");
   IISEG_CHECK(N > 0 && H > 0 && W > 0 && C > 0 && c0 >= 0 && c0 + C <= Cs && Cpad >= C && Cpad % 8 == 0, "bn_relu_pack: bad shape C=%d Cs=%d Cpad=%d", C, Cs, Cpad);
@@ -210,7 +218,7 @@ extern "C" int iiseg_bn_relu_pack(const float* x, int N, int H, int W, int Cs, i
   if (blocks > cap) blocks = cap;
   blocks = (blocks + unit - 1) / unit * unit;
   bn_relu_pack_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, P, Cs, c0, C, mean, inv_std, gamma, beta, relu, reinterpret_cast<uint4*>(out), C8);
+      x, P, Cs, c0, C, mean, inv_std, gamma, beta, relu, reinterpret_cast<uint4*>(out), C8, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -44,11 +44,9 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
                         params=fcn_params, precision=precision)
         padding = 100
     elif segm_net == 'densenet':
-        if precision != 'bf16':
-            raise NotImplementedError('FC-DenseNet103 is built for precision=bf16 only')
         fcn = build_fcdensenet(None, dae_dict['concat_h'], nb_in_channels, n_classes, output_d='4d', from_gt=False,
                                weight_path=os.path.join(weights_path or '', dataset, 'DenseNet103', 'weights',
-                                                        'FC-DenseNet103_weights.npz'), params=fcn_params)
+                                                        'FC-DenseNet103_weights.npz'), params=fcn_params, precision=precision)
         padding = 0
     elif segm_net == 'fcn_fcresnet':
         raise NotImplementedError

@@ -48,13 +48,19 @@ class _Stack(object):
 
 class DenseNetNet(object):
     def __init__(self, nb_in_channels, n_classes, params, n_first=48, n_pool=5, growth=16,
-                 n_layers=N_LAYERS_103, device='cuda'):
+                 n_layers=N_LAYERS_103, device='cuda', precision='bf16'):
+        """precision: 'bf16' (bf16 conv operands, fp32 stacks / statistics / accumulation) or 'fp32x3' / 'mixed' (the net
+        has no expanding path of the DAE kind, so both mean: every conv fp32-accurate -- BN + rectify packs the (hi, lo)
+        bf16 pair of its fp32 result and each conv accumulates hi*hi + lo*hi + hi*lo; see DAENet)."""
         K.require_device()
+        assert precision in ('bf16', 'fp32x3', 'mixed'), precision
+        self.precision = precision
         assert n_classes <= 16 and nb_in_channels <= 16 and growth == 16
         self.nb_in, self.n_classes = nb_in_channels, n_classes
         self.n_first, self.n_pool, self.growth, self.n_layers = n_first, n_pool, growth, list(n_layers)
         self.device = dev = torch.device(device)
-        self.split, self.cm = False, 1          # interface shared with FCN8Net (precision 'bf16' only)
+        self.split = sp = precision != 'bf16'     # interface shared with FCN8Net
+        self.cm = 2 if sp else 1
         it = iter(params)
 
         def vec(a):
@@ -64,11 +70,11 @@ class DenseNetNet(object):
             beta, gamma, _mean, _inv_std = next(it), next(it), next(it), next(it)   # stored averages are never read (:187)
             W, b = next(it), next(it)
             assert tuple(W.shape[1:]) == (cin, k, k), (tuple(W.shape), cin, k)
-            Wk, bk = pack_conv(W, b, [(cin, _r64(cin))], cout_pad, dev)
+            Wk, bk = pack_conv(W, b, [(cin, _r64(cin))], cout_pad, dev, split=sp)
             return {'gamma': vec(gamma), 'beta': vec(beta), 'W': Wk, 'b': bk, 'cin': cin}
 
         W, b = next(it), next(it)
-        self.first = pack_conv(W, b, [(nb_in_channels, 16)], _r64(n_first), dev)
+        self.first = pack_conv(W, b, [(nb_in_channels, 64 if sp else 16)], _r64(n_first), dev, split=sp)
         n = n_first
         self.down, self.td, self.skip_ch = [], [], []
         for i in range(n_pool):
@@ -100,7 +106,7 @@ class DenseNetNet(object):
             up_ch = growth * n_layers[n_pool + i + 1]
         W, b = next(it), next(it)
         assert tuple(W.shape) == (n_classes, n, 1, 1)
-        self.final = pack_conv(W, b, [(n, _r64(n))], 16, dev)
+        self.final = pack_conv(W, b, [(n, _r64(n))], 16, dev, split=sp)
         self.final_in = n
         assert next(it, None) is None, 'unused parameters'
         self._ws = {}
@@ -119,7 +125,7 @@ class DenseNetNet(object):
                 ah = [2, 0] if py == 0 else [1]
                 aw = [2, 0] if px == 0 else [1]
                 Wc = Wf[:, :, ah][:, :, :, aw].permute(1, 0, 2, 3).contiguous()      # (out, in, R, S)
-                row.append(pack_conv(Wc, b, [(cin, _r64(cin))], _r64(keep), self.device) + (len(ah), len(aw)))
+                row.append(pack_conv(Wc, b, [(cin, _r64(cin))], _r64(keep), self.device, split=getattr(self, 'split', False)) + (len(ah), len(aw)))
             phases.append(row)
         return {'phases': phases, 'cin': cin, 'keep': keep}
 
@@ -135,7 +141,7 @@ class DenseNetNet(object):
         key = ('pack', B, H, W, C)
         t = self._ws.get(key)
         if t is None:
-            t = self._ws[key] = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=self.device)
+            t = self._ws[key] = torch.empty((B, H, W, self.cm * C), dtype=torch.bfloat16, device=self.device)
         return t
 
     def _stats(self, st, c0, C):
@@ -148,8 +154,8 @@ class DenseNetNet(object):
         C = lay['cin']
         assert st.n == C
         xb = K.bn_relu_pack(st.t, C, self._packbuf(B, H, W, _r64(C)), stats=(st.mean, st.inv_std), gamma=lay['gamma'],
-                            beta=lay['beta'], relu=True)
-        K.conv2d(xb, lay['W'], lay['b'], 3, 3, 1, relu=False, out_f32=True, out_slice=(st.t, C))
+                            beta=lay['beta'], relu=True, split=self.split)
+        K.conv2d(xb, lay['W'], lay['b'], 3, 3, 1, relu=False, out_f32=True, out_slice=(st.t, C), split=self.split)
         self._stats(st, C, 16)
         st.n = C + 16
 
@@ -182,9 +188,10 @@ class DenseNetNet(object):
         assert Cin == self.nb_in
         dev, g = X.device, self.growth
         out = {}
-        x16 = K.pack_nchw(X.contiguous(), 16)
+        sp = self.split
+        x16 = K.pack_nchw(X.contiguous(), 64 if sp else 16, split=sp)
         st = _Stack(B, H, W, self.skip_ch[0], dev)
-        first = K.conv2d(x16, self.first[0], self.first[1], 3, 3, 1, relu=False, out_f32=True)     # 64-padded fp32
+        first = K.conv2d(x16, self.first[0], self.first[1], 3, 3, 1, relu=False, out_f32=True, split=sp)     # 64-padded fp32
         st.t[..., :self.n_first].copy_(first[..., :self.n_first])
         st.n = self.n_first
         self._stats(st, 0, self.n_first)
@@ -197,8 +204,8 @@ class DenseNetNet(object):
             # TransitionDown: BN_ReLU_Conv(stack, n, 1x1) -> maxpool 2
             td, C = self.td[i], st.n
             xb = K.bn_relu_pack(st.t, C, self._packbuf(B, h, w, _r64(C)), stats=(st.mean, st.inv_std), gamma=td['gamma'],
-                                beta=td['beta'], relu=True)
-            y = K.conv2d(xb, td['W'], td['b'], 1, 1, 0, relu=False, out_f32=True)
+                                beta=td['beta'], relu=True, split=sp)
+            y = K.conv2d(xb, td['W'], td['b'], 1, 1, 0, relu=False, out_f32=True, split=sp)
             h, w = h // 2, w // 2
             n_next = self.skip_ch[i + 1] if i + 1 < self.n_pool else self.bott_in + g * self.n_layers[self.n_pool]
             nxt = _Stack(B, h, w, n_next, dev)
@@ -209,8 +216,8 @@ class DenseNetNet(object):
             name = 'pool%d' % (i + 1)
             if name in want:      # the stack right after the transition (models/FCDenseNet.py:96-97)
                 out[name] = st.t[..., :C].contiguous()                                   # fp32 NHWC [B,h,w,C]
-                out[name + '_bf16'] = K.bn_relu_pack(st.t, C, torch.empty((B, h, w, _r64(C)), dtype=torch.bfloat16, device=dev),
-                                                     relu=False)                          # what DAENet.logits reads
+                out[name + '_bf16'] = K.bn_relu_pack(st.t, C, torch.empty((B, h, w, self.cm * _r64(C)), dtype=torch.bfloat16, device=dev),
+                                                     relu=False, split=sp)                # what DAENet.logits reads
         for lay in self.bottleneck:
             self._dense_layer(st, lay)
         up_c0, up_ch = self.bott_in, g * self.n_layers[self.n_pool]       # block_to_upsample = the block's new maps
@@ -218,13 +225,13 @@ class DenseNetNet(object):
             tu, skip = self.tu[i], skips[self.n_pool - 1 - i]
             keep = tu['keep']
             # Deconv2DLayer(3, stride 2) of the (un-normalised) block maps, as four phase convolutions
-            xb = K.bn_relu_pack(st.t, up_ch, self._packbuf(B, h, w, _r64(up_ch)), c0=up_c0, relu=False)
+            xb = K.bn_relu_pack(st.t, up_ch, self._packbuf(B, h, w, _r64(up_ch)), c0=up_c0, relu=False, split=sp)
             phases = []
             for py in range(2):
                 row = []
                 for px in range(2):
                     Wk, bk, R, S = tu['phases'][py][px]
-                    row.append(K.conv2d(xb, Wk, bk, R, S, 1, relu=False, out_f32=True,
+                    row.append(K.conv2d(xb, Wk, bk, R, S, 1, relu=False, out_f32=True, split=sp,
                                         window=(1 if R == 1 else 0, 1 if S == 1 else 0, h + 1, w + 1)))
                 phases.append(row)
             sh, sw = skip.t.shape[1], skip.t.shape[2]
@@ -244,13 +251,13 @@ class DenseNetNet(object):
             for lay in self.up[i]:
                 self._dense_layer(st, lay)
         assert st.n == self.final_in and (h, w) == (H, W)
-        xb = K.bn_relu_pack(st.t, st.n, self._packbuf(B, h, w, _r64(st.n)), relu=False)          # SoftmaxLayer: no BN
-        logits = K.conv2d(xb, self.final[0], self.final[1], 1, 1, 0, relu=False, out_f32=True)
+        xb = K.bn_relu_pack(st.t, st.n, self._packbuf(B, h, w, _r64(st.n)), relu=False, split=sp)          # SoftmaxLayer: no BN
+        logits = K.conv2d(xb, self.final[0], self.final[1], 1, 1, 0, relu=False, out_f32=True, split=sp)
         probs = torch.empty((B, self.n_classes, H, W), dtype=torch.float32, device=dev)
         y_bf16 = None
         if y_bf16_cpad:
-            y_bf16 = torch.empty((B, H, W, y_bf16_cpad), dtype=torch.bfloat16, device=dev)
-        K.softmax_nchw(logits, self.n_classes, probs, y_bf16)
+            y_bf16 = torch.empty((B, H, W, self.cm * y_bf16_cpad), dtype=torch.bfloat16, device=dev)
+        K.softmax_nchw(logits, self.n_classes, probs, y_bf16, split=sp)
         out['probs_dimshuffle'] = probs
         out['y_bf16'] = y_bf16
         return out
@@ -261,7 +268,7 @@ _POOL_CHANNELS_103 = {'pool1': 112, 'pool2': 192, 'pool3': 304, 'pool4': 464, 'p
 
 def build_fcdensenet(input_var, layer, nb_in_channels=3, n_classes=11, output_d='4d', from_gt=False,
                      weight_path='/data/lisatmp4/romerosa/itinf/models/camvid/DenseNet103/weights/FC-DenseNet103_weights.npz',
-                     params=None):
+                     params=None, precision='bf16'):
     """Same arguments as the reference builder (models/FCDenseNet.py:196-198); `input_var` (a Theano
     symbol there) is ignored, `params` (the positional checkpoint arrays) may replace `weight_path`.
     Returns hidden_outputs (one handle per 'poolK' in `layer`) + [output] unless from_gt."""
@@ -269,7 +276,7 @@ def build_fcdensenet(input_var, layer, nb_in_channels=3, n_classes=11, output_d=
         raise NotImplementedError("output_d='2d' is not used on the iterative-inference path")
     if params is None:
         params = load_npz_params(weight_path)
-    net = DenseNetNet(nb_in_channels, n_classes, params)
+    net = DenseNetNet(nb_in_channels, n_classes, params, precision=precision)
     handles = []
     for el in layer:
         if el not in _POOL_CHANNELS_103:

@@ -10,7 +10,11 @@ from oracle import densenet as OD, lasagne_semantics as L, nets, weights
 
 pytestmark = pytest.mark.gpu
 NCLS = 11
-TOL_H, TOL_P, MIN_AGREE = 5e-2, 0.15, 0.97     # bf16 operands through 103 conv layers + a peaky softmax (logit gain 4)
+# bf16 operands through 103 conv layers + a peaky softmax (logit gain 4).  Measured on the B200 (and reproduced by a CPU
+# emulation of the same roundings): pool4 2.34e-2 of the feature scale, probabilities 8.9e-2 max-abs
+# (1.8e-3 mean-abs), argmax agreement 98.85 %; asserted with ~25 % headroom.  The fp32-accurate variant
+# (test_densenet_fp32_accurate_variant_vs_oracle) is held to 2e-3 / 99.9 %.
+TOL_H, TOL_P, MIN_AGREE = 3e-2, 0.11, 0.985
 
 
 def test_channel_stats_and_bn_pack(cuda):
@@ -65,6 +69,24 @@ def test_maxpool_f32_and_deconv_phases(cuda):
     ref = ref[:, :, (2 * H + 1 - skip_h) // 2:(2 * H + 1 - skip_h) // 2 + skip_h, :skip_w]
     got = o[..., :keep].cpu().permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_densenet_fp32_accurate_variant_vs_oracle(cuda):
+    """precision='fp32x3': BN + rectify packs (hi, lo) bf16 pairs, every conv accumulates three products.  The 103-layer
+    forward then tracks the fp32 oracle like an fp32 implementation would (a CPU emulation of the same arithmetic gives
+    pool4 6e-5 of the feature scale, probabilities 2e-4): asserted at 2e-3 / 99.9 %, the bar of the FCN8 path."""
+    from iterative_inference_segm_b200.models.FCDenseNet import build_fcdensenet
+    from iterative_inference_segm_b200.functions import function_pred_fcn
+    params = OD.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0)
+    fcn = build_fcdensenet(None, ['pool4'], 3, NCLS, params=params, precision='fp32x3')
+    X, _, _ = weights.synthetic_batch(2, 64, 96, NCLS, seed=9)
+    h_o, p_o = OD.densenet_forward(params, X, NCLS, layer=['pool4'])
+    h_d, p_d = function_pred_fcn(fcn)(X.numpy())
+    eh = float(np.abs(h_d - h_o.numpy()).max()) / float(h_o.abs().max())
+    ep = float(np.abs(p_d - p_o.numpy()).max())
+    agree = float((p_d.argmax(1) == p_o.numpy().argmax(1)).mean())
+    print('densenet fp32x3 parity: pool4 max-abs/scale %.3e  probs max-abs %.3e  argmax agree %.5f' % (eh, ep, agree))
+    assert eh < 1e-3 and ep < 2e-3 and agree >= 0.999
 
 
 @pytest.fixture(scope='module')
