@@ -116,6 +116,13 @@ typedef struct iiseg_conv_desc {
   int depool_out_H2, depool_out_W2, depool_out_ph0, depool_out_pw0;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   const float* bias;  /* fp32 [Cout]                                        */
+  /* Optional per-channel affine applied AFTER the rectifier and before the pool / store: x * post_scale[c] + post_shift[c]
+   * (fp32 [Cout] each, both or neither).  Folds the deterministic BatchNormLayer that follows the rectified convs of the
+   * DAE's contracting path when bn=1 (models/fcn_down.py:113-115: conv -> rectify -> BatchNormLayer -> Pool2DLayer; with
+   * deterministic=True, iterative_inference.py:189-190, the layer is (x - mean) * (gamma * inv_std) + beta on its stored
+   * averages).  The fused pool and its tie mask then see the normalised values, as DePool2D does. */
+  const float* post_scale;
+  const float* post_shift;
   int Cout;           /* padded: 16, or a multiple of 64                    */
   int R, S, pad;      /* filter extent and symmetric zero padding           */
   /* Output window: out pixel (oh,ow) is conv pixel (oh+oh0, ow+ow0); only the

@@ -77,7 +77,7 @@ def conv_out_size(H, W, R, S, pad):
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
            out_slice=None, pool_zmask=None, depool=None, depool_out=None, addend_pair_hi=False, out_strided=None,
-           src_pair_hi=False):
+           src_pair_hi=False, post_affine=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -94,6 +94,9 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     out_strided = (dest, stride, (h0, w0)): output pixel (oh, ow) goes to dest[n, oh*stride + h0, ow*stride + w0]
     (dest: [N,DH,DW,cm*Cout], bf16 or fp32 per out_f32) and the addend, if any, is read at the same stride from
     `addend_off` -- one output phase of a transposed convolution (iiseg_conv_desc.out_stride).  Returns dest.
+
+    post_affine = (scale, shift): fp32 [Cout] vectors applied after the rectifier, before pool / store (a folded
+    deterministic BatchNormLayer, iiseg_conv_desc.post_scale).
 
     src_pair_hi: src0 is a (hi | lo) pair tensor [N,H,W,2*C0] of which a plain bf16 conv reads the hi halves.
 
@@ -197,6 +200,11 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32), addend_cs=addend_cs,
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if post_affine is not None:
+        _chk(post_affine[0], F32, 'post_affine.scale')
+        _chk(post_affine[1], F32, 'post_affine.shift')
+        assert post_affine[0].numel() == Cout == post_affine[1].numel()
+        d.post_scale, d.post_shift = post_affine[0].data_ptr(), post_affine[1].data_ptr()
     if out_strided is not None:
         d.out, d.out_stride, d.out_H, d.out_W, d.out_h0, d.out_w0 = dest.data_ptr(), ostride, dest.shape[1], dest.shape[2], oh_0, ow_0
     if depool_out is not None:

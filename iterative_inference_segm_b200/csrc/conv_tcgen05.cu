@@ -66,6 +66,8 @@ struct alignas(64) ConvParams {
   CUtensorMap tm_w;
   CUtensorMap tm_mask;                   // fused DePool2D loader: the tie-mask words [N,H/2,W/2,C/8] (uint32)
   const float* bias;
+  const float* post_scale;   // post-activation per-channel affine (deterministic BatchNormLayer after the rectifier): x*s + t
+  const float* post_shift;
   const __nv_bfloat16* addend;
   void* out;
   int32_t* diag;
@@ -635,12 +637,25 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         // the rounding); split variant: rectify in fp32, then hi = bf16(x), lo = bf16(x - hi).
         uint32_t hi[16], lo[kSplit ? 16 : 1];
 #pragma unroll
+        const bool post = p.post_scale != nullptr;     // deterministic BatchNormLayer behind the rectifier (DAE_h bn=1)
+        if (post) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
+            float* ff = f + 4 * j4;
+            if (p.relu) { ff[0] = fmaxf(ff[0], 0.f); ff[1] = fmaxf(ff[1], 0.f); ff[2] = fmaxf(ff[2], 0.f); ff[3] = fmaxf(ff[3], 0.f); }
+            ff[0] = __fmaf_rn(ff[0], sc.x, sh.x); ff[1] = __fmaf_rn(ff[1], sc.y, sh.y);
+            ff[2] = __fmaf_rn(ff[2], sc.z, sh.z); ff[3] = __fmaf_rn(ff[3], sc.w, sh.w);
+          }
+        }
+#pragma unroll
         for (int j = 0; j < 16; ++j) {
           float a = f[2 * j], b = f[2 * j + 1];
-          if (kSplit && p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          if (kSplit && p.relu && !post) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
           hi[j] = pack_bf16x2(a, b);
           if (kSplit) lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), b - bf16_hi(hi[j]));
-          else if (p.relu && !(p.pooled != nullptr && p.pool_zmask != nullptr)) hi[j] = bf16x2_max(hi[j], 0u);   // (training: rectified at pool time)
+          else if (p.relu && !post && !(p.pooled != nullptr && p.pool_zmask != nullptr)) hi[j] = bf16x2_max(hi[j], 0u);   // (training: rectified at pool time)
         }
         if (p.out_f32) {          // fp32 rows (the hoisted term itself): 128 contiguous bytes per thread
           if (valid) {
@@ -1222,6 +1237,18 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         }
         continue;
       }
+      const bool post = p.post_scale != nullptr;       // deterministic BatchNormLayer behind the rectifier (DAE_h bn=1)
+      if (post) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
+          float* ff = f + 4 * j4;
+          if (p.relu) { ff[0] = fmaxf(ff[0], 0.f); ff[1] = fmaxf(ff[1], 0.f); ff[2] = fmaxf(ff[2], 0.f); ff[3] = fmaxf(ff[3], 0.f); }
+          ff[0] = __fmaf_rn(ff[0], sc.x, sh.x); ff[1] = __fmaf_rn(ff[1], sc.y, sh.y);
+          ff[2] = __fmaf_rn(ff[2], sc.z, sh.z); ff[3] = __fmaf_rn(ff[3], sc.w, sh.w);
+        }
+      }
       uint32_t hi[8], zw[2] = {0u, 0u};
 #pragma unroll
       for (int j = 0; j < 8; ++j) hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -1236,7 +1263,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
           zw[g] = part;
         }
       }
-      if (p.relu) {
+      if (p.relu && !post) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) hi[j] = bf16x2_max(hi[j], 0u);      // max(x, 0) commutes with the bf16 rounding
       }
@@ -1335,6 +1362,15 @@ __device__ __forceinline__ void halo_epilogue_split(const ConvParams& p, uint32_
       if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (p.post_scale != nullptr) {                    // deterministic BatchNormLayer behind the rectifier (DAE_h bn=1)
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
+          f[4 * j4] = __fmaf_rn(f[4 * j4], sc.x, sh.x); f[4 * j4 + 1] = __fmaf_rn(f[4 * j4 + 1], sc.y, sh.y);
+          f[4 * j4 + 2] = __fmaf_rn(f[4 * j4 + 2], sc.z, sh.z); f[4 * j4 + 3] = __fmaf_rn(f[4 * j4 + 3], sc.w, sh.w);
+        }
       }
       uint32_t hi[8], lo[8];
 #pragma unroll
@@ -1914,6 +1950,9 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
   IISEG_CHECK(d->N >= 1, "conv: empty batch");
+  IISEG_CHECK((d->post_scale == nullptr) == (d->post_shift == nullptr) &&
+              (d->post_scale == nullptr || (d->Cout % 64 == 0 && !d->out_f32 && d->pool_zmask == nullptr && d->depool_out == nullptr)),
+              "conv: post_scale / post_shift come together and need a bf16 (or split) output with Cout %% 64 == 0");
   if (d->out_stride > 1) {
     IISEG_CHECK(d->out != nullptr && d->pooled == nullptr && d->upd_y == nullptr && d->depool_out == nullptr && d->out_cs == 0 &&
                 d->out_h0 >= 0 && d->out_w0 >= 0 && d->out_h0 + (d->OH - 1) * d->out_stride < d->out_H &&
@@ -2070,6 +2109,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   const int w_rows_all = wgroups > 0 ? d->w_rows_total : d->Cout;
   if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN, KB, d->weight_ld)) return -1;
   p.bias = d->bias;
+  p.post_scale = d->post_scale; p.post_shift = d->post_shift;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
   p.diag = diag_device_ptr();

@@ -30,7 +30,7 @@ def _levels(concat_h, additional_pool):
 
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
-                 n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind'):
+                 n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind', bn=False):
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
         hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
@@ -64,6 +64,33 @@ class DAENet(object):
         assert self.n_pool >= 1, 'conditioning must be concatenated at a pool layer'
         self.device = torch.device(device)
         self.y_cpad = K.pad_channels(n_classes, narrow=True)    # channels of the bf16 copy of y (16: 32-byte K blocks)
+        # bn=1 (models/fcn_down.py:113-115, models/fcn_up.py:91-93): a BatchNormLayer behind every conv.  At inference the graph
+        # is built with deterministic=True (iterative_inference.py:189-190), so the layer is the affine map
+        # (x - mean) * (gamma * inv_std) + beta on its stored averages (checkpoint order beta, gamma, mean, inv_std):
+        #   contracting path: conv -> rectify -> BN -> pool  = a per-channel scale / shift in the conv epilogue, after the
+        #                     rectifier and before the pool + tie mask (iiseg_conv_desc.post_scale);
+        #   expanding path  : conv (linear) -> BN -> skip-sum = folded into the conv's weights and bias when packing.
+        self.bn = bool(bn)
+        self.post = [None] * self.total
+        if self.bn:
+            from .._packing import _as_f32
+            k_up = 2 if unpool_type == 'standard' else 6
+            assert len(params) == (6 + k_up) * self.total, 'bn=1: expected %d arrays, got %d' % ((6 + k_up) * self.total, len(params))
+            flat = []
+            for i in range(self.total):
+                W, b, beta, gamma, mean, inv_std = [_as_f32(a, self.device) for a in params[6 * i:6 * i + 6]]
+                s_ = gamma * inv_std
+                self.post[i] = (s_.contiguous(), (beta - mean * s_).contiguous())
+                flat += [W, b]
+            for i in range(self.total):
+                grp = [_as_f32(a, self.device) for a in params[6 * self.total + k_up * i:6 * self.total + k_up * (i + 1)]]
+                W, b = grp[0], grp[1]
+                if k_up == 6:
+                    beta, gamma, mean, inv_std = grp[2:]
+                    s_ = gamma * inv_std
+                    W, b = W * s_.view(-1, 1, 1, 1), b * s_ + (beta - mean * s_)
+                flat += [W, b]
+            params = flat
         assert len(params) == 4 * self.total, 'expected %d arrays, got %d' % (4 * self.total, len(params))
         # filters per level: n_filters * 2**p, p < 6 (models/fcn_down.py:96-99)
         self.filters = []
@@ -262,10 +289,10 @@ class DAENet(object):
             # pre-pool map is consumed on chip and never written (nothing else reads it)
             if p == self.n_pool:
                 K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
-                         addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0), split=sp)
+                         addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0), split=sp, post_affine=self.post[p])
             else:
                 K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
-                         split=sp)
+                         split=sp, post_affine=self.post[p])
             x = ws['pool'][p]
         if self.unpool_type == 'standard':
             return self._up_standard(ws, sizes, B, H, W)
@@ -371,16 +398,16 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     import warnings
     if unpool_type not in ('trackind', 'inverse', 'standard'):
         raise ValueError('Unkown unpool type')                       # models/fcn_up.py:115
-    if not skip or conv_before_pool != 1 or bn or ae_h:
+    if not skip or conv_before_pool != 1 or ae_h:
         raise NotImplementedError('B200 DAE_h supports unpool_type in (trackind, inverse, standard), skip=True, '
-                                  'conv_before_pool=1, bn=0, ae_h=False')
+                                  'conv_before_pool=1, ae_h=False')
     # dropout: DropoutLayer is the identity under deterministic=True (iterative_inference.py:189-190), so it does not
     # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
     # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
     # build is the deterministic graph; warn so that a caller comparing against such a reference run knows.
-    if unpool_type == 'trackind' and (noise > 0 or dropout > 0):
-        warnings.warn('buildDAE: noise=%s dropout=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
-                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks' % (noise, dropout), stacklevel=2)
+    if unpool_type == 'trackind' and (noise > 0 or dropout > 0 or bn):
+        warnings.warn('buildDAE: noise=%s dropout=%s bn=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
+                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks' % (noise, dropout, bn), stacklevel=2)
     concat_h = list(concat_h)
     if len(concat_h) != 1 or 'pool' not in concat_h[-1]:
         raise NotImplementedError('B200 DAE_h concatenates h at one pool layer (e.g. concat_h=[\'pool4\'])')
@@ -389,5 +416,5 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
             raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
-                 n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type)
+                 n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type, bn=bn)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -130,8 +130,16 @@ def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
     return shapes
 
 
+def batchnorm_deterministic(x, beta, gamma, mean, inv_std):
+    """lasagne BatchNormLayer under deterministic=True: (x - mean) * (gamma * inv_std) + beta on the STORED averages
+    (parameter order beta, gamma, mean, inv_std).  Reference: models/fcn_down.py:113-115, models/fcn_up.py:91-93 with
+    get_output(dae, deterministic=True), iterative_inference.py:189-190."""
+    v = lambda a: a.view(1, -1, 1, 1)          # noqa: E731
+    return (x - v(mean)) * (v(gamma) * v(inv_std)) + v(beta)
+
+
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
-                return_logits=False, unpool_type='trackind'):
+                return_logits=False, unpool_type='trackind', bn=False):
     """One application DAE(y, h) -> probabilities, same size as y.
 
     Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
@@ -148,8 +156,16 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
     crop='valid', linear) and NO convolution; skip-sum / crop as above (centre crop of the larger map).
     """
     n_pool, total = dae_levels(concat_h, additional_pool)
-    Wd = [(params[2 * i], params[2 * i + 1]) for i in range(total)]
-    Wu = [(params[2 * (total + i)], params[2 * (total + i) + 1]) for i in range(total)]
+    if bn:     # bn=1: a BatchNormLayer (4 arrays) behind every conv of both paths, except after 'standard' deconvs
+        k_up = 2 if unpool_type == 'standard' else 6
+        Wd = [tuple(params[6 * i:6 * i + 2]) for i in range(total)]
+        BNd = [tuple(params[6 * i + 2:6 * i + 6]) for i in range(total)]
+        Wu = [tuple(params[6 * total + k_up * i:6 * total + k_up * i + 2]) for i in range(total)]
+        BNu = [tuple(params[6 * total + k_up * i + 2:6 * total + k_up * i + 6]) if k_up == 6 else None for i in range(total)]
+    else:
+        Wd = [(params[2 * i], params[2 * i + 1]) for i in range(total)]
+        Wu = [(params[2 * (total + i)], params[2 * (total + i) + 1]) for i in range(total)]
+        BNd = BNu = [None] * total
     x = y
     if concat_h[-1] == 'input':
         x = torch.cat([h, x], dim=1)
@@ -158,6 +174,8 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input'
                      and padding > 0)
         x = L.conv2d(x, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+        if BNd[p] is not None:
+            x = batchnorm_deterministic(x, *BNd[p])
         pre.append(x)
         x = L.maxpool2(x)
         pools.append(x)
@@ -170,6 +188,8 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         elif unpool_type in ('trackind', 'inverse'):
             u = L.depool2d(u, pre[p - 1])
             u = L.conv2d(u, *Wu[i], pad='same', relu=False)
+            if BNu[i] is not None:
+                u = batchnorm_deterministic(u, *BNu[i])
         else:
             raise ValueError('Unkown unpool type')
         if p > 1:
