@@ -578,7 +578,8 @@ def test_dae_with_batchnorm_vs_oracle(cuda, unpool_type):
     # within 2^-17 |t| of the all-zero windows' constant become false ties, a handful of mask flips per application that this
     # test's BN gains (gamma * inv_std up to 3 per layer) amplify.  The fp32 oracle shows no such ties (fp32-vs-fp64 8e-8).
     tol_f32 = TOL_F32 if unpool_type == 'standard' else 6e-3       # measured: 3.7e-3 (fp32x3), 4.2e-3 (mixed)
-    for precision, tol in (('fp32x3', tol_f32), ('mixed', tol_f32), ('bf16', 2e-2)):
+    tol_bf16 = 2e-2 if unpool_type == 'standard' else 6e-2         # measured 4.2e-2 with DePool2D (tie flips x BN gains)
+    for precision, tol in (('fp32x3', tol_f32), ('mixed', tol_f32), ('bf16', tol_bf16)):
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0, n_filters=64,
