@@ -480,7 +480,7 @@ def roofline_leg(ctx, dae, ii, precision):
     breakdown = {'ms_per_dae_application': {k: round(v, 4) for k, v in other.items()},
                  'conv_ms_in_launch_order': [round(ms, 4) for _, ms in convs],
                  'conv_tensor_tflops_in_launch_order': [round(f * BATCH / (ms * 1e-3) / 1e12, 1) for f, (_, ms) in zip(flt, convs)],
-                 'conv_kernel_in_launch_order': ['%s<%d>' % (('per_tap', 'pair', 'halo')[tag[-1][0]], tag[-1][1]) for tag, _ in convs],
+                 'conv_kernel_in_launch_order': ['%s<%d>' % (('per_tap', 'pair', 'halo', 'npack')[tag[-1][0]], tag[-1][1]) for tag, _ in convs],
                  'unpool_gbs': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9,
                  'unpool_frac_of_hbm': unpool_b / (other.get('unpool2', 1e9) * 1e-3) / 1e9 / peaks['hbm_gbs'],
                  'hbm_peak_gbs': peaks['hbm_gbs'],

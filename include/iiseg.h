@@ -115,6 +115,12 @@ typedef struct iiseg_conv_desc {
   int depool_out_VH, depool_out_VW, depool_out_h0, depool_out_w0;
   int depool_out_H2, depool_out_W2, depool_out_ph0, depool_out_pw0;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
+  /* Optional (3x3, Cout = 16, one 64-channel source, fp32 or fused-update output: the DAE's logits conv): the same filter
+   * re-packed for the N-packed kernel, bf16 [39*16][64] -- for filter row r and input-column phase c = j + s (0..5) the
+   * 16-row blocks W[.][r][c - j][.] of the output pixels j = max(0, c-2) .. min(3, c) one after the other, in (r, c) order,
+   * with three zero blocks behind block (0, 0).  Four adjacent output pixels then share one accumulator row (N = 16..48 per
+   * instruction instead of 16).  NULL: the plain kernels run. */
+  const void* weight_npack;
   const float* bias;  /* fp32 [Cout]                                        */
   /* Optional per-channel affine applied AFTER the rectifier and before the pool / store: x * post_scale[c] + post_shift[c]
    * (fp32 [Cout] each, both or neither).  Folds the deterministic BatchNormLayer that follows the rectified convs of the
@@ -190,7 +196,7 @@ typedef struct iiseg_conv_desc {
 } iiseg_conv_desc;
 int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream);
 /* Which kernel the calling thread's last iiseg_conv2d_fwd launched: *kernel = 0 per-tap, 1 CTA pair (cta_group::2),
- * 2 halo tile; *bn = N tile, *kb = channels per K block.  Measurement tooling (bench.py groups launches by kernel). */
+ * 2 halo tile, 3 N-packed 16-channel kernel; *bn = N tile, *kb = channels per K block.  Measurement tooling (bench.py groups launches by kernel). */
 int iiseg_last_conv_plan(int* kernel, int* bn, int* kb);
 
 /* ---- pooling: lasagne Pool2DLayer(2) + DePool2D -------------------------

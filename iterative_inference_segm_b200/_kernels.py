@@ -77,7 +77,7 @@ def conv_out_size(H, W, R, S, pad):
 def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=None, out=None,
            out_f32=False, addend_off=(0, 0), pooled=None, pool_mask=None, split=False, update=None,
            out_slice=None, pool_zmask=None, depool=None, depool_out=None, addend_pair_hi=False, out_strided=None,
-           src_pair_hi=False, post_affine=None):
+           src_pair_hi=False, post_affine=None, weight_npack=None):
     """src0/src1: NHWC bf16; weight: bf16 [Cout, R*S*(C0+C1)]; bias fp32 [Cout].
     window = (oh0, ow0, OH, OW) selects the output window (default: all).
 
@@ -94,6 +94,9 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     out_strided = (dest, stride, (h0, w0)): output pixel (oh, ow) goes to dest[n, oh*stride + h0, ow*stride + w0]
     (dest: [N,DH,DW,cm*Cout], bf16 or fp32 per out_f32) and the addend, if any, is read at the same stride from
     `addend_off` -- one output phase of a transposed convolution (iiseg_conv_desc.out_stride).  Returns dest.
+
+    weight_npack: the same 16-row 3x3 filter re-packed by _packing.pack_npack16; the library then runs the N-packed kernel
+    where it applies (iiseg_conv_desc.weight_npack).
 
     post_affine = (scale, shift): fp32 [Cout] vectors applied after the rectifier, before pool / store (a folded
     deterministic BatchNormLayer, iiseg_conv_desc.post_scale).
@@ -200,6 +203,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
                       AH=addend.shape[1] if addend is not None else 0, AW=addend.shape[2] if addend is not None else 0,
                       ah0=addend_off[0], aw0=addend_off[1], addend_f32=int(addend_f32), addend_cs=addend_cs,
                       relu=int(bool(relu)), split=int(bool(split and not out_f32)), out_f32=int(bool(out_f32)))
+    if weight_npack is not None:
+        _chk(weight_npack, BF16, 'weight_npack')
+        assert tuple(weight_npack.shape) == (39 * 16, 64) and Cout == 16 and R == 3 and S == 3
+        d.weight_npack = weight_npack.data_ptr()
     if post_affine is not None:
         _chk(post_affine[0], F32, 'post_affine.scale')
         _chk(post_affine[1], F32, 'post_affine.shift')

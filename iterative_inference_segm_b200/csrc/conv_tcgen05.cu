@@ -1865,6 +1865,304 @@ static int launch_conv_halo_depool(const ConvParams& p, int smem_bytes, cudaStre
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// N-packed 3x3 conv for a 16-channel output (the DAE's logits conv up_conv1: 64 -> 11(16) channels at full resolution).
+//
+// With N = 16 an M128 x K16 MMA still fetches its whole A operand (128 rows x 32 B) from shared memory and takes ~46 cycles
+// where 8 would be tensor-bound, so the plain halo-tile kernel spends 36 such instructions per 128 output pixels.  Here FOUR
+// horizontally adjacent output pixels share one accumulator row: row m = (line i, column group g) holds pixels
+// (i, 4g + j), j = 0..3, in columns 16j .. 16j+15.  For filter row r and input-column phase c = j + s (0..5) the A operand
+// is the pixels x[i + r - 1][4g + c - 1]: one TMA box per phase with element stride 4 along W (every fourth pixel arrives
+// as consecutive 128-byte swizzled rows; tools/experiments/tma_stride_test.cu) covering TH + 2 lines, so the filter row is
+// again a descriptor advanced by r*G rows.  Phase c feeds the output pixels j with 0 <= c - j <= 2, i.e. a contiguous
+// range of 1..3 column groups: the instruction for (r, c) has N = 16 * (number of such j), writes the accumulator at
+// column 16 * jlo(c), and its B operand is the 16-row blocks W[.][r][c - j][.] stacked over j -- no zero blocks except in
+// the very first instruction of a tile (r = 0, c = 0), which is N = 64 with zero rows for j >= 1 so that it initialises all
+// 64 columns (accumulate = 0).  18 x 4 instructions per 512 output pixels instead of 4 x 36.
+// Bank (host-packed, resident): 39 blocks of 16 rows x 64 channels = 78 KB.  A blocks stream through the halo kernel's ring
+// protocol (two issuer warps, two sub-rings).  Epilogue: two groups of four warps; a thread owns an accumulator row = four
+// pixels, and either stores fp32 logits (4 x 64 contiguous bytes) or runs the fused softmax tail + update on them
+// (conv_epilogue16_update's arithmetic, operation for operation: same bits), reading / writing the fp32 NCHW master y as one
+// float4 per class.
+// ---------------------------------------------------------------------------
+constexpr int kNpThreads = 384;            // 4 pipeline warps + 8 epilogue warps (two groups)
+constexpr int kNpUnits = 39;               // 16-row filter blocks in the bank
+constexpr int kNpBankBytes = kNpUnits * 16 * 128;
+
+__device__ __forceinline__ int np_jlo(int c) { return c <= 2 ? 0 : c - 2; }
+__device__ __forceinline__ int np_jn(int c) { return c <= 2 ? c + 1 : 6 - c; }            // output pixels fed by phase c: 1 2 3 3 2 1
+// first 16-row unit of block (r, c): per filter row 12 units (1 + 2 + 3 + 3 + 2 + 1), plus 3 zero units behind (0, 0)
+__device__ __forceinline__ int np_unit(int r, int c) {
+  const int within = c <= 3 ? (c * (c + 1)) / 2 : (c == 4 ? 9 : 11);          // 0 1 3 6 9 11
+  return r * 12 + within + ((r > 0 || c > 0) ? 3 : 0);
+}
+
+template <bool kUpdate>
+__device__ __forceinline__ void npack_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
+                                               uint32_t tmem_empty_bar0, int warp, int lane) {
+  const int q = warp & 3;
+  const int grp = (warp - 4) >> 2;                 // 0..1
+  const int macc = q * 32 + lane;
+  const int G = p.pitch;
+  const int il = macc / G, gl = macc - il * G;
+  const bool in_box = il < p.TH;
+  const int C = p.upd_C;
+  const size_t HW = static_cast<size_t>(p.OH) * p.OW;
+  const float upd_step = (kUpdate && p.upd_step_dev != nullptr) ? __ldg(p.upd_step_dev) : p.upd_step;
+  unsigned long long fx_acc = 0ull;
+  int n_acc = -1;
+  auto flush = [&]() {
+    unsigned long long fx = fx_acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    if (lane == 0 && fx != 0ull) atomicAdd(p.upd_norm_acc + n_acc, fx);
+    fx_acc = 0ull;
+  };
+  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+    const int as = iter & 3;
+    const uint32_t aphase = static_cast<uint32_t>(iter >> 2) & 1u;
+    const int oh = tc.th * p.TH + il, ow0 = tc.tw * p.TW + 4 * gl;          // first of this row's four pixels
+    const bool row_ok = in_box && oh < p.OH && ow0 < p.OW;
+    const int npx = row_ok ? (p.OW - ow0 < 4 ? p.OW - ow0 : 4) : 0;          // pixels of the row inside the output
+    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * 64) + (static_cast<uint32_t>(q * 32) << 16);
+    float yv[16][4];
+    bool go = false;
+    float* yb = nullptr;
+    if constexpr (kUpdate) {
+      if (tc.n != n_acc) { if (n_acc >= 0) flush(); n_acc = tc.n; }          // warp-uniform
+      const bool act = p.upd_active == nullptr || __ldg(p.upd_active + tc.n) != 0;
+      go = npx > 0 && act;
+      yb = p.upd_y + static_cast<size_t>(tc.n) * C * HW + static_cast<size_t>(oh) * p.OW + ow0;
+      if (go) {            // requested before the accumulator wait: the loads overlap the tile's MMAs
+        if (npx == 4 && (p.OW & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) if (c < C) {
+            const float4 t = *reinterpret_cast<const float4*>(yb + static_cast<size_t>(c) * HW);
+            yv[c][0] = t.x; yv[c][1] = t.y; yv[c][2] = t.z; yv[c][3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yv[c][j] = j < npx ? yb[static_cast<size_t>(c) * HW + j] : 0.f;
+          }
+        }
+      }
+    }
+    mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v[16];
+      tmem_ld_x16(taddr + 16 * j, v);
+      tmem_ld_wait();
+      if (j == 3) {                     // all TMEM reads of this accumulator are done
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty_bar0 + 8u * as);
+      }
+      float l[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + j4);
+        l[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; l[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
+        l[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; l[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+      }
+      if constexpr (!kUpdate) {
+        if (j < npx) {
+          float* o = reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow0 + j) * p.out_cs;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            stg_v4(o + 4 * j4, make_uint4(__float_as_uint(l[4 * j4]), __float_as_uint(l[4 * j4 + 1]), __float_as_uint(l[4 * j4 + 2]), __float_as_uint(l[4 * j4 + 3])));
+        }
+      } else {
+        float nrm = 0.f;
+        if (go && j < npx) {
+          float mx = l[0];
+#pragma unroll
+          for (int c = 1; c < 16; ++c) if (c < C) mx = fmaxf(mx, l[c]);
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { l[c] = c < C ? softmax_exp(l[c] - mx) : 0.f; sum += l[c]; }
+          const float inv = 1.0f / sum;
+          float ss = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c < C) {
+              const float g = __fsub_rn(yv[c][j], __fmul_rn(l[c], inv));      // explicit roundings: same bits as update.cu
+              ss = __fmaf_rn(g, g, ss);
+              l[c] = fminf(fmaxf(__fsub_rn(yv[c][j], __fmul_rn(upd_step, g)), 0.f), 1.f);
+              yv[c][j] = l[c];
+            } else l[c] = 0.f;
+          }
+          nrm = sqrtf(ss);
+          uint32_t hw[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hw[k] = pack_bf16x2(l[2 * k], l[2 * k + 1]);
+          const size_t pixoff = static_cast<size_t>(tc.n) * HW + static_cast<size_t>(oh) * p.OW + ow0 + j;
+          if (!p.upd_split) {
+            uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pixoff * p.upd_cpad);
+            stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+            for (int k = 2; k < p.upd_cpad / 8; ++k) stg_v4(o + k, make_uint4(0, 0, 0, 0));
+          } else {
+            uint32_t lw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) lw[k] = pack_bf16x2(l[2 * k] - bf16_lo(hw[k]), l[2 * k + 1] - bf16_hi(hw[k]));
+            uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pixoff * (2 * p.upd_cpad));
+            const int half = p.upd_cpad / 8;
+            stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+            stg_v4(o + half, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+            stg_v4(o + half + 1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+            for (int k = 2; k < half; ++k) { stg_v4(o + k, make_uint4(0, 0, 0, 0)); stg_v4(o + half + k, make_uint4(0, 0, 0, 0)); }
+          }
+        }
+        const float scaled = nrm * 1048576.0f;       // 2^-40 fixed point, as conv_epilogue16_update
+        const float ip = floorf(scaled);
+        fx_acc += (static_cast<unsigned long long>(__float2uint_rz(ip)) << 20) + __float2uint_rz((scaled - ip) * 1048576.0f);
+      }
+    }
+    if constexpr (kUpdate) {
+      if (go) {
+        if (npx == 4 && (p.OW & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) if (c < C)
+            *reinterpret_cast<float4*>(yb + static_cast<size_t>(c) * HW) = make_float4(yv[c][0], yv[c][1], yv[c][2], yv[c][3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < npx) yb[static_cast<size_t>(c) * HW + j] = yv[c][j];
+          }
+        }
+      }
+    }
+  }
+  if constexpr (kUpdate) { if (n_acc >= 0) flush(); }
+}
+
+__global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) mbar_timeout(p.diag, 9, 0);
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_bank = a_ring + static_cast<uint32_t>(p.n_a * p.a_blk_bytes);
+  const uint32_t bars = b_bank + kNpBankBytes;
+  constexpr int kMaxA = 8;
+  auto a_full = [&](int i) { return bars + 8u * i; };
+  auto a_empty = [&](int i) { return bars + 8u * (kMaxA + i); };
+  auto tmem_full_bar = [&](int i) { return bars + 8u * (2 * kMaxA + i); };
+  auto tmem_empty_bar = [&](int i) { return bars + 8u * (2 * kMaxA + 4 + i); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kMaxA + 8);
+  const uint32_t b_res_bar = bars + 8u * (2 * kMaxA + 9);
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = p.pitch;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&p.tm_src[0]); prefetch_tmap(&p.tm_w); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(b_res_bar, 1);
+    for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const int n_half = p.n_a >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(b_res_bar, kNpBankBytes);
+      for (int u = 0; u < kNpUnits; ++u) tma_load_2d(b_bank + u * 2048, &p.tm_w, b_res_bar, 0, u * 16);
+      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * G) * 128u;
+      int iter = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
+        const TileCoord tc = decode_tile(p, t);
+        const int h_base = tc.th * p.TH + p.in_off_h, w_base = tc.tw * p.TW + p.in_off_w;
+        for (int c = 0; c < 6; ++c) {
+          const int lstep = (iter >> 1) * 6 + c;
+          const int slot = (iter & 1) * n_half + lstep % n_half;
+          const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
+          mbar_wait(a_empty(slot), phase ^ 1u, p.diag, 5, slot);
+          mbar_arrive_expect_tx(a_full(slot), a_bytes);
+          tma_load_4d(a_ring + slot * p.a_blk_bytes, &p.tm_src[0], a_full(slot), 0, w_base + c, h_base, tc.n);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (alternate tiles) =====================
+    const int w = warp == 1 ? 0 : 1;
+    constexpr uint64_t kDescHi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
+    mbar_wait(b_res_bar, 0, p.diag, 10, 0);
+    for (int iter = w; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
+      const int as = iter & 3;
+      const uint32_t aphase = static_cast<uint32_t>(iter >> 2) & 1u;
+      mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.diag, 2, as);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 64);
+      for (int c = 0; c < 6; ++c) {
+        const int lstep = (iter >> 1) * 6 + c;
+        const int slot = w * n_half + lstep % n_half;
+        const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
+        mbar_wait(a_full(slot), phase, p.diag, 7, slot);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t a0 = kDescHi | static_cast<uint64_t>(((a_ring + slot * p.a_blk_bytes) >> 4) & 0x3FFFu);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const bool first = (c == 0 && r == 0);
+            const int nj = first ? 4 : np_jn(c);
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>((16 * nj) >> 3) << 17);
+            const int unit = first ? 0 : np_unit(r, c);
+            const uint64_t b_desc = kDescHi | static_cast<uint64_t>(((b_bank + static_cast<uint32_t>(unit) * 2048u) >> 4) & 0x3FFFu);
+            const uint64_t a_desc = a0 + static_cast<uint32_t>(r * G) * 8u;         // 8 descriptor units (128 B) per row
+            const uint32_t d = d_tmem + static_cast<uint32_t>(first ? 0 : 16 * np_jlo(c));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d, a_desc + 2u * k, b_desc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(a_empty(slot));
+          if (c == 5) umma_commit(tmem_full_bar(as));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    if (p.upd_y != nullptr) npack_epilogue<true>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    else npack_epilogue<false>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// NHWC bf16 tensor as (C, W, H, N) with element stride 4 along W: box = 64 channels x G pixels (every fourth, spanning 4G) x
+// lines x 1 image; 128-byte swizzle; out-of-bounds reads give zeros (the conv's padding).
+static int encode_nhwc_stride4(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int Cs, int lines, int G) {
+  if (Cs == 0) Cs = C;
+  EncodeTiledFn fn = get_encode_fn();
+  IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(4 * G), (cuuint32_t)lines, 1};
+  cuuint32_t estr[4] = {1, 4, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc stride 4, W=%d G=%d lines=%d) failed: %d", W, G, lines, (int)r);
+  return 0;
+}
+
 template <int BN>
 static int launch_conv(const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
@@ -1970,6 +2268,53 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   if (d->addend != nullptr && d->out_stride <= 1)
     IISEG_CHECK(d->ah0 >= 0 && d->aw0 >= 0 && d->ah0 + d->OH <= d->AH && d->aw0 + d->OW <= d->AW,
                 "conv: addend window [%d+%d, %d+%d] outside %dx%d", d->ah0, d->OH, d->aw0, d->OW, d->AH, d->AW);
+
+  // ---- N-packed kernel for 16-channel 3x3 convs of one 64-channel source (up_conv1): see conv_npack_kernel ----
+  {
+    static const int env_npack = getenv("IISEG_CONV_NPACK") ? atoi(getenv("IISEG_CONV_NPACK")) : 1;
+    if (env_npack && d->weight_npack != nullptr && d->R == 3 && d->S == 3 && d->Cout == 16 && d->C[0] == 64 && d->src[1] == nullptr &&
+        !d->split && d->addend == nullptr && d->pooled == nullptr && d->depool_mask == nullptr && d->depool_out == nullptr &&
+        d->out_stride <= 1 && d->post_scale == nullptr && (d->out_f32 || d->upd_y != nullptr) && d->OW >= 32 && d->OH >= 2) {
+      ConvParams q;
+      memset(&q, 0, sizeof(q));
+      // G column groups (4G output columns) x TH lines per tile, TH * G <= 128 accumulator rows: fewest tiles, then the fullest
+      int bestG = 0, bestTH = 0; long best_tiles = -1; int best_rows = 0;
+      for (int G = 8; G <= 32; ++G) {
+        int TH = 128 / G;
+        if (TH > d->OH) TH = d->OH;
+        const long tiles = (long)ceil_div(d->OW, 4 * G) * ceil_div(d->OH, TH);
+        if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && TH * G > best_rows)) { best_tiles = tiles; bestG = G; bestTH = TH; best_rows = TH * G; }
+      }
+      q.TH = bestTH; q.TW = 4 * bestG; q.pitch = bestG;
+      const int rows_box = (q.TH + 2) * bestG, rows_read = 2 * bestG + kBlockM;
+      q.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * 128 + 1023) / 1024 * 1024;
+      q.n_a = (227 * 1024 - 512 - kNpBankBytes) / q.a_blk_bytes;
+      if (q.n_a > 8) q.n_a = 8;
+      q.n_a &= ~1;
+      if (q.n_a >= 2) {
+        if (encode_nhwc_stride4(&q.tm_src[0], d->src[0], d->N, d->H, d->W, 64, d->Cs[0], q.TH + 2, bestG)) return -1;
+        if (encode_weight(&q.tm_w, d->weight_npack, kNpUnits * 16, 64, 16, 64)) return -1;
+        q.bias = d->bias; q.out = d->out; q.diag = diag_device_ptr();
+        q.R = 3; q.S = 3; q.in_off_h = d->oh0 - d->pad; q.in_off_w = d->ow0 - d->pad;
+        q.tiles_h = ceil_div(d->OH, q.TH); q.tiles_w = ceil_div(d->OW, q.TW); q.n_ntiles = 1;
+        q.num_tiles = d->N * q.tiles_h * q.tiles_w;
+        IISEG_CHECK(q.num_tiles < (1 << 21), "conv: too many tiles (%d)", q.num_tiles);
+        q.inv_ntiles = 1.0f; q.inv_tiles_w = 1.0f / q.tiles_w; q.inv_tiles_h = 1.0f / q.tiles_h; q.inv_tw2 = 1.0f;
+        q.OH = d->OH; q.OW = d->OW; q.Cout = 16; q.out_cs = d->out_cs > 0 ? d->out_cs : 16; q.out_f32 = 1;
+        q.upd_y = d->upd_y; q.upd_y_bf16 = reinterpret_cast<__nv_bfloat16*>(d->upd_y_bf16); q.upd_active = d->upd_active;
+        q.upd_norm_acc = reinterpret_cast<unsigned long long*>(d->upd_norm_acc); q.upd_step = d->upd_step; q.upd_step_dev = d->upd_step_dev;
+        q.upd_C = d->upd_C; q.upd_cpad = d->upd_cpad; q.upd_split = d->upd_split;
+        { static const int env_dbg = getenv("IISEG_CONV_DBG") ? atoi(getenv("IISEG_CONV_DBG")) : 0; q.dbg = env_dbg; }
+        IISEG_SMEM_OPT_IN(conv_npack_kernel, 227 * 1024);
+        const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
+        const int smem = q.n_a * q.a_blk_bytes + kNpBankBytes + 512;
+        g_last_plan[0] = 3; g_last_plan[1] = 16; g_last_plan[2] = 64;
+        conv_npack_kernel<<<grid, kNpThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+        IISEG_LAUNCH_CHECK();
+        return 0;
+      }
+    }
+  }
 
   ConvParams p;
   memset(&p, 0, sizeof(p));

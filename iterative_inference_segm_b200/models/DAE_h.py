@@ -18,7 +18,7 @@ import os
 import torch
 
 from .. import _kernels as K
-from .._packing import pack_conv, load_npz_params
+from .._packing import pack_conv, pack_npack16, load_npz_params
 from .fcn8 import LayerHandle
 
 
@@ -141,6 +141,10 @@ class DAENet(object):
             else:
                 self.up.append(pack_conv(W, b, [(up_in, up_in)], cout_pad, self.device, split=self.split_up))
             up_in = n_cl
+        # up_conv1 (64 -> n_classes at full resolution, bf16 operands): the N-packed filter bank (iiseg_conv_desc.weight_npack)
+        self.up1_npack = None
+        if unpool_type != 'standard' and not self.split_up and self.filters[0] == 64:
+            self.up1_npack = pack_npack16(self.up[-1][0])
         # the softmax tail + update can run in the epilogue of the last conv when that conv is a bf16 3x3 conv
         self.fusable_update = unpool_type != 'standard' and not self.split_up
         self._ws = {}
@@ -334,10 +338,11 @@ class DAENet(object):
                 u_origin = (hl, wl)
             else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
                 if update is not None:
-                    K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True,
+                    K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True, weight_npack=self.up1_npack,
                              update=dict(update, y_bf16=y_bf16, C=self.n_classes, y_split=sp))
                     return None
-                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=spu)
+                K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, out=ws['logits'], out_f32=True, split=spu,
+                         weight_npack=self.up1_npack)
         return ws['logits']
 
 

@@ -371,3 +371,42 @@ def test_mixed_precision_plumbing(cuda):
         ref = K.conv2d(x, Wt[:cout].contiguous(), b[:cout].contiguous(), 3, 3, 1, relu=False,
                        addend=add_hi[..., :cout].contiguous(), addend_off=(2, 1))
         assert torch.equal(got, ref)
+
+
+NPACK_CASES = [
+    # N, H, W, window (oh0, ow0, OH, OW), pad
+    (2, 40, 132, None, 1),                      # whole map, OW multiple of 4
+    (1, 37, 45, None, 1),                       # odd sizes, OW % 4 != 0 (ragged last pixel group)
+    (3, 64, 200, (1, 1, 62, 198), 1),           # the crop window of up_conv1 (origin 1, 1)
+    (2, 50, 70, (5, 7, 24, 33), 1),             # odd window origin and extent
+    (1, 362, 482, (1, 1, 360, 480), 1),         # BASELINE size: 4 x 120-pixel tiles per line
+]
+
+
+@pytest.mark.parametrize('case', NPACK_CASES, ids=[str(c) for c in NPACK_CASES])
+def test_npack_logits_conv_matches_plain_kernel_and_reference(cuda, case):
+    """The N-packed kernel of the 16-channel logits conv (four adjacent output pixels per accumulator row, TMA boxes with
+    element stride 4): same result as the plain halo-tile kernel up to fp32 summation order, and as an fp32 convolution of
+    the same bf16-rounded operands."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200._packing import pack_conv, pack_npack16
+    N, H, W, window, pad = case
+    torch.manual_seed(5)
+    x = torch.randn(N, 64, H, W, device=cuda).to(torch.bfloat16)
+    Wt = (torch.randn(11, 64, 3, 3, device=cuda) / 24).to(torch.bfloat16).float()
+    b = torch.randn(11, device=cuda)
+    xs = x.permute(0, 2, 3, 1).contiguous()
+    Wk, bk = pack_conv(Wt, b, [(64, 64)], 16, cuda)
+    plain = K.conv2d(xs, Wk, bk, 3, 3, pad, relu=False, window=window, out_f32=True)
+    assert K.last_conv_plan()[0] == 2
+    packed = K.conv2d(xs, Wk, bk, 3, 3, pad, relu=False, window=window, out_f32=True, weight_npack=pack_npack16(Wk))
+    assert K.last_conv_plan() == (3, 16, 64), K.last_conv_plan()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float(), Wt, b, padding=pad)
+    if window:
+        oh0, ow0, OH, OW = window
+        ref = ref[:, :, oh0:oh0 + OH, ow0:ow0 + OW]
+    got = packed[..., :11].permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((packed - plain).abs().max()) < 2e-5 * max(1.0, float(plain.abs().max()))
+    assert float(packed[..., 11:].abs().max()) == 0.0

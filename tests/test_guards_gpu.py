@@ -66,13 +66,14 @@ def test_fused_update_and_streaming_kernels_stay_inside_their_tensors(cuda):
     torch.manual_seed(1)
     N, H, W, C = 2, 34, 50, 64
     x = K.pack_nchw(torch.randn(N, C, H, W, device=cuda), C)
+    from iterative_inference_segm_b200._packing import pack_npack16
     Wk, bk = pack_conv(torch.randn(11, C, 3, 3, device=cuda) / 24, torch.randn(11, device=cuda), [(C, C)], 16, cuda)
     win = (1, 1, H - 2, W - 2)
-    for ysp in (False, True):
+    for ysp, npk in ((False, None), (True, None), (False, pack_npack16(Wk)), (True, pack_npack16(Wk))):
         fy, y = _guarded((N, 11, H - 2, W - 2), torch.float32, cuda, 0.25)
         fb, yb = _guarded((N, H - 2, W - 2, 32 if ysp else 16), torch.bfloat16, cuda, 7.0)
         acc = torch.zeros(N, dtype=torch.int64, device=cuda)
-        K.conv2d(x, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True,
+        K.conv2d(x, Wk, bk, 3, 3, 1, relu=False, window=win, out_f32=True, weight_npack=npk,
                  update=dict(y=y, y_bf16=yb, active=torch.ones(N, dtype=torch.int32, device=cuda), norm_acc=acc, step=0.05, C=11, y_split=ysp))
         torch.cuda.synchronize()
         assert _intact(fy, 0.25) and _intact(fb, 7.0) and bool((yb != 7.0).all()) and bool((acc > 0).all())
