@@ -116,10 +116,10 @@ typedef struct iiseg_conv_desc {
   int depool_out_H2, depool_out_W2, depool_out_ph0, depool_out_pw0;
   const void* weight; /* bf16 [Cout][R*S][sum C] (K-major GEMM B operand)   */
   /* Optional (3x3, Cout = 16, one 64-channel source, fp32 or fused-update output: the DAE's logits conv): the same filter
-   * re-packed for the N-packed kernel, bf16 [39*16][64] -- for filter row r and input-column phase c = j + s (0..5) the
-   * 16-row blocks W[.][r][c - j][.] of the output pixels j = max(0, c-2) .. min(3, c) one after the other, in (r, c) order,
-   * with three zero blocks behind block (0, 0).  Four adjacent output pixels then share one accumulator row (N = 16..48 per
-   * instruction instead of 16).  NULL: the plain kernels run. */
+   * re-packed for the N-packed kernel, bf16 [39*16][64] -- for filter column s and input-line phase c = j + r (0..5) the
+   * 16-row blocks W[.][c - j][s][.] of the output pixels j = max(0, c-2) .. min(3, c) one after the other, in (s, c) order,
+   * with three zero blocks behind block (0, 0).  Four vertically adjacent output pixels then share one accumulator row
+   * (N = 16..48 per instruction instead of 16).  NULL: the plain kernels run. */
   const void* weight_npack;
   const float* bias;  /* fp32 [Cout]                                        */
   /* Optional per-channel affine applied AFTER the rectifier and before the pool / store: x * post_scale[c] + post_shift[c]

@@ -47,18 +47,18 @@ def pack_conv(W, b, splits, cout_pad, device, split=False):
 
 def pack_npack16(Wk):
     """Re-pack a 16-row 3x3 filter bank of one 64-channel source, bf16 [16, 9*64] (pack_conv's layout: tap-major, then
-    channel), for the N-packed kernel (iiseg_conv_desc.weight_npack): for filter row r and input-column phase c = j + s
-    (0..5), the 16-row blocks W[.][r][c - j][.] of the output pixels j = max(0, c-2) .. min(3, c) one after the other, in
-    (r, c) order; three zero blocks follow block (0, 0) (that instruction initialises all four pixel groups).
+    channel), for the N-packed kernel (iiseg_conv_desc.weight_npack): for filter column s and input-line phase c = j + r
+    (0..5), the 16-row blocks W[.][c - j][s][.] of the output pixels j = max(0, c-2) .. min(3, c) one after the other, in
+    (s, c) order; three zero blocks follow block (0, 0) (that instruction initialises all four pixel groups).
     Returns bf16 [39*16, 64]."""
     assert Wk.dtype == torch.bfloat16 and tuple(Wk.shape) == (16, 9 * 64), tuple(Wk.shape)
     W = Wk.view(16, 3, 3, 64)
     blocks = []
-    for r in range(3):
+    for s_ in range(3):
         for c in range(6):
             for j in range(max(0, c - 2), min(3, c) + 1):
-                blocks.append(W[:, r, c - j, :])
-            if r == 0 and c == 0:
+                blocks.append(W[:, c - j, s_, :])
+            if s_ == 0 and c == 0:
                 blocks += [torch.zeros_like(W[:, 0, 0, :])] * 3
     out = torch.cat(blocks, dim=0).contiguous()
     assert tuple(out.shape) == (39 * 16, 64)

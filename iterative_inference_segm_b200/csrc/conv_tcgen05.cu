@@ -1870,45 +1870,58 @@ static int launch_conv_halo_depool(const ConvParams& p, int smem_bytes, cudaStre
 //
 // With N = 16 an M128 x K16 MMA still fetches its whole A operand (128 rows x 32 B) from shared memory and takes ~46 cycles
 // where 8 would be tensor-bound, so the plain halo-tile kernel spends 36 such instructions per 128 output pixels.  Here FOUR
-// horizontally adjacent output pixels share one accumulator row: row m = (line i, column group g) holds pixels
-// (i, 4g + j), j = 0..3, in columns 16j .. 16j+15.  For filter row r and input-column phase c = j + s (0..5) the A operand
-// is the pixels x[i + r - 1][4g + c - 1]: one TMA box per phase with element stride 4 along W (every fourth pixel arrives
-// as consecutive 128-byte swizzled rows; tools/experiments/tma_stride_test.cu) covering TH + 2 lines, so the filter row is
-// again a descriptor advanced by r*G rows.  Phase c feeds the output pixels j with 0 <= c - j <= 2, i.e. a contiguous
-// range of 1..3 column groups: the instruction for (r, c) has N = 16 * (number of such j), writes the accumulator at
-// column 16 * jlo(c), and its B operand is the 16-row blocks W[.][r][c - j][.] stacked over j -- no zero blocks except in
-// the very first instruction of a tile (r = 0, c = 0), which is N = 64 with zero rows for j >= 1 so that it initialises all
-// 64 columns (accumulate = 0).  18 x 4 instructions per 512 output pixels instead of 4 x 36.
+// vertically adjacent output pixels share one accumulator row: row m = (line group lg, column w) holds the pixels
+// (4 lg + j, w), j = 0..3, in columns 16j .. 16j+15.  For filter column s and input-line phase c = j + r (0..5) the A
+// operand is the pixels x[4 lg + c - 1][w + s - 1]: one TMA box per phase with element stride 4 along H (every fourth line;
+// the W-axis variant of the same trick is tools/experiments/tma_stride_test.cu) covering TW + 2 columns, so the filter column
+// is a descriptor advanced by s rows.  Phase c feeds the output pixels j with 0 <= c - j <= 2, i.e. a contiguous range of
+// 1..3 column groups: the instruction for (s, c) has N = 16 * (number of such j), writes the accumulator at column
+// 16 * jlo(c), and its B operand is the 16-row blocks W[.][c - j][s][.] stacked over j -- no zero blocks except in the very
+// first instruction of a tile (s = 0, c = 0), which is N = 64 with zero rows for j >= 1 so that it initialises all 64
+// columns (accumulate = 0).  18 x 4 instructions per 4 x TW output pixels instead of 4 x 36 per 4 x 128.  Packing lines
+// (not columns) keeps accumulator rows = consecutive pixels of a line, so the epilogue's accesses to the fp32 NCHW master y
+// stay coalesced (a first version packed four adjacent COLUMNS: its stride-4 lanes made the epilogue's loads / stores the
+// bound, 105 us against 114 for the plain kernel).
 // Bank (host-packed, resident): 39 blocks of 16 rows x 64 channels = 78 KB.  A blocks stream through the halo kernel's ring
-// protocol (two issuer warps, two sub-rings).  Epilogue: two groups of four warps; a thread owns an accumulator row = four
-// pixels, and either stores fp32 logits (4 x 64 contiguous bytes) or runs the fused softmax tail + update on them
-// (conv_epilogue16_update's arithmetic, operation for operation: same bits), reading / writing the fp32 NCHW master y as one
-// float4 per class.
+// protocol (two issuer warps, two sub-rings).  Epilogue: four groups of four warps, group j owning pixel j of every row
+// (columns 16j..16j+15) of every tile; a thread either stores its pixel's fp32 logits or runs the fused softmax tail +
+// update on them (conv_epilogue16_update's arithmetic, operation for operation: same bits).
 // ---------------------------------------------------------------------------
-constexpr int kNpThreads = 384;            // 4 pipeline warps + 8 epilogue warps (two groups)
+constexpr int kNpThreads = 640;            // 4 pipeline warps + 16 epilogue warps (four groups: one per pixel of an accumulator row)
 constexpr int kNpUnits = 39;               // 16-row filter blocks in the bank
 constexpr int kNpBankBytes = kNpUnits * 16 * 128;
 
 __device__ __forceinline__ int np_jlo(int c) { return c <= 2 ? 0 : c - 2; }
 __device__ __forceinline__ int np_jn(int c) { return c <= 2 ? c + 1 : 6 - c; }            // output pixels fed by phase c: 1 2 3 3 2 1
-// first 16-row unit of block (r, c): per filter row 12 units (1 + 2 + 3 + 3 + 2 + 1), plus 3 zero units behind (0, 0)
+// first 16-row unit of block (s, c): per filter column 12 units (1 + 2 + 3 + 3 + 2 + 1), plus 3 zero units behind (0, 0)
 __device__ __forceinline__ int np_unit(int r, int c) {
   const int within = c <= 3 ? (c * (c + 1)) / 2 : (c == 4 ? 9 : 11);          // 0 1 3 6 9 11
   return r * 12 + within + ((r > 0 || c > 0) ? 3 : 0);
 }
 
-template <bool kUpdate>
+// kC > 0: the class count is a compile-time constant (11, CamVid): the softmax / update loops then carry no padded classes
+// (the epilogue is bound by its instruction count: ~65 us of the launch remain with every load, store and MMA removed).
+template <bool kUpdate, int kC>
 __device__ __forceinline__ void npack_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t tmem_full_bar0,
                                                uint32_t tmem_empty_bar0, int warp, int lane) {
+  // 16 epilogue warps = four groups of four (one warp per TMEM lane quadrant).  Group j drains columns 16j .. 16j+15 -- pixel j
+  // of every accumulator row -- of EVERY tile, so a thread owns one pixel per tile (short dependency chain) and the four
+  // groups work on one tile concurrently; each of the 512 threads arrives on the stage's tmem_empty barrier.
   const int q = warp & 3;
-  const int grp = (warp - 4) >> 2;                 // 0..1
+  const int j = (warp - 4) >> 2;                   // 0..3: which of the row's four pixels
   const int macc = q * 32 + lane;
-  const int G = p.pitch;
-  const int il = macc / G, gl = macc - il * G;
-  const bool in_box = il < p.TH;
-  const int C = p.upd_C;
+  const int lg = macc / p.pitch, wl = macc - lg * p.pitch;         // line group, column inside the tile
+  const bool in_box = (4 * lg < p.TH) && (wl < p.TW);
+  const int C = kC > 0 ? kC : p.upd_C;
+  constexpr int kCmax = kC > 0 ? kC : 16;
   const size_t HW = static_cast<size_t>(p.OH) * p.OW;
   const float upd_step = (kUpdate && p.upd_step_dev != nullptr) ? __ldg(p.upd_step_dev) : p.upd_step;
+  float bias[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + j4);
+    bias[4 * j4] = b.x; bias[4 * j4 + 1] = b.y; bias[4 * j4 + 2] = b.z; bias[4 * j4 + 3] = b.w;
+  }
   unsigned long long fx_acc = 0ull;
   int n_acc = -1;
   auto flush = [&]() {
@@ -1918,125 +1931,109 @@ __device__ __forceinline__ void npack_epilogue(const ConvParams& p, uint32_t tme
     if (lane == 0 && fx != 0ull) atomicAdd(p.upd_norm_acc + n_acc, fx);
     fx_acc = 0ull;
   };
-  for (int iter = grp; blockIdx.x + iter * gridDim.x < p.num_tiles; iter += 2) {
-    const TileCoord tc = decode_tile(p, blockIdx.x + iter * gridDim.x);
+  struct PixelRef { float* yb; bool go; bool valid; int n; size_t pixoff; };
+  auto locate = [&](int it) {
+    PixelRef r;
+    const TileCoord tc = decode_tile(p, blockIdx.x + it * gridDim.x);
+    const int oh = tc.th * p.TH + 4 * lg + j, ow = tc.tw * p.TW + wl;
+    r.valid = in_box && (oh < p.OH) && (ow < p.OW);
+    const bool act = !kUpdate || p.upd_active == nullptr || __ldg(p.upd_active + tc.n) != 0;    // frozen images are untouched
+    r.n = tc.n;
+    r.go = r.valid && act;
+    r.pixoff = static_cast<size_t>(oh) * p.OW + ow;
+    r.yb = kUpdate ? p.upd_y + static_cast<size_t>(tc.n) * C * HW + r.pixoff : nullptr;
+    return r;
+  };
+  float yn[16];
+  PixelRef nxt;
+  nxt.go = false; nxt.valid = false; nxt.yb = nullptr; nxt.n = 0; nxt.pixoff = 0;
+  if (blockIdx.x < p.num_tiles) {
+    nxt = locate(0);
+    if (kUpdate && nxt.go && !(p.dbg & 64)) {
+#pragma unroll
+      for (int c = 0; c < kCmax; ++c) if (c < C) yn[c] = nxt.yb[static_cast<size_t>(c) * HW];
+    }
+  }
+  for (int iter = 0; blockIdx.x + iter * gridDim.x < p.num_tiles; ++iter) {
+    const PixelRef cur = nxt;
+    if (kUpdate && cur.n != n_acc) { if (n_acc >= 0) flush(); n_acc = cur.n; }     // warp-uniform
     const int as = iter & 3;
     const uint32_t aphase = static_cast<uint32_t>(iter >> 2) & 1u;
-    const int oh = tc.th * p.TH + il, ow0 = tc.tw * p.TW + 4 * gl;          // first of this row's four pixels
-    const bool row_ok = in_box && oh < p.OH && ow0 < p.OW;
-    const int npx = row_ok ? (p.OW - ow0 < 4 ? p.OW - ow0 : 4) : 0;          // pixels of the row inside the output
-    const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * 64) + (static_cast<uint32_t>(q * 32) << 16);
-    float yv[16][4];
-    bool go = false;
-    float* yb = nullptr;
-    if constexpr (kUpdate) {
-      if (tc.n != n_acc) { if (n_acc >= 0) flush(); n_acc = tc.n; }          // warp-uniform
-      const bool act = p.upd_active == nullptr || __ldg(p.upd_active + tc.n) != 0;
-      go = npx > 0 && act;
-      yb = p.upd_y + static_cast<size_t>(tc.n) * C * HW + static_cast<size_t>(oh) * p.OW + ow0;
-      if (go) {            // requested before the accumulator wait: the loads overlap the tile's MMAs
-        if (npx == 4 && (p.OW & 3) == 0) {
+    float yv[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) if (c < C) {
-            const float4 t = *reinterpret_cast<const float4*>(yb + static_cast<size_t>(c) * HW);
-            yv[c][0] = t.x; yv[c][1] = t.y; yv[c][2] = t.z; yv[c][3] = t.w;
-          }
-        } else {
+    for (int c = 0; c < 16; ++c) yv[c] = yn[c];
+    if (blockIdx.x + (iter + 1) * gridDim.x < p.num_tiles) {        // request the next tile's y before waiting
+      nxt = locate(iter + 1);
+      if (kUpdate && nxt.go && !(p.dbg & 64)) {          // (tuning bit 6: no y loads)
 #pragma unroll
-          for (int c = 0; c < 16; ++c) if (c < C) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) yv[c][j] = j < npx ? yb[static_cast<size_t>(c) * HW + j] : 0.f;
-          }
-        }
+        for (int c = 0; c < kCmax; ++c) if (c < C) yn[c] = nxt.yb[static_cast<size_t>(c) * HW];
       }
     }
     mbar_wait(tmem_full_bar0 + 8u * as, aphase, p.diag, 4, as, (p.dbg & 1024) == 0);
     tcgen05_fence_after();
+    uint32_t v[16];
+    tmem_ld_x16(tmem_base + static_cast<uint32_t>(as * 64 + 16 * j) + (static_cast<uint32_t>(q * 32) << 16), v);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    mbar_arrive(tmem_empty_bar0 + 8u * as);
+    float l[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t v[16];
-      tmem_ld_x16(taddr + 16 * j, v);
-      tmem_ld_wait();
-      if (j == 3) {                     // all TMEM reads of this accumulator are done
-        tcgen05_fence_before();
-        mbar_arrive(tmem_empty_bar0 + 8u * as);
+    for (int c = 0; c < 16; ++c) l[c] = __uint_as_float(v[c]) + bias[c];
+    if constexpr (!kUpdate) {
+      if (cur.valid) {
+        float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(cur.n) * HW + cur.pixoff) * p.out_cs;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          stg_v4(o + 4 * j4, make_uint4(__float_as_uint(l[4 * j4]), __float_as_uint(l[4 * j4 + 1]), __float_as_uint(l[4 * j4 + 2]), __float_as_uint(l[4 * j4 + 3])));
       }
-      float l[16];
+    } else {
+      float nrm = 0.f;
+      if (cur.go) {
+        float pr[16];
+        float mx = l[0];
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias) + j4);
-        l[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; l[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-        l[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; l[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
-      }
-      if constexpr (!kUpdate) {
-        if (j < npx) {
-          float* o = reinterpret_cast<float*>(p.out) + ((static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow0 + j) * p.out_cs;
+        for (int c = 1; c < kCmax; ++c) if (c < C) mx = fmaxf(mx, l[c]);
+        float sum = 0.f;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            stg_v4(o + 4 * j4, make_uint4(__float_as_uint(l[4 * j4]), __float_as_uint(l[4 * j4 + 1]), __float_as_uint(l[4 * j4 + 2]), __float_as_uint(l[4 * j4 + 3])));
+        for (int c = 0; c < 16; ++c) { pr[c] = (c < kCmax && c < C) ? softmax_exp(l[c] - mx) : 0.f; if (c < kCmax) sum += pr[c]; }
+        const float inv = 1.0f / sum;
+        float ss = 0.f, outv[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c < kCmax && c < C) {
+            const float g = __fsub_rn(yv[c], __fmul_rn(pr[c], inv));      // explicit roundings: same bits as update.cu
+            ss = __fmaf_rn(g, g, ss);
+            outv[c] = fminf(fmaxf(__fsub_rn(yv[c], __fmul_rn(upd_step, g)), 0.f), 1.f);
+            if (!(p.dbg & 128)) cur.yb[static_cast<size_t>(c) * HW] = outv[c];        // (tuning bit 7: no y stores)
+          } else outv[c] = 0.f;
         }
-      } else {
-        float nrm = 0.f;
-        if (go && j < npx) {
-          float mx = l[0];
+        nrm = sqrtf(ss);
+        uint32_t hw[8];
 #pragma unroll
-          for (int c = 1; c < 16; ++c) if (c < C) mx = fmaxf(mx, l[c]);
-          float sum = 0.f;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) { l[c] = c < C ? softmax_exp(l[c] - mx) : 0.f; sum += l[c]; }
-          const float inv = 1.0f / sum;
-          float ss = 0.f;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            if (c < C) {
-              const float g = __fsub_rn(yv[c][j], __fmul_rn(l[c], inv));      // explicit roundings: same bits as update.cu
-              ss = __fmaf_rn(g, g, ss);
-              l[c] = fminf(fmaxf(__fsub_rn(yv[c][j], __fmul_rn(upd_step, g)), 0.f), 1.f);
-              yv[c][j] = l[c];
-            } else l[c] = 0.f;
-          }
-          nrm = sqrtf(ss);
-          uint32_t hw[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) hw[k] = pack_bf16x2(l[2 * k], l[2 * k + 1]);
-          const size_t pixoff = static_cast<size_t>(tc.n) * HW + static_cast<size_t>(oh) * p.OW + ow0 + j;
-          if (!p.upd_split) {
-            uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pixoff * p.upd_cpad);
-            stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-            stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
-            for (int k = 2; k < p.upd_cpad / 8; ++k) stg_v4(o + k, make_uint4(0, 0, 0, 0));
-          } else {
-            uint32_t lw[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) lw[k] = pack_bf16x2(l[2 * k] - bf16_lo(hw[k]), l[2 * k + 1] - bf16_hi(hw[k]));
-            uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pixoff * (2 * p.upd_cpad));
-            const int half = p.upd_cpad / 8;
-            stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-            stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
-            stg_v4(o + half, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-            stg_v4(o + half + 1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
-            for (int k = 2; k < half; ++k) { stg_v4(o + k, make_uint4(0, 0, 0, 0)); stg_v4(o + half + k, make_uint4(0, 0, 0, 0)); }
-          }
-        }
-        const float scaled = nrm * 1048576.0f;       // 2^-40 fixed point, as conv_epilogue16_update
-        const float ip = floorf(scaled);
-        fx_acc += (static_cast<unsigned long long>(__float2uint_rz(ip)) << 20) + __float2uint_rz((scaled - ip) * 1048576.0f);
-      }
-    }
-    if constexpr (kUpdate) {
-      if (go) {
-        if (npx == 4 && (p.OW & 3) == 0) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) if (c < C)
-            *reinterpret_cast<float4*>(yb + static_cast<size_t>(c) * HW) = make_float4(yv[c][0], yv[c][1], yv[c][2], yv[c][3]);
+        for (int k = 0; k < 8; ++k) hw[k] = pack_bf16x2(outv[2 * k], outv[2 * k + 1]);
+        const size_t pix = static_cast<size_t>(cur.n) * HW + cur.pixoff;
+        if (p.dbg & 16) {                 // (tuning bit 4: no bf16 stores)
+        } else if (!p.upd_split) {
+          uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pix * p.upd_cpad);
+          stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+          for (int k = 2; k < p.upd_cpad / 8; ++k) stg_v4(o + k, make_uint4(0, 0, 0, 0));
         } else {
+          uint32_t lw[8];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) if (c < C) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < npx) yb[static_cast<size_t>(c) * HW + j] = yv[c][j];
-          }
+          for (int k = 0; k < 8; ++k) lw[k] = pack_bf16x2(outv[2 * k] - bf16_lo(hw[k]), outv[2 * k + 1] - bf16_hi(hw[k]));
+          uint4* o = reinterpret_cast<uint4*>(p.upd_y_bf16 + pix * (2 * p.upd_cpad));
+          const int half = p.upd_cpad / 8;
+          stg_v4(o, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          stg_v4(o + 1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+          stg_v4(o + half, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          stg_v4(o + half + 1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+          for (int k = 2; k < half; ++k) { stg_v4(o + k, make_uint4(0, 0, 0, 0)); stg_v4(o + half + k, make_uint4(0, 0, 0, 0)); }
         }
       }
+      const float scaled = nrm * 1048576.0f;       // 2^-40 fixed point, as conv_epilogue16_update
+      const float ip = floorf(scaled);
+      fx_acc += (static_cast<unsigned long long>(__float2uint_rz(ip)) << 20) + __float2uint_rz((scaled - ip) * 1048576.0f);
     }
   }
   if constexpr (kUpdate) { if (n_acc >= 0) flush(); }
@@ -2059,12 +2056,11 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
   uint8_t* smem_gen = smem_raw;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int G = p.pitch;
   if (warp == 0 && lane == 0) { prefetch_tmap(&p.tm_src[0]); prefetch_tmap(&p.tm_w); }
   if (warp == 1 && lane == 0) {
     mbar_init(b_res_bar, 1);
     for (int i = 0; i < p.n_a; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tmem_full_bar(i), 1); mbar_init(tmem_empty_bar(i), 512); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -2082,7 +2078,7 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(b_res_bar, kNpBankBytes);
       for (int u = 0; u < kNpUnits; ++u) tma_load_2d(b_bank + u * 2048, &p.tm_w, b_res_bar, 0, u * 16);
-      const uint32_t a_bytes = static_cast<uint32_t>((p.TH + 2) * G) * 128u;
+      const uint32_t a_bytes = static_cast<uint32_t>((p.TH >> 2) * p.pitch) * 128u;          // TH / 4 lines of pitch pixels
       int iter = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++iter) {
         const TileCoord tc = decode_tile(p, t);
@@ -2092,8 +2088,9 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
           const int slot = (iter & 1) * n_half + lstep % n_half;
           const uint32_t phase = static_cast<uint32_t>(lstep / n_half) & 1u;
           mbar_wait(a_empty(slot), phase ^ 1u, p.diag, 5, slot);
+          if (p.dbg & 1) { mbar_arrive(a_full(slot)); continue; }          // tuning: no activation loads
           mbar_arrive_expect_tx(a_full(slot), a_bytes);
-          tma_load_4d(a_ring + slot * p.a_blk_bytes, &p.tm_src[0], a_full(slot), 0, w_base + c, h_base, tc.n);
+          tma_load_4d(a_ring + slot * p.a_blk_bytes, &p.tm_src[0], a_full(slot), 0, w_base, h_base + c, tc.n);
         }
       }
     }
@@ -2123,8 +2120,9 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
             const uint32_t idesc = idesc0 | (static_cast<uint32_t>((16 * nj) >> 3) << 17);
             const int unit = first ? 0 : np_unit(r, c);
             const uint64_t b_desc = kDescHi | static_cast<uint64_t>(((b_bank + static_cast<uint32_t>(unit) * 2048u) >> 4) & 0x3FFFu);
-            const uint64_t a_desc = a0 + static_cast<uint32_t>(r * G) * 8u;         // 8 descriptor units (128 B) per row
+            const uint64_t a_desc = a0 + static_cast<uint32_t>(r) * 8u;             // filter column r: r rows further (8 descriptor units = 128 B per row)
             const uint32_t d = d_tmem + static_cast<uint32_t>(first ? 0 : 16 * np_jlo(c));
+            if (p.dbg & 2) continue;                                          // tuning: no MMAs
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(d, a_desc + 2u * k, b_desc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
           }
@@ -2135,8 +2133,10 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
       }
     }
   } else if (warp >= 4) {
-    if (p.upd_y != nullptr) npack_epilogue<true>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
-    else npack_epilogue<false>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    if (p.upd_y != nullptr) {
+      if (p.upd_C == 11) npack_epilogue<true, 11>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else npack_epilogue<true, 0>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else npack_epilogue<false, 0>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -2146,20 +2146,20 @@ __global__ void __launch_bounds__(kNpThreads, 1) conv_npack_kernel(const __grid_
   }
 }
 
-// NHWC bf16 tensor as (C, W, H, N) with element stride 4 along W: box = 64 channels x G pixels (every fourth, spanning 4G) x
-// lines x 1 image; 128-byte swizzle; out-of-bounds reads give zeros (the conv's padding).
-static int encode_nhwc_stride4(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int Cs, int lines, int G) {
+// NHWC bf16 tensor as (C, W, H, N) with element stride 4 along H: box = 64 channels x `cols` pixels x `lines` lines (every
+// fourth, spanning 4 * lines) x 1 image; 128-byte swizzle; out-of-bounds reads give zeros (the conv's padding).
+static int encode_nhwc_hstride4(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int Cs, int cols, int lines) {
   if (Cs == 0) Cs = C;
   EncodeTiledFn fn = get_encode_fn();
   IISEG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(4 * G), (cuuint32_t)lines, 1};
-  cuuint32_t estr[4] = {1, 4, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)cols, (cuuint32_t)(4 * lines), 1};
+  cuuint32_t estr[4] = {1, 1, 4, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc stride 4, W=%d G=%d lines=%d) failed: %d", W, G, lines, (int)r);
+  IISEG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc line stride 4, H=%d cols=%d lines=%d) failed: %d", H, cols, lines, (int)r);
   return 0;
 }
 
@@ -2277,22 +2277,25 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
         d->out_stride <= 1 && d->post_scale == nullptr && (d->out_f32 || d->upd_y != nullptr) && d->OW >= 32 && d->OH >= 2) {
       ConvParams q;
       memset(&q, 0, sizeof(q));
-      // G column groups (4G output columns) x TH lines per tile, TH * G <= 128 accumulator rows: fewest tiles, then the fullest
-      int bestG = 0, bestTH = 0; long best_tiles = -1; int best_rows = 0;
-      for (int G = 8; G <= 32; ++G) {
-        int TH = 128 / G;
-        if (TH > d->OH) TH = d->OH;
-        const long tiles = (long)ceil_div(d->OW, 4 * G) * ceil_div(d->OH, TH);
-        if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && TH * G > best_rows)) { best_tiles = tiles; bestG = G; bestTH = TH; best_rows = TH * G; }
+      // tile = LG line groups (4 LG output lines) x TW columns on accumulator rows of pitch TW + 2, LG * pitch <= 128:
+      // fewest tiles, then the fullest accumulator
+      int bestTW = 0, bestLG = 0; long best_tiles = -1; int best_rows = 0;
+      for (int TW = 14; TW <= 126; ++TW) {
+        int LG = 128 / (TW + 2);
+        if (4 * LG > ((d->OH + 3) & ~3)) LG = (d->OH + 3) / 4;
+        if (LG < 1) continue;
+        const long tiles = (long)ceil_div(d->OW, TW) * ceil_div(d->OH, 4 * LG);
+        const int rows = LG * (TW < d->OW ? TW : d->OW);
+        if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && rows > best_rows)) { best_tiles = tiles; bestTW = TW; bestLG = LG; best_rows = rows; }
       }
-      q.TH = bestTH; q.TW = 4 * bestG; q.pitch = bestG;
-      const int rows_box = (q.TH + 2) * bestG, rows_read = 2 * bestG + kBlockM;
+      q.TH = 4 * bestLG; q.TW = bestTW; q.pitch = bestTW + 2;
+      const int rows_box = bestLG * q.pitch, rows_read = 2 + kBlockM;
       q.a_blk_bytes = ((rows_box > rows_read ? rows_box : rows_read) * 128 + 1023) / 1024 * 1024;
       q.n_a = (227 * 1024 - 512 - kNpBankBytes) / q.a_blk_bytes;
       if (q.n_a > 8) q.n_a = 8;
       q.n_a &= ~1;
       if (q.n_a >= 2) {
-        if (encode_nhwc_stride4(&q.tm_src[0], d->src[0], d->N, d->H, d->W, 64, d->Cs[0], q.TH + 2, bestG)) return -1;
+        if (encode_nhwc_hstride4(&q.tm_src[0], d->src[0], d->N, d->H, d->W, 64, d->Cs[0], q.pitch, bestLG)) return -1;
         if (encode_weight(&q.tm_w, d->weight_npack, kNpUnits * 16, 64, 16, 64)) return -1;
         q.bias = d->bias; q.out = d->out; q.diag = diag_device_ptr();
         q.R = 3; q.S = 3; q.in_off_h = d->oh0 - d->pad; q.in_off_w = d->ow0 - d->pad;
