@@ -1,5 +1,7 @@
 """Summarises an `ncu --page raw --csv` export into profiles/<name>.md (+ profiles/traffic.json).
-    python tools/summarize_ncu.py gpurun_out/prof_steady_full_raw.csv profiles/r01_ncu_steady_application_v16"""
+    python tools/summarize_ncu.py gpurun_out/prof_steady_full_raw.csv profiles/r01_ncu_steady_application_v16 [tag]
+`tag` (e.g. the precision variant): traffic.json keeps its other entries and gains `<kernel>/<tag>` ones, plus
+`conv_igemm_pair_kernel/<tag>` = the mean over every CTA-pair launch (the dominant kernel of bench.py's roofline)."""
 import csv
 import json
 import sys
@@ -13,7 +15,7 @@ COLS = [('gpu__time_duration.sum', 'us'), ('sm__cycles_elapsed.avg', 'SM cycles'
         ('launch__shared_mem_per_block_dynamic', 'dyn smem')]
 
 
-def main(src, dst):
+def main(src, dst, tag=None):
     rows = list(csv.reader(open(src)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = [(hdr.index(c), c, label) for c, label in COLS if c in hdr]
@@ -32,10 +34,18 @@ def main(src, dst):
                  'Per-launch times are cold-cache and serialised (ncu replays each kernel); shares, not absolutes, compare with bench.py.\n\n')
         fh.write('\n'.join(lines) + '\n')
     out = {k: {'dram_bytes_per_launch': sum(v) / len(v), 'launches': len(v)} for k, v in traffic.items()}
+    if tag:
+        import os
+        old = json.load(open('profiles/traffic.json')) if os.path.exists('profiles/traffic.json') else {}
+        pair = [b for k, v in traffic.items() if k.startswith('conv_igemm_pair_kernel') for b in v]
+        old.update({'%s/%s' % (k, tag): v for k, v in out.items()})
+        if pair:
+            old['conv_igemm_pair_kernel/' + tag] = {'dram_bytes_per_launch': sum(pair) / len(pair), 'launches': len(pair)}
+        out = old
     with open('profiles/traffic.json', 'w') as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     print('\n'.join(lines))
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2])
+    main(*sys.argv[1:4])
