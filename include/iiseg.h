@@ -324,7 +324,8 @@ int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10
 
 /* ---- DAE training step (train_dae.py:243-335) around the tensor-core GEMMs -------------------------
  * iiseg_noise_pack: GaussianNoiseLayer (models/fcn_down.py:60-67) + layout change: dst = bf16 NHWC
- *   [N,H,W,Cpad] of y + sigma*noise (y, noise NCHW fp32; noise == NULL: plain pack).
+ *   [N,H,W,Cpad] of y + sigma*noise (y, noise NCHW fp32; noise == NULL: plain pack); split = 1: [N,H,W,2*Cpad], the
+ *   (hi | lo) pair.  Also used at inference for the reference's stochastic DePool2D mask sub-graph (layers/mylayers.py:91-93).
  * iiseg_loss_grad: masked crossentropy (metrics.py:68-91, clip 1e-7, void label = C) + lmb * masked
  *   squared_error (metrics.py:144-156) of softmax(logits) against the one-hot target (NCHW fp32,
  *   C+1 channels).  sums (fp64[4]) = {sum mask*CE, sum mask, sum m2*mean_c (p-t)^2, sum m2}: the loss
@@ -348,7 +349,7 @@ int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10
  *   3 * Cin_pad; bias gradient in column bias_col); re-emits the bf16 forward bank wb and, if wt != NULL, the
  *   flipped / transposed bank of the data-gradient conv wt[ci-ci0][taps-1-tap][co] ([Ci_t][taps][Co_pad]). */
 int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H,
-                     int W, int Cpad, void* stream);
+                     int W, int Cpad, int split, void* stream);
 int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb,
                     double* sums, void* dlogits, int passes, void* stream);
 int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,

@@ -425,16 +425,16 @@ def deconv_interleave(phases, C_, crop, out):
 
 
 # ---- DAE training step kernels ------------------------------------------------------
-def noise_pack(y, noise, sigma, cpad, out=None):
-    """bf16 NHWC [N,H,W,cpad] of y + sigma*noise (NCHW fp32 inputs; noise=None: plain pack)."""
+def noise_pack(y, noise, sigma, cpad, out=None, split=False):
+    """bf16 NHWC [N,H,W,cpad] of y + sigma*noise (NCHW fp32 inputs; noise=None: plain pack); split: the (hi | lo) pair."""
     _chk(y, F32, 'y')
     N, Cc, H, W = y.shape
     if noise is not None:
         _chk(noise, F32, 'noise')
         assert noise.shape == y.shape
     if out is None:
-        out = torch.empty((N, H, W, cpad), dtype=BF16, device=y.device)
-    _lib.call('iiseg_noise_pack', _ptr(y), _ptr(noise), C.c_float(sigma), _ptr(out), N, Cc, H, W, cpad, _stream())
+        out = torch.empty((N, H, W, (2 if split else 1) * cpad), dtype=BF16, device=y.device)
+    _lib.call('iiseg_noise_pack', _ptr(y), _ptr(noise), C.c_float(sigma), _ptr(out), N, Cc, H, W, cpad, int(bool(split)), _stream())
     return out
 
 

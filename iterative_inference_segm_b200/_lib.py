@@ -87,7 +87,7 @@ SIGNATURES = {
     'iiseg_channel_stats': (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     'iiseg_maxpool2_f32': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     'iiseg_deconv_interleave': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
-    'iiseg_noise_pack': (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_noise_pack': (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_loss_grad': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -21,7 +21,7 @@ namespace iiseg {
 
 // ---- y + sigma * noise -> bf16 NHWC (GaussianNoiseLayer, models/fcn_down.py:60-67) -----------------
 __global__ void __launch_bounds__(256) noise_pack_kernel(const float* __restrict__ y, const float* __restrict__ noise, float sigma,
-                                                         uint4* __restrict__ dst, int C, int HW, int C8, long long total) {
+                                                         uint4* __restrict__ dst, int C, int HW, int C8, long long total, int split) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
     const int pix = (int)(t % HW); t /= HW;
@@ -37,8 +37,15 @@ __global__ void __launch_bounds__(256) noise_pack_kernel(const float* __restrict
         v[k] = noise != nullptr ? __fmaf_rn(sigma, noise[j], y[j]) : y[j];
       }
     }
-    stg_v4(dst + (n * HW + pix) * C8 + cg, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]), h2 = pack_bf16x2(v[4], v[5]), h3 = pack_bf16x2(v[6], v[7]);
+    if (!split) {
+      stg_v4(dst + (n * HW + pix) * C8 + cg, make_uint4(h0, h1, h2, h3));
+    } else {          // (hi | lo) pair of the fp32 value (the operand format of the fp32-accurate convs)
+      uint4* row = dst + (n * HW + pix) * (2 * C8);
+      stg_v4(row + cg, make_uint4(h0, h1, h2, h3));
+      stg_v4(row + C8 + cg, make_uint4(pack_bf16x2(v[0] - bf16_lo(h0), v[1] - bf16_hi(h0)), pack_bf16x2(v[2] - bf16_lo(h1), v[3] - bf16_hi(h1)),
+                                       pack_bf16x2(v[4] - bf16_lo(h2), v[5] - bf16_hi(h2)), pack_bf16x2(v[6] - bf16_lo(h3), v[7] - bf16_hi(h3))));
+    }
   }
 }
 
@@ -381,13 +388,13 @@ static int tgrid(long long total) {
 }  // namespace iiseg
 
 extern "C" int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H, int W,
-                                int Cpad, void* stream) {
+                                int Cpad, int split, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(y && dst, "noise_pack: null tensor");
   IISEG_CHECK(N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && Cpad % 8 == 0, "noise_pack: bad shape");
   const long long total = (long long)N * (Cpad / 8) * H * W;
   noise_pack_kernel<<<tgrid(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, noise, sigma, reinterpret_cast<uint4*>(dst), C,
-                                                                                      H * W, Cpad / 8, total);
+                                                                                      H * W, Cpad / 8, total, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -63,7 +63,7 @@ class _DaeCallable(object):
         yc, as_np = _to_cuda(y)
         h_bf16 = K.pack_nchw(hc, net.h_pad, split=net.split)
         y_bf16 = K.pack_nchw(yc, net.y_cpad, split=net.split)
-        logits = net.logits(h_bf16, y_bf16)
+        logits = net.logits(h_bf16, y_bf16, y_f32=yc)
         out = torch.empty_like(yc)
         if self.grad:
             K.softmax_grad(logits, yc, out)
@@ -193,11 +193,11 @@ class IterativeInference(object):
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
             if self.fuse_update and net.fusable_update:
                 # softmax tail + update + norm in the epilogue of up_conv1: the logits never reach HBM
-                net.logits(st['h'], st['y_bf16'], full_down=(it == 0),
+                net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'],
                            update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))
                 K.norm_finalize_fixed(st['norm_acc'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             else:
-                logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0))
+                logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'])
                 K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
                 K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])

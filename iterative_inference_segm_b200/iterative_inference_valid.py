@@ -24,7 +24,7 @@ STEPS = [.01, .02, .05, .08, .1, .5, 1.]      # iterative_inference_valid.py:373
 
 def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, which_set='val', data_iter=None,
           fcn_params=None, dae_params=None, weights_path=None, loadpath=None, verbose=True,
-          precision='bf16', savepath=None, eps=_EPSILON):
+          precision='bf16', savepath=None, eps=_EPSILON, stochastic_masks=False):
     """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter]).  `eps` is the convergence
     threshold of the loop (the reference's _EPSILON = 1e-3, iterative_inference_valid.py:53)."""
     dae_dict = dict(DAE_DICT_DEFAULTS)
@@ -33,7 +33,7 @@ def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, whic
         data_iter = load_data(dataset, {}, one_hot=True, batch_size=[10, 10, 10], which_set=which_set)
     n_classes, void_labels = data_iter.non_void_nclasses, data_iter.void_labels
     fcn, dae = build_networks(segm_net, dae_dict, n_classes, data_iter.data_shape[0], void_labels, weights_path,
-                              loadpath, dataset, fcn_params, dae_params, precision=precision)
+                              loadpath, dataset, fcn_params, dae_params, precision=precision, stochastic_masks=stochastic_masks)
     pred_fcn_fn = F.function_pred_fcn(fcn)
     loop = F.IterativeInference(dae, n_classes, void_labels)
     valid_mats = np.zeros((len(steps), 2, n_classes, num_iter))        # float64 like the reference (:231)

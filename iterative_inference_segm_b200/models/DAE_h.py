@@ -30,7 +30,8 @@ def _levels(concat_h, additional_pool):
 
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
-                 n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind', bn=False):
+                 n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind', bn=False,
+                 mask_noise=0.0):
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
         hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
@@ -44,6 +45,12 @@ class DAENet(object):
         # (models/fcn_up.py:37-63) replaces unpool + conv by Deconv2DLayer(4, stride=2), run as four 2x2 phase convs
         assert unpool_type in ('trackind', 'inverse', 'standard'), unpool_type
         self.unpool_type = unpool_type
+        # mask_noise > 0 (opt-in, `buildDAE(..., stochastic_masks=True)`): the reference's DePool2D builds its tie masks with
+        # lasagne.layers.get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93), so when the DAE was built with
+        # noise > 0 the masks come from a SEPARATE pass of the contracting path on y + N(0, noise^2), even at inference.  In
+        # this mode every application runs the contracting path twice: once on the noised input for the masks, once on y for
+        # the values.
+        self.mask_noise = float(mask_noise) if unpool_type != 'standard' else 0.0
         self.precision = precision
         self.split = precision != 'bf16'          # contracting path (and the h / y input format)
         self.split_up = precision == 'fp32x3'     # expanding path
@@ -258,14 +265,16 @@ class DAENet(object):
         return ws
 
     # -- one application ----------------------------------------------------
-    def logits(self, h_bf16, y_bf16, full_down=True, update=None):
+    def logits(self, h_bf16, y_bf16, full_down=True, update=None, y_f32=None, noise=None):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
         Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16).
         `full_down=False` recomputes only the y-dependent windows of the contracting path; valid when
         the workspace already holds a full pass for the same h (see `down_windows`).
         `update` (bf16 expanding path: 'bf16' and 'mixed'): dict(y, active, norm_acc, step) -- the softmax tail and the
         iterative-inference update run in the epilogue of the last conv (y and y_bf16 are updated in
-        place, the logits are never stored) and None is returned."""
+        place, the logits are never stored) and None is returned.
+        `y_f32` (NCHW fp32, the values y_bf16 was packed from) and optionally `noise` (same shape, N(0,1); drawn here when
+        None) are needed when the net was built with mask_noise > 0."""
         B, H, W, _ = y_bf16.shape
         if self.unpool_type == 'standard':
             full_down = True          # (no crop cone / y-dependent windows for this variant: every level is computed in full)
@@ -282,22 +291,35 @@ class DAENet(object):
         if full_down:       # new h: the iteration-invariant half of the concat conv, once per batch, fp32
             K.conv2d(h_bf16, self.hproj_w[0], self.hproj_w[1], 3, 3, 1, relu=False, out=ws['hproj'], out_f32=True,
                      split=sp)
-        for p in range(self.total):
-            Wk, bk = self.down[p]
-            pad = self.padding if (p == 0 and self.padding > 0) else 1
-            win = None
-            if D is not None:
-                hl, hh, wl, wh = D[p + 1]
-                win = (hl, wl, hh - hl, wh - wl)
-            # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
-            # pre-pool map is consumed on chip and never written (nothing else reads it)
-            if p == self.n_pool:
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
-                         addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0), split=sp, post_affine=self.post[p])
-            else:
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=ws['pool'][p], pool_mask=ws['mask'][p],
-                         split=sp, post_affine=self.post[p])
-            x = ws['pool'][p]
+        passes = [(x, True)]
+        if self.mask_noise > 0:
+            # the mask sub-graph: the contracting path on y + sigma * noise writes the tie masks (its pooled values go to a
+            # scratch set), then the value pass below leaves the masks alone
+            assert y_f32 is not None, 'mask_noise > 0 needs the fp32 y (y_f32=) to draw the noised input of the mask pass'
+            if noise is None:
+                noise = torch.randn(y_f32.shape, dtype=torch.float32, device=y_f32.device)
+            x_noisy = K.noise_pack(y_f32, noise, self.mask_noise, self.y_cpad, split=sp)
+            if 'pool_m' not in ws:
+                ws['pool_m'] = [torch.empty_like(t) for t in ws['pool']]
+            passes = [(x_noisy, 'masks'), (x, 'values')]
+        for x, role in passes:
+            pools = ws['pool_m'] if role == 'masks' else ws['pool']
+            for p in range(self.total):
+                Wk, bk = self.down[p]
+                pad = self.padding if (p == 0 and self.padding > 0) else 1
+                win = None
+                if D is not None:
+                    hl, hh, wl, wh = D[p + 1]
+                    win = (hl, wl, hh - hl, wh - wl)
+                # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
+                # pre-pool map is consumed on chip and never written (nothing else reads it)
+                pm = ws['mask'][p] if role in (True, 'masks') else None
+                kw = {}
+                if p == self.n_pool:
+                    kw = dict(addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0))
+                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=pools[p], pool_mask=pm, split=sp,
+                         post_affine=self.post[p], **kw)
+                x = pools[p]
         if self.unpool_type == 'standard':
             return self._up_standard(ws, sizes, B, H, W)
         u, u_origin = ws['pool'][-1], (0, 0)
@@ -393,7 +415,7 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
              model_name='dae_model.npz', trainable=False, load_weights=False,
              out_nonlin=None, concat_h=['input'], noise=0.1, n_filters=64,
              conv_before_pool=1, additional_pool=0, dropout=0., skip=False,
-             unpool_type='standard', bn=0, params=None, precision='bf16'):
+             unpool_type='standard', bn=0, params=None, precision='bf16', stochastic_masks=False):
     """Same arguments as the reference builder (models/DAE_h.py:12-17); returns the handle
     of 'probs_dimshuffle'.  The symbolic inputs are ignored.  Built for the benchmark
     configuration; other variants raise.  `noise` only matters for training and for the
@@ -410,9 +432,9 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
     # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
     # build is the deterministic graph; warn so that a caller comparing against such a reference run knows.
-    if unpool_type == 'trackind' and (noise > 0 or dropout > 0 or bn):
+    if unpool_type == 'trackind' and (dropout > 0 or bn or (noise > 0 and not stochastic_masks)):
         warnings.warn('buildDAE: noise=%s dropout=%s bn=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
-                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks' % (noise, dropout, bn), stacklevel=2)
+                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise: pass stochastic_masks=True for the reference\'s noised mask pass)' % (noise, dropout, bn), stacklevel=2)
     concat_h = list(concat_h)
     if len(concat_h) != 1 or 'pool' not in concat_h[-1]:
         raise NotImplementedError('B200 DAE_h concatenates h at one pool layer (e.g. concat_h=[\'pool4\'])')
@@ -421,5 +443,6 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
             raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
-                 n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type, bn=bn)
+                 n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type, bn=bn,
+                 mask_noise=noise if stochastic_masks else 0.0)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -139,7 +139,7 @@ def batchnorm_deterministic(x, beta, gamma, mean, inv_std):
 
 
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
-                return_logits=False, unpool_type='trackind', bn=False):
+                return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None):
     """One application DAE(y, h) -> probabilities, same size as y.
 
     Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
@@ -152,6 +152,10 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
     unpool_type='inverse' (models/fcn_up.py:76-79): lasagne InverseLayer(prev, pool_p) = the gradient of
     the max-pool w.r.t. its input with `prev` as the upstream gradient; with Theano's CPU MaxPoolGrad
     (every tied maximum receives it) that is exactly DePool2D's repeat * tie-mask, so it shares the code.
+    mask_source_y: the reference builds DePool2D's mask sub-graph with get_output(...) WITHOUT deterministic=True
+    (layers/mylayers.py:91-93): when the DAE has noise > 0 its tie masks come from a SEPARATE pass of the
+    contracting path on y + N(0, noise^2), even at inference.  Pass that noised input here to restate it
+    (None: the deterministic graph, masks from the same pass).
     unpool_type='standard' (models/fcn_up.py:37-63): up_p = Deconv2DLayer(prev, n_cl, 4, stride=2,
     crop='valid', linear) and NO convolution; skip-sum / crop as above (centre crop of the larger map).
     """
@@ -181,6 +185,17 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         pools.append(x)
         if p + 1 == n_pool and n_pool > 0:
             x = torch.cat([h, x], dim=1)
+    if mask_source_y is not None:          # the non-deterministic mask sub-graph: same weights, noised input
+        xm, pre = mask_source_y, []
+        for p in range(total):
+            first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input' and padding > 0)
+            xm = L.conv2d(xm, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+            if BNd[p] is not None:
+                xm = batchnorm_deterministic(xm, *BNd[p])
+            pre.append(xm)
+            xm = L.maxpool2(xm)
+            if p + 1 == n_pool and n_pool > 0:
+                xm = torch.cat([h, xm], dim=1)
     u = pools[-1]
     for i, p in enumerate(range(total, 0, -1)):
         if unpool_type == 'standard':

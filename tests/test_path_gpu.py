@@ -588,3 +588,43 @@ def test_dae_with_batchnorm_vs_oracle(cuda, unpool_type):
         err = float(np.abs(p_d - p_o.numpy()).max())
         print('bn=1 %s %s: p max-abs %.3e' % (unpool_type, precision, err))
         assert err < tol, (precision, err)
+
+
+def test_stochastic_mask_subgraph_opt_in(cuda):
+    """The reference's DePool2D builds its masks with get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93): for a
+    DAE built with noise > 0 (the README's 0.5) the tie masks come from a separate pass of the contracting path on
+    y + N(0, noise^2), even at inference.  `buildDAE(..., stochastic_masks=True)` restates that: with the SAME noise tensor the
+    device application tracks the oracle's `mask_source_y` form; the default build stays the deterministic graph (and warns)."""
+    import warnings
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import IterativeInference
+    from iterative_inference_segm_b200 import _kernels as K
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    kw = dict(padding=100, concat_h=['pool4'], n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind',
+              params=pd, precision='mixed')
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, **kw)
+        assert any('deterministic masks' in str(x.message) for x in w)
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, stochastic_masks=True, **kw)
+    net = dae.net
+    X, L, lab = weights.synthetic_batch(2, 32, 40, NCLS, seed=23)
+    h, y0 = nets.fcn8_forward(pf, X, NCLS)
+    noise = torch.randn(y0.shape, generator=torch.Generator().manual_seed(5))
+    p_o = nets.dae_forward(pd, y0, h, 100, mask_source_y=y0 + 0.5 * noise)
+    p_det = nets.dae_forward(pd, y0, h, 100)
+    assert float((p_o - p_det).abs().max()) > 2 * TOL_F32               # the noised masks matter (7.7e-3 here)
+    yd = y0.to(cuda)
+    logits = net.logits(K.pack_nchw(h.to(cuda), net.h_pad, split=True), K.pack_nchw(yd, net.y_cpad, split=True), y_f32=yd,
+                        noise=noise.to(cuda))
+    p_d = torch.empty_like(yd)
+    K.softmax_nchw(logits, NCLS, p_d)
+    assert float((p_d.cpu() - p_o).abs().max()) < TOL_F32, float((p_d.cpu() - p_o).abs().max())
+    # the loop draws its own noise every iteration (inside the captured graph): runs, stays a distribution, differs from the
+    # deterministic loop, and two replays differ from each other (fresh noise)
+    ii = IterativeInference(dae, NCLS, [NCLS])
+    r1 = ii.run(h.to(cuda), yd, 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))['y'].clone()
+    r2 = ii.run(h.to(cuda), yd, 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))['y'].clone()
+    assert bool(torch.isfinite(r1).all()) and float(r1.min()) >= 0 and float(r1.max()) <= 1
+    assert not torch.equal(r1, r2)
