@@ -443,8 +443,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
     dae_dict.update(dae_dict_updates)
     if optimizer != 'rmsprop':
         raise NotImplementedError('B200 train step implements lasagne.updates.rmsprop (the benchmark optimiser)')
-    if dae_dict['kind'] != 'standard' or dae_dict['unpool_type'] != 'trackind' or segm_net != 'fcn8':
-        raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net=fcn8')
+    if dae_dict['kind'] != 'standard' or dae_dict['unpool_type'] != 'trackind' or segm_net not in ('fcn8', 'densenet'):
+        raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net in (fcn8, densenet)')
     if sorted(training_loss) != ['crossentropy', 'squared_error']:
         raise NotImplementedError('B200 train step: training_loss = [crossentropy, squared_error]')
     exp_name = build_experiment_name(segm_net, training_loss=training_loss, data_aug=bool(data_augmentation),
@@ -459,8 +459,16 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
         train_iter = load_data(dataset, data_augmentation, one_hot=True, batch_size=batch_size, which_set='train')
         val_iter = load_data(dataset, {}, one_hot=True, batch_size=batch_size, which_set='val')
     n_classes = train_iter.non_void_nclasses
-    fcn = buildFCN8(train_iter.data_shape[0], None, n_classes=n_classes, layer=dae_dict['concat_h'] + [dae_dict['layer']],
-                    path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'), params=fcn_params)
+    if segm_net == 'fcn8':           # train_dae.py:156-163
+        fcn = buildFCN8(train_iter.data_shape[0], None, n_classes=n_classes, layer=dae_dict['concat_h'] + [dae_dict['layer']],
+                        path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'), params=fcn_params)
+        padding, hkey = 100, dae_dict['concat_h'][-1]
+    else:                            # train_dae.py:164-168: FC-DenseNet103 conditioning, no padding
+        from .models.FCDenseNet import build_fcdensenet
+        fcn = build_fcdensenet(None, dae_dict['concat_h'], train_iter.data_shape[0], n_classes,
+                               weight_path=os.path.join(weights_path or '', dataset, 'DenseNet103', 'weights', 'FC-DenseNet103_weights.npz'),
+                               params=fcn_params)
+        padding, hkey = 0, dae_dict['concat_h'][-1] + '_bf16'
     fnet = fcn[0].net
     if dae_params is None:
         if resume:
@@ -469,7 +477,7 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
             from . import synthetic
             dae_params = synthetic.synthetic_dae_params(n_classes, fcn[0].output_shape[1], seed=seed, n_filters=dae_dict['n_filters'],
                                                         concat_h=tuple(dae_dict['concat_h']), additional_pool=dae_dict['additional_pool'])
-    tr = DAETrainer(n_classes, fcn[0].output_shape[1], 100, dae_params, concat_h=tuple(dae_dict['concat_h']),
+    tr = DAETrainer(n_classes, fcn[0].output_shape[1], padding, dae_params, concat_h=tuple(dae_dict['concat_h']),
                     n_filters=dae_dict['n_filters'], additional_pool=dae_dict['additional_pool'],
                     learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb)
     gen = torch.Generator(device=tr.dev).manual_seed(seed)
@@ -479,9 +487,9 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
         X, L = it.next()
         Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(tr.dev)
         Ld = torch.from_numpy(np.ascontiguousarray(L, dtype=np.float32)).to(tr.dev)
-        out = fnet.forward(Xd, want=('pool4', 'probs_dimshuffle'))
+        out = fnet.forward(Xd, want=(dae_dict['concat_h'][-1], 'probs_dimshuffle'))
         y = Ld[:, :n_classes].contiguous() if dae_dict['from_gt'] else out['probs_dimshuffle']
-        return out['pool4'], y, Ld
+        return out[hkey], y, Ld
 
     err_train, err_valid, jacc_val_arr, mse_val_arr = [], [], [], []
     patience, best_err_val = 0, None

@@ -3,6 +3,8 @@
 tensors with fp32 accumulation: per-parameter gradients within 15 % relative L2 error (stated tolerance; measured
 2-7 %, largest on the first layer, whose gradient has crossed all twelve), the
 loss within 1e-3 relative, the rmsprop update applied to exactly those gradients."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -209,3 +211,36 @@ def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
     errs = [_rel(g.cpu(), go) for g, go in zip(tr.grads_lasagne(), grads_o)]
     print('teacher-forced masks, relative L2 gradient errors vs the fp32 oracle:', ' '.join('%.4f' % e for e in errs))
     assert max(errs) < TOL_GRAD_FORCED, errs
+
+
+@pytest.mark.parametrize('segm_net', ['fcn8', 'densenet'])
+def test_train_loop_runs_and_writes_the_reference_checkpoints(cuda, tmp_path, segm_net):
+    """train() -- the host loop of train_dae.py:351-457 -- on a tiny synthetic set: epochs with validation, lr annealing (the
+    captured step graph follows it), best / last checkpoints in the positional .npz layout that buildDAE reads back."""
+    from iterative_inference_segm_b200.train_dae import train
+    from iterative_inference_segm_b200.data_loader import SyntheticSegmentationIterator
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200 import synthetic as S
+    size = (32, 40) if segm_net == 'fcn8' else (64, 96)
+    if segm_net == 'fcn8':
+        pf = S.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    else:
+        pf = S.synthetic_densenet_params(3, NCLS, seed=2, logit_gain=4.0)
+    dd = {'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0.5, 'concat_h': ['pool4'], 'from_gt': False,
+          'n_filters': 64, 'conv_before_pool': 1, 'additional_pool': 2, 'temperature': 1.0, 'path_weights': '', 'layer': 'probs_dimshuffle',
+          'exp_name': 't_', 'bn': 0}
+    mk = lambda n, seed: SyntheticSegmentationIterator(n, 2, size[0], size[1], NCLS, seed=seed)         # noqa: E731
+    out = train('camvid', segm_net, learning_rate=1e-3, lr_anneal=0.5, num_epochs=3, max_patience=5, optimizer='rmsprop',
+                training_loss=['crossentropy', 'squared_error'], dae_dict_updates=dd, savepath=str(tmp_path), loadpath=None,
+                train_iter=mk(4, 1), val_iter=mk(2, 2), fcn_params=pf, verbose=False)
+    assert len(out['err_train']) == 3 and all(np.isfinite(out['err_train'])) and all(np.isfinite(out['err_valid']))
+    assert out['err_train'][-1] < out['err_train'][0]                       # it descends on the (tiny, repeated) training set
+    assert abs(out['trainer'].lr - 1e-3 * 0.5 ** 3) < 1e-12                  # lr.set_value(lr * lr_anneal) every epoch
+    files = os.listdir(out['savepath'])
+    assert 'output.log' in files and ('dae_model_best.npz' in files or 'dae_model_last.npz' in files)
+    name = 'dae_model_best.npz' if 'dae_model_best.npz' in files else 'dae_model_last.npz'
+    nb = 512 if segm_net == 'fcn8' else 464
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=nb, padding=100 if segm_net == 'fcn8' else 0, concat_h=['pool4'], noise=0.0,
+                   n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind', load_weights=True,
+                   path_weights=out['savepath'], model_name=name)
+    assert dae.net.total == 6
