@@ -47,6 +47,10 @@ int iiseg_read_diag(int32_t* out, int n);
 /* Tuning aid: with IISEG_CONV_DBG=4 block 0 of every conv launch stamps clock64() at fixed points
  * of its first 32 tiles (16 slots each); returns the words copied. */
 int iiseg_debug_read_timeline(long long* out, int n);
+/* Leave `n` SMs free: the persistent kernels (one CTA per SM, all of its shared memory) size their grids for SM count - n,
+ * so that another stream's kernels -- NCCL's all-reduce CTAs under the data-parallel backward pass -- can be resident at the
+ * same time.  Returns the previous value; 0 restores the full machine. */
+int iiseg_reserve_sms(int n);
 /* Number of kernel launches issued through this library since load. */
 int64_t iiseg_launch_count(void);
 

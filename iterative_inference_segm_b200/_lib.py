@@ -66,6 +66,7 @@ SIGNATURES = {
     'iiseg_device_check': (_i, [_i]),
     'iiseg_read_diag': (_i, [_vp, _i]),
     'iiseg_launch_count': (C.c_int64, []),
+    'iiseg_reserve_sms': (_i, [_i]),
     'iiseg_debug_read_timeline': (_i, [_vp, _i]),
     'iiseg_pack_nchw_f32_to_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_unpack_nhwc_bf16_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

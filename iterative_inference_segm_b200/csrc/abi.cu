@@ -30,6 +30,8 @@ int current_device() {
   return dev;
 }
 
+static std::atomic<int> g_sm_reserve{0};
+
 int num_sms() {           // per device ordinal: a process may drive several GPUs
   static int sms[kMaxDevices] = {0};
   const int dev = current_device();
@@ -38,7 +40,8 @@ int num_sms() {           // per device ordinal: a process may drive several GPU
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     sms[dev] = n;
   }
-  return sms[dev];
+  const int r = g_sm_reserve.load(std::memory_order_relaxed);
+  return (r > 0 && r < sms[dev] - 16) ? sms[dev] - r : sms[dev];
 }
 
 // 64 pinned, device-mapped words.  A kernel whose mbarrier wait times out writes
@@ -61,6 +64,10 @@ int32_t* diag_device_ptr() {
 }  // namespace iiseg
 
 extern "C" int iiseg_abi_version(void) { return IISEG_ABI_VERSION; }
+extern "C" int iiseg_reserve_sms(int n) {
+  const int old = iiseg::g_sm_reserve.exchange(n < 0 ? 0 : n, std::memory_order_relaxed);
+  return old;
+}
 extern "C" int iiseg_conv_desc_size(void) { return (int)sizeof(iiseg_conv_desc); }
 extern "C" int iiseg_conv_desc_last_offset(void) { return (int)offsetof(iiseg_conv_desc, upd_cpad); }
 extern "C" int iiseg_deconv_desc_size(void) { return (int)sizeof(iiseg_deconv_desc); }

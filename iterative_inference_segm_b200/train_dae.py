@@ -82,6 +82,10 @@ class _Layer(object):
 
 
 class DAETrainer(object):
+    # SMs left free for NCCL's CTAs during the data-parallel backward (iiseg_reserve_sms).  Measured on 2 x B200
+    # (tools/train_dp_overlap.py): no exchange 4.91 ms, one blocking all-reduce 5.36, buckets under backward 5.17 with 0 SMs
+    # reserved, 5.18 with 4, 5.34 with 8, 5.35 with 16 -- the lost compute costs more than the overlap gains, so: 0.
+    DP_RESERVED_SMS = int(__import__('os').environ.get('IISEG_DP_RESERVED_SMS', '0'))
     BUCKET_BYTES = 32 << 20        # gradient all-reduce bucket size (NVSwitch: sized for launch latency / overlap, not link count)
 
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
@@ -344,8 +348,15 @@ class DAETrainer(object):
         """Data-parallel step with the gradient all-reduce bucketed (BUCKET_BYTES) and launched under backward: bucket k
         is reduced on NCCL's stream while the layers of bucket k+1.. are still being differentiated; the update waits
         for the last bucket only.  Same result as `step(..., world=world)` (same sums, same order inside NCCL)."""
+        from . import _lib
         self.forward(h_bf16, y, noise_main, noise_mask)
-        self.backward(target, world, overlap=True)
+        # the persistent conv kernels take every SM and all of its shared memory, so NCCL's CTAs mostly start in the gaps
+        # between them; DP_RESERVED_SMS > 0 leaves SMs free while gradients are in flight (measured: not a win, see above)
+        prev = _lib.load().iiseg_reserve_sms(self.DP_RESERVED_SMS if (world is not None and world.size > 1) else 0)
+        try:
+            self.backward(target, world, overlap=True)
+        finally:
+            _lib.load().iiseg_reserve_sms(prev)
         for w in self._works:
             w.wait()                   # stream-level wait: the update kernels queue behind the reductions
         self._works, self._dp_world = [], None
