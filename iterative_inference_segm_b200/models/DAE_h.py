@@ -31,7 +31,7 @@ def _levels(concat_h, additional_pool):
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
                  n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind', bn=False,
-                 mask_noise=0.0):
+                 mask_noise=0.0, skip=True):
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
         hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
@@ -51,6 +51,9 @@ class DAENet(object):
         # this mode every application runs the contracting path twice: once on the noised input for the masks, once on y for
         # the values.
         self.mask_noise = float(mask_noise) if unpool_type != 'standard' else 0.0
+        # skip=False (models/fcn_up.py:103-113): no ElemwiseSumLayer; the up-conv is only centre-cropped to the size of
+        # pool_{p-1} (CroppingLayer with merge_function = lambda input, deconv: deconv) -- the same windows, no addend
+        self.skip = bool(skip)
         self.precision = precision
         self.split = precision != 'bf16'          # contracting path (and the h / y input format)
         self.split_up = precision == 'fp32x3'     # expanding path
@@ -346,7 +349,7 @@ class DAENet(object):
                 up = K.unpool2(u, ws['mask'][p - 1], h, w, out=ws['unpool'][p], u_origin=u_origin,
                                window=(ul, vl, uh - ul, vh - vl), split=(2 if (mixed and i == 0) else spu))
             win = (hl - ul, wl - vl, hh - hl, wh - wl)     # conv window inside the unpooled window tensor
-            if p > 1 and self.fuse_depool_out and not sp and not (p == 2 and self.fuse_depool):
+            if p > 1 and self.fuse_depool_out and self.skip and not sp and not (p == 2 and self.fuse_depool):
                 # skip-sum, then DePool2D for the next level written straight from this conv's epilogue (u itself is
                 # never stored): one launch and one round trip of u through HBM less per level
                 nul, _, nvl, _ = Wu[p - 1]
@@ -355,8 +358,8 @@ class DAENet(object):
                 prefilled = True
             elif p > 1:   # skip-sum with pool_{p-1} (full map) read at the window offset
                 prefilled = False
-                u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2],
-                             addend_off=(hl, wl), out=ws['upconv'][p], split=spu, addend_pair_hi=mixed)
+                u = K.conv2d(up, Wk, bk, 3, 3, 1, relu=False, window=win, addend=ws['pool'][p - 2] if self.skip else None,
+                             addend_off=(hl, wl), out=ws['upconv'][p], split=spu, addend_pair_hi=mixed and self.skip)
                 u_origin = (hl, wl)
             else:       # centre crop (CroppingLayer, layers/mylayers.py:36-57): exactly the H x W window
                 if update is not None:
@@ -399,7 +402,7 @@ def _up_standard(self, ws, sizes, B, H, W):
                 n0, nw, o_w0 = _phase_range(wp, Sw, cw, px)
                 Wk, bk = self.up[i][py][px]
                 kw = {}
-                if p > 1:       # skip partner, same size as the cropped map (pool_{p-1} never is the larger one)
+                if p > 1 and self.skip:       # skip partner, same size as the cropped map (pool_{p-1} never is the larger one)
                     kw = dict(addend=ws['pool'][p - 2], addend_off=(o_h0, o_w0), addend_pair_hi=mixed)
                 K.conv2d(prev, Wk, bk, 2, 2, 1, relu=False, window=(m0, n0, mh, nw), out_f32=(p == 1), split=spu,
                          out_strided=(dest, 2, (o_h0, o_w0)), src_pair_hi=prev_pair_hi, **kw)
@@ -425,9 +428,10 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     import warnings
     if unpool_type not in ('trackind', 'inverse', 'standard'):
         raise ValueError('Unkown unpool type')                       # models/fcn_up.py:115
-    if not skip or conv_before_pool != 1 or ae_h:
-        raise NotImplementedError('B200 DAE_h supports unpool_type in (trackind, inverse, standard), skip=True, '
-                                  'conv_before_pool=1, ae_h=False')
+    if conv_before_pool != 1:
+        raise NotImplementedError('B200 DAE_h supports unpool_type in (trackind, inverse, standard), conv_before_pool=1')
+    # ae_h (models/DAE_h.py:12-49): names the layers 'h_to_recon' / 'h_hat' and freezes the pre-h parameters for the
+    # training loss of train_dae.py:317-320; the graph that produces 'probs_dimshuffle' is unchanged -> nothing to do here.
     # dropout: DropoutLayer is the identity under deterministic=True (iterative_inference.py:189-190), so it does not
     # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
     # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
@@ -444,5 +448,5 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
                  n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type, bn=bn,
-                 mask_noise=noise if stochastic_masks else 0.0)
+                 mask_noise=noise if stochastic_masks else 0.0, skip=skip)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -139,7 +139,7 @@ def batchnorm_deterministic(x, beta, gamma, mean, inv_std):
 
 
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
-                return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None):
+                return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None, skip=True):
     """One application DAE(y, h) -> probabilities, same size as y.
 
     Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
@@ -209,7 +209,7 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
             raise ValueError('Unkown unpool type')
         if p > 1:
             a, b = L.center_crop_pair(u, pools[p - 2])
-            u = a + b
+            u = a + b if skip else a          # skip=False: CroppingLayer keeps the (cropped) up-conv only, models/fcn_up.py:103-113
         else:
             u = L.center_crop_to(u, y.shape[2], y.shape[3])
     if return_logits:

@@ -628,3 +628,24 @@ def test_stochastic_mask_subgraph_opt_in(cuda):
     r2 = ii.run(h.to(cuda), yd, 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))['y'].clone()
     assert bool(torch.isfinite(r1).all()) and float(r1.min()) >= 0 and float(r1.max()) <= 1
     assert not torch.equal(r1, r2)
+
+
+@pytest.mark.parametrize('unpool_type', ['trackind', 'standard'])
+def test_dae_without_skip_connections_and_ae_h_flag(cuda, unpool_type):
+    """skip=False (models/fcn_up.py:103-113): the up-conv of each level is only centre-cropped to the size of pool_{p-1}, nothing is
+    added.  ae_h=True only renames layers / freezes parameters for the training loss: same inference graph."""
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import function_pred_dae
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1, unpool_type=unpool_type)
+    X, _, _ = weights.synthetic_batch(2, 37, 45, NCLS, seed=19)
+    h, y0 = nets.fcn8_forward(pf, X, NCLS)
+    p_o = nets.dae_forward(pd, y0, h, 100, unpool_type=unpool_type, skip=False)
+    assert float((p_o - nets.dae_forward(pd, y0, h, 100, unpool_type=unpool_type)).abs().max()) > 1e-3      # the skips matter
+    kw = dict(nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0, n_filters=64, conv_before_pool=1, additional_pool=2,
+              unpool_type=unpool_type, params=pd, precision='mixed')
+    dae = buildDAE([None], None, NCLS, skip=False, **kw)
+    p_d = function_pred_dae(dae)(h.numpy(), y0.numpy())
+    assert float(np.abs(p_d - p_o.numpy()).max()) < TOL_F32, float(np.abs(p_d - p_o.numpy()).max())
+    dae_ae = buildDAE([None], None, NCLS, skip=False, ae_h=True, **kw)
+    assert np.array_equal(function_pred_dae(dae_ae)(h.numpy(), y0.numpy()), p_d)
