@@ -31,7 +31,7 @@ def _levels(concat_h, additional_pool):
 class DAENet(object):
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',),
                  n_filters=64, additional_pool=2, device='cuda', precision='bf16', unpool_type='trackind', bn=False,
-                 mask_noise=0.0, skip=True):
+                 mask_noise=0.0, skip=True, conv_before_pool=1):
         """precision: 'bf16' (bf16 operands, fp32 accumulation: the throughput variant), 'fp32x3'
         (every activation and weight is a (hi, lo) bf16 pair and each conv accumulates
         hi*hi + lo*hi + hi*lo on the same tensor-core loop: fp32-accurate, ~3x the MMA work) or
@@ -80,6 +80,21 @@ class DAENet(object):
         #   contracting path: conv -> rectify -> BN -> pool  = a per-channel scale / shift in the conv epilogue, after the
         #                     rectifier and before the pool + tie mask (iiseg_conv_desc.post_scale);
         #   expanding path  : conv (linear) -> BN -> skip-sum = folded into the conv's weights and bias when packing.
+        # conv_before_pool = k > 1 (models/fcn_down.py:83-115): k rectified 3x3 convs per level, 'same' padding after the first;
+        # the pool (and its tie mask) follows the last one.  The extra convs run on full maps every iteration (no y-dependent
+        # windows: the region that depends on y then grows faster on the way down than the crop cone does on the way up).
+        self.cbp = int(conv_before_pool)
+        assert self.cbp >= 1 and not (self.cbp > 1 and bn), 'conv_before_pool > 1 is built for bn=0'
+        self.down_extra = [[] for _ in range(self.total)]
+        if self.cbp > 1:
+            k = self.cbp
+            assert len(params) == 2 * (k + 1) * self.total, 'conv_before_pool=%d: expected %d arrays, got %d' % (k, 2 * (k + 1) * self.total, len(params))
+            first, extra = [], []
+            for lvl in range(self.total):
+                grp = params[2 * k * lvl:2 * k * (lvl + 1)]
+                first += grp[:2]
+                extra.append(grp[2:])
+            params = first + list(params[2 * k * self.total:])
         self.bn = bool(bn)
         self.post = [None] * self.total
         if self.bn:
@@ -129,6 +144,10 @@ class DAENet(object):
             else:
                 self.down.append(pack_conv(W, b, [(cin_real, cin_pad)], self.filters[p], self.device, split=self.split))
             cin_real = cin_pad = self.filters[p]
+            if self.cbp > 1:
+                f_ = self.filters[p]
+                self.down_extra[p] = [pack_conv(extra[p][2 * i], extra[p][2 * i + 1], [(f_, f_)], f_, self.device, split=self.split)
+                                      for i in range(self.cbp - 1)]
         up_in = self.filters[-1]
         for i, p in enumerate(range(self.total, 0, -1)):
             W, b = params[2 * (self.total + i)], params[2 * (self.total + i) + 1]
@@ -279,8 +298,8 @@ class DAENet(object):
         `y_f32` (NCHW fp32, the values y_bf16 was packed from) and optionally `noise` (same shape, N(0,1); drawn here when
         None) are needed when the net was built with mask_noise > 0."""
         B, H, W, _ = y_bf16.shape
-        if self.unpool_type == 'standard':
-            full_down = True          # (no crop cone / y-dependent windows for this variant: every level is computed in full)
+        if self.unpool_type == 'standard' or self.cbp > 1:
+            full_down = True          # (no y-dependent windows for these variants: every level is computed in full)
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
         Wc, Wu = ws['Wc'], ws['Wu']
@@ -320,8 +339,21 @@ class DAENet(object):
                 kw = {}
                 if p == self.n_pool:
                     kw = dict(addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0))
-                K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=pools[p], pool_mask=pm, split=sp,
-                         post_affine=self.post[p], **kw)
+                if self.cbp > 1:      # conv_p_1 .. conv_p_{k-1} write full pre-pool maps, conv_p_k carries the pool
+                    pre = ws.setdefault(('pre', p), [None, None])
+                    hh_, ww_ = sizes[p]
+                    for i in range(self.cbp):
+                        last = i == self.cbp - 1
+                        Wi, bi = (Wk, bk) if i == 0 else self.down_extra[p][i - 1]
+                        if last:
+                            K.conv2d(x, Wi, bi, 3, 3, 1, relu=True, pooled=pools[p], pool_mask=pm, split=sp)
+                        else:
+                            if pre[i & 1] is None:
+                                pre[i & 1] = torch.empty((B, hh_, ww_, self.cm * self.filters[p]), dtype=torch.bfloat16, device=self.device)
+                            x = K.conv2d(x, Wi, bi, 3, 3, pad if i == 0 else 1, relu=True, out=pre[i & 1], split=sp, **(kw if i == 0 else {}))
+                else:
+                    K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, window=win, pooled=pools[p], pool_mask=pm, split=sp,
+                             post_affine=self.post[p], **kw)
                 x = pools[p]
         if self.unpool_type == 'standard':
             return self._up_standard(ws, sizes, B, H, W)
@@ -428,8 +460,8 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     import warnings
     if unpool_type not in ('trackind', 'inverse', 'standard'):
         raise ValueError('Unkown unpool type')                       # models/fcn_up.py:115
-    if conv_before_pool != 1:
-        raise NotImplementedError('B200 DAE_h supports unpool_type in (trackind, inverse, standard), conv_before_pool=1')
+    if conv_before_pool > 1 and bn:
+        raise NotImplementedError('B200 DAE_h: conv_before_pool > 1 is built for bn=0')
     # ae_h (models/DAE_h.py:12-49): names the layers 'h_to_recon' / 'h_hat' and freezes the pre-h parameters for the
     # training loss of train_dae.py:317-320; the graph that produces 'probs_dimshuffle' is unchanged -> nothing to do here.
     # dropout: DropoutLayer is the identity under deterministic=True (iterative_inference.py:189-190), so it does not
@@ -448,5 +480,5 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
         params = load_npz_params(os.path.join(path_weights, model_name))
     net = DAENet(n_classes, nb_features_to_concat, padding, params, concat_h=tuple(concat_h),
                  n_filters=n_filters, additional_pool=additional_pool, precision=precision, unpool_type=unpool_type, bn=bn,
-                 mask_noise=noise if stochastic_masks else 0.0, skip=skip)
+                 mask_noise=noise if stochastic_masks else 0.0, skip=skip, conv_before_pool=conv_before_pool)
     return LayerHandle(net, 'probs_dimshuffle', n_classes)

@@ -98,7 +98,7 @@ def dae_levels(concat_h=('pool4',), additional_pool=2):
 
 
 def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
-                     concat_h=('pool4',), additional_pool=2, unpool_type='trackind'):
+                     concat_h=('pool4',), additional_pool=2, unpool_type='trackind', conv_before_pool=1):
     """[(name, W shape, b shape)] in checkpoint order: conv1_1..convP_1 then
     up_convP..up_conv1.  Filter counts: n_filters*2**p for p<6
     (models/fcn_down.py:96-99); up_conv_p outputs the channel count of
@@ -113,9 +113,10 @@ def dae_param_shapes(n_classes, nb_features_to_concat, n_filters=64,
     for p in range(total):
         if p < 6:
             filters = n_filters * (2 ** p)
-        shapes.append(('conv%d_1' % (p + 1), (filters, cin, 3, 3), (filters,)))
+        for i in range(1, conv_before_pool + 1):       # models/fcn_down.py:83-104
+            shapes.append(('conv%d_%d' % (p + 1, i), (filters, cin, 3, 3), (filters,)))
+            cin = filters
         conv_out.append(filters)
-        cin = filters
         if p + 1 == n_pool and n_pool > 0:  # concat h after pool{n_pool}
             cin += nb_features_to_concat
     up_in = conv_out[-1]
@@ -139,7 +140,8 @@ def batchnorm_deterministic(x, beta, gamma, mean, inv_std):
 
 
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
-                return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None, skip=True):
+                return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None, skip=True,
+                conv_before_pool=1):
     """One application DAE(y, h) -> probabilities, same size as y.
 
     Down (models/fcn_down.py:77-136): conv3x3 ReLU (pad=`padding` on the first
@@ -166,10 +168,18 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         BNd = [tuple(params[6 * i + 2:6 * i + 6]) for i in range(total)]
         Wu = [tuple(params[6 * total + k_up * i:6 * total + k_up * i + 2]) for i in range(total)]
         BNu = [tuple(params[6 * total + k_up * i + 2:6 * total + k_up * i + 6]) if k_up == 6 else None for i in range(total)]
+    elif conv_before_pool > 1:     # k convs per level (models/fcn_down.py:83-104): the first as below, then 'same' convs
+        k = conv_before_pool
+        Wd = [(params[2 * k * i], params[2 * k * i + 1]) for i in range(total)]
+        Wd_extra = [[(params[2 * k * i + 2 * j], params[2 * k * i + 2 * j + 1]) for j in range(1, k)] for i in range(total)]
+        Wu = [(params[2 * (k * total + i)], params[2 * (k * total + i) + 1]) for i in range(total)]
+        BNd = BNu = [None] * total
     else:
         Wd = [(params[2 * i], params[2 * i + 1]) for i in range(total)]
         Wu = [(params[2 * (total + i)], params[2 * (total + i) + 1]) for i in range(total)]
         BNd = BNu = [None] * total
+    if conv_before_pool <= 1:
+        Wd_extra = [[] for _ in range(total)]
     x = y
     if concat_h[-1] == 'input':
         x = torch.cat([h, x], dim=1)
@@ -178,6 +188,8 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input'
                      and padding > 0)
         x = L.conv2d(x, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+        for We in Wd_extra[p]:
+            x = L.conv2d(x, *We, pad='same', relu=True)
         if BNd[p] is not None:
             x = batchnorm_deterministic(x, *BNd[p])
         pre.append(x)

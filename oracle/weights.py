@@ -41,7 +41,7 @@ def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
 
 
 def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
-                         concat_h=('pool4',), additional_pool=2, out_gain=1.0, unpool_type='trackind'):
+                         concat_h=('pool4',), additional_pool=2, out_gain=1.0, unpool_type='trackind', conv_before_pool=1):
     """Lasagne defaults: GlorotUniform W, zero b (the benign
     regime).  `out_gain` rescales the last conv (up_conv1): with random weights
     the iterated map amplifies pool-mask flips, and out_gain < 1 makes it
@@ -50,7 +50,7 @@ def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
     gen = torch.Generator().manual_seed(seed)
     params = []
     for name, ws, bs in dae_param_shapes(n_classes, nb_features_to_concat, n_filters,
-                                         concat_h, additional_pool, unpool_type):
+                                         concat_h, additional_pool, unpool_type, conv_before_pool):
         W = glorot_uniform(ws, gen)
         if name in ('up_conv1', 'up1'):
             W = W * out_gain

@@ -649,3 +649,25 @@ def test_dae_without_skip_connections_and_ae_h_flag(cuda, unpool_type):
     assert float(np.abs(p_d - p_o.numpy()).max()) < TOL_F32, float(np.abs(p_d - p_o.numpy()).max())
     dae_ae = buildDAE([None], None, NCLS, skip=False, ae_h=True, **kw)
     assert np.array_equal(function_pred_dae(dae_ae)(h.numpy(), y0.numpy()), p_d)
+
+
+def test_dae_with_two_convs_before_each_pool(cuda):
+    """conv_before_pool=2 (models/fcn_down.py:83-104): conv_p_1, conv_p_2 (rectified, 'same' after the pad-100 first one), then the
+    pool; 36 parameter arrays.  One application and a 3-step loop against the oracle at the fp32 bar."""
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import function_pred_dae, IterativeInference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=6, out_gain=0.1, conv_before_pool=2)
+    assert len(pd) == 36
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=0.0, n_filters=64,
+                   conv_before_pool=2, additional_pool=2, skip=True, unpool_type='trackind', params=pd, precision='mixed')
+    X, L, lab = weights.synthetic_batch(2, 37, 45, NCLS, seed=29)
+    h, y0 = nets.fcn8_forward(pf, X, NCLS)
+    p_o = nets.dae_forward(pd, y0, h, 100, conv_before_pool=2)
+    p_d = function_pred_dae(dae)(h.numpy(), y0.numpy())
+    assert float(np.abs(p_d - p_o.numpy()).max()) < TOL_F32, float(np.abs(p_d - p_o.numpy()).max())
+    y_o = y0.clone()
+    for _ in range(3):
+        y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, h, 100, conv_before_pool=2)), 0, 1)
+    y = IterativeInference(dae, NCLS, [NCLS]).run(h.to(cuda), y0.to(cuda), 0.05, 3, eps=0.0)['y'].cpu()
+    assert float((y - y_o).abs().max()) < TOL_F32 and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= MIN_ARGMAX_F32
