@@ -529,9 +529,9 @@ __device__ __forceinline__ void conv_epilogue16_update(const ConvParams& p, uint
   if (n_acc >= 0) flush();
 }
 
-template <int BN, bool kSplit, bool kShflPool>
-__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
-                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
+template <int BN, bool kSplit, bool kShflPool, bool kPost>
+__device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                                   uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
   const int q = warp & 3;
   const int grp = (warp - 4) >> 2;
   const int macc = q * 32 + lane;         // accumulator row
@@ -637,8 +637,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
         // the rounding); split variant: rectify in fp32, then hi = bf16(x), lo = bf16(x - hi).
         uint32_t hi[16], lo[kSplit ? 16 : 1];
 #pragma unroll
-        const bool post = p.post_scale != nullptr;     // deterministic BatchNormLayer behind the rectifier (DAE_h bn=1)
-        if (post) {
+        constexpr bool post = kPost;                   // deterministic BatchNormLayer behind the rectifier (DAE_h bn=1)
+        if constexpr (post) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
@@ -859,6 +859,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
   }
 }
 
+// The common epilogue is inlined into the kernels; the variant with the post-rectifier affine (DAE_h bn=1, rare) is a separate
+// non-inlined function so that its extra live values do not raise the register pressure (and spill) in the hot kernels.
+template <int BN, bool kSplit, bool kShflPool>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                              uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
+  conv_epilogue_impl<BN, kSplit, kShflPool, false>(p, tmem_base, smem_stage_out, tmem_full_bar0, tmem_empty_bar0, warp, lane);
+}
+template <int BN, bool kSplit>
+__device__ __noinline__ void conv_epilogue_post(const ConvParams& p, uint32_t tmem_base, uint32_t smem_stage_out,
+                                                uint32_t tmem_full_bar0, uint32_t tmem_empty_bar0, int warp, int lane) {
+  conv_epilogue_impl<BN, kSplit, false, true>(p, tmem_base, smem_stage_out, tmem_full_bar0, tmem_empty_bar0, warp, lane);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -984,6 +997,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_igemm_kernel(const __grid
     if constexpr (BN == 16) {
       if (p.upd_y != nullptr) conv_epilogue16_update<2>(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else conv_epilogue16(p, tmem_base, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else if (p.post_scale != nullptr) {
+      if (p.split) conv_epilogue_post<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue_post<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     } else if (p.split) {
       if (p.pooled != nullptr && p.pitch == 16 && p.TH == 8) conv_epilogue<BN, true, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
@@ -1145,7 +1161,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) conv
       }
     }
   } else if (warp >= 4) {
-    if (p.split) {
+    if (p.post_scale != nullptr) {
+      if (p.split) conv_epilogue_post<BN, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+      else conv_epilogue_post<BN, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
+    } else if (p.split) {
       if (p.pooled != nullptr && p.pitch == 16 && p.TH == 8) conv_epilogue<BN, true, true>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
       else conv_epilogue<BN, true, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
     } else conv_epilogue<BN, false, false>(p, tmem_base, smem_stage_out, tmem_full_bar(0), tmem_empty_bar(0), warp, lane);
@@ -1189,7 +1208,10 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
     const int oh = tc.th * p.TH + hl, ow = tc.tw * p.TW + wl;
     const bool valid = in_box && (oh < p.OH) && (ow < p.OW);
     const size_t pix = (static_cast<size_t>(tc.n) * p.OH + oh) * p.OW + ow;
-    const bool has_add = !kPool && (p.addend != nullptr) && valid;
+    const bool has_add = !kPool && (p.addend != nullptr) && !p.addend_f32 && valid;
+    // fp32 operand (the hoisted iteration-invariant half of a concat conv: concat_h = ['input'] puts it on the first layer)
+    const bool has_add32 = (p.addend != nullptr) && p.addend_f32 && in_box && (oh < p.OH) && (ow < p.OW);
+    const size_t apix32 = (static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0;
     const __nv_bfloat16* arow = p.addend + ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.addend_cs;
     uint4 add[2];
     if (has_add) { add[0] = ldg_nc_v4(arow); add[1] = ldg_nc_v4(arow + 8); }      // before the accumulator is ready
@@ -1224,6 +1246,15 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int k = 0; k < 8; ++k) { f[2 * k] += bf16_lo(aw[k]); f[2 * k + 1] += bf16_hi(aw[k]); }
+      }
+      if (has_add32) {
+        const float* a32 = reinterpret_cast<const float*>(p.addend) + apix32 * p.addend_cs + cbase;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 t = ldg_nc_v4(a32 + 4 * j);
+          f[4 * j] += __uint_as_float(t.x); f[4 * j + 1] += __uint_as_float(t.y);
+          f[4 * j + 2] += __uint_as_float(t.z); f[4 * j + 3] += __uint_as_float(t.w);
+        }
       }
       if (!kPool && p.out_f32) {          // fp32 rows (DenseNet's first conv): 64 contiguous bytes per thread
         if (valid) {
@@ -1358,6 +1389,16 @@ __device__ __forceinline__ void halo_epilogue_split(const ConvParams& p, uint32_
         const float4 b = __ldg(bias4 + j4);
         f[4 * j4] = __uint_as_float(v[4 * j4]) + b.x; f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
         f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z; f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
+      }
+      if (p.addend != nullptr && p.addend_f32 && in_box && oh < p.OH && ow < p.OW) {      // hoisted fp32 term of a concat conv
+        const float* a32 = reinterpret_cast<const float*>(p.addend) +
+                           ((static_cast<size_t>(tc.n) * p.AH + oh + p.ah0) * p.AW + ow + p.aw0) * p.addend_cs + cbase;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 t = ldg_nc_v4(a32 + 4 * j);
+          f[4 * j] += __uint_as_float(t.x); f[4 * j + 1] += __uint_as_float(t.y);
+          f[4 * j + 2] += __uint_as_float(t.z); f[4 * j + 3] += __uint_as_float(t.w);
+        }
       }
       if (p.relu) {
 #pragma unroll
@@ -2210,7 +2251,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   // output, no skip-sum / training mask / DePool2D fusion.  The kernel loads the hi and lo blocks once each and keeps
   // W_hi and W_lo resident (hi*W_hi + hi*W_lo + lo*W_hi).
   const bool hsplit_ok = d->split && d->src[2] != nullptr && d->src[3] == nullptr && d->src[2] == d->src[0] && d->C[0] == d->C[1] &&
-                         d->C[0] == d->C[2] && d->Cs[0] == d->Cs[2] && d->addend == nullptr && d->pool_zmask == nullptr &&
+                         d->C[0] == d->C[2] && d->Cs[0] == d->Cs[2] && (d->addend == nullptr || d->addend_f32) && d->pool_zmask == nullptr &&
                          d->depool_mask == nullptr && d->depool_out == nullptr && d->w_groups == 0;
   // K blocks of 64 channels (128-byte rows), or -- one 16-channel source, 3x3 filter, halo-tile kernel only -- of 16
   int KB = (d->C[0] == 16 && (d->src[1] == nullptr || hsplit_ok)) ? 16 : 64;

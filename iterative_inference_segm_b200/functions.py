@@ -43,7 +43,9 @@ def function_pred_fcn(fcn):
         res = []
         for hd in fcn:
             t = out[hd.name]
-            if hd.name.startswith('pool'):    # poolK features (NHWC bf16 / fp32 inside) leave as the reference's NCHW float32
+            if hd.name == 'input':
+                t = t.clone()
+            elif hd.name.startswith('pool'):    # poolK features (NHWC bf16 / fp32 inside) leave as the reference's NCHW float32
                 t = K.unpack_nhwc(t, hd.output_shape[1], split=net.split and t.dtype == torch.bfloat16)
             res.append(_ret(t, as_np))
         return res

@@ -69,9 +69,14 @@ class DAENet(object):
         self.n_classes = n_classes
         self.nb_h = nb_features_to_concat
         self.h_pad = K.pad_channels(nb_features_to_concat)
-        self.padding = padding
+        # concat_h = ['poolN']: h joins the DAE's own pool_N (n_pool = N); concat_h = ['input']: h (the image, 'input' layer of
+        # the segmentation net) joins y at the DAE's input (n_pool = 0, models/model_helpers.py:86-96) and -- concatenation
+        # only at the input -- the first conv is not padded by `padding` but 'same' (models/fcn_down.py:90-95)
         self.n_pool, self.total = _levels(concat_h, additional_pool)
-        assert self.n_pool >= 1, 'conditioning must be concatenated at a pool layer'
+        assert self.total >= 1, 'It seems your DAE will have no conv/pooling layers!'      # models/fcn_down.py:73-74
+        if self.n_pool == 0:
+            padding = 0
+        self.padding = padding
         self.device = torch.device(device)
         self.y_cpad = K.pad_channels(n_classes, narrow=True)    # channels of the bf16 copy of y (16: 32-byte K blocks)
         # bn=1 (models/fcn_down.py:113-115, models/fcn_up.py:91-93): a BatchNormLayer behind every conv.  At inference the graph
@@ -190,6 +195,8 @@ class DAENet(object):
         return sizes
 
     def h_spatial(self, H, W):
+        if self.n_pool == 0:
+            return H, W
         s = self.level_sizes(H, W)[self.n_pool - 1]
         return s[0] // 2, s[1] // 2
 
@@ -472,8 +479,10 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
         warnings.warn('buildDAE: noise=%s dropout=%s bn=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
                       'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise: pass stochastic_masks=True for the reference\'s noised mask pass)' % (noise, dropout, bn), stacklevel=2)
     concat_h = list(concat_h)
-    if len(concat_h) != 1 or 'pool' not in concat_h[-1]:
-        raise NotImplementedError('B200 DAE_h concatenates h at one pool layer (e.g. concat_h=[\'pool4\'])')
+    if len(concat_h) != 1 or not (concat_h[-1] == 'input' or concat_h[-1] in ('pool1', 'pool2', 'pool3', 'pool4', 'pool5')):
+        # (several entries share ONE nb_features_to_concat in the reference, models/model_helpers.py:91, so they only build
+        # there when all conditioning tensors have the same channel count)
+        raise NotImplementedError('B200 DAE_h concatenates one conditioning tensor: concat_h=[\'input\'] or [\'poolN\']')
     if params is None:
         if not load_weights:
             raise ValueError('buildDAE needs weights: pass params= or load_weights=True with path_weights')

@@ -77,6 +77,8 @@ class FCN8Net(object):
         assert Cin == self.nb_in_channels
         out = {}
         sp, cm = self.split, self.cm
+        if 'input' in want:          # net['input'] (models/fcn8.py:30): the image itself, the conditioning of concat_h=['input']
+            out['input'] = X
         x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=True), split=sp)
         for si, stage in enumerate(VGG_STAGES):
             for ci, (name, cout) in enumerate(stage):
@@ -142,8 +144,10 @@ def buildFCN8(nb_in_channels, input_var=None,
     for el in layer:
         if el in _POOL_CHANNELS:
             handles.append(LayerHandle(net, el, _POOL_CHANNELS[el]))
+        elif el == 'input':
+            handles.append(LayerHandle(net, el, nb_in_channels))
         elif el == 'probs_dimshuffle':
             handles.append(LayerHandle(net, el, n_classes))
         else:
-            raise ValueError('layer %r is not exposed by the B200 FCN8 (pool1..pool5, probs_dimshuffle)' % el)
+            raise ValueError('layer %r is not exposed by the B200 FCN8 (input, pool1..pool5, probs_dimshuffle)' % el)
     return handles

@@ -671,3 +671,37 @@ def test_dae_with_two_convs_before_each_pool(cuda):
         y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, h, 100, conv_before_pool=2)), 0, 1)
     y = IterativeInference(dae, NCLS, [NCLS]).run(h.to(cuda), y0.to(cuda), 0.05, 3, eps=0.0)['y'].cpu()
     assert float((y - y_o).abs().max()) < TOL_F32 and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= MIN_ARGMAX_F32
+
+
+@pytest.mark.parametrize('precision', ['mixed', 'bf16'])
+def test_dae_conditioned_on_the_input_image(cuda, precision):
+    """concat_h=['input'] (models/model_helpers.py:86-96, models/fcn_down.py:69-74,90-95): the conditioning tensor is the image
+    (the segmentation net's 'input' layer, 3 channels), concatenated BEFORE y at the DAE's input; no pool precedes it, so the
+    DAE has `additional_pool` levels and its first conv is 'same'-padded (no pad 100).  The iteration-invariant image half of
+    conv1_1 is hoisted like the h half of conv5_1.  Through the drop-in callables: buildFCN8(layer=['input', ...]) ->
+    pred_fcn_fn -> the loop, against the oracle."""
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200.functions import function_pred_fcn, function_pred_dae, IterativeInference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pd = weights.synthetic_dae_params(NCLS, 3, seed=8, out_gain=0.1, concat_h=('input',), additional_pool=3)
+    assert len(pd) == 12 and tuple(pd[0].shape) == (64, 3 + NCLS, 3, 3)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['input', 'probs_dimshuffle'], params=pf, precision=precision)
+    assert fcn[0].output_shape[1] == 3
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=fcn[0].output_shape[1], padding=100, concat_h=['input'], noise=0.0,
+                   n_filters=64, conv_before_pool=1, additional_pool=3, skip=True, unpool_type='trackind', params=pd, precision=precision)
+    tol, agree = (TOL_F32, MIN_ARGMAX_F32) if precision == 'mixed' else (TOL_DAE_P, MIN_ARGMAX)
+    X, L, lab = weights.synthetic_batch(2, 40, 56, NCLS, seed=31)
+    _, y0 = nets.fcn8_forward(pf, X, NCLS)
+    h_d, y0_d = function_pred_fcn(fcn)(X.numpy())
+    assert np.array_equal(h_d, X.numpy())
+    kw = dict(concat_h=('input',), additional_pool=3)
+    p_o = nets.dae_forward(pd, y0, X, 100, **kw)
+    p_d = function_pred_dae(dae)(X.numpy(), y0.numpy())
+    assert float(np.abs(p_d - p_o.numpy()).max()) < tol, float(np.abs(p_d - p_o.numpy()).max())
+    y_o = y0.clone()
+    for _ in range(3):
+        y_o = torch.clamp(y_o - 0.05 * (y_o - nets.dae_forward(pd, y_o, X, 100, **kw)), 0, 1)
+    res = IterativeInference(dae, NCLS, [NCLS]).run(X.to(cuda), y0.to(cuda), 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))
+    y = res['y'].cpu()
+    assert float((y - y_o).abs().max()) < tol and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
