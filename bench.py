@@ -286,12 +286,19 @@ class Ctx(object):
         return float(ms[0]), float(ms[1])
 
 
-def build_inference(ctx, precision, segm='fcn8'):
+def build_inference(ctx, precision, segm='fcn8', kind='standard'):
     from iterative_inference_segm_b200.models.fcn8 import buildFCN8
     from iterative_inference_segm_b200.models.FCDenseNet import build_fcdensenet
     from iterative_inference_segm_b200.models.DAE_h import buildDAE
     from iterative_inference_segm_b200.functions import IterativeInference
     from iterative_inference_segm_b200 import synthetic as weights
+    if kind == 'contextmod':       # the reference CLI's default DAE: context module conditioned on the image
+        from iterative_inference_segm_b200.models.contextmod_dae import buildDAE_contextmod
+        fcn = buildFCN8(3, None, n_classes=NCLS, layer=['input', 'probs_dimshuffle'],
+                        params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
+        dae = buildDAE_contextmod([None], None, NCLS, concat_h=['input'], noise=0.0,
+                                  params=weights.synthetic_contextmod_params(NCLS, 3, seed=3), nb_features_to_concat=3)
+        return fcn, dae, IterativeInference(dae, NCLS, [NCLS])
     if segm == 'fcn8':
         fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'],
                         params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
@@ -306,16 +313,17 @@ def build_inference(ctx, precision, segm='fcn8'):
     return fcn, dae, IterativeInference(dae, NCLS, [NCLS])
 
 
-def measure_inference(ctx, precision, segm='fcn8', n_iter=N_ITER, with_e2e=True, clocks=False, strong=False):
+def measure_inference(ctx, precision, segm='fcn8', n_iter=N_ITER, with_e2e=True, clocks=False, strong=False, kind='standard'):
     """Times the step (FCN forward + n_iter loop iterations + metrics + the confusion-matrix all-reduce) on this rank's
     batches.  Returns (record, objects for the roofline leg)."""
     torch, dist, args = ctx.torch, ctx.dist, ctx.args
     from iterative_inference_segm_b200 import _lib
     from iterative_inference_segm_b200 import synthetic as weights
     from iterative_inference_segm_b200.sharding import shard_range, allreduce_metrics
-    fcn, dae, ii = build_inference(ctx, precision, segm)
+    fcn, dae, ii = build_inference(ctx, precision, segm, kind)
     fnet = fcn[0].net
-    hkey = 'pool4' if segm == 'fcn8' else 'pool4_bf16'
+    hkey = 'input' if kind == 'contextmod' else 'pool4' if segm == 'fcn8' else 'pool4_bf16'
+    want = ('input', 'probs_dimshuffle') if kind == 'contextmod' else ('pool4', 'probs_dimshuffle')
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
     if strong:       # a fixed set of STRONG_SET images = batches of 10; rank r owns batches [lo, hi)
         lo, hi = shard_range(STRONG_SET // BATCH, rank, world)
@@ -331,7 +339,7 @@ def measure_inference(ctx, precision, segm='fcn8', n_iter=N_ITER, with_e2e=True,
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def batch_device(Xd, Ld):
-        out = fnet.forward(Xd, want=('pool4', 'probs_dimshuffle'))
+        out = fnet.forward(Xd, want=want)
         res = ii.run(out[hkey], out['probs_dimshuffle'], STEP, n_iter, onehot=Ld)
         cm_total.add_(res['cm'].sum(0))
         counts.add_(res['counts'].sum(0))
@@ -488,6 +496,41 @@ def roofline_leg(ctx, dae, ii, precision):
     return roof, breakdown
 
 
+def contextmod_leg(ctx, strong=False):
+    """kind='contextmod' (models/contextmod_dae.py, the reference CLI's default DAE; concat_h=['input']): FCN8 + 50 iterations
+    of the context module on the same batch, plus the application's time against the fp32 FMA rate of the CUDA cores (the
+    module is 11-channel fp32 stencil work: csrc/contextmod.cu)."""
+    torch = ctx.torch
+    rec, (fcn, dae, ii) = measure_inference(ctx, 'mixed', kind='contextmod', strong=strong)
+    out = {'workload': 'FCN8 (fp32-accurate) + context-module DAE (concat_h=input, fp32), batch 10 x 360x480, 11 classes, 50 steps, step 0.05, metrics.py Jaccard',
+           'value': rec['value'], 'unit': 'images/s', 'ms_per_step': rec['ms_per_step'], 'e2e': rec['e2e'],
+           'dtype': 'f32 (CUDA-core FMA) in the context module', 'executed_iterations': rec['executed_iterations'],
+           'parity': 'tests/test_path_gpu.py::test_contextmod_dae_vs_oracle: probabilities within 2e-5 of the fp32 oracle'}
+    if ctx.rank == 0:
+        net = dae.net
+        X = torch.rand((BATCH, 3, H, W), device=ctx.dev)
+        y = torch.softmax(torch.randn((BATCH, NCLS, H, W), device=ctx.dev), 1)
+        net.logits(X, None, full_down=True, y_f32=y)
+        n = 20
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(n):
+            net.logits(X, None, full_down=False, y_f32=y)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / n
+        fl = sum(net.executed_conv_flops(H, W)) * BATCH
+        props = torch.cuda.get_device_properties(ctx.dev)
+        peak = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12          # 128 FMA lanes per SM at the 1965 MHz boost clock
+        out['application'] = {'ms': ms, 'launches': 7, 'fp32_tflops': fl / (ms * 1e-3) / 1e12, 'fp32_peak_nominal_tflops': peak,
+                              'frac': fl / (ms * 1e-3) / 1e12 / peak,
+                              'note': 'executed 2*MAC of the 8 conv layers (real 11 channels) over the event-timed application; peak = SMs x 128 lanes x 2 x 1.965 GHz (nominal, the GPU runs ~1.65-1.9 GHz under load)'}
+    del fcn, dae, ii
+    torch.cuda.empty_cache()
+    return out
+
+
 def config4_leg(ctx):
     """train_dae.py step (config 4): rank r trains on its own batch of 10 crops; global loss denominators and the 24
     gradient matrices are all-reduced over NCCL (sharding.World)."""
@@ -542,7 +585,7 @@ def run_b200(args):
     torch, dist = ctx.torch, ctx.dist
     from iterative_inference_segm_b200.functions import jaccard_from_cm
     rank, world = ctx.rank, ctx.world
-    sections = set(args.sections.split(',')) if args.sections else {'headline', 'bf16', 'roofline', 'cpu', 'config3', 'config4', 'sweep'}
+    sections = set(args.sections.split(',')) if args.sections else {'headline', 'bf16', 'roofline', 'cpu', 'config3', 'config4', 'sweep', 'contextmod'}
     strong = args.scaling == 'strong'
     line = None
 
@@ -603,6 +646,8 @@ def run_b200(args):
                                                'parity': 'tests/test_densenet_gpu.py::test_densenet_fp32_accurate_variant_vs_oracle: probabilities within 2e-3, argmax >= 99.9 %'}
             del objs
             torch.cuda.empty_cache()
+        if 'contextmod' in sections:
+            line['contextmod'] = contextmod_leg(ctx, strong)
         if 'config4' in sections:
             line['config4'] = config4_leg(ctx)
         if rank == 0 and world == 1 and 'cpu' in sections and not args.no_cpu_baseline:
@@ -645,7 +690,7 @@ def main():
                     help='BASELINE.json config that is the headline of the line: 2 FCN8+DAE (default), 3 FC-DenseNet103+DAE, 4 train step')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='strong: a fixed set of 80 images is sharded over the ranks in whole batches')
-    ap.add_argument('--sections', default='', help='development runs: comma list of headline,bf16,roofline,cpu,config3,config4,sweep')
+    ap.add_argument('--sections', default='', help='development runs: comma list of headline,bf16,roofline,cpu,config3,config4,sweep,contextmod')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='development runs: skip the CPU oracle timing')
     ap.add_argument('--precision', default='mixed', choices=['mixed', 'bf16', 'fp32x3'],
                     help="arithmetic of the headline: mixed (parity-grade, default), bf16 (throughput variant), fp32x3 (every conv fp32-accurate)")

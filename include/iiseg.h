@@ -244,6 +244,36 @@ typedef struct iiseg_deconv_desc {
 } iiseg_deconv_desc;
 int iiseg_deconv2d_fwd(const iiseg_deconv_desc* d, void* stream);
 
+/* ---- context-module DAE: small-channel (dilated) 3x3 convolution --------
+ * models/contextmod_dae.py:72-103 (kind='contextmod'): Conv2DLayer(n_classes, 3, pad='same', flip_filters=False) on
+ * [h | y], PadLayer(32), DilatedConv2DLayer(n_classes, 3, dilation 1/2/4/8/16/1, 'valid', rectify) and a 1x1 linear
+ * DilatedConv2DLayer, all on <= 16 channels at image resolution: fp32 FMA work, exact float32 like the reference.
+ * Planar fp32 tensors.  For n < N, f < Cout, (oh, ow) in [0,OH) x [0,OW):
+ *   v = bias[f] + sum_{c,r,s} weight[c][r][s][f] * in[n][c][oh + in_h0 + r*dil][ow + in_w0 + s*dil]
+ *       (check != 0: taps outside [0,Hin) x [0,Win) read zero -- 'same' padding; check == 0: they must be inside)
+ *   v += addend[n][f][oh][ow]            (addend != NULL: planar [N,Cout,OH,OW], the hoisted W_h * h term)
+ *   out[n][f][oh + out_h0][ow + out_w0] = relu ? max(v, 0) : v          (out planar [N,Cout,Hout,Wout])
+ * weight2 != NULL fuses the 1x1 linear conv behind it: out is then fp32 NHWC16 [N,OH,OW,16] logits rows,
+ *   out[n][oh][ow][g] = bias2[g] + sum_f weight2[f][g] * (relu ? max(v_f, 0) : v_f), zero for g >= C2.
+ * weight / bias / weight2 / bias2 are HOST pointers (fp32): they are copied into the kernel's parameter block at
+ * launch (and with it into a captured CUDA graph).  Images with active[n] == 0 are skipped (active may be NULL). */
+typedef struct iiseg_ctx_conv_desc {
+  const float* in; int N, Cin, Hin, Win;
+  int in_h0, in_w0, check, dil;
+  float* out; int Cout, Hout, Wout, out_h0, out_w0, OH, OW;
+  const float* weight;               /* HOST [Cin][3][3][Cout]              */
+  const float* bias;                 /* HOST [Cout]                         */
+  const float* addend;
+  const int32_t* active;
+  int relu;
+  const float* weight2;              /* HOST [Cout][C2] or NULL             */
+  const float* bias2;                /* HOST [C2]                           */
+  int C2;
+  void* stream;
+} iiseg_ctx_conv_desc;
+int iiseg_ctx_conv_desc_size(void);
+int iiseg_ctx_conv(const iiseg_ctx_conv_desc* d);
+
 /* ---- softmax tail + iterative-inference update --------------------------
  * Channel softmax (models/fcn_up.py:154-169, models/fcn8.py:120-191) of fp32
  * NHWC16 logits [N,H,W,16] over the first C channels.

@@ -54,6 +54,18 @@ class DeconvDesc(C.Structure):
     ]
 
 
+class CtxConvDesc(C.Structure):
+    """struct iiseg_ctx_conv_desc (include/iiseg.h)."""
+    _fields_ = [
+        ('in_', C.c_void_p), ('N', C.c_int), ('Cin', C.c_int), ('Hin', C.c_int), ('Win', C.c_int),
+        ('in_h0', C.c_int), ('in_w0', C.c_int), ('check', C.c_int), ('dil', C.c_int),
+        ('out', C.c_void_p), ('Cout', C.c_int), ('Hout', C.c_int), ('Wout', C.c_int), ('out_h0', C.c_int), ('out_w0', C.c_int),
+        ('OH', C.c_int), ('OW', C.c_int),
+        ('weight', C.c_void_p), ('bias', C.c_void_p), ('addend', C.c_void_p), ('active', C.c_void_p), ('relu', C.c_int),
+        ('weight2', C.c_void_p), ('bias2', C.c_void_p), ('C2', C.c_int), ('stream', C.c_void_p),
+    ]
+
+
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/iiseg.h declares
@@ -76,6 +88,8 @@ SIGNATURES = {
     'iiseg_unpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_unpool2_mask_window_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_deconv2d_fwd': (_i, [C.POINTER(DeconvDesc), _vp]),
+    'iiseg_ctx_conv_desc_size': (_i, []),
+    'iiseg_ctx_conv': (_i, [C.POINTER(CtxConvDesc)]),
     'iiseg_update_blocks': (_i, [_i, _i]),
     'iiseg_softmax_nchw': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_softmax_update': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
@@ -121,7 +135,8 @@ def load():
         # the hand-mirrored descriptor structs must have the C layout: a stale library or an edited struct would otherwise
         # hand misaligned descriptors to the kernels
         if (C.sizeof(ConvDesc) != lib.iiseg_conv_desc_size() or ConvDesc.upd_cpad.offset != lib.iiseg_conv_desc_last_offset()
-                or C.sizeof(DeconvDesc) != lib.iiseg_deconv_desc_size()):
+                or C.sizeof(DeconvDesc) != lib.iiseg_deconv_desc_size()
+                or C.sizeof(CtxConvDesc) != lib.iiseg_ctx_conv_desc_size()):
             raise IisegError('ctypes mirror of iiseg_conv_desc / iiseg_deconv_desc does not match libiiseg.so '
                              '(conv %d vs %d bytes, last field at %d vs %d, deconv %d vs %d bytes): rebuild the library'
                              % (C.sizeof(ConvDesc), lib.iiseg_conv_desc_size(), ConvDesc.upd_cpad.offset,

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['abi.cu', 'conv_tcgen05.cu', 'pool.cu', 'update.cu', 'metrics.cu', 'layout.cu', 'deconv.cu', 'densenet.cu', 'train.cu']
+SOURCES = ['abi.cu', 'conv_tcgen05.cu', 'pool.cu', 'update.cu', 'metrics.cu', 'layout.cu', 'deconv.cu', 'densenet.cu', 'train.cu', 'contextmod.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'iiseg.h')]
 LIB = os.path.join(HERE, 'libiiseg.so')
 STAMP = os.path.join(HERE, '.libiiseg.stamp')

@@ -52,6 +52,14 @@ def function_pred_fcn(fcn):
     return pred_fcn_fn
 
 
+def _pack_h(net, h, out=None):
+    """The conditioning tensor in the layout the DAE reads: NHWC bf16 (pairs) for the tensor-core DAE_h; nets with their
+    own layout (the fp32 context module) provide pack_h."""
+    if hasattr(net, 'pack_h'):
+        return net.pack_h(h, out)
+    return K.pack_nchw(h.contiguous(), net.h_pad, out=out, split=net.split)
+
+
 class _DaeCallable(object):
     def __init__(self, dae, grad):
         self.net = dae.net
@@ -63,7 +71,7 @@ class _DaeCallable(object):
         net = self.net
         hc, _ = _to_cuda(h)
         yc, as_np = _to_cuda(y)
-        h_bf16 = K.pack_nchw(hc, net.h_pad, split=net.split)
+        h_bf16 = _pack_h(net, hc)
         y_bf16 = K.pack_nchw(yc, net.y_cpad, split=net.split)
         logits = net.logits(h_bf16, y_bf16, y_f32=yc)
         out = torch.empty_like(yc)
@@ -160,7 +168,8 @@ class IterativeInference(object):
             dev = self.net.device
             hs = self.net.h_spatial(H, W)
             st = {
-                'h': torch.zeros((B,) + hs + (self.net.cm * self.net.h_pad,), dtype=torch.bfloat16, device=dev),
+                'h': self.net.alloc_h(B, H, W) if hasattr(self.net, 'alloc_h') else
+                     torch.zeros((B,) + hs + (self.net.cm * self.net.h_pad,), dtype=torch.bfloat16, device=dev),
                 'y': torch.zeros((B, self.C, H, W), dtype=torch.float32, device=dev),
                 'y_bf16': torch.zeros((B, H, W, self.net.cm * self.net.y_cpad), dtype=torch.bfloat16, device=dev),
                 'labels': torch.zeros((B, H, W), dtype=torch.int32, device=dev),
@@ -199,7 +208,8 @@ class IterativeInference(object):
                            update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))
                 K.norm_finalize_fixed(st['norm_acc'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             else:
-                logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'])
+                kw = {'active': st['active']} if getattr(net, 'takes_active', False) else {}
+                logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'], **kw)
                 K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
                 K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             st['norm_hist'][it].copy_(st['norm'])
@@ -230,7 +240,7 @@ class IterativeInference(object):
         if h.dtype == torch.bfloat16:
             st['h'].copy_(h)
         else:
-            K.pack_nchw(h.contiguous(), self.net.h_pad, out=st['h'], split=self.net.split)
+            _pack_h(self.net, h, st['h'])
         st['y'].copy_(y0)
         K.pack_nchw(st['y'], self.net.y_cpad, out=st['y_bf16'], split=self.net.split)
         if onehot is not None:

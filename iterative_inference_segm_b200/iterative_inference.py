@@ -23,6 +23,7 @@ from . import functions as F
 from .data_loader import load_data
 from .helpers import build_experiment_name, print_results, results_values
 from .models.DAE_h import buildDAE
+from .models.contextmod_dae import buildDAE_contextmod
 from .models.fcn8 import buildFCN8
 from .models.FCDenseNet import build_fcdensenet
 
@@ -63,8 +64,13 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
                        additional_pool=dae_dict['additional_pool'], dropout=dae_dict['dropout'],
                        skip=dae_dict['skip'], unpool_type=dae_dict['unpool_type'], bn=dae_dict['bn'],
                        params=dae_params, precision=precision, stochastic_masks=stochastic_masks)
-    elif dae_dict['kind'] in ('fcn8', 'contextmod'):
-        raise NotImplementedError('DAE kind %r is outside the B200 hot path (kind=standard)' % dae_dict['kind'])
+    elif dae_dict['kind'] == 'contextmod':       # iterative_inference.py:171-177 -- the reference CLI's default kind
+        dae = buildDAE_contextmod([None] * len(dae_dict['concat_h']), None, n_classes, path_weights=loadpath or '',
+                                  model_name='dae_model_best.npz', trainable=True, load_weights=True,
+                                  noise=dae_dict['noise'], concat_h=dae_dict['concat_h'], params=dae_params,
+                                  nb_features_to_concat=fcn[0].output_shape[1])
+    elif dae_dict['kind'] == 'fcn8':
+        raise NotImplementedError('DAE kind %r is not built on the B200 path (kinds: standard, contextmod)' % dae_dict['kind'])
     else:
         raise ValueError('Unknown dae kind')
     return fcn, dae
@@ -246,8 +252,8 @@ def _literal_dict(v):
 
 def main():
     """Same flags as the reference's CLI (iterative_inference.py:329-394).  `-dae_dict` / `-training_dict` take a Python
-    dict literal; the defaults are the benchmark's DAE (kind=standard, concat_h=[pool4]) -- the reference's default
-    kind, contextmod on the input, is outside the B200 hot path and raises NotImplementedError."""
+    dict literal; the defaults are the benchmark's DAE (kind=standard, concat_h=[pool4]); the reference's default
+    (kind=contextmod, concat_h=[input]) is selected with -dae_dict "{'kind': 'contextmod', 'concat_h': ['input']}"."""
     parser = argparse.ArgumentParser(description='Iterative inference.')
     parser.add_argument('-dataset', type=str, default='camvid', help='Dataset.')
     parser.add_argument('-segmentation_net', type=str, default='fcn8', help='Segmentation network: fcn8 | densenet')

@@ -82,6 +82,28 @@ def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
     return params
 
 
+def synthetic_contextmod_params(n_classes, nb_features_to_concat=3, seed=3, out_gain=4.0):
+    """Context module (models/contextmod_dae.py:72-103): conv1 (C, nb_h + C, 3, 3), dilconv1..6 (C, C, 3, 3) and dilconv7
+    (C, C, 1, 1) in DilatedConv2DLayer's (in, out) order.  The reference starts the dilated convs at the identity
+    (IdentityInit, :61-71); the stand-in for a trained module is identity centre taps + half-scale Glorot-uniform noise
+    on every weight, biases U(-0.05, 0.05), the output conv x out_gain."""
+    gen = torch.Generator().manual_seed(seed)
+    C_ = n_classes
+    shapes = [('conv1', (C_, nb_features_to_concat + C_, 3, 3))] + [('dilconv%d' % (i + 1), (C_, C_, 3, 3)) for i in range(6)] + \
+             [('dilconv7', (C_, C_, 1, 1))]
+    params = []
+    for name, ws in shapes:
+        W = _uniform(ws, np.sqrt(6.0 / ((ws[0] + ws[1]) * int(np.prod(ws[2:])))), gen) * 0.5
+        if name != 'conv1':
+            k = ws[2] // 2
+            for i in range(ws[0]):
+                W[i, i, k, k] += 1.0
+        if name == 'dilconv7':
+            W = W * out_gain
+        params += [W, (torch.rand((C_,), generator=gen) - 0.5) * 0.1]
+    return params
+
+
 N_LAYERS_103 = [4, 5, 7, 10, 12, 15, 12, 10, 7, 5, 4]
 
 

@@ -80,3 +80,19 @@ def channel_softmax(x):
     """dimshuffle(0,2,3,1) -> reshape(N,C) -> softmax rows -> back to NCHW.
     Reference: models/fcn_up.py:154-169, models/fcn8.py:120-191."""
     return torch.softmax(x, dim=1)
+
+
+def dilated_conv2d(x, W, b, dilation, relu):
+    """lasagne.layers.DilatedConv2DLayer(num_filters, filter_size, dilation, pad=0, flip_filters=False): W has shape
+    (num_input_channels, num_filters, kh, kw) -- "first two sizes are swapped compared to a forward convolution" -- and
+    the layer computes, via the backward-pass-wrt-weights op with subsample = dilation,
+        out[n, f, i, j] = b[f] + sum_{c, r, s} W[c, f, r, s] * x[n, c, i + r*d, j + s*d]          ('valid', unflipped)
+    so the output shrinks by (k - 1) * d.  lasagne is an un-vendored dependency of the reference (README.md:17-22, Lasagne
+    0.2.dev1): restated from its published layer; used at models/contextmod_dae.py:76-103."""
+    out = F.conv2d(x, W.permute(1, 0, 2, 3).contiguous(), b, padding=0, dilation=dilation)
+    return torch.relu(out) if relu else out
+
+
+def pad_layer(x, width):
+    """lasagne.layers.PadLayer(width, val=0, batch_ndim=2): zero border on the two spatial axes (models/contextmod_dae.py:75)."""
+    return F.pad(x, (width, width, width, width))

@@ -227,3 +227,34 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
     if return_logits:
         return u
     return L.channel_softmax(u)
+
+
+# ---------------------------------------------------------------------------
+# Context-module DAE (models/contextmod_dae.py:19-138), kind='contextmod'
+# ---------------------------------------------------------------------------
+
+CONTEXTMOD_DILATIONS = (1, 2, 4, 8, 16, 1)
+
+
+def contextmod_param_shapes(n_classes, nb_features_to_concat=3):
+    """[(name, W shape, b shape)] in checkpoint order: conv1 is a Conv2DLayer (out, in, 3, 3) on [h | y]; dilconv1..7 are
+    DilatedConv2DLayers, W (in, out, k, k), the last one 1x1 (models/contextmod_dae.py:72-103)."""
+    C = n_classes
+    shapes = [('conv1', (C, nb_features_to_concat + C, 3, 3), (C,))]
+    shapes += [('dilconv%d' % (i + 1), (C, C, 3, 3), (C,)) for i in range(6)]
+    shapes.append(('dilconv7', (C, C, 1, 1), (C,)))
+    return shapes
+
+
+def contextmod_forward(params, y, h, return_logits=False):
+    """One application of the context module -> probabilities, same size as y.  deterministic=True: the
+    GaussianNoiseLayer on y is the identity (models/contextmod_dae.py:50-57); h (the image) is concatenated BEFORE y
+    (models/model_helpers.py:91-93); conv1 'same' rectify, PadLayer(32), six dilated 3x3 rectify convs, a 1x1 linear one,
+    channel softmax (out_nonlin=softmax, iterative_inference.py:176)."""
+    x = L.conv2d(torch.cat([h, y], dim=1), params[0], params[1], 'same', relu=True)
+    x = L.pad_layer(x, 32)
+    for i, d in enumerate(CONTEXTMOD_DILATIONS):
+        x = L.dilated_conv2d(x, params[2 + 2 * i], params[3 + 2 * i], d, relu=True)
+    x = L.dilated_conv2d(x, params[14], params[15], 1, relu=False)
+    assert x.shape[2:] == y.shape[2:]
+    return x if return_logits else L.channel_softmax(x)

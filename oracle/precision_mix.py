@@ -7,6 +7,7 @@ argmax agreement) against the fp32 oracle, next to the oracle's own fp32-vs-fp64
     'f32'  : the oracle's conv (what 'x3' approximates to ~2^-17)
     'x3'   : operands as (hi, lo) bf16 pairs, hi*hi + lo*hi + hi*lo, output stored as a pair
     'bf16' : operands rounded to bf16, fp32 accumulation, output stored as bf16
+    'f16'  : operands rounded to IEEE half, fp32 accumulation, output stored as half
 
     python -m oracle.precision_mix [H W N] -- prints one table per candidate mix
 
@@ -26,6 +27,10 @@ def bf(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def hf(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
 def pair(x):
     hi = bf(x)
     return hi, bf(x - hi)
@@ -38,6 +43,8 @@ def conv_mode(x, W, b, pad, mode):
         return F.conv2d(x, W, b, padding=pad)
     if mode == 'bf16':
         return F.conv2d(bf(x), bf(W), None, padding=pad) + b.view(1, -1, 1, 1)
+    if mode == 'f16':       # operands rounded to IEEE half (11 significant bits), fp32 accumulation
+        return F.conv2d(hf(x), hf(W), None, padding=pad) + b.view(1, -1, 1, 1)
     if mode == 'x3':
         xh, xl = pair(x)
         wh, wl = pair(W)
@@ -56,6 +63,8 @@ def store(x, mode):
     """What the kernel writes: bf16, the (hi, lo) pair (16 significant bits), or fp32."""
     if mode == 'bf16':
         return bf(x)
+    if mode == 'f16':
+        return hf(x)
     if mode in ('x3', 'x2a'):
         hi, lo = pair(x)
         return hi + lo
@@ -87,7 +96,7 @@ def dae_forward_mix(params, y, h, padding, down_modes, up_modes, n_pool=4, total
         u = conv_mode(u, *Wu[i], pad='same', mode=m)
         if p > 1:
             a, b = L.center_crop_pair(u, pools[p - 2])
-            u = store(a + (bf(b) if m == 'bf16' else b), m)      # bf16 expanding path: skip-sum with the hi half of the pool pair
+            u = store(a + (bf(b) if m == 'bf16' else hf(b) if m == 'f16' else b), m)      # bf16 expanding path: skip-sum with the hi half of the pool pair
         else:
             u = L.center_crop_to(u, y.shape[2], y.shape[3])
     return L.channel_softmax(u)
@@ -99,6 +108,13 @@ MIXES = {
     'down1-4-x3/rest-bf16': (['x3'] * 4 + ['bf16'] * 2, ['bf16'] * 6),
     'down1-5-x3/rest-bf16': (['x3'] * 5 + ['bf16'] * 1, ['bf16'] * 6),
     'all-bf16': (['bf16'] * 6, ['bf16'] * 6),
+    'all-f16': (['f16'] * 6, ['f16'] * 6),
+    'down-x3/up-f16': (['x3'] * 6, ['f16'] * 6),
+    'down1-2-f16,3-6-x3/up-bf16': (['f16'] * 2 + ['x3'] * 4, ['bf16'] * 6),
+    'down1-4-x3,5-6-f16/up-bf16': (['x3'] * 4 + ['f16'] * 2, ['bf16'] * 6),
+    'down1-f16,2-6-x3/up-bf16': (['f16'] + ['x3'] * 5, ['bf16'] * 6),
+    'down1-5-x3,6-f16/up-bf16': (['x3'] * 5 + ['f16'], ['bf16'] * 6),
+    'down-f16/up-bf16': (['f16'] * 6, ['bf16'] * 6),
     'down5-6-x3/rest-bf16': (['bf16'] * 4 + ['x3'] * 2, ['bf16'] * 6),
     'down2-6-x3/rest-bf16': (['bf16'] + ['x3'] * 5, ['bf16'] * 6),
     'down3-6-x3/rest-bf16': (['bf16'] * 2 + ['x3'] * 4, ['bf16'] * 6),

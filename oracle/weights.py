@@ -8,7 +8,7 @@ Checkpoint format: np.savez(path, *get_all_param_values(net)) -> arr_0..arr_k
 import numpy as np
 import torch
 
-from .nets import dae_param_shapes, fcn8_param_shapes
+from .nets import contextmod_param_shapes, dae_param_shapes, fcn8_param_shapes
 
 
 def glorot_uniform(shape, gen):
@@ -55,6 +55,25 @@ def synthetic_dae_params(n_classes, nb_features_to_concat, seed=1, n_filters=64,
         if name in ('up_conv1', 'up1'):
             W = W * out_gain
         params += [W, torch.zeros(bs)]
+    return params
+
+
+def synthetic_contextmod_params(n_classes, nb_features_to_concat=3, seed=3, out_gain=4.0):
+    """The reference initialises the dilated convs to the identity (IdentityInit, models/contextmod_dae.py:61-71) and
+    trains from there; a trained module is identity + a learned perturbation.  Synthetic stand-in: identity centre taps
+    plus Glorot-uniform noise on every weight (so each tap, channel pair and dilation contributes), small random biases,
+    `out_gain` on the 1x1 output conv for peaky probabilities."""
+    gen = torch.Generator().manual_seed(seed)
+    params = []
+    for name, ws, bs in contextmod_param_shapes(n_classes, nb_features_to_concat):
+        W = glorot_uniform(ws, gen) * 0.5
+        if name != 'conv1':
+            k = ws[2] // 2
+            for i in range(ws[0]):
+                W[i, i, k, k] += 1.0
+        if name == 'dilconv7':
+            W = W * out_gain
+        params += [W, (torch.rand(bs, generator=gen) - 0.5) * 0.1]
     return params
 
 

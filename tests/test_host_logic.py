@@ -98,6 +98,8 @@ def test_synthetic_recipe_matches_oracle_copy():
         assert torch.equal(a, b)
     for a, b in zip(S.synthetic_dae_params(11, 512, seed=1, out_gain=0.1), OW.synthetic_dae_params(11, 512, seed=1, out_gain=0.1)):
         assert torch.equal(a, b)
+    for a, b in zip(S.synthetic_contextmod_params(11, 3, seed=3), OW.synthetic_contextmod_params(11, 3, seed=3)):
+        assert torch.equal(a, b)
     for a, b in zip(S.synthetic_batch(2, 12, 16, 11, seed=7), OW.synthetic_batch(2, 12, 16, 11, seed=7)):
         assert torch.equal(a, b)
     from oracle import densenet as OD

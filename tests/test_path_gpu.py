@@ -705,3 +705,117 @@ def test_dae_conditioned_on_the_input_image(cuda, precision):
     res = IterativeInference(dae, NCLS, [NCLS]).run(X.to(cuda), y0.to(cuda), 0.05, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))
     y = res['y'].cpu()
     assert float((y - y_o).abs().max()) < tol and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
+
+
+def test_ctx_conv_kernel_vs_torch(cuda):
+    """csrc/contextmod.cu against conv2d on the same values: dilations 1..16, 'same' zero padding, the output window inside
+    a larger tensor (PadLayer interior), the hoisted addend, frozen images, the padded <16,16> instantiation and the fused
+    1x1 tail.  fp32 FMA chains in a different order than the CPU's: 1e-5 of the output scale."""
+    from iterative_inference_segm_b200 import _kernels as K
+    import torch.nn.functional as Fn
+    g = torch.Generator().manual_seed(5)
+    for (cin, cout, dil, H, W) in [(11, 11, 1, 37, 70), (11, 11, 16, 40, 97), (3, 11, 1, 21, 33), (5, 7, 4, 30, 65), (16, 16, 2, 19, 40)]:
+        x = torch.randn(3, cin, H, W, generator=g)
+        Wt = torch.randn(cin, cout, 3, 3, generator=g) / (cin * 9) ** 0.5          # DilatedConv2DLayer layout (in, out, r, s)
+        b = torch.randn(cout, generator=g)
+        wk = np.ascontiguousarray(Wt.permute(0, 2, 3, 1).numpy())
+        ref = torch.relu(Fn.conv2d(x, Wt.permute(1, 0, 2, 3), b, dilation=dil))
+        OH, OW = H - 2 * dil, W - 2 * dil
+        if OH >= 1 and OW >= 1:
+            out = torch.full((3, cout, OH + 5, OW + 9), -7.0, device=cuda)
+            act = torch.tensor([1, 0, 1], dtype=torch.int32, device=cuda)
+            K.ctx_conv(x.to(cuda), wk, b.numpy(), dil, out, relu=True, out_origin=(2, 3), size=(OH, OW), active=act)
+            got = out.cpu()
+            assert float((got[[0, 2], :, 2:2 + OH, 3:3 + OW] - ref[[0, 2]]).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+            assert float((got[1] + 7.0).abs().max()) == 0.0                        # frozen image untouched
+            got[:, :, 2:2 + OH, 3:3 + OW] = -7.0
+            assert float((got + 7.0).abs().max()) == 0.0                           # nothing outside the window
+        # 'same' zero padding + addend, linear
+        add = torch.randn(3, cout, H, W, generator=g)
+        ref = Fn.conv2d(x, Wt.permute(1, 0, 2, 3), b, dilation=dil, padding=dil) + add
+        out = torch.empty((3, cout, H, W), device=cuda)
+        K.ctx_conv(x.to(cuda), wk, b.numpy(), dil, out, relu=False, origin=(-dil, -dil), check=True, addend=add.to(cuda))
+        assert float((out.cpu() - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+        if cin != 3:
+            # fused 1x1 tail -> NHWC16 logits rows, zero beyond C2
+            c2 = min(cout, 11)
+            W2 = torch.randn(cout, c2, generator=g)
+            b2 = torch.randn(c2, generator=g)
+            ref = torch.einsum('nfhw,fg->nhwg', torch.relu(Fn.conv2d(x, Wt.permute(1, 0, 2, 3), b, dilation=dil, padding=dil)), W2) + b2
+            lg = torch.full((3, H, W, 16), 9.0, device=cuda)
+            K.ctx_conv(x.to(cuda), wk, b.numpy(), dil, lg, relu=True, origin=(-dil, -dil), check=True,
+                       tail=(np.ascontiguousarray(W2.numpy()), b2.numpy()))
+            assert float((lg[..., :c2].cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+            assert float(lg[..., c2:].abs().max()) == 0.0
+
+
+def test_contextmod_dae_vs_oracle(cuda):
+    """kind='contextmod' (models/contextmod_dae.py:19-138, the reference CLI's default DAE) through the drop-in callables:
+    buildFCN8(layer=['input', 'probs_dimshuffle']) -> pred_fcn_fn -> pred_dae_fn / de_fn / the device loop with early exit
+    and metrics, against the oracle.  The module computes in fp32 on the device as in the reference: 2e-5 on probabilities
+    (fp32 summation order), argmax identical away from exact ties."""
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.models.contextmod_dae import buildDAE_contextmod
+    from iterative_inference_segm_b200.functions import function_pred_fcn, function_pred_dae, function_de, IterativeInference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pc = weights.synthetic_contextmod_params(NCLS, 3, seed=3)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=['input', 'probs_dimshuffle'], params=pf, precision='mixed')
+    dae = buildDAE_contextmod([None], None, NCLS, concat_h=['input'], noise=0.0, params=pc,
+                              nb_features_to_concat=fcn[0].output_shape[1])
+    X, L, lab = weights.synthetic_batch(3, 45, 70, NCLS, seed=12)
+    _, y0 = nets.fcn8_forward(pf, X, NCLS)
+    p_o = nets.contextmod_forward(pc, y0, X)
+    p_d = function_pred_dae(dae)(X.numpy(), y0.numpy())
+    e = float(np.abs(p_d - p_o.numpy()).max())
+    assert e < 2e-5, e
+    g_d = function_de(dae)(X.numpy(), y0.numpy())
+    assert float(np.abs(g_d - (y0 - p_o).numpy()).max()) < 2e-5
+    # the loop: 6 iterations, step 0.5, an eps that freezes some images early (oracle.loop semantics)
+    from oracle import loop as oloop
+    step, n_it = 0.5, 6
+    ys, norms = [], []
+    for b in range(3):
+        y = y0[b:b + 1].clone()
+        nb = []
+        for _ in range(n_it):
+            gr = y - nets.contextmod_forward(pc, y, X[b:b + 1])
+            y = torch.clamp(y - step * gr, 0, 1)
+            nb.append(float(torch.linalg.vector_norm(gr, dim=1).mean()))
+        ys.append(y); norms.append(nb)
+    eps = 0.5 * (sorted(n[2] for n in norms)[0] + sorted(n[2] for n in norms)[1])      # one image stops after 3 iterations
+    res = IterativeInference(dae, NCLS, [NCLS]).run(X.to(cuda), y0.to(cuda), step, n_it, eps=eps, labels=lab.to(torch.int32).to(cuda))
+    n_exec = res['n_exec'].cpu().tolist()
+    exp_exec = [next((k + 1 for k, v in enumerate(nb) if v < eps), n_it) for nb in norms]
+    assert n_exec == exp_exec and min(n_exec) < n_it, (n_exec, exp_exec)
+    for b in range(3):
+        y = y0[b:b + 1].clone()
+        for _ in range(n_exec[b]):
+            y = torch.clamp(y - step * (y - nets.contextmod_forward(pc, y, X[b:b + 1])), 0, 1)
+        assert float((res['y'][b:b + 1].cpu() - y).abs().max()) < 5e-5
+
+
+def test_inference_script_with_the_reference_default_dae_kind(cuda, tmp_path):
+    """inference(...) with the reference CLI's default dae_dict (iterative_inference.py:355-362: kind='contextmod',
+    concat_h=['input'], step 1.0 from :341): the fused device loop equals the literal per-image loop over the callables,
+    the saved batches track the oracle, and the script-level Jaccard counts equal metrics on the oracle's output up to
+    the (fp32-accurate FCN8's) argmax disagreement."""
+    from iterative_inference_segm_b200.iterative_inference import inference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    pc = weights.synthetic_contextmod_params(NCLS, 3, seed=3)
+    dd = dict(DAE_DICT, kind='contextmod', concat_h=['input'])
+    kw = dict(dae_dict_updates=dd, savepath=str(tmp_path), loadpath=str(tmp_path), fcn_params=pf, dae_params=pc, verbose=False,
+              precision='mixed')
+    a = inference('camvid', 'fcn8', 1.0, 3, data_iter=_tiny_iter(), fused=True, save_batches=True, **kw)
+    b = inference('camvid', 'fcn8', 1.0, 3, data_iter=_tiny_iter(), fused=False, **kw)
+    assert a['n_exec'] == b['n_exec'] == [3, 3, 3]
+    assert np.array_equal(a['jacc_tot'], b['jacc_tot'])
+    it = _tiny_iter()
+    for i in range(it.nbatches):
+        X, L = it.next()
+        Xt = torch.from_numpy(X)
+        _, y = nets.fcn8_forward(pf, Xt, NCLS)
+        for _ in range(3):
+            y = torch.clamp(y - 1.0 * (y - nets.contextmod_forward(pc, y, Xt)), 0, 1)
+        saved = np.load(os.path.join(a['savepath'], 'batch%d.npz' % i))
+        assert float(np.abs(saved['Y_ii'] - y.numpy()).max()) < TOL_F32
+        assert float((saved['Y_ii'].argmax(1) == y.numpy().argmax(1)).mean()) >= MIN_ARGMAX_F32
