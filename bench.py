@@ -299,6 +299,14 @@ def build_inference(ctx, precision, segm='fcn8', kind='standard'):
         dae = buildDAE_contextmod([None], None, NCLS, concat_h=['input'], noise=0.0,
                                   params=weights.synthetic_contextmod_params(NCLS, 3, seed=3), nb_features_to_concat=3)
         return fcn, dae, IterativeInference(dae, NCLS, [NCLS])
+    if kind == 'fcn8':             # inference()'s own default kind (iterative_inference.py:64): the FCN8-shaped DAE, h = pool4
+        from iterative_inference_segm_b200.models.fcn8_dae import buildFCN8_DAE
+        fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'],
+                        params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
+        dae = buildFCN8_DAE([None], None, NCLS, nb_in_channels=NCLS, concat_h=['pool4'], noise=0.0, precision=precision,
+                            params=weights.synthetic_fcn8_params(NCLS, NCLS, seed=6, logit_gain=LOGIT_GAIN, concat=('pool4', 512)),
+                            nb_features_to_concat=512)
+        return fcn, dae, IterativeInference(dae, NCLS, [NCLS])
     if segm == 'fcn8':
         fcn = buildFCN8(3, None, n_classes=NCLS, layer=['pool4', 'probs_dimshuffle'],
                         params=weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=LOGIT_GAIN), precision=precision)
@@ -585,7 +593,7 @@ def run_b200(args):
     torch, dist = ctx.torch, ctx.dist
     from iterative_inference_segm_b200.functions import jaccard_from_cm
     rank, world = ctx.rank, ctx.world
-    sections = set(args.sections.split(',')) if args.sections else {'headline', 'bf16', 'roofline', 'cpu', 'config3', 'config4', 'sweep', 'contextmod'}
+    sections = set(args.sections.split(',')) if args.sections else {'headline', 'bf16', 'roofline', 'cpu', 'config3', 'config4', 'sweep', 'contextmod', 'fcn8dae'}
     strong = args.scaling == 'strong'
     line = None
 
@@ -648,6 +656,14 @@ def run_b200(args):
             torch.cuda.empty_cache()
         if 'contextmod' in sections:
             line['contextmod'] = contextmod_leg(ctx, strong)
+        if 'fcn8dae' in sections:
+            rk, objs = measure_inference(ctx, 'mixed', kind='fcn8', strong=strong)
+            line['fcn8_dae'] = {'workload': 'FCN8 + FCN8-shaped DAE (kind=fcn8, concat_h=pool4; a full VGG16/fc6/fc7 forward per iteration), batch 10 x 360x480, 11 classes, 50 steps, step 0.05, metrics.py Jaccard',
+                                'value': rk['value'], 'unit': 'images/s', 'ms_per_step': rk['ms_per_step'], 'e2e': rk['e2e'],
+                                'dtype': DTYPES['fp32x3'], 'executed_iterations': rk['executed_iterations'],
+                                'parity': 'tests/test_path_gpu.py::test_fcn8_shaped_dae_vs_oracle: within 2e-3 / 99.9 % of the fp32 oracle'}
+            del objs
+            torch.cuda.empty_cache()
         if 'config4' in sections:
             line['config4'] = config4_leg(ctx)
         if rank == 0 and world == 1 and 'cpu' in sections and not args.no_cpu_baseline:
@@ -690,7 +706,7 @@ def main():
                     help='BASELINE.json config that is the headline of the line: 2 FCN8+DAE (default), 3 FC-DenseNet103+DAE, 4 train step')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='strong: a fixed set of 80 images is sharded over the ranks in whole batches')
-    ap.add_argument('--sections', default='', help='development runs: comma list of headline,bf16,roofline,cpu,config3,config4,sweep,contextmod')
+    ap.add_argument('--sections', default='', help='development runs: comma list of headline,bf16,roofline,cpu,config3,config4,sweep,contextmod,fcn8dae')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='development runs: skip the CPU oracle timing')
     ap.add_argument('--precision', default='mixed', choices=['mixed', 'bf16', 'fp32x3'],
                     help="arithmetic of the headline: mixed (parity-grade, default), bf16 (throughput variant), fp32x3 (every conv fp32-accurate)")

@@ -24,6 +24,7 @@ from .data_loader import load_data
 from .helpers import build_experiment_name, print_results, results_values
 from .models.DAE_h import buildDAE
 from .models.contextmod_dae import buildDAE_contextmod
+from .models.fcn8_dae import buildFCN8_DAE
 from .models.fcn8 import buildFCN8
 from .models.FCDenseNet import build_fcdensenet
 
@@ -69,8 +70,11 @@ def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, w
                                   model_name='dae_model_best.npz', trainable=True, load_weights=True,
                                   noise=dae_dict['noise'], concat_h=dae_dict['concat_h'], params=dae_params,
                                   nb_features_to_concat=fcn[0].output_shape[1])
-    elif dae_dict['kind'] == 'fcn8':
-        raise NotImplementedError('DAE kind %r is not built on the B200 path (kinds: standard, contextmod)' % dae_dict['kind'])
+    elif dae_dict['kind'] == 'fcn8':             # iterative_inference.py:165-170
+        dae = buildFCN8_DAE([None] * len(dae_dict['concat_h']), None, n_classes, nb_in_channels=n_classes,
+                            path_weights=loadpath or '', model_name='dae_model_best.npz', trainable=True, load_weights=True,
+                            pretrained=True, pascal=False, concat_h=dae_dict['concat_h'], noise=dae_dict['noise'],
+                            params=dae_params, precision=precision, nb_features_to_concat=fcn[0].output_shape[1])
     else:
         raise ValueError('Unknown dae kind')
     return fcn, dae

@@ -38,9 +38,13 @@ class LayerHandle(object):
 
 
 class FCN8Net(object):
-    def __init__(self, nb_in_channels, n_classes, params, temperature=1.0, device='cuda', precision='bf16'):
+    def __init__(self, nb_in_channels, n_classes, params, temperature=1.0, device='cuda', precision='bf16', concat=None):
         """precision: 'bf16', or 'fp32x3' / 'mixed' (see DAENet; FCN8 has no expanding path of its own and its output
-        y0 enters y directly, so both run every layer fp32-accurate)."""
+        y0 enters y directly, so both run every layer fp32-accurate).
+        `concat` = (layer, nb_h), layer in 'input', 'pool1'..'pool4': the FCN8-shaped DAE (models/fcn8_dae.py:46-115) --
+        nb_h conditioning channels are concatenated in front of that layer's output, so the next conv has nb_h more input
+        channels.  Its h half is iteration-invariant: it is packed as a separate bias-free conv whose fp32 result
+        (`forward(h=...)`, once per batch) the conv on the other half adds in its epilogue."""
         K.require_device()
         assert precision in ('bf16', 'fp32x3', 'mixed'), precision
         self.precision = precision
@@ -54,11 +58,27 @@ class FCN8Net(object):
         P = {n: (params[2 * i], params[2 * i + 1]) for i, n in enumerate(PARAM_ORDER)}
         self.w = {}
         cin = nb_in_channels
-        for stage in VGG_STAGES:
+        self.concat, self.concat_conv, self.hproj = concat, None, None
+        if concat is not None:
+            assert concat[0] in ('input', 'pool1', 'pool2', 'pool3', 'pool4'), concat
+        pending = concat is not None and concat[0] == 'input'
+        for si, stage in enumerate(VGG_STAGES):
             for name, cout in stage:
+                Wn, bn = P[name]
+                if pending:        # W[:, :nb_h] acts on h (ConcatLayer((h, layer)), models/model_helpers.py:91-93)
+                    nb_h = concat[1]
+                    assert Wn.shape[1] == nb_h + cin, (name, tuple(Wn.shape), nb_h, cin)
+                    self.concat_conv = name
+                    self.h_pad = K.pad_channels(nb_h)        # (the fp32-out hoisted conv runs on the 64-channel-block kernels)
+                    self.w['hproj'] = pack_conv(Wn[:, :nb_h], torch.zeros_like(torch.as_tensor(bn)), [(nb_h, self.h_pad)], cout,
+                                                self.device, split=sp)
+                    Wn = Wn[:, nb_h:]
+                    pending = False
                 cpad = K.pad_channels(cin, narrow=(name == 'conv1_1'))
-                self.w[name] = pack_conv(*P[name], [(cin, cpad)], cout, self.device, split=sp)
+                self.w[name] = pack_conv(Wn, bn, [(cin, cpad)], cout, self.device, split=sp)
                 cin = cout
+            if concat is not None and concat[0] == 'pool%d' % (si + 1):
+                pending = True
         self.w['fc6'] = pack_conv(*P['fc6'], [(512, 512)], 4096, self.device, split=sp)
         self.w['fc7'] = pack_conv(*P['fc7'], [(4096, 4096)], 4096, self.device, split=sp)
         self.w['score_fr'] = pack_conv(*P['score_fr'], [(4096, 4096)], 16, self.device, split=sp)
@@ -69,27 +89,42 @@ class FCN8Net(object):
         # temperature divides upsample.W and .b (models/fcn8.py:193-198)
         self.w['upsample'] = pack_deconv16(*P['upsample'], self.device, scale=1.0 / float(temperature))
 
-    def forward(self, X, want=('pool4', 'probs_dimshuffle'), y_bf16_cpad=None):
+    def forward(self, X, want=('pool4', 'probs_dimshuffle'), y_bf16_cpad=None, x_packed=None, h=None):
         """X: NCHW fp32 CUDA (B, nb_in_channels, H, W).  Returns a dict with the
-        requested names: 'poolK' -> NHWC bf16, 'probs_dimshuffle' -> NCHW fp32, plus
-        'y_bf16' (NHWC bf16, `y_bf16_cpad` channels) when requested."""
-        B, Cin, H, W = X.shape
-        assert Cin == self.nb_in_channels
-        out = {}
+        requested names: 'poolK' -> NHWC bf16, 'probs_dimshuffle' -> NCHW fp32, 'logits' -> the fp32 NHWC16 rows in front
+        of the softmax, plus 'y_bf16' (NHWC bf16, `y_bf16_cpad` channels) when requested.
+        `x_packed`: the input already as NHWC bf16 (pairs), (B, H, W, cm*16), instead of X.
+        `h` (nets built with concat=): the packed conditioning tensor (NHWC bf16 (pairs), h_pad channels); given once per
+        batch, it refreshes the hoisted fp32 term the concat conv adds, which is kept for the following calls."""
         sp, cm = self.split, self.cm
-        if 'input' in want:          # net['input'] (models/fcn8.py:30): the image itself, the conditioning of concat_h=['input']
-            out['input'] = X
-        x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=True), split=sp)
+        out = {}
+        if x_packed is not None:
+            B, H, W, _ = x_packed.shape
+            assert x_packed.shape[3] == cm * K.pad_channels(self.nb_in_channels, narrow=True)
+            x = x_packed
+        else:
+            B, Cin, H, W = X.shape
+            assert Cin == self.nb_in_channels
+            if 'input' in want:          # net['input'] (models/fcn8.py:30): the image itself, the conditioning of concat_h=['input']
+                out['input'] = X
+            x = K.pack_nchw(X.contiguous(), K.pad_channels(Cin, narrow=True), split=sp)
+        dev = x.device
+        if self.concat is not None:
+            if h is not None:
+                pad = 100 if self.concat_conv == 'conv1_1' else 1
+                self.hproj = K.conv2d(h, *self.w['hproj'], 3, 3, pad, relu=False, out_f32=True, split=sp)
+            assert self.hproj is not None, 'FCN8 with a concatenated input: pass h= on the first call of a batch'
         for si, stage in enumerate(VGG_STAGES):
             for ci, (name, cout) in enumerate(stage):
                 Wk, bk = self.w[name]
                 pad = 100 if name == 'conv1_1' else 1
+                kw = dict(addend=self.hproj) if name == self.concat_conv else {}
                 if ci == len(stage) - 1:    # last conv of the stage: max-pool fused in the epilogue
                     oh, ow = K.conv_out_size(x.shape[1], x.shape[2], 3, 3, pad)
-                    pooled = torch.empty((B, oh // 2, ow // 2, cm * cout), dtype=torch.bfloat16, device=X.device)
+                    pooled = torch.empty((B, oh // 2, ow // 2, cm * cout), dtype=torch.bfloat16, device=dev)
                     x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, pooled=pooled, split=sp)
                 else:
-                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, split=sp)
+                    x = K.conv2d(x, Wk, bk, 3, 3, pad, relu=True, split=sp, **kw)
             out['pool%d' % (si + 1)] = x
         x = K.conv2d(x, *self.w['fc6'], 7, 7, 0, relu=True, split=sp)
         x = K.conv2d(x, *self.w['fc7'], 1, 1, 0, relu=True, split=sp)
@@ -103,10 +138,14 @@ class FCN8Net(object):
         fH, fW = (final.shape[1] - 1) * 8 + 16, (final.shape[2] - 1) * 8 + 16
         assert fH >= H and fW >= W
         logits = K.deconv16(final, *self.w['upsample'], 16, 8, window=((fH - H) // 2, (fW - W) // 2, H, W))
-        probs = torch.empty((B, self.n_classes, H, W), dtype=torch.float32, device=X.device)
+        if 'logits' in want:
+            out['logits'] = logits
+            if 'probs_dimshuffle' not in want:
+                return {k: v for k, v in out.items() if k in want}
+        probs = torch.empty((B, self.n_classes, H, W), dtype=torch.float32, device=dev)
         y_bf16 = None
         if y_bf16_cpad:
-            y_bf16 = torch.empty((B, H, W, cm * y_bf16_cpad), dtype=torch.bfloat16, device=X.device)
+            y_bf16 = torch.empty((B, H, W, cm * y_bf16_cpad), dtype=torch.bfloat16, device=dev)
         K.softmax_nchw(logits, self.n_classes, probs, y_bf16, split=sp)
         out['probs_dimshuffle'] = probs
         out['y_bf16'] = y_bf16

@@ -18,12 +18,18 @@ _VGG = [('conv1_1', 64), ('conv1_2', 64), ('conv2_1', 128), ('conv2_2', 128), ('
         ('conv5_3', 512)]
 
 
-def fcn8_shapes(nb_in_channels, n_classes):
-    """(name, W shape, b shape) of the 21 parameterised FCN8 layers (models/fcn8.py:33-110)."""
+def fcn8_shapes(nb_in_channels, n_classes, concat=None):
+    """(name, W shape, b shape) of the 21 parameterised FCN8 layers (models/fcn8.py:33-110).  `concat` = (layer, nb_h): the
+    FCN8-shaped DAE's conditioning channels in front of the named layer's consumer (models/fcn8_dae.py:46-115)."""
     out, cin = [], nb_in_channels
+    if concat is not None and concat[0] == 'input':
+        cin += concat[1]
+    last_of_stage = {'conv1_2': 'pool1', 'conv2_2': 'pool2', 'conv3_3': 'pool3', 'conv4_3': 'pool4', 'conv5_3': 'pool5'}
     for name, cout in _VGG:
         out.append((name, (cout, cin, 3, 3), (cout,)))
         cin = cout
+        if concat is not None and last_of_stage.get(name) == concat[0]:
+            cin += concat[1]
     c = n_classes
     out += [('fc6', (4096, 512, 7, 7), (4096,)), ('fc7', (4096, 4096, 1, 1), (4096,)),
             ('score_fr', (c, 4096, 1, 1), (c,)), ('score2', (c, c, 4, 4), (c,)),
@@ -61,11 +67,11 @@ def _uniform(shape, a, gen):
     return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * a
 
 
-def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
+def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0, concat=None):
     """lasagne.init.HeUniform (a = sqrt(6 / fan_in)) W, zero b; `upsample` W x logit_gain."""
     gen = torch.Generator().manual_seed(seed)
     params = []
-    for name, ws, bs in fcn8_shapes(nb_in_channels, n_classes):
+    for name, ws, bs in fcn8_shapes(nb_in_channels, n_classes, concat):
         W = _uniform(ws, np.sqrt(6.0 / int(np.prod(ws[1:]))), gen)
         params += [W * logit_gain if name == 'upsample' else W, torch.zeros(bs)]
     return params

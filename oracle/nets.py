@@ -21,16 +21,22 @@ VGG_CFG = [  # (name, out_channels) grouped per pooling stage; models/fcn8.py:33
 ]
 
 
-def fcn8_param_shapes(nb_in_channels, n_classes):
+def fcn8_param_shapes(nb_in_channels, n_classes, concat=None):
     """[(name, W shape, b shape)] in checkpoint order: 13 VGG convs, fc6, fc7,
     score_fr, score2, score_pool4, score4, score_pool3, upsample (42 arrays).
-    Conv W is (out,in,kh,kw); Deconv W is (in,out,kh,kw)."""
+    Conv W is (out,in,kh,kw); Deconv W is (in,out,kh,kw).
+    `concat` = (layer name, nb_h): the FCN8-shaped DAE (models/fcn8_dae.py:46-48,60-115) concatenates nb_h conditioning
+    channels BEFORE the named layer's output ('input', 'pool1'..'pool4'), widening the next conv's input."""
     shapes = []
     cin = nb_in_channels
-    for stage in VGG_CFG:
+    if concat is not None and concat[0] == 'input':
+        cin += concat[1]
+    for si, stage in enumerate(VGG_CFG):
         for name, cout in stage:
             shapes.append((name, (cout, cin, 3, 3), (cout,)))
             cin = cout
+        if concat is not None and concat[0] == 'pool%d' % (si + 1):
+            cin += concat[1]
     shapes.append(('fc6', (4096, 512, 7, 7), (4096,)))
     shapes.append(('fc7', (4096, 4096, 1, 1), (4096,)))
     shapes.append(('score_fr', (n_classes, 4096, 1, 1), (n_classes,)))
@@ -43,7 +49,7 @@ def fcn8_param_shapes(nb_in_channels, n_classes):
 
 
 def fcn8_forward(params, X, n_classes, layer=('pool4', 'probs_dimshuffle'),
-                 temperature=1.0):
+                 temperature=1.0, concat=None):
     """models/fcn8.py:30-130,187-200.  Returns [net[el] for el in layer].
     `temperature` divides upsample.W and .b (models/fcn8.py:193-198).
     Dropout layers are identity (deterministic=True, iterative_inference.py:187).
@@ -52,13 +58,17 @@ def fcn8_forward(params, X, n_classes, layer=('pool4', 'probs_dimshuffle'),
     P = {n: (params[2 * i], params[2 * i + 1]) for i, n in enumerate(names)}
     net = {}
     x = X
+    if concat is not None and concat[0] == 'input':       # (h, layer): ConcatLayer((h, net[layer])), models/model_helpers.py:91-93
+        x = torch.cat([concat[1], x], dim=1)
     for si, stage in enumerate(VGG_CFG):
         for ci, (name, _) in enumerate(stage):
             pad = 100 if name == 'conv1_1' else 'same'
             x = L.conv2d(x, *P[name], pad=pad, relu=True)
             net[name] = x
         x = L.maxpool2(x)
-        net['pool%d' % (si + 1)] = x
+        net['pool%d' % (si + 1)] = x               # score_pool3 / score_pool4 read the un-concatenated pool
+        if concat is not None and concat[0] == 'pool%d' % (si + 1):
+            x = torch.cat([concat[1], x], dim=1)
     x = L.conv2d(x, *P['fc6'], pad='valid', relu=True)
     net['fc6'] = x
     x = L.conv2d(x, *P['fc7'], pad='valid', relu=True)
@@ -258,3 +268,11 @@ def contextmod_forward(params, y, h, return_logits=False):
     x = L.dilated_conv2d(x, params[14], params[15], 1, relu=False)
     assert x.shape[2:] == y.shape[2:]
     return x if return_logits else L.channel_softmax(x)
+
+
+def fcn8_dae_forward(params, y, h, n_classes, concat_h=('pool4',)):
+    """kind='fcn8' (models/fcn8_dae.py:19-271): the FCN8 graph with y as its input (nb_in_channels = n_classes,
+    iterative_inference.py:166-170) and h concatenated before y at 'input' or before pool_N's output at 'poolN' -- layer for
+    layer models/fcn8.py otherwise (noise and dropout are the identity under deterministic=True).  -> probabilities."""
+    assert len(concat_h) == 1
+    return fcn8_forward(params, y, n_classes, layer=('probs_dimshuffle',), concat=(concat_h[0], h))[0]

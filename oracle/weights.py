@@ -26,13 +26,13 @@ def he_uniform(shape, gen):
     return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * a
 
 
-def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0):
+def synthetic_fcn8_params(nb_in_channels, n_classes, seed=0, logit_gain=1.0, concat=None):
     """He-uniform W, zero b.  With random weights the FCN8 logits are tiny, so
     `logit_gain` rescales the final `upsample` kernel to give peaky y0 (the
     same lever as temperature<1, models/fcn8.py:193-198)."""
     gen = torch.Generator().manual_seed(seed)
     params = []
-    for name, ws, bs in fcn8_param_shapes(nb_in_channels, n_classes):
+    for name, ws, bs in fcn8_param_shapes(nb_in_channels, n_classes, concat):
         W = he_uniform(ws, gen)
         if name == 'upsample':
             W = W * logit_gain

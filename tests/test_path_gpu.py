@@ -794,15 +794,19 @@ def test_contextmod_dae_vs_oracle(cuda):
         assert float((res['y'][b:b + 1].cpu() - y).abs().max()) < 5e-5
 
 
-def test_inference_script_with_the_reference_default_dae_kind(cuda, tmp_path):
+@pytest.mark.parametrize('kind', ['contextmod', 'fcn8'])
+def test_inference_script_with_the_other_dae_kinds(cuda, tmp_path, kind):
     """inference(...) with the reference CLI's default dae_dict (iterative_inference.py:355-362: kind='contextmod',
-    concat_h=['input'], step 1.0 from :341): the fused device loop equals the literal per-image loop over the callables,
-    the saved batches track the oracle, and the script-level Jaccard counts equal metrics on the oracle's output up to
-    the (fp32-accurate FCN8's) argmax disagreement."""
+    concat_h=['input'], step 1.0 from :341) and with inference()'s own default kind='fcn8' (:64, here with concat_h=['pool4']):
+    the fused device loop equals the literal per-image loop over the callables and the saved batches track the oracle."""
     from iterative_inference_segm_b200.iterative_inference import inference
     pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
-    pc = weights.synthetic_contextmod_params(NCLS, 3, seed=3)
-    dd = dict(DAE_DICT, kind='contextmod', concat_h=['input'])
+    if kind == 'contextmod':
+        pc = weights.synthetic_contextmod_params(NCLS, 3, seed=3)
+        dd = dict(DAE_DICT, kind='contextmod', concat_h=['input'])
+    else:
+        pc = weights.synthetic_fcn8_params(NCLS, NCLS, seed=6, logit_gain=10.0, concat=('pool4', 512))
+        dd = dict(DAE_DICT, kind='fcn8', concat_h=['pool4'])
     kw = dict(dae_dict_updates=dd, savepath=str(tmp_path), loadpath=str(tmp_path), fcn_params=pf, dae_params=pc, verbose=False,
               precision='mixed')
     a = inference('camvid', 'fcn8', 1.0, 3, data_iter=_tiny_iter(), fused=True, save_batches=True, **kw)
@@ -813,9 +817,43 @@ def test_inference_script_with_the_reference_default_dae_kind(cuda, tmp_path):
     for i in range(it.nbatches):
         X, L = it.next()
         Xt = torch.from_numpy(X)
-        _, y = nets.fcn8_forward(pf, Xt, NCLS)
+        h, y = nets.fcn8_forward(pf, Xt, NCLS)
         for _ in range(3):
-            y = torch.clamp(y - 1.0 * (y - nets.contextmod_forward(pc, y, Xt)), 0, 1)
+            p = nets.contextmod_forward(pc, y, Xt) if kind == 'contextmod' else nets.fcn8_dae_forward(pc, y, h, NCLS, concat_h=('pool4',))
+            y = torch.clamp(y - 1.0 * (y - p), 0, 1)
         saved = np.load(os.path.join(a['savepath'], 'batch%d.npz' % i))
         assert float(np.abs(saved['Y_ii'] - y.numpy()).max()) < TOL_F32
         assert float((saved['Y_ii'].argmax(1) == y.numpy().argmax(1)).mean()) >= MIN_ARGMAX_F32
+
+
+@pytest.mark.parametrize('concat_h,precision', [('pool4', 'mixed'), ('pool4', 'bf16'), ('input', 'mixed'), ('pool2', 'mixed')])
+def test_fcn8_shaped_dae_vs_oracle(cuda, concat_h, precision):
+    """kind='fcn8' (models/fcn8_dae.py:19-271): the FCN8 graph on y with h concatenated at 'input' / 'poolN', through the
+    drop-in callables and the device loop, against the oracle.  The h half of the widened conv is hoisted (computed with the
+    first iteration, reused by the next ones)."""
+    from iterative_inference_segm_b200.models.fcn8 import buildFCN8
+    from iterative_inference_segm_b200.models.fcn8_dae import buildFCN8_DAE
+    from iterative_inference_segm_b200.functions import function_pred_fcn, function_pred_dae, IterativeInference
+    pf = weights.synthetic_fcn8_params(3, NCLS, seed=0, logit_gain=10.0)
+    fcn = buildFCN8(3, None, n_classes=NCLS, layer=[concat_h, 'probs_dimshuffle'], params=pf, precision=precision)
+    nb_h = fcn[0].output_shape[1]
+    pdae = weights.synthetic_fcn8_params(NCLS, NCLS, seed=6, logit_gain=10.0, concat=(concat_h, nb_h))
+    dae = buildFCN8_DAE([None], None, NCLS, nb_in_channels=NCLS, concat_h=[concat_h], noise=0.0, params=pdae, precision=precision,
+                        nb_features_to_concat=nb_h)
+    tol, agree = (TOL_F32, MIN_ARGMAX_F32) if precision == 'mixed' else (TOL_FCN_PROBS, 0.98)
+    X, L, lab = weights.synthetic_batch(2, 32, 40, NCLS, seed=17)
+    if concat_h == 'input':
+        h_o, y0 = X, nets.fcn8_forward(pf, X, NCLS, layer=('probs_dimshuffle',))[0]
+    else:
+        h_o, y0 = nets.fcn8_forward(pf, X, NCLS, layer=(concat_h, 'probs_dimshuffle'))
+    p_o = nets.fcn8_dae_forward(pdae, y0, h_o, NCLS, concat_h=(concat_h,))
+    p_d = function_pred_dae(dae)(h_o.numpy(), y0.numpy())
+    assert float(np.abs(p_d - p_o.numpy()).max()) < tol, float(np.abs(p_d - p_o.numpy()).max())
+    y_o = y0.clone()
+    for _ in range(3):
+        y_o = torch.clamp(y_o - 0.5 * (y_o - nets.fcn8_dae_forward(pdae, y_o, h_o, NCLS, concat_h=(concat_h,))), 0, 1)
+    res = IterativeInference(dae, NCLS, [NCLS]).run(h_o.to(cuda), y0.to(cuda), 0.5, 3, eps=0.0, labels=lab.to(torch.int32).to(cuda))
+    y = res['y'].cpu()
+    print('fcn8 dae %s %s: p %.2e  y %.2e  argmax %.4f' % (concat_h, precision, float(np.abs(p_d - p_o.numpy()).max()),
+                                                         float((y - y_o).abs().max()), float((y.argmax(1) == y_o.argmax(1)).float().mean())))
+    assert float((y - y_o).abs().max()) < tol and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
