@@ -6,9 +6,8 @@
 // operands still cross HBM); the layers are fp32 FMA work on the CUDA cores, exact in the reference's float32:
 //   * activations are planar fp32 [N, C, H, W] (the layout of the loop's master y): a warp reads / writes 128
 //     contiguous bytes per channel plane, any dilation;
-//   * a thread owns two pixels (ow, ow + 32) x all COUT channels in registers; the COUT x CIN x 9 weights travel
-//     in the kernel's parameter block (constant bank), so every FFMA takes its weight as a constant operand and
-//     the inner loop is 2 loads per 2*COUT FMAs;
+//   * a thread owns four pixels (2 rows x columns ow, ow + 32) x all COUT channels in registers; the COUT x CIN x 9
+//     weights travel in the kernel's parameter block (constant bank) and the FMAs are FFMA2 on output-channel pairs;
 //   * conv1 stores straight into the interior of the zero-bordered PadLayer buffer, adding the hoisted
 //     iteration-invariant W_h * h term; the last dilated conv carries the 1x1 conv and writes the fp32 NHWC16
 //     logits rows iiseg_softmax_update consumes.
@@ -21,81 +20,117 @@ namespace iiseg {
 
 template <int CIN, int COUT>
 struct CtxParams {
+  static constexpr int CP = (COUT + 1) & ~1;         // output channels padded to whole FFMA2 pairs
   const float* in; float* out; const float* addend; const int32_t* active;
   int cin, cout;                             // real channel counts (<= CIN / COUT; the rest of w is zero)
   int Hin, Win, in_h0, in_w0, check, dil;
   int Hout, Wout, out_h0, out_w0, OH, OW;
   int relu;
-  float b[COUT];
-  float w[CIN * 9 * COUT];                   // [ci][tap][co]
+  alignas(16) float b[CP];
+  alignas(16) float w[CIN * 9 * CP];         // [ci][tap][co]
   float b2[16];
   float w2[COUT * 16];                       // [ci][co2] of the fused 1x1 tail
 };
 
-constexpr int kCtxThreads = 128;             // 4 warps = 4 output rows of 64 pixels
+constexpr int kCtxThreads = 128;             // 4 warps; a warp computes 2 output rows x 64 pixels
 
-template <int CIN, int COUT, bool kTail>
+// two IEEE fp32 FMAs per issued instruction (FFMA2, sm_100): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long dup_f32(float x) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+// The kernel is bound by instruction issue, not by memory (ncu: L2 9-16 %, DRAM < 15 %): with scalar FFMAs two thirds of
+// the issue slots are FMAs and the FMA pipe sits at 48 %.  So: a thread owns FOUR pixels (2 rows x columns ow, ow + 32)
+// x all channels, accumulators are channel PAIRS and the FMAs are FFMA2 (x duplicated into both halves, two adjacent
+// output-channel weights from the constant bank): per (input channel, tap) 4 loads + 4 moves + the weight fetches feed
+// 4 * CP/2 FFMA2 = 2 * CP FMA-pipe cycles.
+template <int CIN, int COUT, bool kTail, bool kCheck>
 __global__ void __launch_bounds__(kCtxThreads) ctx_conv_kernel(const __grid_constant__ CtxParams<CIN, COUT> P) {
+  constexpr int CP = CtxParams<CIN, COUT>::CP, NP = CP / 2;
   const int n = blockIdx.z;
   if (P.active != nullptr && P.active[n] == 0) return;        // frozen image
   const int lane = threadIdx.x & 31;
-  const int oh = blockIdx.y * (kCtxThreads / 32) + (threadIdx.x >> 5);
+  const int oh = 2 * (blockIdx.y * (kCtxThreads / 32) + (threadIdx.x >> 5));
   if (oh >= P.OH) return;
   const int ow0 = blockIdx.x * 64 + lane;
-  const bool v0 = ow0 < P.OW, v1 = ow0 + 32 < P.OW;
-  float a0[COUT], a1[COUT];
+  const bool vr[2] = {true, oh + 1 < P.OH};
+  const bool vc[2] = {ow0 < P.OW, ow0 + 32 < P.OW};
+  unsigned long long acc[4][NP];             // pixel k = 2 * row + col
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) { a0[co] = P.b[co]; a1[co] = P.b[co]; }
+  for (int j = 0; j < NP; ++j) {
+    const unsigned long long bj = *reinterpret_cast<const unsigned long long*>(&P.b[2 * j]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k][j] = bj;
+  }
   const size_t plane = static_cast<size_t>(P.Hin) * P.Win;
-  const float* inb = P.in + static_cast<size_t>(n) * P.cin * plane;
+  const float* inb = P.in + static_cast<size_t>(n) * P.cin * plane;        // warp-uniform; per-thread offsets are 32-bit
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const int ih = oh + P.in_h0 + r * P.dil;
-    const bool rok = !P.check || (ih >= 0 && ih < P.Hin);
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      const int iw = ow0 + P.in_w0 + s * P.dil;
-      const bool ok0 = v0 && rok && (!P.check || (iw >= 0 && iw < P.Win));
-      const bool ok1 = v1 && rok && (!P.check || (iw + 32 >= 0 && iw + 32 < P.Win));
-      const float* q = inb + static_cast<ptrdiff_t>(ih) * P.Win + iw;
+      const int ih = oh + P.in_h0 + r * P.dil, iw = ow0 + P.in_w0 + s * P.dil;
+      bool ok[4];
+      uint32_t off[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int y = ih + (k >> 1), x = iw + 32 * (k & 1);
+        // valid pixels of a 'valid' conv read inside the plane by construction; overhanging (never stored) pixels and,
+        // with kCheck, the taps in the zero padding are redirected to element 0 (kCheck: and contribute zero)
+        ok[k] = vr[k >> 1] && vc[k & 1] && (!kCheck || (y >= 0 && y < P.Hin && x >= 0 && x < P.Win));
+        off[k] = ok[k] ? static_cast<uint32_t>(y * P.Win + x) : 0u;
+      }
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
         if (CIN != 16 || ci < P.cin) {          // (the padded <16,16> instantiation serves any smaller channel count)
-          const float x0 = ok0 ? __ldg(q + ci * plane) : 0.f;
-          const float x1 = ok1 ? __ldg(q + ci * plane + 32) : 0.f;
+          const float* pl = inb + ci * plane;
+          unsigned long long xx[4];
 #pragma unroll
-          for (int co = 0; co < COUT; ++co) {
-            const float wv = P.w[(ci * 9 + r * 3 + s) * COUT + co];
-            a0[co] = fmaf(x0, wv, a0[co]);
-            a1[co] = fmaf(x1, wv, a1[co]);
+          for (int k = 0; k < 4; ++k) {
+            const float x = __ldg(pl + off[k]);
+            xx[k] = dup_f32(kCheck ? (ok[k] ? x : 0.f) : x);
+          }
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const unsigned long long wv = *reinterpret_cast<const unsigned long long*>(&P.w[(ci * 9 + r * 3 + s) * CP + 2 * j]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ffma2(acc[k][j], xx[k], wv);
           }
         }
       }
     }
   }
-  if constexpr (!kTail) {
-    const size_t oplane = static_cast<size_t>(P.Hout) * P.Wout;
-    float* ob = P.out + static_cast<size_t>(n) * P.cout * oplane + static_cast<size_t>(oh + P.out_h0) * P.Wout + ow0 + P.out_w0;
-    const float* ab = P.addend == nullptr ? nullptr
-                                          : P.addend + (static_cast<size_t>(n) * P.cout * P.OH + oh) * P.OW + ow0;
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-      if (COUT != 16 || co < P.cout) {
-        float r0 = a0[co], r1 = a1[co];
-        if (ab != nullptr) {
-          if (v0) r0 += __ldg(ab + static_cast<size_t>(co) * P.OH * P.OW);
-          if (v1) r1 += __ldg(ab + static_cast<size_t>(co) * P.OH * P.OW + 32);
+  for (int k = 0; k < 4; ++k) {
+    if (!(vr[k >> 1] && vc[k & 1])) continue;
+    const int ohk = oh + (k >> 1), owk = ow0 + 32 * (k & 1);
+    float a[CP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { const float2 t = unpack_f32x2(acc[k][j]); a[2 * j] = t.x; a[2 * j + 1] = t.y; }
+    if constexpr (!kTail) {
+      const size_t oplane = static_cast<size_t>(P.Hout) * P.Wout;
+      float* ob = P.out + static_cast<size_t>(n) * P.cout * oplane + static_cast<size_t>(ohk + P.out_h0) * P.Wout + owk + P.out_w0;
+      const float* ab = P.addend == nullptr ? nullptr : P.addend + (static_cast<size_t>(n) * P.cout * P.OH + ohk) * P.OW + owk;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        if (COUT != 16 || co < P.cout) {
+          float v = a[co];
+          if (ab != nullptr) v += __ldg(ab + static_cast<size_t>(co) * P.OH * P.OW);
+          if (P.relu) v = fmaxf(v, 0.f);
+          ob[co * oplane] = v;
         }
-        if (P.relu) { r0 = fmaxf(r0, 0.f); r1 = fmaxf(r1, 0.f); }
-        if (v0) ob[co * oplane] = r0;
-        if (v1) ob[co * oplane + 32] = r1;
       }
-    }
-  } else {
-    // rectify, then the 1x1 conv (dilconv7, linear) on registers; one fp32 NHWC16 logits row per pixel
-#pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      float* a = px == 0 ? a0 : a1;
+    } else {
+      // rectify, then the 1x1 conv (dilconv7, linear) on registers; one fp32 NHWC16 logits row per pixel
       float l[16];
 #pragma unroll
       for (int c2 = 0; c2 < 16; ++c2) l[c2] = P.b2[c2];
@@ -105,31 +140,31 @@ __global__ void __launch_bounds__(kCtxThreads) ctx_conv_kernel(const __grid_cons
 #pragma unroll
         for (int c2 = 0; c2 < 16; ++c2) l[c2] = fmaf(x, P.w2[co * 16 + c2], l[c2]);
       }
-      if (px == 0 ? v0 : v1) {
-        float* o = P.out + ((static_cast<size_t>(n) * P.OH + oh) * P.OW + ow0 + 32 * px) * 16;
+      float* o = P.out + ((static_cast<size_t>(n) * P.OH + ohk) * P.OW + owk) * 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg_v4(o + 4 * j, make_uint4(__float_as_uint(l[4 * j]), __float_as_uint(l[4 * j + 1]), __float_as_uint(l[4 * j + 2]),
-                                       __float_as_uint(l[4 * j + 3])));
-      }
+      for (int j = 0; j < 4; ++j)
+        stg_v4(o + 4 * j, make_uint4(__float_as_uint(l[4 * j]), __float_as_uint(l[4 * j + 1]), __float_as_uint(l[4 * j + 2]),
+                                     __float_as_uint(l[4 * j + 3])));
     }
   }
 }
 
 template <int CIN, int COUT>
 static int launch_ctx(const iiseg_ctx_conv_desc* d) {
-  static thread_local CtxParams<CIN, COUT> P;      // ~10 KB: filled here, passed to the kernel by value (constant bank)
-  static_assert(sizeof(CtxParams<CIN, COUT>) < 32000, "kernel parameter block");
+  using PT = CtxParams<CIN, COUT>;
+  constexpr int CP = PT::CP;
+  static thread_local PT P;      // ~5-11 KB: filled here, passed to the kernel by value (constant bank)
+  static_assert(sizeof(PT) < 32000, "kernel parameter block");
   P.in = d->in; P.out = d->out; P.addend = d->addend; P.active = d->active;
   P.cin = d->Cin; P.cout = d->Cout;
   P.Hin = d->Hin; P.Win = d->Win; P.in_h0 = d->in_h0; P.in_w0 = d->in_w0; P.check = d->check; P.dil = d->dil;
   P.Hout = d->Hout; P.Wout = d->Wout; P.out_h0 = d->out_h0; P.out_w0 = d->out_w0; P.OH = d->OH; P.OW = d->OW;
   P.relu = d->relu;
-  for (int co = 0; co < COUT; ++co) P.b[co] = co < d->Cout ? d->bias[co] : 0.f;
+  for (int co = 0; co < CP; ++co) P.b[co] = co < d->Cout ? d->bias[co] : 0.f;
   for (int ci = 0; ci < CIN; ++ci)
     for (int t = 0; t < 9; ++t)
-      for (int co = 0; co < COUT; ++co)
-        P.w[(ci * 9 + t) * COUT + co] = (ci < d->Cin && co < d->Cout) ? d->weight[(static_cast<size_t>(ci) * 9 + t) * d->Cout + co] : 0.f;
+      for (int co = 0; co < CP; ++co)
+        P.w[(ci * 9 + t) * CP + co] = (ci < d->Cin && co < d->Cout) ? d->weight[(static_cast<size_t>(ci) * 9 + t) * d->Cout + co] : 0.f;
   const bool tail = d->weight2 != nullptr;
   if (tail) {
     for (int c2 = 0; c2 < 16; ++c2) P.b2[c2] = c2 < d->C2 ? d->bias2[c2] : 0.f;
@@ -137,10 +172,15 @@ static int launch_ctx(const iiseg_ctx_conv_desc* d) {
       for (int c2 = 0; c2 < 16; ++c2)
         P.w2[co * 16 + c2] = (co < d->Cout && c2 < d->C2) ? d->weight2[co * d->C2 + c2] : 0.f;
   }
-  const dim3 grid(ceil_div(d->OW, 64), ceil_div(d->OH, kCtxThreads / 32), d->N);
+  const dim3 grid(ceil_div(d->OW, 64), ceil_div(d->OH, 2 * (kCtxThreads / 32)), d->N);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(d->stream);
-  if (tail) ctx_conv_kernel<CIN, COUT, true><<<grid, kCtxThreads, 0, st>>>(P);
-  else ctx_conv_kernel<CIN, COUT, false><<<grid, kCtxThreads, 0, st>>>(P);
+  if (tail) {
+    if (d->check) ctx_conv_kernel<CIN, COUT, true, true><<<grid, kCtxThreads, 0, st>>>(P);
+    else ctx_conv_kernel<CIN, COUT, true, false><<<grid, kCtxThreads, 0, st>>>(P);
+  } else {
+    if (d->check) ctx_conv_kernel<CIN, COUT, false, true><<<grid, kCtxThreads, 0, st>>>(P);
+    else ctx_conv_kernel<CIN, COUT, false, false><<<grid, kCtxThreads, 0, st>>>(P);
+  }
   IISEG_LAUNCH_CHECK();
   return 0;
 }
@@ -154,7 +194,7 @@ extern "C" int iiseg_ctx_conv(const iiseg_ctx_conv_desc* d) {
   IISEG_CHECK(d != nullptr && d->in && d->out && d->weight && d->bias, "ctx_conv: null tensor");
   IISEG_CHECK(d->N >= 1 && d->Cin >= 1 && d->Cin <= 16 && d->Cout >= 1 && d->Cout <= 16, "ctx_conv: 1..16 channels (got %d -> %d)", d->Cin, d->Cout);
   IISEG_CHECK(d->dil >= 1 && d->OH >= 1 && d->OW >= 1 && d->Hin >= 1 && d->Win >= 1, "ctx_conv: bad shape");
-  IISEG_CHECK(d->N <= 65535 && ceil_div(d->OH, 4) <= 65535, "ctx_conv: grid too large");
+  IISEG_CHECK(d->N <= 65535 && ceil_div(d->OH, 8) <= 65535, "ctx_conv: grid too large");
   if (!d->check)
     IISEG_CHECK(d->in_h0 >= 0 && d->in_w0 >= 0 && d->OH - 1 + d->in_h0 + 2 * d->dil < d->Hin && d->OW - 1 + d->in_w0 + 2 * d->dil < d->Win,
                 "ctx_conv: a 'valid' window must lie inside the input (set check for zero padding)");

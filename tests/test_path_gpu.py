@@ -714,7 +714,8 @@ def test_ctx_conv_kernel_vs_torch(cuda):
     from iterative_inference_segm_b200 import _kernels as K
     import torch.nn.functional as Fn
     g = torch.Generator().manual_seed(5)
-    for (cin, cout, dil, H, W) in [(11, 11, 1, 37, 70), (11, 11, 16, 40, 97), (3, 11, 1, 21, 33), (5, 7, 4, 30, 65), (16, 16, 2, 19, 40)]:
+    for (cin, cout, dil, H, W) in [(11, 11, 1, 37, 70), (11, 11, 16, 40, 97), (11, 11, 8, 50, 130), (11, 11, 2, 16, 65),
+                                   (3, 11, 1, 21, 33), (5, 7, 4, 30, 65), (16, 16, 2, 19, 40)]:
         x = torch.randn(3, cin, H, W, generator=g)
         Wt = torch.randn(cin, cout, 3, 3, generator=g) / (cin * 9) ** 0.5          # DilatedConv2DLayer layout (in, out, r, s)
         b = torch.randn(cout, generator=g)
