@@ -204,7 +204,30 @@ class ClockSampler(object):
                               '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
         return [p.strip() for p in out.strip().split(',')]
 
+    def _run_nvml(self):
+        """NVML in-process (about a millisecond per sample, so that even a sub-second timed region is sampled many times);
+        same fields as the nvidia-smi query."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [getattr(nv, 'nvmlClocksEventReason' + n, None) or getattr(nv, 'nvmlClocksThrottleReason' + n)
+                for n in ('HwSlowdown', 'HwThermalSlowdown', 'SwThermalSlowdown', 'SwPowerCap')]
+        limit = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+        while not self._stop.is_set():
+            r = get_reasons(h)
+            self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                ['Active' if (r & b) else 'Not Active' for b in bits] +
+                                [str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), str(limit)])
+            self._stop.wait(0.02)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass                    # no NVML binding / call refused: fall back to polling nvidia-smi
         fields = self.QUERY
         while not self._stop.is_set():
             try:

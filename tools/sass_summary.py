@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'iterative_inference_segm_b200', 'csrc', 'libiiseg.so')
-OPS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'HMMA', 'STG', 'LDG', 'SHFL']
+OPS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UTCBAR', 'SYNCS', 'HMMA', 'FFMA2', 'STG', 'LDG', 'SHFL']
 
 
 def main():
