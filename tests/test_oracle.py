@@ -210,3 +210,74 @@ def test_golden(name):
             assert np.array_equal(a, b), k
         else:
             assert np.allclose(a, b, atol=5e-5, rtol=1e-4), (k, float(np.abs(a - b).max()))
+
+
+def test_dilated_conv_is_lasagne_dilatedconv2dlayer():
+    """DilatedConv2DLayer (models/contextmod_dae.py:76-103): W is (in, out, kh, kw), unflipped, 'valid';
+    out[n, f, i, j] = b[f] + sum_{c, r, s} W[c, f, r, s] x[n, c, i + r*d, j + s*d] -- written out as loops."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 9, 11, generator=g)
+    W = torch.randn(3, 4, 3, 3, generator=g)
+    b = torch.randn(4, generator=g)
+    for d in (1, 2, 3):
+        out = L.dilated_conv2d(x, W, b, d, relu=False)
+        assert tuple(out.shape) == (2, 4, 9 - 2 * d, 11 - 2 * d)
+        ref = torch.zeros_like(out)
+        for f in range(4):
+            for c in range(3):
+                for r in range(3):
+                    for s in range(3):
+                        ref[:, f] += W[c, f, r, s] * x[:, c, r * d:r * d + out.shape[2], s * d:s * d + out.shape[3]]
+            ref[:, f] += b[f]
+        assert torch.allclose(out, ref, atol=1e-5)
+    assert float(L.dilated_conv2d(x, W, b, 2, relu=True).min()) >= 0.0
+
+
+def test_contextmod_with_identity_init_returns_its_first_conv():
+    """The reference initialises dilconv1..7 with IdentityInit (models/contextmod_dae.py:61-71, centre tap = identity, zero
+    bias): every dilated conv then returns the centre crop of its (non-negative) input, PadLayer(32) is exactly the total
+    shrink 2 * (1 + 2 + 4 + 8 + 16 + 1) = 64, and the module's logits are relu(conv1([h | y])) at the input size."""
+    C, nb_h = 5, 3
+    shapes = nets.contextmod_param_shapes(C, nb_h)
+    assert [s[0] for s in shapes] == ['conv1'] + ['dilconv%d' % i for i in range(1, 8)]
+    assert shapes[0][1] == (C, nb_h + C, 3, 3) and shapes[1][1] == (C, C, 3, 3) and shapes[7][1] == (C, C, 1, 1)
+    g = torch.Generator().manual_seed(1)
+    params = [torch.randn(shapes[0][1], generator=g) * 0.3, torch.randn(C, generator=g) * 0.1]
+    for name, ws, bs in shapes[1:]:
+        W = torch.zeros(ws)
+        for i in range(C):
+            W[i, i, ws[2] // 2, ws[3] // 2] = 1.0
+        params += [W, torch.zeros(bs)]
+    y = torch.softmax(torch.randn(2, C, 13, 17, generator=g), 1)
+    h = torch.rand(2, nb_h, 13, 17, generator=g)
+    logits = nets.contextmod_forward(params, y, h, return_logits=True)
+    ref = torch.relu(F.conv2d(torch.cat([h, y], 1), params[0], params[1], padding=1))
+    assert torch.equal(logits, ref)
+    p = nets.contextmod_forward(params, y, h)
+    assert torch.allclose(p.sum(1), torch.ones(2, 13, 17), atol=1e-6)
+
+
+@pytest.mark.parametrize('concat', ['input', 'pool2'])
+def test_fcn8_shaped_dae_concatenates_h_in_front(concat):
+    """models/fcn8_dae.py:46-48,60-115 + models/model_helpers.py:91-93: h joins IN FRONT of the layer's channels, so the widened
+    conv's W[:, :nb_h] acts on h.  With those weights zeroed the DAE equals the plain FCN8 on y; with the y part zeroed its
+    output does not depend on y's channels at that conv (checked through the parameter shapes)."""
+    C = 4
+    nb_h = 3 if concat == 'input' else 128
+    shapes = nets.fcn8_param_shapes(C, C, concat=(concat, nb_h))
+    widened = 'conv1_1' if concat == 'input' else 'conv3_1'
+    base = dict((n, ws) for n, ws, _ in nets.fcn8_param_shapes(C, C))
+    for n, ws, _ in shapes:
+        assert ws[1] == base[n][1] + (nb_h if n == widened else 0), (n, ws)
+    pdae = weights.synthetic_fcn8_params(C, C, seed=2, logit_gain=5.0, concat=(concat, nb_h))
+    idx = [n for n, _, _ in shapes].index(widened)
+    pdae[2 * idx][:, :nb_h] = 0.0
+    plain = [p.clone() for p in pdae]
+    plain[2 * idx] = pdae[2 * idx][:, nb_h:].clone()
+    g = torch.Generator().manual_seed(3)
+    y = torch.softmax(torch.randn(1, C, 32, 40, generator=g), 1)
+    hs = (32, 40) if concat == 'input' else ((32 + 198) // 4, (40 + 198) // 4)
+    h = torch.randn(1, nb_h, *hs, generator=g)
+    a = nets.fcn8_dae_forward(pdae, y, h, C, concat_h=(concat,))
+    b = nets.fcn8_forward(plain, y, C, layer=('probs_dimshuffle',))[0]
+    assert torch.allclose(a, b, atol=1e-6)
