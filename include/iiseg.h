@@ -269,6 +269,10 @@ typedef struct iiseg_ctx_conv_desc {
   const float* weight2;              /* HOST [Cout][C2] or NULL             */
   const float* bias2;                /* HOST [C2]                           */
   int C2;
+  int in_nhwc, out_nhwc;             /* != 0: `in` is channels-last [N,Hin,Win,(Cin+3)&~3] / `out` and `addend` are
+                                        [N,Hout,Wout,(Cout+3)&~3] and [N,OH,OW,(Cout+3)&~3] (pad channels read as anything
+                                        with zero weight, written as 0); the layout of the module's intermediate tensors.
+                                        in_nhwc requires check == 0 and Cin >= 4  */
   void* stream;
 } iiseg_ctx_conv_desc;
 int iiseg_ctx_conv_desc_size(void);

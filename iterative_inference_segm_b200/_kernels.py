@@ -312,23 +312,35 @@ def deconv16(x, weight, bias, k, stride, window=None, addend=None, addend_off=(0
 
 # ---- context-module DAE: small-channel (dilated) 3x3 conv on planar fp32 ---------
 def ctx_conv(x, weight, bias, dil, out, relu=True, origin=(0, 0), check=False, out_origin=(0, 0), size=None, addend=None,
-             active=None, tail=None):
-    """models/contextmod_dae.py:72-103 on the CUDA cores (csrc/contextmod.cu).  x planar fp32 [N,Cin,Hin,Win]; weight / bias
-    are HOST numpy float32 arrays ([Cin,3,3,Cout] and [Cout]): they ride in the kernel's parameter block.  `size` = (OH, OW)
-    computed; output pixel (oh, ow), tap (r, s) reads x[.., oh + origin[0] + r*dil, ow + origin[1] + s*dil] (`check`: zero
-    outside x).  out planar fp32 [N,Cout,Hout,Wout], written at `out_origin`; or with tail=(w2 [Cout,C2], b2 [C2]) the
-    1x1 linear conv is applied to the rectified result and out is the fp32 NHWC16 logits tensor [N,OH,OW,16]."""
+             active=None, tail=None, in_nhwc=False, out_nhwc=False):
+    """models/contextmod_dae.py:72-103 on the CUDA cores (csrc/contextmod.cu).  x planar fp32 [N,Cin,Hin,Win], or with
+    `in_nhwc` channels-last [N,Hin,Win,pad4(Cin)]; weight / bias are HOST numpy float32 arrays ([Cin,3,3,Cout] and [Cout]):
+    they ride in the kernel's parameter block.  `size` = (OH, OW) computed; output pixel (oh, ow), tap (r, s) reads
+    x[.., oh + origin[0] + r*dil, ow + origin[1] + s*dil] (`check`: zero outside x).  out planar fp32 [N,Cout,Hout,Wout]
+    (`out_nhwc`: [N,Hout,Wout,pad4(Cout)], as is `addend` then), written at `out_origin`; or with tail=(w2 [Cout,C2], b2 [C2])
+    the 1x1 linear conv is applied to the rectified result and out is the fp32 NHWC16 logits tensor [N,OH,OW,16]."""
     import numpy as np
     _chk(x, F32, 'x')
     _chk(out, F32, 'out')
-    N, Cin, Hin, Win = x.shape
-    assert isinstance(weight, np.ndarray) and weight.dtype == np.float32 and weight.flags['C_CONTIGUOUS'] and weight.shape[0] == Cin \
+    Cin = weight.shape[0]
+    pad4 = lambda c: (c + 3) & ~3          # noqa: E731
+    if in_nhwc:
+        N, Hin, Win, cpi = x.shape
+        assert cpi == pad4(Cin), (tuple(x.shape), Cin)
+    else:
+        N, c_, Hin, Win = x.shape
+        assert c_ == Cin, (tuple(x.shape), Cin)
+    assert isinstance(weight, np.ndarray) and weight.dtype == np.float32 and weight.flags['C_CONTIGUOUS'] \
         and weight.shape[1:3] == (3, 3), 'weight: host float32 [Cin,3,3,Cout]'
     Cout = weight.shape[3]
     assert isinstance(bias, np.ndarray) and bias.dtype == np.float32 and bias.shape == (Cout,)
     if tail is None:
-        assert out.shape[0] == N and out.shape[1] == Cout
-        Hout, Wout = out.shape[2], out.shape[3]
+        if out_nhwc:
+            assert out.shape[0] == N and out.shape[3] == pad4(Cout), (tuple(out.shape), Cout)
+            Hout, Wout = out.shape[1], out.shape[2]
+        else:
+            assert out.shape[0] == N and out.shape[1] == Cout
+            Hout, Wout = out.shape[2], out.shape[3]
         OH, OW = size if size is not None else (Hout, Wout)
         w2 = b2 = None
         C2 = 0
@@ -341,14 +353,14 @@ def ctx_conv(x, weight, bias, dil, out, relu=True, origin=(0, 0), check=False, o
         Hout, Wout = OH, OW
     if addend is not None:
         _chk(addend, F32, 'addend')
-        assert tuple(addend.shape) == (N, Cout, OH, OW)
+        assert tuple(addend.shape) == ((N, OH, OW, pad4(Cout)) if out_nhwc else (N, Cout, OH, OW))
     d = _lib.CtxConvDesc(in_=x.data_ptr(), N=N, Cin=Cin, Hin=Hin, Win=Win, in_h0=origin[0], in_w0=origin[1], check=int(check),
                          dil=dil, out=out.data_ptr(), Cout=Cout, Hout=Hout, Wout=Wout, out_h0=out_origin[0],
                          out_w0=out_origin[1], OH=OH, OW=OW, weight=weight.ctypes.data, bias=bias.ctypes.data,
                          addend=addend.data_ptr() if addend is not None else None,
                          active=active.data_ptr() if active is not None else None, relu=int(relu),
                          weight2=w2.ctypes.data if w2 is not None else None, bias2=b2.ctypes.data if b2 is not None else None,
-                         C2=C2, stream=torch.cuda.current_stream().cuda_stream)
+                         C2=C2, in_nhwc=int(in_nhwc), out_nhwc=int(out_nhwc), stream=torch.cuda.current_stream().cuda_stream)
     _lib.call('iiseg_ctx_conv', C.byref(d))
     return out
 

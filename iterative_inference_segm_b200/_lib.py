@@ -62,7 +62,7 @@ class CtxConvDesc(C.Structure):
         ('out', C.c_void_p), ('Cout', C.c_int), ('Hout', C.c_int), ('Wout', C.c_int), ('out_h0', C.c_int), ('out_w0', C.c_int),
         ('OH', C.c_int), ('OW', C.c_int),
         ('weight', C.c_void_p), ('bias', C.c_void_p), ('addend', C.c_void_p), ('active', C.c_void_p), ('relu', C.c_int),
-        ('weight2', C.c_void_p), ('bias2', C.c_void_p), ('C2', C.c_int), ('stream', C.c_void_p),
+        ('weight2', C.c_void_p), ('bias2', C.c_void_p), ('C2', C.c_int), ('in_nhwc', C.c_int), ('out_nhwc', C.c_int), ('stream', C.c_void_p),
     ]
 
 

@@ -5,7 +5,8 @@
 
 h is the image (concat_h=['input'], the only value the reference accepts: models/contextmod_dae.py:42); the context
 module keeps the image resolution.  Every layer has n_classes channels, so this is fp32 CUDA-core work (csrc/contextmod.cu),
-exact float32 like the reference: planar fp32 activations, the weights in the kernels' parameter blocks.  Per application:
+exact float32 like the reference: fp32 activations (the master y and the image are read as planar NCHW, the module's own
+tensors are channels-last with 12 channels), the weights in the kernels' parameter blocks.  Per application:
 conv1 (+ the hoisted, iteration-invariant W_h * h term, computed once per batch) writes into the interior of the
 zero-bordered PadLayer buffer, five dilated convs ping-pong between two buffers, and the sixth carries the 1x1 conv and
 writes the fp32 NHWC16 logits the loop's softmax / update kernel consumes.  Frozen images (active == 0) are skipped.
@@ -77,11 +78,12 @@ class ContextModNet(object):
         ws = self._ws.get(key)
         if ws is None:
             C_, dev = self.n_classes, self.device
-            n = B * C_ * (H + 2 * PAD) * (W + 2 * PAD)
-            ws = {'padded': torch.zeros((B, C_, H + 2 * PAD, W + 2 * PAD), dtype=torch.float32, device=dev),   # border = PadLayer zeros
+            c4 = (C_ + 3) & ~3          # the module's own tensors are channels-last, channels padded to whole 16-byte accesses
+            n = B * c4 * (H + 2 * PAD) * (W + 2 * PAD)
+            ws = {'padded': torch.zeros((B, H + 2 * PAD, W + 2 * PAD, c4), dtype=torch.float32, device=dev),   # border = PadLayer zeros
                   'ping': torch.empty((n,), dtype=torch.float32, device=dev),
                   'pong': torch.empty((n,), dtype=torch.float32, device=dev),
-                  'hproj': torch.empty((B, C_, H, W), dtype=torch.float32, device=dev),
+                  'hproj': torch.empty((B, H, W, c4), dtype=torch.float32, device=dev),
                   'logits': torch.empty((B, H, W, 16), dtype=torch.float32, device=dev)}
             self._ws[key] = ws
         return ws
@@ -106,21 +108,22 @@ class ContextModNet(object):
         assert C_ == self.n_classes and tuple(h.shape) == (B, self.nb_h, H, W), (tuple(h.shape), tuple(y_f32.shape))
         ws = self.workspace(B, H, W)
         if full_down:
-            K.ctx_conv(h, self.w_h, self.zero_b, 1, ws['hproj'], relu=False, origin=(-1, -1), check=True)
+            K.ctx_conv(h, self.w_h, self.zero_b, 1, ws['hproj'], relu=False, origin=(-1, -1), check=True, out_nhwc=True)
         K.ctx_conv(y_f32, self.w_y, self.b1, 1, ws['padded'], relu=True, origin=(-1, -1), check=True, out_origin=(PAD, PAD),
-                   size=(H, W), addend=ws['hproj'], active=active)
+                   size=(H, W), addend=ws['hproj'], active=active, out_nhwc=True)
         x, s = ws['padded'], 2 * PAD
+        c4 = (C_ + 3) & ~3
         bufs = (ws['ping'], ws['pong'])
         for i, d in enumerate(DILATIONS):
             s -= 2 * d
             Wk, bk = self.dil[i]
             if i < 5:
-                out = bufs[i & 1][:B * C_ * (H + s) * (W + s)].view(B, C_, H + s, W + s)
-                K.ctx_conv(x, Wk, bk, d, out, relu=True, active=active)
+                out = bufs[i & 1][:B * c4 * (H + s) * (W + s)].view(B, H + s, W + s, c4)
+                K.ctx_conv(x, Wk, bk, d, out, relu=True, active=active, in_nhwc=True, out_nhwc=True)
                 x = out
             else:
                 assert s == 0
-                K.ctx_conv(x, Wk, bk, d, ws['logits'], relu=True, tail=(self.w7, self.b7), active=active)
+                K.ctx_conv(x, Wk, bk, d, ws['logits'], relu=True, tail=(self.w7, self.b7), active=active, in_nhwc=True)
         return ws['logits']
 
 

@@ -748,6 +748,35 @@ def test_ctx_conv_kernel_vs_torch(cuda):
                        tail=(np.ascontiguousarray(W2.numpy()), b2.numpy()))
             assert float((lg[..., :c2].cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
             assert float(lg[..., c2:].abs().max()) == 0.0
+        # channels-last tensors (the module's intermediate layout): [N,H,W,pad4(C)], pad channels of the input hold garbage
+        # (they have no weights), pad channels of the output are written as zero
+        if cin >= 4 and OH >= 1 and OW >= 1:
+            ci4, co4 = (cin + 3) & ~3, (cout + 3) & ~3
+            xcl = torch.full((3, H, W, ci4), 123.0)
+            xcl[..., :cin] = x.permute(0, 2, 3, 1)
+            ref = torch.relu(Fn.conv2d(x, Wt.permute(1, 0, 2, 3), b, dilation=dil))
+            add = torch.randn(3, OH, OW, co4, generator=g)
+            add[..., cout:] = 0
+            refa = torch.relu(Fn.conv2d(x, Wt.permute(1, 0, 2, 3), b, dilation=dil) + add[..., :cout].permute(0, 3, 1, 2))
+            ocl = torch.full((3, OH + 4, OW + 6, co4), -7.0, device=cuda)
+            K.ctx_conv(xcl.to(cuda), wk, b.numpy(), dil, ocl, relu=True, out_origin=(1, 2), size=(OH, OW), in_nhwc=True, out_nhwc=True,
+                       addend=add.to(cuda))
+            got = ocl.cpu()[:, 1:1 + OH, 2:2 + OW]
+            assert float((got[..., :cout].permute(0, 3, 1, 2) - refa).abs().max()) < 1e-5 * max(1.0, float(refa.abs().max()))
+            assert co4 == cout or float(got[..., cout:].abs().max()) == 0.0
+            opl = torch.empty((3, cout, OH, OW), device=cuda)           # channels-last in, planar out
+            K.ctx_conv(xcl.to(cuda), wk, b.numpy(), dil, opl, relu=True, in_nhwc=True)
+            assert float((opl.cpu() - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+            ocl2 = torch.empty((3, OH, OW, co4), device=cuda)           # planar in, channels-last out
+            K.ctx_conv(x.to(cuda), wk, b.numpy(), dil, ocl2, relu=True, out_nhwc=True)
+            assert float((ocl2.cpu()[..., :cout].permute(0, 3, 1, 2) - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+            c2 = min(cout, 11)
+            W2 = torch.randn(cout, c2, generator=g)
+            b2 = torch.randn(c2, generator=g)
+            reft = torch.einsum('nfhw,fg->nhwg', ref, W2) + b2
+            lg = torch.empty((3, OH, OW, 16), device=cuda)
+            K.ctx_conv(xcl.to(cuda), wk, b.numpy(), dil, lg, relu=True, in_nhwc=True, tail=(np.ascontiguousarray(W2.numpy()), b2.numpy()))
+            assert float((lg[..., :c2].cpu() - reft).abs().max()) < 2e-5 * max(1.0, float(reft.abs().max()))
 
 
 def test_contextmod_dae_vs_oracle(cuda):
