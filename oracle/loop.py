@@ -18,18 +18,19 @@ def de_fn(params, h, y, padding, **dae_kw):
 
 def iterate_image(params, h_im, y_im, step, num_iter, padding, eps=EPSILON,
                   t_im=None, n_classes=None, void_labels=(), record=False,
-                  **dae_kw):
+                  forward=None, **dae_kw):
     """Per-image loop (iterative_inference.py:265-280):
         grad = de_fn(h, y); y = clip(y - step*grad, 0, 1)
         norm = mean_{b,h,w} ||grad||_2 over channels; break if norm < eps
         (the break is after the update and before that iteration's val_fn).
     Returns (y, n_executed, per_iter) where per_iter[it] = (acc, jacc, mse) of
-    the iterations that reached val_fn; `record` additionally keeps y and p."""
+    the iterations that reached val_fn; `record` additionally keeps y and p.
+    `forward(y, h) -> p` replaces DAE_h by another DAE kind (contextmod, fcn8: iterative_inference.py:165-179)."""
     y = y_im.clone()
     per_iter, trace = [], []
     n_exec = 0
     for it in range(num_iter):
-        p = dae_forward(params, y, h_im, padding, **dae_kw)
+        p = forward(y, h_im) if forward is not None else dae_forward(params, y, h_im, padding, **dae_kw)
         grad = y - p
         y = torch.clamp(y - step * grad, 0.0, 1.0)
         n_exec += 1
@@ -44,7 +45,7 @@ def iterate_image(params, h_im, y_im, step, num_iter, padding, eps=EPSILON,
 
 
 def inference_batch(params_dae, H, Y, step, num_iter, padding, L=None,
-                    n_classes=None, void_labels=(), eps=EPSILON, **dae_kw):
+                    n_classes=None, void_labels=(), eps=EPSILON, forward=None, **dae_kw):
     """One batch of iterative_inference.py:258-291: per-image loops, then the
     batch-level val_fn on the concatenated result.  Also accumulates the
     valid-script matrix valid_mat[:, :, it] += jacc_iter
@@ -57,7 +58,7 @@ def inference_batch(params_dae, H, Y, step, num_iter, padding, L=None,
         y, n_exec, per_iter, _ = iterate_image(
             params_dae, H[im:im + 1], Y[im:im + 1], step, num_iter, padding,
             eps=eps, t_im=t_im, n_classes=n_classes, void_labels=void_labels,
-            **dae_kw)
+            forward=forward, **dae_kw)
         outs.append(y)
         n_execs.append(n_exec)
         if L is not None:

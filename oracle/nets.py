@@ -149,6 +149,16 @@ def batchnorm_deterministic(x, beta, gamma, mean, inv_std):
     return (x - v(mean)) * (v(gamma) * v(inv_std)) + v(beta)
 
 
+def batchnorm_batch_stats(x, beta, gamma, epsilon=1e-4):
+    """lasagne BatchNormLayer with deterministic=False: normalises with the mean and the biased variance of the current
+    batch over (batch, rows, cols), inv_std = 1 / sqrt(var + 1e-4); the stored averages are not read (and not updated: the
+    reference collects no updates at inference)."""
+    v = lambda a: a.view(1, -1, 1, 1)          # noqa: E731
+    mean = x.mean(dim=(0, 2, 3))
+    inv_std = 1.0 / torch.sqrt(x.var(dim=(0, 2, 3), unbiased=False) + epsilon)
+    return (x - v(mean)) * (v(gamma) * v(inv_std)) + v(beta)
+
+
 def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
                 return_logits=False, unpool_type='trackind', bn=False, mask_source_y=None, skip=True,
                 conv_before_pool=1):
@@ -207,13 +217,22 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         pools.append(x)
         if p + 1 == n_pool and n_pool > 0:
             x = torch.cat([h, x], dim=1)
-    if mask_source_y is not None:          # the non-deterministic mask sub-graph: same weights, noised input
-        xm, pre = mask_source_y, []
+    if mask_source_y is not None or (bn and unpool_type == 'trackind'):
+        # DePool2D's own sub-graph, built by get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93): same
+        # weights, the noised input when noise > 0, and -- deterministic being False there -- every BatchNormLayer on the
+        # statistics of ITS OWN BATCH (lasagne: batch_norm_use_averages defaults to `deterministic`), not on the stored
+        # averages.  Found by running the reference (tests/golden/ref_bn.npz); 'inverse' (InverseLayer) receives the
+        # deterministic expressions and is not affected.
+        xm, pre = (y if mask_source_y is None else mask_source_y), []
+        if concat_h[-1] == 'input':
+            xm = torch.cat([h, xm], dim=1)
         for p in range(total):
             first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input' and padding > 0)
             xm = L.conv2d(xm, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+            for We in Wd_extra[p]:
+                xm = L.conv2d(xm, *We, pad='same', relu=True)
             if BNd[p] is not None:
-                xm = batchnorm_deterministic(xm, *BNd[p])
+                xm = batchnorm_batch_stats(xm, BNd[p][0], BNd[p][1])
             pre.append(xm)
             xm = L.maxpool2(xm)
             if p + 1 == n_pool and n_pool > 0:

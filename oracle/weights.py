@@ -95,3 +95,21 @@ def synthetic_batch(B, H, W, n_classes=11, seed=0):
     lab = torch.randint(0, n_classes + 1, (B, H, W), generator=gen)
     L = torch.nn.functional.one_hot(lab, n_classes + 1).permute(0, 3, 1, 2).float()
     return X, L.contiguous(), lab
+
+
+def with_batchnorm(pd, n_levels, unpool_type, seed=21):
+    """Insert BatchNormLayer parameters (beta, gamma, mean, inv_std -- lasagne's order) behind every conv of a DAE_h
+    checkpoint, as bn=1 saves them (models/fcn_down.py:113-115, models/fcn_up.py:91-93; none behind the 'standard'
+    deconvolutions); a few negative gammas so that nothing relies on a sign."""
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(2 * n_levels):
+        W, b = pd[2 * i], pd[2 * i + 1]
+        out += [W, b]
+        if i >= n_levels and unpool_type == 'standard':
+            continue
+        c = b.shape[0]
+        gamma = 0.5 + torch.rand(c, generator=gen)
+        gamma[::7] *= -1.0
+        out += [0.1 * torch.randn(c, generator=gen), gamma, 0.05 * torch.randn(c, generator=gen), 0.5 + 1.5 * torch.rand(c, generator=gen)]
+    return out

@@ -1,0 +1,212 @@
+"""Generates tests/golden/ref_*.npz by EXECUTING THE REFERENCE'S OWN SOURCES (read from /root/reference, unmodified) in this
+container -- outputs of the reference itself, not of the oracle restatement.
+
+    python -m tests.golden.make_reference_golden            # needs /root/reference; the fixtures it writes are committed
+
+How: oracle/refrun installs stand-ins for `theano` and `lasagne` (neither is installable here: Python 2, README.md:17-22) and
+an import hook that loads the reference's Python-2 modules in memory.  This script then calls the reference's drivers,
+
+    iterative_inference.py:inference()            (FCN8 -> pred_dae_fn -> per-image loop -> val_fn; writes batch<i>.npz)
+    iterative_inference_valid.py:inference()      (the same loop + valid_mat; writes iterations<step>.npz)
+
+which build the nets with models/fcn8.py:buildFCN8, models/DAE_h.py:buildDAE (fcn_down / fcn_up / model_helpers /
+layers/mylayers.py), models/contextmod_dae.py:buildDAE_contextmod, models/fcn8_dae.py:buildFCN8_DAE, load the checkpoints with
+lasagne.layers.set_all_param_values, compile pred_fcn_fn / pred_dae_fn / de_fn / val_fn (metrics.py) and run the loop body.
+What is supplied from outside the reference: the dataset iterator (dataset_loaders is an absent dependency; a seeded
+synthetic CamVid-shaped iterator with the attributes iterative_inference.py:117-125 reads) and the checkpoints (seeded
+synthetic weights from oracle/weights.py, saved positionally as np.savez(*params), the format train_dae.py:436-445 writes).
+Nothing from /root/reference is copied; only the arrays the reference computed are stored.
+
+Each fixture stores the case description (json), the arrays the reference saved (`Y_ii`, `Y_fcn`, `valid_mat`, `res`) and its
+captured stdout (per-iteration `rec acc jaccard` lines and the print_results blocks).  Inputs and weights are regenerated
+from the seeds in the description.
+"""
+import contextlib
+import getpass
+import io
+import json
+import os
+import shutil
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WORK = os.path.join(HERE, '_work')
+NCLS = 11
+
+TRAINING_DICT = {'training_loss': ['crossentropy', 'squared_error'], 'learning_rate': 0.001, 'lr_anneal': 0.99,
+                 'weight_decay': 0.0001, 'optimizer': 'rmsprop'}
+
+
+def dae_dict(**kw):
+    d = {'kind': 'standard', 'dropout': 0, 'skip': True, 'unpool_type': 'trackind', 'noise': 0, 'concat_h': ['pool4'],
+         'from_gt': False, 'n_filters': 64, 'conv_before_pool': 1, 'additional_pool': 2, 'path_weights': '',
+         'layer': 'probs_dimshuffle', 'exp_name': 'ref_', 'bn': 0}
+    d.update(kw)
+    return d
+
+
+# name -> description.  `dae` = dae_dict passed to the reference; `weights` = how the synthetic checkpoint is drawn
+# (tests/test_oracle.py:_reference_case_params rebuilds it from this); sizes are small so that the whole file regenerates in
+# a few minutes on CPU and each fixture replays in seconds.
+CASES = {
+    'ref_standard_trackind': dict(script='inference', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, num_iter=6, step=0.05,
+                                  weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_valid_trackind': dict(script='valid', dae=dae_dict(), H=37, W=45, B=2, nbatches=2, num_iter=5, step=0.1,
+                               weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_early_exit': dict(script='valid', dae=dae_dict(), H=32, W=40, B=2, nbatches=1, num_iter=8, step=0.5,
+                           weights=dict(fn='dae', seed=1, out_gain=0.002)),
+    'ref_unpool_standard': dict(script='inference', dae=dae_dict(unpool_type='standard'), H=32, W=40, B=2, nbatches=1, num_iter=4,
+                                step=0.05, weights=dict(fn='dae', seed=4, out_gain=0.1)),
+    'ref_unpool_inverse': dict(script='inference', dae=dae_dict(unpool_type='inverse'), H=32, W=40, B=2, nbatches=1, num_iter=4,
+                               step=0.05, weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_noskip': dict(script='inference', dae=dae_dict(skip=False), H=32, W=40, B=2, nbatches=1, num_iter=4, step=0.05,
+                       weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_bn': dict(script='inference', dae=dae_dict(bn=1), H=37, W=45, B=2, nbatches=1, num_iter=4, step=0.05,
+                   weights=dict(fn='dae', seed=1, out_gain=0.1, bn_seed=21)),
+    'ref_conv_before_pool2': dict(script='inference', dae=dae_dict(conv_before_pool=2), H=32, W=40, B=2, nbatches=1, num_iter=4,
+                                  step=0.05, weights=dict(fn='dae', seed=6, out_gain=0.1)),
+    'ref_concat_input': dict(script='inference', dae=dae_dict(concat_h=['input'], additional_pool=3), H=32, W=40, B=2, nbatches=1,
+                             num_iter=4, step=0.05, weights=dict(fn='dae', seed=8, out_gain=0.1)),
+    'ref_contextmod': dict(script='inference', dae=dae_dict(kind='contextmod', concat_h=['input']), H=32, W=40, B=2, nbatches=1,
+                           num_iter=4, step=0.05, weights=dict(fn='contextmod', seed=3)),
+    'ref_fcn8_dae': dict(script='inference', dae=dae_dict(kind='fcn8', concat_h=['pool4']), H=32, W=40, B=1, nbatches=1, num_iter=3,
+                         step=0.05, weights=dict(fn='fcn8_dae', seed=6, logit_gain=10.0)),
+    'ref_temperature': dict(script='fcn8_only', temperature=2.5, H=32, W=40, B=2, nbatches=1),
+}
+
+FCN8_WEIGHTS = dict(seed=0, logit_gain=10.0)
+
+
+def case_dae_params(case):
+    """The synthetic DAE checkpoint of a case, as a list of torch tensors in the reference's positional order."""
+    from oracle import weights
+    w, d = case['weights'], case['dae']
+    if w['fn'] == 'contextmod':
+        return weights.synthetic_contextmod_params(NCLS, 3, seed=w['seed'])
+    if w['fn'] == 'fcn8_dae':
+        return weights.synthetic_fcn8_params(NCLS, NCLS, seed=w['seed'], logit_gain=w['logit_gain'], concat=(d['concat_h'][0], 512))
+    nb_h = 3 if d['concat_h'][-1] == 'input' else 512
+    pd = weights.synthetic_dae_params(NCLS, nb_h, seed=w['seed'], out_gain=w['out_gain'], concat_h=tuple(d['concat_h']),
+                                      additional_pool=d['additional_pool'], unpool_type=d['unpool_type'],
+                                      conv_before_pool=d['conv_before_pool'], n_filters=d['n_filters'])
+    if d['bn']:
+        n_levels = (int(d['concat_h'][-1][-1]) if 'pool' in d['concat_h'][-1] else 0) + d['additional_pool']
+        pd = weights.with_batchnorm(pd, n_levels, d['unpool_type'], seed=w['bn_seed'])
+    return pd
+
+
+def case_batch(case, i):
+    """Batch i of a case: (X, L one-hot with the void channel) as numpy float32 (oracle/weights.py:synthetic_batch)."""
+    from oracle import weights
+    X, L, _ = weights.synthetic_batch(case['B'], case['H'], case['W'], NCLS, seed=100 + i)
+    return X.numpy(), L.numpy()
+
+
+class SyntheticCamvidIterator(object):
+    """The attributes and the `next()` protocol iterative_inference.py:117-125,249 use from a dataset_loaders iterator."""
+
+    def __init__(self, case):
+        self.case = case
+        self.cmap = np.zeros((NCLS + 1, 3), np.float32)
+        self.nbatches = case['nbatches']
+        self.non_void_nclasses = NCLS
+        self.void_labels = [NCLS]
+        self.data_shape = (3, case['H'], case['W'])
+        self.mask_labels = ['class%d' % i for i in range(NCLS)] + ['void']
+        self.i = 0
+
+    def next(self):
+        X, L = case_batch(self.case, self.i % self.nbatches)
+        self.i += 1
+        return X, L
+
+    __next__ = next
+
+
+def install_environment():
+    """Stand-ins for what the reference imports besides its own modules."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.refrun import py2import
+    py2import.install()
+    getpass.getuser = lambda: 'romerosa'          # iterative_inference.py:31-51 raises for unknown users
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    current = {}
+    module('data_loader', load_data=lambda dataset, *a, **kw: SyntheticCamvidIterator(current['case']))
+    module('distutils', dir_util=module('distutils.dir_util', copy_tree=lambda *a, **kw: None))      # removed in Python 3.12
+    module('skimage', color=module('skimage.color', rgb2gray=None, gray2rgb=None), img_as_float=None)
+    module('seaborn')
+    module('FC_DenseNet', layers=module('FC_DenseNet.layers', BN_ReLU_Conv=None, TransitionDown=None, TransitionUp=None,
+                                        SoftmaxLayer=None))                                           # un-vendored dependency
+    return current
+
+
+def run_case(name, case, current):
+    from oracle import weights
+    current['case'] = case
+    shutil.rmtree(WORK, ignore_errors=True)
+    wdir = os.path.join(WORK, 'weights', 'camvid')
+    os.makedirs(wdir)
+    weights.save_npz(os.path.join(wdir, 'fcn8_model.npz'), weights.synthetic_fcn8_params(3, NCLS, **FCN8_WEIGHTS))
+    out = {'case': np.array(json.dumps(case))}
+    buf = io.StringIO()
+    if case['script'] == 'fcn8_only':
+        # models/fcn8.py:193-198 (temperature): the builder itself, called as iterative_inference.py:135-139 calls it
+        import lasagne
+        import theano
+        import theano.tensor as T
+        from models.fcn8 import buildFCN8
+        x = T.tensor4('input_x_var')
+        with contextlib.redirect_stdout(buf):
+            fcn = buildFCN8(3, input_var=x, n_classes=NCLS, void_labels=[NCLS], path_weights=os.path.join(wdir, 'fcn8_model.npz'),
+                            trainable=False, load_weights=True, layer=['pool4', 'probs_dimshuffle'], temperature=case['temperature'])
+            fn = theano.function([x], lasagne.layers.get_output(fcn, deterministic=True, batch_norm_use_averages=False))
+            h, y = fn(case_batch(case, 0)[0])
+        out.update(pool4=h, Y_fcn=y)
+    else:
+        import helpers
+        mod = __import__('iterative_inference' if case['script'] == 'inference' else 'iterative_inference_valid')
+        mod.WEIGHTS_PATH = os.path.join(WORK, 'weights') + os.sep
+        d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
+        with contextlib.redirect_stdout(io.StringIO()):
+            exp_name = helpers.build_experiment_name('fcn8', data_aug=False, ae_h=False, **dict(list(d.items()) + list(TRAINING_DICT.items())))
+        ldir = os.path.join(WORK, 'load', 'camvid', exp_name)
+        os.makedirs(ldir)
+        weights.save_npz(os.path.join(ldir, 'dae_model_best.npz'), case_dae_params(case))
+        with contextlib.redirect_stdout(buf):
+            res = mod.inference('camvid', 'fcn8', learn_step=case['step'], num_iter=case['num_iter'],
+                                dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])), training_dict=dict(TRAINING_DICT),
+                                data_augmentation=False, which_set='test', ae_h=False, savepath=os.path.join(WORK, 'save'),
+                                loadpath=os.path.join(WORK, 'load'))
+        if case['script'] == 'inference':
+            sdir = os.path.join(WORK, 'save', 'camvid', exp_name, 'img_plots')
+            for i in range(case['nbatches']):
+                with np.load(os.path.join(sdir, 'testbatch%d.npz' % i)) as f:      # `savepath+'batch'+str(i)`: no separator
+                    X, L = case_batch(case, i)
+                    assert np.array_equal(f['X'], X) and np.array_equal(f['L'], L)
+                    out['Y_ii_%d' % i] = f['Y_ii']
+                    out['Y_fcn_%d' % i] = f['Y_fcn']
+        else:
+            sdir = os.path.join(WORK, 'save', 'camvid', exp_name, 'img_plots', str(case['step']), 'test')
+            with np.load(os.path.join(sdir, 'iterations%s.npz' % str(case['step']))) as f:
+                out['valid_mat'] = f['arr_0']
+            out['res'] = np.asarray(res)
+    out['stdout'] = np.array(buf.getvalue())
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    shutil.rmtree(WORK, ignore_errors=True)
+    return out
+
+
+if __name__ == '__main__':
+    current = install_environment()
+    names = sys.argv[1:] or list(CASES)
+    for name in names:
+        out = run_case(name, CASES[name], current)
+        print(name, {k: (v.shape if v.ndim else '...') for k, v in out.items()})

@@ -1,7 +1,9 @@
 """Pins the CPU oracle: the reference ships no tests or fixtures ("parity unpinned"), so the
 oracle is checked against what CAN be derived from the reference code by hand -- the shape
 tables, the Lasagne layer identities, hand-computed metric examples -- against an fp64 re-run
-of itself, and against the committed golden vectors (tests/golden/, made by make_golden.py)."""
+of itself, against the committed golden vectors (tests/golden/, made by make_golden.py) -- and, since round 2, against
+OUTPUTS OF THE REFERENCE ITSELF: tests/golden/ref_*.npz hold what the reference's own drivers, model builders and metrics
+computed when executed in the build container through oracle/refrun (tests/golden/make_reference_golden.py)."""
 import os
 
 import numpy as np
@@ -281,3 +283,103 @@ def test_fcn8_shaped_dae_concatenates_h_in_front(concat):
     a = nets.fcn8_dae_forward(pdae, y, h, C, concat_h=(concat,))
     b = nets.fcn8_forward(plain, y, C, layer=('probs_dimshuffle',))[0]
     assert torch.allclose(a, b, atol=1e-6)
+
+
+# ---- the oracle against outputs of the reference's own code (tests/golden/ref_*.npz) ------------------------------------
+from tests import reference_fixtures as RF  # noqa: E402
+
+REF_TOL = 2e-6          # float32 CPU arithmetic on both sides, different conv algorithms (measured: <= 3e-7)
+
+
+def _oracle_replay(case):
+    """The oracle's version of what the reference's driver did for `case`: per batch (Y_fcn, Y_ii, n_exec, batch metrics,
+    FCN metrics, FCN+DAE metrics, per-image per-iteration metrics) and the accumulated valid_mat."""
+    G = RF.G
+    pf = weights.synthetic_fcn8_params(3, RF.NCLS, **G.FCN8_WEIGHTS)
+    pd = G.case_dae_params(case)
+    d, kw, forward = case['dae'], {}, None
+    if d['kind'] == 'standard':
+        kw = RF.dae_kwargs(case)
+    elif d['kind'] == 'contextmod':
+        forward = lambda y, h: nets.contextmod_forward(pd, y, h)          # noqa: E731
+    else:
+        forward = lambda y, h: nets.fcn8_dae_forward(pd, y, h, RF.NCLS, concat_h=tuple(d['concat_h']))          # noqa: E731
+    out, valid_mat = [], np.zeros((2, RF.NCLS, case['num_iter']))
+    for i in range(case['nbatches']):
+        X, Lb = G.case_batch(case, i)
+        Xt = torch.from_numpy(X)
+        if d['concat_h'][0] == 'input':          # layer=['input', ...]: h is the image itself (iterative_inference.py:139)
+            h, y0 = Xt, nets.fcn8_forward(pf, Xt, RF.NCLS, layer=('probs_dimshuffle',))[0]
+        else:
+            h, y0 = nets.fcn8_forward(pf, Xt, RF.NCLS, layer=(d['concat_h'][0], 'probs_dimshuffle'))
+        m_fcn = M.val_fn(y0.numpy(), Lb, RF.NCLS, [RF.NCLS])
+        p = forward(y0, h) if forward else nets.dae_forward(pd, y0, h, 100, **kw)
+        m_dae = M.val_fn(p.numpy(), Lb, RF.NCLS, [RF.NCLS])
+        per_image, ys, n_exec = [], [], []
+        for im in range(X.shape[0]):          # iterative_inference.py:258-284; valid_mat: iterative_inference_valid.py:288
+            y, n, per_iter, _ = loop.iterate_image(pd, h[im:im + 1], y0[im:im + 1], case['step'], case['num_iter'], 100,
+                                                   t_im=Lb[im:im + 1], n_classes=RF.NCLS, void_labels=[RF.NCLS], forward=forward, **kw)
+            per_image.append(per_iter)
+            ys.append(y)
+            n_exec.append(n)
+            for it, (_, jacc_iter, _) in enumerate(per_iter):
+                valid_mat[:, :, it] += jacc_iter
+        Y = torch.cat(ys, dim=0)
+        bm = M.val_fn(Y.numpy(), Lb, RF.NCLS, [RF.NCLS])
+        out.append(dict(Y_fcn=y0.numpy(), Y_ii=Y.numpy(), n_exec=n_exec, m_ii=bm, m_fcn=m_fcn, m_dae=m_dae, per_image=per_image))
+    return out, valid_mat
+
+
+@pytest.mark.parametrize('name', RF.LOOP_CASES)
+def test_oracle_vs_reference_run(name):
+    """The oracle restatement against what the reference's own code computed (iterative_inference.py:inference /
+    iterative_inference_valid.py:inference executed through oracle/refrun): FCN8 probabilities, the loop's final y, the
+    per-iteration and per-batch metrics it printed, valid_mat."""
+    fx, case = RF.load(name)
+    got, valid_mat = _oracle_replay(case)
+    per_iter_ref, blocks = RF.parse_stdout(str(fx['stdout']))
+    rel = lambda a, b: abs(a - b) <= 2e-6 * max(1.0, abs(b)) or (np.isnan(a) and np.isnan(b))          # noqa: E731
+    # per-image, per-iteration `rec acc jaccard` lines: same COUNT (the early exit) and same values
+    flat = [pi for g in got for pi in g['per_image']]
+    assert [len(p) for p in flat] == [len(p) for p in per_iter_ref], 'iterations that reached val_fn differ (early exit)'
+    for po, pr in zip(flat, per_iter_ref):
+        for (acc, jacc, mse), (rec_r, acc_r, jm_r) in zip(po, pr):
+            with np.errstate(divide='ignore', invalid='ignore'):
+                jm = float(np.nanmean(jacc[0] / jacc[1]))
+            assert rel(float(mse), rec_r) and rel(float(acc), acc_r) and rel(jm, jm_r), ((mse, acc, jm), (rec_r, acc_r, jm_r))
+    # print_results blocks: running totals / (i + 1) of FCN, FCN+DAE and (inference script) ITERATIVE INFERENCE
+    tot = {k: [0.0, 0.0, np.zeros((2, RF.NCLS))] for k in ('m_fcn', 'm_dae', 'm_ii')}
+    expect = []
+    for i, g in enumerate(got):
+        for key, title in (('m_fcn', 'FCN'), ('m_dae', 'FCN+DAE'), ('m_ii', 'ITERATIVE INFERENCE')):
+            acc, jacc, mse = g[key]
+            tot[key][0] += float(mse)
+            tot[key][1] += float(acc)
+            tot[key][2] = tot[key][2] + jacc
+            if key != 'm_ii' or case['script'] == 'inference':
+                expect.append((title,) + tuple(float(v) for v in M.print_results_values(tot[key][0], tot[key][1], tot[key][2], i + 1)))
+    n_summary = 3 if case['script'] == 'inference' else 2
+    assert len(blocks) == len(expect) + n_summary
+    for (t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o) in zip(blocks, expect):
+        assert t_r == t_o and rel(l_o, l_r) and rel(a_o, a_r) and rel(j_o, j_r), ((t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o))
+    if case['script'] == 'inference':
+        for i, g in enumerate(got):
+            assert float(np.abs(g['Y_fcn'] - fx['Y_fcn_%d' % i]).max()) < REF_TOL
+            assert float(np.abs(g['Y_ii'] - fx['Y_ii_%d' % i]).max()) < REF_TOL
+    else:
+        assert np.array_equal(valid_mat, fx['valid_mat'])          # integer counts: exact
+        with np.errstate(divide='ignore', invalid='ignore'):
+            res = np.nanmean(valid_mat[0] / valid_mat[1], axis=0)
+        assert np.allclose(res, fx['res'], rtol=1e-12, atol=0, equal_nan=True)
+
+
+def test_oracle_temperature_vs_reference_run():
+    """models/fcn8.py:193-198 executed by the reference's buildFCN8 with temperature = 2.5."""
+    fx, case = RF.load('ref_temperature')
+    pf = weights.synthetic_fcn8_params(3, RF.NCLS, **RF.G.FCN8_WEIGHTS)
+    X, _ = RF.G.case_batch(case, 0)
+    h, y = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS, temperature=case['temperature'])
+    assert float(np.abs(h.numpy() - fx['pool4']).max()) < REF_TOL * max(1.0, float(np.abs(fx['pool4']).max()))
+    assert float(np.abs(y.numpy() - fx['Y_fcn']).max()) < REF_TOL
+    y1 = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)[1]
+    assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
