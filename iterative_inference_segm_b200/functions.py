@@ -199,16 +199,19 @@ class IterativeInference(object):
         if per_iter:
             for acc in st['iter']:
                 acc.zero_()
+        # bn=1 + DePool2D: the reference iterates one image at a time, so its mask pass sees per-image batch statistics
+        stats_kw = {'per_image_stats': True} if getattr(net, 'bn_batch_masks', False) else {}
         for it in range(num_iter):
             # the first iteration of a batch computes the whole contracting path (h is new); later ones only
             # its y-dependent windows -- everything outside them is iteration-invariant (DAENet.down_windows)
             if self.fuse_update and net.fusable_update:
                 # softmax tail + update + norm in the epilogue of up_conv1: the logits never reach HBM
                 net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'],
-                           update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step))
+                           update=dict(y=st['y'], active=st['active'], norm_acc=st['norm_acc'], step=step), **stats_kw)
                 K.norm_finalize_fixed(st['norm_acc'], st['norm'], st['active'], st['n_exec'], H, W, eps)
             else:
                 kw = {'active': st['active']} if getattr(net, 'takes_active', False) else {}
+                kw.update(stats_kw)
                 logits = net.logits(st['h'], st['y_bf16'], full_down=(it == 0), y_f32=st['y'], **kw)
                 K.softmax_update(logits, st['y'], st['y_bf16'], st['active'], st['partial'], step, split=net.split)
                 K.norm_finalize(st['partial'], st['norm'], st['active'], st['n_exec'], H, W, eps)

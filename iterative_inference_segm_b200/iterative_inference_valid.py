@@ -77,10 +77,22 @@ def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, whic
 
 
 def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
-              data_augmentation=False, which_set='val', ae_h=False, full_im_ft=False, savepath=None, loadpath=None,
+              data_augmentation=False, which_set='test', ae_h=False, full_im_ft=False, savepath=None, loadpath=None,
               test_from_0_255=False, **kw):
-    """Single-step form with the reference's signature (iterative_inference_valid.py:56-59): returns
+    """Single-step form with the reference's signature and directory layout (iterative_inference_valid.py:56-93): the DAE
+    checkpoint is read from `<loadpath>/<dataset>/<exp_name>/dae_model_best.npz`, `iterations<step>.npz` (valid_mat, :303) is
+    written to `<savepath>/<dataset>/<exp_name>/img_plots/<step>/<which_set>/`; returns
     `res = nanmean(valid_mat[0] / valid_mat[1], axis=0)` (`:297`)."""
+    from .helpers import build_experiment_name
+    dae_dict = dict(DAE_DICT_DEFAULTS)
+    dae_dict.update(dae_dict_updates)
+    exp_name = build_experiment_name(segm_net, data_aug=data_augmentation, ae_h=ae_h,
+                                     **dict(list(dae_dict.items()) + list(training_dict.items())))
+    exp_name += '_ftsmall' if full_im_ft else ''
+    if savepath is None:
+        raise ValueError('A saving directory must be specified')
+    savepath = os.path.join(savepath, dataset, exp_name, 'img_plots', str(learn_step), which_set)
+    loadpath = os.path.join(loadpath or '', dataset, exp_name)
     res, _ = sweep(dataset, segm_net, [learn_step], num_iter, dae_dict_updates, which_set, loadpath=loadpath,
                    savepath=savepath, **kw)
     return res[0]

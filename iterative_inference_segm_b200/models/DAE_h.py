@@ -102,6 +102,15 @@ class DAENet(object):
             params = first + list(params[2 * k * self.total:])
         self.bn = bool(bn)
         self.post = [None] * self.total
+        self.bn_gb = [None] * self.total
+        # bn=1 with DePool2D: the reference builds the tie masks in a sub-graph of its own, lasagne.layers.get_output(...)
+        # WITHOUT deterministic=True (layers/mylayers.py:91-93), where every BatchNormLayer normalises with the statistics of
+        # the CURRENT BATCH instead of its stored averages (lasagne: batch_norm_use_averages defaults to `deterministic`).
+        # Observed by executing the reference (tests/golden/ref_bn.npz).  Every application therefore runs the contracting
+        # path twice: the mask pass (conv -> fp32 map -> iiseg_channel_stats -> conv again with the batch-statistics affine,
+        # pool and tie mask in its epilogue) and the value pass on the stored averages.  'inverse' (InverseLayer) and
+        # 'standard' take the deterministic expressions and need no second pass.
+        self.bn_batch_masks = self.bn and unpool_type == 'trackind'
         if self.bn:
             from .._packing import _as_f32
             k_up = 2 if unpool_type == 'standard' else 6
@@ -111,6 +120,7 @@ class DAENet(object):
                 W, b, beta, gamma, mean, inv_std = [_as_f32(a, self.device) for a in params[6 * i:6 * i + 6]]
                 s_ = gamma * inv_std
                 self.post[i] = (s_.contiguous(), (beta - mean * s_).contiguous())
+                self.bn_gb[i] = (beta.contiguous(), gamma.contiguous())
                 flat += [W, b]
             for i in range(self.total):
                 grp = [_as_f32(a, self.device) for a in params[6 * self.total + k_up * i:6 * self.total + k_up * (i + 1)]]
@@ -294,7 +304,40 @@ class DAENet(object):
         return ws
 
     # -- one application ----------------------------------------------------
-    def logits(self, h_bf16, y_bf16, full_down=True, update=None, y_f32=None, noise=None):
+    def _bn_mask_level(self, ws, x, p, pools, pad, kw, sizes, per_image):
+        """One level of the bn=1 mask pass: conv + rectify to an fp32 map, its per-channel batch statistics
+        (iiseg_channel_stats: mean and 1 / sqrt(biased variance + 1e-4) over batch, rows, cols), then the same conv again with
+        (x - mean) * (gamma * inv_std) + beta, the 2x2 pool and the tie mask in its epilogue.  `per_image`: statistics per
+        image -- the reference's loop calls de_fn on one image at a time (iterative_inference.py:261-268)."""
+        B = x.shape[0]
+        Wk, bk = self.down[p]
+        beta, gamma = self.bn_gb[p]
+        hh, ww = sizes[p]
+        C_ = self.filters[p]
+        key = ('bn_z', p, B)
+        if key not in ws:
+            need = K._lib.load().iiseg_channel_stats_chunks(B, hh, ww) * C_ * 2
+            ws[key] = (torch.empty((B, hh, ww, self.cm * C_), dtype=torch.bfloat16, device=self.device),
+                       torch.empty((B, hh, ww, C_), dtype=torch.float32, device=self.device),
+                       torch.empty((C_,), dtype=torch.float32, device=self.device),
+                       torch.empty((C_,), dtype=torch.float32, device=self.device),
+                       torch.empty((need,), dtype=torch.float64, device=self.device))
+        zb, z, mean, inv_std, scratch = ws[key]
+        for a, b in ([(i, i + 1) for i in range(B)] if per_image else [(0, B)]):
+            kwg = dict(kw)
+            if 'addend' in kwg:
+                kwg['addend'] = kwg['addend'][a:b]
+            K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, out=zb[a:b], split=self.split, **kwg)
+            if self.split:        # the (hi | lo) pair back to one fp32 value per element
+                torch.add(zb[a:b, :, :, :C_], zb[a:b, :, :, C_:], out=z[a:b])
+            else:
+                z[a:b].copy_(zb[a:b])
+            K.channel_stats(z[a:b], 0, C_, mean, inv_std, scratch, eps=1e-4)
+            s_ = gamma * inv_std
+            K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, pooled=pools[p][a:b], pool_mask=ws['mask'][p][a:b], split=self.split,
+                     post_affine=(s_, beta - mean * s_), **kwg)
+
+    def logits(self, h_bf16, y_bf16, full_down=True, update=None, y_f32=None, noise=None, per_image_stats=False):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
         Returns fp32 NHWC16 logits of the centre-crop window (B, H, W, 16).
         `full_down=False` recomputes only the y-dependent windows of the contracting path; valid when
@@ -305,7 +348,7 @@ class DAENet(object):
         `y_f32` (NCHW fp32, the values y_bf16 was packed from) and optionally `noise` (same shape, N(0,1); drawn here when
         None) are needed when the net was built with mask_noise > 0."""
         B, H, W, _ = y_bf16.shape
-        if self.unpool_type == 'standard' or self.cbp > 1:
+        if self.unpool_type == 'standard' or self.cbp > 1 or self.bn_batch_masks:
             full_down = True          # (no y-dependent windows for these variants: every level is computed in full)
         ws = self.workspace(B, H, W)
         sizes = self.level_sizes(H, W)
@@ -331,6 +374,10 @@ class DAENet(object):
             if 'pool_m' not in ws:
                 ws['pool_m'] = [torch.empty_like(t) for t in ws['pool']]
             passes = [(x_noisy, 'masks'), (x, 'values')]
+        elif self.bn_batch_masks:
+            if 'pool_m' not in ws:
+                ws['pool_m'] = [torch.empty_like(t) for t in ws['pool']]
+            passes = [(x, 'masks'), (x, 'values')]
         for x, role in passes:
             pools = ws['pool_m'] if role == 'masks' else ws['pool']
             for p in range(self.total):
@@ -346,7 +393,9 @@ class DAENet(object):
                 kw = {}
                 if p == self.n_pool:
                     kw = dict(addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0))
-                if self.cbp > 1:      # conv_p_1 .. conv_p_{k-1} write full pre-pool maps, conv_p_k carries the pool
+                if role == 'masks' and self.bn_batch_masks:
+                    self._bn_mask_level(ws, x, p, pools, pad, kw, sizes, per_image_stats)
+                elif self.cbp > 1:      # conv_p_1 .. conv_p_{k-1} write full pre-pool maps, conv_p_k carries the pool
                     pre = ws.setdefault(('pre', p), [None, None])
                     hh_, ww_ = sizes[p]
                     for i in range(self.cbp):
@@ -475,9 +524,9 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
     # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
     # build is the deterministic graph; warn so that a caller comparing against such a reference run knows.
-    if unpool_type == 'trackind' and (dropout > 0 or bn or (noise > 0 and not stochastic_masks)):
-        warnings.warn('buildDAE: noise=%s dropout=%s bn=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
-                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise: pass stochastic_masks=True for the reference\'s noised mask pass)' % (noise, dropout, bn), stacklevel=2)
+    if unpool_type == 'trackind' and (dropout > 0 or (noise > 0 and not stochastic_masks)):
+        warnings.warn('buildDAE: noise=%s dropout=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
+                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise: pass stochastic_masks=True for the reference\'s noised mask pass; bn=1: the batch-statistics mask pass is always built)' % (noise, dropout), stacklevel=2)
     concat_h = list(concat_h)
     if len(concat_h) != 1 or not (concat_h[-1] == 'input' or concat_h[-1] in ('pool1', 'pool2', 'pool3', 'pool4', 'pool5')):
         # (several entries share ONE nb_features_to_concat in the reference, models/model_helpers.py:91, so they only build

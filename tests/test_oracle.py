@@ -339,6 +339,9 @@ def test_oracle_vs_reference_run(name):
     got, valid_mat = _oracle_replay(case)
     per_iter_ref, blocks = RF.parse_stdout(str(fx['stdout']))
     rel = lambda a, b: abs(a - b) <= 2e-6 * max(1.0, abs(b)) or (np.isnan(a) and np.isnan(b))          # noqa: E731
+    # accuracy / Jaccard are argmax counts: probabilities that agree to 2e-7 can still break one near-tie differently
+    # (ref_bn: one pixel of 3330 in the plain DAE pass, 4.6e-6 on the mean Jaccard)
+    cnt = lambda a, b: abs(a - b) <= 2e-5 or (np.isnan(a) and np.isnan(b))          # noqa: E731
     # per-image, per-iteration `rec acc jaccard` lines: same COUNT (the early exit) and same values
     flat = [pi for g in got for pi in g['per_image']]
     assert [len(p) for p in flat] == [len(p) for p in per_iter_ref], 'iterations that reached val_fn differ (early exit)'
@@ -346,7 +349,7 @@ def test_oracle_vs_reference_run(name):
         for (acc, jacc, mse), (rec_r, acc_r, jm_r) in zip(po, pr):
             with np.errstate(divide='ignore', invalid='ignore'):
                 jm = float(np.nanmean(jacc[0] / jacc[1]))
-            assert rel(float(mse), rec_r) and rel(float(acc), acc_r) and rel(jm, jm_r), ((mse, acc, jm), (rec_r, acc_r, jm_r))
+            assert rel(float(mse), rec_r) and cnt(float(acc), acc_r) and cnt(jm, jm_r), ((mse, acc, jm), (rec_r, acc_r, jm_r))
     # print_results blocks: running totals / (i + 1) of FCN, FCN+DAE and (inference script) ITERATIVE INFERENCE
     tot = {k: [0.0, 0.0, np.zeros((2, RF.NCLS))] for k in ('m_fcn', 'm_dae', 'm_ii')}
     expect = []
@@ -361,7 +364,7 @@ def test_oracle_vs_reference_run(name):
     n_summary = 3 if case['script'] == 'inference' else 2
     assert len(blocks) == len(expect) + n_summary
     for (t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o) in zip(blocks, expect):
-        assert t_r == t_o and rel(l_o, l_r) and rel(a_o, a_r) and rel(j_o, j_r), ((t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o))
+        assert t_r == t_o and rel(l_o, l_r) and cnt(a_o, a_r) and cnt(j_o, j_r), ((t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o))
     if case['script'] == 'inference':
         for i, g in enumerate(got):
             assert float(np.abs(g['Y_fcn'] - fx['Y_fcn_%d' % i]).max()) < REF_TOL

@@ -577,7 +577,10 @@ def test_dae_with_batchnorm_vs_oracle(cuda, unpool_type):
     # relative to that VALUE (dominated by the shift t), not relative to the distance from t -- small positive activations
     # within 2^-17 |t| of the all-zero windows' constant become false ties, a handful of mask flips per application that this
     # test's BN gains (gamma * inv_std up to 3 per layer) amplify.  The fp32 oracle shows no such ties (fp32-vs-fp64 8e-8).
-    tol_f32 = TOL_F32 if unpool_type == 'standard' else 6e-3       # measured: 3.7e-3 (fp32x3), 4.2e-3 (mixed)
+    # Since the oracle follows the reference's batch-statistics mask pass (oracle/nets.py:batchnorm_batch_stats, found by
+    # executing the reference: tests/golden/ref_bn.npz, which this build meets at 1.2e-3) the same false ties are measured at
+    # 6.6e-3 (fp32x3) on this test's gains.
+    tol_f32 = TOL_F32 if unpool_type == 'standard' else 9e-3       # measured: 6.6e-3 (fp32x3)
     tol_bf16 = 2e-2 if unpool_type == 'standard' else 6e-2         # measured 4.2e-2 with DePool2D (tie flips x BN gains)
     for precision, tol in (('fp32x3', tol_f32), ('mixed', tol_f32), ('bf16', tol_bf16)):
         with warnings.catch_warnings():
@@ -887,3 +890,93 @@ def test_fcn8_shaped_dae_vs_oracle(cuda, concat_h, precision):
     print('fcn8 dae %s %s: p %.2e  y %.2e  argmax %.4f' % (concat_h, precision, float(np.abs(p_d - p_o.numpy()).max()),
                                                          float((y - y_o).abs().max()), float((y.argmax(1) == y_o.argmax(1)).float().mean())))
     assert float((y - y_o).abs().max()) < tol and float((y.argmax(1) == y_o.argmax(1)).float().mean()) >= agree
+
+
+# ---- the CUDA path against OUTPUTS OF THE REFERENCE ITSELF (tests/golden/ref_*.npz) ------------------------------------------
+# The fixtures hold what the reference's own iterative_inference.py:inference / iterative_inference_valid.py:inference wrote
+# and printed when executed through oracle/refrun (tests/golden/make_reference_golden.py).  These tests call this package's
+# drop-ins for the same two functions, with the same arguments, the same checkpoints on disk in the reference's directory
+# layout and the same data iterator, and compare what they save and return.
+from tests import reference_fixtures as RF  # noqa: E402
+
+# ref_bn: with bn=1 the reference's DePool2D mask sub-graph normalises with BATCH statistics (lasagne BatchNormLayer under
+# deterministic=False, layers/mylayers.py:91-93); see test_dae_with_batchnorm_vs_oracle and DESIGN.md 3.10.
+_REF_PRECISIONS = [('mixed', 2e-3, 0.999, 2e-3), ('bf16', 3e-2, 0.99, 2e-2)]      # (precision, max-abs on y, argmax agreement, metric tolerance)
+
+
+def _reference_layout(tmp_path, case, exp_name):
+    """Checkpoints on disk where the reference looks for them: WEIGHTS_PATH/<dataset>/fcn8_model.npz (iterative_inference.py:137)
+    and LOADPATH/<dataset>/<exp_name>/dae_model_best.npz (:93, :150)."""
+    wdir = tmp_path / 'weights' / 'camvid'
+    wdir.mkdir(parents=True)
+    weights.save_npz(str(wdir / 'fcn8_model.npz'), weights.synthetic_fcn8_params(3, NCLS, **RF.G.FCN8_WEIGHTS))
+    ldir = tmp_path / 'load' / 'camvid' / exp_name
+    ldir.mkdir(parents=True)
+    weights.save_npz(str(ldir / 'dae_model_best.npz'), RF.G.case_dae_params(case))
+    return str(tmp_path / 'weights'), str(tmp_path / 'load'), str(tmp_path / 'save')
+
+
+@pytest.mark.parametrize('name', [n for n in RF.LOOP_CASES if RF.G.CASES[n]['script'] == 'inference'])
+def test_inference_dropin_vs_reference_run(cuda, tmp_path, name):
+    """iterative_inference.inference() of this package against the reference's own run of iterative_inference.py:inference():
+    the saved batch<i>.npz (Y_fcn, Y_ii) and the three print_results blocks of the summary."""
+    import warnings
+    from iterative_inference_segm_b200.iterative_inference import inference
+    from iterative_inference_segm_b200.helpers import build_experiment_name
+    fx, case = RF.load(name)
+    _, blocks = RF.parse_stdout(str(fx['stdout']))
+    d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
+    exp_name = build_experiment_name('fcn8', data_aug=False, ae_h=False, **dict(list(d.items()) + list(RF.G.TRAINING_DICT.items())))
+    for precision, tol, agree, mtol in _REF_PRECISIONS:
+        if case['dae']['kind'] == 'contextmod' and precision == 'bf16':
+            continue          # the context module is fp32 either way
+        root = tmp_path / precision
+        root.mkdir()
+        wpath, lpath, spath = _reference_layout(root, case, exp_name)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = inference('camvid', 'fcn8', learn_step=case['step'], num_iter=case['num_iter'],
+                            dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])), training_dict=dict(RF.G.TRAINING_DICT),
+                            data_augmentation=False, which_set='test', ae_h=False, savepath=spath, loadpath=lpath, weights_path=wpath,
+                            data_iter=RF.G.SyntheticCamvidIterator(case), save_batches=True, verbose=False, precision=precision)
+        worst = 0.0
+        for i in range(case['nbatches']):
+            with np.load(os.path.join(out['savepath'], 'batch%d.npz' % i)) as f:
+                for key in ('Y_fcn', 'Y_ii'):
+                    ref = fx['%s_%d' % (key, i)]
+                    err = float(np.abs(f[key] - ref).max())
+                    worst = max(worst, err)
+                    assert f[key].shape == ref.shape and err < tol, (name, precision, key, i, err)
+                    assert float((f[key].argmax(1) == ref.argmax(1)).mean()) >= agree, (name, precision, key, i)
+        # the summary blocks the reference printed last: FCN, FCN+DAE, ITERATIVE INFERENCE (loss, accuracy, mean Jaccard)
+        for (title, loss_r, acc_r, jacc_r), key in zip(blocks[-3:], ('fcn', 'fcn_dae', 'iterative')):
+            loss, acc, jacc = [float(v) for v in out[key]]
+            assert abs(loss - loss_r) < mtol and abs(acc - acc_r) < mtol and abs(jacc - jacc_r) < mtol, (name, precision, title, out[key], (loss_r, acc_r, jacc_r))
+        print('%s %s: worst max-abs vs the reference run %.2e' % (name, precision, worst))
+
+
+@pytest.mark.parametrize('name', [n for n in RF.LOOP_CASES if RF.G.CASES[n]['script'] == 'valid'])
+def test_valid_dropin_vs_reference_run(cuda, tmp_path, name):
+    """iterative_inference_valid.inference() against the reference's own run: the saved iterations<step>.npz (valid_mat, the
+    per-iteration Jaccard numerators / denominators summed over images -- zero columns where every image had converged) and
+    the returned per-iteration mean Jaccard."""
+    import warnings
+    from iterative_inference_segm_b200.iterative_inference_valid import inference
+    from iterative_inference_segm_b200.helpers import build_experiment_name
+    fx, case = RF.load(name)
+    d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
+    exp_name = build_experiment_name('fcn8', data_aug=False, ae_h=False, **dict(list(d.items()) + list(RF.G.TRAINING_DICT.items())))
+    wpath, lpath, spath = _reference_layout(tmp_path, case, exp_name)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        res = inference('camvid', 'fcn8', learn_step=case['step'], num_iter=case['num_iter'], dae_dict_updates=d,
+                        training_dict=dict(RF.G.TRAINING_DICT), which_set='test', savepath=spath, loadpath=lpath,
+                        weights_path=wpath, data_iter=RF.G.SyntheticCamvidIterator(case), verbose=False, precision='mixed')
+    with np.load(os.path.join(spath, 'camvid', exp_name, 'img_plots', str(case['step']), 'test', 'iterations%s.npz' % str(case['step']))) as f:
+        vm = f['arr_0']
+    ref = fx['valid_mat']
+    assert vm.shape == ref.shape
+    assert np.array_equal(vm.sum(axis=(0, 1)) == 0, ref.sum(axis=(0, 1)) == 0), 'iterations reached (early exit) differ'
+    n_pix = case['B'] * case['nbatches'] * case['H'] * case['W']
+    assert float(np.abs(vm - ref).max()) <= 2e-3 * n_pix, float(np.abs(vm - ref).max())          # a handful of argmax flips at most
+    assert np.allclose(res, fx['res'], atol=1e-3, equal_nan=True), (res, fx['res'])
