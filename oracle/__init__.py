@@ -7,12 +7,17 @@ Theano/Lasagne) and exists to check the CUDA path.  Only ``tests/``,
 reference`` legs may import it.  The product package
 (``iterative_inference_segm_b200``) never imports it and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and
-Theano/Lasagne (pinned at Theano ddafc3e2, Lasagne 45bb5689, reference
-README.md:142) cannot be installed here, so the oracle could not be checked
-against outputs of the reference itself.  What pins it instead: the shape
-tables derivable from the reference code, hand-computed metric examples, the
-Lasagne semantics restated in SURVEY.md App. A, and an fp64 re-run of the same
-restatement (tests/test_oracle.py).
+PARITY PINNED BY EXECUTING THE REFERENCE (round 2).  The reference ships no tests, golden vectors or fixtures, and
+Theano / Lasagne (Theano ddafc3e2, Lasagne 45bb5689, reference README.md:142) cannot be installed here.  `oracle/refrun`
+therefore provides stand-ins for the small part of both libraries the reference uses, plus a Python-2 import hook, and
+`tests/golden/make_reference_golden.py` runs the reference's OWN, unmodified sources with them: its drivers
+(iterative_inference.py:inference, iterative_inference_valid.py:inference), model builders (models/fcn8.py, DAE_h.py,
+fcn_down.py, fcn_up.py, model_helpers.py, contextmod_dae.py, fcn8_dae.py, layers/mylayers.py), metrics.py and, for the
+training step, train_dae.py:train.  Their outputs are committed as tests/golden/ref_*.npz and this restatement replays
+every one of them to 3e-7 (tests/test_oracle.py::test_oracle_vs_reference_run; integer matrices exactly).  What remains
+restated rather than executed: the arithmetic of the Lasagne layers inside oracle/refrun/stubs/lasagne (written
+independently of oracle/lasagne_semantics.py) and Theano's CPU MaxPoolGrad tie rule; FC-DenseNet103 stays unpinned (its
+layers come from the absent FC_DenseNet package).  Also pinned by hand: the shape tables, hand-computed metric examples and
+an fp64 re-run (tests/test_oracle.py).
 """
 from . import lasagne_semantics, nets, metrics, loop, weights  # noqa: F401

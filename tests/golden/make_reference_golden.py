@@ -75,6 +75,10 @@ CASES = {
     'ref_fcn8_dae': dict(script='inference', dae=dae_dict(kind='fcn8', concat_h=['pool4']), H=32, W=40, B=1, nbatches=1, num_iter=3,
                          step=0.05, weights=dict(fn='fcn8_dae', seed=6, logit_gain=10.0)),
     'ref_temperature': dict(script='fcn8_only', temperature=2.5, H=32, W=40, B=2, nbatches=1),
+    # train_dae.py:train(): two epochs of two rmsprop steps each (lr annealed in between) + validation, resumed from a seeded
+    # checkpoint; noise = 0 (the MRG stream is not reproduced)
+    'ref_train': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2, learning_rate=0.001,
+                      lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'], weights=dict(fn='dae', seed=1, out_gain=0.1)),
 }
 
 FCN8_WEIGHTS = dict(seed=0, logit_gain=10.0)
@@ -98,20 +102,29 @@ def case_dae_params(case):
     return pd
 
 
-def case_batch(case, i):
+def case_batch(case, i, which='test'):
     """Batch i of a case: (X, L one-hot with the void channel) as numpy float32 (oracle/weights.py:synthetic_batch)."""
     from oracle import weights
-    X, L, _ = weights.synthetic_batch(case['B'], case['H'], case['W'], NCLS, seed=100 + i)
+    X, L, _ = weights.synthetic_batch(case['B'], case['H'], case['W'], NCLS, seed={'test': 100, 'train': 100, 'val': 500}[which] + i)
     return X.numpy(), L.numpy()
+
+
+def param_digest(i, after, before):
+    """What the fixture keeps of a trained parameter array: a strided sample of up to 4096 values, and the sum / L2 norm of its
+    change from the initial checkpoint (float64)."""
+    flat = np.asarray(after, np.float32).reshape(-1)
+    idx = np.unique(np.linspace(0, flat.size - 1, min(flat.size, 4096)).astype(np.int64))
+    delta = flat.astype(np.float64) - np.asarray(before, np.float64).reshape(-1)
+    return {'p%d_sample' % i: flat[idx], 'p%d_delta' % i: np.array([delta.sum(), np.sqrt((delta ** 2).sum()), np.abs(delta).max()])}
 
 
 class SyntheticCamvidIterator(object):
     """The attributes and the `next()` protocol iterative_inference.py:117-125,249 use from a dataset_loaders iterator."""
 
-    def __init__(self, case):
-        self.case = case
+    def __init__(self, case, which='test'):
+        self.case, self.which = case, which
         self.cmap = np.zeros((NCLS + 1, 3), np.float32)
-        self.nbatches = case['nbatches']
+        self.nbatches = case['val_nbatches'] if which == 'val' else case['nbatches']
         self.non_void_nclasses = NCLS
         self.void_labels = [NCLS]
         self.data_shape = (3, case['H'], case['W'])
@@ -119,7 +132,7 @@ class SyntheticCamvidIterator(object):
         self.i = 0
 
     def next(self):
-        X, L = case_batch(self.case, self.i % self.nbatches)
+        X, L = case_batch(self.case, self.i % self.nbatches, self.which)
         self.i += 1
         return X, L
 
@@ -139,7 +152,11 @@ def install_environment():
         sys.modules[name] = m
         return m
     current = {}
-    module('data_loader', load_data=lambda dataset, *a, **kw: SyntheticCamvidIterator(current['case']))
+    def load_data(dataset, *a, **kw):
+        if kw.get('which_set', 'all') == 'all':          # train_dae.py:127-133 unpacks (train, val, test)
+            return [SyntheticCamvidIterator(current['case'], 'train'), SyntheticCamvidIterator(current['case'], 'val'), None]
+        return SyntheticCamvidIterator(current['case'])
+    module('data_loader', load_data=load_data)
     module('distutils', dir_util=module('distutils.dir_util', copy_tree=lambda *a, **kw: None))      # removed in Python 3.12
     module('skimage', color=module('skimage.color', rgb2gray=None, gray2rgb=None), img_as_float=None)
     module('seaborn')
@@ -170,6 +187,36 @@ def run_case(name, case, current):
             fn = theano.function([x], lasagne.layers.get_output(fcn, deterministic=True, batch_norm_use_averages=False))
             h, y = fn(case_batch(case, 0)[0])
         out.update(pool4=h, Y_fcn=y)
+    elif case['script'] == 'train':
+        import helpers
+        import train_dae
+        train_dae.WEIGHTS_PATH = os.path.join(WORK, 'weights') + os.sep
+        d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
+        with contextlib.redirect_stdout(io.StringIO()):
+            exp_name = helpers.build_experiment_name('fcn8', training_loss=case['training_loss'], data_aug=True,
+                                                     learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
+                                                     optimizer='rmsprop', ae_h=False, **d)
+        ldir = os.path.join(WORK, 'load', 'camvid', exp_name)
+        os.makedirs(ldir)
+        weights.save_npz(os.path.join(ldir, 'dae_model_best.npz'), case_dae_params(case))          # resume=True reads it (train_dae.py:186)
+        with contextlib.redirect_stdout(buf):
+            train_dae.train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
+                            num_epochs=case['num_epochs'], max_patience=100, optimizer='rmsprop', training_loss=list(case['training_loss']),
+                            batch_size=[case['B']] * 3, ae_h=False, dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
+                            data_augmentation={'crop_size': None}, savepath=os.path.join(WORK, 'save'), loadpath=os.path.join(WORK, 'load'),
+                            resume=True, lmb=case['lmb'])
+        sdir = os.path.join(WORK, 'save', 'camvid', exp_name)
+        saved = sorted(f for f in os.listdir(sdir) if f.startswith('dae_model_'))
+        assert len(saved) == 1, saved          # epoch 1 writes dae_model_best.npz (improved) or dae_model_last.npz
+        out['saved_as'] = np.array(saved[0])
+        init = [p.numpy() for p in case_dae_params(case)]
+        with np.load(os.path.join(sdir, saved[0])) as f:          # 55 M parameters: store a digest, not the arrays
+            assert len(f.files) == len(init)
+            for i in range(len(f.files)):
+                out.update(param_digest(i, f['arr_%d' % i], init[i]))
+        with np.load(os.path.join(sdir, saved[0].replace('model', 'errors'))) as f:
+            out['err_train'], out['err_valid'], out['jacc_val'], out['mse_val'] = [np.asarray(f['arr_%d' % i]) for i in range(4)]
+        out['output_log'] = np.array(open(os.path.join(sdir, 'output.log')).read())
     else:
         import helpers
         mod = __import__('iterative_inference' if case['script'] == 'inference' else 'iterative_inference_valid')

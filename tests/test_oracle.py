@@ -386,3 +386,56 @@ def test_oracle_temperature_vs_reference_run():
     assert float(np.abs(y.numpy() - fx['Y_fcn']).max()) < REF_TOL
     y1 = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)[1]
     assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
+
+
+def test_oracle_train_step_vs_reference_run():
+    """oracle/train.py against the reference's own train_dae.py:train() (two epochs of two rmsprop steps, the learning rate
+    annealed in between, validation after each epoch; tests/golden/ref_train.npz): per-epoch training / validation cost,
+    validation Jaccard and squared error, and the parameters the reference saved after the fourth step (digest: 4096 strided
+    samples per array + the sum / norm / max of each array's change)."""
+    from oracle import train as T_
+    G = RF.G
+    fx, case = RF.load('ref_train')
+    pf = weights.synthetic_fcn8_params(3, RF.NCLS, **G.FCN8_WEIGHTS)
+    init = G.case_dae_params(case)
+    params, accus = [p.clone() for p in init], [torch.zeros_like(p) for p in init]
+    lr = np.float32(case['learning_rate'])
+    err_train, err_valid, jacc_val, mse_val = [], [], [], []
+    for epoch in range(case['num_epochs']):
+        tot = 0.0
+        for i in range(case['nbatches']):                      # train_dae.py:356-383
+            X, Lb = G.case_batch(case, i, 'train')
+            h, y = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)
+            loss, _, params, accus = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'])
+            tot += loss
+        err_train.append(tot / case['nbatches'])
+        cost, jacc, mse = 0.0, 0.0, 0.0
+        for i in range(case['val_nbatches']):                  # train_dae.py:387-411
+            X, Lb = G.case_batch(case, i, 'val')
+            h, y = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)
+            with torch.no_grad():
+                logits = T_.dae_forward_train(params, y, h, 100)
+                cost += float(T_.loss_fn(logits, torch.from_numpy(Lb), RF.NCLS, lmb=case['lmb']))
+                p = torch.softmax(logits, dim=1).numpy()
+            jacc = jacc + M.jaccard(p, Lb, RF.NCLS)
+            mse += float(M.squared_error(p, Lb, RF.NCLS))
+        err_valid.append(cost / case['val_nbatches'])
+        jacc_val.append(float(np.mean(jacc[0] / jacc[1])))
+        mse_val.append(mse / case['val_nbatches'])
+        lr = np.float32(float(lr) * case['lr_anneal'])          # train_dae.py:424: lr.set_value(float(lr.get_value() * lr_anneal)), a float32 shared variable
+    assert np.allclose(err_train, fx['err_train'], rtol=2e-6, atol=0), (err_train, fx['err_train'])
+    assert np.allclose(err_valid, fx['err_valid'], rtol=2e-6, atol=0), (err_valid, fx['err_valid'])
+    assert np.allclose(mse_val, fx['mse_val'], rtol=2e-6, atol=0)
+    assert np.allclose(jacc_val, fx['jacc_val'], rtol=0, atol=2e-5)
+    assert str(fx['saved_as']) == ('dae_model_best.npz' if err_valid[1] < err_valid[0] else 'dae_model_last.npz')
+    worst = 0.0
+    for i, (p_new, p_old) in enumerate(zip(params, init)):
+        dig = G.param_digest(i, p_new.numpy(), p_old.numpy())
+        step = float(fx['p%d_delta' % i][2])                      # largest change of any element of this array over the 4 steps
+        err = float(np.abs(dig['p%d_sample' % i] - fx['p%d_sample' % i]).max())
+        worst = max(worst, err / step)
+        # rmsprop divides by sqrt(accumulated g^2): an element whose gradient is ~0 amplifies rounding, hence a tolerance
+        # relative to the array's largest update rather than per element
+        assert err <= 2e-3 * step, (i, err, step)
+        assert np.allclose(dig['p%d_delta' % i][1], fx['p%d_delta' % i][1], rtol=1e-3), (i, dig['p%d_delta' % i], fx['p%d_delta' % i])
+    print('trained parameters: worst sample error / largest update = %.2e' % worst)
