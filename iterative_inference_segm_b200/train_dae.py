@@ -463,6 +463,7 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
                                      optimizer=optimizer, ae_h=ae_h, **dae_dict)
     if savepath is None:
         raise ValueError('A saving directory must be specified')
+    loadpath_init = os.path.join(loadpath, dataset, exp_name) if loadpath is not None else None      # train_dae.py:96
     exp_name += '_ft' if full_im_ft else ''
     savepath = os.path.join(savepath, dataset, exp_name)
     os.makedirs(savepath, exist_ok=True)
@@ -483,7 +484,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
     fnet = fcn[0].net
     if dae_params is None:
         if resume:
-            dae_params = load_npz_params(os.path.join(loadpath or savepath, 'dae_model_best.npz'))
+            # resume / full_im_ft read <loadpath>/<dataset>/<exp_name>/dae_model_best.npz (train_dae.py:96,186-187)
+            dae_params = load_npz_params(os.path.join(loadpath_init or savepath, 'dae_model_best.npz'))
         else:
             from . import synthetic
             dae_params = synthetic.synthetic_dae_params(n_classes, fcn[0].output_shape[1], seed=seed, n_filters=dae_dict['n_filters'],

@@ -244,3 +244,54 @@ def test_train_loop_runs_and_writes_the_reference_checkpoints(cuda, tmp_path, se
                    n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind', load_weights=True,
                    path_weights=out['savepath'], model_name=name)
     assert dae.net.total == 6
+
+
+def test_train_dropin_vs_reference_run(cuda, tmp_path):
+    """train() of this package against the reference's OWN run of train_dae.py:train() (executed through oracle/refrun,
+    tests/golden/ref_train.npz): same arguments, the seeded checkpoint on disk where `resume=True` reads it, the same iterators;
+    two epochs of two rmsprop steps with the annealed learning rate and a validation pass each.  The step computes with bf16
+    operands (fp32 accumulation, fp32 master weights), so the comparison carries that variant's tolerance: per-epoch costs
+    and, for every parameter array, the norm of its change over the four steps."""
+    from tests import reference_fixtures as RF
+    from iterative_inference_segm_b200.train_dae import train
+    from iterative_inference_segm_b200.helpers import build_experiment_name
+    G = RF.G
+    fx, case = RF.load('ref_train')
+    d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
+    exp_name = build_experiment_name('fcn8', training_loss=case['training_loss'], data_aug=True, learning_rate=case['learning_rate'],
+                                     lr_anneal=case['lr_anneal'], weight_decay=1e-4, optimizer='rmsprop', ae_h=False, **d)
+    wdir = tmp_path / 'weights' / 'camvid'
+    wdir.mkdir(parents=True)
+    weights.save_npz(str(wdir / 'fcn8_model.npz'), weights.synthetic_fcn8_params(3, NCLS, **G.FCN8_WEIGHTS))
+    ldir = tmp_path / 'load' / 'camvid' / exp_name
+    ldir.mkdir(parents=True)
+    init = G.case_dae_params(case)
+    weights.save_npz(str(ldir / 'dae_model_best.npz'), init)
+    out = train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
+                num_epochs=case['num_epochs'], max_patience=100, optimizer='rmsprop', training_loss=list(case['training_loss']),
+                batch_size=[case['B']] * 3, ae_h=False, dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
+                data_augmentation={'crop_size': None}, savepath=str(tmp_path / 'save'), loadpath=str(tmp_path / 'load'), resume=True,
+                lmb=case['lmb'], train_iter=G.SyntheticCamvidIterator(case, 'train'), val_iter=G.SyntheticCamvidIterator(case, 'val'),
+                weights_path=str(tmp_path / 'weights'), verbose=False)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())          # noqa: E731
+    e_tr, e_va, e_mse = rel(out['err_train'], fx['err_train']), rel(out['err_valid'], fx['err_valid']), rel(out['mse_val'], fx['mse_val'])
+    print('train drop-in vs reference run: err_train %.2e err_valid %.2e mse_val %.2e (relative)' % (e_tr, e_va, e_mse))
+    assert e_tr < 1e-3 and e_va < 1e-3 and e_mse < 1e-3          # measured 1.5e-4 / 2.4e-5 / 1.1e-5
+    assert abs(out['jacc_val'][-1] - float(fx['jacc_val'][-1])) < 5e-3
+    saved = sorted(f for f in os.listdir(out['savepath']) if f.startswith('dae_model_'))
+    assert saved == [str(fx['saved_as'])]
+    with np.load(os.path.join(out['savepath'], saved[0])) as f:
+        arrays = [f['arr_%d' % i] for i in range(len(f.files))]
+    assert len(arrays) == len(init)
+    worst_norm, worst_sample, norms = 0.0, 0.0, []
+    for i, (a, p0) in enumerate(zip(arrays, init)):
+        dig = G.param_digest(i, a, p0.numpy())
+        n_ref, n_dev = float(fx['p%d_delta' % i][1]), float(dig['p%d_delta' % i][1])
+        worst_norm = max(worst_norm, abs(n_dev - n_ref) / n_ref)
+        norms.append(abs(n_dev - n_ref) / n_ref)
+        worst_sample = max(worst_sample, float(np.abs(dig['p%d_sample' % i] - fx['p%d_sample' % i]).max()) / float(fx['p%d_delta' % i][2]))
+    print('trained parameters vs reference run: |delta| norm mismatch per array: median %.3f worst %.3f (array %d); worst sample error / largest update %.3f'
+          % (float(np.median(norms)), worst_norm, int(np.argmax(norms)), worst_sample))
+    # rmsprop normalises every element's step to ~lr whatever its gradient's size: the NORM of an array's change is robust, single
+    # elements whose gradient is ~0 are not (their sign is rounding, and bf16 operands flip pool ties: DESIGN.md 3.9)
+    assert float(np.median(norms)) < 0.05 and worst_norm < 0.25          # measured: worst 0.15
