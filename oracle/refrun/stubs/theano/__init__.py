@@ -68,7 +68,9 @@ class Variable(object):
 
     @property
     def shape(self):
-        return Variable(lambda v: tuple(int(s) for s in v.shape), [self], name='shape', ndim=1)
+        sh = Variable(lambda v: tuple(int(s) for s in v.shape), [self], name='shape', ndim=1)
+        sh._len = self._ndim          # `b, c, rows, cols = x.shape` (models/FCDenseNet.py:135) unpacks it
+        return sh
 
     def __bool__(self):
         if self._is_nonzero:
@@ -123,7 +125,10 @@ class Variable(object):
         return Variable(_getitem, [self, idx], ndim=nd, base=self, index=idx)
 
     def __iter__(self):
-        raise TypeError('iteration over a symbolic variable')
+        n = getattr(self, '_len', None)
+        if n is None:
+            raise TypeError('iteration over a symbolic variable of unknown length')
+        return iter([self[i] for i in range(n)])
 
     # ---- methods the reference calls ----
     def dimshuffle(self, *pattern):

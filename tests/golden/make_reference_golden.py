@@ -75,6 +75,10 @@ CASES = {
     'ref_fcn8_dae': dict(script='inference', dae=dae_dict(kind='fcn8', concat_h=['pool4']), H=32, W=40, B=1, nbatches=1, num_iter=3,
                          step=0.05, weights=dict(fn='fcn8_dae', seed=6, logit_gain=10.0)),
     'ref_temperature': dict(script='fcn8_only', temperature=2.5, H=32, W=40, B=2, nbatches=1),
+    # FC-DenseNet103 conditioning (models/FCDenseNet.py:Network / build_fcdensenet are the reference's; its four layer helpers
+    # come from the absent FC_DenseNet package and are restated in oracle/refrun/stubs/FC_DenseNet/layers.py)
+    'ref_densenet': dict(script='inference', segm_net='densenet', dae=dae_dict(), H=64, W=96, B=2, nbatches=1, num_iter=3, step=0.05,
+                         weights=dict(fn='dae', seed=1, out_gain=0.1, nb_h=464), densenet=dict(seed=2, logit_gain=4.0, bn_seed=5)),
     # train_dae.py:train(): two epochs of two rmsprop steps each (lr annealed in between) + validation, resumed from a seeded
     # checkpoint; noise = 0 (the MRG stream is not reproduced)
     'ref_train': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2, learning_rate=0.001,
@@ -92,7 +96,7 @@ def case_dae_params(case):
         return weights.synthetic_contextmod_params(NCLS, 3, seed=w['seed'])
     if w['fn'] == 'fcn8_dae':
         return weights.synthetic_fcn8_params(NCLS, NCLS, seed=w['seed'], logit_gain=w['logit_gain'], concat=(d['concat_h'][0], 512))
-    nb_h = 3 if d['concat_h'][-1] == 'input' else 512
+    nb_h = 3 if d['concat_h'][-1] == 'input' else w.get('nb_h', 512)
     pd = weights.synthetic_dae_params(NCLS, nb_h, seed=w['seed'], out_gain=w['out_gain'], concat_h=tuple(d['concat_h']),
                                       additional_pool=d['additional_pool'], unpool_type=d['unpool_type'],
                                       conv_before_pool=d['conv_before_pool'], n_filters=d['n_filters'])
@@ -100,6 +104,31 @@ def case_dae_params(case):
         n_levels = (int(d['concat_h'][-1][-1]) if 'pool' in d['concat_h'][-1] else 0) + d['additional_pool']
         pd = weights.with_batchnorm(pd, n_levels, d['unpool_type'], seed=w['bn_seed'])
     return pd
+
+
+DENSENET_HARDCODED_PATH = '/data/lisatmp4/romerosa/itinf/models/camvid/DenseNet103/weights/FC-DenseNet103_weights.npz'          # models/FCDenseNet.py:198
+
+
+def case_densenet_params(case):
+    """Synthetic FC-DenseNet103 checkpoint (oracle/densenet.py recipe) with NON-trivial BatchNorm arrays, so that a wrong
+    position of beta / gamma / mean / inv_std in the positional checkpoint cannot go unnoticed."""
+    import torch
+    from oracle import densenet as OD
+    w = case['densenet']
+    params = OD.synthetic_densenet_params(3, NCLS, seed=w['seed'], logit_gain=w['logit_gain'])
+    gen = torch.Generator().manual_seed(w['bn_seed'])
+    k = 0
+    for name, kind, ws in OD.densenet_param_shapes(3, NCLS):
+        if kind == 'bnconv':
+            c = params[k].shape[0]
+            params[k] = 0.2 * torch.randn(c, generator=gen)                    # beta
+            params[k + 1] = 0.75 + 0.5 * torch.rand(c, generator=gen)          # gamma
+            params[k + 2] = torch.randn(c, generator=gen)                      # mean    (stored averages: never read,
+            params[k + 3] = 0.5 + torch.rand(c, generator=gen)                 # inv_std  batch_norm_use_averages=False)
+            k += 6
+        else:
+            k += 2
+    return params
 
 
 def case_batch(case, i, which='test'):
@@ -160,8 +189,6 @@ def install_environment():
     module('distutils', dir_util=module('distutils.dir_util', copy_tree=lambda *a, **kw: None))      # removed in Python 3.12
     module('skimage', color=module('skimage.color', rgb2gray=None, gray2rgb=None), img_as_float=None)
     module('seaborn')
-    module('FC_DenseNet', layers=module('FC_DenseNet.layers', BN_ReLU_Conv=None, TransitionDown=None, TransitionUp=None,
-                                        SoftmaxLayer=None))                                           # un-vendored dependency
     return current
 
 
@@ -227,11 +254,20 @@ def run_case(name, case, current):
         ldir = os.path.join(WORK, 'load', 'camvid', exp_name)
         os.makedirs(ldir)
         weights.save_npz(os.path.join(ldir, 'dae_model_best.npz'), case_dae_params(case))
+        segm_net = case.get('segm_net', 'fcn8')
+        if segm_net == 'densenet':          # build_fcdensenet restores from a hard-coded absolute path: serve it from the work directory
+            weights.save_npz(os.path.join(wdir, 'densenet.npz'), case_densenet_params(case))
+            real_load = np.load
+            np.load = lambda path, *a, **kw: real_load(os.path.join(wdir, 'densenet.npz') if path == DENSENET_HARDCODED_PATH else path, *a, **kw)
+            os.rename(ldir, ldir.replace(exp_name, exp_name.replace('fcn8', 'densenet', 1)))
+            exp_name = exp_name.replace('fcn8', 'densenet', 1)
         with contextlib.redirect_stdout(buf):
-            res = mod.inference('camvid', 'fcn8', learn_step=case['step'], num_iter=case['num_iter'],
+            res = mod.inference('camvid', segm_net, learn_step=case['step'], num_iter=case['num_iter'],
                                 dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])), training_dict=dict(TRAINING_DICT),
                                 data_augmentation=False, which_set='test', ae_h=False, savepath=os.path.join(WORK, 'save'),
                                 loadpath=os.path.join(WORK, 'load'))
+        if segm_net == 'densenet':
+            np.load = real_load
         if case['script'] == 'inference':
             sdir = os.path.join(WORK, 'save', 'camvid', exp_name, 'img_plots')
             for i in range(case['nbatches']):

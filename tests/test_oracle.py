@@ -305,19 +305,26 @@ def _oracle_replay(case):
     else:
         forward = lambda y, h: nets.fcn8_dae_forward(pd, y, h, RF.NCLS, concat_h=tuple(d['concat_h']))          # noqa: E731
     out, valid_mat = [], np.zeros((2, RF.NCLS, case['num_iter']))
+    densenet = case.get('segm_net') == 'densenet'
+    padding = 0 if densenet else 100          # iterative_inference.py:140,145
+    if densenet:
+        from oracle import densenet as OD
+        pdn = G.case_densenet_params(case)
     for i in range(case['nbatches']):
         X, Lb = G.case_batch(case, i)
         Xt = torch.from_numpy(X)
-        if d['concat_h'][0] == 'input':          # layer=['input', ...]: h is the image itself (iterative_inference.py:139)
+        if densenet:
+            h, y0 = OD.densenet_forward(pdn, Xt, RF.NCLS, layer=list(d['concat_h']))
+        elif d['concat_h'][0] == 'input':          # layer=['input', ...]: h is the image itself (iterative_inference.py:139)
             h, y0 = Xt, nets.fcn8_forward(pf, Xt, RF.NCLS, layer=('probs_dimshuffle',))[0]
         else:
             h, y0 = nets.fcn8_forward(pf, Xt, RF.NCLS, layer=(d['concat_h'][0], 'probs_dimshuffle'))
         m_fcn = M.val_fn(y0.numpy(), Lb, RF.NCLS, [RF.NCLS])
-        p = forward(y0, h) if forward else nets.dae_forward(pd, y0, h, 100, **kw)
+        p = forward(y0, h) if forward else nets.dae_forward(pd, y0, h, padding, **kw)
         m_dae = M.val_fn(p.numpy(), Lb, RF.NCLS, [RF.NCLS])
         per_image, ys, n_exec = [], [], []
         for im in range(X.shape[0]):          # iterative_inference.py:258-284; valid_mat: iterative_inference_valid.py:288
-            y, n, per_iter, _ = loop.iterate_image(pd, h[im:im + 1], y0[im:im + 1], case['step'], case['num_iter'], 100,
+            y, n, per_iter, _ = loop.iterate_image(pd, h[im:im + 1], y0[im:im + 1], case['step'], case['num_iter'], padding,
                                                    t_im=Lb[im:im + 1], n_classes=RF.NCLS, void_labels=[RF.NCLS], forward=forward, **kw)
             per_image.append(per_iter)
             ys.append(y)
