@@ -16,8 +16,8 @@ fcn_down.py, fcn_up.py, model_helpers.py, contextmod_dae.py, fcn8_dae.py, layers
 training step, train_dae.py:train.  Their outputs are committed as tests/golden/ref_*.npz and this restatement replays
 every one of them to 3e-7 (tests/test_oracle.py::test_oracle_vs_reference_run; integer matrices exactly).  What remains
 restated rather than executed: the arithmetic of the Lasagne layers inside oracle/refrun/stubs/lasagne (written
-independently of oracle/lasagne_semantics.py) and Theano's CPU MaxPoolGrad tie rule; FC-DenseNet103 stays unpinned (its
-layers come from the absent FC_DenseNet package).  Also pinned by hand: the shape tables, hand-computed metric examples and
+independently of oracle/lasagne_semantics.py), Theano's CPU MaxPoolGrad tie rule, and the four layer helpers FC-DenseNet103
+imports from the absent FC_DenseNet package (the network that calls them, models/FCDenseNet.py, is executed).  Also pinned by hand: the shape tables, hand-computed metric examples and
 an fp64 re-run (tests/test_oracle.py).
 """
 from . import lasagne_semantics, nets, metrics, loop, weights  # noqa: F401

@@ -16,9 +16,11 @@ variance over axes (0,2,3).  The scripts evaluate with batch_norm_use_averages=F
 (iterative_inference.py:187), i.e. BATCH statistics even at test time, so the stored running mean /
 inv_std are never read; results depend on the batch composition.
 
-PARITY UNPINNED twice over: the reference has no tests or vectors, and FC_DenseNet.layers is not
-in the tree -- the helper semantics above are restated from the public repository, not checked
-against the pinned code.  Parameters are a flat list in creation order (= Lasagne's topological
+PINNING: the network wiring, the hidden outputs and the 590-array positional checkpoint order are checked against the
+reference's own models/FCDenseNet.py (Network / build_fcdensenet / restore), executed through oracle/refrun
+(tests/golden/ref_densenet.npz, tests/test_oracle.py::test_oracle_vs_reference_run[ref_densenet], 3e-7).  What stays restated:
+the four helpers of FC_DenseNet.layers above (the package is not in the tree; oracle/refrun/stubs/FC_DenseNet/layers.py
+restates them a second time on the Lasagne stand-in).  Parameters are a flat list in creation order (= Lasagne's topological
 order for this graph): conv W,b ; per BN_ReLU_Conv: beta, gamma, mean, inv_std, W, b ; deconv W,b.
 """
 import torch
