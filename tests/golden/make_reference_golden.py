@@ -75,6 +75,10 @@ CASES = {
     'ref_fcn8_dae': dict(script='inference', dae=dae_dict(kind='fcn8', concat_h=['pool4']), H=32, W=40, B=1, nbatches=1, num_iter=3,
                          step=0.05, weights=dict(fn='fcn8_dae', seed=6, logit_gain=10.0)),
     'ref_temperature': dict(script='fcn8_only', temperature=2.5, H=32, W=40, B=2, nbatches=1),
+    # BASELINE.json configs[1], one image of it (the reference iterates image by image): 360x480, 50 iterations, step 0.05.
+    # The fixture keeps the argmax labels in full and every third pixel of the probabilities (`sub`).
+    'ref_full_size': dict(script='inference', dae=dae_dict(), H=360, W=480, B=1, nbatches=1, num_iter=50, step=0.05, sub=3,
+                          weights=dict(fn='dae', seed=1, out_gain=0.1)),
     # FC-DenseNet103 conditioning (models/FCDenseNet.py:Network / build_fcdensenet are the reference's; its four layer helpers
     # come from the absent FC_DenseNet package and are restated in oracle/refrun/stubs/FC_DenseNet/layers.py)
     'ref_densenet': dict(script='inference', segm_net='densenet', dae=dae_dict(), H=64, W=96, B=2, nbatches=1, num_iter=3, step=0.05,
@@ -274,8 +278,14 @@ def run_case(name, case, current):
                 with np.load(os.path.join(sdir, 'testbatch%d.npz' % i)) as f:      # `savepath+'batch'+str(i)`: no separator
                     X, L = case_batch(case, i)
                     assert np.array_equal(f['X'], X) and np.array_equal(f['L'], L)
-                    out['Y_ii_%d' % i] = f['Y_ii']
-                    out['Y_fcn_%d' % i] = f['Y_fcn']
+                    if 'sub' in case:
+                        k = case['sub']
+                        out['Y_ii_%d' % i], out['Y_fcn_%d' % i] = f['Y_ii'][:, :, ::k, ::k], f['Y_fcn'][:, :, ::k, ::k]
+                        out['labels_ii_%d' % i] = f['Y_ii'].argmax(1).astype(np.uint8)
+                        out['labels_fcn_%d' % i] = f['Y_fcn'].argmax(1).astype(np.uint8)
+                    else:
+                        out['Y_ii_%d' % i] = f['Y_ii']
+                        out['Y_fcn_%d' % i] = f['Y_fcn']
         else:
             sdir = os.path.join(WORK, 'save', 'camvid', exp_name, 'img_plots', str(case['step']), 'test')
             with np.load(os.path.join(sdir, 'iterations%s.npz' % str(case['step']))) as f:

@@ -373,9 +373,15 @@ def test_oracle_vs_reference_run(name):
     for (t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o) in zip(blocks, expect):
         assert t_r == t_o and rel(l_o, l_r) and cnt(a_o, a_r) and cnt(j_o, j_r), ((t_r, l_r, a_r, j_r), (t_o, l_o, a_o, j_o))
     if case['script'] == 'inference':
+        k = case.get('sub', 1)          # ref_full_size keeps every k-th pixel of the probabilities and all argmax labels
         for i, g in enumerate(got):
-            assert float(np.abs(g['Y_fcn'] - fx['Y_fcn_%d' % i]).max()) < REF_TOL
-            assert float(np.abs(g['Y_ii'] - fx['Y_ii_%d' % i]).max()) < REF_TOL
+            assert float(np.abs(g['Y_fcn'][:, :, ::k, ::k] - fx['Y_fcn_%d' % i]).max()) < REF_TOL
+            # 50 free-running iterations at 360x480: two float32 CPU evaluations with different summation orders drift apart
+            # through pool ties (measured 9.9e-5 here; the oracle's own fp32-vs-fp64 drift is 1.2e-4, oracle/validate_recipe.py)
+            assert float(np.abs(g['Y_ii'][:, :, ::k, ::k] - fx['Y_ii_%d' % i]).max()) < (REF_TOL if k == 1 else 5e-4)
+            if k > 1:
+                assert float((g['Y_fcn'].argmax(1) == fx['labels_fcn_%d' % i]).mean()) >= 0.9999
+                assert float((g['Y_ii'].argmax(1) == fx['labels_ii_%d' % i]).mean()) >= 0.9995          # measured 0.99985 (26 pixels)
     else:
         assert np.array_equal(valid_mat, fx['valid_mat'])          # integer counts: exact
         with np.errstate(divide='ignore', invalid='ignore'):

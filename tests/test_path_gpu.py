@@ -933,6 +933,8 @@ def test_inference_dropin_vs_reference_run(cuda, tmp_path, name):
     segm_net = case.get('segm_net', 'fcn8')
     exp_name = build_experiment_name(segm_net, data_aug=False, ae_h=False, **dict(list(d.items()) + list(RF.G.TRAINING_DICT.items())))
     for precision, tol, agree, mtol in _REF_PRECISIONS:
+        if 'sub' in case and precision == 'bf16':
+            agree = 0.985          # full size, 50 iterations: the bf16 variant's measured 98.9 %
         if segm_net == 'densenet' and precision == 'bf16':
             tol, agree, mtol = 0.15, 0.97, 5e-2          # the bf16 DenseNet's own tolerance (tests/test_densenet_gpu.py)
         if case['dae']['kind'] == 'contextmod' and precision == 'bf16':
@@ -949,12 +951,15 @@ def test_inference_dropin_vs_reference_run(cuda, tmp_path, name):
         worst = {'Y_fcn': 0.0, 'Y_ii': 0.0}
         for i in range(case['nbatches']):
             with np.load(os.path.join(out['savepath'], 'batch%d.npz' % i)) as f:
+                k = case.get('sub', 1)      # ref_full_size keeps every k-th pixel of the probabilities and all argmax labels
                 for key in ('Y_fcn', 'Y_ii'):
                     ref = fx['%s_%d' % (key, i)]
-                    err = float(np.abs(f[key] - ref).max())
+                    got = f[key][:, :, ::k, ::k]
+                    err = float(np.abs(got - ref).max())
                     worst[key] = max(worst[key], err)
-                    assert f[key].shape == ref.shape and err < tol, (name, precision, key, i, err)
-                    assert float((f[key].argmax(1) == ref.argmax(1)).mean()) >= agree, (name, precision, key, i)
+                    assert got.shape == ref.shape and err < tol, (name, precision, key, i, err)
+                    lab_ref = fx['labels_%s_%d' % (key[2:], i)] if k > 1 else ref.argmax(1)
+                    assert float((f[key].argmax(1) == lab_ref).mean()) >= agree, (name, precision, key, i)
         # the summary blocks the reference printed last: FCN, FCN+DAE, ITERATIVE INFERENCE (loss, accuracy, mean Jaccard)
         for (title, loss_r, acc_r, jacc_r), key in zip(blocks[-3:], ('fcn', 'fcn_dae', 'iterative')):
             loss, acc, jacc = [float(v) for v in out[key]]
