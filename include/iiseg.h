@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IISEG_ABI_VERSION 4
+#define IISEG_ABI_VERSION 5
 #define IISEG_MAX_SRC 6
 #define IISEG_MAX_WGROUPS 9
 
@@ -133,6 +133,11 @@ typedef struct iiseg_conv_desc {
    * averages).  The fused pool and its tie mask then see the normalised values, as DePool2D does. */
   const float* post_scale;
   const float* post_shift;
+  /* Optional third vector (fp32 [Cout]): when non-NULL the epilogue evaluates lasagne's own expression,
+   * ((x - post_mean[c]) * post_scale[c]) + post_shift[c] with post_scale = gamma * inv_std and post_shift = beta, one fp32
+   * rounding per operation instead of one fused multiply-add: values that round onto the window's exact zeros then tie in
+   * the pool exactly where they do in the reference (DePool2D's tie-inclusive mask). */
+  const float* post_mean;
   int Cout;           /* padded: 16, or a multiple of 64                    */
   int R, S, pad;      /* filter extent and symmetric zero padding           */
   /* Output window: out pixel (oh,ow) is conv pixel (oh+oh0, ow+ow0); only the

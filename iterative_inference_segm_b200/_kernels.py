@@ -99,7 +99,8 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
     where it applies (iiseg_conv_desc.weight_npack).
 
     post_affine = (scale, shift): fp32 [Cout] vectors applied after the rectifier, before pool / store (a folded
-    deterministic BatchNormLayer, iiseg_conv_desc.post_scale).
+    deterministic BatchNormLayer, iiseg_conv_desc.post_scale); (scale, shift, mean): ((x - mean) * scale) + shift with one
+    rounding per operation -- lasagne's (x - mean) * (gamma * inv_std) + beta (iiseg_conv_desc.post_mean).
 
     src_pair_hi: src0 is a (hi | lo) pair tensor [N,H,W,2*C0] of which a plain bf16 conv reads the hi halves.
 
@@ -212,6 +213,10 @@ def conv2d(src0, weight, bias, R, S, pad, relu, src1=None, addend=None, window=N
         _chk(post_affine[1], F32, 'post_affine.shift')
         assert post_affine[0].numel() == Cout == post_affine[1].numel()
         d.post_scale, d.post_shift = post_affine[0].data_ptr(), post_affine[1].data_ptr()
+        if len(post_affine) == 3:          # (gamma * inv_std, beta, mean): ((x - mean) * scale) + shift, rounded like lasagne's expression
+            _chk(post_affine[2], F32, 'post_affine.mean')
+            assert post_affine[2].numel() == Cout
+            d.post_mean = post_affine[2].data_ptr()
     if out_strided is not None:
         d.out, d.out_stride, d.out_H, d.out_W, d.out_h0, d.out_w0 = dest.data_ptr(), ostride, dest.shape[1], dest.shape[2], oh_0, ow_0
     if depool_out is not None:

@@ -14,7 +14,7 @@ class IisegError(RuntimeError):
     pass
 
 
-ABI_VERSION = 4      # IISEG_ABI_VERSION
+ABI_VERSION = 5      # IISEG_ABI_VERSION
 MAX_SRC = 6          # IISEG_MAX_SRC
 MAX_WGROUPS = 9      # IISEG_MAX_WGROUPS
 
@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
         ('depool_out', C.c_void_p), ('depool_out_mask', C.c_void_p), ('depool_out_VH', C.c_int), ('depool_out_VW', C.c_int),
         ('depool_out_h0', C.c_int), ('depool_out_w0', C.c_int),
         ('depool_out_H2', C.c_int), ('depool_out_W2', C.c_int), ('depool_out_ph0', C.c_int), ('depool_out_pw0', C.c_int),
-        ('weight', C.c_void_p), ('weight_npack', C.c_void_p), ('bias', C.c_void_p), ('post_scale', C.c_void_p), ('post_shift', C.c_void_p),
+        ('weight', C.c_void_p), ('weight_npack', C.c_void_p), ('bias', C.c_void_p), ('post_scale', C.c_void_p), ('post_shift', C.c_void_p), ('post_mean', C.c_void_p),
         ('Cout', C.c_int), ('R', C.c_int), ('S', C.c_int), ('pad', C.c_int),
         ('oh0', C.c_int), ('ow0', C.c_int), ('OH', C.c_int), ('OW', C.c_int),
         ('out', C.c_void_p), ('out_stride', C.c_int), ('out_H', C.c_int), ('out_W', C.c_int), ('out_h0', C.c_int), ('out_w0', C.c_int),

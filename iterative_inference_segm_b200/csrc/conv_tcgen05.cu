@@ -41,6 +41,18 @@ constexpr int kNumThreads = 384;             // per-tap kernel: 4 pipeline warps
 constexpr int kNumThreadsHalo = 640;         // halo-tile kernel: 4 pipeline warps + 16 epilogue warps
 constexpr int kEpilogueThreads = 256;
 constexpr long long kTimeoutCycles = 4000000000LL;  // ~2 s: a stuck pipeline traps instead of hanging
+// Split precision, fused Pool2DLayer(2): the window maximum and the tie-inclusive mask are decided on the fp32 values (after
+// bias / rectifier / BatchNorm affine) BEFORE they are split into (hi, lo) bf16 pairs.  A pair has 16 significant bits, so
+// two fp32 values closer than 2^-17 relative collapse into the same pair; deciding on the pairs marks both as maxima (a
+// "false tie" the float32 reference does not have).  The pooled value is the same either way (the pair of the maximum).
+constexpr bool kTieFp32 = true;
+
+// BatchNormLayer behind the rectifier.  `three`: lasagne's own expression (x - mean) * (gamma * inv_std) + beta, one fp32 rounding
+// per operation -- a value so small that x - mean rounds to -mean then ties with the exact zeros of its pool window, as it does
+// in the reference; the folded form x * s + t (one fused multiply-add) rounds at a different place and breaks such ties differently.
+__device__ __forceinline__ float post_bn(float x, float mn, float sc, float sh, bool three) {
+  return three ? __fadd_rn(__fmul_rn(__fsub_rn(x, mn), sc), sh) : __fmaf_rn(x, sc, sh);
+}
 
 // BN output channels per tile; G k-blocks (64 channels of one tap) per pipeline stage.  The
 // producer/MMA handshake costs ~350 cycles per stage whatever it carries (measured), so narrow
@@ -68,6 +80,7 @@ struct alignas(64) ConvParams {
   const float* bias;
   const float* post_scale;   // post-activation per-channel affine (deterministic BatchNormLayer after the rectifier): x*s + t
   const float* post_shift;
+  const float* post_mean;    // non-NULL: ((x - mean) * s) + t with one rounding per operation (lasagne's expression order)
   const __nv_bfloat16* addend;
   void* out;
   int32_t* diag;
@@ -643,10 +656,12 @@ __device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
             const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
+            const bool three = p.post_mean != nullptr;
+            const float4 mn = three ? __ldg(reinterpret_cast<const float4*>(p.post_mean + cbase) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
             float* ff = f + 4 * j4;
             if (p.relu) { ff[0] = fmaxf(ff[0], 0.f); ff[1] = fmaxf(ff[1], 0.f); ff[2] = fmaxf(ff[2], 0.f); ff[3] = fmaxf(ff[3], 0.f); }
-            ff[0] = __fmaf_rn(ff[0], sc.x, sh.x); ff[1] = __fmaf_rn(ff[1], sc.y, sh.y);
-            ff[2] = __fmaf_rn(ff[2], sc.z, sh.z); ff[3] = __fmaf_rn(ff[3], sc.w, sh.w);
+            ff[0] = post_bn(ff[0], mn.x, sc.x, sh.x, three); ff[1] = post_bn(ff[1], mn.y, sc.y, sh.y, three);
+            ff[2] = post_bn(ff[2], mn.z, sc.z, sh.z, three); ff[3] = post_bn(ff[3], mn.w, sc.w, sh.w, three);
           }
         }
 #pragma unroll
@@ -690,10 +705,17 @@ __device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t
           // staging, no named barriers.  The lane at window position 0 writes the pair of the maximum and the mask words.
           const int pos = ((lane >> 4) << 1) | (lane & 1);
           uint32_t word[4] = {0u, 0u, 0u, 0u};
+          if constexpr (kTieFp32) {          // ties decided on the fp32 values themselves (f is not yet rectified on this path)
+            if (p.relu && !post) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
-            f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+              for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
+              f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -762,7 +784,19 @@ __device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t
           // chunks.  Plain: two 32-channel accumulator chunks fill a row, then the group pools 64
           // channels.  Split: one accumulator chunk fills a row as (32 hi | 32 lo), pooled at once.
           const int half = kSplit ? 0 : (chunk & 1);
-          if (in_box) {
+          if (kSplit && kTieFp32) {
+            // split: the row holds the 32 fp32 values of this accumulator chunk (8 swizzled 16-byte chunks of 4 channels)
+            if (in_box) {
+#pragma unroll
+              for (int cc = 0; cc < 8; ++cc) {
+                float a0 = f[4 * cc], a1 = f[4 * cc + 1], a2 = f[4 * cc + 2], a3 = f[4 * cc + 3];
+                if (p.relu && !post) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+                const uint32_t addr = sbuf + m * 128 + ((cc ^ (m & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)),
+                             "r"(__float_as_uint(a2)), "r"(__float_as_uint(a3)) : "memory");
+              }
+            }
+          } else if (in_box) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               const uint32_t addr = sbuf + m * 128 + (((half * 4 + cc) ^ (m & 7)) << 4);
@@ -795,6 +829,12 @@ __device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int mm = m00 + (e >> 1) * p.TW + (e & 1);
+                  if constexpr (kSplit && kTieFp32) {       // channels 8*cgp .. 8*cgp+7 as fp32: chunks 2*cgp and 2*cgp + 1
+                    const uint32_t a0 = sbuf + mm * 128 + (((2 * cgp) ^ (mm & 7)) << 4), a1 = sbuf + mm * 128 + (((2 * cgp + 1) ^ (mm & 7)) << 4);
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(a0));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wl_[e][0]), "=r"(wl_[e][1]), "=r"(wl_[e][2]), "=r"(wl_[e][3]) : "r"(a1));
+                    continue;
+                  }
                   const uint32_t addr = sbuf + mm * 128 + ((cgp ^ (mm & 7)) << 4);
                   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[e][0]), "=r"(w[e][1]), "=r"(w[e][2]), "=r"(w[e][3]) : "r"(addr));
                   if (kSplit) {
@@ -819,6 +859,24 @@ __device__ __forceinline__ void conv_epilogue_impl(const ConvParams& p, uint32_t
                     outw[k] = bf16x2_max(bf16x2_max(w[0][k], w[1][k]), bf16x2_max(w[2][k], w[3][k]));
 #pragma unroll
                     for (int e = 0; e < 4; ++e) bits |= tie_bits(bf16x2_eq_mask(w[e][k], outw[k]), k, e);
+                  }
+                } else if constexpr (kTieFp32) {      // w[e][0..3] | wl_[e][0..3] = the 8 channels of window element e as fp32
+                  float mx8[8];
+#pragma unroll
+                  for (int ch = 0; ch < 8; ++ch) {
+                    float fv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) fv[e] = __uint_as_float(ch < 4 ? w[e][ch] : wl_[e][ch - 4]);
+                    const float mx = fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3]));
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                      if (fv[e] == mx) bits |= 1u << (16 * (ch & 1) + 4 * (ch >> 1) + e);      // channel ch = word ch >> 1, half ch & 1
+                    mx8[ch] = mx;
+                  }
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {          // the pair of the window maximum
+                    outw[k] = pack_bf16x2(mx8[2 * k], mx8[2 * k + 1]);
+                    outl[k] = pack_bf16x2(mx8[2 * k] - bf16_lo(outw[k]), mx8[2 * k + 1] - bf16_hi(outw[k]));
                   }
                 } else {      // pool and tie mask compare the reconstructed fp32 values hi + lo
 #pragma unroll
@@ -1274,10 +1332,12 @@ __device__ __forceinline__ void halo_epilogue(const ConvParams& p, uint32_t tmem
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
           const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
+          const bool three = p.post_mean != nullptr;
+          const float4 mn = three ? __ldg(reinterpret_cast<const float4*>(p.post_mean + cbase) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
           float* ff = f + 4 * j4;
           if (p.relu) { ff[0] = fmaxf(ff[0], 0.f); ff[1] = fmaxf(ff[1], 0.f); ff[2] = fmaxf(ff[2], 0.f); ff[3] = fmaxf(ff[3], 0.f); }
-          ff[0] = __fmaf_rn(ff[0], sc.x, sh.x); ff[1] = __fmaf_rn(ff[1], sc.y, sh.y);
-          ff[2] = __fmaf_rn(ff[2], sc.z, sh.z); ff[3] = __fmaf_rn(ff[3], sc.w, sh.w);
+          ff[0] = post_bn(ff[0], mn.x, sc.x, sh.x, three); ff[1] = post_bn(ff[1], mn.y, sc.y, sh.y, three);
+          ff[2] = post_bn(ff[2], mn.z, sc.z, sh.z, three); ff[3] = post_bn(ff[3], mn.w, sc.w, sh.w, three);
         }
       }
       uint32_t hi[8], zw[2] = {0u, 0u};
@@ -1409,8 +1469,10 @@ __device__ __forceinline__ void halo_epilogue_split(const ConvParams& p, uint32_
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 sc = __ldg(reinterpret_cast<const float4*>(p.post_scale + cbase) + j4);
           const float4 sh = __ldg(reinterpret_cast<const float4*>(p.post_shift + cbase) + j4);
-          f[4 * j4] = __fmaf_rn(f[4 * j4], sc.x, sh.x); f[4 * j4 + 1] = __fmaf_rn(f[4 * j4 + 1], sc.y, sh.y);
-          f[4 * j4 + 2] = __fmaf_rn(f[4 * j4 + 2], sc.z, sh.z); f[4 * j4 + 3] = __fmaf_rn(f[4 * j4 + 3], sc.w, sh.w);
+          const bool three = p.post_mean != nullptr;
+          const float4 mn = three ? __ldg(reinterpret_cast<const float4*>(p.post_mean + cbase) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          f[4 * j4] = post_bn(f[4 * j4], mn.x, sc.x, sh.x, three); f[4 * j4 + 1] = post_bn(f[4 * j4 + 1], mn.y, sc.y, sh.y, three);
+          f[4 * j4 + 2] = post_bn(f[4 * j4 + 2], mn.z, sc.z, sh.z, three); f[4 * j4 + 3] = post_bn(f[4 * j4 + 3], mn.w, sc.w, sh.w, three);
         }
       }
       uint32_t hi[8], lo[8];
@@ -1430,10 +1492,12 @@ __device__ __forceinline__ void halo_epilogue_split(const ConvParams& p, uint32_
       } else {
         // r = hi + lo, window max and tie bits over the four lanes of the window
         uint32_t word[2] = {0u, 0u};
+        if constexpr (!kTieFp32) {          // (kTieFp32: f already holds the rectified / normalised fp32 values)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
-          f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+          for (int j = 0; j < 8; ++j) {
+            f[2 * j] = bf16_lo(hi[j]) + bf16_lo(lo[j]);
+            f[2 * j + 1] = bf16_hi(hi[j]) + bf16_hi(lo[j]);
+          }
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -2289,6 +2353,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   IISEG_CHECK(d->OH >= 1 && d->OW >= 1 && d->oh0 >= 0 && d->ow0 >= 0 && d->oh0 + d->OH <= fullOH && d->ow0 + d->OW <= fullOW,
               "conv: output window [%d+%d, %d+%d] outside %dx%d", d->oh0, d->OH, d->ow0, d->OW, fullOH, fullOW);
   IISEG_CHECK(d->N >= 1, "conv: empty batch");
+  IISEG_CHECK(d->post_mean == nullptr || d->post_scale != nullptr, "conv: post_mean needs post_scale / post_shift");
   IISEG_CHECK((d->post_scale == nullptr) == (d->post_shift == nullptr) &&
               (d->post_scale == nullptr || (d->Cout % 64 == 0 && !d->out_f32 && d->pool_zmask == nullptr && d->depool_out == nullptr)),
               "conv: post_scale / post_shift come together and need a bf16 (or split) output with Cout %% 64 == 0");
@@ -2498,7 +2563,7 @@ extern "C" int iiseg_conv2d_fwd(const iiseg_conv_desc* d, void* stream) {
   const int w_rows_all = wgroups > 0 ? d->w_rows_total : d->Cout;
   if (encode_weight(&p.tm_w, d->weight, w_rows_all, Kw, BN, KB, d->weight_ld)) return -1;
   p.bias = d->bias;
-  p.post_scale = d->post_scale; p.post_shift = d->post_shift;
+  p.post_scale = d->post_scale; p.post_shift = d->post_shift; p.post_mean = d->post_mean;
   p.addend = reinterpret_cast<const __nv_bfloat16*>(d->addend);
   p.out = d->out;
   p.diag = diag_device_ptr();

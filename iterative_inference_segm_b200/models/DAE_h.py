@@ -119,7 +119,8 @@ class DAENet(object):
             for i in range(self.total):
                 W, b, beta, gamma, mean, inv_std = [_as_f32(a, self.device) for a in params[6 * i:6 * i + 6]]
                 s_ = gamma * inv_std
-                self.post[i] = (s_.contiguous(), (beta - mean * s_).contiguous())
+                # (scale, shift, mean): the epilogue evaluates ((x - mean) * (gamma * inv_std)) + beta with lasagne's roundings
+                self.post[i] = (s_.contiguous(), beta.contiguous(), mean.contiguous())
                 self.bn_gb[i] = (beta.contiguous(), gamma.contiguous())
                 flat += [W, b]
             for i in range(self.total):
@@ -333,9 +334,8 @@ class DAENet(object):
             else:
                 z[a:b].copy_(zb[a:b])
             K.channel_stats(z[a:b], 0, C_, mean, inv_std, scratch, eps=1e-4)
-            s_ = gamma * inv_std
             K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, pooled=pools[p][a:b], pool_mask=ws['mask'][p][a:b], split=self.split,
-                     post_affine=(s_, beta - mean * s_), **kwg)
+                     post_affine=(gamma * inv_std, beta, mean), **kwg)
 
     def logits(self, h_bf16, y_bf16, full_down=True, update=None, y_f32=None, noise=None, per_image_stats=False):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).

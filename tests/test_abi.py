@@ -25,7 +25,7 @@ def test_binding_table_matches_header(lib):
 
 
 def test_abi_version_and_error_text(lib):
-    assert lib.iiseg_abi_version() == 4
+    assert lib.iiseg_abi_version() == 5
     assert isinstance(lib.iiseg_last_error(), bytes)
 
 
