@@ -111,12 +111,17 @@ class ReferenceFinder(importlib.abc.MetaPathFinder):
         return None
 
 
-def install():
-    """Puts the stubs (theano, lasagne) and the reference finder in place.  Idempotent."""
-    if not os.path.isdir(REF_ROOT):
-        raise RuntimeError('%s is not present: the reference can only be executed in the build container' % REF_ROOT)
+def install_stubs():
+    """Puts the stand-ins (theano, lasagne, FC_DenseNet) on sys.path.  Idempotent; needs no reference tree."""
     stubs = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'stubs')
     if stubs not in sys.path:
         sys.path.insert(0, stubs)
+
+
+def install():
+    """Puts the stubs and the reference finder in place.  Idempotent."""
+    if not os.path.isdir(REF_ROOT):
+        raise RuntimeError('%s is not present: the reference can only be executed in the build container' % REF_ROOT)
+    install_stubs()
     if not any(isinstance(f, ReferenceFinder) for f in sys.meta_path):
         sys.meta_path.append(ReferenceFinder([REF_ROOT, os.path.join(REF_ROOT, 'models')]))
