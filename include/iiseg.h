@@ -65,6 +65,10 @@ int iiseg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C,
  * src is [N,H,W,2*Cpad] and dst = hi + lo. */
 int iiseg_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C,
                                        int H, int W, int Cpad, int split, void* stream);
+/* NHWC bf16 [pixels, C] (split = 1: the (hi | lo) pair [pixels, 2*C], dst = hi + lo) -> NHWC fp32 [pixels, C]; C % 8 == 0.
+ * Feeds iiseg_channel_stats with a rectified conv output (the batch-statistics BatchNormLayer of DePool2D's mask
+ * sub-graph, layers/mylayers.py:91-93 with models/fcn_down.py:113-115). */
+int iiseg_widen_nhwc_bf16_to_f32(const void* src, float* dst, long long pixels, int C, int split, void* stream);
 /* NHWC fp32 [N,H,W,Cpad] -> NCHW fp32 [N,C,H,W]. */
 int iiseg_unpack_nhwc_f32_to_nchw_f32(const float* src, float* dst, int N, int C,
                                       int H, int W, int Cpad, void* stream);

@@ -69,6 +69,16 @@ def unpack_nhwc(src, c, out=None, split=False):
     return out
 
 
+def widen_nhwc(src, out, split=False):
+    """NHWC bf16 [N,H,W,C] (split: the (hi | lo) pair [N,H,W,2C]) -> NHWC fp32 `out` [N,H,W,C] (= hi + lo)."""
+    _chk(src, BF16, 'src')
+    _chk(out, F32, 'out')
+    Cc = out.shape[3]
+    assert tuple(src.shape[:3]) == tuple(out.shape[:3]) and src.shape[3] == (2 * Cc if split else Cc) and Cc % 8 == 0
+    _lib.call('iiseg_widen_nhwc_bf16_to_f32', _ptr(src), _ptr(out), out.shape[0] * out.shape[1] * out.shape[2], Cc, int(bool(split)), _stream())
+    return out
+
+
 # ---- convolution ------------------------------------------------------------
 def conv_out_size(H, W, R, S, pad):
     return H + 2 * pad - R + 1, W + 2 * pad - S + 1

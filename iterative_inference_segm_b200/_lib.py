@@ -83,6 +83,7 @@ SIGNATURES = {
     'iiseg_pack_nchw_f32_to_nhwc_bf16': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_unpack_nhwc_bf16_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_unpack_nhwc_f32_to_nchw_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'iiseg_widen_nhwc_bf16_to_f32': (_i, [_vp, _vp, C.c_longlong, _i, _i, _vp]),
     'iiseg_conv2d_fwd': (_i, [C.POINTER(ConvDesc), _vp]),
     'iiseg_maxpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_unpool2_mask_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

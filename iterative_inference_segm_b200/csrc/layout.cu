@@ -54,6 +54,29 @@ static int grid_for(long long total) {
   return (int)(b < cap ? b : cap);
 }
 
+// NHWC bf16 (or the (hi | lo) pair) -> NHWC fp32, 8 channels per thread: the input of iiseg_channel_stats when the batch
+// statistics of a rectified conv output are needed (DAE_h bn=1: DePool2D's mask pass, models/DAE_h.py).
+__global__ void __launch_bounds__(256) widen_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, int C8, long long total,
+                                                    int split) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C8;
+    const int cg = (int)(i - pix * C8);
+    const uint4 h = ldg_nc_v4(src + pix * (split ? 2 * C8 : C8) + cg);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[2 * k] = bf16_lo(hw[k]); v[2 * k + 1] = bf16_hi(hw[k]); }
+    if (split) {
+      const uint4 l = ldg_nc_v4(src + pix * 2 * C8 + C8 + cg);
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { v[2 * k] += bf16_lo(lw[k]); v[2 * k + 1] += bf16_hi(lw[k]); }
+    }
+    dst[i * 2] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[i * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 }  // namespace iiseg
 
 extern "C" int iiseg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cpad,
@@ -76,6 +99,17 @@ extern "C" int iiseg_unpack_nhwc_bf16_to_nchw_f32(const void* src, float* dst, i
   const long long total = (long long)N * C * H * W;
   unpack_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), dst, C, H * W, Cpad, total, split);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_widen_nhwc_bf16_to_f32(const void* src, float* dst, long long pixels, int C, int split, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(src && dst, "widen: null tensor");
+  IISEG_CHECK(pixels > 0 && C > 0 && C % 8 == 0, "widen: bad shape pixels=%lld C=%d", pixels, C);
+  const long long total = pixels * (C / 8);
+  widen_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), C / 8, total, split);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -329,10 +329,7 @@ class DAENet(object):
             if 'addend' in kwg:
                 kwg['addend'] = kwg['addend'][a:b]
             K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, out=zb[a:b], split=self.split, **kwg)
-            if self.split:        # the (hi | lo) pair back to one fp32 value per element
-                torch.add(zb[a:b, :, :, :C_], zb[a:b, :, :, C_:], out=z[a:b])
-            else:
-                z[a:b].copy_(zb[a:b])
+            K.widen_nhwc(zb[a:b], z[a:b], split=self.split)        # (the (hi | lo) pair back to) one fp32 value per element
             K.channel_stats(z[a:b], 0, C_, mean, inv_std, scratch, eps=1e-4)
             K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, pooled=pools[p][a:b], pool_mask=ws['mask'][p][a:b], split=self.split,
                      post_affine=(gamma * inv_std, beta, mean), **kwg)

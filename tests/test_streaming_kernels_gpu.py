@@ -161,3 +161,20 @@ def test_metrics_active_gating_and_accumulation(cuda):
     K.metrics_accumulate(y, cm, cnt, se, labels=lab, active=active, void_label=C)
     assert int(cm[1].sum()) == 0 and int(cnt[1].sum()) == 0
     assert int(cm[0].sum()) == 2 * int((lab[0] < C).sum())
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_widen_nhwc_bf16_to_f32(cuda, split):
+    """iiseg_widen_nhwc_bf16_to_f32: NHWC bf16 (or the (hi | lo) pair) -> NHWC fp32 = hi (+ lo), exactly."""
+    from iterative_inference_segm_b200 import _kernels as K
+    torch.manual_seed(3)
+    x = torch.randn(3, 24, 5, 7, device=cuda)
+    src = K.pack_nchw(x, 24, split=split)                       # [3,5,7,24] or [3,5,7,48]
+    out = torch.full((3, 5, 7, 24), -1.0, device=cuda)
+    K.widen_nhwc(src, out, split=split)
+    want = src[..., :24].float() + (src[..., 24:].float() if split else 0.0)
+    assert torch.equal(out, want)
+    assert float((out.permute(0, 3, 1, 2) - x).abs().max()) < (2e-5 if split else 2e-2)
+    part = torch.full((3, 5, 7, 24), -1.0, device=cuda)         # a batch slice, as the bn=1 mask pass calls it
+    K.widen_nhwc(src[1:2], part[1:2], split=split)
+    assert torch.equal(part[1], want[1]) and float(part[0].max()) == -1.0 and float(part[2].max()) == -1.0
