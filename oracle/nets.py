@@ -177,7 +177,8 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
     mask_source_y: the reference builds DePool2D's mask sub-graph with get_output(...) WITHOUT deterministic=True
     (layers/mylayers.py:91-93): when the DAE has noise > 0 its tie masks come from a SEPARATE pass of the
     contracting path on y + N(0, noise^2), even at inference.  Pass that noised input here to restate it
-    (None: the deterministic graph, masks from the same pass).
+    (None: the deterministic graph, masks from the same pass; a LIST of `total` noised inputs: the reference's actual graph,
+    an independent noise draw per DePool2D, level p's mask from a pass on entry p - 1).
     unpool_type='standard' (models/fcn_up.py:37-63): up_p = Deconv2DLayer(prev, n_cl, 4, stride=2,
     crop='valid', linear) and NO convolution; skip-sum / crop as above (centre crop of the larger map).
     """
@@ -223,20 +224,30 @@ def dae_forward(params, y, h, padding, concat_h=('pool4',), additional_pool=2,
         # statistics of ITS OWN BATCH (lasagne: batch_norm_use_averages defaults to `deterministic`), not on the stored
         # averages.  Found by running the reference (tests/golden/ref_bn.npz); 'inverse' (InverseLayer) receives the
         # deterministic expressions and is not affected.
-        xm, pre = (y if mask_source_y is None else mask_source_y), []
-        if concat_h[-1] == 'input':
-            xm = torch.cat([h, xm], dim=1)
-        for p in range(total):
-            first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input' and padding > 0)
-            xm = L.conv2d(xm, *Wd[p], pad=padding if first_pad else 'same', relu=True)
-            for We in Wd_extra[p]:
-                xm = L.conv2d(xm, *We, pad='same', relu=True)
-            if BNd[p] is not None:
-                xm = batchnorm_batch_stats(xm, BNd[p][0], BNd[p][1])
-            pre.append(xm)
-            xm = L.maxpool2(xm)
-            if p + 1 == n_pool and n_pool > 0:
+        def mask_pass(xm, upto):
+            out = []
+            if concat_h[-1] == 'input':
                 xm = torch.cat([h, xm], dim=1)
+            for p in range(upto):
+                first_pad = (p == 0 and len(concat_h) == 1 and concat_h[-1] != 'input' and padding > 0)
+                xm = L.conv2d(xm, *Wd[p], pad=padding if first_pad else 'same', relu=True)
+                for We in Wd_extra[p]:
+                    xm = L.conv2d(xm, *We, pad='same', relu=True)
+                if BNd[p] is not None:
+                    xm = batchnorm_batch_stats(xm, BNd[p][0], BNd[p][1])
+                out.append(xm)
+                xm = L.maxpool2(xm)
+                if p + 1 == n_pool and n_pool > 0:
+                    xm = torch.cat([h, xm], dim=1)
+            return out
+        if isinstance(mask_source_y, (list, tuple)):
+            # one noised input PER DePool2D: every DePool2D calls get_output(...) itself (layers/mylayers.py:91-93), and every
+            # symbolic call of GaussianNoiseLayer is a new, independent random stream in Theano -- level p's mask comes from its
+            # own pass on y + N_p (observed by executing the reference with logged draws: tests/golden/ref_noise.npz)
+            assert len(mask_source_y) == total
+            pre = [mask_pass(mask_source_y[p], p + 1)[p] for p in range(total)]
+        else:
+            pre = mask_pass(y if mask_source_y is None else mask_source_y, total)
     u = pools[-1]
     for i, p in enumerate(range(total, 0, -1)):
         if unpool_type == 'standard':

@@ -131,7 +131,24 @@ def get_all_layers(layer, treat_as_input=None):
     return result
 
 
+GET_OUTPUT_LOG = []          # top-level get_output calls: which random nodes each one created (see theano.sandbox.rng_mrg)
+_DEPTH = [0]
+
+
 def get_output(layer_or_layers, inputs=None, **kwargs):
+    from theano.sandbox import rng_mrg
+    top = _DEPTH[0] == 0
+    before = rng_mrg.STATE['created']
+    _DEPTH[0] += 1
+    try:
+        return _get_output(layer_or_layers, inputs, **kwargs)
+    finally:
+        _DEPTH[0] -= 1
+        if top:
+            GET_OUTPUT_LOG.append({'kwargs': dict(kwargs), 'created': (before, rng_mrg.STATE['created'])})
+
+
+def _get_output(layer_or_layers, inputs=None, **kwargs):
     treat_as_input = list(inputs.keys()) if isinstance(inputs, dict) else []
     all_layers = get_all_layers(layer_or_layers, treat_as_input)
     all_outputs = dict((layer, layer.input_var) for layer in all_layers if isinstance(layer, InputLayer) and layer not in treat_as_input)
@@ -658,12 +675,14 @@ class DropoutLayer(Layer):
 class GaussianNoiseLayer(Layer):
     def __init__(self, incoming, sigma=0.1, **kwargs):
         Layer.__init__(self, incoming, **kwargs)
+        from theano.sandbox.rng_mrg import MRG_RandomStreams as RandomStreams
+        self._srng = RandomStreams(get_rng().randint(1, 2147462579))
         self.sigma = sigma
 
     def get_output_for(self, input, deterministic=False, **kwargs):
         if deterministic or self.sigma == 0:
             return input
-        raise NotImplementedError('random streams are not reproduced by the stand-in')
+        return input + self._srng.normal(input.shape, avg=0.0, std=self.sigma)          # a NEW random node per symbolic call
 
 
 class BatchNormLayer(Layer):

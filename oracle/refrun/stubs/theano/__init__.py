@@ -261,6 +261,8 @@ class Function(object):
 
     def __call__(self, *args):
         assert len(args) == len(self.inputs), 'expected %d inputs, got %d' % (len(self.inputs), len(args))
+        from .sandbox import rng_mrg
+        rng_mrg.STATE['call'] += 1          # random draws are logged with the function call that consumed them
         env = {}
         for var, val in zip(self.inputs, args):
             t = torch.tensor(np.asarray(val), dtype=_dtype(var.dtype))

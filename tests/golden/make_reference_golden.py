@@ -79,6 +79,11 @@ CASES = {
     # The fixture keeps the argmax labels in full and every third pixel of the probabilities (`sub`).
     'ref_full_size': dict(script='inference', dae=dae_dict(), H=360, W=480, B=1, nbatches=1, num_iter=50, step=0.05, sub=3,
                           weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    # noise > 0 (the valid script's default 0.5): every DePool2D's mask sub-graph draws its own Gaussian noise, even at inference
+    # (layers/mylayers.py:91-93).  The stand-in's draws are logged, so the fixture records which draw fed which DePool2D level
+    # in which function call (`noise_k`) and a test regenerates the same numbers (oracle/refrun/stubs/theano/sandbox/rng_mrg.py).
+    'ref_noise': dict(script='inference', dae=dae_dict(noise=0.5), H=32, W=40, B=2, nbatches=1, num_iter=3, step=0.05,
+                      weights=dict(fn='dae', seed=1, out_gain=0.1)),
     # FC-DenseNet103 conditioning (models/FCDenseNet.py:Network / build_fcdensenet are the reference's; its four layer helpers
     # come from the absent FC_DenseNet package and are restated in oracle/refrun/stubs/FC_DenseNet/layers.py)
     'ref_densenet': dict(script='inference', segm_net='densenet', dae=dae_dict(), H=64, W=96, B=2, nbatches=1, num_iter=3, step=0.05,
@@ -149,6 +154,26 @@ def param_digest(i, after, before):
     idx = np.unique(np.linspace(0, flat.size - 1, min(flat.size, 4096)).astype(np.int64))
     delta = flat.astype(np.float64) - np.asarray(before, np.float64).reshape(-1)
     return {'p%d_sample' % i: flat[idx], 'p%d_delta' % i: np.array([delta.sum(), np.sqrt((delta ** 2).sum()), np.abs(delta).max()])}
+
+
+def noise_log(case, get_output_calls, draws):
+    """Which logged draw fed which DePool2D in which function call.  The graph of pred_dae (and of de = y - pred_dae) is the
+    top-level get_output(dae, deterministic=True) call: its main GaussianNoiseLayer is the identity, so the random nodes it
+    created are exactly the DePool2D sub-graphs', in get_all_layers order up_P .. up_1.  -> noise_k [calls, levels]: entry
+    [c, p - 1] = index k of the draw that level p's mask pass used in the c-th pred_dae_fn / de_fn call."""
+    total = (int(case['dae']['concat_h'][-1][-1]) if 'pool' in case['dae']['concat_h'][-1] else 0) + case['dae']['additional_pool']
+    cands = [g['created'] for g in get_output_calls if g['kwargs'] == {'deterministic': True} and g['created'][1] - g['created'][0] == total]
+    assert len(cands) == 1, cands
+    a, b = cands[0]
+    rows = {}
+    for d in draws:
+        if a <= d['created'] < b:
+            level = total - (d['created'] - a)                     # created in the order up_P .. up_1
+            rows.setdefault(d['call'], {})[level] = (d['k'], d['shape'])
+    calls = sorted(rows)
+    assert all(sorted(rows[c]) == list(range(1, total + 1)) for c in calls)
+    return {'noise_k': np.array([[rows[c][l][0] for l in range(1, total + 1)] for c in calls], np.int64),
+            'noise_batch': np.array([rows[c][1][1][0] for c in calls], np.int64)}
 
 
 class SyntheticCamvidIterator(object):
@@ -265,11 +290,16 @@ def run_case(name, case, current):
             np.load = lambda path, *a, **kw: real_load(os.path.join(wdir, 'densenet.npz') if path == DENSENET_HARDCODED_PATH else path, *a, **kw)
             os.rename(ldir, ldir.replace(exp_name, exp_name.replace('fcn8', 'densenet', 1)))
             exp_name = exp_name.replace('fcn8', 'densenet', 1)
+        import lasagne.layers as LL
+        from theano.sandbox import rng_mrg
+        n_go, n_draws = len(LL.GET_OUTPUT_LOG), len(rng_mrg.STATE['log'])
         with contextlib.redirect_stdout(buf):
             res = mod.inference('camvid', segm_net, learn_step=case['step'], num_iter=case['num_iter'],
                                 dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])), training_dict=dict(TRAINING_DICT),
                                 data_augmentation=False, which_set='test', ae_h=False, savepath=os.path.join(WORK, 'save'),
                                 loadpath=os.path.join(WORK, 'load'))
+        if case['dae']['noise'] > 0:
+            out.update(noise_log(case, LL.GET_OUTPUT_LOG[n_go:], rng_mrg.STATE['log'][n_draws:]))
         if segm_net == 'densenet':
             np.load = real_load
         if case['script'] == 'inference':

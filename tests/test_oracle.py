@@ -291,6 +291,18 @@ from tests import reference_fixtures as RF  # noqa: E402
 REF_TOL = 2e-6          # float32 CPU arithmetic on both sides, different conv algorithms (measured: <= 3e-7)
 
 
+def fx_noise_rows(fx):
+    """Per pred_dae_fn / de_fn call of the reference run, in order: shape -> [N(0,1) tensor of level 1, ..., level P]."""
+    from oracle.refrun import py2import
+    py2import.install_stubs()
+    from theano.sandbox import rng_mrg
+    for ks, nb in zip(fx['noise_k'], fx['noise_batch']):
+        def make(shape, ks=ks, nb=nb):
+            assert shape[0] == nb, (tuple(shape), nb)
+            return [rng_mrg.draw(int(k), shape) for k in ks]
+        yield make
+
+
 def _oracle_replay(case):
     """The oracle's version of what the reference's driver did for `case`: per batch (Y_fcn, Y_ii, n_exec, batch metrics,
     FCN metrics, FCN+DAE metrics, per-image per-iteration metrics) and the accumulated valid_mat."""
@@ -307,6 +319,11 @@ def _oracle_replay(case):
     out, valid_mat = [], np.zeros((2, RF.NCLS, case['num_iter']))
     densenet = case.get('segm_net') == 'densenet'
     padding = 0 if densenet else 100          # iterative_inference.py:140,145
+    if d['kind'] == 'standard' and d['noise'] > 0:
+        # the DePool2D mask sub-graphs are noised even at inference: one independent draw per DePool2D and per function call.
+        # The fixture logged which draw of the stand-in's stream each one consumed; regenerate the same numbers.
+        noise_rows = iter(fx_noise_rows(case['_fixture']))
+        forward = lambda y, h: nets.dae_forward(pd, y, h, padding, mask_source_y=[y + d['noise'] * n for n in next(noise_rows)(y.shape)], **kw)          # noqa: E731
     if densenet:
         from oracle import densenet as OD
         pdn = G.case_densenet_params(case)
@@ -343,7 +360,7 @@ def test_oracle_vs_reference_run(name):
     iterative_inference_valid.py:inference executed through oracle/refrun): FCN8 probabilities, the loop's final y, the
     per-iteration and per-batch metrics it printed, valid_mat."""
     fx, case = RF.load(name)
-    got, valid_mat = _oracle_replay(case)
+    got, valid_mat = _oracle_replay(dict(case, _fixture=fx))
     per_iter_ref, blocks = RF.parse_stdout(str(fx['stdout']))
     rel = lambda a, b: abs(a - b) <= 2e-6 * max(1.0, abs(b)) or (np.isnan(a) and np.isnan(b))          # noqa: E731
     # accuracy / Jaccard are argmax counts: probabilities that agree to 2e-7 can still break one near-tie differently
