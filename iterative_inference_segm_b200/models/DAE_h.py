@@ -50,7 +50,7 @@ class DAENet(object):
         # noise > 0 the masks come from a SEPARATE pass of the contracting path on y + N(0, noise^2), even at inference.  In
         # this mode every application runs the contracting path twice: once on the noised input for the masks, once on y for
         # the values.
-        self.mask_noise = float(mask_noise) if unpool_type != 'standard' else 0.0
+        self.mask_noise = float(mask_noise) if unpool_type == 'trackind' else 0.0          # InverseLayer / Deconv2DLayer take the deterministic expressions
         # skip=False (models/fcn_up.py:103-113): no ElemwiseSumLayer; the up-conv is only centre-cropped to the size of
         # pool_{p-1} (CroppingLayer with merge_function = lambda input, deconv: deconv) -- the same windows, no addend
         self.skip = bool(skip)
@@ -305,7 +305,7 @@ class DAENet(object):
         return ws
 
     # -- one application ----------------------------------------------------
-    def _bn_mask_level(self, ws, x, p, pools, pad, kw, sizes, per_image):
+    def _bn_mask_level(self, ws, x, p, pools, pad, kw, sizes, per_image, pm):
         """One level of the bn=1 mask pass: conv + rectify to an fp32 map, its per-channel batch statistics
         (iiseg_channel_stats: mean and 1 / sqrt(biased variance + 1e-4) over batch, rows, cols), then the same conv again with
         (x - mean) * (gamma * inv_std) + beta, the 2x2 pool and the tie mask in its epilogue.  `per_image`: statistics per
@@ -331,8 +331,8 @@ class DAENet(object):
             K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, out=zb[a:b], split=self.split, **kwg)
             K.widen_nhwc(zb[a:b], z[a:b], split=self.split)        # (the (hi | lo) pair back to) one fp32 value per element
             K.channel_stats(z[a:b], 0, C_, mean, inv_std, scratch, eps=1e-4)
-            K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, pooled=pools[p][a:b], pool_mask=ws['mask'][p][a:b], split=self.split,
-                     post_affine=(gamma * inv_std, beta, mean), **kwg)
+            K.conv2d(x[a:b], Wk, bk, 3, 3, pad, relu=True, pooled=pools[p][a:b], pool_mask=pm[a:b] if pm is not None else None,
+                     split=self.split, post_affine=(gamma * inv_std, beta, mean), **kwg)
 
     def logits(self, h_bf16, y_bf16, full_down=True, update=None, y_f32=None, noise=None, per_image_stats=False):
         """h_bf16: NHWC bf16 (B, Hh, Wh, h_pad); y_bf16: NHWC bf16 (B, H, W, y_cpad).
@@ -342,8 +342,8 @@ class DAENet(object):
         `update` (bf16 expanding path: 'bf16' and 'mixed'): dict(y, active, norm_acc, step) -- the softmax tail and the
         iterative-inference update run in the epilogue of the last conv (y and y_bf16 are updated in
         place, the logits are never stored) and None is returned.
-        `y_f32` (NCHW fp32, the values y_bf16 was packed from) and optionally `noise` (same shape, N(0,1); drawn here when
-        None) are needed when the net was built with mask_noise > 0."""
+        `y_f32` (NCHW fp32, the values y_bf16 was packed from) and optionally `noise` (a list of `total` N(0,1) tensors of that
+        shape, one per DePool2D, level 1 first; drawn here when None) are needed when the net was built with mask_noise > 0."""
         B, H, W, _ = y_bf16.shape
         if self.unpool_type == 'standard' or self.cbp > 1 or self.bn_batch_masks:
             full_down = True          # (no y-dependent windows for these variants: every level is computed in full)
@@ -360,24 +360,33 @@ class DAENet(object):
         if full_down:       # new h: the iteration-invariant half of the concat conv, once per batch, fp32
             K.conv2d(h_bf16, self.hproj_w[0], self.hproj_w[1], 3, 3, 1, relu=False, out=ws['hproj'], out_f32=True,
                      split=sp)
-        passes = [(x, True)]
+        # (input, role, levels computed, the one level whose mask this pass writes or None = all)
+        passes = [(x, True, self.total, None)]
         if self.mask_noise > 0:
-            # the mask sub-graph: the contracting path on y + sigma * noise writes the tie masks (its pooled values go to a
-            # scratch set), then the value pass below leaves the masks alone
+            # DePool2D's mask sub-graphs: every DePool2D calls lasagne.layers.get_output(...) itself (layers/mylayers.py:91-93)
+            # and every symbolic call of the GaussianNoiseLayer is an independent random stream, so level p's tie mask comes
+            # from ITS OWN pass of the contracting path (levels 1..p) on y + sigma * N_p -- observed by executing the reference
+            # with logged draws (tests/golden/ref_noise.npz).  The pooled values of those passes go to a scratch set; the value
+            # pass below leaves the masks alone.  `noise`: a list of `total` N(0,1) tensors (level 1 first); None: drawn here;
+            # a single tensor: one shared pass for all levels (the same marginal distribution per level, not the same joint).
             assert y_f32 is not None, 'mask_noise > 0 needs the fp32 y (y_f32=) to draw the noised input of the mask pass'
             if noise is None:
-                noise = torch.randn(y_f32.shape, dtype=torch.float32, device=y_f32.device)
-            x_noisy = K.noise_pack(y_f32, noise, self.mask_noise, self.y_cpad, split=sp)
+                noise = [torch.randn(y_f32.shape, dtype=torch.float32, device=y_f32.device) for _ in range(self.total)]
             if 'pool_m' not in ws:
                 ws['pool_m'] = [torch.empty_like(t) for t in ws['pool']]
-            passes = [(x_noisy, 'masks'), (x, 'values')]
+            if isinstance(noise, (list, tuple)):
+                assert len(noise) == self.total
+                passes = [(K.noise_pack(y_f32, nz, self.mask_noise, self.y_cpad, split=sp), 'masks', lvl + 1, lvl) for lvl, nz in enumerate(noise)]
+            else:
+                passes = [(K.noise_pack(y_f32, noise, self.mask_noise, self.y_cpad, split=sp), 'masks', self.total, None)]
+            passes.append((x, 'values', self.total, None))
         elif self.bn_batch_masks:
             if 'pool_m' not in ws:
                 ws['pool_m'] = [torch.empty_like(t) for t in ws['pool']]
-            passes = [(x, 'masks'), (x, 'values')]
-        for x, role in passes:
+            passes = [(x, 'masks', self.total, None), (x, 'values', self.total, None)]
+        for x, role, upto, only in passes:
             pools = ws['pool_m'] if role == 'masks' else ws['pool']
-            for p in range(self.total):
+            for p in range(upto):
                 Wk, bk = self.down[p]
                 pad = self.padding if (p == 0 and self.padding > 0) else 1
                 win = None
@@ -386,12 +395,12 @@ class DAENet(object):
                     win = (hl, wl, hh - hl, wh - wl)
                 # conv + ReLU with Pool2DLayer(2) and the DePool2D tie mask fused in the epilogue: the
                 # pre-pool map is consumed on chip and never written (nothing else reads it)
-                pm = ws['mask'][p] if role in (True, 'masks') else None
+                pm = ws['mask'][p] if (role is True or (role == 'masks' and only in (None, p))) else None
                 kw = {}
                 if p == self.n_pool:
                     kw = dict(addend=ws['hproj'], addend_off=(win[0], win[1]) if win else (0, 0))
                 if role == 'masks' and self.bn_batch_masks:
-                    self._bn_mask_level(ws, x, p, pools, pad, kw, sizes, per_image_stats)
+                    self._bn_mask_level(ws, x, p, pools, pad, kw, sizes, per_image_stats, pm)
                 elif self.cbp > 1:      # conv_p_1 .. conv_p_{k-1} write full pre-pool maps, conv_p_k carries the pool
                     pre = ws.setdefault(('pre', p), [None, None])
                     hh_, ww_ = sizes[p]

@@ -989,3 +989,47 @@ def test_valid_dropin_vs_reference_run(cuda, tmp_path, name):
     n_pix = case['B'] * case['nbatches'] * case['H'] * case['W']
     assert float(np.abs(vm - ref).max()) <= 2e-3 * n_pix, float(np.abs(vm - ref).max())          # a handful of argmax flips at most
     assert np.allclose(res, fx['res'], atol=1e-3, equal_nan=True), (res, fx['res'])
+
+
+def test_noised_mask_subgraphs_vs_reference_run(cuda):
+    """noise > 0 at inference (the valid script's default is 0.5): in the reference every DePool2D's mask sub-graph is noised
+    with ITS OWN draw (layers/mylayers.py:91-93; one independent random stream per symbolic call).  tests/golden/ref_noise.npz
+    is the reference's own run with the stand-in's logged, reproducible draws; feeding the same numbers to
+    `buildDAE(..., stochastic_masks=True)` -- level p's mask from a pass on y + 0.5 * N_p -- reproduces its loop at the fp32 bar."""
+    from tests.test_oracle import fx_noise_rows
+    from iterative_inference_segm_b200.models.DAE_h import buildDAE
+    from iterative_inference_segm_b200 import _kernels as K
+    G = RF.G
+    fx, case = RF.load('ref_noise')
+    pf = weights.synthetic_fcn8_params(3, NCLS, **G.FCN8_WEIGHTS)
+    pd = G.case_dae_params(case)
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, padding=100, concat_h=['pool4'], noise=case['dae']['noise'],
+                   n_filters=64, conv_before_pool=1, additional_pool=2, skip=True, unpool_type='trackind', params=pd, precision='mixed',
+                   stochastic_masks=True)
+    net = dae.net
+    X, _ = G.case_batch(case, 0)
+    h, y0 = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+    rows = list(fx_noise_rows(fx))
+    c, outs, shared = 1, [], []          # row 0 is the batch-of-2 pred_dae_fn call; then de_fn per image and iteration
+    for im in range(case['B']):
+        hd = K.pack_nchw(h[im:im + 1].to(cuda), net.h_pad, split=True)
+        y = y0[im:im + 1].to(cuda)
+        ys = y.clone()
+        for it in range(case['num_iter']):
+            noise = [n.to(cuda) for n in rows[c](y.shape)]
+            c += 1
+            for yy, nz, dst in ((y, noise, 'y'), (ys, noise[0], 'ys')):          # per-DePool2D draws / one shared draw
+                logits = net.logits(hd, K.pack_nchw(yy, net.y_cpad, split=True), y_f32=yy, noise=nz)
+                p = torch.empty_like(yy)
+                K.softmax_nchw(logits, NCLS, p)
+                if dst == 'y':
+                    y = torch.clamp(y - case['step'] * (y - p), 0.0, 1.0)
+                else:
+                    ys = torch.clamp(ys - case['step'] * (ys - p), 0.0, 1.0)
+        outs.append(y.cpu())
+        shared.append(ys.cpu())
+    err = float((torch.cat(outs).numpy() - fx['Y_ii_0']).__abs__().max())
+    err_shared = float((torch.cat(shared).numpy() - fx['Y_ii_0']).__abs__().max())
+    print('noise 0.5, per-DePool2D draws: y max-abs vs the reference run %.2e (one shared draw: %.2e)' % (err, err_shared))
+    assert err < TOL_F32, err
+    assert err_shared > 3 * err          # the joint distribution matters: a shared draw is not what the reference computes
