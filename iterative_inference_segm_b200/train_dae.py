@@ -153,12 +153,12 @@ class DAETrainer(object):
         return out
 
     # ------------------------------------------------------------------ forward
-    def _down(self, x0, h):
+    def _down(self, x0, h, upto=None):
         geo, sizes = self.geo, self._sizes
         pools, masks, zmasks = [], [], []
         x = x0
         B = x0.shape[0]
-        for p, lay in enumerate(self.down):
+        for p, lay in enumerate(self.down[:upto]):
             hh, ww = sizes[p]
             pooled = torch.empty((B, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
             mask = torch.empty((B, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
@@ -174,6 +174,8 @@ class DAETrainer(object):
 
     def forward(self, h_bf16, y, noise_main=None, noise_mask=None, forced=None):
         """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits.
+        `noise_mask`: [P, B, C, H, W] = one N(0,1) tensor per DePool2D, level 1 first (the reference's graph); [B, C, H, W] = one
+        shared mask pass; None = masks from the main pass.
         `forced` (parity tooling): dict(masksA, zmasks, masksB[, positive]) of per-level tensors that REPLACE the discrete
         decisions this pass takes -- which window elements are maxima (tie masks, nibble layout), which pre-rectifier
         values are exactly zero, and (`positive`: bool [B,h/2,w/2,C] per level) whether a window's maximum is positive, i.e.
@@ -186,7 +188,14 @@ class DAETrainer(object):
         st = self.st = {'B': B, 'H': H, 'W': W, 'h': h_bf16}
         st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
         st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
-        if noise_mask is not None:     # the DePool2D mask sub-graph: a separately noised contracting path
+        if noise_mask is not None and noise_mask.dim() == 5:
+            # the DePool2D mask sub-graphs as the reference's graph has them: every DePool2D re-evaluates the contracting path
+            # up to its own pool with an independent noise draw (layers/mylayers.py:91-93; tests/golden/ref_noise.npz), so
+            # level p's mask comes from a pass over levels 1..p on y + sigma * noise_mask[p - 1]
+            assert noise_mask.shape[0] == geo.total
+            st['masksB'] = [self._down(K.noise_pack(y, noise_mask[lvl], self.sigma, 16), h_bf16, upto=lvl + 1)[1][lvl]
+                            for lvl in range(geo.total)]
+        elif noise_mask is not None:     # one shared, separately noised contracting path for all levels
             _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
         else:
             st['masksB'] = st['masksA']
@@ -514,7 +523,7 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
             nm = nk = None
             if tr.sigma > 0:
                 nm = torch.randn(y.shape, device=tr.dev, generator=gen)
-                nk = torch.randn(y.shape, device=tr.dev, generator=gen)
+                nk = torch.randn((tr.geo.total,) + tuple(y.shape), device=tr.dev, generator=gen)      # one draw per DePool2D
             tr.step_graphed(h, y, Ld, nm, nk)
             cost += tr.loss_value()
         err_train.append(cost / train_iter.nbatches)

@@ -75,14 +75,16 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
     Wd = [(q(params[2 * i]), params[2 * i + 1]) for i in range(total)]
     Wu = [(q(params[2 * (total + i)]), params[2 * (total + i) + 1]) for i in range(total)]
     y_noisy, h = q(y_noisy), q(h)
-    if mask_source_y is not None:
+    if isinstance(mask_source_y, (list, tuple)):
+        mask_source_y = [q(m) for m in mask_source_y]
+    elif mask_source_y is not None:
         mask_source_y = q(mask_source_y)
 
     zero = []
 
-    def down(x, differentiable):
+    def down(x, differentiable, upto=total):
         pre, pools = [], []
-        for p in range(total):
+        for p in range(upto):
             pad = padding if (p == 0 and padding > 0) else 1
             a = q(F.conv2d(x, Wd[p][0], Wd[p][1], padding=pad))
             if differentiable:
@@ -101,6 +103,11 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
     pre, pools = down(y_noisy, True)
     if mask_source_y is None:
         masks = [L.tie_mask(r.detach()) for r in pre]
+    elif isinstance(mask_source_y, (list, tuple)):
+        # the reference's graph: an independent noise draw per DePool2D, level p's mask from its own pass over levels 1..p
+        assert len(mask_source_y) == total
+        with torch.no_grad():
+            masks = [L.tie_mask(down(mask_source_y[p], False, upto=p + 1)[0][p]) for p in range(total)]
     else:
         with torch.no_grad():
             pre_m, _ = down(mask_source_y, False)
@@ -151,7 +158,10 @@ def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=N
     lasagne.updates.rmsprop: a <- rho*a + (1-rho)*g^2 ; p <- p - lr * g / sqrt(a + eps)."""
     ps = [p.clone().requires_grad_(True) for p in params]
     y_main = y if noise_main is None else y + noise_main
-    y_mask = None if noise_mask is None else y + noise_mask
+    if isinstance(noise_mask, (list, tuple)) or (noise_mask is not None and noise_mask.dim() == 5):
+        y_mask = [y + n for n in noise_mask]          # one draw per DePool2D (level 1 first)
+    else:
+        y_mask = None if noise_mask is None else y + noise_mask
     logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, tap=tap, **dae_kw)
     loss = loss_fn(logits, target, n_classes, lmb=lmb)
     grads = torch.autograd.grad(loss, ps)

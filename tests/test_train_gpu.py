@@ -295,3 +295,36 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path):
     # rmsprop normalises every element's step to ~lr whatever its gradient's size: the NORM of an array's change is robust, single
     # elements whose gradient is ~0 are not (their sign is rounding, and bf16 operands flip pool ties: DESIGN.md 3.9)
     assert float(np.median(norms)) < 0.05 and worst_norm < 0.25          # measured: worst 0.15
+
+
+def test_train_forward_draws_one_mask_noise_per_depool(cuda):
+    """Training graph with noise > 0: the reference's DePool2D sub-graphs each carry their own GaussianNoiseLayer draw
+    (layers/mylayers.py:91-93; observed in tests/golden/ref_noise.npz), so level p's mask comes from a pass over levels 1..p on
+    y + sigma * N_p.  `noise_mask` of shape [P, B, C, H, W] selects that; the masks follow the oracle's per-level passes, and are
+    NOT those of one shared pass."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    from tests.test_streaming_kernels_gpu import _mask_to_dense
+    pd, h, y, L, nm, _ = _setup(cuda, structured=True)
+    sigma = 0.5
+    nk = torch.randn((6,) + tuple(y.shape), generator=torch.Generator().manual_seed(11))
+    tap, tap_shared = {}, {}
+    OT.dae_forward_train(pd, y + sigma * nm, h, 100, mask_source_y=[y + sigma * n for n in nk], emulate_bf16=True, tap=tap)
+    OT.dae_forward_train(pd, y + sigma * nm, h, 100, mask_source_y=y + sigma * nk[0], emulate_bf16=True, tap=tap_shared)
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=sigma)
+    tr.forward(K.pack_nchw(h.to(cuda), 512), y.to(cuda), nm.to(cuda), nk.to(cuda))
+    torch.cuda.synchronize()
+    for lvl in range(6):
+        C = tap['masksB'][lvl].shape[1]
+        got = _mask_to_dense(tr.st['masksB'][lvl], C)
+        want = tap['masksB'][lvl][:, :, :got.shape[2], :got.shape[3]].numpy()
+        shared = tap_shared['masksB'][lvl][:, :, :got.shape[2], :got.shape[3]].numpy()
+        agree, agree_shared = float((got == want).mean()), float((got == shared).mean())
+        print('level %d: mask agreement with the per-DePool2D oracle pass %.5f, with one shared pass %.5f' % (lvl + 1, agree, agree_shared))
+        assert agree > 0.998, (lvl, agree)
+        if lvl > 0:
+            assert agree_shared < agree - 0.002, (lvl, agree, agree_shared)          # level 1 uses draw 0 in both; measured 0.977-0.997 vs >= 0.99998
+    # the graphed step takes the same 5-D tensor
+    loss = tr.step_graphed(K.pack_nchw(h.to(cuda), 512), y.to(cuda), L.to(cuda), nm.to(cuda), nk.to(cuda))
+    loss = tr.step_graphed(K.pack_nchw(h.to(cuda), 512), y.to(cuda), L.to(cuda), nm.to(cuda), nk.to(cuda))
+    assert np.isfinite(float(loss))
