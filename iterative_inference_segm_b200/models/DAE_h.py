@@ -47,9 +47,9 @@ class DAENet(object):
         self.unpool_type = unpool_type
         # mask_noise > 0 (opt-in, `buildDAE(..., stochastic_masks=True)`): the reference's DePool2D builds its tie masks with
         # lasagne.layers.get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93), so when the DAE was built with
-        # noise > 0 the masks come from a SEPARATE pass of the contracting path on y + N(0, noise^2), even at inference.  In
-        # this mode every application runs the contracting path twice: once on the noised input for the masks, once on y for
-        # the values.
+        # noise > 0 the masks come from SEPARATE passes of the contracting path on y + N(0, noise^2), even at inference: one
+        # per DePool2D, each with its own draw (see `logits`).  In this mode every application runs the value pass on y plus,
+        # for level p, a mask pass over levels 1..p.
         self.mask_noise = float(mask_noise) if unpool_type == 'trackind' else 0.0          # InverseLayer / Deconv2DLayer take the deterministic expressions
         # skip=False (models/fcn_up.py:103-113): no ElemwiseSumLayer; the up-conv is only centre-cropped to the size of
         # pool_{p-1} (CroppingLayer with merge_function = lambda input, deconv: deconv) -- the same windows, no addend
