@@ -917,7 +917,8 @@ def _reference_layout(tmp_path, case, exp_name):
     return str(tmp_path / 'weights'), str(tmp_path / 'load'), str(tmp_path / 'save')
 
 
-@pytest.mark.parametrize('name', [n for n in RF.LOOP_CASES if RF.G.CASES[n]['script'] == 'inference'])
+# (ref_noise draws random numbers: test_noised_mask_subgraphs_vs_reference_run replays it with the logged draws)
+@pytest.mark.parametrize('name', [n for n in RF.LOOP_CASES if RF.G.CASES[n]['script'] == 'inference' and not RF.G.CASES[n]['dae']['noise']])
 def test_inference_dropin_vs_reference_run(cuda, tmp_path, name):
     """iterative_inference.inference() of this package against the reference's own run of iterative_inference.py:inference():
     the saved batch<i>.npz (Y_fcn, Y_ii) and the three print_results blocks of the summary."""
