@@ -36,11 +36,11 @@ DAE_DICT_DEFAULTS = {'kind': 'fcn8', 'dropout': 0.0, 'skip': True, 'unpool_type'
 
 
 def build_networks(segm_net, dae_dict, n_classes, nb_in_channels, void_labels, weights_path=None, loadpath=None,
-                   dataset='camvid', fcn_params=None, dae_params=None, precision='bf16', stochastic_masks=False):
+                   dataset='camvid', fcn_params=None, dae_params=None, precision='bf16', stochastic_masks=None):
     """The network-construction block of `inference` (iterative_inference.py:127-179).
     `precision` ('bf16' | 'fp32x3' | 'mixed') selects the arithmetic of both nets (see models/DAE_h.py).
-    `stochastic_masks`: restate the reference's non-deterministic DePool2D mask sub-graph when dae_dict['noise'] > 0
-    (layers/mylayers.py:91-93; default: the deterministic graph, with a warning)."""
+    `stochastic_masks`: the reference's non-deterministic DePool2D mask sub-graphs when dae_dict['noise'] > 0
+    (layers/mylayers.py:91-93): None = as the reference (on), False = the deterministic graph, with a warning."""
     if segm_net == 'fcn8':
         fcn = buildFCN8(nb_in_channels, None, n_classes=n_classes, void_labels=void_labels,
                         path_weights=os.path.join(weights_path or '', dataset, 'fcn8_model.npz'),
@@ -123,7 +123,7 @@ class _BatchStager(object):
 def inference(dataset, segm_net, learn_step=0.005, num_iter=500, dae_dict_updates={}, training_dict={},
               data_augmentation=False, which_set='test', ae_h=False, full_im_ft=False, savepath=None,
               loadpath=None, test_from_0_255=False, data_iter=None, fcn_params=None, dae_params=None,
-              weights_path=None, fused=True, verbose=True, save_batches=False, precision='bf16', stochastic_masks=False):
+              weights_path=None, fused=True, verbose=True, save_batches=False, precision='bf16', stochastic_masks=None):
     dae_dict = dict(DAE_DICT_DEFAULTS)
     dae_dict.update(dae_dict_updates)
     exp_name = build_experiment_name(segm_net, data_aug=data_augmentation, ae_h=ae_h,
@@ -280,7 +280,7 @@ def main():
     parser.add_argument('-loadpath', type=str, default='./iiseg_models/')
     parser.add_argument('-weights_path', type=str, default='./iiseg_models/')
     parser.add_argument('-precision', type=str, default='bf16', choices=['bf16', 'fp32x3', 'mixed'])
-    parser.add_argument('-stochastic_masks', type=_flag, default=False,
+    parser.add_argument('-stochastic_masks', type=_flag, default=None,
                         help="DePool2D masks from a separately noised pass when dae_dict['noise'] > 0, as the reference's graph does")
     args = parser.parse_args()
     inference(args.dataset, args.segmentation_net, float(args.step), int(args.num_iter), which_set=args.which_set,

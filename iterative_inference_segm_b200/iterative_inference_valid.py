@@ -24,7 +24,7 @@ STEPS = [.01, .02, .05, .08, .1, .5, 1.]      # iterative_inference_valid.py:373
 
 def sweep(dataset, segm_net, steps=STEPS, num_iter=50, dae_dict_updates={}, which_set='val', data_iter=None,
           fcn_params=None, dae_params=None, weights_path=None, loadpath=None, verbose=True,
-          precision='bf16', savepath=None, eps=_EPSILON, stochastic_masks=False):
+          precision='bf16', savepath=None, eps=_EPSILON, stochastic_masks=None):
     """Returns (all_results[len(steps), num_iter], valid_mats[len(steps), 2, C, num_iter]).  `eps` is the convergence
     threshold of the loop (the reference's _EPSILON = 1e-3, iterative_inference_valid.py:53)."""
     dae_dict = dict(DAE_DICT_DEFAULTS)

@@ -45,7 +45,7 @@ class DAENet(object):
         # (models/fcn_up.py:37-63) replaces unpool + conv by Deconv2DLayer(4, stride=2), run as four 2x2 phase convs
         assert unpool_type in ('trackind', 'inverse', 'standard'), unpool_type
         self.unpool_type = unpool_type
-        # mask_noise > 0 (opt-in, `buildDAE(..., stochastic_masks=True)`): the reference's DePool2D builds its tie masks with
+        # mask_noise > 0 (`buildDAE(..., noise > 0)`; `stochastic_masks=False` turns it off): the reference's DePool2D builds its tie masks with
         # lasagne.layers.get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93), so when the DAE was built with
         # noise > 0 the masks come from SEPARATE passes of the contracting path on y + N(0, noise^2), even at inference: one
         # per DePool2D, each with its own draw (see `logits`).  In this mode every application runs the value pass on y plus,
@@ -512,7 +512,7 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
              model_name='dae_model.npz', trainable=False, load_weights=False,
              out_nonlin=None, concat_h=['input'], noise=0.1, n_filters=64,
              conv_before_pool=1, additional_pool=0, dropout=0., skip=False,
-             unpool_type='standard', bn=0, params=None, precision='bf16', stochastic_masks=False):
+             unpool_type='standard', bn=0, params=None, precision='bf16', stochastic_masks=None):
     """Same arguments as the reference builder (models/DAE_h.py:12-17); returns the handle
     of 'probs_dimshuffle'.  The symbolic inputs are ignored.  Built for the benchmark
     configuration; other variants raise.  `noise` only matters for training and for the
@@ -530,9 +530,11 @@ def buildDAE(input_concat_h_vars, input_mask_var, n_classes, nb_features_to_conc
     # change inference.  NB the reference builds DePool2D's mask sub-graph WITHOUT deterministic (layers/mylayers.py:91-93):
     # with noise > 0 or dropout > 0 its masks come from a separately noised / dropped-out pass even at test time.  This
     # build is the deterministic graph; warn so that a caller comparing against such a reference run knows.
+    if stochastic_masks is None:          # as the reference: its DePool2D mask sub-graphs are noised whenever the DAE has noise > 0
+        stochastic_masks = noise > 0
     if unpool_type == 'trackind' and (dropout > 0 or (noise > 0 and not stochastic_masks)):
         warnings.warn('buildDAE: noise=%s dropout=%s only affect the reference\'s non-deterministic DePool2D mask sub-graph at '
-                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise: pass stochastic_masks=True for the reference\'s noised mask pass; bn=1: the batch-statistics mask pass is always built)' % (noise, dropout), stacklevel=2)
+                      'inference (layers/mylayers.py:91-93); this build uses the deterministic masks (noise > 0 with stochastic_masks=False was requested, or dropout, whose mask stream is not built; bn=1: the batch-statistics mask pass is always built)' % (noise, dropout), stacklevel=2)
     concat_h = list(concat_h)
     if len(concat_h) != 1 or not (concat_h[-1] == 'input' or concat_h[-1] in ('pool1', 'pool2', 'pool3', 'pool4', 'pool5')):
         # (several entries share ONE nb_features_to_concat in the reference, models/model_helpers.py:91, so they only build

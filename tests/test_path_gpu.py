@@ -593,8 +593,9 @@ def test_dae_with_batchnorm_vs_oracle(cuda, unpool_type):
 def test_stochastic_mask_subgraph_opt_in(cuda):
     """The reference's DePool2D builds its masks with get_output(...) WITHOUT deterministic=True (layers/mylayers.py:91-93): for a
     DAE built with noise > 0 (the README's 0.5) the tie masks come from a separate pass of the contracting path on
-    y + N(0, noise^2), even at inference.  `buildDAE(..., stochastic_masks=True)` restates that: with the SAME noise tensor the
-    device application tracks the oracle's `mask_source_y` form; the default build stays the deterministic graph (and warns)."""
+    y + N(0, noise^2), even at inference.  `buildDAE(..., noise > 0)` does the same (`stochastic_masks=False` asks for the
+    deterministic graph and warns): with the SAME noise tensor the device application tracks the oracle's `mask_source_y` form
+    (here one shared draw; test_noised_mask_subgraphs_vs_reference_run covers the reference's one draw per DePool2D)."""
     import warnings
     from iterative_inference_segm_b200.models.DAE_h import buildDAE
     from iterative_inference_segm_b200.functions import IterativeInference
@@ -605,10 +606,11 @@ def test_stochastic_mask_subgraph_opt_in(cuda):
               params=pd, precision='mixed')
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter('always')
-        buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, **kw)
-        assert any('deterministic masks' in str(x.message) for x in w)
-    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, stochastic_masks=True, **kw)
+        det = buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, stochastic_masks=False, **kw)
+        assert any('deterministic masks' in str(x.message) for x in w) and det.net.mask_noise == 0.0
+    dae = buildDAE([None], None, NCLS, nb_features_to_concat=512, noise=0.5, **kw)          # default: as the reference
     net = dae.net
+    assert net.mask_noise == 0.5
     X, L, lab = weights.synthetic_batch(2, 32, 40, NCLS, seed=23)
     h, y0 = nets.fcn8_forward(pf, X, NCLS)
     noise = torch.randn(y0.shape, generator=torch.Generator().manual_seed(5))
