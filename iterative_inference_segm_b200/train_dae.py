@@ -172,6 +172,32 @@ class DAETrainer(object):
             x = pooled
         return pools, masks, zmasks
 
+    batched_mask_passes = True
+
+    def _down_mask_passes(self, y, noise_mask, h):
+        """The P mask passes of the per-DePool2D noise graph run TOGETHER: pass p needs levels 1..p, so level l is one launch over
+        the passes l..P that still need it (batch (P - l + 1) * B instead of P - l + 1 launches of batch B); pass l's images come
+        first in that batch, its mask is the first B images of the level's mask tensor, and the rest moves on.  Per-image results
+        do not depend on the batch they are computed in, so the masks are bit-identical to those of separate passes."""
+        geo, sizes = self.geo, self._sizes
+        P, B = geo.total, y.shape[0]
+        x = K.noise_pack(y.repeat(P, 1, 1, 1), noise_mask.reshape((P * B,) + tuple(y.shape[1:])), self.sigma, 16)
+        masks = []
+        for p, lay in enumerate(self.down):
+            n = (P - p) * B
+            hh, ww = sizes[p]
+            pooled = torch.empty((n, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
+            mask = torch.empty((n, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
+            zmask = torch.empty_like(mask)
+            pad = geo.padding if (p == 0 and geo.padding > 0) else 1
+            if p == geo.n_pool:
+                K.conv2d(h.repeat(P - p, 1, 1, 1), lay.wb, lay.b, 3, 3, pad, relu=True, src1=x, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            else:
+                K.conv2d(x, lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            masks.append(mask[:B])
+            x = pooled[B:]
+        return masks
+
     def forward(self, h_bf16, y, noise_main=None, noise_mask=None, forced=None):
         """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits.
         `noise_mask`: [P, B, C, H, W] = one N(0,1) tensor per DePool2D, level 1 first (the reference's graph); [B, C, H, W] = one
@@ -193,8 +219,11 @@ class DAETrainer(object):
             # up to its own pool with an independent noise draw (layers/mylayers.py:91-93; tests/golden/ref_noise.npz), so
             # level p's mask comes from a pass over levels 1..p on y + sigma * noise_mask[p - 1]
             assert noise_mask.shape[0] == geo.total
-            st['masksB'] = [self._down(K.noise_pack(y, noise_mask[lvl], self.sigma, 16), h_bf16, upto=lvl + 1)[1][lvl]
-                            for lvl in range(geo.total)]
+            if self.batched_mask_passes:
+                st['masksB'] = self._down_mask_passes(y, noise_mask, h_bf16)
+            else:
+                st['masksB'] = [self._down(K.noise_pack(y, noise_mask[lvl], self.sigma, 16), h_bf16, upto=lvl + 1)[1][lvl]
+                                for lvl in range(geo.total)]
         elif noise_mask is not None:     # one shared, separately noised contracting path for all levels
             _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
         else:

@@ -325,6 +325,12 @@ def test_train_forward_draws_one_mask_noise_per_depool(cuda):
         if lvl > 0:
             assert agree_shared < agree - 0.002, (lvl, agree, agree_shared)          # level 1 uses draw 0 in both; measured 0.977-0.997 vs >= 0.99998
     # the graphed step takes the same 5-D tensor
+    # the six passes run batched level by level (DAETrainer._down_mask_passes): bit-identical to six separate passes
+    batched = [m.clone() for m in tr.st['masksB']]
+    tr.batched_mask_passes = False
+    tr.forward(K.pack_nchw(h.to(cuda), 512), y.to(cuda), nm.to(cuda), nk.to(cuda))
+    assert all(torch.equal(a, b) for a, b in zip(batched, tr.st['masksB']))
+    tr.batched_mask_passes = True
     for _ in range(2):          # eager, then captured
         tr.step_graphed(K.pack_nchw(h.to(cuda), 512), y.to(cuda), L.to(cuda), nm.to(cuda), nk.to(cuda))
     assert np.isfinite(tr.loss_value())
