@@ -221,7 +221,7 @@ def install_environment():
     return current
 
 
-def run_case(name, case, current):
+def run_case(name, case, current, write=True):
     from oracle import weights
     current['case'] = case
     shutil.rmtree(WORK, ignore_errors=True)
@@ -292,6 +292,7 @@ def run_case(name, case, current):
             exp_name = exp_name.replace('fcn8', 'densenet', 1)
         import lasagne.layers as LL
         from theano.sandbox import rng_mrg
+        rng_mrg.STATE['evaluated'] = 0          # draw k of THIS case (the fixture does not depend on what ran before it)
         n_go, n_draws = len(LL.GET_OUTPUT_LOG), len(rng_mrg.STATE['log'])
         with contextlib.redirect_stdout(buf):
             res = mod.inference('camvid', segm_net, learn_step=case['step'], num_iter=case['num_iter'],
@@ -322,12 +323,35 @@ def run_case(name, case, current):
                 out['valid_mat'] = f['arr_0']
             out['res'] = np.asarray(res)
     out['stdout'] = np.array(buf.getvalue())
-    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    if write:
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     shutil.rmtree(WORK, ignore_errors=True)
     return out
 
 
+def check(names):
+    """`--check NAME...`: execute the reference again and compare with the committed fixtures (nothing is written).  Arrays must
+    be identical; the captured stdout may differ only in the absolute paths it prints."""
+    current = install_environment()
+    global WORK
+    WORK = os.path.join(HERE, '_work_check')
+    for name in names:
+        out = run_case(name, CASES[name], current, write=False)
+        with np.load(os.path.join(HERE, name + '.npz')) as f:
+            assert sorted(f.files) == sorted(out), (sorted(f.files), sorted(out))
+            for k in f.files:
+                if k == 'stdout':
+                    strip = lambda t: [ln for ln in str(t).split('\n') if '_work' not in ln]          # noqa: E731
+                    assert strip(f[k]) == strip(out[k]), 'stdout of %s differs' % name
+                else:
+                    assert np.array_equal(f[k], out[k]), '%s: %s differs from the committed fixture' % (name, k)
+        print('%s: the reference, executed again, reproduces the committed fixture exactly' % name)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:2] == ['--check']:
+        check(sys.argv[2:])
+        sys.exit(0)
     current = install_environment()
     names = sys.argv[1:] or list(CASES)
     for name in names:

@@ -469,3 +469,17 @@ def test_oracle_train_step_vs_reference_run():
         assert err <= 2e-3 * step, (i, err, step)
         assert np.allclose(dig['p%d_delta' % i][1], fx['p%d_delta' % i][1], rtol=1e-3), (i, dig['p%d_delta' % i], fx['p%d_delta' % i])
     print('trained parameters: worst sample error / largest update = %.2e' % worst)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='the reference tree only exists in the build container')
+def test_reference_executed_again_reproduces_the_fixtures():
+    """Where /root/reference is present, EXECUTE THE REFERENCE (its own inference() drivers, through oracle/refrun) again and
+    require the committed fixtures bit for bit: the fixtures are what the reference computes, not hand-edited arrays.  Runs in a
+    subprocess (the harness replaces modules such as data_loader); two small cases, ~40 s."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'tests.golden.make_reference_golden', '--check', 'ref_noskip', 'ref_noise'], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count('reproduces the committed fixture exactly') == 2
