@@ -70,6 +70,8 @@ CASES = {
                                   step=0.05, weights=dict(fn='dae', seed=6, out_gain=0.1)),
     'ref_concat_input': dict(script='inference', dae=dae_dict(concat_h=['input'], additional_pool=3), H=32, W=40, B=2, nbatches=1,
                              num_iter=4, step=0.05, weights=dict(fn='dae', seed=8, out_gain=0.1)),
+    'ref_pool3': dict(script='inference', dae=dae_dict(concat_h=['pool3'], additional_pool=1), H=32, W=40, B=2, nbatches=1, num_iter=4,
+                      step=0.05, weights=dict(fn='dae', seed=9, out_gain=0.1, nb_h=256)),
     'ref_contextmod': dict(script='inference', dae=dae_dict(kind='contextmod', concat_h=['input']), H=32, W=40, B=2, nbatches=1,
                            num_iter=4, step=0.05, weights=dict(fn='contextmod', seed=3)),
     'ref_fcn8_dae': dict(script='inference', dae=dae_dict(kind='fcn8', concat_h=['pool4']), H=32, W=40, B=1, nbatches=1, num_iter=3,
