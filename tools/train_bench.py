@@ -18,7 +18,7 @@ gen = torch.Generator(device='cuda').manual_seed(1)
 
 def step():
     nm = torch.randn(y.shape, device='cuda', generator=gen)
-    nk = torch.randn(y.shape, device='cuda', generator=gen)
+    nk = torch.randn((6,) + tuple(y.shape), device='cuda', generator=gen)      # one mask-noise draw per DePool2D (the reference's graph)
     tr.step(h, y, L, nm, nk)
 
 losses = []
@@ -35,7 +35,7 @@ ms = s.elapsed_time(e) / n
 losses.append(tr.loss_value())
 def step_g():
     nm = torch.randn(y.shape, device='cuda', generator=gen)
-    nk = torch.randn(y.shape, device='cuda', generator=gen)
+    nk = torch.randn((6,) + tuple(y.shape), device='cuda', generator=gen)      # one mask-noise draw per DePool2D (the reference's graph)
     tr.step_graphed(h, y, L, nm, nk)
 
 for _ in range(3):
