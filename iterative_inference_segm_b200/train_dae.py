@@ -454,11 +454,13 @@ class DAETrainer(object):
 # The host loop of the reference's train() (train_dae.py:351-457): epochs, validation, learning-rate annealing,
 # patience, best / last checkpoints in the reference's positional .npz layout.
 # ---------------------------------------------------------------------------
-def validate(trainer, h_bf16, y, target):
-    """`val_fn` of train_dae.py:338: [test_loss, test_jacc (2, C) float32, test_mse_loss] with the deterministic DAE
-    (no noise; with noise == 0 at build time the mask sub-graph is deterministic too, layers/mylayers.py:91-93)."""
+def validate(trainer, h_bf16, y, target, noise_mask=None):
+    """`val_fn` of train_dae.py:338: [test_loss, test_jacc (2, C) float32, test_mse_loss].  deterministic=True switches the
+    main GaussianNoiseLayer off, but NOT the DePool2D sub-graphs (layers/mylayers.py:91-93): for a DAE with noise > 0 the
+    reference's validation masks are noised as well, one draw per DePool2D (`noise_mask` [P, B, C, H, W]; tests/golden/
+    ref_train_noise.npz); with noise == 0 everything is deterministic."""
     from .functions import MetricsAccumulator, jaccard_from_cm
-    logits = trainer.forward(h_bf16, y, None, None)
+    logits = trainer.forward(h_bf16, y, None, noise_mask)
     K.loss_grad(logits, target, trainer.C, trainer.lmb, trainer.sums, passes=1)          # loss sums only
     s = trainer.sums.cpu()
     loss = float(s[0] / s[1] + trainer.lmb * s[2] / s[3])
@@ -559,7 +561,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
         cv, jv, mv = 0.0, 0, 0.0
         for _ in range(val_iter.nbatches):
             h, y, Ld = batch(val_iter)
-            c, j, m = validate(tr, h, y, Ld)
+            nk = torch.randn((tr.geo.total,) + tuple(y.shape), device=tr.dev, generator=gen) if tr.sigma > 0 else None
+            c, j, m = validate(tr, h, y, Ld, nk)
             cv += c; jv = jv + j; mv += m
         err_valid.append(cv / val_iter.nbatches)
         with np.errstate(divide='ignore', invalid='ignore'):

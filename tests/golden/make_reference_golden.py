@@ -92,6 +92,11 @@ CASES = {
                          weights=dict(fn='dae', seed=1, out_gain=0.1, nb_h=464), densenet=dict(seed=2, logit_gain=4.0, bn_seed=5)),
     # train_dae.py:train(): two epochs of two rmsprop steps each (lr annealed in between) + validation, resumed from a seeded
     # checkpoint; noise = 0 (the MRG stream is not reproduced)
+    # ... and with noise = 0.5 (BASELINE config 4): the stand-in's draws are logged, so the fixture records which draw was the
+    # main GaussianNoiseLayer's and which fed which DePool2D, in training AND in validation (whose masks are noised too)
+    'ref_train_noise': dict(script='train', dae=dae_dict(noise=0.5), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
+                            learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'],
+                            weights=dict(fn='dae', seed=1, out_gain=0.1)),
     'ref_train': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2, learning_rate=0.001,
                       lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'], weights=dict(fn='dae', seed=1, out_gain=0.1)),
 }
@@ -178,6 +183,30 @@ def noise_log(case, get_output_calls, draws):
             'noise_batch': np.array([rows[c][1][1][0] for c in calls], np.int64)}
 
 
+def train_noise_log(case, get_output_calls, draws):
+    """train_dae.py with noise > 0.  The training graph is get_output(dae_lays, batch_norm_use_averages=False): it creates the
+    main GaussianNoiseLayer node (first: the layer sits at the bottom of the net) and one node per DePool2D (up_P .. up_1); the
+    validation graph get_output(dae_lays, deterministic=True, batch_norm_use_averages=False) only the DePool2D ones.
+    -> train_k [train_fn calls, 1 + P] (main, level 1 .. P) and val_k [val_fn calls, P] of draw indices."""
+    total = (int(case['dae']['concat_h'][-1][-1]) if 'pool' in case['dae']['concat_h'][-1] else 0) + case['dae']['additional_pool']
+    tr = [g['created'] for g in get_output_calls if g['kwargs'] == {'batch_norm_use_averages': False} and g['created'][1] - g['created'][0] == total + 1]
+    va = [g['created'] for g in get_output_calls if g['kwargs'] == {'deterministic': True, 'batch_norm_use_averages': False}
+          and g['created'][1] - g['created'][0] == total]
+    assert len(tr) == 1 and len(va) == 1, (tr, va)
+    rows_t, rows_v = {}, {}
+    for d in draws:
+        if tr[0][0] <= d['created'] < tr[0][1]:
+            j = d['created'] - tr[0][0]                               # 0 = main, then up_P .. up_1
+            rows_t.setdefault(d['call'], {})[0 if j == 0 else total + 1 - j] = d['k']
+        elif va[0][0] <= d['created'] < va[0][1]:
+            rows_v.setdefault(d['call'], {})[total - (d['created'] - va[0][0])] = d['k']
+    ct, cv = sorted(rows_t), sorted(rows_v)
+    assert all(sorted(rows_t[c]) == list(range(total + 1)) for c in ct) and all(sorted(rows_v[c]) == list(range(1, total + 1)) for c in cv)
+    return {'train_k': np.array([[rows_t[c][j] for j in range(total + 1)] for c in ct], np.int64),
+            'val_k': np.array([[rows_v[c][l] for l in range(1, total + 1)] for c in cv], np.int64),
+            'call_order': np.array([0 if c in rows_t else 1 for c in sorted(ct + cv)], np.int64)}
+
+
 class SyntheticCamvidIterator(object):
     """The attributes and the `next()` protocol iterative_inference.py:117-125,249 use from a dataset_loaders iterator."""
 
@@ -257,6 +286,10 @@ def run_case(name, case, current, write=True):
         ldir = os.path.join(WORK, 'load', 'camvid', exp_name)
         os.makedirs(ldir)
         weights.save_npz(os.path.join(ldir, 'dae_model_best.npz'), case_dae_params(case))          # resume=True reads it (train_dae.py:186)
+        import lasagne.layers as LL
+        from theano.sandbox import rng_mrg
+        rng_mrg.STATE['evaluated'] = 0
+        n_go, n_draws = len(LL.GET_OUTPUT_LOG), len(rng_mrg.STATE['log'])
         with contextlib.redirect_stdout(buf):
             train_dae.train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
                             num_epochs=case['num_epochs'], max_patience=100, optimizer='rmsprop', training_loss=list(case['training_loss']),
@@ -275,6 +308,8 @@ def run_case(name, case, current, write=True):
         with np.load(os.path.join(sdir, saved[0].replace('model', 'errors'))) as f:
             out['err_train'], out['err_valid'], out['jacc_val'], out['mse_val'] = [np.asarray(f['arr_%d' % i]) for i in range(4)]
         out['output_log'] = np.array(open(os.path.join(sdir, 'output.log')).read())
+        if case['dae']['noise'] > 0:
+            out.update(train_noise_log(case, LL.GET_OUTPUT_LOG[n_go:], rng_mrg.STATE['log'][n_draws:]))
     else:
         import helpers
         mod = __import__('iterative_inference' if case['script'] == 'inference' else 'iterative_inference_valid')

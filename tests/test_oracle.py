@@ -418,14 +418,22 @@ def test_oracle_temperature_vs_reference_run():
     assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
 
 
-def test_oracle_train_step_vs_reference_run():
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise'])
+def test_oracle_train_step_vs_reference_run(name):
     """oracle/train.py against the reference's own train_dae.py:train() (two epochs of two rmsprop steps, the learning rate
-    annealed in between, validation after each epoch; tests/golden/ref_train.npz): per-epoch training / validation cost,
+    annealed in between, validation after each epoch; tests/golden/ref_train.npz, and ref_train_noise.npz with noise = 0.5 and
+    the logged draws): per-epoch training / validation cost,
     validation Jaccard and squared error, and the parameters the reference saved after the fourth step (digest: 4096 strided
     samples per array + the sum / norm / max of each array's change)."""
     from oracle import train as T_
     G = RF.G
-    fx, case = RF.load('ref_train')
+    fx, case = RF.load(name)
+    sigma = case['dae']['noise']
+    if sigma > 0:          # ref_train_noise: regenerate the numbers the reference consumed (main draw + one per DePool2D, also in validation)
+        from oracle.refrun import py2import
+        py2import.install_stubs()
+        from theano.sandbox import rng_mrg
+        train_k, val_k = iter(fx['train_k']), iter(fx['val_k'])
     pf = weights.synthetic_fcn8_params(3, RF.NCLS, **G.FCN8_WEIGHTS)
     init = G.case_dae_params(case)
     params, accus = [p.clone() for p in init], [torch.zeros_like(p) for p in init]
@@ -436,7 +444,11 @@ def test_oracle_train_step_vs_reference_run():
         for i in range(case['nbatches']):                      # train_dae.py:356-383
             X, Lb = G.case_batch(case, i, 'train')
             h, y = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)
-            loss, _, params, accus = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'])
+            nkw = {}
+            if sigma > 0:
+                ks = next(train_k)
+                nkw = dict(noise_main=sigma * rng_mrg.draw(int(ks[0]), y.shape), noise_mask=[sigma * rng_mrg.draw(int(k), y.shape) for k in ks[1:]])
+            loss, _, params, accus = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], **nkw)
             tot += loss
         err_train.append(tot / case['nbatches'])
         cost, jacc, mse = 0.0, 0.0, 0.0
@@ -444,7 +456,9 @@ def test_oracle_train_step_vs_reference_run():
             X, Lb = G.case_batch(case, i, 'val')
             h, y = nets.fcn8_forward(pf, torch.from_numpy(X), RF.NCLS)
             with torch.no_grad():
-                logits = T_.dae_forward_train(params, y, h, 100)
+                # validation: deterministic=True switches the main noise off, but the DePool2D sub-graphs stay noised
+                msk = [y + sigma * rng_mrg.draw(int(k), y.shape) for k in next(val_k)] if sigma > 0 else None
+                logits = T_.dae_forward_train(params, y, h, 100, mask_source_y=msk)
                 cost += float(T_.loss_fn(logits, torch.from_numpy(Lb), RF.NCLS, lmb=case['lmb']))
                 p = torch.softmax(logits, dim=1).numpy()
             jacc = jacc + M.jaccard(p, Lb, RF.NCLS)

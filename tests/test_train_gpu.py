@@ -334,3 +334,47 @@ def test_train_forward_draws_one_mask_noise_per_depool(cuda):
     for _ in range(2):          # eager, then captured
         tr.step_graphed(K.pack_nchw(h.to(cuda), 512), y.to(cuda), L.to(cuda), nm.to(cuda), nk.to(cuda))
     assert np.isfinite(tr.loss_value())
+
+
+def test_train_steps_with_noise_vs_reference_run(cuda):
+    """BASELINE config 4 semantics (noise = 0.5) against the reference's own train_dae.py:train() run with logged draws
+    (tests/golden/ref_train_noise.npz): four rmsprop steps and two validation passes replayed with the very noise the reference
+    consumed -- the main GaussianNoiseLayer's draw plus one per DePool2D in training, one per DePool2D in validation (whose
+    masks the reference noises as well).  bf16 operands: per-epoch costs within 2e-3 relative."""
+    from oracle.refrun import py2import
+    py2import.install_stubs()
+    from theano.sandbox import rng_mrg
+    from tests import reference_fixtures as RF
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer, validate
+    G = RF.G
+    fx, case = RF.load('ref_train_noise')
+    sigma = case['dae']['noise']
+    pf = weights.synthetic_fcn8_params(3, NCLS, **G.FCN8_WEIGHTS)
+    tr = DAETrainer(NCLS, 512, 100, G.case_dae_params(case), learning_rate=case['learning_rate'], noise=sigma, lmb=case['lmb'])
+    train_k, val_k = iter(fx['train_k']), iter(fx['val_k'])
+    dev = lambda ks, shape: torch.stack([rng_mrg.draw(int(k), shape) for k in ks]).to(cuda)          # noqa: E731
+    err_train, err_valid, mse_val = [], [], []
+    for epoch in range(case['num_epochs']):
+        tot = 0.0
+        for i in range(case['nbatches']):
+            X, Lb = G.case_batch(case, i, 'train')
+            h, y = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+            ks = next(train_k)
+            tr.step(K.pack_nchw(h.to(cuda), 512), y.to(cuda), torch.from_numpy(Lb).to(cuda), dev(ks[:1], y.shape)[0], dev(ks[1:], y.shape))
+            tot += tr.loss_value()
+        err_train.append(tot / case['nbatches'])
+        cv, mv = 0.0, 0.0
+        for i in range(case['val_nbatches']):
+            X, Lb = G.case_batch(case, i, 'val')
+            h, y = nets.fcn8_forward(pf, torch.from_numpy(X), NCLS)
+            c, _, m = validate(tr, K.pack_nchw(h.to(cuda), 512), y.to(cuda), torch.from_numpy(Lb).to(cuda), dev(next(val_k), y.shape))
+            cv += c
+            mv += m
+        err_valid.append(cv / case['val_nbatches'])
+        mse_val.append(mv / case['val_nbatches'])
+        tr.lr = float(np.float32(tr.lr * case['lr_anneal']))
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())          # noqa: E731
+    e = (rel(err_train, fx['err_train']), rel(err_valid, fx['err_valid']), rel(mse_val, fx['mse_val']))
+    print('noisy training vs the reference run: err_train %.2e err_valid %.2e mse_val %.2e (relative)' % e)
+    assert max(e) < 2e-3, e
