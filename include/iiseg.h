@@ -415,6 +415,15 @@ int iiseg_sum_slabs(const float* in, float* out, int S, long long n, void* strea
 int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt,
                        int Cout, int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0,
                        int Ci_t, int Co_pad, float lr, float rho, float eps, void* stream);
+/* lasagne.updates.adam, the other optimiser of train_dae.py:326-331, on the same layouts:
+ * m <- beta1 m + (1-beta1) g; v <- beta2 v + (1-beta2) g^2; w <- w - a_t m / (sqrt(v) + eps), with
+ * a_t = lr sqrt(1 - beta2^t) / (1 - beta1^t) read from device memory (`a_t` = state + 1).  iiseg_adam_advance does
+ * state[0] = t <- t + 1, state[1] = a_t once per step (fp32, like lasagne's shared scalar), so that a captured CUDA graph
+ * replays with the right step count. */
+int iiseg_adam_pack(float* w, float* m, float* v, float* b, float* m_b, float* v_b, const float* g, void* wb, void* wt,
+                    int Cout, int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad,
+                    const float* a_t, float beta1, float beta2, float eps, void* stream);
+int iiseg_adam_advance(float* state, float lr, float beta1, float beta2, void* stream);
 
 #ifdef __cplusplus
 }

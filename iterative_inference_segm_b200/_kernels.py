@@ -643,6 +643,28 @@ def rmsprop_pack(w, acc, b, acc_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t
               g.shape[1], g_rstride, bias_col, ci0, ci_t, co_pad, C.c_float(lr), C.c_float(rho), C.c_float(eps), _stream())
 
 
+def adam_pack(w, m, v, b, m_b, v_b, g, wb, wt, taps, cin_pad, bias_col, ci0, ci_t, state, beta1, beta2, eps, g_rstride=0):
+    """lasagne.updates.adam on the layouts of `rmsprop_pack`; `state` = fp32 [2] device tensor (t, a_t) kept by `adam_advance`."""
+    for t_, n_ in ((w, 'w'), (m, 'm'), (v, 'v'), (b, 'b'), (m_b, 'm_b'), (v_b, 'v_b'), (g, 'g'), (state, 'state')):
+        _chk(t_, F32, n_)
+    _chk(wb, BF16, 'wb')
+    Cout = w.shape[0]
+    assert w.numel() == Cout * taps * cin_pad == m.numel() == v.numel() == wb.numel() and g.shape[0] == Cout and state.numel() == 2
+    co_pad = 0
+    if wt is not None:
+        _chk(wt, BF16, 'wt')
+        assert wt.shape[0] == ci_t and wt.shape[1] % taps == 0
+        co_pad = wt.shape[1] // taps
+    _lib.call('iiseg_adam_pack', _ptr(w), _ptr(m), _ptr(v), _ptr(b), _ptr(m_b), _ptr(v_b), _ptr(g), _ptr(wb), _ptr(wt), Cout, taps, cin_pad,
+              g.shape[1], g_rstride, bias_col, ci0, ci_t, co_pad, state.data_ptr() + 4, C.c_float(beta1), C.c_float(beta2), C.c_float(eps), _stream())
+
+
+def adam_advance(state, lr, beta1, beta2):
+    """t <- t + 1, a_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), on the device (once per training step)."""
+    _chk(state, F32, 'state')
+    _lib.call('iiseg_adam_advance', _ptr(state), C.c_float(lr), C.c_float(beta1), C.c_float(beta2), _stream())
+
+
 # ---- metrics ------------------------------------------------------------------
 def metrics_accumulate(y, cm, counts, sqerr, onehot=None, labels=None, active=None, void_label=-1):
     _chk(y, F32, 'y')

@@ -112,6 +112,8 @@ SIGNATURES = {
     'iiseg_bias_grad': (_i, [_vp, C.c_longlong, _i, _vp, _i, _vp, _i, _vp]),
     'iiseg_sum_slabs': (_i, [_vp, _vp, _i, C.c_longlong, _vp]),
     'iiseg_rmsprop_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _vp]),
+    'iiseg_adam_pack': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _vp]),
+    'iiseg_adam_advance': (_i, [_vp, _f, _f, _f, _vp]),
     'iiseg_metrics_accumulate': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 

@@ -263,10 +263,21 @@ __global__ void __launch_bounds__(256) transpose_shift_kernel(const TransposePar
 // [Cout][ldg] (taps*Cin_pad filter columns, then the bias column at `bias_col`).  Emits the bf16 forward bank
 // and, if wt != NULL, the bank of the data-gradient conv: wt[ci][R*S-1-tap][co] (flipped taps, transposed channels),
 // for the ci range [ci0, ci0 + Ci_t) only (the concat conv propagates to its own half), padded to Co_pad columns.
+// lasagne.updates.adam (the other optimiser train_dae.py:326-331 offers) runs in the same kernel when `m` is set:
+// m <- beta1*m + (1-beta1)*g ; v <- beta2*v + (1-beta2)*g^2 (v lives in `acc`, beta2 in `rho`) ; w <- w - a_t * m / (sqrt(v) + eps),
+// a_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from device memory (iiseg_adam_advance updates it once per step, so a captured
+// graph replays with the right step count).
 struct RmspropParams {
   float* w; float* acc; float* b; float* acc_b; const float* g; __nv_bfloat16* wb; __nv_bfloat16* wt;
   int Cout, taps, Cin_pad, ldg, bias_col, ci0, Ci_t, Co_pad, g_rstride; float lr, rho, eps; long long total;
+  float* m; float* m_b; const float* a_t; float beta1;
 };
+
+__global__ void adam_advance_kernel(float* state, float lr, float beta1, float beta2) {
+  const float t = state[0] + 1.f;                      // t_prev + 1 (float32, as lasagne's shared scalar)
+  state[0] = t;
+  state[1] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
+}
 
 __global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p) {
   // One block = 64 output channels x 16 input channels of one tap.  Thread (r, q) owns 4 consecutive input channels
@@ -287,10 +298,20 @@ __global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p
     const float4 g = *reinterpret_cast<const float4*>(p.g + (size_t)co * p.ldg + fr * p.g_rstride + (rem - fr * 3 * p.Cin_pad));
     float4 a = *reinterpret_cast<const float4*>(p.acc + i);
     float4 w = *reinterpret_cast<const float4*>(p.w + i);
-    a.x = p.rho * a.x + (1.f - p.rho) * g.x * g.x; w.x -= p.lr * g.x / sqrtf(a.x + p.eps);
-    a.y = p.rho * a.y + (1.f - p.rho) * g.y * g.y; w.y -= p.lr * g.y / sqrtf(a.y + p.eps);
-    a.z = p.rho * a.z + (1.f - p.rho) * g.z * g.z; w.z -= p.lr * g.z / sqrtf(a.z + p.eps);
-    a.w = p.rho * a.w + (1.f - p.rho) * g.w * g.w; w.w -= p.lr * g.w / sqrtf(a.w + p.eps);
+    if (p.m != nullptr) {          // adam
+      const float at = __ldg(p.a_t), b1 = p.beta1;
+      float4 m = *reinterpret_cast<const float4*>(p.m + i);
+      m.x = b1 * m.x + (1.f - b1) * g.x; a.x = p.rho * a.x + (1.f - p.rho) * g.x * g.x; w.x -= at * m.x / (sqrtf(a.x) + p.eps);
+      m.y = b1 * m.y + (1.f - b1) * g.y; a.y = p.rho * a.y + (1.f - p.rho) * g.y * g.y; w.y -= at * m.y / (sqrtf(a.y) + p.eps);
+      m.z = b1 * m.z + (1.f - b1) * g.z; a.z = p.rho * a.z + (1.f - p.rho) * g.z * g.z; w.z -= at * m.z / (sqrtf(a.z) + p.eps);
+      m.w = b1 * m.w + (1.f - b1) * g.w; a.w = p.rho * a.w + (1.f - p.rho) * g.w * g.w; w.w -= at * m.w / (sqrtf(a.w) + p.eps);
+      *reinterpret_cast<float4*>(p.m + i) = m;
+    } else {
+      a.x = p.rho * a.x + (1.f - p.rho) * g.x * g.x; w.x -= p.lr * g.x / sqrtf(a.x + p.eps);
+      a.y = p.rho * a.y + (1.f - p.rho) * g.y * g.y; w.y -= p.lr * g.y / sqrtf(a.y + p.eps);
+      a.z = p.rho * a.z + (1.f - p.rho) * g.z * g.z; w.z -= p.lr * g.z / sqrtf(a.z + p.eps);
+      a.w = p.rho * a.w + (1.f - p.rho) * g.w * g.w; w.w -= p.lr * g.w / sqrtf(a.w + p.eps);
+    }
     *reinterpret_cast<float4*>(p.acc + i) = a;
     *reinterpret_cast<float4*>(p.w + i) = w;
     packed0 = pack_bf16x2(w.x, w.y); packed1 = pack_bf16x2(w.z, w.w);
@@ -299,7 +320,13 @@ __global__ void __launch_bounds__(256) rmsprop_pack_kernel(const RmspropParams p
       const float gb = p.g[(size_t)co * p.ldg + p.bias_col];
       const float ab = p.rho * p.acc_b[co] + (1.f - p.rho) * gb * gb;
       p.acc_b[co] = ab;
-      p.b[co] -= p.lr * gb / sqrtf(ab + p.eps);
+      if (p.m != nullptr) {
+        const float mb = p.beta1 * p.m_b[co] + (1.f - p.beta1) * gb;
+        p.m_b[co] = mb;
+        p.b[co] -= __ldg(p.a_t) * mb / (sqrtf(ab) + p.eps);
+      } else {
+        p.b[co] -= p.lr * gb / sqrtf(ab + p.eps);
+      }
     }
   }
   if (p.wt == nullptr || ci_base < p.ci0 || ci_base >= p.ci0 + p.Ci_t) return;      // block-uniform
@@ -464,9 +491,37 @@ extern "C" int iiseg_transpose_shift(const void* x, int N, int H, int W, int Cs,
   return 0;
 }
 
+static int optimiser_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt, int Cout,
+                          int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad, float lr,
+                          float rho, float eps, float* m, float* m_b, const float* a_t, float beta1, void* stream);
+
 extern "C" int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt, int Cout,
                                   int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad, float lr,
                                   float rho, float eps, void* stream) {
+  return optimiser_pack(w, acc, b, acc_b, g, wb, wt, Cout, taps, Cin_pad, ldg, g_rstride, bias_col, ci0, Ci_t, Co_pad, lr, rho, eps,
+                        nullptr, nullptr, nullptr, 0.f, stream);
+}
+
+extern "C" int iiseg_adam_pack(float* w, float* m, float* v, float* b, float* m_b, float* v_b, const float* g, void* wb, void* wt,
+                               int Cout, int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad,
+                               const float* a_t, float beta1, float beta2, float eps, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(m && m_b && a_t, "adam_pack: null tensor");
+  return optimiser_pack(w, v, b, v_b, g, wb, wt, Cout, taps, Cin_pad, ldg, g_rstride, bias_col, ci0, Ci_t, Co_pad, 0.f, beta2, eps,
+                        m, m_b, a_t, beta1, stream);
+}
+
+extern "C" int iiseg_adam_advance(float* state, float lr, float beta1, float beta2, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(state != nullptr, "adam_advance: null state");
+  adam_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(state, lr, beta1, beta2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int optimiser_pack(float* w, float* acc, float* b, float* acc_b, const float* g, void* wb, void* wt, int Cout,
+                          int taps, int Cin_pad, int ldg, int g_rstride, int bias_col, int ci0, int Ci_t, int Co_pad, float lr,
+                          float rho, float eps, float* m, float* m_b, const float* a_t, float beta1, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(w && acc && b && acc_b && g && wb, "rmsprop_pack: null tensor");
   if (g_rstride == 0) g_rstride = 3 * Cin_pad;
@@ -477,6 +532,7 @@ extern "C" int iiseg_rmsprop_pack(float* w, float* acc, float* b, float* acc_b, 
   p.w = w; p.acc = acc; p.b = b; p.acc_b = acc_b; p.g = g; p.wb = reinterpret_cast<__nv_bfloat16*>(wb); p.wt = reinterpret_cast<__nv_bfloat16*>(wt);
   p.Cout = Cout; p.taps = taps; p.Cin_pad = Cin_pad; p.ldg = ldg; p.bias_col = bias_col; p.ci0 = ci0; p.Ci_t = Ci_t; p.Co_pad = Co_pad; p.g_rstride = g_rstride;
   p.lr = lr; p.rho = rho; p.eps = eps; p.total = (long long)Cout * taps * Cin_pad;
+  p.m = m; p.m_b = m_b; p.a_t = a_t; p.beta1 = beta1;
   IISEG_CHECK(Cin_pad % 16 == 0 && Cout % 4 == 0 && ldg % 4 == 0 && (wt == nullptr || (ci0 % 16 == 0 && Ci_t % 16 == 0 && Co_pad % 4 == 0)),
               "rmsprop_pack: channel counts must be padded (Cin %% 16, Cout %% 4, transposed range %% 16)");
   IISEG_CHECK((Cout + 63) / 64 <= 65535, "rmsprop_pack: too many output channels");

@@ -89,10 +89,16 @@ class DAETrainer(object):
     BUCKET_BYTES = 32 << 20        # gradient all-reduce bucket size (NVSwitch: sized for launch latency / overlap, not link count)
 
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
-                 additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda'):
+                 additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda',
+                 optimizer='rmsprop', beta1=0.9, beta2=0.999, adam_epsilon=1e-8):
         K.require_device()
         self.dev = dev = torch.device(device)
         self.C, self.lr, self.sigma, self.lmb, self.rho, self.eps = n_classes, learning_rate, noise, lmb, rho, epsilon
+        # lasagne.updates.rmsprop(loss, params, learning_rate=lr) or lasagne.updates.adam(...) with lasagne's defaults
+        # (train_dae.py:326-331): adam keeps a first-moment bank per layer and the step counter t / step size a_t on the device
+        assert optimizer in ('rmsprop', 'adam'), optimizer
+        self.optimizer, self.beta1, self.beta2, self.adam_eps = optimizer, beta1, beta2, adam_epsilon
+        self.adam_state = torch.zeros((2,), dtype=torch.float32, device=dev)
         geo = self.geo = DAENet.__new__(DAENet)          # geometry helpers only (level sizes, crop cone)
         geo.n_classes, geo.nb_h, geo.h_pad, geo.padding = n_classes, nb_features_to_concat, _r64(nb_features_to_concat), padding
         last = concat_h[-1]
@@ -370,6 +376,14 @@ class DAETrainer(object):
         return float(s[0] / s[1] + self.lmb * s[2] / s[3])
 
     def update(self):
+        if self.optimizer == 'adam':
+            K.adam_advance(self.adam_state, self.lr, self.beta1, self.beta2)
+            for lay in self.layers():
+                if not hasattr(lay, 'mom'):
+                    lay.mom, lay.mom_b = torch.zeros_like(lay.w), torch.zeros_like(lay.b)
+                K.adam_pack(lay.w, lay.mom, lay.acc, lay.b, lay.mom_b, lay.acc_b, lay.grad, lay.wb, lay.wt, 9, lay.cin_pad, lay.bias_col,
+                            lay.ci0, lay.ci_t, self.adam_state, self.beta1, self.beta2, self.adam_eps, g_rstride=lay.g_rstride)
+            return
         for lay in self.layers():
             K.rmsprop_pack(lay.w, lay.acc, lay.b, lay.acc_b, lay.grad, lay.wb, lay.wt, 9, lay.cin_pad, lay.bias_col,
                            lay.ci0, lay.ci_t, self.lr, self.rho, self.eps, g_rstride=lay.g_rstride)
@@ -492,8 +506,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
     dae_dict = dict(DAE_DICT_DEFAULTS)
     dae_dict['path_weights'] = ''
     dae_dict.update(dae_dict_updates)
-    if optimizer != 'rmsprop':
-        raise NotImplementedError('B200 train step implements lasagne.updates.rmsprop (the benchmark optimiser)')
+    if optimizer not in ('rmsprop', 'adam'):
+        raise ValueError('Unknown optimizer')          # train_dae.py:331
     if dae_dict['kind'] != 'standard' or dae_dict['unpool_type'] != 'trackind' or segm_net not in ('fcn8', 'densenet'):
         raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net in (fcn8, densenet)')
     if sorted(training_loss) != ['crossentropy', 'squared_error']:
@@ -532,7 +546,7 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
                                                         concat_h=tuple(dae_dict['concat_h']), additional_pool=dae_dict['additional_pool'])
     tr = DAETrainer(n_classes, fcn[0].output_shape[1], padding, dae_params, concat_h=tuple(dae_dict['concat_h']),
                     n_filters=dae_dict['n_filters'], additional_pool=dae_dict['additional_pool'],
-                    learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb)
+                    learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb, optimizer=optimizer)
     gen = torch.Generator(device=tr.dev).manual_seed(seed)
     say = print if verbose else (lambda *a, **k: None)
 

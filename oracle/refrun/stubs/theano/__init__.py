@@ -101,6 +101,7 @@ class Variable(object):
     def __rtruediv__(self, o): return self._bin(o, _div, True)
     def __floordiv__(self, o): return self._bin(o, lambda a, b: a // b)
     def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
+    def __rpow__(self, o): return self._bin(o, lambda a, b: a ** b, True)
     def __neg__(self): return Variable(lambda a: -a, [self], ndim=self._ndim)
 
     def _cmp(self, o, f):

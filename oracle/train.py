@@ -152,6 +152,22 @@ def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True):
     return loss
 
 
+def adam_update(params, moms, vels, grads, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """lasagne.updates.adam with its defaults (train_dae.py:328-329): t <- t_prev + 1 (float32);
+    a_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t); m <- beta1 m + (1-beta1) g; v <- beta2 v + (1-beta2) g^2;
+    p <- p - a_t m / (sqrt(v) + eps).  Returns (new_params, new_moms, new_vels, t)."""
+    t = torch.tensor(float(t), dtype=torch.float32) + 1.0
+    a_t = lr * torch.sqrt(1.0 - torch.tensor(beta2, dtype=torch.float32) ** t) / (1.0 - torch.tensor(beta1, dtype=torch.float32) ** t)
+    new_p, new_m, new_v = [], [], []
+    for p, m, v, g in zip(params, moms, vels, grads):
+        m2 = beta1 * m + (1 - beta1) * g
+        v2 = beta2 * v + (1 - beta2) * g * g
+        new_m.append(m2)
+        new_v.append(v2)
+        new_p.append(p - a_t * m2 / (torch.sqrt(v2) + eps))
+    return new_p, new_m, new_v, float(t)
+
+
 def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=None, noise_mask=None, lmb=1.0,
                rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, **dae_kw):
     """One train_fn call (train_dae.py:334-335): returns (loss, grads, new_params, new_accus).

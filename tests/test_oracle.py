@@ -418,7 +418,7 @@ def test_oracle_temperature_vs_reference_run():
     assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
 
 
-@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise'])
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise', 'ref_train_adam'])
 def test_oracle_train_step_vs_reference_run(name):
     """oracle/train.py against the reference's own train_dae.py:train() (two epochs of two rmsprop steps, the learning rate
     annealed in between, validation after each epoch; tests/golden/ref_train.npz, and ref_train_noise.npz with noise = 0.5 and
@@ -437,6 +437,7 @@ def test_oracle_train_step_vs_reference_run(name):
     pf = weights.synthetic_fcn8_params(3, RF.NCLS, **G.FCN8_WEIGHTS)
     init = G.case_dae_params(case)
     params, accus = [p.clone() for p in init], [torch.zeros_like(p) for p in init]
+    moms, t_adam = [torch.zeros_like(p) for p in init], 0.0
     lr = np.float32(case['learning_rate'])
     err_train, err_valid, jacc_val, mse_val = [], [], [], []
     for epoch in range(case['num_epochs']):
@@ -448,7 +449,11 @@ def test_oracle_train_step_vs_reference_run(name):
             if sigma > 0:
                 ks = next(train_k)
                 nkw = dict(noise_main=sigma * rng_mrg.draw(int(ks[0]), y.shape), noise_mask=[sigma * rng_mrg.draw(int(k), y.shape) for k in ks[1:]])
-            loss, _, params, accus = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], **nkw)
+            loss, grads, p_rms, a_rms = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], **nkw)
+            if case.get('optimizer') == 'adam':          # lasagne.updates.adam (train_dae.py:328-329)
+                params, moms, accus, t_adam = T_.adam_update(params, moms, accus, grads, t_adam, float(lr))
+            else:
+                params, accus = p_rms, a_rms
             tot += loss
         err_train.append(tot / case['nbatches'])
         cost, jacc, mse = 0.0, 0.0, 0.0

@@ -246,7 +246,8 @@ def test_train_loop_runs_and_writes_the_reference_checkpoints(cuda, tmp_path, se
     assert dae.net.total == 6
 
 
-def test_train_dropin_vs_reference_run(cuda, tmp_path):
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_adam'])
+def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     """train() of this package against the reference's OWN run of train_dae.py:train() (executed through oracle/refrun,
     tests/golden/ref_train.npz): same arguments, the seeded checkpoint on disk where `resume=True` reads it, the same iterators;
     two epochs of two rmsprop steps with the annealed learning rate and a validation pass each.  The step computes with bf16
@@ -256,10 +257,11 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path):
     from iterative_inference_segm_b200.train_dae import train
     from iterative_inference_segm_b200.helpers import build_experiment_name
     G = RF.G
-    fx, case = RF.load('ref_train')
+    fx, case = RF.load(name)
+    optimizer = case.get('optimizer', 'rmsprop')          # ref_train_adam: lasagne.updates.adam (train_dae.py:328-329)
     d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
     exp_name = build_experiment_name('fcn8', training_loss=case['training_loss'], data_aug=True, learning_rate=case['learning_rate'],
-                                     lr_anneal=case['lr_anneal'], weight_decay=1e-4, optimizer='rmsprop', ae_h=False, **d)
+                                     lr_anneal=case['lr_anneal'], weight_decay=1e-4, optimizer=optimizer, ae_h=False, **d)
     wdir = tmp_path / 'weights' / 'camvid'
     wdir.mkdir(parents=True)
     weights.save_npz(str(wdir / 'fcn8_model.npz'), weights.synthetic_fcn8_params(3, NCLS, **G.FCN8_WEIGHTS))
@@ -268,7 +270,7 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path):
     init = G.case_dae_params(case)
     weights.save_npz(str(ldir / 'dae_model_best.npz'), init)
     out = train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
-                num_epochs=case['num_epochs'], max_patience=100, optimizer='rmsprop', training_loss=list(case['training_loss']),
+                num_epochs=case['num_epochs'], max_patience=100, optimizer=optimizer, training_loss=list(case['training_loss']),
                 batch_size=[case['B']] * 3, ae_h=False, dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
                 data_augmentation={'crop_size': None}, savepath=str(tmp_path / 'save'), loadpath=str(tmp_path / 'load'), resume=True,
                 lmb=case['lmb'], train_iter=G.SyntheticCamvidIterator(case, 'train'), val_iter=G.SyntheticCamvidIterator(case, 'val'),
