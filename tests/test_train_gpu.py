@@ -278,8 +278,14 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())          # noqa: E731
     e_tr, e_va, e_mse = rel(out['err_train'], fx['err_train']), rel(out['err_valid'], fx['err_valid']), rel(out['mse_val'], fx['mse_val'])
     print('train drop-in vs reference run: err_train %.2e err_valid %.2e mse_val %.2e (relative)' % (e_tr, e_va, e_mse))
-    assert e_tr < 1e-3 and e_va < 1e-3 and e_mse < 1e-3          # measured 1.5e-4 / 2.4e-5 / 1.1e-5
-    assert abs(out['jacc_val'][-1] - float(fx['jacc_val'][-1])) < 5e-3
+    # rmsprop: measured 1.5e-4 / 2.4e-5 / 1.1e-5.  adam: 3.9e-3 / 2.7e-3 / 4.0e-3 -- its first steps are lr * sign(g) for EVERY element
+    # (m / sqrt(v) = g / |g| at t = 1, epsilon 1e-8), so the rounding of the bf16 operands decides the direction of every element whose
+    # gradient is ~0; the oracle with the same operand rounding (emulate_bf16=True) is 2.2e-3 / 2.8e-2 off the reference run on err_train
+    tol = 1e-2 if optimizer == 'adam' else 1e-3
+    assert e_tr < tol and e_va < tol and e_mse < tol
+    # the validation Jaccard of these near-random 2 x 32 x 40 predictions is 0.03-0.05: a handful of argmax flips move it
+    print('validation Jaccard %.4f vs the reference run %.4f' % (out['jacc_val'][-1], float(fx['jacc_val'][-1])))
+    assert abs(out['jacc_val'][-1] - float(fx['jacc_val'][-1])) < (2e-2 if optimizer == 'adam' else 5e-3)          # adam: measured 1.3e-2
     saved = sorted(f for f in os.listdir(out['savepath']) if f.startswith('dae_model_'))
     assert saved == [str(fx['saved_as'])]
     with np.load(os.path.join(out['savepath'], saved[0])) as f:
@@ -297,6 +303,40 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     # rmsprop normalises every element's step to ~lr whatever its gradient's size: the NORM of an array's change is robust, single
     # elements whose gradient is ~0 are not (their sign is rounding, and bf16 operands flip pool ties: DESIGN.md 3.9)
     assert float(np.median(norms)) < 0.05 and worst_norm < 0.25          # measured: worst 0.15
+
+
+def test_adam_update_matches_lasagne_definition(cuda):
+    """`iiseg_adam_pack` / `iiseg_adam_advance` against lasagne.updates.adam as the oracle restates it (oracle/train.py:adam_update;
+    train_dae.py:328-329), on the step's OWN gradients so that only the optimiser's arithmetic is compared: three steps (the step
+    counter and a_t live on the device), parameters, first and second moments to fp32 rounding; the bf16 forward bank follows the
+    updated fp32 master weights."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    pd, h, y, L, nm, _ = _setup(cuda)
+    lr = 1e-3
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=0.5, optimizer='adam')
+    h_b = K.pack_nchw(h.to(cuda), 512)
+    params = [p.cpu().clone() for p in tr.params()]
+    moms, vels, t = [torch.zeros_like(p) for p in params], [torch.zeros_like(p) for p in params], 0.0
+    for step in range(3):
+        tr.forward(h_b, y.to(cuda), nm.to(cuda), None)
+        tr.backward(L.to(cuda))
+        grads = [g.cpu().clone() for g in tr.grads_lasagne()]
+        tr.update()
+        torch.cuda.synchronize()
+        params, moms, vels, t = OT.adam_update(params, moms, vels, grads, t, lr)
+        st = tr.adam_state.cpu()
+        assert float(st[0]) == t == step + 1
+        a_t = lr * np.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        assert abs(float(st[1]) - a_t) < 1e-5 * a_t
+        worst = 0.0
+        for p_dev, p_ref in zip(tr.params(), params):
+            worst = max(worst, float((p_dev.cpu() - p_ref).abs().max()))
+            # every element moves by <= ~lr per step; fp32 rounding of a_t (powf) and of m / (sqrt(v) + eps) is what remains
+            assert torch.allclose(p_dev.cpu(), p_ref, rtol=0, atol=2e-3 * lr), (step, float((p_dev.cpu() - p_ref).abs().max()))
+        print('adam step %d: t = %g, a_t = %.6e, worst parameter difference %.2e (lr %.0e)' % (step + 1, t, float(st[1]), worst, lr))
+    lay = tr.layers()[0]
+    assert torch.equal(lay.wb.view(-1).float(), lay.w.view(-1).to(torch.bfloat16).float())
 
 
 def test_train_forward_draws_one_mask_noise_per_depool(cuda):
