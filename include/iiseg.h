@@ -379,6 +379,11 @@ int iiseg_deconv_interleave(const float* p00, const float* p01, const float* p10
  *   is sums[0]/sums[1] + lmb*sums[2]/sums[3]; dlogits = bf16 NHWC16 gradient of that loss.
  *   passes: bit 0 = accumulate sums (zeroing them first), bit 1 = write dlogits using sums[1], sums[3]
  *   as the denominators (data-parallel ranks all-reduce `sums` between the two passes).
+ * iiseg_loss_grad_terms: the same with the terms train_dae.py:278-294 adds up selectable: `terms` = bit 0 crossentropy |
+ *   bit 1 lmb * squared_error | bit 2 dice_loss (metrics.py:93-113: -(2 I + 1) / (T + P + 1) on channel 1 of the softmax
+ *   output and of the one-hot target, entries whose int32 target VALUE equals the void label id C dropped).  With bit 2
+ *   `sums` is fp64[8]: sums[4] = I = sum t1 p1, sums[5] = T = sum t1, sums[6] = P = sum p1; the loss gains
+ *   -(2 sums[4] + 1) / (sums[5] + sums[6] + 1).  iiseg_loss_grad == terms 3.
  * iiseg_depool2_bwd: DePool2D backward, g_u[ph,pw] = sum over the 2x2 window of mask * g_v (g_v a
  *   dense window [N,VH,VW,C] at full-resolution origin (v_h0,v_w0), zero outside; g_u dense
  *   [N,UH,UW,C] at pooled origin (u_h0,u_w0); mask full [N,H/2,W/2,C/8]).
@@ -399,6 +404,8 @@ int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst,
                      int W, int Cpad, int split, void* stream);
 int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb,
                     double* sums, void* dlogits, int passes, void* stream);
+int iiseg_loss_grad_terms(const float* logits, const float* target, int N, int C, int H, int W,
+                          float lmb, int terms, double* sums, void* dlogits, int passes, void* stream);
 int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,
                       int VH, int VW, int v_h0, int v_w0, int UH, int UW, int u_h0, int u_w0,
                       void* stream);

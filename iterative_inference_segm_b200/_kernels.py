@@ -508,16 +508,33 @@ def noise_pack(y, noise, sigma, cpad, out=None, split=False):
     return out
 
 
-def loss_grad(logits, target, n_classes, lmb, sums, dlogits=None, passes=3):
+LOSS_TERMS = {'crossentropy': 1, 'squared_error': 2, 'dice': 4}          # `terms` bits of iiseg_loss_grad_terms
+
+
+def loss_grad(logits, target, n_classes, lmb, sums, dlogits=None, passes=3, terms=3):
+    """Loss sums and d loss / d logits of the terms train_dae.py:278-294 adds up (`terms`: OR of LOSS_TERMS values)."""
     _chk(logits, F32, 'logits')
     _chk(target, F32, 'target')
     N, H, W, c16 = logits.shape
-    assert c16 == 16 and tuple(target.shape) == (N, n_classes + 1, H, W) and sums.dtype == torch.float64 and sums.numel() >= 4
+    assert c16 == 16 and tuple(target.shape) == (N, n_classes + 1, H, W) and sums.dtype == torch.float64
+    assert sums.numel() >= (8 if terms & 4 else 4)
     if dlogits is None:
         dlogits = torch.empty((N, H, W, 16), dtype=BF16, device=logits.device)
-    _lib.call('iiseg_loss_grad', _ptr(logits), _ptr(target), N, n_classes, H, W, C.c_float(lmb), _ptr(sums), _ptr(dlogits), passes,
-              _stream())
+    _lib.call('iiseg_loss_grad_terms', _ptr(logits), _ptr(target), N, n_classes, H, W, C.c_float(lmb), int(terms), _ptr(sums), _ptr(dlogits),
+              passes, _stream())
     return dlogits
+
+
+def loss_from_sums(s, lmb, terms=3):
+    """The scalar loss from the (host) sums of `loss_grad`."""
+    loss = 0.0
+    if terms & 1:
+        loss += float(s[0] / s[1])
+    if terms & 4:
+        loss += float(-(2.0 * s[4] + 1.0) / (s[5] + s[6] + 1.0))
+    if terms & 2:
+        loss += lmb * float(s[2] / s[3])
+    return loss
 
 
 def depool2_bwd(gv, mask, H, W, v_origin, u_origin, u_size):

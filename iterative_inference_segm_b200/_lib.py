@@ -105,6 +105,7 @@ SIGNATURES = {
     'iiseg_deconv_interleave': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     'iiseg_noise_pack': (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_loss_grad': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
+    'iiseg_loss_grad_terms': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _vp]),
     'iiseg_depool2_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_pool2_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'iiseg_transpose_shift': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, C.c_longlong, C.c_longlong, _i, C.c_longlong, _vp]),

@@ -55,12 +55,17 @@ __global__ void __launch_bounds__(256) noise_pack_kernel(const float* __restrict
 // the two denominators and writes dlogits (bf16 NHWC16):
 //   dL/dp_k = -[k == true] * mask / (p_true * N_ce)   (0 where p_true was clipped)  +  lmb * 2 (p_k - t_k) m2 / (C * N_mse)
 //   dL/dlogit_c = p_c * (dL/dp_c - sum_k dL/dp_k p_k)
+// `terms` selects what train_dae.py:278-294 adds up: bit 0 crossentropy, bit 1 lmb * squared_error, bit 2 dice_loss
+// (metrics.py:93-113) = -(2 I + 1) / (T + P + 1) on channel 1, I = sum t1 p1 (sums[4]), T = sum t1 (sums[5]), P = sum p1 (sums[6])
+// over the entries whose target VALUE (int32 cast of the one-hot 0/1) differs from the void label id C:
+//   dL/dp_1 += -(2 t1 (T + P + 1) - (2 I + 1)) / (T + P + 1)^2   for those entries.
+constexpr int kTermCE = 1, kTermMSE = 2, kTermDice = 4;
 __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                         int C, int HW, float lmb, double* __restrict__ sums,
-                                                        __nv_bfloat16* __restrict__ dlogits, int pass) {
+                                                        __nv_bfloat16* __restrict__ dlogits, int pass, int terms) {
   const int n = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
-  double ce_s = 0.0, mk_s = 0.0, se_s = 0.0, m2_s = 0.0;
+  double ce_s = 0.0, mk_s = 0.0, se_s = 0.0, m2_s = 0.0, di_s = 0.0, dt_s = 0.0, dp_s = 0.0;
   if (pix < HW) {
     float l[16], p[16], t[17];
     const uint4* q = reinterpret_cast<const uint4*>(logits + ((size_t)n * HW + pix) * 16);
@@ -97,17 +102,26 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
     }
     const bool clipped = ptrue < 1e-7f || ptrue > 1.0f - 1e-7f;
     const float pc = fminf(fmaxf(ptrue, 1e-7f), 1.0f - 1e-7f);
+    const int t1i = (int)t[1];                                  // T.cast(y_true_f, 'int32')
+    const bool dice_keep = (terms & kTermDice) && t1i != C;     // T.neq(y_true_f, void_class[i]).nonzero()
     if (pass == 0) {
       ce_s = (double)(-logf(pc) * mask); mk_s = (double)mask; se_s = (double)(se / (float)C * m2); m2_s = (double)m2;
+      if (dice_keep) { di_s = (double)((float)t1i * p[1]); dt_s = (double)t1i; dp_s = (double)p[1]; }
     } else {
       const float n_ce = (float)sums[1], n_mse = (float)sums[3];
+      float dice_d = 0.f;
+      if (dice_keep) {
+        const double S = sums[5] + sums[6] + 1.0, I2 = 2.0 * sums[4] + 1.0;
+        dice_d = (float)(-(2.0 * (double)t1i * S - I2) / (S * S));
+      }
       float dp[16], dot = 0.f;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         dp[c] = 0.f;
         if (c < C) {
-          dp[c] = lmb * 2.f * (p[c] - t[c]) * m2 / ((float)C * n_mse);
-          if (c == idx && !clipped) dp[c] -= mask / (pc * n_ce);
+          if (terms & kTermMSE) dp[c] = lmb * 2.f * (p[c] - t[c]) * m2 / ((float)C * n_mse);
+          if ((terms & kTermCE) && c == idx && !clipped) dp[c] -= mask / (pc * n_ce);
+          if (c == 1) dp[c] += dice_d;
           dot += dp[c] * p[c];
         }
       }
@@ -132,6 +146,20 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
       double a = 0.0;
       for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
       atomicAdd(sums + threadIdx.x, a);
+    }
+    if (terms & kTermDice) {          // block-uniform
+      __syncthreads();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        di_s += __shfl_xor_sync(0xffffffffu, di_s, o); dt_s += __shfl_xor_sync(0xffffffffu, dt_s, o); dp_s += __shfl_xor_sync(0xffffffffu, dp_s, o);
+      }
+      if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; red[0][w] = di_s; red[1][w] = dt_s; red[2][w] = dp_s; }
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        double a = 0.0;
+        for (int w = 0; w < 8; ++w) a += red[threadIdx.x][w];
+        atomicAdd(sums + 4 + threadIdx.x, a);
+      }
     }
   }
 }
@@ -426,20 +454,26 @@ extern "C" int iiseg_noise_pack(const float* y, const float* noise, float sigma,
   return 0;
 }
 
-extern "C" int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb, double* sums,
-                               void* dlogits, int passes, void* stream) {
+extern "C" int iiseg_loss_grad_terms(const float* logits, const float* target, int N, int C, int H, int W, float lmb, int terms,
+                                     double* sums, void* dlogits, int passes, void* stream) {
   using namespace iiseg;
   IISEG_CHECK(logits && target && sums && dlogits, "loss_grad: null tensor");
   IISEG_CHECK(N > 0 && C >= 1 && C <= 16 && H > 0 && W > 0, "loss_grad: bad shape");
+  IISEG_CHECK(terms > 0 && terms < 8 && (!(terms & kTermDice) || C >= 2), "loss_grad: terms = bit 0 crossentropy | bit 1 squared_error | bit 2 dice (channel 1)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (passes & 1) IISEG_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), s));
+  if (passes & 1) IISEG_CUDA(cudaMemsetAsync(sums, 0, ((terms & kTermDice) ? 8 : 4) * sizeof(double), s));
   dim3 grid((H * W + 255) / 256, N);
   for (int pass = 0; pass < 2; ++pass) {
     if (!(passes & (1 << pass))) continue;
-    loss_grad_kernel<<<grid, 256, 0, s>>>(logits, target, C, H * W, lmb, sums, reinterpret_cast<__nv_bfloat16*>(dlogits), pass);
+    loss_grad_kernel<<<grid, 256, 0, s>>>(logits, target, C, H * W, lmb, sums, reinterpret_cast<__nv_bfloat16*>(dlogits), pass, terms);
     IISEG_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb, double* sums,
+                               void* dlogits, int passes, void* stream) {
+  return iiseg_loss_grad_terms(logits, target, N, C, H, W, lmb, iiseg::kTermCE | iiseg::kTermMSE, sums, dlogits, passes, stream);
 }
 
 extern "C" int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C, int VH, int VW,

@@ -90,7 +90,7 @@ class DAETrainer(object):
 
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
                  additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda',
-                 optimizer='rmsprop', beta1=0.9, beta2=0.999, adam_epsilon=1e-8):
+                 optimizer='rmsprop', beta1=0.9, beta2=0.999, adam_epsilon=1e-8, training_loss=('crossentropy', 'squared_error')):
         K.require_device()
         self.dev = dev = torch.device(device)
         self.C, self.lr, self.sigma, self.lmb, self.rho, self.eps = n_classes, learning_rate, noise, lmb, rho, epsilon
@@ -99,6 +99,11 @@ class DAETrainer(object):
         assert optimizer in ('rmsprop', 'adam'), optimizer
         self.optimizer, self.beta1, self.beta2, self.adam_eps = optimizer, beta1, beta2, adam_epsilon
         self.adam_state = torch.zeros((2,), dtype=torch.float32, device=dev)
+        # the loss terms train_dae.py:278-294 adds up: crossentropy, dice (metrics.py:93-113, channel 1), lmb * squared_error
+        unknown = sorted(set(training_loss) - set(K.LOSS_TERMS))
+        if unknown or not training_loss:
+            raise NotImplementedError('B200 train step: training_loss terms %s (built: %s)' % (unknown, sorted(K.LOSS_TERMS)))
+        self.terms = sum(K.LOSS_TERMS[t] for t in set(training_loss))
         geo = self.geo = DAENet.__new__(DAENet)          # geometry helpers only (level sizes, crop cone)
         geo.n_classes, geo.nb_h, geo.h_pad, geo.padding = n_classes, nb_features_to_concat, _r64(nb_features_to_concat), padding
         last = concat_h[-1]
@@ -127,7 +132,7 @@ class DAETrainer(object):
                                   (0, up_in)))
             self._splits.append([(up_in, up_in)])
             up_in = n_cl
-        self.sums = torch.zeros((4,), dtype=torch.float64, device=dev)
+        self.sums = torch.zeros((8,), dtype=torch.float64, device=dev)
         self._graphs = {}
         self.last_loss = None
         # One flat fp32 buffer holds the 24 weight-gradient matrices in the order backward produces them (expanding path
@@ -316,11 +321,11 @@ class DAETrainer(object):
         B, H, W = st['B'], st['H'], st['W']
         sizes, Wc, Wu, P = self._sizes, self.Wc, self.Wu, geo.total
         if world is None:
-            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums)      # dL/dlogits over Wc[1]
-        else:       # the loss is a masked mean over the GLOBAL batch (metrics.py:88-89,153-154): global denominators
-            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, passes=1)
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, terms=self.terms)      # dL/dlogits over Wc[1]
+        else:       # the loss is a masked mean over the GLOBAL batch (metrics.py:88-89,153-154): global denominators (and dice sums)
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, passes=1, terms=self.terms)
             world.allreduce_sum(self.sums)
-            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, dlogits=g_c, passes=2)
+            g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, dlogits=g_c, passes=2, terms=self.terms)
         skip = {}                                                                      # level p -> (grad of pool_p from the skip-sum, its window)
         g_u = None
         for i, p in enumerate(range(1, P + 1)):          # expanding path, output towards the bottleneck
@@ -368,12 +373,11 @@ class DAETrainer(object):
                 buf[:, pw[0]:pw[1], pw[2]:pw[3]].copy_(gs_prev)       # data movement only: the skip gradient in place
                 g_in = self._dgrad(lay, g_a, (1, 1, hp, wp), addend=buf)
         s = self.sums
-        self.last_loss = s     # device tensor; loss = s0/s1 + lmb*s2/s3
+        self.last_loss = s     # device tensor; loss = s0/s1 + lmb*s2/s3 (+ the dice term): K.loss_from_sums
         return [lay.grad for lay in self.layers()]
 
     def loss_value(self):
-        s = self.sums.cpu()
-        return float(s[0] / s[1] + self.lmb * s[2] / s[3])
+        return K.loss_from_sums(self.sums.cpu(), self.lmb, self.terms)
 
     def update(self):
         if self.optimizer == 'adam':
@@ -475,9 +479,8 @@ def validate(trainer, h_bf16, y, target, noise_mask=None):
     ref_train_noise.npz); with noise == 0 everything is deterministic."""
     from .functions import MetricsAccumulator, jaccard_from_cm
     logits = trainer.forward(h_bf16, y, None, noise_mask)
-    K.loss_grad(logits, target, trainer.C, trainer.lmb, trainer.sums, passes=1)          # loss sums only
-    s = trainer.sums.cpu()
-    loss = float(s[0] / s[1] + trainer.lmb * s[2] / s[3])
+    K.loss_grad(logits, target, trainer.C, trainer.lmb, trainer.sums, passes=1, terms=trainer.terms)          # loss sums only
+    loss = K.loss_from_sums(trainer.sums.cpu(), trainer.lmb, trainer.terms)
     B, _, H, W = y.shape
     p = torch.empty((B, trainer.C, H, W), dtype=torch.float32, device=y.device)
     K.softmax_nchw(logits, trainer.C, p)
@@ -510,8 +513,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
         raise ValueError('Unknown optimizer')          # train_dae.py:331
     if dae_dict['kind'] != 'standard' or dae_dict['unpool_type'] != 'trackind' or segm_net not in ('fcn8', 'densenet'):
         raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net in (fcn8, densenet)')
-    if sorted(training_loss) != ['crossentropy', 'squared_error']:
-        raise NotImplementedError('B200 train step: training_loss = [crossentropy, squared_error]')
+    if not training_loss or set(training_loss) - set(K.LOSS_TERMS):
+        raise NotImplementedError('B200 train step: training_loss terms among %s (squared_error_h is not built)' % sorted(K.LOSS_TERMS))
     exp_name = build_experiment_name(segm_net, training_loss=training_loss, data_aug=bool(data_augmentation),
                                      learning_rate=learning_rate, lr_anneal=lr_anneal, weight_decay=weight_decay,
                                      optimizer=optimizer, ae_h=ae_h, **dae_dict)
@@ -546,7 +549,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
                                                         concat_h=tuple(dae_dict['concat_h']), additional_pool=dae_dict['additional_pool'])
     tr = DAETrainer(n_classes, fcn[0].output_shape[1], padding, dae_params, concat_h=tuple(dae_dict['concat_h']),
                     n_filters=dae_dict['n_filters'], additional_pool=dae_dict['additional_pool'],
-                    learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb, optimizer=optimizer)
+                    learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb, optimizer=optimizer,
+                    training_loss=tuple(training_loss))
     gen = torch.Generator(device=tr.dev).manual_seed(seed)
     say = print if verbose else (lambda *a, **k: None)
 

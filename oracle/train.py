@@ -132,9 +132,23 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
     return u
 
 
-def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True):
-    """crossentropy (metrics.py:68-91, one_hot=True, void = n_classes) + lmb * squared_error
-    (metrics.py:144-156, void int) of softmax(logits) against the one-hot target (B, C+1, H, W)."""
+def dice_loss(p, target, void_labels, class_for_dice=1):
+    """metrics.py:93-113: -(2 sum(t p) + 1) / (sum t + sum p + 1) over the flattened channel `class_for_dice` of the softmax
+    output p and of the one-hot target (cast to int32); entries whose TARGET VALUE equals a void label are dropped first
+    (a comparison of 0/1 values with the label id, as the reference writes it -- not of the pixel's class)."""
+    t = target[:, class_for_dice].reshape(-1).to(torch.int32)
+    q = p[:, class_for_dice].reshape(-1)
+    for v in void_labels:
+        keep = t != int(v)
+        q, t = q[keep], t[keep]
+    inter = (t * q).sum()
+    return -(2.0 * inter + 1) / (t.sum() + q.sum() + 1)
+
+
+def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True, use_dice=False):
+    """crossentropy (metrics.py:68-91, one_hot=True, void = n_classes) [+ dice_loss (metrics.py:93-113, void_labels =
+    [n_classes])] + lmb * squared_error (metrics.py:144-156, void int) of softmax(logits) against the one-hot target
+    (B, C+1, H, W), in the order train_dae.py:278-294 adds them."""
     p = torch.softmax(logits, dim=1)
     true = target.argmax(dim=1)
     mask = (true != n_classes).to(p.dtype)
@@ -144,6 +158,8 @@ def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True):
         idx = (true * mask.long()).unsqueeze(1)                       # void pixels point at class 0, then get masked
         ce = -torch.log(pc.gather(1, idx)).squeeze(1)
         loss = loss + (ce * mask).sum() / mask.sum()
+    if use_dice:
+        loss = loss + dice_loss(p, target, [n_classes])
     if use_mse:
         t = target[:, :n_classes]
         se = ((p - t) ** 2).mean(dim=1)
@@ -169,7 +185,7 @@ def adam_update(params, moms, vels, grads, t, lr, beta1=0.9, beta2=0.999, eps=1e
 
 
 def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=None, noise_mask=None, lmb=1.0,
-               rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, **dae_kw):
+               rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, loss_terms=None, **dae_kw):
     """One train_fn call (train_dae.py:334-335): returns (loss, grads, new_params, new_accus).
     lasagne.updates.rmsprop: a <- rho*a + (1-rho)*g^2 ; p <- p - lr * g / sqrt(a + eps)."""
     ps = [p.clone().requires_grad_(True) for p in params]
@@ -179,7 +195,7 @@ def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=N
     else:
         y_mask = None if noise_mask is None else y + noise_mask
     logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, tap=tap, **dae_kw)
-    loss = loss_fn(logits, target, n_classes, lmb=lmb)
+    loss = loss_fn(logits, target, n_classes, lmb=lmb, **(loss_terms or {}))
     grads = torch.autograd.grad(loss, ps)
     new_p, new_a = [], []
     for p, a, g in zip(params, accus, grads):

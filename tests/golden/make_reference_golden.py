@@ -100,6 +100,9 @@ CASES = {
     'ref_train_adam': dict(script='train', optimizer='adam', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
                            learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'],
                            weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_train_dice': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
+                           learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'dice', 'squared_error'],
+                           weights=dict(fn='dae', seed=1, out_gain=0.1)),
     'ref_train': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2, learning_rate=0.001,
                       lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'], weights=dict(fn='dae', seed=1, out_gain=0.1)),
 }

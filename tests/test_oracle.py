@@ -418,7 +418,7 @@ def test_oracle_temperature_vs_reference_run():
     assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
 
 
-@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise', 'ref_train_adam'])
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise', 'ref_train_adam', 'ref_train_dice'])
 def test_oracle_train_step_vs_reference_run(name):
     """oracle/train.py against the reference's own train_dae.py:train() (two epochs of two rmsprop steps, the learning rate
     annealed in between, validation after each epoch; tests/golden/ref_train.npz, and ref_train_noise.npz with noise = 0.5 and
@@ -439,6 +439,8 @@ def test_oracle_train_step_vs_reference_run(name):
     params, accus = [p.clone() for p in init], [torch.zeros_like(p) for p in init]
     moms, t_adam = [torch.zeros_like(p) for p in init], 0.0
     lr = np.float32(case['learning_rate'])
+    tl = case['training_loss']          # ref_train_dice: crossentropy + dice_loss + squared_error (train_dae.py:278-294)
+    terms = dict(use_ce='crossentropy' in tl, use_mse='squared_error' in tl, use_dice='dice' in tl)
     err_train, err_valid, jacc_val, mse_val = [], [], [], []
     for epoch in range(case['num_epochs']):
         tot = 0.0
@@ -449,7 +451,7 @@ def test_oracle_train_step_vs_reference_run(name):
             if sigma > 0:
                 ks = next(train_k)
                 nkw = dict(noise_main=sigma * rng_mrg.draw(int(ks[0]), y.shape), noise_mask=[sigma * rng_mrg.draw(int(k), y.shape) for k in ks[1:]])
-            loss, grads, p_rms, a_rms = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], **nkw)
+            loss, grads, p_rms, a_rms = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], loss_terms=terms, **nkw)
             if case.get('optimizer') == 'adam':          # lasagne.updates.adam (train_dae.py:328-329)
                 params, moms, accus, t_adam = T_.adam_update(params, moms, accus, grads, t_adam, float(lr))
             else:
@@ -464,7 +466,7 @@ def test_oracle_train_step_vs_reference_run(name):
                 # validation: deterministic=True switches the main noise off, but the DePool2D sub-graphs stay noised
                 msk = [y + sigma * rng_mrg.draw(int(k), y.shape) for k in next(val_k)] if sigma > 0 else None
                 logits = T_.dae_forward_train(params, y, h, 100, mask_source_y=msk)
-                cost += float(T_.loss_fn(logits, torch.from_numpy(Lb), RF.NCLS, lmb=case['lmb']))
+                cost += float(T_.loss_fn(logits, torch.from_numpy(Lb), RF.NCLS, lmb=case['lmb'], **terms))
                 p = torch.softmax(logits, dim=1).numpy()
             jacc = jacc + M.jaccard(p, Lb, RF.NCLS)
             mse += float(M.squared_error(p, Lb, RF.NCLS))

@@ -107,6 +107,38 @@ def test_backward_kernels_against_definitions(cuda):
     assert torch.equal(out[16:48, :P].float(), ref) and float(out[:16].abs().max()) == 0 and float(out[:, P:].abs().max()) == 0
 
 
+LOSS_TERM_SETS = [('crossentropy',), ('squared_error',), ('dice',), ('crossentropy', 'dice'), ('crossentropy', 'dice', 'squared_error')]
+
+
+@pytest.mark.parametrize('tl', LOSS_TERM_SETS, ids=['+'.join(t) for t in LOSS_TERM_SETS])
+def test_loss_terms_against_the_oracle(cuda, tl):
+    """`iiseg_loss_grad_terms`: every combination of the terms train_dae.py:278-294 adds up (crossentropy, dice_loss on channel 1,
+    lmb * squared_error; the reference's DEFAULT is ['squared_error'] alone, train_dae.py:56) against oracle/train.py:loss_fn and its
+    autograd gradient with respect to the logits.  Void pixels (label = n_classes) included; lmb = 0.7."""
+    from iterative_inference_segm_b200 import _kernels as K
+    N, H, W, lmb = 2, 19, 23, 0.7
+    gen = torch.Generator().manual_seed(3)
+    logits = (3.0 * torch.randn((N, NCLS, H, W), generator=gen)).requires_grad_(True)
+    lab = torch.randint(0, NCLS + 1, (N, H, W), generator=gen)
+    target = torch.nn.functional.one_hot(lab, NCLS + 1).permute(0, 3, 1, 2).float().contiguous()
+    kw = dict(use_ce='crossentropy' in tl, use_mse='squared_error' in tl, use_dice='dice' in tl)
+    loss_o = OT.loss_fn(logits, target, NCLS, lmb=lmb, **kw)
+    g_o, = torch.autograd.grad(loss_o, logits)
+    terms = sum(K.LOSS_TERMS[t] for t in tl)
+    l16 = torch.zeros((N, H, W, 16), dtype=torch.float32, device=cuda)
+    l16[..., :NCLS] = logits.detach().permute(0, 2, 3, 1).to(cuda)
+    sums = torch.full((8,), 123.0, dtype=torch.float64, device=cuda)          # stale contents: pass 0 zeroes what it uses
+    g = K.loss_grad(l16, target.to(cuda), NCLS, lmb, sums, terms=terms)
+    torch.cuda.synchronize()
+    loss_d = K.loss_from_sums(sums.cpu(), lmb, terms)
+    g_d = g.float().cpu()[..., :NCLS].permute(0, 3, 1, 2)
+    err = float((g_d - g_o).norm() / g_o.norm())
+    print('loss terms %s: loss %.7f vs oracle %.7f; gradient relative L2 error %.2e (bf16 output)' % ('+'.join(tl), loss_d, float(loss_o), err))
+    assert abs(loss_d - float(loss_o)) < 2e-6 * abs(float(loss_o))
+    assert err < 3e-3                                     # the gradient is stored in bf16 (2^-9 relative per element)
+    assert float(g.float()[..., NCLS:].abs().max()) == 0          # padded channels carry no gradient
+
+
 # (Cg, cin_pad, K, slabs, K offsets of the three tap rows): CTA-pair and single-CTA launches, 16-row groups, odd M
 WGRAD_CASES = [(16, 64, 4096, 1, (0, 72, 144)), (128, 256, 8192, 4, (0, 72, 144)), (64, 16, 8192, 2, (0, 32, 64)),
                (256, 512, 4096, 2, (0, 32, 64)), (128, 128, 4096 * 3, 3, (0, 216, 432))]
@@ -246,7 +278,7 @@ def test_train_loop_runs_and_writes_the_reference_checkpoints(cuda, tmp_path, se
     assert dae.net.total == 6
 
 
-@pytest.mark.parametrize('name', ['ref_train', 'ref_train_adam'])
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_adam', 'ref_train_dice'])
 def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     """train() of this package against the reference's OWN run of train_dae.py:train() (executed through oracle/refrun,
     tests/golden/ref_train.npz): same arguments, the seeded checkpoint on disk where `resume=True` reads it, the same iterators;
