@@ -51,8 +51,13 @@ def run(out_dir, distributed):
             tr.step_dp(sl(h), sl(y), sl(L), sl(nm), sl(nk), world=w)
         torch.cuda.synchronize()
         outs.append(([p.cpu().numpy() for p in tr.params()], tr.loss_value()))
+    # adam + the dice term: its three whole-batch sums are all-reduced with the loss denominators between the two loss passes
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=0.5, optimizer='adam', training_loss=('crossentropy', 'dice', 'squared_error'))
+    tr.step(sl(h), sl(y), sl(L), sl(nm), sl(nk), world=world if distributed else None)
+    torch.cuda.synchronize()
+    loss_ad, w_ad = tr.loss_value(), tr.params()[-2].cpu().numpy()
     if world.rank == 0:
-        np.savez(os.path.join(out_dir, 'result_%d.npz' % world.size), cm=a['cm'], jacc=a['jacc_tot'], jacc_fcn=a['jacc_tot_fcn'],
+        np.savez(os.path.join(out_dir, 'result_%d.npz' % world.size), loss_adam_dice=np.array([loss_ad]), w_last_adam_dice=w_ad, cm=a['cm'], jacc=a['jacc_tot'], jacc_fcn=a['jacc_tot_fcn'],
                  it=np.array(a['iterative'], dtype=np.float64), n_exec=np.array(a['n_exec']), mats=mats, res=res,
                  loss=np.array([outs[0][1], outs[1][1]]),
                  same=np.array([all(np.array_equal(x, z) for x, z in zip(outs[0][0], outs[1][0]))]),

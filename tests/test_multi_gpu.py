@@ -42,3 +42,10 @@ def test_two_ranks_equal_one_rank(cuda, tmp_path):
     for k in ('w0', 'w_last'):            # the weight UPDATE of two ranks vs one, relative L2 (bf16 gradients, different summation order)
         upd = np.linalg.norm(one[k] - one[k + '_init'])
         assert np.linalg.norm(one[k] - two[k]) < 0.05 * upd, (k, np.linalg.norm(one[k] - two[k]), upd)
+    # adam + crossentropy / dice / squared_error: the dice term's whole-batch sums (I, T, P) are global -> the same loss on 1 and 2 ranks
+    assert abs(one['loss_adam_dice'][0] - two['loss_adam_dice'][0]) < 1e-6 * abs(one['loss_adam_dice'][0])
+    assert abs(one['loss_adam_dice'][0] - one['loss'][0]) > 1e-4          # the dice term is in the loss
+    upd = np.linalg.norm(one['w_last_adam_dice'] - one['w_last_init'])
+    d = np.linalg.norm(one['w_last_adam_dice'] - two['w_last_adam_dice'])
+    print('adam + dice, 2 ranks vs 1: weight update differs by %.3f of its norm' % (d / upd))
+    assert d < 0.2 * upd          # adam's first step is lr * sign(g): only elements with ~0 gradient may differ (summation order)
