@@ -62,8 +62,11 @@ def _q_bf16(x):
 
 
 def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=('pool4',), additional_pool=2,
-                      emulate_bf16=False, tap=None):
+                      emulate_bf16=False, tap=None, ae_out=None):
     """Differentiable DAE forward -> logits (before the softmax), cropped to the input size.
+    `ae_out` (dict): receives the two layers the `ae_h` loss term compares (train_dae.py:238-239,317-319): 'h' = the layer named
+    'h_to_recon', the DAE's own pool_{n_pool} (models/fcn_down.py:117-122), and 'h_hat' = the layer named 'h_hat',
+    fused_up_{n_pool+1} = up_conv_{n_pool+1} + pool_{n_pool} (models/fcn_up.py:145-146).
     `mask_source_y`: input of the separate contracting-path forward the DePool2D masks are taken from
     (None: the same forward).  Masks are constants (detached).  `emulate_bf16`: weights, inputs and every
     stored activation are rounded to bf16 (straight-through), as on the B200 path; the arithmetic stays fp32.
@@ -126,6 +129,8 @@ def dae_forward_train(params, y_noisy, h, padding, mask_source_y=None, concat_h=
         c = F.conv2d(v, Wu[i][0], Wu[i][1], padding=1)
         if p > 1:
             a, b = L.center_crop_pair(c, pools[p - 2])
+            if ae_out is not None and p == n_pool + 1:
+                ae_out['h'], ae_out['h_hat'] = pools[n_pool - 1], a + b
             u = q(a + b)
         else:
             u = L.center_crop_to(c, y_noisy.shape[2], y_noisy.shape[3])
@@ -143,6 +148,14 @@ def dice_loss(p, target, void_labels, class_for_dice=1):
         q, t = q[keep], t[keep]
     inter = (t * q).sum()
     return -(2.0 * inter + 1) / (t.sum() + q.sum() + 1)
+
+
+def ae_h_loss(ae):
+    """train_dae.py:317-319: `squared_error_L(h, h_hat).mean()`.  NB h_hat = up_conv + h (skip sum), so the term is the mean square
+    of up_conv_{n_pool+1}'s output up to fp32 rounding, and its gradient with respect to h cancels exactly (2 (h - h_hat) / n from
+    `h`, the negative of it through the sum).  `freezeParameters(net['pool' + str(n_pool)])` (models/fcn_down.py:80-81, single=True)
+    touches the pooling layer only, which has no parameters: nothing is frozen."""
+    return ((ae['h'] - ae['h_hat']) ** 2).mean()
 
 
 def loss_fn(logits, target, n_classes, lmb=1.0, use_ce=True, use_mse=True, use_dice=False):
@@ -185,7 +198,7 @@ def adam_update(params, moms, vels, grads, t, lr, beta1=0.9, beta2=0.999, eps=1e
 
 
 def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=None, noise_mask=None, lmb=1.0,
-               rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, loss_terms=None, **dae_kw):
+               rho=0.9, eps=1e-6, emulate_bf16=False, tap=None, loss_terms=None, ae_h=False, **dae_kw):
     """One train_fn call (train_dae.py:334-335): returns (loss, grads, new_params, new_accus).
     lasagne.updates.rmsprop: a <- rho*a + (1-rho)*g^2 ; p <- p - lr * g / sqrt(a + eps)."""
     ps = [p.clone().requires_grad_(True) for p in params]
@@ -194,8 +207,11 @@ def train_step(params, accus, y, h, target, n_classes, padding, lr, noise_main=N
         y_mask = [y + n for n in noise_mask]          # one draw per DePool2D (level 1 first)
     else:
         y_mask = None if noise_mask is None else y + noise_mask
-    logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, tap=tap, **dae_kw)
+    ae = {} if ae_h else None
+    logits = dae_forward_train(ps, y_main, h, padding, mask_source_y=y_mask, emulate_bf16=emulate_bf16, tap=tap, ae_out=ae, **dae_kw)
     loss = loss_fn(logits, target, n_classes, lmb=lmb, **(loss_terms or {}))
+    if ae_h:
+        loss = loss + ae_h_loss(ae)
     grads = torch.autograd.grad(loss, ps)
     new_p, new_a = [], []
     for p, a, g in zip(params, accus, grads):

@@ -100,6 +100,9 @@ CASES = {
     'ref_train_adam': dict(script='train', optimizer='adam', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
                            learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'],
                            weights=dict(fn='dae', seed=1, out_gain=0.1)),
+    'ref_train_aeh': dict(script='train', ae_h=True, dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
+                          learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'squared_error'],
+                          weights=dict(fn='dae', seed=1, out_gain=0.1)),
     'ref_train_dice': dict(script='train', dae=dae_dict(), H=32, W=40, B=2, nbatches=2, val_nbatches=1, num_epochs=2,
                            learning_rate=0.001, lr_anneal=0.99, lmb=1, training_loss=['crossentropy', 'dice', 'squared_error'],
                            weights=dict(fn='dae', seed=1, out_gain=0.1)),
@@ -288,7 +291,7 @@ def run_case(name, case, current, write=True):
         with contextlib.redirect_stdout(io.StringIO()):
             exp_name = helpers.build_experiment_name('fcn8', training_loss=case['training_loss'], data_aug=True,
                                                      learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
-                                                     optimizer=case.get('optimizer', 'rmsprop'), ae_h=False, **d)
+                                                     optimizer=case.get('optimizer', 'rmsprop'), ae_h=case.get('ae_h', False), **d)
         ldir = os.path.join(WORK, 'load', 'camvid', exp_name)
         os.makedirs(ldir)
         weights.save_npz(os.path.join(ldir, 'dae_model_best.npz'), case_dae_params(case))          # resume=True reads it (train_dae.py:186)
@@ -299,7 +302,7 @@ def run_case(name, case, current, write=True):
         with contextlib.redirect_stdout(buf):
             train_dae.train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
                             num_epochs=case['num_epochs'], max_patience=100, optimizer=case.get('optimizer', 'rmsprop'), training_loss=list(case['training_loss']),
-                            batch_size=[case['B']] * 3, ae_h=False, dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
+                            batch_size=[case['B']] * 3, ae_h=case.get('ae_h', False), dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
                             data_augmentation={'crop_size': None}, savepath=os.path.join(WORK, 'save'), loadpath=os.path.join(WORK, 'load'),
                             resume=True, lmb=case['lmb'])
         sdir = os.path.join(WORK, 'save', 'camvid', exp_name)

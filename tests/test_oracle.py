@@ -418,7 +418,7 @@ def test_oracle_temperature_vs_reference_run():
     assert float(np.abs(y1.numpy() - fx['Y_fcn']).max()) > 1e-2          # the temperature does something
 
 
-@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise', 'ref_train_adam', 'ref_train_dice'])
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_noise', 'ref_train_adam', 'ref_train_dice', 'ref_train_aeh'])
 def test_oracle_train_step_vs_reference_run(name):
     """oracle/train.py against the reference's own train_dae.py:train() (two epochs of two rmsprop steps, the learning rate
     annealed in between, validation after each epoch; tests/golden/ref_train.npz, and ref_train_noise.npz with noise = 0.5 and
@@ -451,7 +451,7 @@ def test_oracle_train_step_vs_reference_run(name):
             if sigma > 0:
                 ks = next(train_k)
                 nkw = dict(noise_main=sigma * rng_mrg.draw(int(ks[0]), y.shape), noise_mask=[sigma * rng_mrg.draw(int(k), y.shape) for k in ks[1:]])
-            loss, grads, p_rms, a_rms = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], loss_terms=terms, **nkw)
+            loss, grads, p_rms, a_rms = T_.train_step(params, accus, y, h, torch.from_numpy(Lb), RF.NCLS, 100, float(lr), lmb=case['lmb'], loss_terms=terms, ae_h=case.get('ae_h', False), **nkw)
             if case.get('optimizer') == 'adam':          # lasagne.updates.adam (train_dae.py:328-329)
                 params, moms, accus, t_adam = T_.adam_update(params, moms, accus, grads, t_adam, float(lr))
             else:
@@ -465,8 +465,11 @@ def test_oracle_train_step_vs_reference_run(name):
             with torch.no_grad():
                 # validation: deterministic=True switches the main noise off, but the DePool2D sub-graphs stay noised
                 msk = [y + sigma * rng_mrg.draw(int(k), y.shape) for k in next(val_k)] if sigma > 0 else None
-                logits = T_.dae_forward_train(params, y, h, 100, mask_source_y=msk)
+                ae = {} if case.get('ae_h') else None          # ref_train_aeh: + squared_error(h, h_hat).mean() (train_dae.py:317-319)
+                logits = T_.dae_forward_train(params, y, h, 100, mask_source_y=msk, ae_out=ae)
                 cost += float(T_.loss_fn(logits, torch.from_numpy(Lb), RF.NCLS, lmb=case['lmb'], **terms))
+                if ae is not None:
+                    cost += float(T_.ae_h_loss(ae))
                 p = torch.softmax(logits, dim=1).numpy()
             jacc = jacc + M.jaccard(p, Lb, RF.NCLS)
             mse += float(M.squared_error(p, Lb, RF.NCLS))
