@@ -406,6 +406,13 @@ int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int 
                     double* sums, void* dlogits, int passes, void* stream);
 int iiseg_loss_grad_terms(const float* logits, const float* target, int N, int C, int H, int W,
                           float lmb, int terms, double* sums, void* dlogits, int passes, void* stream);
+/* The ae_h loss term of train_dae.py:238-239,317-319: squared_error(h, h_hat).mean(), h = the DAE's own pool_{n_pool}
+ * ('h_to_recon', models/fcn_down.py:117-122), h_hat = fused_up_{n_pool+1} = up_conv_{n_pool+1} + h ('h_hat', models/fcn_up.py:145-146)
+ * -> the mean square of that conv's output c (the h parts cancel, in the value up to fp32 rounding and in the gradient exactly).
+ * iiseg_sq_sum: sums2[0] += sum of x^2 (x bf16, n elements, n % 8 == 0), sums2[1] += n (fp64; data-parallel ranks all-reduce
+ * both).  iiseg_ae_grad_add: g += 2 c / sums2[1] (g, c bf16, same n): the term's gradient with respect to c. */
+int iiseg_sq_sum(const void* x, long long n, double* sums2, void* stream);
+int iiseg_ae_grad_add(void* g, const void* c, long long n, const double* sums2, void* stream);
 int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,
                       int VH, int VW, int v_h0, int v_w0, int UH, int UW, int u_h0, int u_w0,
                       void* stream);

@@ -525,9 +525,24 @@ def loss_grad(logits, target, n_classes, lmb, sums, dlogits=None, passes=3, term
     return dlogits
 
 
-def loss_from_sums(s, lmb, terms=3):
-    """The scalar loss from the (host) sums of `loss_grad`."""
-    loss = 0.0
+def sq_sum(x, sums2):
+    """sums2[0] += sum x^2, sums2[1] += x.numel() (the ae_h term of train_dae.py:317-319; x bf16, sums2 fp64 [2])."""
+    _chk(x, BF16, 'x')
+    assert sums2.dtype == torch.float64 and sums2.numel() == 2 and sums2.is_contiguous()
+    _lib.call('iiseg_sq_sum', _ptr(x), x.numel(), _ptr(sums2), _stream())
+
+
+def ae_grad_add(g, c, sums2):
+    """g += 2 c / sums2[1]: the gradient of mean(c^2) over the (global) element count held on the device."""
+    _chk(g, BF16, 'g')
+    _chk(c, BF16, 'c')
+    assert g.shape == c.shape and sums2.dtype == torch.float64 and sums2.numel() == 2
+    _lib.call('iiseg_ae_grad_add', _ptr(g), _ptr(c), g.numel(), _ptr(sums2), _stream())
+
+
+def loss_from_sums(s, lmb, terms=3, ae_h=False):
+    """The scalar loss from the (host) sums of `loss_grad` (+ `sq_sum` in s[8:10] with ae_h)."""
+    loss = float(s[8] / s[9]) if ae_h else 0.0
     if terms & 1:
         loss += float(s[0] / s[1])
     if terms & 4:

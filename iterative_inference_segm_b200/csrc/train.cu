@@ -440,6 +440,42 @@ static int tgrid(long long total) {
   return (int)(b < cap ? b : cap);
 }
 
+// ---- ae_h term (train_dae.py:317-319): squared_error(h, h_hat).mean() with h_hat = c + h (skip sum) ---------------
+// = mean(c^2) of the expanding-path conv c = up_conv_{n_pool+1} (the h parts cancel, also in the gradient): sums2[0] += sum c^2,
+// sums2[1] += element count (fp64; data-parallel ranks all-reduce both), then g += 2 c / sums2[1].
+__global__ void __launch_bounds__(256) sq_sum_kernel(const uint4* __restrict__ x, long long n8, double* __restrict__ sums2) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    const uint4 v = ldg_nc_v4(x + i);
+    const float a0 = bf16_lo(v.x), a1 = bf16_hi(v.x), a2 = bf16_lo(v.y), a3 = bf16_hi(v.y);
+    const float a4 = bf16_lo(v.z), a5 = bf16_hi(v.z), a6 = bf16_lo(v.w), a7 = bf16_hi(v.w);
+    acc += (double)(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3) + (double)(a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7);
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    atomicAdd(sums2, a);
+    if (blockIdx.x == 0) atomicAdd(sums2 + 1, (double)(n8 * 8));
+  }
+}
+
+__global__ void __launch_bounds__(256) ae_grad_add_kernel(uint4* __restrict__ g, const uint4* __restrict__ c, long long n8,
+                                                          const double* __restrict__ sums2) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const float k = (float)(2.0 / sums2[1]);
+  const uint4 a = g[i], b = ldg_nc_v4(c + i);
+  stg_v4(g + i, make_uint4(pack_bf16x2(bf16_lo(a.x) + k * bf16_lo(b.x), bf16_hi(a.x) + k * bf16_hi(b.x)),
+                           pack_bf16x2(bf16_lo(a.y) + k * bf16_lo(b.y), bf16_hi(a.y) + k * bf16_hi(b.y)),
+                           pack_bf16x2(bf16_lo(a.z) + k * bf16_lo(b.z), bf16_hi(a.z) + k * bf16_hi(b.z)),
+                           pack_bf16x2(bf16_lo(a.w) + k * bf16_lo(b.w), bf16_hi(a.w) + k * bf16_hi(b.w))));
+}
+
 }  // namespace iiseg
 
 extern "C" int iiseg_noise_pack(const float* y, const float* noise, float sigma, void* dst, int N, int C, int H, int W,
@@ -474,6 +510,29 @@ extern "C" int iiseg_loss_grad_terms(const float* logits, const float* target, i
 extern "C" int iiseg_loss_grad(const float* logits, const float* target, int N, int C, int H, int W, float lmb, double* sums,
                                void* dlogits, int passes, void* stream) {
   return iiseg_loss_grad_terms(logits, target, N, C, H, W, lmb, iiseg::kTermCE | iiseg::kTermMSE, sums, dlogits, passes, stream);
+}
+
+extern "C" int iiseg_sq_sum(const void* x, long long n, double* sums2, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(x && sums2, "sq_sum: null tensor");
+  IISEG_CHECK(n > 0 && n % 8 == 0, "sq_sum: element count must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  const long long want = (n8 + 255) / 256;
+  const int blocks = (int)(want < 4 * 148 ? want : 4 * 148);          // grid-stride: a few blocks per SM, one atomic each
+  sq_sum_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x), n8, sums2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_ae_grad_add(void* g, const void* c, long long n, const double* sums2, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(g && c && sums2, "ae_grad_add: null tensor");
+  IISEG_CHECK(n > 0 && n % 8 == 0, "ae_grad_add: element count must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  ae_grad_add_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint4*>(g), reinterpret_cast<const uint4*>(c), n8, sums2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C, int VH, int VW,

@@ -90,7 +90,7 @@ class DAETrainer(object):
 
     def __init__(self, n_classes, nb_features_to_concat, padding, params, concat_h=('pool4',), n_filters=64,
                  additional_pool=2, learning_rate=1e-3, noise=0.5, lmb=1.0, rho=0.9, epsilon=1e-6, device='cuda',
-                 optimizer='rmsprop', beta1=0.9, beta2=0.999, adam_epsilon=1e-8, training_loss=('crossentropy', 'squared_error')):
+                 optimizer='rmsprop', beta1=0.9, beta2=0.999, adam_epsilon=1e-8, training_loss=('crossentropy', 'squared_error'), ae_h=False):
         K.require_device()
         self.dev = dev = torch.device(device)
         self.C, self.lr, self.sigma, self.lmb, self.rho, self.eps = n_classes, learning_rate, noise, lmb, rho, epsilon
@@ -104,6 +104,11 @@ class DAETrainer(object):
         if unknown or not training_loss:
             raise NotImplementedError('B200 train step: training_loss terms %s (built: %s)' % (unknown, sorted(K.LOSS_TERMS)))
         self.terms = sum(K.LOSS_TERMS[t] for t in set(training_loss))
+        # ae_h (train_dae.py:238-239,317-319): + squared_error(h_to_recon, h_hat).mean() = the mean square of up_conv_{n_pool+1}
+        # over its WHOLE map (h_hat = up_conv + h): the crop cone is widened to the full maps from that level down
+        self.ae_h = bool(ae_h)
+        if self.ae_h and additional_pool < 1:
+            raise ValueError('ae_h needs additional_pool >= 1: no layer is named h_hat otherwise (models/fcn_up.py:145-146)')
         geo = self.geo = DAENet.__new__(DAENet)          # geometry helpers only (level sizes, crop cone)
         geo.n_classes, geo.nb_h, geo.h_pad, geo.padding = n_classes, nb_features_to_concat, _r64(nb_features_to_concat), padding
         last = concat_h[-1]
@@ -132,7 +137,7 @@ class DAETrainer(object):
                                   (0, up_in)))
             self._splits.append([(up_in, up_in)])
             up_in = n_cl
-        self.sums = torch.zeros((8,), dtype=torch.float64, device=dev)
+        self.sums = torch.zeros((10,), dtype=torch.float64, device=dev)      # 0-3 CE / MSE, 4-6 dice, 8-9 ae_h
         self._graphs = {}
         self.last_loss = None
         # One flat fp32 buffer holds the 24 weight-gradient matrices in the order backward produces them (expanding path
@@ -222,6 +227,9 @@ class DAETrainer(object):
         B, _, H, W = y.shape
         self._sizes = sizes = geo.level_sizes(H, W)
         self.Wc, self.Wu = geo.cone_windows(H, W)
+        if self.ae_h:
+            for p in range(geo.n_pool + 1, geo.total + 1):
+                self.Wc[p] = self.Wu[p] = (0, sizes[p - 1][0], 0, sizes[p - 1][1])
         st = self.st = {'B': B, 'H': H, 'W': W, 'h': h_bf16}
         st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
         st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
@@ -259,7 +267,13 @@ class DAETrainer(object):
             st['v'][p] = v
             lay = self.up[i]
             win = (hl - ul, wl - vl, hh2 - hl, wh - wl)
-            if p > 1:
+            if self.ae_h and p == geo.n_pool + 1:
+                # h_hat = up_conv_p + pool_{p-1} over the full map; the conv's own output is kept for the ae_h term
+                assert lay.cout == lay.cout_pad and (hl, wl) == (0, 0)
+                st['ae_c'] = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win)
+                u = st['ae_c'] + st['pools'][p - 2]
+                u_origin = (0, 0)
+            elif p > 1:
                 u = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win, addend=st['pools'][p - 2], addend_off=(hl, wl))
                 u_origin = (hl, wl)
             else:
@@ -320,6 +334,8 @@ class DAETrainer(object):
         st, geo = self.st, self.geo
         B, H, W = st['B'], st['H'], st['W']
         sizes, Wc, Wu, P = self._sizes, self.Wc, self.Wu, geo.total
+        if self.ae_h:
+            self._ae_sums()
         if world is None:
             g_c = K.loss_grad(st['logits'], target, self.C, self.lmb, self.sums, terms=self.terms)      # dL/dlogits over Wc[1]
         else:       # the loss is a masked mean over the GLOBAL batch (metrics.py:88-89,153-154): global denominators (and dice sums)
@@ -338,12 +354,17 @@ class DAETrainer(object):
             # pooled positions under the unpooled window
             S2h, S2w = sizes[p - 1][0] // 2, sizes[p - 1][1] // 2
             pu = (ul // 2, min((uh - 1) // 2 + 1, S2h), vl // 2, min((vh - 1) // 2 + 1, S2w))
-            if p < P:
+            ae_level = self.ae_h and p == geo.n_pool          # the level whose fused sum is h_hat = c_{p+1} + pool_p
+            if p < P and not ae_level:
                 assert pu == tuple(Wc[p + 1]), (pu, Wc[p + 1])
             g_u = K.depool2_bwd(g_v, st['masksB'][p - 1], sizes[p - 1][0], sizes[p - 1][1], (ul, vl), (pu[0], pu[2]),
                                 (pu[1] - pu[0], pu[3] - pu[2]))
             skip[p] = (g_u, pu)          # u_p = c_{p+1} + pool_p (p < P) or pool_P itself: gradient of pool_p over window pu
             g_c = g_u                    # ... and of c_{p+1}
+            if ae_level:                 # + d mean((h - h_hat)^2) / d c_{p+1} = 2 c / n over the whole map (pool_p's share cancels)
+                g_c = torch.zeros_like(st['ae_c'])
+                g_c[:, pu[0]:pu[1], pu[2]:pu[3]].copy_(g_u)
+                K.ae_grad_add(g_c, st['ae_c'], self.sums[8:10])
         # contracting path, bottleneck towards the input
         g_in = None
         for p in range(P, 0, -1):
@@ -376,8 +397,12 @@ class DAETrainer(object):
         self.last_loss = s     # device tensor; loss = s0/s1 + lmb*s2/s3 (+ the dice term): K.loss_from_sums
         return [lay.grad for lay in self.layers()]
 
+    def _ae_sums(self):
+        self.sums[8:10].zero_()
+        K.sq_sum(self.st['ae_c'], self.sums[8:10])
+
     def loss_value(self):
-        return K.loss_from_sums(self.sums.cpu(), self.lmb, self.terms)
+        return K.loss_from_sums(self.sums.cpu(), self.lmb, self.terms, self.ae_h)
 
     def update(self):
         if self.optimizer == 'adam':
@@ -480,7 +505,9 @@ def validate(trainer, h_bf16, y, target, noise_mask=None):
     from .functions import MetricsAccumulator, jaccard_from_cm
     logits = trainer.forward(h_bf16, y, None, noise_mask)
     K.loss_grad(logits, target, trainer.C, trainer.lmb, trainer.sums, passes=1, terms=trainer.terms)          # loss sums only
-    loss = K.loss_from_sums(trainer.sums.cpu(), trainer.lmb, trainer.terms)
+    if trainer.ae_h:          # test_loss += squared_error_L(h_test, h_hat_test).mean() (train_dae.py:319)
+        trainer._ae_sums()
+    loss = K.loss_from_sums(trainer.sums.cpu(), trainer.lmb, trainer.terms, trainer.ae_h)
     B, _, H, W = y.shape
     p = torch.empty((B, trainer.C, H, W), dtype=torch.float32, device=y.device)
     K.softmax_nchw(logits, trainer.C, p)
@@ -515,6 +542,8 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
         raise NotImplementedError('B200 train step: kind=standard, unpool_type=trackind, segmentation_net in (fcn8, densenet)')
     if not training_loss or set(training_loss) - set(K.LOSS_TERMS):
         raise NotImplementedError('B200 train step: training_loss terms among %s (squared_error_h is not built)' % sorted(K.LOSS_TERMS))
+    if ae_h and 'pool' not in dae_dict['concat_h'][-1]:
+        raise ValueError('Plug&Play version needs concat_h to be different than input')          # train_dae.py:179-180
     exp_name = build_experiment_name(segm_net, training_loss=training_loss, data_aug=bool(data_augmentation),
                                      learning_rate=learning_rate, lr_anneal=lr_anneal, weight_decay=weight_decay,
                                      optimizer=optimizer, ae_h=ae_h, **dae_dict)
@@ -550,7 +579,7 @@ def train(dataset, segm_net, learning_rate=0.005, lr_anneal=1.0, weight_decay=1e
     tr = DAETrainer(n_classes, fcn[0].output_shape[1], padding, dae_params, concat_h=tuple(dae_dict['concat_h']),
                     n_filters=dae_dict['n_filters'], additional_pool=dae_dict['additional_pool'],
                     learning_rate=learning_rate, noise=dae_dict['noise'], lmb=lmb, optimizer=optimizer,
-                    training_loss=tuple(training_loss))
+                    training_loss=tuple(training_loss), ae_h=ae_h)
     gen = torch.Generator(device=tr.dev).manual_seed(seed)
     say = print if verbose else (lambda *a, **k: None)
 

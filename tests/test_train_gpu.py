@@ -174,12 +174,14 @@ def test_bias_grad_matches_sum(cuda):
         assert (out[:, :5] == 0).all() and (out[:, 6:] == 0).all()
 
 
-def test_graphed_step_equals_eager_step(cuda):
-    """DAETrainer.step_graphed (eager, then capture + replay, then replay) == DAETrainer.step, bit for bit, over four steps."""
+@pytest.mark.parametrize('kw', [{}, {'optimizer': 'adam', 'ae_h': True}], ids=['rmsprop', 'adam+ae_h'])
+def test_graphed_step_equals_eager_step(cuda, kw):
+    """DAETrainer.step_graphed (eager, then capture + replay, then replay) == DAETrainer.step, bit for bit, over four steps
+    (adam: the step counter and a_t live on the device, so the replayed graph advances them; ae_h: its sums are zeroed in the graph)."""
     from iterative_inference_segm_b200 import _kernels as K
     from iterative_inference_segm_b200.train_dae import DAETrainer
     pd, h, y, L, nm, nk = _setup(cuda)
-    trs = [DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=0.5) for _ in range(2)]
+    trs = [DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=0.5, **kw) for _ in range(2)]
     h_b = K.pack_nchw(h.to(cuda), 512)
     y, L = y.to(cuda), L.to(cuda)
     gen = torch.Generator(device=cuda).manual_seed(11)
@@ -188,9 +190,14 @@ def test_graphed_step_equals_eager_step(cuda):
         n2 = torch.randn(y.shape, device=cuda, generator=gen)
         trs[0].step(h_b, y, L, n1, n2)
         trs[1].step_graphed(h_b, y, L, n1, n2)
-        assert trs[0].loss_value() == trs[1].loss_value(), k
+        if kw:          # the ae_h sum is an fp64 atomic accumulation: equal to the last few bits
+            assert abs(trs[0].loss_value() - trs[1].loss_value()) < 1e-12 * abs(trs[0].loss_value()), k
+        else:
+            assert trs[0].loss_value() == trs[1].loss_value(), k
     for a, b in zip(trs[0].params(), trs[1].params()):
         assert torch.equal(a, b)
+    if kw.get('optimizer') == 'adam':
+        assert float(trs[1].adam_state[0]) == 4.0
 
 
 def _dense_to_mask(dense, cuda):
@@ -211,8 +218,8 @@ TOL_GRAD_FORCED = 8e-3       # teacher-forced discrete decisions: bf16 arithmeti
                              # activations and gradients with the same decisions forced gives 2e-3 .. 5e-3 per array; measured on the B200: <= 5.4e-3)
 
 
-@pytest.mark.parametrize('with_mask_noise', [False, True])
-def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
+@pytest.mark.parametrize('with_mask_noise,ae_h', [(False, False), (True, False), (False, True)], ids=['main-pass-masks', 'mask-noise', 'ae_h'])
+def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise, ae_h):
     """Separates the two sources of gradient error.  The step's discontinuous decisions are: which
     window elements are maxima (pool backward routing, DePool2D masks), which pre-rectifier values are exactly zero
     (rectify'(0) = 0.5) and whether a window's maximum is positive (the rectifier gate).  A window that falls on the other
@@ -221,7 +228,9 @@ def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
     ~1e-3 of the windows doing so is what the 5-15 % of test_train_step_gradients_loss_and_update consists of.  Here the PURE
     fp32 oracle's decisions are forced into the CUDA path (DAETrainer.forward(forced=...)), so what is left is the
     arithmetic -- bf16 operands and bf16 gradient tensors with fp32 accumulation -- and every one of the 24 gradient arrays
-    must agree with the fp32 autograd oracle to 1 % relative L2."""
+    must agree with the fp32 autograd oracle to 1 % relative L2.
+    `ae_h`: with the term squared_error(h_to_recon, h_hat).mean() of train_dae.py:317-319 (added with weight 1): its gradient enters at up_conv5 over the WHOLE map, so the
+    expanding path runs on full maps from level 5 down instead of the crop cone."""
     from iterative_inference_segm_b200 import _kernels as K
     from iterative_inference_segm_b200.train_dae import DAETrainer
     pd, h, y, L, nm, nk = _setup(cuda, structured=True)
@@ -229,12 +238,12 @@ def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
     acc = [torch.zeros_like(p) for p in pd]
     tap = {}
     loss_o, grads_o, _, _ = OT.train_step(pd, acc, y, h, L, NCLS, 100, lr, noise_main=sigma * nm,
-                                          noise_mask=sigma * nk if with_mask_noise else None, tap=tap)     # fp32, no emulation
+                                          noise_mask=sigma * nk if with_mask_noise else None, tap=tap, ae_h=ae_h)     # fp32, no emulation
     forced = {'masksA': [_dense_to_mask(m, cuda) for m in tap['masksA']],
               'zmasks': [_dense_to_mask(z, cuda) for z in tap['zero']],
               'masksB': [_dense_to_mask(m, cuda) for m in tap['masksB']],
               'positive': [(torch.nn.functional.max_pool2d(a.detach(), 2, 2) > 0).permute(0, 2, 3, 1).contiguous().to(cuda) for a in tap['pre_act']]}
-    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=sigma)
+    tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=lr, noise=sigma, ae_h=ae_h)
     h_b = K.pack_nchw(h.to(cuda), 512)
     tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda) if with_mask_noise else None, forced=forced)
     tr.backward(L.to(cuda))
@@ -243,6 +252,11 @@ def test_train_gradients_with_teacher_forced_masks(cuda, with_mask_noise):
     errs = [_rel(g.cpu(), go) for g, go in zip(tr.grads_lasagne(), grads_o)]
     print('teacher-forced masks, relative L2 gradient errors vs the fp32 oracle:', ' '.join('%.4f' % e for e in errs))
     assert max(errs) < TOL_GRAD_FORCED, errs
+    if ae_h:          # the term is in the loss and in the gradients: without it the same step differs
+        s = tr.sums.cpu()
+        loss_plain = OT.train_step(pd, acc, y, h, L, NCLS, 100, lr, noise_main=sigma * nm)[0]
+        print('ae_h term: %.6f on the device, %.6f in the oracle' % (float(s[8] / s[9]), loss_o - loss_plain))
+        assert abs(float(s[8] / s[9]) - (loss_o - loss_plain)) < 2e-3 * (loss_o - loss_plain)
 
 
 @pytest.mark.parametrize('segm_net', ['fcn8', 'densenet'])
@@ -278,7 +292,7 @@ def test_train_loop_runs_and_writes_the_reference_checkpoints(cuda, tmp_path, se
     assert dae.net.total == 6
 
 
-@pytest.mark.parametrize('name', ['ref_train', 'ref_train_adam', 'ref_train_dice'])
+@pytest.mark.parametrize('name', ['ref_train', 'ref_train_adam', 'ref_train_dice', 'ref_train_aeh'])
 def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     """train() of this package against the reference's OWN run of train_dae.py:train() (executed through oracle/refrun,
     tests/golden/ref_train.npz): same arguments, the seeded checkpoint on disk where `resume=True` reads it, the same iterators;
@@ -293,7 +307,7 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     optimizer = case.get('optimizer', 'rmsprop')          # ref_train_adam: lasagne.updates.adam (train_dae.py:328-329)
     d = dict(case['dae'], concat_h=list(case['dae']['concat_h']))
     exp_name = build_experiment_name('fcn8', training_loss=case['training_loss'], data_aug=True, learning_rate=case['learning_rate'],
-                                     lr_anneal=case['lr_anneal'], weight_decay=1e-4, optimizer=optimizer, ae_h=False, **d)
+                                     lr_anneal=case['lr_anneal'], weight_decay=1e-4, optimizer=optimizer, ae_h=case.get('ae_h', False), **d)
     wdir = tmp_path / 'weights' / 'camvid'
     wdir.mkdir(parents=True)
     weights.save_npz(str(wdir / 'fcn8_model.npz'), weights.synthetic_fcn8_params(3, NCLS, **G.FCN8_WEIGHTS))
@@ -303,7 +317,7 @@ def test_train_dropin_vs_reference_run(cuda, tmp_path, name):
     weights.save_npz(str(ldir / 'dae_model_best.npz'), init)
     out = train('camvid', 'fcn8', learning_rate=case['learning_rate'], lr_anneal=case['lr_anneal'], weight_decay=1e-4,
                 num_epochs=case['num_epochs'], max_patience=100, optimizer=optimizer, training_loss=list(case['training_loss']),
-                batch_size=[case['B']] * 3, ae_h=False, dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
+                batch_size=[case['B']] * 3, ae_h=case.get('ae_h', False), dae_dict_updates=dict(case['dae'], concat_h=list(case['dae']['concat_h'])),
                 data_augmentation={'crop_size': None}, savepath=str(tmp_path / 'save'), loadpath=str(tmp_path / 'load'), resume=True,
                 lmb=case['lmb'], train_iter=G.SyntheticCamvidIterator(case, 'train'), val_iter=G.SyntheticCamvidIterator(case, 'val'),
                 weights_path=str(tmp_path / 'weights'), verbose=False)
