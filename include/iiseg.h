@@ -410,7 +410,10 @@ int iiseg_loss_grad_terms(const float* logits, const float* target, int N, int C
  * ('h_to_recon', models/fcn_down.py:117-122), h_hat = fused_up_{n_pool+1} = up_conv_{n_pool+1} + h ('h_hat', models/fcn_up.py:145-146)
  * -> the mean square of that conv's output c (the h parts cancel, in the value up to fp32 rounding and in the gradient exactly).
  * iiseg_sq_sum: sums2[0] += sum of x^2 (x bf16, n elements, n % 8 == 0), sums2[1] += n (fp64; data-parallel ranks all-reduce
- * both).  iiseg_ae_grad_add: g += 2 c / sums2[1] (g, c bf16, same n): the term's gradient with respect to c. */
+ * both).  iiseg_ae_grad_add: g += 2 c / sums2[1] (g, c bf16, same n): the term's gradient with respect to c.
+ * iiseg_add_bf16: out = a + b (bf16, fp32 sum, one rounding): the skip sum h_hat = c + h when c is kept on its own
+ * (ElemwiseSumLayer, models/fcn_up.py:96-100; everywhere else the sum is the conv epilogue's addend). */
+int iiseg_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int iiseg_sq_sum(const void* x, long long n, double* sums2, void* stream);
 int iiseg_ae_grad_add(void* g, const void* c, long long n, const double* sums2, void* stream);
 int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,

@@ -532,6 +532,16 @@ def sq_sum(x, sums2):
     _lib.call('iiseg_sq_sum', _ptr(x), x.numel(), _ptr(sums2), _stream())
 
 
+def add_bf16(a, b):
+    """a + b (bf16 tensors of one shape; fp32 sum, one rounding): a skip sum outside a conv epilogue."""
+    _chk(a, BF16, 'a')
+    _chk(b, BF16, 'b')
+    assert a.shape == b.shape
+    out = torch.empty_like(a)
+    _lib.call('iiseg_add_bf16', _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+    return out
+
+
 def ae_grad_add(g, c, sums2):
     """g += 2 c / sums2[1]: the gradient of mean(c^2) over the (global) element count held on the device."""
     _chk(g, BF16, 'g')

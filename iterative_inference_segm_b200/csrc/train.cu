@@ -464,6 +464,16 @@ __global__ void __launch_bounds__(256) sq_sum_kernel(const uint4* __restrict__ x
   }
 }
 
+__global__ void __launch_bounds__(256) add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 x = ldg_nc_v4(a + i), y = ldg_nc_v4(b + i);
+  stg_v4(out + i, make_uint4(pack_bf16x2(bf16_lo(x.x) + bf16_lo(y.x), bf16_hi(x.x) + bf16_hi(y.x)),
+                             pack_bf16x2(bf16_lo(x.y) + bf16_lo(y.y), bf16_hi(x.y) + bf16_hi(y.y)),
+                             pack_bf16x2(bf16_lo(x.z) + bf16_lo(y.z), bf16_hi(x.z) + bf16_hi(y.z)),
+                             pack_bf16x2(bf16_lo(x.w) + bf16_lo(y.w), bf16_hi(x.w) + bf16_hi(y.w))));
+}
+
 __global__ void __launch_bounds__(256) ae_grad_add_kernel(uint4* __restrict__ g, const uint4* __restrict__ c, long long n8,
                                                           const double* __restrict__ sums2) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -520,6 +530,17 @@ extern "C" int iiseg_sq_sum(const void* x, long long n, double* sums2, void* str
   const long long want = (n8 + 255) / 256;
   const int blocks = (int)(want < 4 * 148 ? want : 4 * 148);          // grid-stride: a few blocks per SM, one atomic each
   sq_sum_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x), n8, sums2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_add_bf16(const void* a, const void* b, void* out, long long n, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(a && b && out, "add_bf16: null tensor");
+  IISEG_CHECK(n > 0 && n % 8 == 0, "add_bf16: element count must be a positive multiple of 8");
+  const long long n8 = n / 8;
+  add_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), reinterpret_cast<uint4*>(out), n8);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

@@ -271,7 +271,7 @@ class DAETrainer(object):
                 # h_hat = up_conv_p + pool_{p-1} over the full map; the conv's own output is kept for the ae_h term
                 assert lay.cout == lay.cout_pad and (hl, wl) == (0, 0)
                 st['ae_c'] = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win)
-                u = st['ae_c'] + st['pools'][p - 2]
+                u = K.add_bf16(st['ae_c'], st['pools'][p - 2])
                 u_origin = (0, 0)
             elif p > 1:
                 u = K.conv2d(v, lay.wb, lay.b, 3, 3, 1, relu=False, window=win, addend=st['pools'][p - 2], addend_off=(hl, wl))
