@@ -124,6 +124,7 @@ def test_loss_terms_against_the_oracle(cuda, tl):
     kw = dict(use_ce='crossentropy' in tl, use_mse='squared_error' in tl, use_dice='dice' in tl)
     loss_o = OT.loss_fn(logits, target, NCLS, lmb=lmb, **kw)
     g_o, = torch.autograd.grad(loss_o, logits)
+    loss_o = loss_o.detach()
     terms = sum(K.LOSS_TERMS[t] for t in tl)
     l16 = torch.zeros((N, H, W, 16), dtype=torch.float32, device=cuda)
     l16[..., :NCLS] = logits.detach().permute(0, 2, 3, 1).to(cuda)
@@ -466,3 +467,62 @@ def test_train_steps_with_noise_vs_reference_run(cuda):
     e = (rel(err_train, fx['err_train']), rel(err_valid, fx['err_valid']), rel(mse_val, fx['mse_val']))
     print('noisy training vs the reference run: err_train %.2e err_valid %.2e mse_val %.2e (relative)' % e)
     assert max(e) < 2e-3, e
+
+
+def test_train_step_full_size_config4(cuda):
+    """BASELINE config 4 at its full size (batch 10 x 224x224, noise 0.5, crossentropy + squared_error, rmsprop 1e-3) through
+    size-independent properties plus an oracle check on a slice the CPU finishes in seconds:
+    * the loss sums of the whole batch equal the sums of its parts [0:3] + [3:10] (per-image results do not depend on the batch
+      they are computed in; fp64 sums), and so does the bias-free check that the step is deterministic (two trainers, same
+      inputs: bit-identical parameters after the update);
+    * the loss of images [0:3] equals the fp32 oracle's loss on the same inputs (forward only) within 1e-3 relative;
+    * one step on the batch lowers the loss on that batch."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    B, H, W, sigma = 10, 224, 224, 0.5
+    pd = weights.synthetic_dae_params(NCLS, 512, seed=1, out_gain=0.1)
+    _, L, _ = weights.synthetic_batch(B, H, W, NCLS, seed=0)
+    y = L[:, :NCLS].contiguous()
+    gen = torch.Generator().manual_seed(21)
+    hs = (((H + 198) // 2 // 2 // 2) // 2, ((W + 198) // 2 // 2 // 2) // 2)
+    h = torch.relu(torch.randn((B, 512) + hs, generator=gen))
+    nm = torch.randn(y.shape, generator=gen)
+    Ld, yd, nmd, h_b = L.to(cuda), y.to(cuda), nm.to(cuda), K.pack_nchw(h.to(cuda), 512)
+
+    def run(lo, hi, update=False):
+        tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=sigma)
+        tr.forward(h_b[lo:hi].contiguous(), yd[lo:hi].contiguous(), nmd[lo:hi].contiguous(), None)
+        tr.backward(Ld[lo:hi].contiguous())
+        if update:
+            tr.update()
+        torch.cuda.synchronize()
+        return tr, tr.sums.cpu().numpy()[:4].copy()
+
+    tr_a, s_full = run(0, B, update=True)
+    tr_b, s_full2 = run(0, B, update=True)
+    assert np.allclose(s_full, s_full2, rtol=1e-13, atol=0)
+    for a, b in zip(tr_a.params(), tr_b.params()):
+        assert torch.equal(a, b)
+    tr_03, s_03 = run(0, 3)
+    _, s_3n = run(3, B)
+    print('config 4 full size: loss sums whole batch', s_full, 'parts', s_03 + s_3n)
+    assert np.allclose(s_full, s_03 + s_3n, rtol=1e-12, atol=0)
+    with torch.no_grad():
+        logits = OT.dae_forward_train(pd, y[:3] + sigma * nm[:3], h[:3], 100)
+        loss_o = float(OT.loss_fn(logits, L[:3], NCLS, lmb=1.0))
+    loss_d = K.loss_from_sums(s_03, 1.0)
+    print('config 4 full size, images 0-2: loss %.6f on the device, %.6f in the fp32 oracle' % (loss_d, loss_o))
+    assert abs(loss_d - loss_o) < 1e-3 * abs(loss_o)
+    # ... and its 24 gradient arrays against the oracle with the device's operand rounding, at the small-size test's tolerance
+    _, grads_o, _, _ = OT.train_step(pd, [torch.zeros_like(p_) for p_ in pd], y[:3], h[:3], L[:3], NCLS, 100, 1e-3,
+                                     noise_main=sigma * nm[:3], emulate_bf16=True)
+    errs = [_rel(g.cpu(), go) for g, go in zip(tr_03.grads_lasagne(), grads_o)]
+    print('config 4 full size, images 0-2: relative L2 gradient errors:', ' '.join('%.3f' % e for e in errs))
+    assert max(errs) < TOL_GRAD, errs
+    before = K.loss_from_sums(s_full, 1.0)
+    tr_a.forward(h_b, yd, nmd, None)
+    K.loss_grad(tr_a.st['logits'], Ld, NCLS, 1.0, tr_a.sums, passes=1)
+    torch.cuda.synchronize()
+    after = K.loss_from_sums(tr_a.sums.cpu().numpy(), 1.0)
+    print('config 4 full size: loss %.6f -> %.6f after one rmsprop step on the same batch' % (before, after))
+    assert after < before
