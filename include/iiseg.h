@@ -414,6 +414,10 @@ int iiseg_loss_grad_terms(const float* logits, const float* target, int N, int C
  * iiseg_add_bf16: out = a + b (bf16, fp32 sum, one rounding): the skip sum h_hat = c + h when c is kept on its own
  * (ElemwiseSumLayer, models/fcn_up.py:96-100; everywhere else the sum is the conv epilogue's addend). */
 int iiseg_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+/* Image 0 of a batched tensor [n][image_bytes] copied to images 1..n-1 (image_bytes % 16 == 0).  The training step's
+ * contracting levels above the h concat (models/fcn_down.py:77-123 with padding 100) compute the y-independent border of their
+ * maps once and broadcast it; the other images run the y-dependent window only. */
+int iiseg_broadcast_image(void* t, long long image_bytes, int n, void* stream);
 int iiseg_sq_sum(const void* x, long long n, double* sums2, void* stream);
 int iiseg_ae_grad_add(void* g, const void* c, long long n, const double* sums2, void* stream);
 int iiseg_depool2_bwd(const void* gv, const uint32_t* mask, void* gu, int N, int H, int W, int C,

@@ -532,6 +532,13 @@ def sq_sum(x, sums2):
     _lib.call('iiseg_sq_sum', _ptr(x), x.numel(), _ptr(sums2), _stream())
 
 
+def broadcast_image(t):
+    """t[1:] = t[0] for a contiguous batched CUDA tensor (bytes per image a multiple of 16)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise _lib.IisegError('broadcast_image: contiguous CUDA tensor expected')
+    _lib.call('iiseg_broadcast_image', _ptr(t), t[0].numel() * t.element_size(), t.shape[0], _stream())
+
+
 def add_bf16(a, b):
     """a + b (bf16 tensors of one shape; fp32 sum, one rounding): a skip sum outside a conv epilogue."""
     _chk(a, BF16, 'a')

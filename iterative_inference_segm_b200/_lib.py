@@ -106,6 +106,7 @@ SIGNATURES = {
     'iiseg_noise_pack': (_i, [_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'iiseg_loss_grad': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp]),
     'iiseg_sq_sum': (_i, [_vp, C.c_longlong, _vp, _vp]),
+    'iiseg_broadcast_image': (_i, [_vp, C.c_longlong, _i, _vp]),
     'iiseg_add_bf16': (_i, [_vp, _vp, _vp, C.c_longlong, _vp]),
     'iiseg_ae_grad_add': (_i, [_vp, _vp, C.c_longlong, _vp, _vp]),
     'iiseg_loss_grad_terms': (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _i, _vp]),

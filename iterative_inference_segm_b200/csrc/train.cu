@@ -464,6 +464,14 @@ __global__ void __launch_bounds__(256) sq_sum_kernel(const uint4* __restrict__ x
   }
 }
 
+// Image 0 of a batched tensor copied to images 1..n-1 (16-byte words): one read, n - 1 writes per thread.
+__global__ void __launch_bounds__(256) broadcast_image_kernel(uint4* __restrict__ t, long long words, int n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= words) return;
+  const uint4 v = t[i];
+  for (int k = 1; k < n; ++k) stg_v4(t + (long long)k * words + i, v);
+}
+
 __global__ void __launch_bounds__(256) add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n8) return;
@@ -530,6 +538,17 @@ extern "C" int iiseg_sq_sum(const void* x, long long n, double* sums2, void* str
   const long long want = (n8 + 255) / 256;
   const int blocks = (int)(want < 4 * 148 ? want : 4 * 148);          // grid-stride: a few blocks per SM, one atomic each
   sq_sum_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(x), n8, sums2);
+  IISEG_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int iiseg_broadcast_image(void* t, long long image_bytes, int n, void* stream) {
+  using namespace iiseg;
+  IISEG_CHECK(t != nullptr, "broadcast_image: null tensor");
+  IISEG_CHECK(image_bytes > 0 && image_bytes % 16 == 0 && n >= 1, "broadcast_image: image size must be a positive multiple of 16 bytes");
+  if (n == 1) return 0;
+  const long long words = image_bytes / 16;
+  broadcast_image_kernel<<<(unsigned)((words + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<uint4*>(t), words, n);
   IISEG_LAUNCH_CHECK();
   return 0;
 }

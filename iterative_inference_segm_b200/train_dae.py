@@ -169,21 +169,51 @@ class DAETrainer(object):
         return out
 
     # ------------------------------------------------------------------ forward
-    def _down(self, x0, h, upto=None):
+    border_once = True        # levels above h: the y-independent border is computed on one image and copied (see _down_level)
+
+    def _down_level(self, p, lay, x, h):
+        """Contracting level p (0-based) for the batch x: conv3x3 + ReLU with the 2x2 pool, the tie mask and the exact-zero mask
+        fused in the epilogue.  Above the h concat, a pixel outside the y-dependent window (DAENet.down_windows: the image, dilated
+        by one pixel per conv, inside the pad-100 border) sees only the zero padding around y and the constant borders of the
+        levels above: it is the same for EVERY image of the batch.  So the full map is computed for image 0 only and copied
+        (data movement), and the other images run the window -- ~30 % of the map with padding 100.  Bit-identical to full
+        launches: a windowed launch produces the values the full launch produces there, and the border values do not depend on
+        the image (tests/test_train_gpu.py::test_border_once_equals_full_launches)."""
         geo, sizes = self.geo, self._sizes
+        n = x.shape[0]
+        hh, ww = sizes[p]
+        pooled = torch.empty((n, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
+        mask = torch.empty((n, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
+        zmask = torch.empty_like(mask)        # exact zeros before the rectifier (gradient 0.5 there)
+        pad = geo.padding if (p == 0 and geo.padding > 0) else 1
+        if p == geo.n_pool:
+            K.conv2d(h, lay.wb, lay.b, 3, 3, pad, relu=True, src1=x, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            return pooled, mask, zmask
+        win = self._dwin.get(p) if self.border_once else None
+        if win is None or n == 1:
+            K.conv2d(x, lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+        else:
+            K.conv2d(x[:1], lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled[:1], pool_mask=mask[:1], pool_zmask=zmask[:1])
+            for t in (pooled, mask, zmask):
+                K.broadcast_image(t)
+            K.conv2d(x[1:], lay.wb, lay.b, 3, 3, pad, relu=True, window=win, pooled=pooled[1:], pool_mask=mask[1:], pool_zmask=zmask[1:])
+        return pooled, mask, zmask
+
+    def _down_windows(self, H, W):
+        """{p (0-based): (oh0, ow0, OH, OW)} for the levels above the h concat whose y-dependent window is worth a separate launch."""
+        geo, sizes = self.geo, self._sizes
+        D, out = geo.down_windows(H, W), {}
+        for p in range(geo.n_pool):
+            hl, hh, wl, wh = D[p + 1]
+            if (hh - hl) * (wh - wl) <= 0.7 * sizes[p][0] * sizes[p][1]:
+                out[p] = (hl, wl, hh - hl, wh - wl)
+        return out
+
+    def _down(self, x0, h, upto=None):
         pools, masks, zmasks = [], [], []
         x = x0
-        B = x0.shape[0]
         for p, lay in enumerate(self.down[:upto]):
-            hh, ww = sizes[p]
-            pooled = torch.empty((B, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
-            mask = torch.empty((B, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
-            zmask = torch.empty_like(mask)        # exact zeros before the rectifier (gradient 0.5 there)
-            pad = geo.padding if (p == 0 and geo.padding > 0) else 1
-            if p == geo.n_pool:
-                K.conv2d(h, lay.wb, lay.b, 3, 3, pad, relu=True, src1=x, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
-            else:
-                K.conv2d(x, lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            pooled, mask, zmask = self._down_level(p, lay, x, h)
             pools.append(pooled); masks.append(mask); zmasks.append(zmask)
             x = pooled
         return pools, masks, zmasks
@@ -200,19 +230,29 @@ class DAETrainer(object):
         x = K.noise_pack(y.repeat(P, 1, 1, 1), noise_mask.reshape((P * B,) + tuple(y.shape[1:])), self.sigma, 16)
         masks = []
         for p, lay in enumerate(self.down):
-            n = (P - p) * B
-            hh, ww = sizes[p]
-            pooled = torch.empty((n, hh // 2, ww // 2, lay.cout_pad), dtype=torch.bfloat16, device=self.dev)
-            mask = torch.empty((n, hh // 2, ww // 2, lay.cout_pad // 8), dtype=torch.int32, device=self.dev)
-            zmask = torch.empty_like(mask)
-            pad = geo.padding if (p == 0 and geo.padding > 0) else 1
-            if p == geo.n_pool:
-                K.conv2d(h.repeat(P - p, 1, 1, 1), lay.wb, lay.b, 3, 3, pad, relu=True, src1=x, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
-            else:
-                K.conv2d(x, lay.wb, lay.b, 3, 3, pad, relu=True, pooled=pooled, pool_mask=mask, pool_zmask=zmask)
+            pooled, mask, _ = self._down_level(p, lay, x, h.repeat(P - p, 1, 1, 1) if p == geo.n_pool else None)
             masks.append(mask[:B])
             x = pooled[B:]
         return masks
+
+    def _down_merged(self, y, noise_main, noise_mask, h):
+        """The main pass and the P noised mask passes as ONE batch per level: [pass l | passes l+1..P | main pass] at level l, so
+        that a level is one launch (plus the shared border, `_down_level`) instead of two; the first B images leave after their
+        level's mask is taken, the main pass rides at the end through all levels.  Per-image results do not depend on the batch,
+        so everything is bit-identical to separate passes.  Returns x0, pools, masksA, zmasks (main pass) and masksB."""
+        geo = self.geo
+        P, B = geo.total, y.shape[0]
+        x = torch.empty(((P + 1) * B, y.shape[2], y.shape[3], 16), dtype=torch.bfloat16, device=self.dev)
+        K.noise_pack(y.repeat(P, 1, 1, 1), noise_mask.reshape((P * B,) + tuple(y.shape[1:])), self.sigma, 16, out=x[:P * B])
+        K.noise_pack(y, noise_main, self.sigma, 16, out=x[P * B:])
+        x0 = x[P * B:]
+        pools, masksA, zmasks, masksB = [], [], [], []
+        for p, lay in enumerate(self.down):
+            pooled, mask, zmask = self._down_level(p, lay, x, h.repeat(P - p + 1, 1, 1, 1) if p == geo.n_pool else None)
+            masksB.append(mask[:B])
+            pools.append(pooled[-B:]); masksA.append(mask[-B:]); zmasks.append(zmask[-B:])
+            x = pooled[B:]
+        return x0, pools, masksA, zmasks, masksB
 
     def forward(self, h_bf16, y, noise_main=None, noise_mask=None, forced=None):
         """Training-mode forward; keeps what the backward pass needs.  Returns fp32 NHWC16 logits.
@@ -227,13 +267,21 @@ class DAETrainer(object):
         B, _, H, W = y.shape
         self._sizes = sizes = geo.level_sizes(H, W)
         self.Wc, self.Wu = geo.cone_windows(H, W)
+        self._dwin = self._down_windows(H, W)
         if self.ae_h:
             for p in range(geo.n_pool + 1, geo.total + 1):
                 self.Wc[p] = self.Wu[p] = (0, sizes[p - 1][0], 0, sizes[p - 1][1])
         st = self.st = {'B': B, 'H': H, 'W': W, 'h': h_bf16}
-        st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
-        st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
-        if noise_mask is not None and noise_mask.dim() == 5:
+        merged = noise_mask is not None and noise_mask.dim() == 5 and self.batched_mask_passes
+        if merged:
+            assert noise_mask.shape[0] == geo.total
+            st['x0'], st['pools'], st['masksA'], st['zmasks'], st['masksB'] = self._down_merged(y, noise_main, noise_mask, h_bf16)
+        else:
+            st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
+            st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
+        if merged:
+            pass
+        elif noise_mask is not None and noise_mask.dim() == 5:
             # the DePool2D mask sub-graphs as the reference's graph has them: every DePool2D re-evaluates the contracting path
             # up to its own pool with an independent noise draw (layers/mylayers.py:91-93; tests/golden/ref_noise.npz), so
             # level p's mask comes from a pass over levels 1..p on y + sigma * noise_mask[p - 1]

@@ -526,3 +526,30 @@ def test_train_step_full_size_config4(cuda):
     after = K.loss_from_sums(tr_a.sums.cpu().numpy(), 1.0)
     print('config 4 full size: loss %.6f -> %.6f after one rmsprop step on the same batch' % (before, after))
     assert after < before
+
+
+def test_border_once_equals_full_launches(cuda):
+    """The contracting levels above the h concat compute the y-independent border of the pad-100 maps once (image 0) and only the
+    y-dependent window for the other images (DAETrainer._down_level).  Against plain full-map launches for every image: pooled
+    maps, tie masks, exact-zero masks, the per-DePool2D masks of the noised passes and the logits are bit-identical."""
+    from iterative_inference_segm_b200 import _kernels as K
+    from iterative_inference_segm_b200.train_dae import DAETrainer
+    pd, h, y, L, nm, _ = _setup(cuda, B=3, H=48, W=56)
+    nk = torch.randn((6,) + tuple(y.shape), generator=torch.Generator().manual_seed(5))
+    h_b = K.pack_nchw(h.to(cuda), 512)
+    sts, logits = [], []
+    for once in (True, False):
+        tr = DAETrainer(NCLS, 512, 100, pd, learning_rate=1e-3, noise=0.5)
+        tr.border_once = once
+        logits.append(tr.forward(h_b, y.to(cuda), nm.to(cuda), nk.to(cuda)).clone())
+        tr.backward(L.to(cuda))
+        torch.cuda.synchronize()
+        sts.append((tr.st, [g.clone() for g in tr.grads_lasagne()], dict(tr._dwin)))
+    assert len(sts[0][2]) == 4, sts[0][2]          # levels 1-4 have a window worth a separate launch at padding 100
+    print('y-dependent windows (oh0, ow0, OH, OW) per level:', sts[0][2], 'level sizes', tr._sizes[:4])
+    for key in ('pools', 'masksA', 'zmasks', 'masksB'):
+        for lvl, (a, b) in enumerate(zip(sts[0][0][key], sts[1][0][key])):
+            assert torch.equal(a, b), (key, lvl)
+    assert torch.equal(logits[0], logits[1])
+    for a, b in zip(sts[0][1], sts[1][1]):
+        assert torch.equal(a, b)
