@@ -329,9 +329,10 @@ class DAETrainer(object):
         return st['logits']
 
     # ------------------------------------------------------------------ backward
-    def _wgrad(self, lay, g, x_srcs, g_origin_in_x, pad):
+    def _wgrad(self, lay, g, x_srcs, g_origin_in_x, pad, bias_from=None):
         """dW (+ db) of `lay` = one GEMM.  g: [B,GH,GW,Cg] gradient w.r.t. the conv output over a window whose origin
-        sits at `g_origin_in_x` in the coordinates of the input tensors; x_srcs: [(tensor, real_channels_padded)]."""
+        sits at `g_origin_in_x` in the coordinates of the input tensors; x_srcs: [(tensor, real_channels_padded)].
+        `bias_from`: the gradient tensor the bias sum runs over when g is only the part that meets a non-zero input."""
         B, GH, GW, Cg = g.shape
         # Both operands live on ONE zero-padded pixel grid of Gh x Gw per image (Gw a multiple of 8): g at the origin, x
         # shifted by `pad`, so that output pixel k meets tap (r, s) at column k + r*Gw + s of x^T.  TMA wants 16-byte
@@ -359,7 +360,7 @@ class DAETrainer(object):
         else:
             groups = [(s_ * lay.cin_pad, r * Gw) for r in range(3) for s_ in range(3)]
             K.wgrad_gemm(gT, xT, lay.cin_pad, groups, slabs, lay.nb, out=lay.grad)
-        K.bias_grad(g, lay.grad, lay.bias_col)
+        K.bias_grad(g if bias_from is None else bias_from, lay.grad, lay.bias_col)
         if self._dp_world is not None:           # data parallel: this layer may complete a bucket -> all-reduce it now
             for lo, hi, last in self._buckets:
                 if last == id(lay):
@@ -435,7 +436,13 @@ class DAETrainer(object):
                 xs = [(st['x0'], 16)]
             else:
                 xs = [(st['pools'][p - 2], st['pools'][p - 2].shape[3])]
-            self._wgrad(lay, g_a, xs, (0, 0), pad)
+            if p == 1 and self.border_once and 0 in self._dwin:
+                # the network input is zero outside the image (padding 100): only the output pixels whose 3x3 field meets it --
+                # the y-dependent window of level 1 -- contribute to dW; the bias sum still runs over the whole map
+                hl, wl, OH, OW = self._dwin[0]
+                self._wgrad(lay, g_a[:, hl:hl + OH, wl:wl + OW].contiguous(), xs, (hl, wl), pad, bias_from=g_a)
+            else:
+                self._wgrad(lay, g_a, xs, (0, 0), pad)
             if p > 1:
                 gs_prev, pw = skip[p - 1]
                 buf = torch.zeros_like(st['pools'][p - 2])
