@@ -395,8 +395,22 @@ __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const uint4* __r
     const int cg = threadIdx.x % ncg, pl = threadIdx.x / ncg;
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (pl < lanes) {
-      for (long long q = p0 + pl; q < p1; q += lanes) {
-        const uint4 v = ldg_nc_v4(g + q * C8 + cg0 + cg);
+      // four independent 16-byte loads in flight per thread; the additions keep the order q, q + lanes, q + 2 lanes, ...
+      const uint4* gp = g + cg0 + cg;
+      long long q = p0 + pl;
+      for (; q + 3LL * lanes < p1; q += 4LL * lanes) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_nc_v4(gp + (q + (long long)u * lanes) * C8);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { a[2 * j] += bf16_lo(w[j]); a[2 * j + 1] += bf16_hi(w[j]); }
+        }
+      }
+      for (; q < p1; q += lanes) {
+        const uint4 v = ldg_nc_v4(gp + q * C8);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) { a[2 * j] += bf16_lo(w[j]); a[2 * j + 1] += bf16_hi(w[j]); }
