@@ -220,21 +220,6 @@ class DAETrainer(object):
 
     batched_mask_passes = True
 
-    def _down_mask_passes(self, y, noise_mask, h):
-        """The P mask passes of the per-DePool2D noise graph run TOGETHER: pass p needs levels 1..p, so level l is one launch over
-        the passes l..P that still need it (batch (P - l + 1) * B instead of P - l + 1 launches of batch B); pass l's images come
-        first in that batch, its mask is the first B images of the level's mask tensor, and the rest moves on.  Per-image results
-        do not depend on the batch they are computed in, so the masks are bit-identical to those of separate passes."""
-        geo, sizes = self.geo, self._sizes
-        P, B = geo.total, y.shape[0]
-        x = K.noise_pack(y.repeat(P, 1, 1, 1), noise_mask.reshape((P * B,) + tuple(y.shape[1:])), self.sigma, 16)
-        masks = []
-        for p, lay in enumerate(self.down):
-            pooled, mask, _ = self._down_level(p, lay, x, h.repeat(P - p, 1, 1, 1) if p == geo.n_pool else None)
-            masks.append(mask[:B])
-            x = pooled[B:]
-        return masks
-
     def _down_merged(self, y, noise_main, noise_mask, h):
         """The main pass and the P noised mask passes as ONE batch per level: [pass l | passes l+1..P | main pass] at level l, so
         that a level is one launch (plus the shared border, `_down_level`) instead of two; the first B images leave after their
@@ -272,29 +257,24 @@ class DAETrainer(object):
             for p in range(geo.n_pool + 1, geo.total + 1):
                 self.Wc[p] = self.Wu[p] = (0, sizes[p - 1][0], 0, sizes[p - 1][1])
         st = self.st = {'B': B, 'H': H, 'W': W, 'h': h_bf16}
-        merged = noise_mask is not None and noise_mask.dim() == 5 and self.batched_mask_passes
-        if merged:
-            assert noise_mask.shape[0] == geo.total
-            st['x0'], st['pools'], st['masksA'], st['zmasks'], st['masksB'] = self._down_merged(y, noise_main, noise_mask, h_bf16)
-        else:
-            st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
-            st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
-        if merged:
-            pass
-        elif noise_mask is not None and noise_mask.dim() == 5:
+        per_depool = noise_mask is not None and noise_mask.dim() == 5
+        if per_depool:
             # the DePool2D mask sub-graphs as the reference's graph has them: every DePool2D re-evaluates the contracting path
             # up to its own pool with an independent noise draw (layers/mylayers.py:91-93; tests/golden/ref_noise.npz), so
             # level p's mask comes from a pass over levels 1..p on y + sigma * noise_mask[p - 1]
             assert noise_mask.shape[0] == geo.total
-            if self.batched_mask_passes:
-                st['masksB'] = self._down_mask_passes(y, noise_mask, h_bf16)
-            else:
+        if per_depool and self.batched_mask_passes:
+            st['x0'], st['pools'], st['masksA'], st['zmasks'], st['masksB'] = self._down_merged(y, noise_main, noise_mask, h_bf16)
+        else:
+            st['x0'] = K.noise_pack(y, noise_main, self.sigma, 16)
+            st['pools'], st['masksA'], st['zmasks'] = self._down(st['x0'], h_bf16)
+            if per_depool:               # one launch sequence per pass (the unbatched form of _down_merged, kept for tests)
                 st['masksB'] = [self._down(K.noise_pack(y, noise_mask[lvl], self.sigma, 16), h_bf16, upto=lvl + 1)[1][lvl]
                                 for lvl in range(geo.total)]
-        elif noise_mask is not None:     # one shared, separately noised contracting path for all levels
-            _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
-        else:
-            st['masksB'] = st['masksA']
+            elif noise_mask is not None:     # one shared, separately noised contracting path for all levels
+                _, st['masksB'], _ = self._down(K.noise_pack(y, noise_mask, self.sigma, 16), h_bf16)
+            else:
+                st['masksB'] = st['masksA']
         if forced is not None:
             if st['masksB'] is st['masksA']:
                 st['masksB'] = [m.clone() for m in st['masksA']]

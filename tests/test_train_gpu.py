@@ -414,7 +414,7 @@ def test_train_forward_draws_one_mask_noise_per_depool(cuda):
         if lvl > 0:
             assert agree_shared < agree - 0.002, (lvl, agree, agree_shared)          # level 1 uses draw 0 in both; measured 0.977-0.997 vs >= 0.99998
     # the graphed step takes the same 5-D tensor
-    # the six passes run batched level by level (DAETrainer._down_mask_passes): bit-identical to six separate passes
+    # the six passes run batched level by level (DAETrainer._down_merged, together with the main pass): bit-identical to six separate passes
     batched = [m.clone() for m in tr.st['masksB']]
     tr.batched_mask_passes = False
     tr.forward(K.pack_nchw(h.to(cuda), 512), y.to(cuda), nm.to(cuda), nk.to(cuda))
