@@ -228,7 +228,8 @@ class DAETrainer(object):
         geo = self.geo
         P, B = geo.total, y.shape[0]
         x = torch.empty(((P + 1) * B, y.shape[2], y.shape[3], 16), dtype=torch.bfloat16, device=self.dev)
-        K.noise_pack(y.repeat(P, 1, 1, 1), noise_mask.reshape((P * B,) + tuple(y.shape[1:])), self.sigma, 16, out=x[:P * B])
+        for lvl in range(P):          # y + sigma * N_l straight into pass l's slot (no P-fold copy of y)
+            K.noise_pack(y, noise_mask[lvl], self.sigma, 16, out=x[lvl * B:(lvl + 1) * B])
         K.noise_pack(y, noise_main, self.sigma, 16, out=x[P * B:])
         x0 = x[P * B:]
         pools, masksA, zmasks, masksB = [], [], [], []
