@@ -149,6 +149,38 @@ for x in g:
     W_.allreduce_sum(x)
 for a, b in zip(g, g_full):
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-8), float((a - b).abs().max())
+# the same with every loss term of the device step: + dice (three whole-batch sums I, T, P all-reduced with the denominators;
+# each rank then differentiates with the GLOBAL sums as constants: dL/dp_1 = -(2 t (T + P + 1) - (2 I + 1)) / (T + P + 1)^2) and
+# + ae_h (sum of squares and element count all-reduced: d/dc = 2 c / n_global) -- iiseg_loss_grad_terms / iiseg_sq_sum protocol
+ps = [p.clone().requires_grad_(True) for p in pd]
+ae = {}
+loss_full = OT.loss_fn(OT.dae_forward_train(ps, y + noise, h, 100, ae_out=ae), L, NCLS, use_dice=True) + OT.ae_h_loss(ae)
+g_full = torch.autograd.grad(loss_full, ps)
+ps = [p.clone().requires_grad_(True) for p in pd]
+ae = {}
+logits = OT.dae_forward_train(ps, (y + noise)[lo:hi], h[lo:hi], 100, ae_out=ae)
+p = torch.softmax(logits, 1)
+ce = -torch.log(torch.clamp(p, 1e-7, 1 - 1e-7).gather(1, (true * mask.long()).unsqueeze(1))).squeeze(1)
+se = ((p - t[:, :NCLS]) ** 2).mean(1)
+t1, p1 = t[:, 1].to(torch.int32).float(), p[:, 1]
+c = ae['h_hat'] - ae['h']
+sums = torch.tensor([float(mask.sum()), float(m2.sum()), float((t1 * p1).sum()), float(t1.sum()), float(p1.sum()),
+                     float((c * c).sum()), float(c.numel())], dtype=torch.float64)
+W_.allreduce_sum(sums)
+n_ce, n_mse, I, T, P, sq, cnt = [float(v) for v in sums]
+S = T + P + 1.0
+loss_global = None          # every rank can form the global loss from the reduced sums (what DAETrainer.loss_value does)
+coef = (-(2.0 * t1 * S - (2.0 * I + 1.0)) / (S * S)).detach()
+surrogate = (ce * mask).sum() / n_ce + (se * m2).sum() / n_mse + (coef * p1).sum() + (c * c).sum() / cnt
+g = [x.clone() for x in torch.autograd.grad(surrogate, ps)]
+for x in g:
+    W_.allreduce_sum(x)
+for a, b in zip(g, g_full):
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-8), float((a - b).abs().max())
+num = torch.tensor([float((ce * mask).sum()), float((se * m2).sum())], dtype=torch.float64)
+W_.allreduce_sum(num)
+loss_global = float(num[0]) / n_ce + float(num[1]) / n_mse - (2.0 * I + 1.0) / S + sq / cnt
+assert abs(loss_global - float(loss_full)) < 1e-5 * abs(float(loss_full)), (loss_global, float(loss_full))
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 '''
@@ -156,7 +188,8 @@ print('rank', rank, 'ok')
 
 def test_two_rank_train_step_allreduce_gloo(tmp_path):
     """Data-parallel DAE train step protocol (config 4): global loss denominators + SUM of per-rank gradients equals
-    the single-device gradient on the concatenated batch (sharding.World over gloo, autograd oracle as the model)."""
+    the single-device gradient on the concatenated batch (sharding.World over gloo, autograd oracle as the model); also with
+    the dice term's whole-batch sums and the ae_h term's sum of squares / element count riding the same all-reduce."""
     script = tmp_path / 'train_worker.py'
     script.write_text(_TRAIN_WORKER % ROOT)
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29547')
