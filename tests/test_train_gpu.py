@@ -528,14 +528,15 @@ def test_train_step_full_size_config4(cuda):
     assert after < before
 
 
-def test_border_once_equals_full_launches(cuda):
+@pytest.mark.parametrize('size', [(48, 56), (37, 45)], ids=['48x56', '37x45-odd'])
+def test_border_once_equals_full_launches(cuda, size):
     """The contracting levels above the h concat compute the y-independent border of the pad-100 maps once (image 0) and only the
     y-dependent window for the other images (DAETrainer._down_level).  Against plain full-map launches for every image: pooled
     maps, tie masks, exact-zero masks, the per-DePool2D masks of the noised passes, the logits and the gradients are bit-identical
     (conv1_1's weight gradient, whose GEMM then runs over the window only, to fp32 summation order)."""
     from iterative_inference_segm_b200 import _kernels as K
     from iterative_inference_segm_b200.train_dae import DAETrainer
-    pd, h, y, L, nm, _ = _setup(cuda, B=3, H=48, W=56)
+    pd, h, y, L, nm, _ = _setup(cuda, B=3, H=size[0], W=size[1])
     nk = torch.randn((6,) + tuple(y.shape), generator=torch.Generator().manual_seed(5))
     h_b = K.pack_nchw(h.to(cuda), 512)
     sts, logits = [], []
